@@ -1,0 +1,633 @@
+// C ABI of libdevqa (include/devqa.h): bank object, workspace, kernel selection, NCCL plumbing.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <atomic>
+#include <mutex>
+#include <new>
+
+#include "scan.cuh"
+#include "topk.cuh"
+#include "nccl_dyn.h"
+
+namespace devqa {
+
+// ---- errors / counters --------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+static std::atomic<int64_t> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+// ---- per-device scratch ---------------------------------------------------------------------------
+// Candidate lists of the scan kernels, pinned staging for the _host entry points.  One search runs
+// per device at a time from one host thread (the reference's usage); work on a
+// different stream than the previous call is ordered behind it with an event.
+struct Scratch {
+  std::mutex mu;
+  int sm_count = 0;
+  uint64_t* cand = nullptr;   size_t cand_bytes = 0;
+  void* dev_io = nullptr;     size_t dev_io_bytes = 0;     // device queries / outputs of _host calls
+  void* pin_io = nullptr;     size_t pin_io_bytes = 0;     // pinned mirror
+  uint64_t* keys = nullptr;   size_t keys_bytes = 0;       // packed local top-k (dist)
+  uint64_t* gathered = nullptr; size_t gathered_bytes = 0; // all-gather target (dist)
+  cudaStream_t last_stream = nullptr;
+  cudaEvent_t done = nullptr;
+  // optional per-kernel timing (devqa_profile_*): event pairs around the scan passes of each search
+  bool profiling = false;
+  static constexpr int kProfSlots = 8192;
+  cudaEvent_t* prof_ev = nullptr;     // [2 * kProfSlots]
+  int prof_used = 0;
+  int64_t prof_scan_launches = 0;
+};
+static Scratch g_scratch[64];
+
+static int grow(void** p, size_t* have, size_t want, bool pinned) {
+  if (*have >= want) return DEVQA_OK;
+  if (*p) {
+    DEVQA_CUDA(cudaDeviceSynchronize());
+    if (pinned) cudaFreeHost(*p); else cudaFree(*p);
+    *p = nullptr; *have = 0;
+  }
+  size_t sz = want + want / 4 + 4096;
+  cudaError_t e = pinned ? cudaMallocHost(p, sz) : cudaMalloc(p, sz);
+  if (e != cudaSuccess) {
+    set_error("%s of %zu bytes failed: %s", pinned ? "cudaMallocHost" : "cudaMalloc", sz, cudaGetErrorString(e));
+    return DEVQA_E_NOMEM;
+  }
+  *have = sz;
+  return DEVQA_OK;
+}
+
+static int scratch_for(int device, Scratch** out) {
+  DEVQA_REQUIRE(device >= 0 && device < 64, "device %d out of range", device);
+  Scratch* s = &g_scratch[device];
+  if (s->sm_count == 0) {
+    int n = 0;
+    DEVQA_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, device));
+    int major = 0;
+    DEVQA_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device));
+    if (major != 10) {
+      set_error("libdevqa is built for sm_100a only; device %d has compute capability %d.x", device, major);
+      return DEVQA_E_UNSUPPORTED;
+    }
+    DEVQA_CUDA(cudaEventCreateWithFlags(&s->done, cudaEventDisableTiming));
+    s->sm_count = n;
+  }
+  *out = s;
+  return DEVQA_OK;
+}
+
+// order this call behind the previous user of the scratch when the stream changed
+static int scratch_enter(Scratch* s, cudaStream_t stream) {
+  if (s->last_stream != stream && s->done) DEVQA_CUDA(cudaStreamWaitEvent(stream, s->done, 0));
+  return DEVQA_OK;
+}
+static int scratch_leave(Scratch* s, cudaStream_t stream) {
+  s->last_stream = stream;
+  cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+  cudaStreamIsCapturing(stream, &st);
+  if (st == cudaStreamCaptureStatusNone) DEVQA_CUDA(cudaEventRecord(s->done, stream));
+  return DEVQA_OK;
+}
+
+// ---- the search pipeline: scan passes -> cross-CTA merge ---------------------------------------------
+struct SearchArgs {
+  const void* bank; int dtype; int64_t n_rows, dim, bank_ld;
+  const float* queries; int64_t n_queries, query_ld;
+  int top_k; unsigned flags; IdMap idmap;
+};
+
+static int validate(const SearchArgs& a) {
+  DEVQA_REQUIRE(a.dim > 0 && a.dim <= (1 << 20), "dim %lld unsupported", (long long)a.dim);
+  DEVQA_REQUIRE(a.n_rows >= 0 && a.n_queries >= 0, "negative sizes");
+  DEVQA_REQUIRE(a.bank_ld >= a.dim && a.query_ld >= a.dim, "row stride smaller than dim");
+  DEVQA_REQUIRE(a.top_k >= 1, "top_k must be >= 1");
+  DEVQA_REQUIRE(a.dtype == DEVQA_F32 || a.dtype == DEVQA_BF16, "unknown bank dtype %d", a.dtype);
+  if (a.top_k > DEVQA_MAX_TOPK) {
+    set_error("top_k %d exceeds DEVQA_MAX_TOPK (%d)", a.top_k, DEVQA_MAX_TOPK);
+    return DEVQA_E_UNSUPPORTED;
+  }
+  DEVQA_REQUIRE(a.n_rows == 0 || a.bank != nullptr, "bank pointer is null");
+  DEVQA_REQUIRE(a.n_queries == 0 || a.queries != nullptr, "queries pointer is null");
+  DEVQA_REQUIRE(a.idmap.base + a.n_rows * (a.idmap.chunk > 0 ? a.idmap.world : 1) <= 0xffffffffll,
+                "corpus ids beyond 2^32 are not supported");
+  return DEVQA_OK;
+}
+
+// Exactly one of out_keys / (out_scores,out_ids).
+static int run_search(Scratch* s, const SearchArgs& a, uint64_t* out_keys, float* out_scores, int64_t* out_ids,
+                      cudaStream_t stream) {
+  if (a.n_queries == 0) return DEVQA_OK;
+  const int kcap = topk_capacity(a.top_k);
+  const int nv_vec = a.dtype == DEVQA_F32 ? 4 : 8;
+  const size_t esz = a.dtype == DEVQA_F32 ? 4 : 2;
+  const bool vectorised = (a.dim % nv_vec == 0) && (a.bank_ld % nv_vec == 0) &&
+                          (reinterpret_cast<uintptr_t>(a.bank) % 16 == 0);
+  (void)esz;
+  const int nv = vectorised ? nv_vec : 1;
+  // widest query tile whose shared-memory footprint fits
+  int qt = 8;
+  while (qt > 1 && (qt / 2 >= a.n_queries || scan_stream_smem_bytes(a.dim, nv, qt, kcap) > 200 * 1024)) qt >>= 1;
+  if (scan_stream_smem_bytes(a.dim, nv, qt, kcap) > 220 * 1024) {
+    set_error("dim %lld with top_k %d does not fit the scan kernel's shared memory", (long long)a.dim, a.top_k);
+    return DEVQA_E_UNSUPPORTED;
+  }
+  const int R = scan_stream_rows_per_group(qt);
+  const int64_t groups = (a.n_rows + R - 1) / R;
+  int64_t want_ctas = (groups + (kScanThreads / 32) - 1) / (kScanThreads / 32);
+  int grid = int(want_ctas < s->sm_count ? want_ctas : s->sm_count);
+  if (grid < 1) grid = 1;
+
+  const size_t cand_bytes = size_t(grid) * a.n_queries * kcap * 8;
+  int rc = grow(reinterpret_cast<void**>(&s->cand), &s->cand_bytes, cand_bytes, false);
+  if (rc) return rc;
+
+  ScanParams p{};
+  p.bank = a.bank; p.n_rows = a.n_rows; p.dim = a.dim; p.bank_ld = a.bank_ld;
+  p.queries = a.queries; p.query_ld = a.query_ld; p.n_queries = int32_t(a.n_queries);
+  p.top_k = a.top_k; p.kcap = kcap; p.flags = a.flags; p.cand = s->cand; p.idmap = a.idmap;
+  const bool prof = s->profiling && s->prof_used < Scratch::kProfSlots;
+  if (prof) DEVQA_CUDA(cudaEventRecord(s->prof_ev[2 * s->prof_used], stream));
+  for (int64_t q0 = 0; q0 < a.n_queries; q0 += qt) {
+    p.q0 = int32_t(q0);
+    p.nq_pass = int32_t(a.n_queries - q0 < qt ? a.n_queries - q0 : qt);
+    rc = scan_stream_launch(p, a.dtype, vectorised, qt, grid, stream);
+    if (rc) return rc;
+    if (prof) s->prof_scan_launches++;
+  }
+  if (prof) {
+    DEVQA_CUDA(cudaEventRecord(s->prof_ev[2 * s->prof_used + 1], stream));
+    s->prof_used++;
+  }
+  return merge_lists_launch(s->cand, grid, a.n_queries, kcap, kcap, a.top_k, out_keys, out_scores, out_ids, stream);
+}
+
+// ---- bank ---------------------------------------------------------------------------------------------
+}  // namespace devqa
+
+struct devqa_bank {
+  int device = 0;
+  int dtype = DEVQA_F32;
+  int64_t dim = 0, ld = 0;
+  int64_t size = 0, capacity = 0;
+  void* data = nullptr;
+  devqa::IdMap idmap{0, 0, 0, 1};
+  size_t esz() const { return dtype == DEVQA_F32 ? 4 : 2; }
+};
+
+struct devqa_comm {
+  int rank = 0, world = 1, device = 0;
+  void* nccl = nullptr;   // ncclComm_t
+};
+
+namespace devqa {
+
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = true;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; return; }
+    if (prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+  }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+#define DEVQA_ON_DEVICE(dev)                                       \
+  ::devqa::DeviceGuard guard__(dev);                               \
+  if (!guard__.ok) { ::devqa::set_error("cudaSetDevice(%d) failed", dev); return DEVQA_E_CUDA; }
+
+static int bank_grow(devqa_bank* b, int64_t want_rows, cudaStream_t stream) {
+  if (want_rows <= b->capacity) return DEVQA_OK;
+  int64_t cap = b->capacity > 0 ? b->capacity : 1024;
+  while (cap < want_rows) cap += cap / 2 + 1024;          // geometric: amortised O(1) per appended row
+  void* fresh = nullptr;
+  const size_t bytes = size_t(cap) * b->ld * b->esz();
+  cudaError_t e = cudaMalloc(&fresh, bytes);
+  if (e != cudaSuccess) {
+    set_error("cudaMalloc of %zu bytes for the bank failed: %s", bytes, cudaGetErrorString(e));
+    return DEVQA_E_NOMEM;
+  }
+  if (b->size > 0)
+    DEVQA_CUDA(cudaMemcpyAsync(fresh, b->data, size_t(b->size) * b->ld * b->esz(), cudaMemcpyDeviceToDevice, stream));
+  if (b->data) {
+    DEVQA_CUDA(cudaStreamSynchronize(stream));
+    DEVQA_CUDA(cudaFree(b->data));
+  }
+  b->data = fresh;
+  b->capacity = cap;
+  return DEVQA_OK;
+}
+
+static SearchArgs bank_args(const devqa_bank* b, const float* q, int64_t nq, int64_t qld, int k, unsigned flags) {
+  SearchArgs a{};
+  a.bank = b->data; a.dtype = b->dtype; a.n_rows = b->size; a.dim = b->dim; a.bank_ld = b->ld;
+  a.queries = q; a.n_queries = nq; a.query_ld = qld; a.top_k = k; a.flags = flags; a.idmap = b->idmap;
+  return a;
+}
+
+// H2D of queries into scratch; returns device pointer
+static int stage_queries(Scratch* s, const float* qh, int64_t nq, int64_t dim, int64_t qld, int top_k,
+                         float** dq, float** d_scores, int64_t** d_ids, cudaStream_t stream) {
+  const size_t qbytes = size_t(nq) * dim * 4;
+  const size_t obytes = size_t(nq) * top_k * 12;
+  const size_t total = ((qbytes + 255) / 256) * 256 + obytes + 256;
+  int rc = grow(&s->dev_io, &s->dev_io_bytes, total, false);
+  if (rc) return rc;
+  rc = grow(&s->pin_io, &s->pin_io_bytes, total, true);
+  if (rc) return rc;
+  float* pq = static_cast<float*>(s->pin_io);
+  for (int64_t i = 0; i < nq; ++i) memcpy(pq + i * dim, qh + i * qld, size_t(dim) * 4);
+  *dq = static_cast<float*>(s->dev_io);
+  char* outs = static_cast<char*>(s->dev_io) + ((qbytes + 255) / 256) * 256;
+  *d_ids = reinterpret_cast<int64_t*>(outs);
+  *d_scores = reinterpret_cast<float*>(outs + size_t(nq) * top_k * 8);
+  DEVQA_CUDA(cudaMemcpyAsync(*dq, pq, qbytes, cudaMemcpyHostToDevice, stream));
+  return DEVQA_OK;
+}
+static int unstage_results(Scratch* s, int64_t nq, int64_t dim, int top_k, float* scores_h, int64_t* ids_h,
+                           cudaStream_t stream) {
+  const size_t qbytes = size_t(nq) * dim * 4;
+  const size_t off = ((qbytes + 255) / 256) * 256;
+  const size_t obytes = size_t(nq) * top_k * 12;
+  char* pin_out = static_cast<char*>(s->pin_io) + off;
+  DEVQA_CUDA(cudaMemcpyAsync(pin_out, static_cast<char*>(s->dev_io) + off, obytes, cudaMemcpyDeviceToHost, stream));
+  DEVQA_CUDA(cudaStreamSynchronize(stream));
+  memcpy(ids_h, pin_out, size_t(nq) * top_k * 8);
+  memcpy(scores_h, pin_out + size_t(nq) * top_k * 8, size_t(nq) * top_k * 4);
+  return DEVQA_OK;
+}
+
+}  // namespace devqa
+
+using namespace devqa;
+
+extern "C" {
+
+int devqa_version(void) { return DEVQA_VERSION; }
+const char* devqa_last_error(void) { return g_err; }
+int64_t devqa_launch_count(void) { return g_launches.load(); }
+
+int devqa_profile_enable(int device, int enable) {
+  Scratch* s = nullptr;
+  int rc = scratch_for(device, &s);
+  if (rc) return rc;
+  DEVQA_ON_DEVICE(device);
+  std::lock_guard<std::mutex> lock(s->mu);
+  if (enable && !s->prof_ev) {
+    s->prof_ev = new (std::nothrow) cudaEvent_t[2 * Scratch::kProfSlots];
+    if (!s->prof_ev) { set_error("host allocation failed"); return DEVQA_E_NOMEM; }
+    for (int i = 0; i < 2 * Scratch::kProfSlots; ++i) DEVQA_CUDA(cudaEventCreate(&s->prof_ev[i]));
+  }
+  s->profiling = enable != 0;
+  s->prof_used = 0;
+  s->prof_scan_launches = 0;
+  return DEVQA_OK;
+}
+
+int devqa_profile_collect(int device, double* scan_ms_total, int64_t* scan_launches, int64_t* searches) {
+  Scratch* s = nullptr;
+  int rc = scratch_for(device, &s);
+  if (rc) return rc;
+  DEVQA_REQUIRE(scan_ms_total && scan_launches && searches, "null outputs");
+  DEVQA_ON_DEVICE(device);
+  std::lock_guard<std::mutex> lock(s->mu);
+  double total = 0.0;
+  for (int i = 0; i < s->prof_used; ++i) {
+    DEVQA_CUDA(cudaEventSynchronize(s->prof_ev[2 * i + 1]));
+    float ms = 0.f;
+    DEVQA_CUDA(cudaEventElapsedTime(&ms, s->prof_ev[2 * i], s->prof_ev[2 * i + 1]));
+    total += ms;
+  }
+  *scan_ms_total = total;
+  *scan_launches = s->prof_scan_launches;
+  *searches = s->prof_used;
+  s->prof_used = 0;
+  s->prof_scan_launches = 0;
+  return DEVQA_OK;
+}
+
+int devqa_search_raw(const void* bank, int bank_dtype, int64_t n_rows, int64_t dim, int64_t bank_ld,
+                     const float* queries, int64_t n_queries, int64_t query_ld, int top_k, unsigned flags,
+                     int64_t id_base, float* out_scores, int64_t* out_ids, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  SearchArgs a{bank, bank_dtype, n_rows, dim, bank_ld, queries, n_queries, query_ld, top_k, flags,
+               IdMap{id_base, 0, 0, 1}};
+  int rc = validate(a);
+  if (rc) return rc;
+  DEVQA_REQUIRE(n_queries == 0 || (out_scores && out_ids), "output pointers are null");
+  int device = 0;
+  DEVQA_CUDA(cudaGetDevice(&device));
+  Scratch* s = nullptr;
+  rc = scratch_for(device, &s);
+  if (rc) return rc;
+  std::lock_guard<std::mutex> lock(s->mu);
+  if ((rc = scratch_enter(s, stream))) return rc;
+  if ((rc = run_search(s, a, nullptr, out_scores, out_ids, stream))) return rc;
+  return scratch_leave(s, stream);
+}
+
+int devqa_normalize_rows(const float* src, int64_t src_ld, float* dst, int64_t dst_ld, int64_t n_rows, int64_t dim,
+                         unsigned flags, void* stream) {
+  DEVQA_REQUIRE(n_rows >= 0 && dim > 0 && src_ld >= dim && dst_ld >= dim, "bad shape");
+  DEVQA_REQUIRE(n_rows == 0 || (src && dst), "null pointers");
+  return normalize_rows_launch(src, src_ld, dst, dst_ld, n_rows, dim, flags, static_cast<cudaStream_t>(stream));
+}
+
+int devqa_bank_create(devqa_bank** out, int device, int64_t dim, int64_t capacity_rows, int dtype) {
+  DEVQA_REQUIRE(out != nullptr, "out is null");
+  DEVQA_REQUIRE(dim > 0 && dim <= (1 << 20), "dim %lld unsupported", (long long)dim);
+  DEVQA_REQUIRE(dtype == DEVQA_F32 || dtype == DEVQA_BF16, "unknown dtype %d", dtype);
+  DEVQA_REQUIRE(capacity_rows >= 0, "negative capacity");
+  Scratch* s = nullptr;
+  int rc = scratch_for(device, &s);
+  if (rc) return rc;
+  DEVQA_ON_DEVICE(device);
+  devqa_bank* b = new (std::nothrow) devqa_bank();
+  if (!b) { set_error("host allocation failed"); return DEVQA_E_NOMEM; }
+  b->device = device; b->dtype = dtype; b->dim = dim;
+  const int64_t align = dtype == DEVQA_F32 ? 4 : 8;          // rows stay 16-byte aligned
+  b->ld = (dim + align - 1) / align * align;
+  if (capacity_rows > 0 && (rc = bank_grow(b, capacity_rows, nullptr))) { delete b; return rc; }
+  *out = b;
+  return DEVQA_OK;
+}
+
+int devqa_bank_destroy(devqa_bank* b) {
+  if (!b) return DEVQA_OK;
+  DEVQA_ON_DEVICE(b->device);
+  if (b->data) { cudaDeviceSynchronize(); cudaFree(b->data); }
+  delete b;
+  return DEVQA_OK;
+}
+
+int64_t devqa_bank_size(const devqa_bank* b) { return b ? b->size : DEVQA_E_INVALID; }
+int64_t devqa_bank_capacity(const devqa_bank* b) { return b ? b->capacity : DEVQA_E_INVALID; }
+int64_t devqa_bank_dim(const devqa_bank* b) { return b ? b->dim : DEVQA_E_INVALID; }
+int devqa_bank_dtype(const devqa_bank* b) { return b ? b->dtype : DEVQA_E_INVALID; }
+int devqa_bank_device(const devqa_bank* b) { return b ? b->device : DEVQA_E_INVALID; }
+const void* devqa_bank_data(const devqa_bank* b) { return b ? b->data : nullptr; }
+
+int devqa_bank_reserve(devqa_bank* b, int64_t capacity_rows, void* stream) {
+  DEVQA_REQUIRE(b != nullptr, "bank is null");
+  DEVQA_ON_DEVICE(b->device);
+  return bank_grow(b, capacity_rows, static_cast<cudaStream_t>(stream));
+}
+
+int devqa_bank_append(devqa_bank* b, const float* rows, int64_t n, int64_t ld, int rows_is_host, void* stream_) {
+  DEVQA_REQUIRE(b != nullptr, "bank is null");
+  DEVQA_REQUIRE(n >= 0, "negative row count");
+  if (n == 0) return DEVQA_OK;
+  DEVQA_REQUIRE(rows != nullptr && ld >= b->dim, "bad rows/ld");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  DEVQA_ON_DEVICE(b->device);
+  int rc = bank_grow(b, b->size + n, stream);
+  if (rc) return rc;
+  char* dst = static_cast<char*>(b->data) + size_t(b->size) * b->ld * b->esz();
+  if (rows_is_host) {
+    if (b->dtype == DEVQA_F32) {
+      DEVQA_CUDA(cudaMemcpy2DAsync(dst, size_t(b->ld) * 4, rows, size_t(ld) * 4, size_t(b->dim) * 4, size_t(n),
+                                   cudaMemcpyHostToDevice, stream));
+      DEVQA_CUDA(cudaStreamSynchronize(stream));
+    } else {
+      float* tmp = nullptr;
+      cudaError_t e = cudaMalloc(&tmp, size_t(n) * b->dim * 4);
+      if (e != cudaSuccess) { set_error("cudaMalloc staging failed: %s", cudaGetErrorString(e)); return DEVQA_E_NOMEM; }
+      DEVQA_CUDA(cudaMemcpy2DAsync(tmp, size_t(b->dim) * 4, rows, size_t(ld) * 4, size_t(b->dim) * 4, size_t(n),
+                                   cudaMemcpyHostToDevice, stream));
+      rc = convert_rows_launch(tmp, b->dim, dst, b->dtype, b->ld, n, b->dim, stream);
+      DEVQA_CUDA(cudaStreamSynchronize(stream));
+      cudaFree(tmp);
+      if (rc) return rc;
+    }
+  } else {
+    if (b->dtype == DEVQA_F32) {
+      DEVQA_CUDA(cudaMemcpy2DAsync(dst, size_t(b->ld) * 4, rows, size_t(ld) * 4, size_t(b->dim) * 4, size_t(n),
+                                   cudaMemcpyDeviceToDevice, stream));
+    } else {
+      if ((rc = convert_rows_launch(rows, ld, dst, b->dtype, b->ld, n, b->dim, stream))) return rc;
+    }
+  }
+  b->size += n;
+  return DEVQA_OK;
+}
+
+int devqa_bank_read_rows(const devqa_bank* b, int64_t first_row, int64_t n, float* dst, int64_t dst_ld, void* stream_) {
+  DEVQA_REQUIRE(b != nullptr, "bank is null");
+  DEVQA_REQUIRE(first_row >= 0 && n >= 0 && first_row + n <= b->size, "row range outside the bank");
+  if (n == 0) return DEVQA_OK;
+  DEVQA_REQUIRE(dst != nullptr && dst_ld >= b->dim, "bad dst/ld");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  DEVQA_ON_DEVICE(b->device);
+  const char* src = static_cast<const char*>(b->data) + size_t(first_row) * b->ld * b->esz();
+  if (b->dtype == DEVQA_F32) {
+    DEVQA_CUDA(cudaMemcpy2DAsync(dst, size_t(dst_ld) * 4, src, size_t(b->ld) * 4, size_t(b->dim) * 4, size_t(n),
+                                 cudaMemcpyDeviceToDevice, stream));
+    return DEVQA_OK;
+  }
+  return widen_rows_launch(src, b->ld, dst, dst_ld, n, b->dim, stream);
+}
+
+int devqa_bank_truncate(devqa_bank* b, int64_t n_rows) {
+  DEVQA_REQUIRE(b != nullptr, "bank is null");
+  DEVQA_REQUIRE(n_rows >= 0 && n_rows <= b->size, "truncate to %lld outside [0, %lld]", (long long)n_rows,
+                (long long)b->size);
+  b->size = n_rows;
+  return DEVQA_OK;
+}
+
+int devqa_bank_set_id_map(devqa_bank* b, int64_t id_base, int64_t chunk_rows, int rank, int world) {
+  DEVQA_REQUIRE(b != nullptr, "bank is null");
+  DEVQA_REQUIRE(id_base >= 0 && chunk_rows >= 0 && world >= 1 && rank >= 0 && rank < world, "bad id map");
+  b->idmap = IdMap{id_base, chunk_rows, rank, world};
+  return DEVQA_OK;
+}
+
+static int bank_search_common(devqa_bank* b, const float* queries, int64_t nq, int64_t qld, int top_k, unsigned flags,
+                              uint64_t* out_keys, float* out_scores, int64_t* out_ids, cudaStream_t stream) {
+  DEVQA_REQUIRE(b != nullptr, "bank is null");
+  SearchArgs a = bank_args(b, queries, nq, qld, top_k, flags);
+  int rc = validate(a);
+  if (rc) return rc;
+  DEVQA_REQUIRE(nq == 0 || out_keys || (out_scores && out_ids), "output pointers are null");
+  DEVQA_ON_DEVICE(b->device);
+  Scratch* s = nullptr;
+  if ((rc = scratch_for(b->device, &s))) return rc;
+  std::lock_guard<std::mutex> lock(s->mu);
+  if ((rc = scratch_enter(s, stream))) return rc;
+  if ((rc = run_search(s, a, out_keys, out_scores, out_ids, stream))) return rc;
+  return scratch_leave(s, stream);
+}
+
+int devqa_bank_search(devqa_bank* b, const float* queries, int64_t nq, int64_t qld, int top_k, unsigned flags,
+                      float* out_scores, int64_t* out_ids, void* stream) {
+  return bank_search_common(b, queries, nq, qld, top_k, flags, nullptr, out_scores, out_ids,
+                            static_cast<cudaStream_t>(stream));
+}
+
+int devqa_bank_search_packed(devqa_bank* b, const float* queries, int64_t nq, int64_t qld, int top_k, unsigned flags,
+                             uint64_t* out_keys, void* stream) {
+  DEVQA_REQUIRE(nq == 0 || out_keys, "out_keys is null");
+  return bank_search_common(b, queries, nq, qld, top_k, flags, out_keys, nullptr, nullptr,
+                            static_cast<cudaStream_t>(stream));
+}
+
+int devqa_bank_search_host(devqa_bank* b, const float* qh, int64_t nq, int64_t qld, int top_k, unsigned flags,
+                           float* scores_h, int64_t* ids_h, void* stream_) {
+  DEVQA_REQUIRE(b != nullptr, "bank is null");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  SearchArgs a = bank_args(b, qh, nq, qld, top_k, flags);
+  int rc = validate(a);
+  if (rc) return rc;
+  if (nq == 0) return DEVQA_OK;
+  DEVQA_REQUIRE(scores_h && ids_h, "output pointers are null");
+  DEVQA_ON_DEVICE(b->device);
+  Scratch* s = nullptr;
+  if ((rc = scratch_for(b->device, &s))) return rc;
+  std::lock_guard<std::mutex> lock(s->mu);
+  if ((rc = scratch_enter(s, stream))) return rc;
+  float* dq; float* ds; int64_t* di;
+  if ((rc = stage_queries(s, qh, nq, b->dim, qld, top_k, &dq, &ds, &di, stream))) return rc;
+  a.queries = dq; a.query_ld = b->dim;
+  if ((rc = run_search(s, a, nullptr, ds, di, stream))) return rc;
+  if ((rc = unstage_results(s, nq, b->dim, top_k, scores_h, ids_h, stream))) return rc;
+  return scratch_leave(s, stream);
+}
+
+int devqa_topk_merge(const uint64_t* gathered, int n_lists, int64_t nq, int top_k, float* out_scores,
+                     int64_t* out_ids, void* stream) {
+  DEVQA_REQUIRE(n_lists >= 1 && nq >= 0 && top_k >= 1, "bad merge shape");
+  if (top_k > DEVQA_MAX_TOPK) { set_error("top_k %d exceeds DEVQA_MAX_TOPK", top_k); return DEVQA_E_UNSUPPORTED; }
+  DEVQA_REQUIRE(nq == 0 || (gathered && out_scores && out_ids), "null pointers");
+  return merge_lists_launch(gathered, n_lists, nq, top_k, top_k, top_k, nullptr, out_scores, out_ids,
+                            static_cast<cudaStream_t>(stream));
+}
+
+// ---- distributed ----------------------------------------------------------------------------------------
+int devqa_dist_unique_id(void* out) {
+  DEVQA_REQUIRE(out != nullptr, "out is null");
+  const NcclApi* api = nccl_api();
+  if (!api) return DEVQA_E_NCCL;
+  ncclUniqueId_ id;
+  int r = api->GetUniqueId(&id);
+  if (r != 0) { set_error("ncclGetUniqueId failed: %s", api->GetErrorString(r)); return DEVQA_E_NCCL; }
+  memcpy(out, &id, sizeof(id));
+  return DEVQA_OK;
+}
+
+int devqa_dist_init(devqa_comm** out, const void* id_bytes, int rank, int world, int device) {
+  DEVQA_REQUIRE(out && id_bytes, "null argument");
+  DEVQA_REQUIRE(world >= 1 && rank >= 0 && rank < world, "bad rank/world %d/%d", rank, world);
+  const NcclApi* api = nccl_api();
+  if (!api) return DEVQA_E_NCCL;
+  Scratch* s = nullptr;
+  int rc = scratch_for(device, &s);
+  if (rc) return rc;
+  DEVQA_CUDA(cudaSetDevice(device));
+  ncclUniqueId_ id;
+  memcpy(&id, id_bytes, sizeof(id));
+  void* comm = nullptr;
+  int r = api->CommInitRank(&comm, world, id, rank);
+  if (r != 0) { set_error("ncclCommInitRank failed: %s", api->GetErrorString(r)); return DEVQA_E_NCCL; }
+  devqa_comm* c = new (std::nothrow) devqa_comm();
+  if (!c) { set_error("host allocation failed"); return DEVQA_E_NOMEM; }
+  c->rank = rank; c->world = world; c->device = device; c->nccl = comm;
+  *out = c;
+  return DEVQA_OK;
+}
+
+int devqa_dist_destroy(devqa_comm* c) {
+  if (!c) return DEVQA_OK;
+  const NcclApi* api = nccl_api();
+  if (api && c->nccl) api->CommDestroy(c->nccl);
+  delete c;
+  return DEVQA_OK;
+}
+int devqa_dist_rank(const devqa_comm* c) { return c ? c->rank : DEVQA_E_INVALID; }
+int devqa_dist_world(const devqa_comm* c) { return c ? c->world : DEVQA_E_INVALID; }
+
+static int dist_search(devqa_bank* b, devqa_comm* c, SearchArgs a, Scratch* s, float* out_scores, int64_t* out_ids,
+                       cudaStream_t stream) {
+  const NcclApi* api = nccl_api();
+  if (!api) return DEVQA_E_NCCL;
+  const size_t per_rank = size_t(a.n_queries) * a.top_k;
+  int rc = grow(reinterpret_cast<void**>(&s->keys), &s->keys_bytes, per_rank * 8, false);
+  if (rc) return rc;
+  if ((rc = grow(reinterpret_cast<void**>(&s->gathered), &s->gathered_bytes, per_rank * 8 * c->world, false))) return rc;
+  if ((rc = run_search(s, a, s->keys, nullptr, nullptr, stream))) return rc;
+  int r = api->AllGather(s->keys, s->gathered, per_rank, /*ncclUint64*/ 5, c->nccl, stream);
+  if (r != 0) { set_error("ncclAllGather failed: %s", api->GetErrorString(r)); return DEVQA_E_NCCL; }
+  return merge_lists_launch(s->gathered, c->world, a.n_queries, a.top_k, a.top_k, a.top_k, nullptr, out_scores,
+                            out_ids, stream);
+}
+
+int devqa_bank_search_dist(devqa_bank* b, devqa_comm* c, const float* queries, int64_t nq, int64_t qld, int top_k,
+                           unsigned flags, float* out_scores, int64_t* out_ids, void* stream_) {
+  DEVQA_REQUIRE(b && c, "null bank/comm");
+  DEVQA_REQUIRE(b->device == c->device, "bank and communicator live on different devices");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  SearchArgs a = bank_args(b, queries, nq, qld, top_k, flags);
+  int rc = validate(a);
+  if (rc) return rc;
+  if (nq == 0) return DEVQA_OK;
+  DEVQA_REQUIRE(out_scores && out_ids, "output pointers are null");
+  DEVQA_ON_DEVICE(b->device);
+  Scratch* s = nullptr;
+  if ((rc = scratch_for(b->device, &s))) return rc;
+  std::lock_guard<std::mutex> lock(s->mu);
+  if ((rc = scratch_enter(s, stream))) return rc;
+  if ((rc = dist_search(b, c, a, s, out_scores, out_ids, stream))) return rc;
+  return scratch_leave(s, stream);
+}
+
+int devqa_bank_search_dist_host(devqa_bank* b, devqa_comm* c, const float* qh, int64_t nq, int64_t qld, int top_k,
+                                unsigned flags, float* scores_h, int64_t* ids_h, void* stream_) {
+  DEVQA_REQUIRE(b && c, "null bank/comm");
+  DEVQA_REQUIRE(b->device == c->device, "bank and communicator live on different devices");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  SearchArgs a = bank_args(b, qh, nq, qld, top_k, flags);
+  int rc = validate(a);
+  if (rc) return rc;
+  if (nq == 0) return DEVQA_OK;
+  DEVQA_REQUIRE(scores_h && ids_h, "output pointers are null");
+  DEVQA_ON_DEVICE(b->device);
+  Scratch* s = nullptr;
+  if ((rc = scratch_for(b->device, &s))) return rc;
+  std::lock_guard<std::mutex> lock(s->mu);
+  if ((rc = scratch_enter(s, stream))) return rc;
+  float* dq; float* ds; int64_t* di;
+  if ((rc = stage_queries(s, qh, nq, b->dim, qld, top_k, &dq, &ds, &di, stream))) return rc;
+  a.queries = dq; a.query_ld = b->dim;
+  if ((rc = dist_search(b, c, a, s, ds, di, stream))) return rc;
+  if ((rc = unstage_results(s, nq, b->dim, top_k, scores_h, ids_h, stream))) return rc;
+  return scratch_leave(s, stream);
+}
+
+// ---- synthetic ----------------------------------------------------------------------------------------------
+int devqa_fill_synthetic(float* dst, int64_t n_rows, int64_t dim, int64_t ld, uint64_t seed, int64_t first_global_row,
+                         int kind, void* stream) {
+  DEVQA_REQUIRE(dst && n_rows >= 0 && dim > 0 && ld >= dim, "bad fill arguments");
+  DEVQA_REQUIRE(kind == 0 || kind == 1, "unknown synthetic kind %d", kind);
+  return fill_synthetic_launch(dst, DEVQA_F32, n_rows, dim, ld, seed, first_global_row, kind,
+                               static_cast<cudaStream_t>(stream));
+}
+
+int devqa_bank_append_synthetic(devqa_bank* b, int64_t n_rows, uint64_t seed, int64_t first_global_row, int kind,
+                                void* stream_) {
+  DEVQA_REQUIRE(b != nullptr && n_rows >= 0, "bad arguments");
+  DEVQA_REQUIRE(kind == 0 || kind == 1, "unknown synthetic kind %d", kind);
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  DEVQA_ON_DEVICE(b->device);
+  int rc = bank_grow(b, b->size + n_rows, stream);
+  if (rc) return rc;
+  char* dst = static_cast<char*>(b->data) + size_t(b->size) * b->ld * b->esz();
+  if ((rc = fill_synthetic_launch(dst, b->dtype, n_rows, b->dim, b->ld, seed, first_global_row, kind, stream))) return rc;
+  b->size += n_rows;
+  return DEVQA_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,117 @@
+// Cross-list top-k merge: reduces the per-CTA candidate lists of scan kernels, and the
+// all-gathered per-GPU lists of the sharded search, to the final result.
+//
+// This is the device-side analogue of the reference's per-(query, candidate) Python heap merge
+// plus final sorted() in util.semantic_search: the inputs are already
+// sorted descending, keys are unique and totally ordered, so the output is independent of list
+// order, grid size and GPU count.
+//
+// One CTA per query.  Each warp folds its share of lists into an accumulator with a bitonic
+// top-k merge (registers + shuffles when the capacity is 32, shared memory otherwise); the warps'
+// accumulators are then tree-merged through shared memory.
+#include "scan.cuh"
+#include "topk.cuh"
+
+namespace devqa {
+namespace {
+
+constexpr int kMergeThreads = 512;
+constexpr int kMergeWarps = kMergeThreads / 32;
+
+__device__ __forceinline__ void emit(uint64_t key, int e, int top_k, int64_t q, uint64_t* out_keys,
+                                     float* out_scores, int64_t* out_ids) {
+  if (e >= top_k) return;
+  const size_t o = size_t(q) * top_k + e;
+  if (out_keys) {
+    out_keys[o] = key;
+  } else {
+    const bool empty = key == kEmptyKey;
+    out_scores[o] = empty ? -INFINITY : key_score(key);
+    out_ids[o] = empty ? int64_t(-1) : int64_t(key_id(key));
+  }
+}
+
+// capacity 32: everything in registers
+__global__ void __launch_bounds__(kMergeThreads) merge32_kernel(const uint64_t* __restrict__ lists, int n_lists,
+                                                               int64_t n_queries, int list_stride, int list_len,
+                                                               int top_k, uint64_t* out_keys, float* out_scores,
+                                                               int64_t* out_ids) {
+  __shared__ uint64_t sacc[kMergeWarps][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t q = blockIdx.x;
+  uint64_t acc = kEmptyKey;
+  const int rev = 31 - lane;
+  for (int l = warp; l < n_lists; l += kMergeWarps) {
+    const uint64_t* src = lists + (size_t(l) * n_queries + q) * list_stride;
+    const uint64_t b = rev < list_len ? src[rev] : kEmptyKey;
+    acc = warp_merge32(acc, b, lane);
+  }
+  sacc[warp][lane] = acc;
+  __syncthreads();
+  for (int s = 1; s < kMergeWarps; s <<= 1) {
+    if ((warp % (2 * s)) == 0 && warp + s < kMergeWarps) {
+      acc = warp_merge32(acc, sacc[warp + s][rev], lane);
+    }
+    __syncthreads();
+    if ((warp % (2 * s)) == 0) sacc[warp][lane] = acc;
+    __syncthreads();
+  }
+  if (warp == 0) emit(acc, lane, top_k, q, out_keys, out_scores, out_ids);
+}
+
+// general capacity (power of two >= 64): accumulators in shared memory
+__global__ void __launch_bounds__(kMergeThreads) merge_generic_kernel(const uint64_t* __restrict__ lists,
+                                                                     int n_lists, int64_t n_queries,
+                                                                     int list_stride, int list_len, int kcap,
+                                                                     int top_k, uint64_t* out_keys,
+                                                                     float* out_scores, int64_t* out_ids) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int nwarps = blockDim.x >> 5;
+  uint64_t* acc = reinterpret_cast<uint64_t*>(smem_raw);       // [warps][kcap]
+  uint64_t* inc = acc + size_t(nwarps) * kcap;                  // [warps][kcap]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t q = blockIdx.x;
+  uint64_t* my_acc = acc + size_t(warp) * kcap;
+  uint64_t* my_inc = inc + size_t(warp) * kcap;
+  for (int e = lane; e < kcap; e += 32) my_acc[e] = kEmptyKey;
+  __syncwarp();
+  for (int l = warp; l < n_lists; l += nwarps) {
+    const uint64_t* src = lists + (size_t(l) * n_queries + q) * list_stride;
+    for (int e = lane; e < kcap; e += 32) my_inc[e] = e < list_len ? src[e] : kEmptyKey;
+    __syncwarp();
+    warp_list_merge(my_acc, my_inc, kcap, lane);
+  }
+  __syncthreads();
+  for (int s = 1; s < nwarps; s <<= 1) {
+    if ((warp % (2 * s)) == 0 && warp + s < nwarps)
+      warp_list_merge(my_acc, acc + size_t(warp + s) * kcap, kcap, lane);
+    __syncthreads();
+  }
+  if (warp == 0)
+    for (int e = lane; e < kcap; e += 32) emit(my_acc[e], e, top_k, q, out_keys, out_scores, out_ids);
+}
+
+}  // namespace
+
+int merge_lists_launch(const uint64_t* lists, int n_lists, int64_t n_queries, int list_stride,
+                       int list_len, int top_k, uint64_t* out_keys, float* out_scores, int64_t* out_ids,
+                       cudaStream_t stream) {
+  if (n_queries == 0) return DEVQA_OK;
+  const int kcap = topk_capacity(top_k > list_len ? top_k : list_len);
+  if (kcap == 32) {
+    merge32_kernel<<<unsigned(n_queries), kMergeThreads, 0, stream>>>(lists, n_lists, n_queries, list_stride,
+                                                                      list_len, top_k, out_keys, out_scores,
+                                                                      out_ids);
+  } else {
+    const int threads = kcap <= 512 ? kMergeThreads : kMergeThreads / 2;   // keep smem <= 128 KB
+    const size_t smem = size_t(2) * (threads / 32) * kcap * 8;
+    DEVQA_CUDA(cudaFuncSetAttribute(merge_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    merge_generic_kernel<<<unsigned(n_queries), threads, smem, stream>>>(
+        lists, n_lists, n_queries, list_stride, list_len, kcap, top_k, out_keys, out_scores, out_ids);
+  }
+  DEVQA_CUDA(cudaGetLastError());
+  count_launch();
+  return DEVQA_OK;
+}
+
+}  // namespace devqa

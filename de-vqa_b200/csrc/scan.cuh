@@ -1,0 +1,50 @@
+// Internal interface between the C ABI (api.cu) and the kernels.
+#pragma once
+#include "common.cuh"
+
+namespace devqa {
+
+constexpr int kScanThreads = 512;   // 16 warps, one CTA per SM (persistent grid)
+
+struct ScanParams {
+  const void* bank;        // [n_rows, dim], row stride bank_ld elements
+  int64_t n_rows;
+  int64_t dim;
+  int64_t bank_ld;
+  const float* queries;    // [n_queries, dim], row stride query_ld
+  int64_t query_ld;
+  int32_t n_queries;       // total queries of the call (candidate buffer layout)
+  int32_t q0;              // first query of this pass
+  int32_t nq_pass;         // queries in this pass (<= QT)
+  int32_t top_k;
+  int32_t kcap;            // topk_capacity(top_k)
+  uint32_t flags;
+  uint64_t* cand;          // [grid, n_queries, kcap] sorted candidate lists (output)
+  IdMap idmap;
+};
+
+size_t scan_stream_smem_bytes(int64_t dim, int nv, int qt, int kcap);
+int scan_stream_rows_per_group(int qt);
+int scan_stream_launch(const ScanParams& p, int bank_dtype, bool vectorised, int qt, int grid,
+                       cudaStream_t stream);
+
+// merge.cu: reduce `n_lists` sorted lists per query ([n_lists, n_queries, list_stride], the first
+// list_len entries of each valid) to the final top_k.  Exactly one of (out_keys) or
+// (out_scores, out_ids) is written: [n_queries, top_k].
+int merge_lists_launch(const uint64_t* lists, int n_lists, int64_t n_queries, int list_stride,
+                       int list_len, int top_k, uint64_t* out_keys, float* out_scores,
+                       int64_t* out_ids, cudaStream_t stream);
+
+// synth.cu
+int fill_synthetic_launch(void* dst, int dtype, int64_t n_rows, int64_t dim, int64_t ld, uint64_t seed,
+                          int64_t first_global_row, int kind, cudaStream_t stream);
+// norm.cu
+int normalize_rows_launch(const float* src, int64_t src_ld, float* dst, int64_t dst_ld, int64_t n_rows, int64_t dim,
+                          unsigned flags, cudaStream_t stream);
+// synth.cu helper kernels
+int widen_rows_launch(const void* src, int64_t src_ld, float* dst, int64_t dst_ld, int64_t n_rows, int64_t dim,
+                      cudaStream_t stream);
+int convert_rows_launch(const float* src, int64_t src_ld, void* dst, int dst_dtype, int64_t dst_ld,
+                        int64_t n_rows, int64_t dim, cudaStream_t stream);
+
+}  // namespace devqa

@@ -1,0 +1,123 @@
+"""Drop-in for the slice of ``sentence_transformers.util`` the reference uses.
+
+Same names, signatures and result format as the helpers DE-VQA calls
+(SURVEY.md 8b and Appendix A), so that reference call sites run unmodified when this
+module is provided as ``sentence_transformers.util``:
+
+    hits = util.semantic_search(q, bank, score_function=util.dot_score, top_k=k)
+        dataset/vllm.py:68; easyeditor/models/ike/ike_main.py:44,202,240;
+        easyeditor/evaluate/multimodal_evaluate.py:412; easyeditor/trainer/algs/HICE.py:177
+
+Everything is computed by libdevqa.so on the GPU.  There is no CPU path: CPU tensors /
+ndarrays are uploaded, and a machine without a B200 raises.  Divergences from upstream,
+all outside the parity contract: ties are ordered by ascending
+corpus id; ``top_k`` is capped at 1024; ``score_function`` must be ``dot_score`` or
+``cos_sim`` (the only two the reference passes or defaults to); chunk-size arguments are
+accepted and ignored (the scan never materialises a score matrix).
+"""
+from __future__ import annotations
+
+from typing import Callable, List
+
+import numpy as np
+import torch
+
+from . import _lib as L
+from .bank import _stream_ptr, hits_from_arrays
+
+
+def _to_tensor(x) -> torch.Tensor:
+    if isinstance(x, torch.Tensor):
+        return x
+    if isinstance(x, (np.ndarray, np.generic)):
+        return torch.from_numpy(np.asarray(x))
+    if isinstance(x, (list, tuple)) and len(x) and isinstance(x[0], torch.Tensor):
+        return torch.stack(list(x))
+    return torch.as_tensor(x)
+
+
+def _matrix(x) -> torch.Tensor:
+    t = _to_tensor(x)
+    return t.unsqueeze(0) if t.dim() == 1 else t
+
+
+def _cuda_f32(t: torch.Tensor, device=None) -> torch.Tensor:
+    if not torch.cuda.is_available():
+        raise RuntimeError("devqa_b200 has no CPU fallback: a CUDA device (B200, sm_100a) is required")
+    if device is None:
+        device = t.device if t.is_cuda else torch.device("cuda", torch.cuda.current_device())
+    t = t.detach().to(device=device, dtype=torch.float32)
+    if t.stride(-1) != 1 or (t.shape[0] > 1 and t.stride(0) < t.shape[1]):
+        t = t.contiguous()
+    return t
+
+
+def _ld(t: torch.Tensor) -> int:
+    return t.stride(0) if t.shape[0] > 1 else t.shape[1]
+
+
+def normalize_embeddings(embeddings: torch.Tensor) -> torch.Tensor:
+    """``x / max(||x||_2, 1e-12)`` per row (``F.normalize(p=2, dim=1)``), on the GPU.
+    Result lives on the input's device (reference: dataset/vllm.py:66,104,117)."""
+    src = _to_tensor(embeddings)
+    if src.dim() != 2:
+        raise ValueError("normalize_embeddings expects a 2-D tensor")
+    x = _cuda_f32(src)
+    out = torch.empty_like(x, memory_format=torch.contiguous_format)
+    with torch.cuda.device(x.device):
+        L.check(L.lib().devqa_normalize_rows(x.data_ptr(), _ld(x), out.data_ptr(), x.shape[1], x.shape[0], x.shape[1],
+                                             0, _stream_ptr(x.device.index)))
+    return out if src.is_cuda else out.to(src.device)
+
+
+def dot_score(a, b) -> torch.Tensor:
+    """Marker + implementation of the reference's ``score_function``.  ``semantic_search``
+    recognises this function and fuses it; called directly it returns the dense ``[len(a),
+    len(b)]`` matrix with torch (off the hot path: no reference call site does that)."""
+    return torch.mm(_matrix(a), _matrix(b).transpose(0, 1))
+
+
+def cos_sim(a, b) -> torch.Tensor:
+    """Upstream's default ``score_function`` (normalise both sides)."""
+    a, b = _matrix(a), _matrix(b)
+    return torch.mm(torch.nn.functional.normalize(a, p=2, dim=1),
+                    torch.nn.functional.normalize(b, p=2, dim=1).transpose(0, 1))
+
+
+def semantic_search_arrays(query_embeddings, corpus_embeddings, top_k: int = 10,
+                           score_function: Callable = cos_sim, flags: int = 0):
+    """Tensor form of ``semantic_search``: ``(scores [Q,k'] fp32, ids [Q,k'] int64)`` CUDA
+    tensors with ``k' = min(top_k, N)``; no host synchronisation."""
+    if score_function is dot_score:
+        nflags = 0
+    elif score_function is cos_sim:
+        nflags = L.NORMALIZE_BANK | L.NORMALIZE_QUERY
+    else:
+        raise ValueError("devqa_b200.util.semantic_search supports score_function=dot_score or cos_sim only")
+    corpus = _matrix(corpus_embeddings)
+    queries = _matrix(query_embeddings)
+    if corpus.dim() != 2 or queries.dim() != 2 or corpus.shape[1] != queries.shape[1]:
+        raise ValueError(f"shape mismatch: queries {tuple(queries.shape)} vs corpus {tuple(corpus.shape)}")
+    corpus = _cuda_f32(corpus)
+    queries = _cuda_f32(queries, device=corpus.device)      # upstream moves the query to the corpus device
+    n, nq = corpus.shape[0], queries.shape[0]
+    if n == 0:
+        raise RuntimeError("semantic_search on an empty corpus (upstream raises in torch.topk as well)")
+    kk = min(int(top_k), n)
+    scores = torch.empty((nq, kk), dtype=torch.float32, device=corpus.device)
+    ids = torch.empty((nq, kk), dtype=torch.int64, device=corpus.device)
+    with torch.cuda.device(corpus.device):
+        L.check(L.lib().devqa_search_raw(corpus.data_ptr(), L.F32, n, corpus.shape[1], _ld(corpus),
+                                         queries.data_ptr(), nq, _ld(queries), kk, nflags | flags, 0,
+                                         scores.data_ptr(), ids.data_ptr(), _stream_ptr(corpus.device.index)))
+    return scores, ids
+
+
+def semantic_search(query_embeddings, corpus_embeddings, query_chunk_size: int = 100,
+                    corpus_chunk_size: int = 500000, top_k: int = 10,
+                    score_function: Callable = cos_sim) -> List[List[dict]]:
+    """Same contract as upstream: list[Q] of list[min(top_k, N)] of
+    ``{"corpus_id": int, "score": float}``, score-descending.  One D2H + sync, like the
+    reference's ``.cpu().tolist()``."""
+    scores, ids = semantic_search_arrays(query_embeddings, corpus_embeddings, top_k, score_function)
+    return hits_from_arrays(scores.cpu().numpy(), ids.cpu().numpy())

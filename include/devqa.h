@@ -1,0 +1,185 @@
+/*
+ * devqa.h -- C ABI of the B200-native fact-bank retrieval library (libdevqa.so).
+ *
+ * This is the drop-in boundary for ONE hot path of sev777/DE-VQA ("LiveEdit"):
+ * the fact-bank similarity search  L2-normalise -> query x bank^T -> row-wise top-k
+ * that the reference reaches through sentence_transformers.util.  Citations are
+ * relative to /root/reference/DE-VQA.
+ *
+ *   reference interface                                   replaced by
+ *   ----------------------------------------------------  --------------------------------
+ *   util.normalize_embeddings(bank)      dataset/vllm.py:104,117; ike_main.py:37,194
+ *   bank / torch.norm(bank)  (no eps)    ike_main.py:238; multimodal_evaluate.py:410;
+ *                                        HICE.py:170            -> flags of devqa_*search*
+ *   util.dot_score(q, bank)              passed at every search site (torch.mm)
+ *   util.semantic_search(q, bank, dot_score, top_k)
+ *                                        dataset/vllm.py:68; ike_main.py:44,202,240;
+ *                                        multimodal_evaluate.py:412; HICE.py:177;
+ *                                        easyeditor/dataset/vqa.py:176; coco_caption.py:174
+ *                                                               -> devqa_search_raw /
+ *                                                                  devqa_bank_search*
+ *   torch.tensor(pkl['embeddings']).to(dev)   dataset/vllm.py:102,116; ike_main.py:36,193
+ *                                                               -> devqa_bank_create/append
+ *   torch.cat([pool, new], 0) per edit   lte_vl.py:150; serac_vl.py:104; recipe_vl.py:163
+ *                                                               -> devqa_bank_append (in place)
+ *
+ * Conventions: plain C types only; every function returns 0 (DEVQA_OK) or a
+ * negative DEVQA_E_* code and leaves a message for devqa_last_error() (thread
+ * local).  Unless a name ends in _host, pointer arguments are DEVICE pointers on
+ * the bank's device, and the call only enqueues work on `stream` (a cudaStream_t
+ * passed as void*; NULL = the legacy default stream) without synchronising.
+ * There is no CPU fallback anywhere in the library.
+ *
+ * Result contract (all search entry points): for each query the min(top_k, N)
+ * best rows, score-descending; ties broken by ascending row id (the reference's
+ * tie order is implementation-defined).  Scores are fp32.
+ * Output arrays are [n_queries, top_k] row-major; when N < top_k the trailing
+ * slots of each row hold score = -inf and id = -1.
+ */
+#ifndef DEVQA_H_
+#define DEVQA_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DEVQA_VERSION 100  /* 0.1.0 */
+
+#if defined(__GNUC__)
+#define DEVQA_API __attribute__((visibility("default")))
+#else
+#define DEVQA_API
+#endif
+
+/* error codes */
+#define DEVQA_OK 0
+#define DEVQA_E_INVALID (-1)     /* bad argument */
+#define DEVQA_E_CUDA (-2)        /* a CUDA runtime call failed */
+#define DEVQA_E_NOMEM (-3)       /* device/host allocation failed */
+#define DEVQA_E_UNSUPPORTED (-4) /* e.g. top_k > DEVQA_MAX_TOPK */
+#define DEVQA_E_NCCL (-5)        /* NCCL missing or a collective failed */
+#define DEVQA_E_STATE (-6)       /* object used in the wrong state */
+
+#define DEVQA_MAX_TOPK 1024
+
+/* bank element types */
+#define DEVQA_F32 0
+#define DEVQA_BF16 1 /* bank rows stored as bf16 (converted on append); scores still fp32 */
+
+/* search flags */
+#define DEVQA_NORMALIZE_BANK (1u << 0)  /* score /= max(||row||_2, 1e-12)  (fused; bank is read once) */
+#define DEVQA_NORMALIZE_QUERY (1u << 1) /* query /= max(||q||_2, 1e-12)                                 */
+#define DEVQA_NOEPS (1u << 2)           /* use x/||x|| with no clamp (HICE call sites); zero row -> NaN,
+                                           and NaN ranks above every number, as torch.topk does        */
+#define DEVQA_FORCE_STREAM (1u << 8)    /* testing/benchmark: force the bank-streaming (CUDA-core) kernel */
+#define DEVQA_FORCE_TENSOR (1u << 9)    /* testing/benchmark: force the tcgen05 contraction kernel       */
+
+typedef struct devqa_bank devqa_bank; /* opaque, library-owned fact bank */
+typedef struct devqa_comm devqa_comm; /* opaque, one NCCL communicator + staging */
+
+/* ---- library ------------------------------------------------------------------------- */
+DEVQA_API int devqa_version(void);
+DEVQA_API const char* devqa_last_error(void);
+/* number of kernels this library has launched in this process (bench.py's gpu_launches) */
+DEVQA_API int64_t devqa_launch_count(void);
+
+/* Per-kernel timing for benchmarks: while enabled, every search records a CUDA-event pair on its
+ * own stream around its scan launches (the dominant kernel); collect() synchronises, returns the
+ * summed scan time, the number of scan launches and searches since the last collect, and resets. */
+DEVQA_API int devqa_profile_enable(int device, int enable);
+DEVQA_API int devqa_profile_collect(int device, double* scan_ms_total, int64_t* scan_launches,
+                                    int64_t* searches);
+
+/* ---- stateless search over a caller-owned bank -----------------------------------------
+ * The literal replacement of  semantic_search(q, corpus, score_function=dot_score, top_k)
+ * on CUDA tensors: `bank` is [n_rows, dim] with row stride `bank_ld` elements (>= dim),
+ * `queries` is [n_queries, dim] fp32 with row stride `query_ld`.  Returned ids are
+ * id_base + row.  */
+DEVQA_API int devqa_search_raw(const void* bank, int bank_dtype, int64_t n_rows, int64_t dim, int64_t bank_ld,
+                     const float* queries, int64_t n_queries, int64_t query_ld, int top_k,
+                     unsigned flags, int64_t id_base, float* out_scores, int64_t* out_ids,
+                     void* stream);
+
+/* Stand-alone row normalisation, dst = src / max(||src||_2, 1e-12) (or / ||src|| with
+ * DEVQA_NOEPS): util.normalize_embeddings (dataset/vllm.py:66,104,117).  dst may equal src.
+ * The search entry points fuse normalisation and do not need this.                        */
+DEVQA_API int devqa_normalize_rows(const float* src, int64_t src_ld, float* dst, int64_t dst_ld, int64_t n_rows,
+                         int64_t dim, unsigned flags, void* stream);
+
+/* ---- library-owned, appendable bank ------------------------------------------------------
+ * Replaces the per-request pickle -> numpy -> torch.tensor -> .to(device) upload and the
+ * O(N) torch.cat append of the lifelong editors with a resident, in-place growable buffer.
+ * capacity_rows is a hint (the bank grows geometrically in place when exceeded).          */
+DEVQA_API int devqa_bank_create(devqa_bank** out, int device, int64_t dim, int64_t capacity_rows, int dtype);
+DEVQA_API int devqa_bank_destroy(devqa_bank* bank);
+DEVQA_API int64_t devqa_bank_size(const devqa_bank* bank);     /* rows currently stored, <0 on error */
+DEVQA_API int64_t devqa_bank_capacity(const devqa_bank* bank); /* rows that fit without growing      */
+DEVQA_API int64_t devqa_bank_dim(const devqa_bank* bank);
+DEVQA_API int devqa_bank_dtype(const devqa_bank* bank);
+DEVQA_API int devqa_bank_device(const devqa_bank* bank);
+DEVQA_API const void* devqa_bank_data(const devqa_bank* bank); /* device pointer to row 0 */
+DEVQA_API int devqa_bank_reserve(devqa_bank* bank, int64_t capacity_rows, void* stream);
+/* Append n fp32 rows (row stride `ld` elements).  rows_is_host != 0: `rows` is host memory
+ * and the call stages + copies it (synchronous w.r.t. the host buffer).                   */
+DEVQA_API int devqa_bank_append(devqa_bank* bank, const float* rows, int64_t n, int64_t ld, int rows_is_host,
+                      void* stream);
+/* Copy rows [first_row, first_row + n) out as fp32 into a DEVICE buffer (bf16 banks are widened). */
+DEVQA_API int devqa_bank_read_rows(const devqa_bank* bank, int64_t first_row, int64_t n, float* dst,
+                                   int64_t dst_ld, void* stream);
+/* Drop rows from the end (restore_to_original_model of the lifelong editors). */
+DEVQA_API int devqa_bank_truncate(devqa_bank* bank, int64_t n_rows);
+/* How local rows map to global corpus ids (multi-GPU sharding):
+ *   global = id_base + ((row / chunk_rows) * world + rank) * chunk_rows + row % chunk_rows
+ * Contiguous shard: chunk_rows = 0 (=> global = id_base + row).                           */
+DEVQA_API int devqa_bank_set_id_map(devqa_bank* bank, int64_t id_base, int64_t chunk_rows, int rank, int world);
+
+DEVQA_API int devqa_bank_search(devqa_bank* bank, const float* queries, int64_t n_queries, int64_t query_ld,
+                      int top_k, unsigned flags, float* out_scores, int64_t* out_ids, void* stream);
+/* Same, with HOST queries and HOST outputs: stages through pinned memory, copies in, runs,
+ * copies out and synchronises -- the one D2H + sync the reference's .cpu().tolist() also pays. */
+DEVQA_API int devqa_bank_search_host(devqa_bank* bank, const float* queries_host, int64_t n_queries,
+                           int64_t query_ld, int top_k, unsigned flags, float* out_scores_host,
+                           int64_t* out_ids_host, void* stream);
+/* Local top-k as order-preserving packed keys, [n_queries, top_k] uint64:
+ *   key = (monotone(score bits) << 32) | (0xFFFFFFFF - global_id); empty slot = 0.        */
+DEVQA_API int devqa_bank_search_packed(devqa_bank* bank, const float* queries, int64_t n_queries,
+                             int64_t query_ld, int top_k, unsigned flags, uint64_t* out_keys,
+                             void* stream);
+
+/* ---- multi-GPU merge ---------------------------------------------------------------------
+ * gathered: [n_lists, n_queries, top_k] packed keys, each [top_k] run sorted descending. */
+DEVQA_API int devqa_topk_merge(const uint64_t* gathered, int n_lists, int64_t n_queries, int top_k,
+                     float* out_scores, int64_t* out_ids, void* stream);
+
+/* One NCCL communicator per process (one process per GPU).  Rank 0 calls
+ * devqa_dist_unique_id, ships the 128 bytes to every rank by any host channel
+ * (torch.distributed, MPI, a file), then every rank calls devqa_dist_init.               */
+DEVQA_API int devqa_dist_unique_id(void* out_id_128_bytes);
+DEVQA_API int devqa_dist_init(devqa_comm** out, const void* id_128_bytes, int rank, int world, int device);
+DEVQA_API int devqa_dist_destroy(devqa_comm* comm);
+DEVQA_API int devqa_dist_rank(const devqa_comm* comm);
+DEVQA_API int devqa_dist_world(const devqa_comm* comm);
+/* scan of the local shard -> ONE ncclAllGather of [n_queries, top_k] packed keys ->
+ * fused merge; every rank receives the full result.  Queries are replicated.             */
+DEVQA_API int devqa_bank_search_dist(devqa_bank* bank, devqa_comm* comm, const float* queries,
+                           int64_t n_queries, int64_t query_ld, int top_k, unsigned flags,
+                           float* out_scores, int64_t* out_ids, void* stream);
+DEVQA_API int devqa_bank_search_dist_host(devqa_bank* bank, devqa_comm* comm, const float* queries_host,
+                                int64_t n_queries, int64_t query_ld, int top_k, unsigned flags,
+                                float* out_scores_host, int64_t* out_ids_host, void* stream);
+
+/* ---- synthetic data (benchmarks, tests) ---------------------------------------------------
+ * Counter-based generator keyed by (seed, global row, column) so any sharding reproduces
+ * the same bank.  kind 0: unit-norm N(0,1) rows (MiniLM-like); kind 1: un-normalised
+ * "hidden-state" rows, N(0,1) * exp(N(0,0.5^2)) per row with 4 outlier columns x50.       */
+DEVQA_API int devqa_fill_synthetic(float* dst, int64_t n_rows, int64_t dim, int64_t ld, uint64_t seed,
+                         int64_t first_global_row, int kind, void* stream);
+DEVQA_API int devqa_bank_append_synthetic(devqa_bank* bank, int64_t n_rows, uint64_t seed,
+                                int64_t first_global_row, int kind, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DEVQA_H_ */

@@ -1,0 +1,132 @@
+"""Full-size runs (BASELINE C3 shape: 1M x 768 fp32, k=32) checked through size-independent
+properties, plus the multi-GPU merge emulated on one GPU.  GPU only; nothing here reads
+/root/reference."""
+import numpy as np
+import pytest
+import torch
+
+import devqa_b200
+from devqa_b200 import FactBank, topk_merge
+from oracle import semantic_search as ss
+
+pytestmark = pytest.mark.gpu
+
+N, D, K = 1_000_000, 768, 32
+
+
+@pytest.fixture(scope="module")
+def big_bank():
+    fb = FactBank(D, capacity=N)
+    for r0 in range(0, N, 250_000):                   # appended in batches: ids are insertion order
+        fb.append_synthetic(250_000, seed=3234, first_global_row=r0)
+    torch.cuda.synchronize()
+    yield fb
+    fb.close()
+
+
+def _queries(nq, seed):
+    g = torch.Generator().manual_seed(seed)
+    return torch.nn.functional.normalize(torch.randn(nq, D, generator=g), dim=1).cuda()
+
+
+def test_synthetic_rows_are_unit_norm_and_sharding_invariant(big_bank):
+    rows = big_bank.rows(499_990, 500_010)            # straddles two append batches
+    torch.testing.assert_close(rows.norm(dim=1), torch.ones(20, device="cuda"), rtol=1e-5, atol=1e-5)
+    other = FactBank(D)
+    other.append_synthetic(20, seed=3234, first_global_row=499_990)
+    assert torch.equal(other.rows(), rows)
+    other.close()
+
+
+def test_self_retrieval_and_planted_neighbours(big_bank):
+    ids = torch.tensor([0, 1, 31, 4097, 499_999, 500_000, 777_777, N - 1])
+    q = torch.cat([big_bank.rows(int(i), int(i) + 1) for i in ids])
+    s, i = big_bank.search(q, K)
+    assert i[:, 0].cpu().tolist() == ids.tolist()
+    torch.testing.assert_close(s[:, 0], torch.ones(len(ids), device="cuda"), rtol=1e-5, atol=1e-5)
+    assert (s[:, 1] < 0.5).all()                      # random 768-d unit vectors: next best is far away
+    # plant near-copies at the end: they must come back ahead of everything else, in planted order
+    g = torch.Generator().manual_seed(7)
+    noise = torch.randn(3, D, generator=g).cuda()
+    planted = torch.nn.functional.normalize(q[:1] + torch.tensor([[0.05], [0.1], [0.2]]).cuda() * noise / noise.norm(dim=1, keepdim=True), dim=1)
+    big_bank.append(planted)
+    s2, i2 = big_bank.search(q[:1], K)
+    assert i2[0, :4].cpu().tolist() == [0, N, N + 1, N + 2]
+    big_bank.truncate(N)
+    s3, i3 = big_bank.search(q[:1], K)
+    assert torch.equal(i3, i[:1]) and torch.equal(s3, s[:1])
+
+
+def test_prefix_idempotence_sortedness(big_bank):
+    for nq in (1, 8, 64):
+        q = _queries(nq, 7678 + nq)
+        s32, i32 = big_bank.search(q, 32)
+        s16, i16 = big_bank.search(q, 16)
+        assert torch.equal(i32[:, :16], i16) and torch.equal(s32[:, :16], s16)     # top-16 is a prefix of top-32
+        s_again, i_again = big_bank.search(q, 32)
+        assert torch.equal(s_again, s32) and torch.equal(i_again, i32)             # idempotent / deterministic
+        assert (s32[:, :-1] >= s32[:, 1:]).all()
+        assert all(len(set(r)) == 32 for r in i32.cpu().tolist())
+        # a query's result does not depend on what else is in the batch
+        s1, i1 = big_bank.search(q[:1], 32)
+        assert torch.equal(i1, i32[:1]) and torch.equal(s1, s32[:1])
+
+
+def test_scores_against_fp64_on_returned_and_sampled_rows(big_bank):
+    """Oracle check at full size: returned scores equal the fp64 dot products of the rows they
+    name; no row of a 20k random sample beats the k-th score by more than the gap."""
+    q = _queries(4, 4242)
+    s, i = big_bank.search(q, K)
+    s, i = s.cpu().numpy(), i.cpu().numpy()
+    g = torch.Generator().manual_seed(1)
+    sample = torch.randint(0, N, (20_000,), generator=g).tolist()
+    for r in range(4):
+        rows = torch.cat([big_bank.rows(int(j), int(j) + 1) for j in i[r]]).cpu()
+        truth = ss.truth_scores_fp64(q[r:r + 1].cpu(), rows)[0]
+        np.testing.assert_allclose(s[r], truth, rtol=1e-5, atol=1e-6)
+    blocks = torch.cat([big_bank.rows(j, j + 1) for j in sample[:2000]]).cpu()
+    truth = ss.truth_scores_fp64(q.cpu(), blocks)
+    for r in range(4):
+        beat = [sample[c] for c in np.nonzero(truth[r] > s[r, -1] + 1e-5)[0]]
+        assert set(beat) <= set(i[r].tolist())
+
+
+def test_sharded_merge_equals_unsharded_bit_for_bit(big_bank):
+    """Multi-GPU path emulated on one GPU: G shard banks with global id bases -> packed local
+    top-k -> [G, Q, k] -> devqa_topk_merge == the unsharded search, exactly."""
+    q = _queries(9, 999)
+    ref_s, ref_i = big_bank.search(q, K)
+    for G in (2, 8):
+        bounds = devqa_b200.dist.shard_bounds(N, G)
+        packed = []
+        for r in range(G):
+            lo, hi = bounds[r], bounds[r + 1]
+            shard = FactBank(D, capacity=hi - lo)
+            shard.append_synthetic(hi - lo, seed=3234, first_global_row=lo)
+            shard.set_id_map(lo)
+            packed.append(shard.search_packed(q, K))
+            shard.close()
+        s, i = topk_merge(torch.stack(packed), K)
+        assert torch.equal(i, ref_i) and torch.equal(s, ref_s)
+
+
+def test_chunked_id_map_on_device():
+    """Round-robin chunk ownership (appendable sharded bank): ids returned are global ids."""
+    n, d, chunk, world = 10_000, 64, 256, 4
+    g = torch.Generator().manual_seed(5)
+    rows = torch.nn.functional.normalize(torch.randn(n, d, generator=g), dim=1)
+    q = rows[[3, 300, 5000, 9999]].cuda()
+    full = FactBank.from_embeddings(rows)
+    ref_s, ref_i = full.search(q, 8)
+    packed = []
+    for r in range(world):
+        shard = FactBank(d)
+        shard.set_id_map(0, chunk, r, world)
+        for off, cnt in devqa_b200.dist.split_append(0, n, chunk, r, world):
+            shard.append(rows[off:off + cnt])
+        packed.append(shard.search_packed(q, 8))
+        shard.close()
+    s, i = topk_merge(torch.stack(packed), 8)
+    assert torch.equal(i, ref_i) and torch.equal(s, ref_s)
+    assert i[:, 0].cpu().tolist() == [3, 300, 5000, 9999]
+    full.close()

@@ -1,0 +1,123 @@
+"""The oracle against the golden vectors (reference glue executed in the build container) and
+against its own invariants.  CPU only."""
+import numpy as np
+import pytest
+import torch
+from hypothesis import given, settings, strategies as st
+
+from oracle import glue
+from oracle import semantic_search as ss
+from oracle.st_shim import StubEncoder
+
+
+def test_golden_bank_layout(golden):
+    """encode_ike_facts_multimodal layout (util.py:54-86): 3 rows per record, interleaved."""
+    recs, bank = golden["records"], golden["bank"]
+    assert len(bank["sentences"]) == 3 * len(recs) == len(golden["embeddings"])
+    rebuilt = glue.build_fact_bank(recs, StubEncoder())
+    assert rebuilt["sentences"] == bank["sentences"]
+    assert rebuilt["images"] == bank["images"]
+    assert rebuilt["prompts"] == bank["prompts"]
+    np.testing.assert_array_equal(rebuilt["embeddings"], golden["embeddings"])
+
+
+def test_golden_finds_sim(golden):
+    """oracle.glue.finds_sim == the reference's finds_sim (dataset/vllm.py:65-87) on 60 cases."""
+    enc = StubEncoder()
+    bank = ss.normalize_embeddings(torch.tensor(golden["embeddings"]))
+    for case in golden["finds_sim"]:
+        ex, img = glue.finds_sim(enc, bank, golden["bank"]["prompts"], golden["bank"]["images"],
+                                 case["src"], case["trg"])
+        assert list(ex) == case["example"] and img == case["image"]
+        q = ss.normalize_embeddings(torch.tensor(enc.encode(case["src"])).unsqueeze(0))
+        hits = ss.semantic_search(q, bank, score_function=ss.dot_score, top_k=5)[0]
+        assert [h["corpus_id"] for h in hits] == case["hit_ids"]
+        np.testing.assert_allclose([h["score"] for h in hits], case["hit_scores"], rtol=1e-6)
+
+
+def test_golden_lookups(golden):
+    """IKE / HICE / select_icl_samples restatements == the reference functions' outputs."""
+    enc = StubEncoder()
+    emb = torch.tensor(golden["embeddings"])
+    sents = golden["bank"]["sentences"]
+    for case in golden["lookups"]:
+        ike = glue.ike_demos(enc, emb, sents, case["prompt"], case["target"], golden["k"])
+        assert ike[:-1] == [sents[i] for i in case["ike_ids"]] and ike[-1] == case["ike_tail"]
+        hice = glue.hice_demos(enc, emb, sents, case["prompt"], case["target"], golden["k"])
+        assert hice[:-1] == [sents[i] for i in case["hice_ids"]] and hice[-1] == case["hice_tail"]
+        sel = glue.select_icl_samples(enc, emb, sents, case["prompt"], case["target"], golden["k"])
+        assert sel == [sents[i] for i in case["select_ids"]]
+        sel40 = glue.select_icl_samples(enc, emb, sents, case["prompt"], case["target"], 40)
+        assert sel40 == [sents[i] for i in case["select_k40_ids"]]
+        assert len(''.join(sel40)) <= glue.DEMO_CHAR_CAP < len(''.join(sel40)) + 400
+
+
+def _rand(n, d, seed):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(n, d, generator=g)
+
+
+def test_semantic_search_matches_bruteforce():
+    q, b = _rand(7, 48, 1), _rand(300, 48, 2)
+    hits = ss.semantic_search(q, b, score_function=ss.dot_score, top_k=10)
+    full = (q @ b.T).numpy()
+    for i, row in enumerate(hits):
+        want = np.argsort(-full[i], kind="stable")[:10]
+        assert [h["corpus_id"] for h in row] == want.tolist()
+        assert all(row[j]["score"] >= row[j + 1]["score"] for j in range(9))
+
+
+def test_chunk_edges_are_invisible():
+    """Results do not depend on the (query, corpus) chunking."""
+    q, b = _rand(5, 16, 3), _rand(257, 16, 4)
+    ref = ss.semantic_search(q, b, score_function=ss.dot_score, top_k=8)
+    for qc, cc in [(1, 64), (2, 100), (100, 256), (3, 257), (5, 1)]:
+        got = ss.semantic_search(q, b, query_chunk_size=qc, corpus_chunk_size=cc, score_function=ss.dot_score, top_k=8)
+        assert [[h["corpus_id"] for h in r] for r in got] == [[h["corpus_id"] for h in r] for r in ref]
+
+
+def test_k_larger_than_corpus_and_1d_query():
+    b = _rand(3, 8, 5)
+    hits = ss.semantic_search(b[0], b, score_function=ss.dot_score, top_k=5)
+    assert len(hits) == 1 and len(hits[0]) == 3 and hits[0][0]["corpus_id"] == 0
+
+
+def test_normalisation_variants():
+    x = _rand(6, 12, 6)
+    x[2] = 0
+    a = ss.normalize_embeddings(x)
+    assert torch.all(a[2] == 0) and torch.allclose(a[0].norm(), torch.tensor(1.0), atol=1e-6)
+    b = ss.normalize_noeps(x)
+    assert torch.isnan(b[2]).all() and torch.allclose(b[0], a[0], atol=1e-7)
+    np.testing.assert_allclose(ss.cos_sim(x[:2], x[3:]).numpy(),
+                               ss.dot_score(a[:2], a[3:]).numpy(), rtol=1e-6, atol=1e-7)
+
+
+def test_default_score_function_is_cos_sim():
+    q, b = _rand(2, 8, 7), _rand(20, 8, 8) * 5
+    got = ss.semantic_search(q, b, top_k=3)
+    want = ss.semantic_search(ss.normalize_embeddings(q), ss.normalize_embeddings(b), score_function=ss.dot_score, top_k=3)
+    assert [[h["corpus_id"] for h in r] for r in got] == [[h["corpus_id"] for h in r] for r in want]
+
+
+@settings(max_examples=40, deadline=None)
+@given(n=st.integers(1, 80), d=st.integers(1, 24), nq=st.integers(1, 5), k=st.integers(1, 40), seed=st.integers(0, 10**6))
+def test_search_arrays_vs_fp64_truth(n, d, nq, k, seed):
+    q, b = _rand(nq, d, seed), _rand(n, d, seed + 1)
+    scores, ids = ss.search_arrays(q, b, k, normalize_bank="eps", normalize_query="eps")
+    truth = ss.truth_scores_fp64(q, b)
+    stats = ss.compare_topk(scores, ids, truth, k, gap=1e-5, rtol=1e-5, atol=1e-6)
+    assert stats["k"] == min(k, n)
+
+
+def test_compare_topk_detects_errors():
+    q, b = _rand(3, 16, 11), _rand(50, 16, 12)
+    scores, ids = ss.search_arrays(q, b, 5, "eps", "eps")
+    truth = ss.truth_scores_fp64(q, b)
+    ss.compare_topk(scores, ids, truth, 5)
+    bad = ids.copy(); bad[1, 0], bad[1, 1] = ids[1, 1], ids[1, 0]
+    with pytest.raises(AssertionError):
+        ss.compare_topk(scores, bad, truth, 5)
+    bad_s = scores.copy(); bad_s[0, 0] *= 1.001
+    with pytest.raises(AssertionError):
+        ss.compare_topk(bad_s, ids, truth, 5)
