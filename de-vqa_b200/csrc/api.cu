@@ -36,6 +36,7 @@ struct Scratch {
   void* pin_io = nullptr;     size_t pin_io_bytes = 0;     // pinned mirror
   uint64_t* keys = nullptr;   size_t keys_bytes = 0;       // packed local top-k (dist)
   uint64_t* gathered = nullptr; size_t gathered_bytes = 0; // all-gather target (dist)
+  void* tiny = nullptr;       size_t tiny_bytes = 0;       // padded copy of banks shorter than one row group
   cudaStream_t last_stream = nullptr;
   cudaEvent_t done = nullptr;
   // optional per-kernel timing (devqa_profile_*): event pairs around the scan passes of each search
@@ -129,7 +130,6 @@ static int run_search(Scratch* s, const SearchArgs& a, uint64_t* out_keys, float
   const size_t esz = a.dtype == DEVQA_F32 ? 4 : 2;
   const bool vectorised = (a.dim % nv_vec == 0) && (a.bank_ld % nv_vec == 0) &&
                           (reinterpret_cast<uintptr_t>(a.bank) % 16 == 0);
-  (void)esz;
   const int nv = vectorised ? nv_vec : 1;
   // widest query tile whose shared-memory footprint fits
   int qt = 8;
@@ -148,8 +148,18 @@ static int run_search(Scratch* s, const SearchArgs& a, uint64_t* out_keys, float
   int rc = grow(reinterpret_cast<void**>(&s->cand), &s->cand_bytes, cand_bytes, false);
   if (rc) return rc;
 
+  const void* bank_ptr = a.bank;
+  if (a.n_rows > 0 && a.n_rows < 8) {
+    // the scan kernel reads whole groups of up to 8 rows: give it a zero-padded copy (rows >= n_rows are masked)
+    const size_t row_bytes = size_t(a.bank_ld) * esz;
+    if ((rc = grow(&s->tiny, &s->tiny_bytes, 8 * row_bytes, false))) return rc;
+    DEVQA_CUDA(cudaMemsetAsync(s->tiny, 0, 8 * row_bytes, stream));
+    DEVQA_CUDA(cudaMemcpyAsync(s->tiny, a.bank, size_t(a.n_rows - 1) * row_bytes + size_t(a.dim) * esz,
+                               cudaMemcpyDeviceToDevice, stream));
+    bank_ptr = s->tiny;
+  }
   ScanParams p{};
-  p.bank = a.bank; p.n_rows = a.n_rows; p.dim = a.dim; p.bank_ld = a.bank_ld;
+  p.bank = bank_ptr; p.n_rows = a.n_rows; p.dim = a.dim; p.bank_ld = a.bank_ld;
   p.queries = a.queries; p.query_ld = a.query_ld; p.n_queries = int32_t(a.n_queries);
   p.top_k = a.top_k; p.kcap = kcap; p.flags = a.flags; p.cand = s->cand; p.idmap = a.idmap;
   const bool prof = s->profiling && s->prof_used < Scratch::kProfSlots;

@@ -61,26 +61,29 @@ __device__ __forceinline__ int transpose_index(int lane) {
   return i;
 }
 
-// ---- element loaders: NV columns per lane per chunk ---------------------------------------
+// ---- element loaders: NV columns per lane per chunk, kept PACKED in the register double buffer ----
 template <typename T, int NV>
 struct Loader;
 template <>
 struct Loader<float, 4> {
-  static __device__ __forceinline__ void load(const float* row, int col, float (&b)[4]) {
-    const float4 t = ld_stream_f4(reinterpret_cast<const float4*>(row + col));
-    b[0] = t.x; b[1] = t.y; b[2] = t.z; b[3] = t.w;
-  }
+  using Raw = float4;
+  static __device__ __forceinline__ Raw load(const float* p) { return ld_stream_f4(reinterpret_cast<const float4*>(p)); }
+  static __device__ __forceinline__ Raw zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+  static __device__ __forceinline__ void unpack(const Raw& t, float (&b)[4]) { b[0] = t.x; b[1] = t.y; b[2] = t.z; b[3] = t.w; }
 };
 template <>
 struct Loader<float, 1> {
-  static __device__ __forceinline__ void load(const float* row, int col, float (&b)[1]) {
-    b[0] = ld_stream_f1(row + col);
-  }
+  using Raw = float;
+  static __device__ __forceinline__ Raw load(const float* p) { return ld_stream_f1(p); }
+  static __device__ __forceinline__ Raw zero() { return 0.f; }
+  static __device__ __forceinline__ void unpack(const Raw& t, float (&b)[1]) { b[0] = t; }
 };
 template <>
 struct Loader<__nv_bfloat16, 8> {
-  static __device__ __forceinline__ void load(const __nv_bfloat16* row, int col, float (&b)[8]) {
-    const uint4 t = ld_stream_u4(reinterpret_cast<const uint4*>(row + col));
+  using Raw = uint4;
+  static __device__ __forceinline__ Raw load(const __nv_bfloat16* p) { return ld_stream_u4(reinterpret_cast<const uint4*>(p)); }
+  static __device__ __forceinline__ Raw zero() { return make_uint4(0u, 0u, 0u, 0u); }
+  static __device__ __forceinline__ void unpack(const Raw& t, float (&b)[8]) {
     b[0] = __uint_as_float(t.x << 16); b[1] = __uint_as_float(t.x & 0xffff0000u);
     b[2] = __uint_as_float(t.y << 16); b[3] = __uint_as_float(t.y & 0xffff0000u);
     b[4] = __uint_as_float(t.z << 16); b[5] = __uint_as_float(t.z & 0xffff0000u);
@@ -89,48 +92,125 @@ struct Loader<__nv_bfloat16, 8> {
 };
 template <>
 struct Loader<__nv_bfloat16, 1> {
-  static __device__ __forceinline__ void load(const __nv_bfloat16* row, int col, float (&b)[1]) {
-    b[0] = __bfloat162float(row[col]);
+  using Raw = float;
+  static __device__ __forceinline__ Raw load(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+  static __device__ __forceinline__ Raw zero() { return 0.f; }
+  static __device__ __forceinline__ void unpack(const Raw& t, float (&b)[1]) { b[0] = t; }
+};
+
+// Shared-memory query layout: chunk-major and lane-interleaved, so that inside the chunk loop a lane
+// reads its QT x (NV/4) float4 slices at compile-time offsets from ONE running pointer:
+//   NV >= 4 : float4 sq4[chunk][q][h][lane]   (h < NV/4)
+//   NV == 1 : float  sq [chunk][q][lane]
+template <int NV, int QT>
+__device__ __forceinline__ int query_slot(int col) {
+  constexpr int CH = 32 * NV;
+  const int c = col / CH, w = col % CH;
+  const int ln = w / NV, e = w % NV;
+  if constexpr (NV >= 4) return ((((c * QT) * (NV / 4) + e / 4) * 32 + ln) * 4) + (e % 4);   // + q * (NV/4)*128
+  else return (c * QT) * 32 + ln;                                                            // + q * 32
+}
+
+template <typename T, int NV, int QT, int R, bool NORM>
+struct ChunkMath {
+  static constexpr int V = QT * R;
+  using Raw = typename Loader<T, NV>::Raw;
+  static __device__ __forceinline__ void load_q(const float* qp, int q, float (&qv)[NV]) {
+    if constexpr (NV >= 4) {
+#pragma unroll
+      for (int h = 0; h < NV / 4; ++h) {
+        const float4 t = *reinterpret_cast<const float4*>(qp + (q * (NV / 4) + h) * 128);
+        qv[4 * h] = t.x; qv[4 * h + 1] = t.y; qv[4 * h + 2] = t.z; qv[4 * h + 3] = t.w;
+      }
+    } else {
+      qv[0] = qp[q * 32];
+    }
+  }
+  // v[q*R + r] += <bank chunk of row r, query q chunk>;  nr[r] += |bank chunk of row r|^2
+  static __device__ __forceinline__ void apply(const Raw (&raw)[R], const float* qp, float (&v)[V], float (&nr)[R]) {
+    if constexpr (R * NV <= 32) {
+      // all rows unpacked once, queries streamed from shared memory
+      float b[R][NV];
+#pragma unroll
+      for (int r = 0; r < R; ++r) Loader<T, NV>::unpack(raw[r], b[r]);
+#pragma unroll
+      for (int q = 0; q < QT; ++q) {
+        float qv[NV];
+        load_q(qp, q, qv);
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+          for (int e = 0; e < NV; ++e) v[q * R + r] = fmaf(b[r][e], qv[e], v[q * R + r]);
+      }
+      if constexpr (NORM) {
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+          for (int e = 0; e < NV; ++e) nr[r] = fmaf(b[r][e], b[r][e], nr[r]);
+      }
+    } else {
+      // wide packed rows (bf16 x 8 rows): hold the few queries, unpack one row at a time
+      static_assert(QT * NV <= 32, "query tile too wide for the row-outer order");
+      float qv[QT][NV];
+#pragma unroll
+      for (int q = 0; q < QT; ++q) load_q(qp, q, qv[q]);
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        float b[NV];
+        Loader<T, NV>::unpack(raw[r], b);
+#pragma unroll
+        for (int q = 0; q < QT; ++q)
+#pragma unroll
+          for (int e = 0; e < NV; ++e) v[q * R + r] = fmaf(b[e], qv[q][e], v[q * R + r]);
+        if constexpr (NORM) {
+#pragma unroll
+          for (int e = 0; e < NV; ++e) nr[r] = fmaf(b[e], b[e], nr[r]);
+        }
+      }
+    }
   }
 };
+
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
 
 template <typename T, int NV, int QT, int R, bool NORM>
 __global__ void __launch_bounds__(kScanThreads, 1) scan_stream_kernel(const ScanParams p) {
   constexpr int V = QT * R;
+  constexpr int CH = 32 * NV;                       // columns one warp covers per chunk
+  constexpr int QSTEP = NV >= 4 ? QT * (NV / 4) * 128 : QT * 32;   // floats of query smem per chunk
   static_assert(V <= 32 && (V & (V - 1)) == 0, "QT*R must be a power of two <= 32");
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int dim = int(p.dim);
-  const int nchunks = (dim + 32 * NV - 1) / (32 * NV);
-  const int dpad = nchunks * 32 * NV;
+  const int nchunks = (dim + CH - 1) / CH;
+  const int dpad = nchunks * CH;
   const int kcap = p.kcap;
 
-  float* sq = reinterpret_cast<float*>(smem_raw);                                  // [QT][dpad]
+  float* sq = reinterpret_cast<float*>(smem_raw);                                   // [nchunks][QT][NV/4][32] x4
   uint64_t* lists = reinterpret_cast<uint64_t*>(smem_raw + size_t(QT) * dpad * 4);  // [warps][QT][kcap]
 
   // ---- prologue: stage (and optionally normalise) this pass's queries; clear the lists --------
   for (int q = warp; q < QT; q += kScanWarps) {
-    float* dst = sq + size_t(q) * dpad;
+    float* dst = sq + (NV >= 4 ? q * (NV / 4) * 128 : q * 32);
+    float inv = 0.f;                                 // dead queries are staged as zeros
+    const float* src = p.queries;
     if (q < p.nq_pass) {
-      const float* src = p.queries + size_t(p.q0 + q) * p.query_ld;
-      float ss = 0.f;
-      for (int c = lane; c < dpad; c += 32) {
-        const float x = c < dim ? src[c] : 0.f;
-        dst[c] = x;
-        ss = fmaf(x, x, ss);
-      }
+      src = p.queries + size_t(p.q0 + q) * p.query_ld;
+      inv = 1.f;
       if (p.flags & DEVQA_NORMALIZE_QUERY) {
+        float ss = 0.f;
+        for (int c = lane; c < dim; c += 32) { const float x = src[c]; ss = fmaf(x, x, ss); }
 #pragma unroll
         for (int off = 16; off >= 1; off >>= 1) ss += __shfl_xor_sync(kFull, ss, off);
         const float nrm = sqrtf(ss);
-        const float inv = 1.0f / ((p.flags & DEVQA_NOEPS) ? nrm : fmaxf(nrm, kNormEps));
-        __syncwarp();
-        for (int c = lane; c < dpad; c += 32) dst[c] *= inv;
+        inv = 1.0f / ((p.flags & DEVQA_NOEPS) ? nrm : fmaxf(nrm, kNormEps));
       }
-    } else {
-      for (int c = lane; c < dpad; c += 32) dst[c] = 0.f;
     }
+    for (int c = lane; c < dpad; c += 32)
+      dst[query_slot<NV, QT>(c)] = (c < dim && q < p.nq_pass) ? src[c] * inv : 0.f;
   }
   for (int i = threadIdx.x; i < kScanWarps * QT * kcap; i += kScanThreads) lists[i] = kEmptyKey;
   __syncthreads();
@@ -145,14 +225,41 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_stream_kernel(const Scan
 
   const int64_t n_groups = (p.n_rows + R - 1) / R;
   const int64_t warp_stride = int64_t(gridDim.x) * kScanWarps;
-  for (int64_t g = int64_t(blockIdx.x) * kScanWarps + warp; g < n_groups; g += warp_stride) {
-    const int64_t row0 = g * R;
-    const T* rp[R];
+  const int lane_col = lane * NV;
+  const T* const bank = static_cast<const T*>(p.bank);
+  const float* const sq_lane = sq + (NV >= 4 ? lane * 4 : lane);
+
+  using Raw = typename Loader<T, NV>::Raw;
+  // Row groups are R consecutive rows.  The last group is shifted back so that it still reads R
+  // in-bounds rows (rows it shares with the previous group are masked), which keeps all row
+  // pointers of a group at a fixed stride.  The host pads banks shorter than R rows.
+  const int64_t max_base = (p.n_rows > R ? p.n_rows : R) - R;
+  const int64_t ld = p.bank_ld;
+  int64_t g = int64_t(blockIdx.x) * kScanWarps + warp;
+  const T* rp[R];                                    // lane's position in chunk 0 of each row of group g
+  Raw b[R];                                          // the chunk being multiplied (register double buffer)
+  int64_t base = g * R < max_base ? g * R : max_base;
 #pragma unroll
-    for (int r = 0; r < R; ++r) {
-      int64_t row = row0 + r;
-      if (row >= p.n_rows) row = p.n_rows - 1;       // clamp: loads stay in bounds, result is masked
-      rp[r] = static_cast<const T*>(p.bank) + row * p.bank_ld;
+  for (int r = 0; r < R; ++r) rp[r] = bank + (base + r) * ld + lane_col;
+  if (g < n_groups && lane_col < dim) {
+#pragma unroll
+    for (int r = 0; r < R; ++r) b[r] = Loader<T, NV>::load(rp[r]);
+  } else {
+#pragma unroll
+    for (int r = 0; r < R; ++r) b[r] = Loader<T, NV>::zero();
+  }
+
+  while (g < n_groups) {
+    const int64_t gn = g + warp_stride;
+    const bool has_next = gn < n_groups;
+    const int64_t base_n = gn * R < max_base ? gn * R : max_base;
+    if (has_next) {                                  // pull the next group's rows into L2 a whole group ahead
+      const int row_bytes = dim * int(sizeof(T));
+      const char* nb = reinterpret_cast<const char*>(bank + base_n * ld);
+#pragma unroll
+      for (int r = 0; r < R; ++r)
+        for (int off = lane * 128; off < row_bytes; off += 32 * 128)
+          prefetch_l2(nb + r * ld * int64_t(sizeof(T)) + off);
     }
     float v[V];
     float nr[R];
@@ -161,42 +268,36 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_stream_kernel(const Scan
 #pragma unroll
     for (int r = 0; r < R; ++r) nr[r] = 0.f;
 
+    const float* qp = sq_lane;
 #pragma unroll 2
-    for (int c = 0; c < nchunks; ++c) {
-      const int col = (c * 32 + lane) * NV;
-      float b[R][NV];
-      if (col < dim) {
+    for (int c = 1; c < nchunks; ++c) {              // multiply chunk c-1 while chunk c is in flight
+      Raw bn[R];
+      if (lane_col + c * CH < dim) {
 #pragma unroll
-        for (int r = 0; r < R; ++r) Loader<T, NV>::load(rp[r], col, b[r]);
+        for (int r = 0; r < R; ++r) bn[r] = Loader<T, NV>::load(rp[r] + c * CH);
       } else {
 #pragma unroll
-        for (int r = 0; r < R; ++r)
-#pragma unroll
-          for (int e = 0; e < NV; ++e) b[r][e] = 0.f;
+        for (int r = 0; r < R; ++r) bn[r] = Loader<T, NV>::zero();
       }
+      ChunkMath<T, NV, QT, R, NORM>::apply(b, qp, v, nr);
+      qp += QSTEP;
 #pragma unroll
-      for (int q = 0; q < QT; ++q) {
-        float qv[NV];
-        if constexpr (NV >= 4) {
+      for (int r = 0; r < R; ++r) b[r] = bn[r];
+    }
+    {                                                // last chunk: chunk 0 of the NEXT group is in flight
+      Raw bn[R];
 #pragma unroll
-          for (int h = 0; h < NV / 4; ++h) {
-            const float4 t = *reinterpret_cast<const float4*>(sq + size_t(q) * dpad + col + 4 * h);
-            qv[4 * h] = t.x; qv[4 * h + 1] = t.y; qv[4 * h + 2] = t.z; qv[4 * h + 3] = t.w;
-          }
-        } else {
-          qv[0] = sq[size_t(q) * dpad + col];
-        }
+      for (int r = 0; r < R; ++r) rp[r] = bank + (base_n + r) * ld + lane_col;
+      if (has_next && lane_col < dim) {
 #pragma unroll
-        for (int r = 0; r < R; ++r)
+        for (int r = 0; r < R; ++r) bn[r] = Loader<T, NV>::load(rp[r]);
+      } else {
 #pragma unroll
-          for (int e = 0; e < NV; ++e) v[q * R + r] = fmaf(b[r][e], qv[e], v[q * R + r]);
+        for (int r = 0; r < R; ++r) bn[r] = Loader<T, NV>::zero();
       }
-      if constexpr (NORM) {
+      ChunkMath<T, NV, QT, R, NORM>::apply(b, qp, v, nr);
 #pragma unroll
-        for (int r = 0; r < R; ++r)
-#pragma unroll
-          for (int e = 0; e < NV; ++e) nr[r] = fmaf(b[r][e], b[r][e], nr[r]);
-      }
+      for (int r = 0; r < R; ++r) b[r] = bn[r];
     }
 
     float score = transpose_reduce<V>(v, lane);
@@ -206,8 +307,8 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_stream_kernel(const Scan
       const float nrm = sqrtf(ss);
       score *= 1.0f / ((p.flags & DEVQA_NOEPS) ? nrm : fmaxf(nrm, kNormEps));
     }
-    const int64_t row = row0 + my_r;
-    const bool live = q_live && row < p.n_rows;
+    const int64_t row = base + my_r;
+    const bool live = q_live && row >= g * R && row < p.n_rows;
     const uint64_t key = live ? pack_key(score, uint32_t(p.idmap(row))) : kEmptyKey;
     unsigned hit = __ballot_sync(kFull, key > thr);
     if (hit) {
@@ -220,6 +321,8 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_stream_kernel(const Scan
       }
       thr = my_lists[size_t(my_q) * kcap + (p.top_k - 1)];
     }
+    base = base_n;
+    g = gn;
   }
 
   // ---- epilogue: tree-merge the warps' lists, one sorted candidate list per (CTA, query) ------
@@ -259,7 +362,7 @@ template <typename T, int NV>
 int launch_qt(const ScanParams& p, int qt, int grid, cudaStream_t stream) {
   switch (qt) {
     case 8: return launch_variant<T, NV, 8, 4>(p, grid, stream);
-    case 4: return launch_variant<T, NV, 4, 8>(p, grid, stream);
+    case 4: return launch_variant<T, NV, 4, 4>(p, grid, stream);
     case 2: return launch_variant<T, NV, 2, 8>(p, grid, stream);
     default: return launch_variant<T, NV, 1, 8>(p, grid, stream);
   }
@@ -272,7 +375,7 @@ size_t scan_stream_smem_bytes(int64_t dim, int nv, int qt, int kcap) {
   return size_t(qt) * nchunks * 32 * nv * 4 + size_t(kScanWarps) * qt * kcap * 8;
 }
 
-int scan_stream_rows_per_group(int qt) { return qt == 8 ? 4 : 8; }
+int scan_stream_rows_per_group(int qt) { return qt >= 4 ? 4 : 8; }
 
 // One pass: queries [q0, q0 + nq_pass) against the whole bank.  `qt` in {1,2,4,8} >= nq_pass.
 int scan_stream_launch(const ScanParams& p, int bank_dtype, bool vectorised, int qt, int grid,
