@@ -363,8 +363,8 @@ int launch_qt(const ScanParams& p, int qt, int grid, cudaStream_t stream) {
   switch (qt) {
     case 8: return launch_variant<T, NV, 8, 4>(p, grid, stream);
     case 4: return launch_variant<T, NV, 4, 4>(p, grid, stream);
-    case 2: return launch_variant<T, NV, 2, 8>(p, grid, stream);
-    default: return launch_variant<T, NV, 1, 8>(p, grid, stream);
+    case 2: return launch_variant<T, NV, 2, 4>(p, grid, stream);
+    default: return launch_variant<T, NV, 1, 4>(p, grid, stream);
   }
 }
 
@@ -375,7 +375,7 @@ size_t scan_stream_smem_bytes(int64_t dim, int nv, int qt, int kcap) {
   return size_t(qt) * nchunks * 32 * nv * 4 + size_t(kScanWarps) * qt * kcap * 8;
 }
 
-int scan_stream_rows_per_group(int qt) { return qt >= 4 ? 4 : 8; }
+int scan_stream_rows_per_group(int qt) { return 4; }
 
 // One pass: queries [q0, q0 + nq_pass) against the whole bank.  `qt` in {1,2,4,8} >= nq_pass.
 int scan_stream_launch(const ScanParams& p, int bank_dtype, bool vectorised, int qt, int grid,
