@@ -46,6 +46,7 @@ def parse_args():
     ap.add_argument("--bank-dtype", default="fp32", choices=["fp32", "bf16"])
     ap.add_argument("--cpu-sample-rows", type=int, default=1_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--flags", type=int, default=0, help="extra DEVQA_* flag bits (debugging)")
     return ap.parse_args()
 
 
@@ -233,7 +234,7 @@ def run_ours(a):
 
     # ---- device-resident throughput ----------------------------------------------------------
     for _ in range(max(a.warmup, 3)):
-        out = bank.search(q_dev, a.topk)
+        out = bank.search(q_dev, a.topk, flags=a.flags)
     barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -244,7 +245,7 @@ def run_ours(a):
     t_wall0 = time.perf_counter()
     ev0.record()
     for _ in range(a.steps):
-        out = bank.search(q_dev, a.topk)
+        out = bank.search(q_dev, a.topk, flags=a.flags)
     ev1.record()
     barrier()
     t_wall1 = time.perf_counter()

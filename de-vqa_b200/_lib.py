@@ -22,6 +22,7 @@ SIGNATURES = {
     "devqa_version": (_i, []),
     "devqa_last_error": (C.c_char_p, []),
     "devqa_launch_count": (_i64, []),
+    "devqa_debug_tc_trace": (_i, [_p]),
     "devqa_profile_enable": (_i, [_i, _i]),
     "devqa_profile_collect": (_i, [_i, C.POINTER(C.c_double), C.POINTER(_i64), C.POINTER(_i64)]),
     "devqa_search_raw": (_i, [_p, _i, _i64, _i64, _i64, _p, _i64, _i64, _i, _u, _i64, _p, _p, _p]),

@@ -37,6 +37,7 @@ struct Scratch {
   uint64_t* keys = nullptr;   size_t keys_bytes = 0;       // packed local top-k (dist)
   uint64_t* gathered = nullptr; size_t gathered_bytes = 0; // all-gather target (dist)
   void* tiny = nullptr;       size_t tiny_bytes = 0;       // padded copy of banks shorter than one row group
+  float* qsplit = nullptr;    size_t qsplit_bytes = 0;     // TF32 hi / lo query planes of the tcgen05 scan
   cudaStream_t last_stream = nullptr;
   cudaEvent_t done = nullptr;
   // optional per-kernel timing (devqa_profile_*): event pairs around the scan passes of each search
@@ -131,6 +132,54 @@ static int run_search(Scratch* s, const SearchArgs& a, uint64_t* out_keys, float
   const bool vectorised = (a.dim % nv_vec == 0) && (a.bank_ld % nv_vec == 0) &&
                           (reinterpret_cast<uintptr_t>(a.bank) % 16 == 0);
   const int nv = vectorised ? nv_vec : 1;
+  int rc;
+  // ---- kernel selection (by batch size only, so that every shard of a sharded bank picks the same one) ----
+  // Q <= 8: one pass of the HBM-bound CUDA-core stream.  Larger batches: tcgen05 contraction (fp32 banks).
+  const bool tc_ok = scan_tc_supported(a.dtype, a.bank, a.dim, a.bank_ld, a.top_k) && a.n_rows > 0;
+  bool use_tc = tc_ok && a.n_queries > 8;
+  if (a.flags & DEVQA_FORCE_STREAM) use_tc = false;
+  if (a.flags & DEVQA_FORCE_TENSOR) {
+    if (!tc_ok) {
+      set_error("DEVQA_FORCE_TENSOR: the tcgen05 scan needs an fp32 bank with 16-byte aligned rows and top_k <= 128");
+      return DEVQA_E_UNSUPPORTED;
+    }
+    use_tc = true;
+  }
+
+  ScanParams p{};
+  p.n_rows = a.n_rows; p.dim = a.dim; p.bank_ld = a.bank_ld;
+  p.queries = a.queries; p.query_ld = a.query_ld; p.n_queries = int32_t(a.n_queries);
+  p.top_k = a.top_k; p.kcap = kcap; p.flags = a.flags; p.idmap = a.idmap;
+  int grid = 1;
+
+  if (use_tc) {
+    int qp = 0, stages = 0;
+    if ((rc = scan_tc_plan(int(a.n_queries), a.dim, kcap, &qp, &stages))) return rc;
+    const int q_pad = int((a.n_queries + qp - 1) / qp) * qp;
+    const int d_pad = scan_tc_dim_pad(a.dim);
+    const size_t plane = size_t(q_pad) * d_pad;
+    if ((rc = grow(reinterpret_cast<void**>(&s->qsplit), &s->qsplit_bytes, 2 * plane * 4, false))) return rc;
+    const int64_t tiles = (a.n_rows + 127) / 128;
+    grid = int(tiles < s->sm_count ? tiles : s->sm_count);
+    if ((rc = grow(reinterpret_cast<void**>(&s->cand), &s->cand_bytes, size_t(grid) * a.n_queries * kcap * 8, false))) return rc;
+    p.bank = a.bank; p.cand = s->cand;
+    const bool prof = s->profiling && s->prof_used < Scratch::kProfSlots;
+    if (prof) DEVQA_CUDA(cudaEventRecord(s->prof_ev[2 * s->prof_used], stream));
+    if ((rc = scan_tc_prep_queries(a.queries, a.query_ld, int(a.n_queries), q_pad, a.dim, a.flags, s->qsplit,
+                                   s->qsplit + plane, stream))) return rc;
+    for (int64_t q0 = 0; q0 < a.n_queries; q0 += qp) {
+      p.q0 = int32_t(q0);
+      p.nq_pass = int32_t(a.n_queries - q0 < qp ? a.n_queries - q0 : qp);
+      if ((rc = scan_tc_launch(p, s->qsplit, s->qsplit + plane, qp, stages, grid, stream))) return rc;
+      if (prof) s->prof_scan_launches++;
+    }
+    if (prof) {
+      DEVQA_CUDA(cudaEventRecord(s->prof_ev[2 * s->prof_used + 1], stream));
+      s->prof_used++;
+    }
+    return merge_lists_launch(s->cand, grid, a.n_queries, kcap, kcap, a.top_k, out_keys, out_scores, out_ids, stream);
+  }
+
   // widest query tile whose shared-memory footprint fits
   int qt = 8;
   while (qt > 1 && (qt / 2 >= a.n_queries || scan_stream_smem_bytes(a.dim, nv, qt, kcap) > 200 * 1024)) qt >>= 1;
@@ -141,12 +190,11 @@ static int run_search(Scratch* s, const SearchArgs& a, uint64_t* out_keys, float
   const int R = scan_stream_rows_per_group(qt);
   const int64_t groups = (a.n_rows + R - 1) / R;
   int64_t want_ctas = (groups + (kScanThreads / 32) - 1) / (kScanThreads / 32);
-  int grid = int(want_ctas < s->sm_count ? want_ctas : s->sm_count);
+  grid = int(want_ctas < s->sm_count ? want_ctas : s->sm_count);
   if (grid < 1) grid = 1;
 
   const size_t cand_bytes = size_t(grid) * a.n_queries * kcap * 8;
-  int rc = grow(reinterpret_cast<void**>(&s->cand), &s->cand_bytes, cand_bytes, false);
-  if (rc) return rc;
+  if ((rc = grow(reinterpret_cast<void**>(&s->cand), &s->cand_bytes, cand_bytes, false))) return rc;
 
   const void* bank_ptr = a.bank;
   if (a.n_rows > 0 && a.n_rows < 8) {
@@ -158,10 +206,7 @@ static int run_search(Scratch* s, const SearchArgs& a, uint64_t* out_keys, float
                                cudaMemcpyDeviceToDevice, stream));
     bank_ptr = s->tiny;
   }
-  ScanParams p{};
-  p.bank = bank_ptr; p.n_rows = a.n_rows; p.dim = a.dim; p.bank_ld = a.bank_ld;
-  p.queries = a.queries; p.query_ld = a.query_ld; p.n_queries = int32_t(a.n_queries);
-  p.top_k = a.top_k; p.kcap = kcap; p.flags = a.flags; p.cand = s->cand; p.idmap = a.idmap;
+  p.bank = bank_ptr; p.cand = s->cand;
   const bool prof = s->profiling && s->prof_used < Scratch::kProfSlots;
   if (prof) DEVQA_CUDA(cudaEventRecord(s->prof_ev[2 * s->prof_used], stream));
   for (int64_t q0 = 0; q0 < a.n_queries; q0 += qt) {
@@ -281,6 +326,11 @@ extern "C" {
 int devqa_version(void) { return DEVQA_VERSION; }
 const char* devqa_last_error(void) { return g_err; }
 int64_t devqa_launch_count(void) { return g_launches.load(); }
+
+int devqa_debug_tc_trace(int64_t* device_buf_16x256) {
+  scan_tc_set_trace(reinterpret_cast<long long*>(device_buf_16x256));
+  return DEVQA_OK;
+}
 
 int devqa_profile_enable(int device, int enable) {
   Scratch* s = nullptr;

@@ -1,0 +1,616 @@
+// Tensor-core scan: the large-query-batch kernel of the retrieval hot path (tcgen05 + TMEM + TMA).
+//
+// Same contract as scan_stream.cu (fused normalise + query x bank contraction + top-k, scores never
+// reach HBM), for batches where the CUDA-core kernel turns FFMA/issue bound.
+//
+//   scores[row, q] = sum_d bank[row, d] * query[q, d]            M = 128 bank rows / tile, N = queries
+//
+// fp32 parity on tensor cores: tcgen05.mma has no fp32-input kind, kind::tf32 reads fp32 words from
+// shared memory and ignores the low 13 mantissa bits.  So every operand is split x = hi + lo:
+//   * queries: a prep kernel normalises them and writes hi = rna_tf32(q), lo = rna_tf32(q - hi);
+//   * bank:    the raw fp32 tile IS the hi operand (the tensor core truncates it), and four "split"
+//              warps (thread <-> row) compute lo = a - trunc_tf32(a) and write it straight into TENSOR
+//              MEMORY (tcgen05.st; the second mma group reads its A operand from TMEM), accumulating
+//              ||row||^2 from the same registers (fused normalise).  Keeping the lo tile out of shared
+//              memory matters: the kernel is shared-memory-bandwidth bound (TMA writes + split reads +
+//              UMMA operand reads), and this removes 32 KB of that traffic per k-block.
+//   D[:, 0:Q)  = A . Qhi^T + Alo . Qhi^T        D[:, Q:2Q) = A . Qlo^T        (lo.lo is < 2^-21, dropped)
+// realised as TWO mma groups per 32-column k-block: A x [Qhi;Qlo] (N = 2Q, A read once) into TMEM
+// columns [0,2Q) and Alo x Qhi (N = Q) into columns [2Q,3Q).  The epilogue adds the three parts and
+// multiplies by 1/||row||.
+//
+// Tensor cores add into the fp32 accumulator with truncation, so a long K chain into one accumulator
+// drifts towards zero (measured 2e-5 relative at D = 4096 with outlier columns).  Two measures keep the
+// result inside the 1e-5 contract: the small lo terms never share columns with the large hi.hi term,
+// and the tensor core accumulates over at most one K-SET of 1024 columns (128 adds); K-sets of the
+// same tile alternate between the two TMEM buffers and are summed in fp32 round-to-nearest in the
+// epilogue threads' registers (MULTI instantiation, D > 1024).
+//
+// Warp roles (384 threads, 1 CTA/SM, persistent over 128-row tiles):
+//   warp 0      TMA producer   bank tile [128 x 32] fp32 + query k-block [2Q x 32] fp32, SWIZZLE_128B
+//   warp 1      MMA issuer     one thread, tcgen05.mma.cta_group::1.kind::tf32, commits to mbarriers
+//   warp 2      TMEM allocator (512 columns = two accumulator buffers)
+//   warps 4-7   split          lo tile -> TMEM (tcgen05.st) + row norms
+//   warps 8-11  epilogue       tcgen05.ld -> scale -> threshold filter -> per-query sorted lists (smem)
+// Pipelines: smem ring (full_tma / full_split / empty), TMEM double buffer (tmem_full / tmem_empty).
+#include <cuda.h>
+
+#include "scan.cuh"
+#include "topk.cuh"
+
+namespace devqa {
+namespace {
+
+constexpr int kTcThreads = 384;
+constexpr int kTileRows = 128;
+constexpr int kBlockK = 32;                          // fp32 columns per k-block = one 128-byte swizzle row
+constexpr int kATileBytes = kTileRows * kBlockK * 4; // 16 KB
+constexpr int kNormRing = 8;
+constexpr int kMaxStages = 8;
+constexpr int kPrefetchAhead = 12;                  // bank k-blocks pulled into L2 ahead of the smem ring
+constexpr int kSetKBlocks = 32;
+// undocumented debugging bits of `flags` (performance bisection only; results are wrong when set)
+constexpr unsigned kDbgNoInsert = 1u << 16, kDbgNoSplit = 1u << 17, kDbgNoMma2 = 1u << 18, kDbgNoQueryTma = 1u << 19, kDbgNoPrefetch = 1u << 20;                     // k-blocks (of 32 columns) accumulated inside the tensor core
+
+// ---- PTX wrappers ---------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return uint32_t(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t"
+      "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* map, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+// D[tmem] (+)= A[smem] . B[smem]^T, TF32 inputs, fp32 accumulate; one thread issues for the CTA
+__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// same, with the A operand read from tensor memory (lane = row, column = k)
+__device__ __forceinline__ void mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t addr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,"
+      "%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};"
+      ::"r"(addr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]),
+        "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]),
+        "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void mma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+template <int N>
+__device__ __forceinline__ void tmem_ld(uint32_t addr, uint32_t (&r)[N]);
+template <>
+__device__ __forceinline__ void tmem_ld<4>(uint32_t addr, uint32_t (&r)[4]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+template <>
+__device__ __forceinline__ void tmem_ld<8>(uint32_t addr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(addr));
+}
+template <>
+__device__ __forceinline__ void tmem_ld<16>(uint32_t addr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(addr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void epilogue_barrier() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (rows of 128 bytes, 8-row atoms of 1024 bytes):
+// start address >> 4 | SBO = 1024 >> 4 at bit 32 | descriptor version 1 at bit 46 | layout 2 at bit 61.
+__device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t smem_addr) {
+  return uint64_t((smem_addr & 0x3ffffu) >> 4) | (uint64_t(1024 >> 4) << 32) | (uint64_t(1) << 46) | (uint64_t(2) << 61);
+}
+// instruction descriptor: fp32 accumulate, TF32 A and B, both K-major, M = 128, N = n
+__host__ __device__ constexpr uint32_t idesc_tf32(int n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | (uint32_t(n >> 3) << 17) | (uint32_t(kTileRows >> 4) << 24);
+}
+
+struct TcParams {
+  int64_t n_rows;
+  int32_t dim;
+  int32_t n_kblocks;       // ceil(dim / 32)
+  int32_t n_tiles;         // ceil(n_rows / 128)
+  int32_t qp;              // queries in this pass, padded to a multiple of 16 (<= 128)
+  int32_t nq_pass;         // live queries in this pass
+  int32_t q0;              // first query of the pass (candidate layout)
+  int32_t n_queries;
+  int32_t top_k, kcap;
+  int32_t stages;
+  uint32_t flags;
+  uint64_t* cand;          // [grid, n_queries, kcap]
+  IdMap idmap;
+  long long* trace;        // optional [16][256] clock64 samples of CTA 0's roles (devqa_debug_tc_trace)
+};
+
+__device__ __forceinline__ void trace_at(const TcParams& p, int role, uint32_t idx) {
+  if (p.trace && blockIdx.x == 0 && idx < 256) p.trace[role * 256 + idx] = clock64();
+}
+
+struct SmemLayout {        // byte offsets from the 1024-aligned base
+  uint32_t a_raw, bq, lists, thr, scratch, norms, bars, tmem_slot, total;
+};
+__host__ __device__ inline SmemLayout tc_layout(int stages, int qp, int kcap) {
+  SmemLayout L;
+  uint32_t off = 0;
+  L.a_raw = off; off += uint32_t(stages) * kATileBytes;
+  L.bq = off;    off += uint32_t(stages) * uint32_t(2 * qp) * 128;           // [2*qp rows x 128 B], 1024-aligned since qp % 16 == 0
+  L.lists = off; off += uint32_t(qp) * kcap * 8;
+  L.thr = off;   off += uint32_t(qp) * 4;
+  L.scratch = off; off += uint32_t(qp < 32 ? qp : 32) * kTileRows * 4;   // score tile [HQ][128]
+  L.norms = off; off += kNormRing * kTileRows * 4;
+  off = (off + 7) & ~7u;
+  L.bars = off;  off += (3 * kMaxStages + 4) * 8;
+  L.tmem_slot = off; off += 16;
+  L.total = off;
+  return L;
+}
+
+// Epilogue phase B, slow path for one query: this warp owns the query's list exclusively.  `bits`
+// (4 per lane) marks which of the lane's four rows of the score tile beat the running threshold.
+// Deliberately out of line and loop-shaped (not unrolled): it must stay small and hot in the I-cache.
+__device__ __noinline__ void epilogue_insert_query(uint64_t* list, float* thr_j, int kcap, int top_k, float4 sc,
+                                                   uint32_t bits, int64_t row0, IdMap idmap, int lane) {
+  for (int t = 0; t < 4; ++t) {
+    const bool on = (bits >> t) & 1u;
+    unsigned m = __ballot_sync(kFull, on);
+    if (!m) continue;
+    const float st = t == 0 ? sc.x : (t == 1 ? sc.y : (t == 2 ? sc.z : sc.w));
+    const uint64_t mine = on ? pack_key(st, uint32_t(idmap(row0 + t))) : kEmptyKey;
+    if (kcap == 32 && __popc(m) >= 6) {
+      // burst (first tiles, thresholds still loose): sort the warp's candidates once and merge
+      const uint64_t sorted = warp_sort32_desc(mine, lane);
+      list[lane] = warp_merge32(list[lane], shfl_u64(sorted, 31 - lane), lane);
+      __syncwarp();
+    } else {
+      while (m) {
+        const int src = __ffs(m) - 1;
+        m &= m - 1;
+        warp_list_insert(list, kcap, top_k, shfl_u64(mine, src), lane);
+      }
+    }
+  }
+  if (lane == 0) {
+    const uint64_t kth = list[top_k - 1];
+    *thr_j = kth == kEmptyKey ? -INFINITY : key_score(kth);
+  }
+  __syncwarp();
+}
+
+template <int QP, bool MULTI>
+__global__ void __launch_bounds__(kTcThreads, 1)
+scan_tc_kernel(const __grid_constant__ CUtensorMap bank_map, const __grid_constant__ CUtensorMap qhi_map,
+               const __grid_constant__ CUtensorMap qlo_map, const __grid_constant__ TcParams p) {
+  extern __shared__ unsigned char smem_unaligned[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_unaligned) + 1023) & ~uintptr_t(1023));
+  const SmemLayout L = tc_layout(p.stages, p.qp, p.kcap);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int S = p.stages;
+  const uint32_t b_stage_bytes = uint32_t(2 * QP) * 128;
+
+  uint64_t* lists = reinterpret_cast<uint64_t*>(smem + L.lists);
+  float* thr = reinterpret_cast<float*>(smem + L.thr);
+  float* norms = reinterpret_cast<float*>(smem + L.norms);
+  uint64_t* full_tma = reinterpret_cast<uint64_t*>(smem + L.bars);
+  uint64_t* full_split = full_tma + kMaxStages;
+  uint64_t* empty = full_split + kMaxStages;
+  uint64_t* tmem_full = empty + kMaxStages;        // [2]
+  uint64_t* tmem_empty = tmem_full + 2;            // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L.tmem_slot);
+
+  // ---- one-time setup ------------------------------------------------------------------------
+  for (int i = threadIdx.x; i < QP * p.kcap; i += kTcThreads) lists[i] = kEmptyKey;
+  for (int i = threadIdx.x; i < QP; i += kTcThreads) thr[i] = -INFINITY;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&bank_map); tma_prefetch_desc(&qhi_map); tma_prefetch_desc(&qlo_map);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < S; ++s) { mbar_init(&full_tma[s], 1); mbar_init(&full_split[s], 128); mbar_init(&empty[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 128); }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  // TMEM columns: two accumulator buffers of 3*QP columns, then one 32-column lo tile per ring stage
+  constexpr uint32_t kAccCols = 3 * QP;
+  const uint32_t tmem_alo = tmem_base + 2 * kAccCols;
+  const int nkb = p.n_kblocks;
+  const int nsets = (nkb + kSetKBlocks - 1) / kSetKBlocks;   // accumulation units per tile (1 unless MULTI)
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      // The smem ring is shallow (16-48 KB per stage), so HBM latency is hidden one level up: bank
+      // k-blocks are prefetched into L2 kPrefetchAhead k-blocks ahead of the ring loads.
+      const int64_t total = int64_t((p.n_tiles - int(blockIdx.x) + int(gridDim.x) - 1) / int(gridDim.x)) * nkb;
+      auto prefetch = [&](int64_t idx) {
+        if (idx < total && !(p.flags & kDbgNoPrefetch)) {
+          const int t = int(blockIdx.x) + int(idx / nkb) * int(gridDim.x);
+          tma_prefetch_l2_2d(&bank_map, int(idx % nkb) * kBlockK, t * kTileRows);
+        }
+      };
+      for (int i = 0; i < kPrefetchAhead; ++i) prefetch(i);
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = it % S;
+          prefetch(int64_t(it) + kPrefetchAhead);
+          mbar_wait(&empty[s], ((it / S) & 1) ^ 1);
+          const bool qtma = !(p.flags & kDbgNoQueryTma);
+          mbar_expect_tx(&full_tma[s], kATileBytes + (qtma ? b_stage_bytes : 0u));
+          tma_load_2d(smem + L.a_raw + s * kATileBytes, &bank_map, &full_tma[s], kb * kBlockK, tile * kTileRows);
+          unsigned char* bq = smem + L.bq + s * b_stage_bytes;
+          if (qtma) {
+            tma_load_2d(bq, &qhi_map, &full_tma[s], kb * kBlockK, 0);
+            tma_load_2d(bq + QP * 128, &qlo_map, &full_tma[s], kb * kBlockK, 0);
+          }
+          trace_at(p, 0, it);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      const uint32_t idesc_cat = idesc_tf32(2 * QP), idesc_hi = idesc_tf32(QP);
+      uint32_t it = 0, unit = 0;
+      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+        for (int set = 0; set < nsets; ++set, ++unit) {
+          const int a = unit & 1;
+          mbar_wait(&tmem_empty[a], ((unit >> 1) & 1) ^ 1);
+          tc_fence_after();
+          const uint32_t d = tmem_base + uint32_t(a) * kAccCols;
+          const int kb_end = min(nkb, (set + 1) * kSetKBlocks);
+          for (int kb = set * kSetKBlocks; kb < kb_end; ++kb, ++it) {
+            const int s = it % S;
+            const uint32_t ph = (it / S) & 1;
+            const uint32_t a_raw = smem_u32(smem + L.a_raw + s * kATileBytes);
+            const uint32_t bq = smem_u32(smem + L.bq + s * b_stage_bytes);
+            const uint32_t first = kb == set * kSetKBlocks ? 0u : 1u;
+            mbar_wait(&full_tma[s], ph);
+            tc_fence_after();
+            trace_at(p, 3, it);
+#pragma unroll
+            for (int kk = 0; kk < kBlockK / 8; ++kk)      // A(hi by truncation) x [Qhi ; Qlo] -> cols [0, 2QP)
+              mma_tf32(d, smem_desc_sw128(a_raw + kk * 32), smem_desc_sw128(bq + kk * 32), idesc_cat, first | uint32_t(kk));
+            mbar_wait(&full_split[s], ph);
+            tc_fence_after();
+            trace_at(p, 4, it);
+            if (!(p.flags & kDbgNoMma2))
+#pragma unroll
+            for (int kk = 0; kk < kBlockK / 8; ++kk)      // Alo x Qhi -> cols [2QP, 3QP)
+              mma_tf32_ts(d + 2 * QP, tmem_alo + uint32_t(s) * kBlockK + kk * 8, smem_desc_sw128(bq + kk * 32), idesc_hi, first | uint32_t(kk));
+            mma_commit(&empty[s]);                        // frees the stage when these MMAs retire
+            trace_at(p, 5, it);
+          }
+          mma_commit(&tmem_full[a]);
+        }
+      }
+    }
+  } else if (warp >= 4 && warp < 8) {
+    // ===== split warps: thread <-> bank row of the tile =====
+    const int row = threadIdx.x - 128;
+    const uint32_t row_off = uint32_t(row) * 128;
+    const uint32_t sw = uint32_t(row & 7);                // 16-byte chunk c of row r lives at chunk c ^ (r & 7)
+    uint32_t it = 0, lt = 0;
+    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++lt) {
+      float ss[8];                                        // one partial sum per 16-byte chunk position
+#pragma unroll
+      for (int c = 0; c < 8; ++c) ss[c] = 0.f;
+      for (int kb = 0; kb < nkb; ++kb, ++it) {
+        const int s = it % S;
+        mbar_wait(&full_tma[s], (it / S) & 1);
+        if (row == 0) trace_at(p, 1, it);
+        const unsigned char* src = smem + L.a_raw + s * kATileBytes + row_off;
+        uint32_t lo[32];
+        if (!(p.flags & kDbgNoSplit)) {
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {                   // logical 16-byte chunk c of the row
+            const float4 v = *reinterpret_cast<const float4*>(src + (uint32_t(c) ^ sw) * 16);
+            lo[4 * c + 0] = __float_as_uint(v.x - __uint_as_float(__float_as_uint(v.x) & 0xffffe000u));
+            lo[4 * c + 1] = __float_as_uint(v.y - __uint_as_float(__float_as_uint(v.y) & 0xffffe000u));
+            lo[4 * c + 2] = __float_as_uint(v.z - __uint_as_float(__float_as_uint(v.z) & 0xffffe000u));
+            lo[4 * c + 3] = __float_as_uint(v.w - __uint_as_float(__float_as_uint(v.w) & 0xffffe000u));
+            ss[c] = fmaf(v.x, v.x, ss[c]); ss[c] = fmaf(v.y, v.y, ss[c]);
+            ss[c] = fmaf(v.z, v.z, ss[c]); ss[c] = fmaf(v.w, v.w, ss[c]);
+          }
+          // lane (= row) x 32 columns of this stage's lo tile; warp w may only touch TMEM lanes 32*(w%4)..
+          tmem_st32(tmem_alo + uint32_t(s) * kBlockK + (uint32_t((warp & 3) * 32) << 16), lo);
+          tmem_st_wait();
+        }
+        if (kb == nkb - 1)
+          norms[(lt % kNormRing) * kTileRows + row] = ((ss[0] + ss[1]) + (ss[2] + ss[3])) + ((ss[4] + ss[5]) + (ss[6] + ss[7]));
+        tc_fence_before();                                // TMEM writes ordered before the MMA issuer's reads
+        mbar_arrive(&full_split[s]);
+        if (row == 0) trace_at(p, 2, it);
+      }
+    }
+  } else if (warp >= 8) {
+    // ===== epilogue warps =====
+    // Phase A: thread <-> TMEM lane <-> bank row: sum the three accumulator parts, scale by 1/||row||
+    //          and drop the scores into a [query][row] shared-memory tile (HQ queries at a time).
+    // Phase B: warp e exclusively owns queries e*HQ/4 .. of the tile: it scans their 128 scores (one
+    //          float4 per lane), filters them against the running k-th score and inserts survivors into
+    //          the query's sorted list.  No locks; two 128-thread named barriers per half tile.
+    constexpr int HQ = QP < 32 ? QP : 32;                 // queries per score-tile fill
+    constexpr int HALVES = QP / HQ;
+    const int e = warp - 8;                               // TMEM lane quarter = warp % 4
+    const int row_in_tile = e * 32 + lane;
+    float* stile = reinterpret_cast<float*>(smem + L.scratch);        // [HQ][128]
+    const bool no_insert = (p.flags & kDbgNoInsert) != 0;
+    uint32_t lt = 0, unit = 0;
+    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++lt) {
+      float acc[MULTI ? QP : 1];                          // fp32 RN sum over the tile's K-sets
+      for (int set = 0; set < nsets; ++set, ++unit) {
+        const int a = unit & 1;
+        const bool last = set == nsets - 1;
+        mbar_wait(&tmem_full[a], (unit >> 1) & 1);
+        tc_fence_after();
+        if (e == 0 && lane == 0) trace_at(p, 6, unit);
+        float inv = 1.f;
+        if (last && (p.flags & DEVQA_NORMALIZE_BANK)) {
+          const float nrm = sqrtf(norms[(lt % kNormRing) * kTileRows + row_in_tile]);
+          inv = 1.0f / ((p.flags & DEVQA_NOEPS) ? nrm : fmaxf(nrm, kNormEps));
+        }
+        const uint32_t taddr = tmem_base + uint32_t(a) * kAccCols + (uint32_t(e * 32) << 16);
+#pragma unroll (MULTI ? HALVES : 1)
+        for (int h = 0; h < HALVES; ++h) {
+          // ---- phase A ----
+#pragma unroll
+          for (int c = 0; c < HQ / 16; ++c) {
+            const int j0 = h * HQ + c * 16;
+            uint32_t d1[16], d2[16], d3[16];
+            tmem_ld<16>(taddr + uint32_t(j0), d1);
+            tmem_ld<16>(taddr + uint32_t(QP + j0), d2);
+            tmem_ld<16>(taddr + uint32_t(2 * QP + j0), d3);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              float v = (__uint_as_float(d2[i]) + __uint_as_float(d3[i])) + __uint_as_float(d1[i]);
+              if constexpr (MULTI) {
+                v = set == 0 ? v : acc[j0 + i] + v;
+                acc[j0 + i] = v;
+              }
+              if (last) stile[(c * 16 + i) * kTileRows + row_in_tile] = v * inv;
+            }
+          }
+          if (h == HALVES - 1) {                          // every TMEM read of this buffer has completed
+            tc_fence_before();
+            mbar_arrive(&tmem_empty[a]);
+          }
+          if (!last) continue;
+          epilogue_barrier();
+          // ---- phase B ----
+          const int64_t row0 = int64_t(tile) * kTileRows + lane * 4;
+          uint32_t rowmask = 0;
+#pragma unroll
+          for (int t = 0; t < 4; ++t) rowmask |= (row0 + t < p.n_rows ? 1u : 0u) << t;
+          if (no_insert) rowmask = 0;
+          for (int i = 0; i < HQ / 4; ++i) {
+            const int jl = e * (HQ / 4) + i;
+            const int j = h * HQ + jl;
+            if (j >= p.nq_pass) break;                    // warp-uniform
+            const float4 sc = *reinterpret_cast<const float4*>(stile + jl * kTileRows + lane * 4);
+            const float th = thr[j];
+            uint32_t bits = (!(sc.x < th) ? 1u : 0u) | (!(sc.y < th) ? 2u : 0u) | (!(sc.z < th) ? 4u : 0u) | (!(sc.w < th) ? 8u : 0u);
+            bits &= rowmask;
+            if (__ballot_sync(kFull, bits != 0))
+              epilogue_insert_query(lists + size_t(j) * p.kcap, &thr[j], p.kcap, p.top_k, sc, bits, row0, p.idmap, lane);
+          }
+          epilogue_barrier();                             // the score tile may be overwritten again
+        }
+        if (e == 0 && lane == 0) trace_at(p, 7, unit);
+      }
+    }
+  }
+
+  // ---- teardown: candidates out, TMEM back ------------------------------------------------------
+  tc_fence_before();
+  __syncthreads();
+  for (int q = warp; q < p.nq_pass; q += kTcThreads / 32) {
+    uint64_t* out = p.cand + (size_t(blockIdx.x) * p.n_queries + (p.q0 + q)) * p.kcap;
+    const uint64_t* src = lists + size_t(q) * p.kcap;
+    for (int i = lane; i < p.kcap; i += 32) out[i] = src[i];
+  }
+  if (warp == 2) tmem_dealloc(tmem_base, 512);
+}
+
+// ---- query preparation: normalise, pad, split into TF32 hi / lo --------------------------------------
+__global__ void __launch_bounds__(256) prep_queries_kernel(const float* __restrict__ q, int64_t q_ld, int n_queries, int dim,
+                                                           int q_pad, int d_pad, unsigned flags, float* __restrict__ qhi,
+                                                           float* __restrict__ qlo) {
+  const int lane = threadIdx.x & 31;
+  const int warps = gridDim.x * (blockDim.x >> 5);
+  for (int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < q_pad; r += warps) {
+    float inv = 0.f;
+    const float* src = q + size_t(r < n_queries ? r : 0) * q_ld;
+    if (r < n_queries) {
+      inv = 1.f;
+      if (flags & DEVQA_NORMALIZE_QUERY) {
+        float ss = 0.f;
+        for (int c = lane; c < dim; c += 32) { const float x = src[c]; ss = fmaf(x, x, ss); }
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) ss += __shfl_xor_sync(kFull, ss, off);
+        const float nrm = sqrtf(ss);
+        inv = 1.0f / ((flags & DEVQA_NOEPS) ? nrm : fmaxf(nrm, kNormEps));
+      }
+    }
+    for (int c = lane; c < d_pad; c += 32) {
+      const float x = (r < n_queries && c < dim) ? src[c] * inv : 0.f;
+      uint32_t hb, lb;
+      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(x));
+      const float hi = __uint_as_float(hb);
+      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lb) : "f"(x - hi));
+      qhi[size_t(r) * d_pad + c] = hi;
+      qlo[size_t(r) * d_pad + c] = __uint_as_float(lb);
+    }
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int make_map(CUtensorMap* map, const void* base, uint64_t cols, uint64_t rows, uint64_t ld_bytes, uint32_t box_rows) {
+  static EncodeTiledFn encode = nullptr;
+  if (!encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) {
+      set_error("cuTensorMapEncodeTiled is not available from the driver");
+      return DEVQA_E_CUDA;
+    }
+    encode = reinterpret_cast<EncodeTiledFn>(fn);
+  }
+  const cuuint64_t gdim[2] = {cols, rows};
+  const cuuint64_t gstride[1] = {ld_bytes};
+  const cuuint32_t box[2] = {kBlockK, box_rows};
+  const cuuint32_t estride[2] = {1, 1};
+  CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), gdim, gstride, box, estride,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult %d (cols %llu rows %llu ld %llu)", int(r),
+              (unsigned long long)cols, (unsigned long long)rows, (unsigned long long)ld_bytes);
+    return DEVQA_E_CUDA;
+  }
+  return DEVQA_OK;
+}
+
+}  // namespace
+
+bool scan_tc_supported(int bank_dtype, const void* bank, int64_t dim, int64_t bank_ld, int top_k) {
+  return bank_dtype == DEVQA_F32 && reinterpret_cast<uintptr_t>(bank) % 16 == 0 && bank_ld % 4 == 0 && dim >= 1 &&
+         topk_capacity(top_k) <= 128;
+}
+
+int scan_tc_query_pad(int n_queries) { return (n_queries + 15) / 16 * 16; }
+int scan_tc_dim_pad(int64_t dim) { return int((dim + kBlockK - 1) / kBlockK * kBlockK); }
+
+// Queries per pass + pipeline depth that fit in shared memory for this k.
+int scan_tc_plan(int n_queries, int64_t dim, int kcap, int* qp_out, int* stages_out) {
+  // D > 1024 sums K-sets in the epilogue's registers (MULTI): 32 queries per pass at most
+  int qp = scan_tc_dim_pad(dim) > kSetKBlocks * kBlockK ? 32 : 64;
+  while (qp > 16 && qp / 2 >= scan_tc_query_pad(n_queries)) qp >>= 1;
+  for (; qp >= 16; qp >>= 1) {
+    for (int stages = kMaxStages; stages >= 3; --stages) {
+      if (6 * qp + stages * kBlockK > 512) continue;        // TMEM: 2 accumulator buffers + one lo tile per stage
+      if (tc_layout(stages, qp, kcap).total + 1024 <= 225 * 1024) {
+        *qp_out = qp; *stages_out = stages;
+        return DEVQA_OK;
+      }
+    }
+  }
+  set_error("tcgen05 scan: no shared-memory plan for kcap %d", kcap);
+  return DEVQA_E_UNSUPPORTED;
+}
+
+int scan_tc_prep_queries(const float* queries, int64_t query_ld, int n_queries, int q_pad, int64_t dim, unsigned flags,
+                         float* qhi, float* qlo, cudaStream_t stream) {
+  const int d_pad = scan_tc_dim_pad(dim);
+  const int grid = (q_pad + 7) / 8;
+  prep_queries_kernel<<<grid, 256, 0, stream>>>(queries, query_ld, n_queries, int(dim), q_pad, d_pad, flags, qhi, qlo);
+  DEVQA_CUDA(cudaGetLastError());
+  count_launch();
+  return DEVQA_OK;
+}
+
+// One pass: prepared queries [q0, q0 + nq_pass) (rows of qhi/qlo) against the whole bank.
+static long long* g_tc_trace = nullptr;
+void scan_tc_set_trace(long long* buf) { g_tc_trace = buf; }
+
+int scan_tc_launch(const ScanParams& sp, const float* qhi, const float* qlo, int qp, int stages, int grid,
+                   cudaStream_t stream) {
+  const int d_pad = scan_tc_dim_pad(sp.dim);
+  CUtensorMap bank_map, qhi_map, qlo_map;
+  int rc = make_map(&bank_map, sp.bank, uint64_t(sp.dim), uint64_t(sp.n_rows), uint64_t(sp.bank_ld) * 4, kTileRows);
+  if (rc) return rc;
+  const size_t qoff = size_t(sp.q0) * d_pad;
+  if ((rc = make_map(&qhi_map, qhi + qoff, uint64_t(d_pad), uint64_t(qp), uint64_t(d_pad) * 4, uint32_t(qp)))) return rc;
+  if ((rc = make_map(&qlo_map, qlo + qoff, uint64_t(d_pad), uint64_t(qp), uint64_t(d_pad) * 4, uint32_t(qp)))) return rc;
+  TcParams p{};
+  p.n_rows = sp.n_rows; p.dim = int(sp.dim); p.n_kblocks = d_pad / kBlockK;
+  p.n_tiles = int((sp.n_rows + kTileRows - 1) / kTileRows);
+  p.qp = qp; p.nq_pass = sp.nq_pass; p.q0 = sp.q0; p.n_queries = sp.n_queries;
+  p.top_k = sp.top_k; p.kcap = sp.kcap; p.stages = stages; p.flags = sp.flags; p.cand = sp.cand; p.idmap = sp.idmap;
+  p.trace = g_tc_trace;
+  const size_t smem = tc_layout(stages, qp, sp.kcap).total + 1024;
+  const bool multi = p.n_kblocks > kSetKBlocks;
+  void (*kern)(CUtensorMap, CUtensorMap, CUtensorMap, TcParams) = nullptr;
+  if (!multi) kern = qp == 64 ? scan_tc_kernel<64, false> : qp == 32 ? scan_tc_kernel<32, false> : scan_tc_kernel<16, false>;
+  else kern = qp == 32 ? scan_tc_kernel<32, true> : scan_tc_kernel<16, true>;
+  if (qp != 16 && qp != 32 && !(qp == 64 && !multi)) {
+    set_error("tcgen05 scan: unsupported queries-per-pass %d", qp);
+    return DEVQA_E_INVALID;
+  }
+  DEVQA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+  kern<<<grid, kTcThreads, smem, stream>>>(bank_map, qhi_map, qlo_map, p);
+  DEVQA_CUDA(cudaGetLastError());
+  count_launch();
+  return DEVQA_OK;
+}
+
+}  // namespace devqa

@@ -61,4 +61,18 @@ __device__ __forceinline__ uint64_t warp_merge32(uint64_t a, uint64_t b_rev, int
   return c;
 }
 
+// Bitonic sort of one key per lane, descending (lane 0 ends with the largest key).
+__device__ __forceinline__ uint64_t warp_sort32_desc(uint64_t v, int lane) {
+#pragma unroll
+  for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      const uint64_t o = shfl_xor_u64(v, j);
+      const bool keep_max = ((lane & j) == 0) == ((lane & k) == 0);
+      v = (keep_max == (v > o)) ? v : o;
+    }
+  }
+  return v;
+}
+
 }  // namespace devqa

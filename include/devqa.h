@@ -92,6 +92,10 @@ DEVQA_API int devqa_profile_enable(int device, int enable);
 DEVQA_API int devqa_profile_collect(int device, double* scan_ms_total, int64_t* scan_launches,
                                     int64_t* searches);
 
+/* Debugging aid: when set to a device buffer of 16 x 256 int64, CTA 0 of the tcgen05 scan records
+ * clock64() samples of its warp roles (producer, split, MMA, epilogue) into it.  NULL disables. */
+DEVQA_API int devqa_debug_tc_trace(int64_t* device_buf_16x256);
+
 /* ---- stateless search over a caller-owned bank -----------------------------------------
  * The literal replacement of  semantic_search(q, corpus, score_function=dot_score, top_k)
  * on CUDA tensors: `bank` is [n_rows, dim] with row stride `bank_ld` elements (>= dim),

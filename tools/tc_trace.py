@@ -1,0 +1,27 @@
+"""Print the per-role clock64 timeline of CTA 0 of the tcgen05 scan (debugging aid)."""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch, devqa_b200
+L = devqa_b200._lib
+rows, q, flags = int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3]) if len(sys.argv) > 3 else 0
+fb = devqa_b200.FactBank(768, capacity=rows)
+fb.append_synthetic(rows, 1)
+qs = torch.nn.functional.normalize(torch.randn(q, 768), dim=1).cuda()
+for _ in range(2):
+    fb.search(qs, 32, flags=L.FORCE_TENSOR | flags)
+buf = torch.zeros(16 * 256, dtype=torch.int64, device="cuda")
+L.check(L.lib().devqa_debug_tc_trace(buf.data_ptr()))
+fb.search(qs, 32, flags=L.FORCE_TENSOR | flags)
+torch.cuda.synchronize()
+L.lib().devqa_debug_tc_trace(None)
+t = buf.cpu().view(16, 256)
+t0 = int(t[0, 0])
+names = ["tma_issue", "split_got", "split_done", "mma_got_tma", "mma_got_split", "mma_commit", "epi_got", "epi_done"]
+n = 60
+for r in range(6):
+    print(names[r].ljust(14), " ".join(f"{int(x) - t0:7d}" if x else "      -" for x in t[r, :n]))
+for r in (6, 7):
+    print(names[r].ljust(14), " ".join(f"{int(x) - t0:7d}" if x else "      -" for x in t[r, :24]))
+print("warp0_passes".ljust(14), " ".join(f"{int(x):7d}" for x in t[8, :24]))
+for r, nm in ((13, "s0_ld_done"), (14, "s0_bits_done"), (9, "step0_body"), (10, "step0_bar"), (11, "step1_bar"), (12, "step2_bar")):
+    print(nm.ljust(14), " ".join(f"{int(x) - t0:7d}" if x else "      -" for x in t[r, :24]))
