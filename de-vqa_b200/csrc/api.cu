@@ -134,9 +134,11 @@ static int run_search(Scratch* s, const SearchArgs& a, uint64_t* out_keys, float
   const int nv = vectorised ? nv_vec : 1;
   int rc;
   // ---- kernel selection (by batch size only, so that every shard of a sharded bank picks the same one) ----
-  // Q <= 8: one pass of the HBM-bound CUDA-core stream.  Larger batches: tcgen05 contraction (fp32 banks).
+  // Q <= 4: one pass of the CUDA-core stream (measured 6.6-7.0 TB/s on 10M x 768).  Larger batches: the
+  // tcgen05 contraction (fp32 banks), which holds ~6.3 TB/s up to 16 queries per pass where the CUDA-core
+  // kernel turns issue-bound (5.4 TB/s at 8 queries, two passes beyond).
   const bool tc_ok = scan_tc_supported(a.dtype, a.bank, a.dim, a.bank_ld, a.top_k) && a.n_rows > 0;
-  bool use_tc = tc_ok && a.n_queries > 8;
+  bool use_tc = tc_ok && a.n_queries > 4;
   if (a.flags & DEVQA_FORCE_STREAM) use_tc = false;
   if (a.flags & DEVQA_FORCE_TENSOR) {
     if (!tc_ok) {
@@ -165,12 +167,12 @@ static int run_search(Scratch* s, const SearchArgs& a, uint64_t* out_keys, float
     p.bank = a.bank; p.cand = s->cand;
     const bool prof = s->profiling && s->prof_used < Scratch::kProfSlots;
     if (prof) DEVQA_CUDA(cudaEventRecord(s->prof_ev[2 * s->prof_used], stream));
-    if ((rc = scan_tc_prep_queries(a.queries, a.query_ld, int(a.n_queries), q_pad, a.dim, a.flags, s->qsplit,
-                                   s->qsplit + plane, stream))) return rc;
+    if ((rc = scan_tc_prep_queries(a.queries, a.query_ld, int(a.n_queries), qp, q_pad, a.dim, a.flags, s->qsplit, stream)))
+      return rc;
     for (int64_t q0 = 0; q0 < a.n_queries; q0 += qp) {
       p.q0 = int32_t(q0);
       p.nq_pass = int32_t(a.n_queries - q0 < qp ? a.n_queries - q0 : qp);
-      if ((rc = scan_tc_launch(p, s->qsplit, s->qsplit + plane, qp, stages, grid, stream))) return rc;
+      if ((rc = scan_tc_launch(p, s->qsplit, qp, stages, grid, stream))) return rc;
       if (prof) s->prof_scan_launches++;
     }
     if (prof) {

@@ -32,12 +32,10 @@ int scan_stream_launch(const ScanParams& p, int bank_dtype, bool vectorised, int
 bool scan_tc_supported(int bank_dtype, const void* bank, int64_t dim, int64_t bank_ld, int top_k);
 int scan_tc_dim_pad(int64_t dim);
 int scan_tc_plan(int n_queries, int64_t dim, int kcap, int* qp_out, int* stages_out);
-// queries -> normalised, zero-padded [q_pad, dim_pad] TF32 hi / lo planes
-int scan_tc_prep_queries(const float* queries, int64_t query_ld, int n_queries, int q_pad, int64_t dim, unsigned flags,
-                         float* qhi, float* qlo, cudaStream_t stream);
-int scan_tc_launch(const ScanParams& p, const float* qhi, const float* qlo, int qp, int stages, int grid,
-                   cudaStream_t stream);
-
+// queries -> normalised TF32 hi / lo split, laid out per pass as the MMA B operand (see scan_tc.cu)
+int scan_tc_prep_queries(const float* queries, int64_t query_ld, int n_queries, int qp, int q_pad, int64_t dim,
+                         unsigned flags, float* qcat, cudaStream_t stream);
+int scan_tc_launch(const ScanParams& p, const float* qcat, int qp, int stages, int grid, cudaStream_t stream);
 void scan_tc_set_trace(long long* buf);
 
 // merge.cu: reduce `n_lists` sorted lists per query ([n_lists, n_queries, list_stride], the first

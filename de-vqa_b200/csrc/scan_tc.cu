@@ -27,7 +27,10 @@
 // epilogue threads' registers (MULTI instantiation, D > 1024).
 //
 // Warp roles (384 threads, 1 CTA/SM, persistent over 128-row tiles):
-//   warp 0      TMA producer   bank tile [128 x 32] fp32 + query k-block [2Q x 32] fp32, SWIZZLE_128B
+//   warp 0      TMA producer   bank tile [128 x 32] fp32 (tensor map, SWIZZLE_128B) + the query k-block
+//                              [2Q x 32] fp32 as ONE contiguous bulk copy (prep kernel pre-swizzles it):
+//                              the TMA engine retires ~one 128-byte box row per 5 cycles, which is the
+//                              per-SM HBM share, so query rows must not go through the tensor path
 //   warp 1      MMA issuer     one thread, tcgen05.mma.cta_group::1.kind::tf32, commits to mbarriers
 //   warp 2      TMEM allocator (512 columns = two accumulator buffers)
 //   warps 4-7   split          lo tile -> TMEM (tcgen05.st) + row norms
@@ -85,6 +88,11 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, u
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
+}
+// contiguous global -> shared bulk copy (one request, no per-row tensor traversal)
+__device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* map, int c0, int c1) {
   asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];"
@@ -161,10 +169,21 @@ __device__ __forceinline__ void epilogue_barrier() { asm volatile("bar.sync 1, 1
 __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t smem_addr) {
   return uint64_t((smem_addr & 0x3ffffu) >> 4) | (uint64_t(1024 >> 4) << 32) | (uint64_t(1) << 46) | (uint64_t(2) << 61);
 }
+// The same descriptor from its two 32-bit halves: the high word is a constant, the low word is the
+// 16-byte-granular start address (LBO = 0), so advancing along K is one 32-bit add.
+constexpr uint32_t kDescHi = uint32_t(1024 >> 4) | (1u << 14) | (2u << 29);
+__device__ __forceinline__ uint64_t desc_from_lo(uint32_t lo) { return (uint64_t(kDescHi) << 32) | lo; }
 // instruction descriptor: fp32 accumulate, TF32 A and B, both K-major, M = 128, N = n
 __host__ __device__ constexpr uint32_t idesc_tf32(int n) {
   return (1u << 4) | (2u << 7) | (2u << 10) | (uint32_t(n >> 3) << 17) | (uint32_t(kTileRows >> 4) << 24);
 }
+
+// Position in a ring of S stages without integer division.
+struct RingPos {
+  int s = 0;
+  uint32_t phase = 0;
+  __device__ __forceinline__ void advance(int S) { if (++s == S) { s = 0; phase ^= 1u; } }
+};
 
 struct TcParams {
   int64_t n_rows;
@@ -178,13 +197,17 @@ struct TcParams {
   int32_t top_k, kcap;
   int32_t stages;
   uint32_t flags;
+  const float* qcat;       // this pass's query operand: [n_kblocks][2*qp rows][32] fp32, rows 128B-swizzled
   uint64_t* cand;          // [grid, n_queries, kcap]
   IdMap idmap;
   long long* trace;        // optional [16][256] clock64 samples of CTA 0's roles (devqa_debug_tc_trace)
 };
 
+// Role timeline tracing (tools/tc_trace.py) is compiled in only with -DDEVQA_TC_TRACE.
 __device__ __forceinline__ void trace_at(const TcParams& p, int role, uint32_t idx) {
+#ifdef DEVQA_TC_TRACE
   if (p.trace && blockIdx.x == 0 && idx < 256) p.trace[role * 256 + idx] = clock64();
+#endif
 }
 
 struct SmemLayout {        // byte offsets from the 1024-aligned base
@@ -206,22 +229,37 @@ __host__ __device__ inline SmemLayout tc_layout(int stages, int qp, int kcap) {
   return L;
 }
 
-// Epilogue phase B, slow path for one query: this warp owns the query's list exclusively.  `bits`
-// (4 per lane) marks which of the lane's four rows of the score tile beat the running threshold.
-// Deliberately out of line and loop-shaped (not unrolled): it must stay small and hot in the I-cache.
-__device__ __noinline__ void epilogue_insert_query(uint64_t* list, float* thr_j, int kcap, int top_k, float4 sc,
-                                                   uint32_t bits, int64_t row0, IdMap idmap, int lane) {
+// Epilogue phase B, slow path for one query whose list this warp owns exclusively.  Returns the new
+// threshold (score of the k-th entry).  Deliberately out of line and loop-shaped (small, I-cache hot).
+// Shared memory is the kernel's scarcest resource (its pipe is ~80% busy with TMA writes, split reads and
+// UMMA operand fetches, so every dependent LDS/STS costs hundreds of cycles): for the common capacity 32
+// the list is pulled into registers once (one key per lane), all inserts are shuffles, and it is written
+// back once.
+__device__ __noinline__ float epilogue_insert_query(uint64_t* list, int kcap, int top_k, const float* tile_row, float th,
+                                                    uint32_t rowmask, int64_t row0, IdMap idmap, int lane) {
+  const float4 sc = *reinterpret_cast<const float4*>(tile_row + lane * 4);
+  const uint32_t bits = ((!(sc.x < th) ? 1u : 0u) | (!(sc.y < th) ? 2u : 0u) | (!(sc.z < th) ? 4u : 0u) | (!(sc.w < th) ? 8u : 0u)) & rowmask;
+  uint64_t mylist = kcap == 32 ? list[lane] : 0ull;
   for (int t = 0; t < 4; ++t) {
     const bool on = (bits >> t) & 1u;
     unsigned m = __ballot_sync(kFull, on);
     if (!m) continue;
     const float st = t == 0 ? sc.x : (t == 1 ? sc.y : (t == 2 ? sc.z : sc.w));
     const uint64_t mine = on ? pack_key(st, uint32_t(idmap(row0 + t))) : kEmptyKey;
-    if (kcap == 32 && __popc(m) >= 6) {
-      // burst (first tiles, thresholds still loose): sort the warp's candidates once and merge
-      const uint64_t sorted = warp_sort32_desc(mine, lane);
-      list[lane] = warp_merge32(list[lane], shfl_u64(sorted, 31 - lane), lane);
-      __syncwarp();
+    if (kcap == 32) {
+      if (__popc(m) >= 6) {                               // burst: sort the candidates once and merge
+        const uint64_t sorted = warp_sort32_desc(mine, lane);
+        mylist = warp_merge32(mylist, shfl_u64(sorted, 31 - lane), lane);
+      } else {
+        while (m) {
+          const int src = __ffs(m) - 1;
+          m &= m - 1;
+          const uint64_t x = shfl_u64(mine, src);
+          const int pos = __popc(__ballot_sync(kFull, mylist > x));
+          const uint64_t up = shfl_u64(mylist, lane > 0 ? lane - 1 : 0);
+          if (pos < top_k) mylist = lane > pos ? up : (lane == pos ? x : mylist);
+        }
+      }
     } else {
       while (m) {
         const int src = __ffs(m) - 1;
@@ -230,17 +268,20 @@ __device__ __noinline__ void epilogue_insert_query(uint64_t* list, float* thr_j,
       }
     }
   }
-  if (lane == 0) {
-    const uint64_t kth = list[top_k - 1];
-    *thr_j = kth == kEmptyKey ? -INFINITY : key_score(kth);
+  uint64_t kth;
+  if (kcap == 32) {
+    list[lane] = mylist;
+    kth = shfl_u64(mylist, top_k - 1);
+  } else {
+    __syncwarp();
+    kth = list[top_k - 1];
   }
-  __syncwarp();
+  return kth == kEmptyKey ? -INFINITY : key_score(kth);
 }
 
 template <int QP, bool MULTI>
 __global__ void __launch_bounds__(kTcThreads, 1)
-scan_tc_kernel(const __grid_constant__ CUtensorMap bank_map, const __grid_constant__ CUtensorMap qhi_map,
-               const __grid_constant__ CUtensorMap qlo_map, const __grid_constant__ TcParams p) {
+scan_tc_kernel(const __grid_constant__ CUtensorMap bank_map, const __grid_constant__ TcParams p) {
   extern __shared__ unsigned char smem_unaligned[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_unaligned) + 1023) & ~uintptr_t(1023));
   const SmemLayout L = tc_layout(p.stages, p.qp, p.kcap);
@@ -249,7 +290,6 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap bank_map, const __grid_consta
   const uint32_t b_stage_bytes = uint32_t(2 * QP) * 128;
 
   uint64_t* lists = reinterpret_cast<uint64_t*>(smem + L.lists);
-  float* thr = reinterpret_cast<float*>(smem + L.thr);
   float* norms = reinterpret_cast<float*>(smem + L.norms);
   uint64_t* full_tma = reinterpret_cast<uint64_t*>(smem + L.bars);
   uint64_t* full_split = full_tma + kMaxStages;
@@ -260,13 +300,12 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap bank_map, const __grid_consta
 
   // ---- one-time setup ------------------------------------------------------------------------
   for (int i = threadIdx.x; i < QP * p.kcap; i += kTcThreads) lists[i] = kEmptyKey;
-  for (int i = threadIdx.x; i < QP; i += kTcThreads) thr[i] = -INFINITY;
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&bank_map); tma_prefetch_desc(&qhi_map); tma_prefetch_desc(&qlo_map);
+    tma_prefetch_desc(&bank_map);
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < S; ++s) { mbar_init(&full_tma[s], 1); mbar_init(&full_split[s], 128); mbar_init(&empty[s], 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 128); }
+    for (int s = 0; s < S; ++s) { mbar_init(&full_tma[s], 1); mbar_init(&full_split[s], 128); mbar_init(&empty[s], 2); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 2); mbar_init(&tmem_empty[a], 128); }
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, 512);
@@ -283,39 +322,39 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap bank_map, const __grid_consta
   if (warp == 0) {
     // ===== TMA producer =====
     if (lane == 0) {
-      // The smem ring is shallow (16-48 KB per stage), so HBM latency is hidden one level up: bank
+      // The smem ring holds a few k-blocks only, so HBM latency is also hidden one level up: bank
       // k-blocks are prefetched into L2 kPrefetchAhead k-blocks ahead of the ring loads.
-      const int64_t total = int64_t((p.n_tiles - int(blockIdx.x) + int(gridDim.x) - 1) / int(gridDim.x)) * nkb;
-      auto prefetch = [&](int64_t idx) {
-        if (idx < total && !(p.flags & kDbgNoPrefetch)) {
-          const int t = int(blockIdx.x) + int(idx / nkb) * int(gridDim.x);
-          tma_prefetch_l2_2d(&bank_map, int(idx % nkb) * kBlockK, t * kTileRows);
+      const bool pf_on = !(p.flags & kDbgNoPrefetch);
+      const bool qtma = !(p.flags & kDbgNoQueryTma);
+      const uint32_t tx_bytes = kATileBytes + (qtma ? b_stage_bytes : 0u);
+      int pf_tile = blockIdx.x, pf_kb = 0;                // next k-block to prefetch
+      auto prefetch_next = [&]() {
+        if (pf_tile < p.n_tiles) {
+          if (pf_on) tma_prefetch_l2_2d(&bank_map, pf_kb * kBlockK, pf_tile * kTileRows);
+          if (++pf_kb == nkb) { pf_kb = 0; pf_tile += gridDim.x; }
         }
       };
-      for (int i = 0; i < kPrefetchAhead; ++i) prefetch(i);
-      uint32_t it = 0;
+      for (int i = 0; i < kPrefetchAhead; ++i) prefetch_next();
+      RingPos r;
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-        for (int kb = 0; kb < nkb; ++kb, ++it) {
-          const int s = it % S;
-          prefetch(int64_t(it) + kPrefetchAhead);
-          mbar_wait(&empty[s], ((it / S) & 1) ^ 1);
-          const bool qtma = !(p.flags & kDbgNoQueryTma);
-          mbar_expect_tx(&full_tma[s], kATileBytes + (qtma ? b_stage_bytes : 0u));
-          tma_load_2d(smem + L.a_raw + s * kATileBytes, &bank_map, &full_tma[s], kb * kBlockK, tile * kTileRows);
-          unsigned char* bq = smem + L.bq + s * b_stage_bytes;
-          if (qtma) {
-            tma_load_2d(bq, &qhi_map, &full_tma[s], kb * kBlockK, 0);
-            tma_load_2d(bq + QP * 128, &qlo_map, &full_tma[s], kb * kBlockK, 0);
-          }
-          trace_at(p, 0, it);
+        for (int kb = 0; kb < nkb; ++kb) {
+          prefetch_next();
+          mbar_wait(&empty[r.s], r.phase ^ 1u);
+          mbar_expect_tx(&full_tma[r.s], tx_bytes);
+          tma_load_2d(smem + L.a_raw + r.s * kATileBytes, &bank_map, &full_tma[r.s], kb * kBlockK, tile * kTileRows);
+          if (qtma)     // the whole [2QP x 32] query k-block is contiguous (and pre-swizzled) in global memory
+            bulk_load(smem + L.bq + r.s * b_stage_bytes, p.qcat + size_t(kb) * (2 * QP * kBlockK), b_stage_bytes, &full_tma[r.s]);
+          r.advance(S);
         }
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer =====
+    // ===== MMA issuer 1: A (hi by truncation, from shared memory) x [Qhi ; Qlo] -> cols [0, 2QP) =====
     if (lane == 0) {
-      const uint32_t idesc_cat = idesc_tf32(2 * QP), idesc_hi = idesc_tf32(QP);
-      uint32_t it = 0, unit = 0;
+      const uint32_t idesc_cat = idesc_tf32(2 * QP);
+      const uint32_t a_lo0 = (smem_u32(smem + L.a_raw) & 0x3ffffu) >> 4, b_lo0 = (smem_u32(smem + L.bq) & 0x3ffffu) >> 4;
+      RingPos r;
+      uint32_t unit = 0;
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
         for (int set = 0; set < nsets; ++set, ++unit) {
           const int a = unit & 1;
@@ -323,27 +362,49 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap bank_map, const __grid_consta
           tc_fence_after();
           const uint32_t d = tmem_base + uint32_t(a) * kAccCols;
           const int kb_end = min(nkb, (set + 1) * kSetKBlocks);
-          for (int kb = set * kSetKBlocks; kb < kb_end; ++kb, ++it) {
-            const int s = it % S;
-            const uint32_t ph = (it / S) & 1;
-            const uint32_t a_raw = smem_u32(smem + L.a_raw + s * kATileBytes);
-            const uint32_t bq = smem_u32(smem + L.bq + s * b_stage_bytes);
+          for (int kb = set * kSetKBlocks; kb < kb_end; ++kb) {
             const uint32_t first = kb == set * kSetKBlocks ? 0u : 1u;
-            mbar_wait(&full_tma[s], ph);
+            const uint32_t a_lo = a_lo0 + uint32_t(r.s) * (kATileBytes >> 4), b_lo = b_lo0 + uint32_t(r.s) * (b_stage_bytes >> 4);
+            mbar_wait(&full_tma[r.s], r.phase);
             tc_fence_after();
-            trace_at(p, 3, it);
 #pragma unroll
-            for (int kk = 0; kk < kBlockK / 8; ++kk)      // A(hi by truncation) x [Qhi ; Qlo] -> cols [0, 2QP)
-              mma_tf32(d, smem_desc_sw128(a_raw + kk * 32), smem_desc_sw128(bq + kk * 32), idesc_cat, first | uint32_t(kk));
-            mbar_wait(&full_split[s], ph);
+            for (int kk = 0; kk < kBlockK / 8; ++kk)
+              mma_tf32(d, desc_from_lo(a_lo + kk * 2), desc_from_lo(b_lo + kk * 2), idesc_cat, first | uint32_t(kk));
+            mma_commit(&empty[r.s]);                      // one of the two arrivals that free the stage
+            r.advance(S);
+          }
+          mma_commit(&tmem_full[a]);
+        }
+      }
+    }
+  } else if (warp == 2) {
+    // ===== MMA issuer 2: Alo (from tensor memory) x Qhi -> cols [2QP, 3QP) =====
+    if (lane == 0) {
+      const uint32_t idesc_hi = idesc_tf32(QP);
+      const uint32_t b_lo0 = (smem_u32(smem + L.bq) & 0x3ffffu) >> 4;
+      const bool on = !(p.flags & kDbgNoMma2);
+      RingPos r;
+      uint32_t unit = 0;
+      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+        for (int set = 0; set < nsets; ++set, ++unit) {
+          const int a = unit & 1;
+          mbar_wait(&tmem_empty[a], ((unit >> 1) & 1) ^ 1);
+          tc_fence_after();
+          const uint32_t d = tmem_base + uint32_t(a) * kAccCols + 2 * QP;
+          const int kb_end = min(nkb, (set + 1) * kSetKBlocks);
+          for (int kb = set * kSetKBlocks; kb < kb_end; ++kb) {
+            const uint32_t first = kb == set * kSetKBlocks ? 0u : 1u;
+            const uint32_t b_lo = b_lo0 + uint32_t(r.s) * (b_stage_bytes >> 4);
+            const uint32_t alo = tmem_alo + uint32_t(r.s) * kBlockK;
+            mbar_wait(&full_split[r.s], r.phase);         // implies full_tma[s]: the split warps waited on it
             tc_fence_after();
-            trace_at(p, 4, it);
-            if (!(p.flags & kDbgNoMma2))
+            if (on) {
 #pragma unroll
-            for (int kk = 0; kk < kBlockK / 8; ++kk)      // Alo x Qhi -> cols [2QP, 3QP)
-              mma_tf32_ts(d + 2 * QP, tmem_alo + uint32_t(s) * kBlockK + kk * 8, smem_desc_sw128(bq + kk * 32), idesc_hi, first | uint32_t(kk));
-            mma_commit(&empty[s]);                        // frees the stage when these MMAs retire
-            trace_at(p, 5, it);
+              for (int kk = 0; kk < kBlockK / 8; ++kk)
+                mma_tf32_ts(d, alo + kk * 8, desc_from_lo(b_lo + kk * 2), idesc_hi, first | uint32_t(kk));
+            }
+            mma_commit(&empty[r.s]);
+            r.advance(S);
           }
           mma_commit(&tmem_full[a]);
         }
@@ -354,15 +415,16 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap bank_map, const __grid_consta
     const int row = threadIdx.x - 128;
     const uint32_t row_off = uint32_t(row) * 128;
     const uint32_t sw = uint32_t(row & 7);                // 16-byte chunk c of row r lives at chunk c ^ (r & 7)
-    uint32_t it = 0, lt = 0;
+    uint32_t lt = 0;
+    RingPos rp;
+    const uint32_t st_lane = uint32_t((warp & 3) * 32) << 16;     // warp w may only touch TMEM lanes 32*(w%4)..
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++lt) {
       float ss[8];                                        // one partial sum per 16-byte chunk position
 #pragma unroll
       for (int c = 0; c < 8; ++c) ss[c] = 0.f;
-      for (int kb = 0; kb < nkb; ++kb, ++it) {
-        const int s = it % S;
-        mbar_wait(&full_tma[s], (it / S) & 1);
-        if (row == 0) trace_at(p, 1, it);
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = rp.s;
+        mbar_wait(&full_tma[s], rp.phase);
         const unsigned char* src = smem + L.a_raw + s * kATileBytes + row_off;
         uint32_t lo[32];
         if (!(p.flags & kDbgNoSplit)) {
@@ -377,14 +439,14 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap bank_map, const __grid_consta
             ss[c] = fmaf(v.z, v.z, ss[c]); ss[c] = fmaf(v.w, v.w, ss[c]);
           }
           // lane (= row) x 32 columns of this stage's lo tile; warp w may only touch TMEM lanes 32*(w%4)..
-          tmem_st32(tmem_alo + uint32_t(s) * kBlockK + (uint32_t((warp & 3) * 32) << 16), lo);
+          tmem_st32(tmem_alo + uint32_t(s) * kBlockK + st_lane, lo);
           tmem_st_wait();
         }
         if (kb == nkb - 1)
           norms[(lt % kNormRing) * kTileRows + row] = ((ss[0] + ss[1]) + (ss[2] + ss[3])) + ((ss[4] + ss[5]) + (ss[6] + ss[7]));
         tc_fence_before();                                // TMEM writes ordered before the MMA issuer's reads
         mbar_arrive(&full_split[s]);
-        if (row == 0) trace_at(p, 2, it);
+        rp.advance(S);
       }
     }
   } else if (warp >= 8) {
@@ -400,6 +462,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap bank_map, const __grid_consta
     const int row_in_tile = e * 32 + lane;
     float* stile = reinterpret_cast<float*>(smem + L.scratch);        // [HQ][128]
     const bool no_insert = (p.flags & kDbgNoInsert) != 0;
+    float thr_reg = -INFINITY;                            // lane l: running k-th score of the l-th query this warp owns
     uint32_t lt = 0, unit = 0;
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++lt) {
       float acc[MULTI ? QP : 1];                          // fp32 RN sum over the tile's K-sets
@@ -448,16 +511,29 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap bank_map, const __grid_consta
 #pragma unroll
           for (int t = 0; t < 4; ++t) rowmask |= (row0 + t < p.n_rows ? 1u : 0u) << t;
           if (no_insert) rowmask = 0;
-          for (int i = 0; i < HQ / 4; ++i) {
-            const int jl = e * (HQ / 4) + i;
-            const int j = h * HQ + jl;
-            if (j >= p.nq_pass) break;                    // warp-uniform
-            const float4 sc = *reinterpret_cast<const float4*>(stile + jl * kTileRows + lane * 4);
-            const float th = thr[j];
-            uint32_t bits = (!(sc.x < th) ? 1u : 0u) | (!(sc.y < th) ? 2u : 0u) | (!(sc.z < th) ? 4u : 0u) | (!(sc.w < th) ? 8u : 0u);
-            bits &= rowmask;
-            if (__ballot_sync(kFull, bits != 0))
-              epilogue_insert_query(lists + size_t(j) * p.kcap, &thr[j], p.kcap, p.top_k, sc, bits, row0, p.idmap, lane);
+          constexpr int NQW = HQ / 4;                     // queries this warp owns per half
+          float4 sc[NQW];
+#pragma unroll
+          for (int i = 0; i < NQW; ++i)                   // all tile reads in flight together
+            sc[i] = *reinterpret_cast<const float4*>(stile + (e * NQW + i) * kTileRows + lane * 4);
+          uint32_t anyq = 0;
+#pragma unroll
+          for (int i = 0; i < NQW; ++i) {
+            const float th = __shfl_sync(kFull, thr_reg, h * NQW + i);
+            const bool hit = (!(sc[i].x < th) && (rowmask & 1u)) || (!(sc[i].y < th) && (rowmask & 2u)) ||
+                             (!(sc[i].z < th) && (rowmask & 4u)) || (!(sc[i].w < th) && (rowmask & 8u));
+            anyq |= (__ballot_sync(kFull, hit) ? 1u : 0u) << i;
+          }
+          while (anyq) {                                  // warp-uniform
+            const int i = __ffs(anyq) - 1;
+            anyq &= anyq - 1;
+            const int j = h * HQ + e * NQW + i;
+            if (j >= p.nq_pass) break;
+            const int oi = h * NQW + i;                   // index among the queries this warp owns
+            const float th = __shfl_sync(kFull, thr_reg, oi);
+            const float nt = epilogue_insert_query(lists + size_t(j) * p.kcap, p.kcap, p.top_k,
+                                                   stile + (e * NQW + i) * kTileRows, th, rowmask, row0, p.idmap, lane);
+            if (lane == oi) thr_reg = nt;
           }
           epilogue_barrier();                             // the score tile may be overwritten again
         }
@@ -477,12 +553,16 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap bank_map, const __grid_consta
   if (warp == 2) tmem_dealloc(tmem_base, 512);
 }
 
-// ---- query preparation: normalise, pad, split into TF32 hi / lo --------------------------------------
+// ---- query preparation: normalise, pad, split into TF32 hi / lo, lay out as the MMA B operand -------------
+// Output per pass of qp queries: [n_kblocks][2*qp rows][32 cols] fp32, rows 0..qp-1 = hi, qp..2qp-1 = lo,
+// each row's eight 16-byte chunks permuted by the 128-byte swizzle (chunk ^= row & 7), so that a k-block
+// is one contiguous, shared-memory-ready copy.  One warp per query.
 __global__ void __launch_bounds__(256) prep_queries_kernel(const float* __restrict__ q, int64_t q_ld, int n_queries, int dim,
-                                                           int q_pad, int d_pad, unsigned flags, float* __restrict__ qhi,
-                                                           float* __restrict__ qlo) {
+                                                           int qp, int n_kblocks, int q_pad, unsigned flags,
+                                                           float* __restrict__ qcat) {
   const int lane = threadIdx.x & 31;
   const int warps = gridDim.x * (blockDim.x >> 5);
+  const int d_pad = n_kblocks * kBlockK;
   for (int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < q_pad; r += warps) {
     float inv = 0.f;
     const float* src = q + size_t(r < n_queries ? r : 0) * q_ld;
@@ -497,14 +577,19 @@ __global__ void __launch_bounds__(256) prep_queries_kernel(const float* __restri
         inv = 1.0f / ((flags & DEVQA_NOEPS) ? nrm : fmaxf(nrm, kNormEps));
       }
     }
+    const int pass = r / qp, rp = r % qp;                 // row rp of the pass: hi at rp, lo at qp + rp
+    float* base = qcat + size_t(pass) * n_kblocks * (2 * qp * kBlockK);
     for (int c = lane; c < d_pad; c += 32) {
       const float x = (r < n_queries && c < dim) ? src[c] * inv : 0.f;
       uint32_t hb, lb;
       asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(x));
       const float hi = __uint_as_float(hb);
       asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lb) : "f"(x - hi));
-      qhi[size_t(r) * d_pad + c] = hi;
-      qlo[size_t(r) * d_pad + c] = __uint_as_float(lb);
+      const int kb = c / kBlockK, w = c % kBlockK;
+      float* blk = base + size_t(kb) * (2 * qp * kBlockK);
+      const int hi_row = rp, lo_row = qp + rp;
+      blk[hi_row * kBlockK + (((w >> 2) ^ (hi_row & 7)) << 2) + (w & 3)] = hi;
+      blk[lo_row * kBlockK + (((w >> 2) ^ (lo_row & 7)) << 2) + (w & 3)] = __uint_as_float(lb);
     }
   }
 }
@@ -568,38 +653,35 @@ int scan_tc_plan(int n_queries, int64_t dim, int kcap, int* qp_out, int* stages_
   return DEVQA_E_UNSUPPORTED;
 }
 
-int scan_tc_prep_queries(const float* queries, int64_t query_ld, int n_queries, int q_pad, int64_t dim, unsigned flags,
-                         float* qhi, float* qlo, cudaStream_t stream) {
-  const int d_pad = scan_tc_dim_pad(dim);
+// qcat must hold q_pad * dim_pad * 2 floats; q_pad is a multiple of qp.
+int scan_tc_prep_queries(const float* queries, int64_t query_ld, int n_queries, int qp, int q_pad, int64_t dim,
+                         unsigned flags, float* qcat, cudaStream_t stream) {
+  const int n_kblocks = scan_tc_dim_pad(dim) / kBlockK;
   const int grid = (q_pad + 7) / 8;
-  prep_queries_kernel<<<grid, 256, 0, stream>>>(queries, query_ld, n_queries, int(dim), q_pad, d_pad, flags, qhi, qlo);
+  prep_queries_kernel<<<grid, 256, 0, stream>>>(queries, query_ld, n_queries, int(dim), qp, n_kblocks, q_pad, flags, qcat);
   DEVQA_CUDA(cudaGetLastError());
   count_launch();
   return DEVQA_OK;
 }
 
-// One pass: prepared queries [q0, q0 + nq_pass) (rows of qhi/qlo) against the whole bank.
 static long long* g_tc_trace = nullptr;
 void scan_tc_set_trace(long long* buf) { g_tc_trace = buf; }
 
-int scan_tc_launch(const ScanParams& sp, const float* qhi, const float* qlo, int qp, int stages, int grid,
-                   cudaStream_t stream) {
+int scan_tc_launch(const ScanParams& sp, const float* qcat, int qp, int stages, int grid, cudaStream_t stream) {
   const int d_pad = scan_tc_dim_pad(sp.dim);
-  CUtensorMap bank_map, qhi_map, qlo_map;
+  CUtensorMap bank_map;
   int rc = make_map(&bank_map, sp.bank, uint64_t(sp.dim), uint64_t(sp.n_rows), uint64_t(sp.bank_ld) * 4, kTileRows);
   if (rc) return rc;
-  const size_t qoff = size_t(sp.q0) * d_pad;
-  if ((rc = make_map(&qhi_map, qhi + qoff, uint64_t(d_pad), uint64_t(qp), uint64_t(d_pad) * 4, uint32_t(qp)))) return rc;
-  if ((rc = make_map(&qlo_map, qlo + qoff, uint64_t(d_pad), uint64_t(qp), uint64_t(d_pad) * 4, uint32_t(qp)))) return rc;
   TcParams p{};
   p.n_rows = sp.n_rows; p.dim = int(sp.dim); p.n_kblocks = d_pad / kBlockK;
   p.n_tiles = int((sp.n_rows + kTileRows - 1) / kTileRows);
   p.qp = qp; p.nq_pass = sp.nq_pass; p.q0 = sp.q0; p.n_queries = sp.n_queries;
   p.top_k = sp.top_k; p.kcap = sp.kcap; p.stages = stages; p.flags = sp.flags; p.cand = sp.cand; p.idmap = sp.idmap;
+  p.qcat = qcat + size_t(sp.q0 / qp) * size_t(d_pad) * 2 * qp;     // pass index = q0 / qp
   p.trace = g_tc_trace;
   const size_t smem = tc_layout(stages, qp, sp.kcap).total + 1024;
   const bool multi = p.n_kblocks > kSetKBlocks;
-  void (*kern)(CUtensorMap, CUtensorMap, CUtensorMap, TcParams) = nullptr;
+  void (*kern)(CUtensorMap, TcParams) = nullptr;
   if (!multi) kern = qp == 64 ? scan_tc_kernel<64, false> : qp == 32 ? scan_tc_kernel<32, false> : scan_tc_kernel<16, false>;
   else kern = qp == 32 ? scan_tc_kernel<32, true> : scan_tc_kernel<16, true>;
   if (qp != 16 && qp != 32 && !(qp == 64 && !multi)) {
@@ -607,7 +689,7 @@ int scan_tc_launch(const ScanParams& sp, const float* qhi, const float* qlo, int
     return DEVQA_E_INVALID;
   }
   DEVQA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-  kern<<<grid, kTcThreads, smem, stream>>>(bank_map, qhi_map, qlo_map, p);
+  kern<<<grid, kTcThreads, smem, stream>>>(bank_map, p);
   DEVQA_CUDA(cudaGetLastError());
   count_launch();
   return DEVQA_OK;
