@@ -6,9 +6,11 @@
         --master-port P bench.py --gpus N --steps K --warmup W
 
 Workload (named in config.workload): the north-star configuration -- a 10M x 768 fp32 fact bank,
-k = 32, Q queries per search call (HBM-bound regime) -- row-sharded over the N GPUs (STRONG
-scaling: the bank is fixed, each GPU scans 10M/N rows).  A "step" is one search call: fused
-normalise + contraction + top-k over the whole bank, (N>1: + one all-gather + merge).
+k = 32, Q = 64 queries per search call (the top of config C3's batch range; tcgen05 kernel) --
+row-sharded over the N GPUs (STRONG scaling: the bank is fixed, each GPU scans 10M/N rows).  A
+"step" is one search call: fused normalise + contraction + top-k over the whole bank, (N>1: + one
+all-gather + merge).  "regimes" adds a short sweep over Q = 1, 4, 16, 64 on the same bank so that
+the HBM-bound small-batch kernels are reported next to the headline.
 
 value  queries/s with queries and bank resident in HBM, CUDA-event timed, max over ranks.
 e2e    the same metric through the host-buffer C-ABI call (numpy queries in, numpy results
@@ -41,11 +43,12 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--rows", type=int, default=10_000_000)
     ap.add_argument("--dim", type=int, default=768)
-    ap.add_argument("--queries", type=int, default=8)
+    ap.add_argument("--queries", type=int, default=64)
     ap.add_argument("--topk", type=int, default=32)
     ap.add_argument("--bank-dtype", default="fp32", choices=["fp32", "bf16"])
     ap.add_argument("--cpu-sample-rows", type=int, default=1_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-regimes", action="store_true", help="skip the short Q sweep reported under \"regimes\"")
     ap.add_argument("--flags", type=int, default=0, help="extra DEVQA_* flag bits (debugging)")
     return ap.parse_args()
 
@@ -281,11 +284,39 @@ def run_ours(a):
     scan_ms_per_launch = scan_ms.value / max(1, scan_launches.value)
     achieved = alg_bytes / (scan_ms_per_launch * 1e-3) / 1e9 if scan_ms_per_launch > 0 else 0.0
     peak, peak_src = measured_peak()
-    roofline = {"bound": "hbm", "kernel": "scan_stream_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+    kernel_name = "scan_tc_kernel (tcgen05/TMEM/TMA)" if (a.queries > 4 and a.bank_dtype == "fp32") else "scan_stream_kernel (CUDA cores)"
+    roofline = {"bound": "hbm", "kernel": kernel_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": ncu_traffic(a, rows_local), "peak_source": peak_src,
                 "frac_of_8TBs_nominal": achieved / 8000.0, "alg_bytes_per_launch": alg_bytes,
                 "launch_ms": scan_ms_per_launch, "launches_timed": scan_launches.value,
                 "scan_share_of_step": scan_ms.value / max(1e-9, ev0.elapsed_time(ev1))}
+
+    # ---- regimes: the same bank at other batch sizes (device-resident, 10 steps each) ----------
+    regimes = []
+    if not a.no_regimes:
+        for nq in (1, 4, 16, 64):
+            gq = torch.Generator().manual_seed(9000 + nq)
+            qd = torch.nn.functional.normalize(torch.randn(nq, a.dim, generator=gq), dim=1).to(dev)
+            for _ in range(3):
+                bank.search(qd, a.topk)
+            barrier()
+            L.check(L.lib().devqa_profile_enable(local_rank, 1))
+            r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            r0.record()
+            for _ in range(10):
+                bank.search(qd, a.topk)
+            r1.record()
+            barrier()
+            ms = max_over_ranks(r0.elapsed_time(r1)) / 10
+            sm, sl, sr = C.c_double(), C.c_int64(), C.c_int64()
+            L.check(L.lib().devqa_profile_collect(local_rank, C.byref(sm), C.byref(sl), C.byref(sr)))
+            L.check(L.lib().devqa_profile_enable(local_rank, 0))
+            scan_ms_call = sm.value / max(1, sr.value)
+            gbs = (rows_local * a.dim * esz * (sl.value / max(1, sr.value))) / (scan_ms_call * 1e-3) / 1e9
+            regimes.append({"queries_per_call": nq, "ms_per_call": ms, "queries_per_s": nq / (ms * 1e-3),
+                            "scan_gbs_per_gpu": gbs, "frac_of_measured_hbm": gbs / peak,
+                            "kernel": "tcgen05" if (nq > 4 and a.bank_dtype == "fp32") else "stream",
+                            "bank_passes_per_call": sl.value / max(1, sr.value)})
 
     if rank == 0:
         cpu = None
@@ -299,6 +330,8 @@ def run_ours(a):
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
                 "aggregate_hbm_gbs": (a.rows * a.dim * esz) / (ms_per_step * 1e-3) / 1e9,
                 "aggregate_hbm_frac_of_measured": (a.rows * a.dim * esz) / (ms_per_step * 1e-3) / 1e9 / (peak * world)}
+        if regimes:
+            line["regimes"] = regimes
         if cpu is not None:
             line["cpu_baseline"] = cpu
         print(json.dumps(line), flush=True)
