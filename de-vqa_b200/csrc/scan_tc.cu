@@ -58,6 +58,11 @@ constexpr unsigned kDbgNoInsert = 1u << 16, kDbgNoSplit = 1u << 17, kDbgNoMma2 =
 // ---- PTX wrappers ---------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return uint32_t(__cvta_generic_to_shared(p)); }
 
+__device__ __forceinline__ float4 lds128(uint32_t saddr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
+  return v;
+}
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
@@ -418,6 +423,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap bank_map, const __grid_consta
     uint32_t lt = 0;
     RingPos rp;
     const uint32_t st_lane = uint32_t((warp & 3) * 32) << 16;     // warp w may only touch TMEM lanes 32*(w%4)..
+    const uint32_t a_raw_s = smem_u32(smem + L.a_raw) + row_off;
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++lt) {
       float ss[8];                                        // one partial sum per 16-byte chunk position
 #pragma unroll
@@ -425,12 +431,12 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap bank_map, const __grid_consta
       for (int kb = 0; kb < nkb; ++kb) {
         const int s = rp.s;
         mbar_wait(&full_tma[s], rp.phase);
-        const unsigned char* src = smem + L.a_raw + s * kATileBytes + row_off;
+        const uint32_t src = a_raw_s + uint32_t(s) * kATileBytes;     // shared-space address of this thread's row
         uint32_t lo[32];
         if (!(p.flags & kDbgNoSplit)) {
 #pragma unroll
           for (int c = 0; c < 8; ++c) {                   // logical 16-byte chunk c of the row
-            const float4 v = *reinterpret_cast<const float4*>(src + (uint32_t(c) ^ sw) * 16);
+            const float4 v = lds128(src + ((uint32_t(c) ^ sw) << 4));
             lo[4 * c + 0] = __float_as_uint(v.x - __uint_as_float(__float_as_uint(v.x) & 0xffffe000u));
             lo[4 * c + 1] = __float_as_uint(v.y - __uint_as_float(__float_as_uint(v.y) & 0xffffe000u));
             lo[4 * c + 2] = __float_as_uint(v.z - __uint_as_float(__float_as_uint(v.z) & 0xffffe000u));
