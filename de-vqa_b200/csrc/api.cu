@@ -162,17 +162,27 @@ static int run_search(Scratch* s, const SearchArgs& a, uint64_t* out_keys, float
     const size_t plane = size_t(q_pad) * d_pad;
     if ((rc = grow(reinterpret_cast<void**>(&s->qsplit), &s->qsplit_bytes, 2 * plane * 4, false))) return rc;
     const int64_t tiles = (a.n_rows + 127) / 128;
-    grid = int(tiles < s->sm_count ? tiles : s->sm_count);
+    // Large banks: one pass per launch on every SM.  Small banks: several passes side by side so that
+    // tiles x passes still covers the SMs.
+    const int n_passes = q_pad / qp;
+    const int tiles_cap = int(tiles < s->sm_count ? tiles : s->sm_count);
+    int side = 1;
+    if (tiles < s->sm_count) side = n_passes < s->sm_count ? n_passes : s->sm_count;
+    int ctas_per_pass = s->sm_count / side;
+    if (ctas_per_pass > tiles_cap) ctas_per_pass = tiles_cap;
+    if (ctas_per_pass < 1) ctas_per_pass = 1;
+    grid = ctas_per_pass;                                   // candidate lists per query
     if ((rc = grow(reinterpret_cast<void**>(&s->cand), &s->cand_bytes, size_t(grid) * a.n_queries * kcap * 8, false))) return rc;
     p.bank = a.bank; p.cand = s->cand;
     const bool prof = s->profiling && s->prof_used < Scratch::kProfSlots;
     if (prof) DEVQA_CUDA(cudaEventRecord(s->prof_ev[2 * s->prof_used], stream));
     if ((rc = scan_tc_prep_queries(a.queries, a.query_ld, int(a.n_queries), qp, q_pad, a.dim, a.flags, s->qsplit, stream)))
       return rc;
-    for (int64_t q0 = 0; q0 < a.n_queries; q0 += qp) {
-      p.q0 = int32_t(q0);
-      p.nq_pass = int32_t(a.n_queries - q0 < qp ? a.n_queries - q0 : qp);
-      if ((rc = scan_tc_launch(p, s->qsplit, qp, stages, grid, stream))) return rc;
+    for (int pass = 0; pass < n_passes; pass += side) {
+      const int now = n_passes - pass < side ? n_passes - pass : side;
+      p.q0 = int32_t(pass * qp);
+      p.nq_pass = qp;
+      if ((rc = scan_tc_launch(p, s->qsplit, qp, stages, now, ctas_per_pass, stream))) return rc;
       if (prof) s->prof_scan_launches++;
     }
     if (prof) {

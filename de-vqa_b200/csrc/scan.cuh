@@ -35,7 +35,9 @@ int scan_tc_plan(int n_queries, int64_t dim, int kcap, int* qp_out, int* stages_
 // queries -> normalised TF32 hi / lo split, laid out per pass as the MMA B operand (see scan_tc.cu)
 int scan_tc_prep_queries(const float* queries, int64_t query_ld, int n_queries, int qp, int q_pad, int64_t dim,
                          unsigned flags, float* qcat, cudaStream_t stream);
-int scan_tc_launch(const ScanParams& p, const float* qcat, int qp, int stages, int grid, cudaStream_t stream);
+// one launch = `passes` consecutive query passes starting at p.q0, each on ctas_per_pass CTAs
+int scan_tc_launch(const ScanParams& p, const float* qcat, int qp, int stages, int passes, int ctas_per_pass,
+                   cudaStream_t stream);
 void scan_tc_set_trace(long long* buf);
 
 // merge.cu: reduce `n_lists` sorted lists per query ([n_lists, n_queries, list_stride], the first

@@ -34,8 +34,11 @@
 //   warp 1      MMA issuer     one thread, tcgen05.mma.cta_group::1.kind::tf32, commits to mbarriers
 //   warp 2      TMEM allocator (512 columns = two accumulator buffers)
 //   warps 4-7   split          lo tile -> TMEM (tcgen05.st) + row norms
-//   warps 8-11  epilogue       tcgen05.ld -> scale -> threshold filter -> per-query sorted lists (smem)
+//   warps 8-11  epilogue         tcgen05.ld -> scale -> threshold filter -> per-query sorted lists (smem)
 // Pipelines: smem ring (full_tma / full_split / empty), TMEM double buffer (tmem_full / tmem_empty).
+// Small banks with many queries (C2: 64 tiles, 8 passes) would leave most SMs idle with one pass per
+// launch, so a launch runs several query passes side by side: CTA c works on pass c % passes and on
+// tiles c / passes, c / passes + ctas_per_pass, ...
 #include <cuda.h>
 
 #include "scan.cuh"
@@ -201,6 +204,7 @@ struct TcParams {
   int32_t n_queries;
   int32_t top_k, kcap;
   int32_t stages;
+  int32_t passes;          // query passes running side by side in this launch (CTA c works on pass c % passes)
   uint32_t flags;
   const float* qcat;       // this pass's query operand: [n_kblocks][2*qp rows][32] fp32, rows 128B-swizzled
   uint64_t* cand;          // [grid, n_queries, kcap]
@@ -318,6 +322,12 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap bank_map, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // this CTA's share of the work
+  const int pass_local = int(blockIdx.x) % p.passes;
+  const int tile0 = int(blockIdx.x) / p.passes, tile_step = int(gridDim.x) / p.passes;
+  const int q0 = p.q0 + pass_local * QP;
+  const int nq_pass = min(QP, p.n_queries - q0);
+  const float* const qcat = p.qcat + size_t(pass_local) * size_t(p.n_kblocks) * (2 * QP * kBlockK);
   // TMEM columns: two accumulator buffers of 3*QP columns, then one 32-column lo tile per ring stage
   constexpr uint32_t kAccCols = 3 * QP;
   const uint32_t tmem_alo = tmem_base + 2 * kAccCols;
@@ -332,23 +342,23 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap bank_map, const __grid_consta
       const bool pf_on = !(p.flags & kDbgNoPrefetch);
       const bool qtma = !(p.flags & kDbgNoQueryTma);
       const uint32_t tx_bytes = kATileBytes + (qtma ? b_stage_bytes : 0u);
-      int pf_tile = blockIdx.x, pf_kb = 0;                // next k-block to prefetch
+      int pf_tile = tile0, pf_kb = 0;                     // next k-block to prefetch
       auto prefetch_next = [&]() {
         if (pf_tile < p.n_tiles) {
           if (pf_on) tma_prefetch_l2_2d(&bank_map, pf_kb * kBlockK, pf_tile * kTileRows);
-          if (++pf_kb == nkb) { pf_kb = 0; pf_tile += gridDim.x; }
+          if (++pf_kb == nkb) { pf_kb = 0; pf_tile += tile_step; }
         }
       };
       for (int i = 0; i < kPrefetchAhead; ++i) prefetch_next();
       RingPos r;
-      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+      for (int tile = tile0; tile < p.n_tiles; tile += tile_step) {
         for (int kb = 0; kb < nkb; ++kb) {
           prefetch_next();
           mbar_wait(&empty[r.s], r.phase ^ 1u);
           mbar_expect_tx(&full_tma[r.s], tx_bytes);
           tma_load_2d(smem + L.a_raw + r.s * kATileBytes, &bank_map, &full_tma[r.s], kb * kBlockK, tile * kTileRows);
           if (qtma)     // the whole [2QP x 32] query k-block is contiguous (and pre-swizzled) in global memory
-            bulk_load(smem + L.bq + r.s * b_stage_bytes, p.qcat + size_t(kb) * (2 * QP * kBlockK), b_stage_bytes, &full_tma[r.s]);
+            bulk_load(smem + L.bq + r.s * b_stage_bytes, qcat + size_t(kb) * (2 * QP * kBlockK), b_stage_bytes, &full_tma[r.s]);
           r.advance(S);
         }
       }
@@ -360,7 +370,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap bank_map, const __grid_consta
       const uint32_t a_lo0 = (smem_u32(smem + L.a_raw) & 0x3ffffu) >> 4, b_lo0 = (smem_u32(smem + L.bq) & 0x3ffffu) >> 4;
       RingPos r;
       uint32_t unit = 0;
-      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+      for (int tile = tile0; tile < p.n_tiles; tile += tile_step) {
         for (int set = 0; set < nsets; ++set, ++unit) {
           const int a = unit & 1;
           mbar_wait(&tmem_empty[a], ((unit >> 1) & 1) ^ 1);
@@ -390,7 +400,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap bank_map, const __grid_consta
       const bool on = !(p.flags & kDbgNoMma2);
       RingPos r;
       uint32_t unit = 0;
-      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+      for (int tile = tile0; tile < p.n_tiles; tile += tile_step) {
         for (int set = 0; set < nsets; ++set, ++unit) {
           const int a = unit & 1;
           mbar_wait(&tmem_empty[a], ((unit >> 1) & 1) ^ 1);
@@ -424,7 +434,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap bank_map, const __grid_consta
     RingPos rp;
     const uint32_t st_lane = uint32_t((warp & 3) * 32) << 16;     // warp w may only touch TMEM lanes 32*(w%4)..
     const uint32_t a_raw_s = smem_u32(smem + L.a_raw) + row_off;
-    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++lt) {
+    for (int tile = tile0; tile < p.n_tiles; tile += tile_step, ++lt) {
       float ss[8];                                        // one partial sum per 16-byte chunk position
 #pragma unroll
       for (int c = 0; c < 8; ++c) ss[c] = 0.f;
@@ -470,7 +480,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap bank_map, const __grid_consta
     const bool no_insert = (p.flags & kDbgNoInsert) != 0;
     float thr_reg = -INFINITY;                            // lane l: running k-th score of the l-th query this warp owns
     uint32_t lt = 0, unit = 0;
-    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++lt) {
+    for (int tile = tile0; tile < p.n_tiles; tile += tile_step, ++lt) {
       float acc[MULTI ? QP : 1];                          // fp32 RN sum over the tile's K-sets
       for (int set = 0; set < nsets; ++set, ++unit) {
         const int a = unit & 1;
@@ -534,7 +544,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap bank_map, const __grid_consta
             const int i = __ffs(anyq) - 1;
             anyq &= anyq - 1;
             const int j = h * HQ + e * NQW + i;
-            if (j >= p.nq_pass) break;
+            if (j >= nq_pass) break;
             const int oi = h * NQW + i;                   // index among the queries this warp owns
             const float th = __shfl_sync(kFull, thr_reg, oi);
             const float nt = epilogue_insert_query(lists + size_t(j) * p.kcap, p.kcap, p.top_k,
@@ -551,8 +561,8 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap bank_map, const __grid_consta
   // ---- teardown: candidates out, TMEM back ------------------------------------------------------
   tc_fence_before();
   __syncthreads();
-  for (int q = warp; q < p.nq_pass; q += kTcThreads / 32) {
-    uint64_t* out = p.cand + (size_t(blockIdx.x) * p.n_queries + (p.q0 + q)) * p.kcap;
+  for (int q = warp; q < nq_pass; q += kTcThreads / 32) {
+    uint64_t* out = p.cand + (size_t(tile0) * p.n_queries + (q0 + q)) * p.kcap;
     const uint64_t* src = lists + size_t(q) * p.kcap;
     for (int i = lane; i < p.kcap; i += 32) out[i] = src[i];
   }
@@ -673,7 +683,9 @@ int scan_tc_prep_queries(const float* queries, int64_t query_ld, int n_queries, 
 static long long* g_tc_trace = nullptr;
 void scan_tc_set_trace(long long* buf) { g_tc_trace = buf; }
 
-int scan_tc_launch(const ScanParams& sp, const float* qcat, int qp, int stages, int grid, cudaStream_t stream) {
+int scan_tc_launch(const ScanParams& sp, const float* qcat, int qp, int stages, int passes, int ctas_per_pass,
+                   cudaStream_t stream) {
+  const int grid = passes * ctas_per_pass;
   const int d_pad = scan_tc_dim_pad(sp.dim);
   CUtensorMap bank_map;
   int rc = make_map(&bank_map, sp.bank, uint64_t(sp.dim), uint64_t(sp.n_rows), uint64_t(sp.bank_ld) * 4, kTileRows);
@@ -682,7 +694,7 @@ int scan_tc_launch(const ScanParams& sp, const float* qcat, int qp, int stages, 
   p.n_rows = sp.n_rows; p.dim = int(sp.dim); p.n_kblocks = d_pad / kBlockK;
   p.n_tiles = int((sp.n_rows + kTileRows - 1) / kTileRows);
   p.qp = qp; p.nq_pass = sp.nq_pass; p.q0 = sp.q0; p.n_queries = sp.n_queries;
-  p.top_k = sp.top_k; p.kcap = sp.kcap; p.stages = stages; p.flags = sp.flags; p.cand = sp.cand; p.idmap = sp.idmap;
+  p.top_k = sp.top_k; p.kcap = sp.kcap; p.stages = stages; p.passes = passes; p.flags = sp.flags; p.cand = sp.cand; p.idmap = sp.idmap;
   p.qcat = qcat + size_t(sp.q0 / qp) * size_t(d_pad) * 2 * qp;     // pass index = q0 / qp
   p.trace = g_tc_trace;
   const size_t smem = tc_layout(stages, qp, sp.kcap).total + 1024;
