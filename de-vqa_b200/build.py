@@ -18,6 +18,8 @@ NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC,-fvisibility=hidden,-Wall", "-DDEVQA_BUILD",
          "-cudart", "static"]
+if os.environ.get("DEVQA_TC_TRACE"):      # role timeline tracing of the tcgen05 scan (tools/tc_trace.py)
+    FLAGS.append("-DDEVQA_TC_TRACE")
 
 
 def _stale():

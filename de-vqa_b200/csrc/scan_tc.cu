@@ -351,6 +351,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap bank_map, const __grid_consta
       };
       for (int i = 0; i < kPrefetchAhead; ++i) prefetch_next();
       RingPos r;
+      uint32_t trace_it = 0;
       for (int tile = tile0; tile < p.n_tiles; tile += tile_step) {
         for (int kb = 0; kb < nkb; ++kb) {
           prefetch_next();
@@ -359,6 +360,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap bank_map, const __grid_consta
           tma_load_2d(smem + L.a_raw + r.s * kATileBytes, &bank_map, &full_tma[r.s], kb * kBlockK, tile * kTileRows);
           if (qtma)     // the whole [2QP x 32] query k-block is contiguous (and pre-swizzled) in global memory
             bulk_load(smem + L.bq + r.s * b_stage_bytes, qcat + size_t(kb) * (2 * QP * kBlockK), b_stage_bytes, &full_tma[r.s]);
+          trace_at(p, 0, trace_it++);
           r.advance(S);
         }
       }
