@@ -160,7 +160,8 @@ static int run_search(Scratch* s, const SearchArgs& a, uint64_t* out_keys, float
     const int q_pad = int((a.n_queries + qp - 1) / qp) * qp;
     const int d_pad = scan_tc_dim_pad(a.dim);
     const size_t plane = size_t(q_pad) * d_pad;
-    if ((rc = grow(reinterpret_cast<void**>(&s->qsplit), &s->qsplit_bytes, 2 * plane * 4, false))) return rc;
+    if ((rc = grow(reinterpret_cast<void**>(&s->qsplit), &s->qsplit_bytes, 2 * plane * 4 + size_t(q_pad) * 4, false))) return rc;
+    uint32_t* gthr = reinterpret_cast<uint32_t*>(s->qsplit + 2 * plane);   // shared per-query thresholds
     const int64_t tiles = (a.n_rows + 127) / 128;
     // Large banks: one pass per launch on every SM.  Small banks: several passes side by side so that
     // tiles x passes still covers the SMs.
@@ -176,13 +177,30 @@ static int run_search(Scratch* s, const SearchArgs& a, uint64_t* out_keys, float
     p.bank = a.bank; p.cand = s->cand;
     const bool prof = s->profiling && s->prof_used < Scratch::kProfSlots;
     if (prof) DEVQA_CUDA(cudaEventRecord(s->prof_ev[2 * s->prof_used], stream));
-    if ((rc = scan_tc_prep_queries(a.queries, a.query_ld, int(a.n_queries), qp, q_pad, a.dim, a.flags, s->qsplit, stream)))
+    if ((rc = scan_tc_prep_queries(a.queries, a.query_ld, int(a.n_queries), qp, q_pad, a.dim, a.flags, s->qsplit, gthr, stream)))
       return rc;
+    // Threshold seeding: scan a prefix sample of the bank (one tile per CTA) first; the k-th best score of a
+    // SUBSET is a lower bound of the k-th best of the whole bank, so the main scan starts with tight
+    // thresholds in every CTA instead of each CTA re-learning them (k ln(n/k) list insertions each).
+    const bool seed = tiles >= 8 * int64_t(ctas_per_pass) && !(a.flags & (1u << 21));
+    if (seed) {
+      ScanParams pre = p;
+      pre.n_rows = int64_t(ctas_per_pass) * 128;
+      for (int pass = 0; pass < n_passes; pass += side) {
+        const int now = n_passes - pass < side ? n_passes - pass : side;
+        pre.q0 = int32_t(pass * qp);
+        pre.nq_pass = qp;
+        if ((rc = scan_tc_launch(pre, s->qsplit, gthr, qp, stages, now, ctas_per_pass, stream))) return rc;
+        if (prof) s->prof_scan_launches++;
+      }
+      if ((rc = merge_lists_launch(s->cand, grid, a.n_queries, kcap, kcap, a.top_k, nullptr, nullptr, nullptr, stream, gthr)))
+        return rc;
+    }
     for (int pass = 0; pass < n_passes; pass += side) {
       const int now = n_passes - pass < side ? n_passes - pass : side;
       p.q0 = int32_t(pass * qp);
       p.nq_pass = qp;
-      if ((rc = scan_tc_launch(p, s->qsplit, qp, stages, now, ctas_per_pass, stream))) return rc;
+      if ((rc = scan_tc_launch(p, s->qsplit, gthr, qp, stages, now, ctas_per_pass, stream))) return rc;
       if (prof) s->prof_scan_launches++;
     }
     if (prof) {

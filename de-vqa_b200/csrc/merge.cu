@@ -19,7 +19,11 @@ constexpr int kMergeThreads = 512;
 constexpr int kMergeWarps = kMergeThreads / 32;
 
 __device__ __forceinline__ void emit(uint64_t key, int e, int top_k, int64_t q, uint64_t* out_keys,
-                                     float* out_scores, int64_t* out_ids) {
+                                     float* out_scores, int64_t* out_ids, uint32_t* kth_codes) {
+  if (kth_codes) {                        // threshold seeding: only the k-th entry's score code is wanted
+    if (e == top_k - 1) kth_codes[q] = uint32_t(key >> 32);
+    return;
+  }
   if (e >= top_k) return;
   const size_t o = size_t(q) * top_k + e;
   if (out_keys) {
@@ -35,7 +39,7 @@ __device__ __forceinline__ void emit(uint64_t key, int e, int top_k, int64_t q, 
 __global__ void __launch_bounds__(kMergeThreads) merge32_kernel(const uint64_t* __restrict__ lists, int n_lists,
                                                                int64_t n_queries, int list_stride, int list_len,
                                                                int top_k, uint64_t* out_keys, float* out_scores,
-                                                               int64_t* out_ids) {
+                                                               int64_t* out_ids, uint32_t* kth_codes) {
   __shared__ uint64_t sacc[kMergeWarps][32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t q = blockIdx.x;
@@ -56,7 +60,7 @@ __global__ void __launch_bounds__(kMergeThreads) merge32_kernel(const uint64_t* 
     if ((warp % (2 * s)) == 0) sacc[warp][lane] = acc;
     __syncthreads();
   }
-  if (warp == 0) emit(acc, lane, top_k, q, out_keys, out_scores, out_ids);
+  if (warp == 0) emit(acc, lane, top_k, q, out_keys, out_scores, out_ids, kth_codes);
 }
 
 // general capacity (power of two >= 64): accumulators in shared memory
@@ -64,7 +68,8 @@ __global__ void __launch_bounds__(kMergeThreads) merge_generic_kernel(const uint
                                                                      int n_lists, int64_t n_queries,
                                                                      int list_stride, int list_len, int kcap,
                                                                      int top_k, uint64_t* out_keys,
-                                                                     float* out_scores, int64_t* out_ids) {
+                                                                     float* out_scores, int64_t* out_ids,
+                                                                     uint32_t* kth_codes) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int nwarps = blockDim.x >> 5;
   uint64_t* acc = reinterpret_cast<uint64_t*>(smem_raw);       // [warps][kcap]
@@ -88,26 +93,26 @@ __global__ void __launch_bounds__(kMergeThreads) merge_generic_kernel(const uint
     __syncthreads();
   }
   if (warp == 0)
-    for (int e = lane; e < kcap; e += 32) emit(my_acc[e], e, top_k, q, out_keys, out_scores, out_ids);
+    for (int e = lane; e < kcap; e += 32) emit(my_acc[e], e, top_k, q, out_keys, out_scores, out_ids, kth_codes);
 }
 
 }  // namespace
 
 int merge_lists_launch(const uint64_t* lists, int n_lists, int64_t n_queries, int list_stride,
                        int list_len, int top_k, uint64_t* out_keys, float* out_scores, int64_t* out_ids,
-                       cudaStream_t stream) {
+                       cudaStream_t stream, uint32_t* kth_codes) {
   if (n_queries == 0) return DEVQA_OK;
   const int kcap = topk_capacity(top_k > list_len ? top_k : list_len);
   if (kcap == 32) {
     merge32_kernel<<<unsigned(n_queries), kMergeThreads, 0, stream>>>(lists, n_lists, n_queries, list_stride,
                                                                       list_len, top_k, out_keys, out_scores,
-                                                                      out_ids);
+                                                                      out_ids, kth_codes);
   } else {
     const int threads = kcap <= 512 ? kMergeThreads : kMergeThreads / 2;   // keep smem <= 128 KB
     const size_t smem = size_t(2) * (threads / 32) * kcap * 8;
     DEVQA_CUDA(cudaFuncSetAttribute(merge_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
     merge_generic_kernel<<<unsigned(n_queries), threads, smem, stream>>>(
-        lists, n_lists, n_queries, list_stride, list_len, kcap, top_k, out_keys, out_scores, out_ids);
+        lists, n_lists, n_queries, list_stride, list_len, kcap, top_k, out_keys, out_scores, out_ids, kth_codes);
   }
   DEVQA_CUDA(cudaGetLastError());
   count_launch();

@@ -34,18 +34,19 @@ int scan_tc_dim_pad(int64_t dim);
 int scan_tc_plan(int n_queries, int64_t dim, int kcap, int* qp_out, int* stages_out);
 // queries -> normalised TF32 hi / lo split, laid out per pass as the MMA B operand (see scan_tc.cu)
 int scan_tc_prep_queries(const float* queries, int64_t query_ld, int n_queries, int qp, int q_pad, int64_t dim,
-                         unsigned flags, float* qcat, cudaStream_t stream);
+                         unsigned flags, float* qcat, uint32_t* gthr /* [q_pad], zeroed */, cudaStream_t stream);
 // one launch = `passes` consecutive query passes starting at p.q0, each on ctas_per_pass CTAs
-int scan_tc_launch(const ScanParams& p, const float* qcat, int qp, int stages, int passes, int ctas_per_pass,
-                   cudaStream_t stream);
+int scan_tc_launch(const ScanParams& p, const float* qcat, uint32_t* gthr, int qp, int stages, int passes,
+                   int ctas_per_pass, cudaStream_t stream);
 void scan_tc_set_trace(long long* buf);
 
 // merge.cu: reduce `n_lists` sorted lists per query ([n_lists, n_queries, list_stride], the first
 // list_len entries of each valid) to the final top_k.  Exactly one of (out_keys) or
-// (out_scores, out_ids) is written: [n_queries, top_k].
+// (out_scores, out_ids) is written: [n_queries, top_k].  With kth_codes != nullptr nothing else is written:
+// kth_codes[q] receives the monotone score code of the k-th best key (0 when fewer than k exist).
 int merge_lists_launch(const uint64_t* lists, int n_lists, int64_t n_queries, int list_stride,
                        int list_len, int top_k, uint64_t* out_keys, float* out_scores,
-                       int64_t* out_ids, cudaStream_t stream);
+                       int64_t* out_ids, cudaStream_t stream, uint32_t* kth_codes = nullptr);
 
 // synth.cu
 int fill_synthetic_launch(void* dst, int dtype, int64_t n_rows, int64_t dim, int64_t ld, uint64_t seed,

@@ -35,6 +35,10 @@
 //   warp 2      TMEM allocator (512 columns = two accumulator buffers)
 //   warps 4-7   split          lo tile -> TMEM (tcgen05.st) + row norms
 //   warps 8-11  epilogue         tcgen05.ld -> scale -> threshold filter -> per-query sorted lists (smem)
+// Thresholds are shared across CTAs: any CTA's local k-th best score is a lower bound of the global k-th
+// best, so each warp publishes its queries' k-th scores with atomicMax into a per-query global array and
+// re-reads it once per tile.  Rows strictly below that bound cannot be in the result, so the filter stays
+// exact while the number of list insertions drops from ~148 x k ln(n/k) to ~k ln(N/k) per query.
 // Pipelines: smem ring (full_tma / full_split / empty), TMEM double buffer (tmem_full / tmem_empty).
 // Small banks with many queries (C2: 64 tiles, 8 passes) would leave most SMs idle with one pass per
 // launch, so a launch runs several query passes side by side: CTA c works on pass c % passes and on
@@ -208,6 +212,7 @@ struct TcParams {
   uint32_t flags;
   const float* qcat;       // this pass's query operand: [n_kblocks][2*qp rows][32] fp32, rows 128B-swizzled
   uint64_t* cand;          // [grid, n_queries, kcap]
+  uint32_t* gthr;          // [n_queries] shared lower bounds of the k-th score (monotone score codes, 0 = none)
   IdMap idmap;
   long long* trace;        // optional [16][256] clock64 samples of CTA 0's roles (devqa_debug_tc_trace)
 };
@@ -480,9 +485,21 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap bank_map, const __grid_consta
     const int row_in_tile = e * 32 + lane;
     float* stile = reinterpret_cast<float*>(smem + L.scratch);        // [HQ][128]
     const bool no_insert = (p.flags & kDbgNoInsert) != 0;
+    int slow_calls = 0;
     float thr_reg = -INFINITY;                            // lane l: running k-th score of the l-th query this warp owns
     uint32_t lt = 0, unit = 0;
+    // lane l of warp e owns query  own_j(l) = (l / NQW_) * HQ + e * NQW_ + l % NQW_   (l < QP / 4)
+    constexpr int NQW_ = HQ / 4;
+    const int own_j = (lane / NQW_) * HQ + e * NQW_ + lane % NQW_;
+    const bool own_live = lane < QP / 4 && own_j < nq_pass;
+    uint32_t* const own_gthr = p.gthr + q0 + (own_live ? own_j : 0);
     for (int tile = tile0; tile < p.n_tiles; tile += tile_step, ++lt) {
+      // pick up the bounds other CTAs have published (one relaxed load per owned query per tile)
+      if (own_live) {
+        uint32_t code;
+        asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(code) : "l"(own_gthr));
+        if (code != 0u) thr_reg = fmaxf(thr_reg, code_score(code));
+      }
       float acc[MULTI ? QP : 1];                          // fp32 RN sum over the tile's K-sets
       for (int set = 0; set < nsets; ++set, ++unit) {
         const int a = unit & 1;
@@ -543,6 +560,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap bank_map, const __grid_consta
             anyq |= (__ballot_sync(kFull, hit) ? 1u : 0u) << i;
           }
           while (anyq) {                                  // warp-uniform
+            ++slow_calls;
             const int i = __ffs(anyq) - 1;
             anyq &= anyq - 1;
             const int j = h * HQ + e * NQW + i;
@@ -551,11 +569,17 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap bank_map, const __grid_consta
             const float th = __shfl_sync(kFull, thr_reg, oi);
             const float nt = epilogue_insert_query(lists + size_t(j) * p.kcap, p.kcap, p.top_k,
                                                    stile + (e * NQW + i) * kTileRows, th, rowmask, row0, p.idmap, lane);
-            if (lane == oi) thr_reg = nt;
+            if (lane == oi && nt > thr_reg) {               // publish: a lower bound of the global k-th score
+              thr_reg = nt;
+              atomicMax(own_gthr, score_code(nt));
+            }
           }
           epilogue_barrier();                             // the score tile may be overwritten again
         }
         if (e == 0 && lane == 0) trace_at(p, 7, unit);
+#ifdef DEVQA_TC_TRACE
+        if (e == 0 && lane == 0 && p.trace && blockIdx.x == 0 && unit < 256) { p.trace[8 * 256 + unit] = slow_calls; slow_calls = 0; }
+#endif
       }
     }
   }
@@ -577,7 +601,9 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap bank_map, const __grid_consta
 // is one contiguous, shared-memory-ready copy.  One warp per query.
 __global__ void __launch_bounds__(256) prep_queries_kernel(const float* __restrict__ q, int64_t q_ld, int n_queries, int dim,
                                                            int qp, int n_kblocks, int q_pad, unsigned flags,
-                                                           float* __restrict__ qcat) {
+                                                           float* __restrict__ qcat, uint32_t* __restrict__ gthr) {
+  if (blockIdx.x == 0)
+    for (int i = threadIdx.x; i < q_pad; i += blockDim.x) gthr[i] = 0u;
   const int lane = threadIdx.x & 31;
   const int warps = gridDim.x * (blockDim.x >> 5);
   const int d_pad = n_kblocks * kBlockK;
@@ -673,10 +699,10 @@ int scan_tc_plan(int n_queries, int64_t dim, int kcap, int* qp_out, int* stages_
 
 // qcat must hold q_pad * dim_pad * 2 floats; q_pad is a multiple of qp.
 int scan_tc_prep_queries(const float* queries, int64_t query_ld, int n_queries, int qp, int q_pad, int64_t dim,
-                         unsigned flags, float* qcat, cudaStream_t stream) {
+                         unsigned flags, float* qcat, uint32_t* gthr, cudaStream_t stream) {
   const int n_kblocks = scan_tc_dim_pad(dim) / kBlockK;
   const int grid = (q_pad + 7) / 8;
-  prep_queries_kernel<<<grid, 256, 0, stream>>>(queries, query_ld, n_queries, int(dim), qp, n_kblocks, q_pad, flags, qcat);
+  prep_queries_kernel<<<grid, 256, 0, stream>>>(queries, query_ld, n_queries, int(dim), qp, n_kblocks, q_pad, flags, qcat, gthr);
   DEVQA_CUDA(cudaGetLastError());
   count_launch();
   return DEVQA_OK;
@@ -685,8 +711,8 @@ int scan_tc_prep_queries(const float* queries, int64_t query_ld, int n_queries, 
 static long long* g_tc_trace = nullptr;
 void scan_tc_set_trace(long long* buf) { g_tc_trace = buf; }
 
-int scan_tc_launch(const ScanParams& sp, const float* qcat, int qp, int stages, int passes, int ctas_per_pass,
-                   cudaStream_t stream) {
+int scan_tc_launch(const ScanParams& sp, const float* qcat, uint32_t* gthr, int qp, int stages, int passes,
+                   int ctas_per_pass, cudaStream_t stream) {
   const int grid = passes * ctas_per_pass;
   const int d_pad = scan_tc_dim_pad(sp.dim);
   CUtensorMap bank_map;
@@ -696,7 +722,7 @@ int scan_tc_launch(const ScanParams& sp, const float* qcat, int qp, int stages, 
   p.n_rows = sp.n_rows; p.dim = int(sp.dim); p.n_kblocks = d_pad / kBlockK;
   p.n_tiles = int((sp.n_rows + kTileRows - 1) / kTileRows);
   p.qp = qp; p.nq_pass = sp.nq_pass; p.q0 = sp.q0; p.n_queries = sp.n_queries;
-  p.top_k = sp.top_k; p.kcap = sp.kcap; p.stages = stages; p.passes = passes; p.flags = sp.flags; p.cand = sp.cand; p.idmap = sp.idmap;
+  p.top_k = sp.top_k; p.kcap = sp.kcap; p.stages = stages; p.passes = passes; p.flags = sp.flags; p.cand = sp.cand; p.gthr = gthr; p.idmap = sp.idmap;
   p.qcat = qcat + size_t(sp.q0 / qp) * size_t(d_pad) * 2 * qp;     // pass index = q0 / qp
   p.trace = g_tc_trace;
   const size_t smem = tc_layout(stages, qp, sp.kcap).total + 1024;
