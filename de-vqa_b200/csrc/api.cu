@@ -103,6 +103,7 @@ struct SearchArgs {
   const void* bank; int dtype; int64_t n_rows, dim, bank_ld;
   const float* queries; int64_t n_queries, query_ld;
   int top_k; unsigned flags; IdMap idmap;
+  const float* row_sumsq = nullptr;
 };
 
 static int validate(const SearchArgs& a) {
@@ -142,7 +143,7 @@ static int run_search(Scratch* s, const SearchArgs& a, uint64_t* out_keys, float
   if (a.flags & DEVQA_FORCE_STREAM) use_tc = false;
   if (a.flags & DEVQA_FORCE_TENSOR) {
     if (!tc_ok) {
-      set_error("DEVQA_FORCE_TENSOR: the tcgen05 scan needs an fp32 bank with 16-byte aligned rows and top_k <= 128");
+      set_error("DEVQA_FORCE_TENSOR: the tcgen05 scan needs 16-byte aligned bank rows and top_k <= 128");
       return DEVQA_E_UNSUPPORTED;
     }
     use_tc = true;
@@ -151,17 +152,16 @@ static int run_search(Scratch* s, const SearchArgs& a, uint64_t* out_keys, float
   ScanParams p{};
   p.n_rows = a.n_rows; p.dim = a.dim; p.bank_ld = a.bank_ld;
   p.queries = a.queries; p.query_ld = a.query_ld; p.n_queries = int32_t(a.n_queries);
-  p.top_k = a.top_k; p.kcap = kcap; p.flags = a.flags; p.idmap = a.idmap;
+  p.top_k = a.top_k; p.kcap = kcap; p.flags = a.flags; p.idmap = a.idmap; p.row_sumsq = a.row_sumsq;
   int grid = 1;
 
   if (use_tc) {
     int qp = 0, stages = 0;
-    if ((rc = scan_tc_plan(int(a.n_queries), a.dim, kcap, &qp, &stages))) return rc;
+    if ((rc = scan_tc_plan(a.dtype, int(a.n_queries), a.dim, kcap, &qp, &stages))) return rc;
     const int q_pad = int((a.n_queries + qp - 1) / qp) * qp;
-    const int d_pad = scan_tc_dim_pad(a.dim);
-    const size_t plane = size_t(q_pad) * d_pad;
-    if ((rc = grow(reinterpret_cast<void**>(&s->qsplit), &s->qsplit_bytes, 2 * plane * 4 + size_t(q_pad) * 4, false))) return rc;
-    uint32_t* gthr = reinterpret_cast<uint32_t*>(s->qsplit + 2 * plane);   // shared per-query thresholds
+    const size_t qcat_bytes = scan_tc_qcat_bytes(a.dtype, a.dim, q_pad);
+    if ((rc = grow(reinterpret_cast<void**>(&s->qsplit), &s->qsplit_bytes, qcat_bytes + size_t(q_pad) * 4, false))) return rc;
+    uint32_t* gthr = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(s->qsplit) + qcat_bytes);   // shared per-query thresholds
     const int64_t tiles = (a.n_rows + 127) / 128;
     // Large banks: one pass per launch on every SM.  Small banks: several passes side by side so that
     // tiles x passes still covers the SMs.
@@ -177,7 +177,7 @@ static int run_search(Scratch* s, const SearchArgs& a, uint64_t* out_keys, float
     p.bank = a.bank; p.cand = s->cand;
     const bool prof = s->profiling && s->prof_used < Scratch::kProfSlots;
     if (prof) DEVQA_CUDA(cudaEventRecord(s->prof_ev[2 * s->prof_used], stream));
-    if ((rc = scan_tc_prep_queries(a.queries, a.query_ld, int(a.n_queries), qp, q_pad, a.dim, a.flags, s->qsplit, gthr, stream)))
+    if ((rc = scan_tc_prep_queries(a.dtype, a.queries, a.query_ld, int(a.n_queries), qp, q_pad, a.dim, a.flags, s->qsplit, gthr, stream)))
       return rc;
     // Threshold seeding: scan a prefix sample of the bank (one tile per CTA) first; the k-th best score of a
     // SUBSET is a lower bound of the k-th best of the whole bank, so the main scan starts with tight
@@ -190,8 +190,7 @@ static int run_search(Scratch* s, const SearchArgs& a, uint64_t* out_keys, float
         const int now = n_passes - pass < side ? n_passes - pass : side;
         pre.q0 = int32_t(pass * qp);
         pre.nq_pass = qp;
-        if ((rc = scan_tc_launch(pre, s->qsplit, gthr, qp, stages, now, ctas_per_pass, stream))) return rc;
-        if (prof) s->prof_scan_launches++;
+        if ((rc = scan_tc_launch(pre, a.dtype, s->qsplit, gthr, qp, stages, now, ctas_per_pass, stream))) return rc;
       }
       if ((rc = merge_lists_launch(s->cand, grid, a.n_queries, kcap, kcap, a.top_k, nullptr, nullptr, nullptr, stream, gthr)))
         return rc;
@@ -200,7 +199,7 @@ static int run_search(Scratch* s, const SearchArgs& a, uint64_t* out_keys, float
       const int now = n_passes - pass < side ? n_passes - pass : side;
       p.q0 = int32_t(pass * qp);
       p.nq_pass = qp;
-      if ((rc = scan_tc_launch(p, s->qsplit, gthr, qp, stages, now, ctas_per_pass, stream))) return rc;
+      if ((rc = scan_tc_launch(p, a.dtype, s->qsplit, gthr, qp, stages, now, ctas_per_pass, stream))) return rc;
       if (prof) s->prof_scan_launches++;
     }
     if (prof) {
@@ -262,6 +261,7 @@ struct devqa_bank {
   int64_t dim = 0, ld = 0;
   int64_t size = 0, capacity = 0;
   void* data = nullptr;
+  float* sumsq = nullptr;          // cached ||row||^2 per stored row (bf16 banks: of the rounded row)
   devqa::IdMap idmap{0, 0, 0, 1};
   size_t esz() const { return dtype == DEVQA_F32 ? 4 : 2; }
 };
@@ -299,11 +299,21 @@ static int bank_grow(devqa_bank* b, int64_t want_rows, cudaStream_t stream) {
   }
   if (b->size > 0)
     DEVQA_CUDA(cudaMemcpyAsync(fresh, b->data, size_t(b->size) * b->ld * b->esz(), cudaMemcpyDeviceToDevice, stream));
+  float* fresh_ss = nullptr;
+  e = cudaMalloc(&fresh_ss, size_t(cap) * 4);
+  if (e != cudaSuccess) {
+    cudaFree(fresh);
+    set_error("cudaMalloc of %zu bytes for the row norms failed: %s", size_t(cap) * 4, cudaGetErrorString(e));
+    return DEVQA_E_NOMEM;
+  }
+  if (b->size > 0) DEVQA_CUDA(cudaMemcpyAsync(fresh_ss, b->sumsq, size_t(b->size) * 4, cudaMemcpyDeviceToDevice, stream));
   if (b->data) {
     DEVQA_CUDA(cudaStreamSynchronize(stream));
     DEVQA_CUDA(cudaFree(b->data));
+    DEVQA_CUDA(cudaFree(b->sumsq));
   }
   b->data = fresh;
+  b->sumsq = fresh_ss;
   b->capacity = cap;
   return DEVQA_OK;
 }
@@ -312,6 +322,7 @@ static SearchArgs bank_args(const devqa_bank* b, const float* q, int64_t nq, int
   SearchArgs a{};
   a.bank = b->data; a.dtype = b->dtype; a.n_rows = b->size; a.dim = b->dim; a.bank_ld = b->ld;
   a.queries = q; a.n_queries = nq; a.query_ld = qld; a.top_k = k; a.flags = flags; a.idmap = b->idmap;
+  a.row_sumsq = b->sumsq;
   return a;
 }
 
@@ -450,7 +461,7 @@ int devqa_bank_create(devqa_bank** out, int device, int64_t dim, int64_t capacit
 int devqa_bank_destroy(devqa_bank* b) {
   if (!b) return DEVQA_OK;
   DEVQA_ON_DEVICE(b->device);
-  if (b->data) { cudaDeviceSynchronize(); cudaFree(b->data); }
+  if (b->data) { cudaDeviceSynchronize(); cudaFree(b->data); cudaFree(b->sumsq); }
   delete b;
   return DEVQA_OK;
 }
@@ -502,6 +513,7 @@ int devqa_bank_append(devqa_bank* b, const float* rows, int64_t n, int64_t ld, i
       if ((rc = convert_rows_launch(rows, ld, dst, b->dtype, b->ld, n, b->dim, stream))) return rc;
     }
   }
+  if ((rc = row_sumsq_launch(dst, b->dtype, n, b->dim, b->ld, b->sumsq + b->size, stream))) return rc;
   b->size += n;
   return DEVQA_OK;
 }
@@ -716,6 +728,7 @@ int devqa_bank_append_synthetic(devqa_bank* b, int64_t n_rows, uint64_t seed, in
   if (rc) return rc;
   char* dst = static_cast<char*>(b->data) + size_t(b->size) * b->ld * b->esz();
   if ((rc = fill_synthetic_launch(dst, b->dtype, n_rows, b->dim, b->ld, seed, first_global_row, kind, stream))) return rc;
+  if ((rc = row_sumsq_launch(dst, b->dtype, n_rows, b->dim, b->ld, b->sumsq + b->size, stream))) return rc;
   b->size += n_rows;
   return DEVQA_OK;
 }

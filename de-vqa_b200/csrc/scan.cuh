@@ -21,6 +21,7 @@ struct ScanParams {
   uint32_t flags;
   uint64_t* cand;          // [grid, n_queries, kcap] sorted candidate lists (output)
   IdMap idmap;
+  const float* row_sumsq;  // optional cached ||row||^2 of library-owned banks (nullptr: computed in-kernel)
 };
 
 size_t scan_stream_smem_bytes(int64_t dim, int nv, int qt, int kcap);
@@ -28,15 +29,16 @@ int scan_stream_rows_per_group(int qt);
 int scan_stream_launch(const ScanParams& p, int bank_dtype, bool vectorised, int qt, int grid,
                        cudaStream_t stream);
 
-// scan_tc.cu: tcgen05 / TMEM / TMA contraction kernel for large query batches (fp32 banks)
+// scan_tc.cu: tcgen05 / TMEM / TMA contraction kernel for large query batches (fp32 and bf16 banks)
 bool scan_tc_supported(int bank_dtype, const void* bank, int64_t dim, int64_t bank_ld, int top_k);
-int scan_tc_dim_pad(int64_t dim);
-int scan_tc_plan(int n_queries, int64_t dim, int kcap, int* qp_out, int* stages_out);
-// queries -> normalised TF32 hi / lo split, laid out per pass as the MMA B operand (see scan_tc.cu)
-int scan_tc_prep_queries(const float* queries, int64_t query_ld, int n_queries, int qp, int q_pad, int64_t dim,
-                         unsigned flags, float* qcat, uint32_t* gthr /* [q_pad], zeroed */, cudaStream_t stream);
+int scan_tc_plan(int bank_dtype, int n_queries, int64_t dim, int kcap, int* qp_out, int* stages_out);
+size_t scan_tc_qcat_bytes(int bank_dtype, int64_t dim, int q_pad);
+// queries -> normalised hi/lo (TF32, fp32 banks) or hi/mid/lo (bf16 banks) split, laid out per pass as the
+// MMA B operand (see scan_tc.cu); also zeroes the shared threshold array gthr [q_pad]
+int scan_tc_prep_queries(int bank_dtype, const float* queries, int64_t query_ld, int n_queries, int qp, int q_pad,
+                         int64_t dim, unsigned flags, void* qcat, uint32_t* gthr, cudaStream_t stream);
 // one launch = `passes` consecutive query passes starting at p.q0, each on ctas_per_pass CTAs
-int scan_tc_launch(const ScanParams& p, const float* qcat, uint32_t* gthr, int qp, int stages, int passes,
+int scan_tc_launch(const ScanParams& p, int bank_dtype, const void* qcat, uint32_t* gthr, int qp, int stages, int passes,
                    int ctas_per_pass, cudaStream_t stream);
 void scan_tc_set_trace(long long* buf);
 
@@ -54,6 +56,8 @@ int fill_synthetic_launch(void* dst, int dtype, int64_t n_rows, int64_t dim, int
 // norm.cu
 int normalize_rows_launch(const float* src, int64_t src_ld, float* dst, int64_t dst_ld, int64_t n_rows, int64_t dim,
                           unsigned flags, cudaStream_t stream);
+// norm.cu: ||row||^2 of n rows (fp32 or bf16 storage), one warp per row
+int row_sumsq_launch(const void* rows, int dtype, int64_t n_rows, int64_t dim, int64_t ld, float* out, cudaStream_t stream);
 // synth.cu helper kernels
 int widen_rows_launch(const void* src, int64_t src_ld, float* dst, int64_t dst_ld, int64_t n_rows, int64_t dim,
                       cudaStream_t stream);

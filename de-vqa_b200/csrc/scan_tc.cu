@@ -26,6 +26,11 @@
 // same tile alternate between the two TMEM buffers and are summed in fp32 round-to-nearest in the
 // epilogue threads' registers (MULTI instantiation, D > 1024).
 //
+// bf16 banks (BF = true): the bank is exact in bf16, so only the queries are split, three ways
+// (hi + mid + lo, each bf16 = 24 mantissa bits): ONE mma group  A x [Qhi;Qmid;Qlo]  (kind::f16, N = 3Q,
+// 64 columns per k-block) fills the same three column groups; the split warps only accumulate
+// ||row||^2 and the second issuer idles.
+//
 // Warp roles (384 threads, 1 CTA/SM, persistent over 128-row tiles):
 //   warp 0      TMA producer   bank tile [128 x 32] fp32 (tensor map, SWIZZLE_128B) + the query k-block
 //                              [2Q x 32] fp32 as ONE contiguous bulk copy (prep kernel pre-swizzles it):
@@ -130,6 +135,15 @@ __device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
       "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// bf16 inputs (K = 16 per instruction), fp32 accumulate
+__device__ __forceinline__ void mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
 // same, with the A operand read from tensor memory (lane = row, column = k)
 __device__ __forceinline__ void mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
@@ -197,6 +211,11 @@ struct RingPos {
   __device__ __forceinline__ void advance(int S) { if (++s == S) { s = 0; phase ^= 1u; } }
 };
 
+// instruction descriptor: fp32 accumulate, BF16 A and B, both K-major, M = 128, N = n
+__host__ __device__ constexpr uint32_t idesc_bf16(int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(n >> 3) << 17) | (uint32_t(kTileRows >> 4) << 24);
+}
+
 struct TcParams {
   int64_t n_rows;
   int32_t dim;
@@ -212,6 +231,7 @@ struct TcParams {
   uint32_t flags;
   const float* qcat;       // this pass's query operand: [n_kblocks][2*qp rows][32] fp32, rows 128B-swizzled
   uint64_t* cand;          // [grid, n_queries, kcap]
+  const float* row_sumsq;  // optional cached ||row||^2 (bf16 variant: replaces the in-kernel norm warps)
   uint32_t* gthr;          // [n_queries] shared lower bounds of the k-th score (monotone score codes, 0 = none)
   IdMap idmap;
   long long* trace;        // optional [16][256] clock64 samples of CTA 0's roles (devqa_debug_tc_trace)
@@ -227,11 +247,11 @@ __device__ __forceinline__ void trace_at(const TcParams& p, int role, uint32_t i
 struct SmemLayout {        // byte offsets from the 1024-aligned base
   uint32_t a_raw, bq, lists, thr, scratch, norms, bars, tmem_slot, total;
 };
-__host__ __device__ inline SmemLayout tc_layout(int stages, int qp, int kcap) {
+__host__ __device__ inline SmemLayout tc_layout(int stages, int qp, int kcap, int b_parts = 2) {
   SmemLayout L;
   uint32_t off = 0;
   L.a_raw = off; off += uint32_t(stages) * kATileBytes;
-  L.bq = off;    off += uint32_t(stages) * uint32_t(2 * qp) * 128;           // [2*qp rows x 128 B], 1024-aligned since qp % 16 == 0
+  L.bq = off;    off += uint32_t(stages) * uint32_t(b_parts * qp) * 128;     // [parts*qp rows x 128 B], 1024-aligned since qp % 16 == 0
   L.lists = off; off += uint32_t(qp) * kcap * 8;
   L.thr = off;   off += uint32_t(qp) * 4;
   L.scratch = off; off += uint32_t(qp < 32 ? qp : 32) * kTileRows * 4;   // score tile [HQ][128]
@@ -293,15 +313,17 @@ __device__ __noinline__ float epilogue_insert_query(uint64_t* list, int kcap, in
   return kth == kEmptyKey ? -INFINITY : key_score(kth);
 }
 
-template <int QP, bool MULTI>
+template <int QP, bool MULTI, bool BF>
 __global__ void __launch_bounds__(kTcThreads, 1)
 scan_tc_kernel(const __grid_constant__ CUtensorMap bank_map, const __grid_constant__ TcParams p) {
   extern __shared__ unsigned char smem_unaligned[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_unaligned) + 1023) & ~uintptr_t(1023));
-  const SmemLayout L = tc_layout(p.stages, p.qp, p.kcap);
+  constexpr int kParts = BF ? 3 : 2;                     // row groups of the query operand per k-block
+  constexpr int kElemsK = BF ? 64 : 32;                  // bank columns per k-block (always 128 bytes)
+  const SmemLayout L = tc_layout(p.stages, p.qp, p.kcap, kParts);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int S = p.stages;
-  const uint32_t b_stage_bytes = uint32_t(2 * QP) * 128;
+  const uint32_t b_stage_bytes = uint32_t(kParts * QP) * 128;
 
   uint64_t* lists = reinterpret_cast<uint64_t*>(smem + L.lists);
   float* norms = reinterpret_cast<float*>(smem + L.norms);
@@ -318,8 +340,8 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap bank_map, const __grid_consta
     tma_prefetch_desc(&bank_map);
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < S; ++s) { mbar_init(&full_tma[s], 1); mbar_init(&full_split[s], 128); mbar_init(&empty[s], 2); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 2); mbar_init(&tmem_empty[a], 128); }
+    for (int s = 0; s < S; ++s) { mbar_init(&full_tma[s], 1); mbar_init(&full_split[s], 128); mbar_init(&empty[s], BF ? 1 : 2); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], BF ? 1 : 2); mbar_init(&tmem_empty[a], 128); }
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, 512);
@@ -332,11 +354,13 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap bank_map, const __grid_consta
   const int tile0 = int(blockIdx.x) / p.passes, tile_step = int(gridDim.x) / p.passes;
   const int q0 = p.q0 + pass_local * QP;
   const int nq_pass = min(QP, p.n_queries - q0);
-  const float* const qcat = p.qcat + size_t(pass_local) * size_t(p.n_kblocks) * (2 * QP * kBlockK);
+  const float* const qcat = p.qcat + size_t(pass_local) * size_t(p.n_kblocks) * (kParts * QP * 32);   // 32 words per 128-byte row
   // TMEM columns: two accumulator buffers of 3*QP columns, then one 32-column lo tile per ring stage
   constexpr uint32_t kAccCols = 3 * QP;
   const uint32_t tmem_alo = tmem_base + 2 * kAccCols;
   const int nkb = p.n_kblocks;
+  // bf16 banks with cached row norms need no pass over the tile by CUDA cores at all
+  const bool norm_warps = !(BF && (p.row_sumsq != nullptr || !(p.flags & DEVQA_NORMALIZE_BANK)));
   const int nsets = (nkb + kSetKBlocks - 1) / kSetKBlocks;   // accumulation units per tile (1 unless MULTI)
 
   if (warp == 0) {
@@ -350,7 +374,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap bank_map, const __grid_consta
       int pf_tile = tile0, pf_kb = 0;                     // next k-block to prefetch
       auto prefetch_next = [&]() {
         if (pf_tile < p.n_tiles) {
-          if (pf_on) tma_prefetch_l2_2d(&bank_map, pf_kb * kBlockK, pf_tile * kTileRows);
+          if (pf_on) tma_prefetch_l2_2d(&bank_map, pf_kb * kElemsK, pf_tile * kTileRows);
           if (++pf_kb == nkb) { pf_kb = 0; pf_tile += tile_step; }
         }
       };
@@ -362,9 +386,9 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap bank_map, const __grid_consta
           prefetch_next();
           mbar_wait(&empty[r.s], r.phase ^ 1u);
           mbar_expect_tx(&full_tma[r.s], tx_bytes);
-          tma_load_2d(smem + L.a_raw + r.s * kATileBytes, &bank_map, &full_tma[r.s], kb * kBlockK, tile * kTileRows);
+          tma_load_2d(smem + L.a_raw + r.s * kATileBytes, &bank_map, &full_tma[r.s], kb * kElemsK, tile * kTileRows);
           if (qtma)     // the whole [2QP x 32] query k-block is contiguous (and pre-swizzled) in global memory
-            bulk_load(smem + L.bq + r.s * b_stage_bytes, qcat + size_t(kb) * (2 * QP * kBlockK), b_stage_bytes, &full_tma[r.s]);
+            bulk_load(smem + L.bq + r.s * b_stage_bytes, qcat + size_t(kb) * (kParts * QP * 32), b_stage_bytes, &full_tma[r.s]);
           trace_at(p, 0, trace_it++);
           r.advance(S);
         }
@@ -373,7 +397,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap bank_map, const __grid_consta
   } else if (warp == 1) {
     // ===== MMA issuer 1: A (hi by truncation, from shared memory) x [Qhi ; Qlo] -> cols [0, 2QP) =====
     if (lane == 0) {
-      const uint32_t idesc_cat = idesc_tf32(2 * QP);
+      const uint32_t idesc_cat = BF ? idesc_bf16(3 * QP) : idesc_tf32(2 * QP);
       const uint32_t a_lo0 = (smem_u32(smem + L.a_raw) & 0x3ffffu) >> 4, b_lo0 = (smem_u32(smem + L.bq) & 0x3ffffu) >> 4;
       RingPos r;
       uint32_t unit = 0;
@@ -390,9 +414,12 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap bank_map, const __grid_consta
             mbar_wait(&full_tma[r.s], r.phase);
             tc_fence_after();
 #pragma unroll
-            for (int kk = 0; kk < kBlockK / 8; ++kk)
-              mma_tf32(d, desc_from_lo(a_lo + kk * 2), desc_from_lo(b_lo + kk * 2), idesc_cat, first | uint32_t(kk));
-            mma_commit(&empty[r.s]);                      // one of the two arrivals that free the stage
+            for (int kk = 0; kk < 4; ++kk) {              // four 32-byte K slices of the 128-byte rows
+              if constexpr (BF) mma_bf16(d, desc_from_lo(a_lo + kk * 2), desc_from_lo(b_lo + kk * 2), idesc_cat, first | uint32_t(kk));
+              else mma_tf32(d, desc_from_lo(a_lo + kk * 2), desc_from_lo(b_lo + kk * 2), idesc_cat, first | uint32_t(kk));
+            }
+            if (BF && norm_warps) mbar_wait(&full_split[r.s], r.phase);   // the norm warps are done reading the stage
+            mma_commit(&empty[r.s]);                      // (one of) the arrival(s) that free the stage
             r.advance(S);
           }
           mma_commit(&tmem_full[a]);
@@ -401,7 +428,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap bank_map, const __grid_consta
     }
   } else if (warp == 2) {
     // ===== MMA issuer 2: Alo (from tensor memory) x Qhi -> cols [2QP, 3QP) =====
-    if (lane == 0) {
+    if (lane == 0 && !BF) {
       const uint32_t idesc_hi = idesc_tf32(QP);
       const uint32_t b_lo0 = (smem_u32(smem + L.bq) & 0x3ffffu) >> 4;
       const bool on = !(p.flags & kDbgNoMma2);
@@ -432,7 +459,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap bank_map, const __grid_consta
         }
       }
     }
-  } else if (warp >= 4 && warp < 8) {
+  } else if (warp >= 4 && warp < 8 && norm_warps) {
     // ===== split warps: thread <-> bank row of the tile =====
     const int row = threadIdx.x - 128;
     const uint32_t row_off = uint32_t(row) * 128;
@@ -449,8 +476,23 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap bank_map, const __grid_consta
         const int s = rp.s;
         mbar_wait(&full_tma[s], rp.phase);
         const uint32_t src = a_raw_s + uint32_t(s) * kATileBytes;     // shared-space address of this thread's row
+        if constexpr (BF) {
+          if (p.flags & DEVQA_NORMALIZE_BANK) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+              const float4 v = lds128(src + (uint32_t(c) << 4));      // order is irrelevant for a sum of squares
+              const uint32_t w[4] = {__float_as_uint(v.x), __float_as_uint(v.y), __float_as_uint(v.z), __float_as_uint(v.w)};
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float e0 = __uint_as_float(w[i] << 16), e1 = __uint_as_float(w[i] & 0xffff0000u);
+                ss[c] = fmaf(e0, e0, ss[c]);
+                ss[c] = fmaf(e1, e1, ss[c]);
+              }
+            }
+          }
+        }
         uint32_t lo[32];
-        if (!(p.flags & kDbgNoSplit)) {
+        if (!BF && !(p.flags & kDbgNoSplit)) {
 #pragma unroll
           for (int c = 0; c < 8; ++c) {                   // logical 16-byte chunk c of the row
             const float4 v = lds128(src + ((uint32_t(c) ^ sw) << 4));
@@ -509,7 +551,10 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap bank_map, const __grid_consta
         if (e == 0 && lane == 0) trace_at(p, 6, unit);
         float inv = 1.f;
         if (last && (p.flags & DEVQA_NORMALIZE_BANK)) {
-          const float nrm = sqrtf(norms[(lt % kNormRing) * kTileRows + row_in_tile]);
+          const int64_t grow = int64_t(tile) * kTileRows + row_in_tile;
+          const float ssq = norm_warps ? norms[(lt % kNormRing) * kTileRows + row_in_tile]
+                                       : (grow < p.n_rows ? p.row_sumsq[grow] : 1.f);
+          const float nrm = sqrtf(ssq);
           inv = 1.0f / ((p.flags & DEVQA_NOEPS) ? nrm : fmaxf(nrm, kNormEps));
         }
         const uint32_t taddr = tmem_base + uint32_t(a) * kAccCols + (uint32_t(e * 32) << 16);
@@ -638,11 +683,55 @@ __global__ void __launch_bounds__(256) prep_queries_kernel(const float* __restri
   }
 }
 
+// bf16-bank variant: three bf16 planes hi + mid + lo (24 mantissa bits together), k-blocks of 64 columns.
+// Output per pass: [n_kblocks][3*qp rows][64 bf16], rows 0..qp-1 = hi, qp.. = mid, 2qp.. = lo, 128B-swizzled.
+__global__ void __launch_bounds__(256) prep_queries_bf16_kernel(const float* __restrict__ q, int64_t q_ld, int n_queries, int dim,
+                                                                int qp, int n_kblocks, int q_pad, unsigned flags,
+                                                                __nv_bfloat16* __restrict__ qcat, uint32_t* __restrict__ gthr) {
+  if (blockIdx.x == 0)
+    for (int i = threadIdx.x; i < q_pad; i += blockDim.x) gthr[i] = 0u;
+  const int lane = threadIdx.x & 31;
+  const int warps = gridDim.x * (blockDim.x >> 5);
+  const int d_pad = n_kblocks * 64;
+  for (int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < q_pad; r += warps) {
+    float inv = 0.f;
+    const float* src = q + size_t(r < n_queries ? r : 0) * q_ld;
+    if (r < n_queries) {
+      inv = 1.f;
+      if (flags & DEVQA_NORMALIZE_QUERY) {
+        float ss = 0.f;
+        for (int c = lane; c < dim; c += 32) { const float x = src[c]; ss = fmaf(x, x, ss); }
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) ss += __shfl_xor_sync(kFull, ss, off);
+        const float nrm = sqrtf(ss);
+        inv = 1.0f / ((flags & DEVQA_NOEPS) ? nrm : fmaxf(nrm, kNormEps));
+      }
+    }
+    const int pass = r / qp, rp = r % qp;
+    __nv_bfloat16* base = qcat + size_t(pass) * n_kblocks * (3 * qp * 64);
+    for (int c = lane; c < d_pad; c += 32) {
+      const float x = (r < n_queries && c < dim) ? src[c] * inv : 0.f;
+      const __nv_bfloat16 hi = __float2bfloat16_rn(x);
+      const float r1 = x - __bfloat162float(hi);
+      const __nv_bfloat16 mid = __float2bfloat16_rn(r1);
+      const __nv_bfloat16 lo = __float2bfloat16_rn(r1 - __bfloat162float(mid));
+      const int kb = c / 64, w = c % 64;
+      __nv_bfloat16* blk = base + size_t(kb) * (3 * qp * 64);
+      const __nv_bfloat16 part[3] = {hi, mid, lo};
+#pragma unroll
+      for (int t = 0; t < 3; ++t) {
+        const int row = t * qp + rp;
+        blk[row * 64 + (((w >> 3) ^ (row & 7)) << 3) + (w & 7)] = part[t];
+      }
+    }
+  }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-int make_map(CUtensorMap* map, const void* base, uint64_t cols, uint64_t rows, uint64_t ld_bytes, uint32_t box_rows) {
+int make_map(CUtensorMap* map, const void* base, bool bf16, uint64_t cols, uint64_t rows, uint64_t ld_bytes, uint32_t box_rows) {
   static EncodeTiledFn encode = nullptr;
   if (!encode) {
     void* fn = nullptr;
@@ -656,9 +745,9 @@ int make_map(CUtensorMap* map, const void* base, uint64_t cols, uint64_t rows, u
   }
   const cuuint64_t gdim[2] = {cols, rows};
   const cuuint64_t gstride[1] = {ld_bytes};
-  const cuuint32_t box[2] = {kBlockK, box_rows};
+  const cuuint32_t box[2] = {bf16 ? 64u : 32u, box_rows};     // 128 bytes of columns either way
   const cuuint32_t estride[2] = {1, 1};
-  CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), gdim, gstride, box, estride,
+  CUresult r = encode(map, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), gdim, gstride, box, estride,
                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -672,22 +761,31 @@ int make_map(CUtensorMap* map, const void* base, uint64_t cols, uint64_t rows, u
 }  // namespace
 
 bool scan_tc_supported(int bank_dtype, const void* bank, int64_t dim, int64_t bank_ld, int top_k) {
-  return bank_dtype == DEVQA_F32 && reinterpret_cast<uintptr_t>(bank) % 16 == 0 && bank_ld % 4 == 0 && dim >= 1 &&
-         topk_capacity(top_k) <= 128;
+  const int64_t align = bank_dtype == DEVQA_F32 ? 4 : 8;      // 16-byte rows for the tensor map
+  return reinterpret_cast<uintptr_t>(bank) % 16 == 0 && bank_ld % align == 0 && dim >= 1 && topk_capacity(top_k) <= 128;
 }
 
-int scan_tc_query_pad(int n_queries) { return (n_queries + 15) / 16 * 16; }
-int scan_tc_dim_pad(int64_t dim) { return int((dim + kBlockK - 1) / kBlockK * kBlockK); }
+// bank columns per 128-byte k-block row, and the padded k-block count
+static int elems_per_kblock(int bank_dtype) { return bank_dtype == DEVQA_F32 ? 32 : 64; }
+int scan_tc_kblocks(int bank_dtype, int64_t dim) { return int((dim + elems_per_kblock(bank_dtype) - 1) / elems_per_kblock(bank_dtype)); }
+// bytes of the prepared query operand for q_pad queries
+size_t scan_tc_qcat_bytes(int bank_dtype, int64_t dim, int q_pad) {
+  return size_t(q_pad) * scan_tc_kblocks(bank_dtype, dim) * 128 * (bank_dtype == DEVQA_F32 ? 2 : 3);
+}
 
-// Queries per pass + pipeline depth that fit in shared memory for this k.
-int scan_tc_plan(int n_queries, int64_t dim, int kcap, int* qp_out, int* stages_out) {
-  // D > 1024 sums K-sets in the epilogue's registers (MULTI): 32 queries per pass at most
-  int qp = scan_tc_dim_pad(dim) > kSetKBlocks * kBlockK ? 32 : 64;
-  while (qp > 16 && qp / 2 >= scan_tc_query_pad(n_queries)) qp >>= 1;
+// Queries per pass + pipeline depth that fit in shared memory / tensor memory for this k.
+int scan_tc_plan(int bank_dtype, int n_queries, int64_t dim, int kcap, int* qp_out, int* stages_out) {
+  const bool bf = bank_dtype != DEVQA_F32;
+  // more than one K-set (1024 fp32 / 2048 bf16 columns) sums K-sets in the epilogue's registers (MULTI):
+  // 32 queries per pass at most
+  int qp = scan_tc_kblocks(bank_dtype, dim) > kSetKBlocks ? 32 : 64;
+  const int q16 = (n_queries + 15) / 16 * 16;
+  while (qp > 16 && qp / 2 >= q16) qp >>= 1;
   for (; qp >= 16; qp >>= 1) {
     for (int stages = kMaxStages; stages >= 3; --stages) {
-      if (6 * qp + stages * kBlockK > 512) continue;        // TMEM: 2 accumulator buffers + one lo tile per stage
-      if (tc_layout(stages, qp, kcap).total + 1024 <= 225 * 1024) {
+      // TMEM: 2 accumulator buffers of 3*qp columns (+ one 32-column lo tile per stage for fp32 banks)
+      if (6 * qp + (bf ? 0 : stages * kBlockK) > 512) continue;
+      if (tc_layout(stages, qp, kcap, bf ? 3 : 2).total + 1024 <= 225 * 1024) {
         *qp_out = qp; *stages_out = stages;
         return DEVQA_OK;
       }
@@ -697,12 +795,17 @@ int scan_tc_plan(int n_queries, int64_t dim, int kcap, int* qp_out, int* stages_
   return DEVQA_E_UNSUPPORTED;
 }
 
-// qcat must hold q_pad * dim_pad * 2 floats; q_pad is a multiple of qp.
-int scan_tc_prep_queries(const float* queries, int64_t query_ld, int n_queries, int qp, int q_pad, int64_t dim,
-                         unsigned flags, float* qcat, uint32_t* gthr, cudaStream_t stream) {
-  const int n_kblocks = scan_tc_dim_pad(dim) / kBlockK;
+// qcat must hold scan_tc_qcat_bytes(); q_pad is a multiple of qp; gthr [q_pad] is zeroed here.
+int scan_tc_prep_queries(int bank_dtype, const float* queries, int64_t query_ld, int n_queries, int qp, int q_pad,
+                         int64_t dim, unsigned flags, void* qcat, uint32_t* gthr, cudaStream_t stream) {
+  const int n_kblocks = scan_tc_kblocks(bank_dtype, dim);
   const int grid = (q_pad + 7) / 8;
-  prep_queries_kernel<<<grid, 256, 0, stream>>>(queries, query_ld, n_queries, int(dim), qp, n_kblocks, q_pad, flags, qcat, gthr);
+  if (bank_dtype == DEVQA_F32)
+    prep_queries_kernel<<<grid, 256, 0, stream>>>(queries, query_ld, n_queries, int(dim), qp, n_kblocks, q_pad, flags,
+                                                  static_cast<float*>(qcat), gthr);
+  else
+    prep_queries_bf16_kernel<<<grid, 256, 0, stream>>>(queries, query_ld, n_queries, int(dim), qp, n_kblocks, q_pad, flags,
+                                                       static_cast<__nv_bfloat16*>(qcat), gthr);
   DEVQA_CUDA(cudaGetLastError());
   count_launch();
   return DEVQA_OK;
@@ -711,25 +814,33 @@ int scan_tc_prep_queries(const float* queries, int64_t query_ld, int n_queries, 
 static long long* g_tc_trace = nullptr;
 void scan_tc_set_trace(long long* buf) { g_tc_trace = buf; }
 
-int scan_tc_launch(const ScanParams& sp, const float* qcat, uint32_t* gthr, int qp, int stages, int passes,
+int scan_tc_launch(const ScanParams& sp, int bank_dtype, const void* qcat, uint32_t* gthr, int qp, int stages, int passes,
                    int ctas_per_pass, cudaStream_t stream) {
   const int grid = passes * ctas_per_pass;
-  const int d_pad = scan_tc_dim_pad(sp.dim);
+  const bool bf = bank_dtype != DEVQA_F32;
+  const int n_kblocks = scan_tc_kblocks(bank_dtype, sp.dim);
   CUtensorMap bank_map;
-  int rc = make_map(&bank_map, sp.bank, uint64_t(sp.dim), uint64_t(sp.n_rows), uint64_t(sp.bank_ld) * 4, kTileRows);
+  int rc = make_map(&bank_map, sp.bank, bf, uint64_t(sp.dim), uint64_t(sp.n_rows), uint64_t(sp.bank_ld) * (bf ? 2 : 4), kTileRows);
   if (rc) return rc;
   TcParams p{};
-  p.n_rows = sp.n_rows; p.dim = int(sp.dim); p.n_kblocks = d_pad / kBlockK;
+  p.n_rows = sp.n_rows; p.dim = int(sp.dim); p.n_kblocks = n_kblocks;
   p.n_tiles = int((sp.n_rows + kTileRows - 1) / kTileRows);
   p.qp = qp; p.nq_pass = sp.nq_pass; p.q0 = sp.q0; p.n_queries = sp.n_queries;
-  p.top_k = sp.top_k; p.kcap = sp.kcap; p.stages = stages; p.passes = passes; p.flags = sp.flags; p.cand = sp.cand; p.gthr = gthr; p.idmap = sp.idmap;
-  p.qcat = qcat + size_t(sp.q0 / qp) * size_t(d_pad) * 2 * qp;     // pass index = q0 / qp
+  p.top_k = sp.top_k; p.kcap = sp.kcap; p.stages = stages; p.passes = passes; p.flags = sp.flags;
+  p.cand = sp.cand; p.gthr = gthr; p.idmap = sp.idmap; p.row_sumsq = sp.row_sumsq;
+  // pass index = q0 / qp; one pass = n_kblocks * parts * qp rows of 128 bytes (32 words)
+  p.qcat = static_cast<const float*>(qcat) + size_t(sp.q0 / qp) * size_t(n_kblocks) * (bf ? 3 : 2) * qp * 32;
   p.trace = g_tc_trace;
-  const size_t smem = tc_layout(stages, qp, sp.kcap).total + 1024;
+  const size_t smem = tc_layout(stages, qp, sp.kcap, bf ? 3 : 2).total + 1024;
   const bool multi = p.n_kblocks > kSetKBlocks;
   void (*kern)(CUtensorMap, TcParams) = nullptr;
-  if (!multi) kern = qp == 64 ? scan_tc_kernel<64, false> : qp == 32 ? scan_tc_kernel<32, false> : scan_tc_kernel<16, false>;
-  else kern = qp == 32 ? scan_tc_kernel<32, true> : scan_tc_kernel<16, true>;
+  if (!bf) {
+    if (!multi) kern = qp == 64 ? scan_tc_kernel<64, false, false> : qp == 32 ? scan_tc_kernel<32, false, false> : scan_tc_kernel<16, false, false>;
+    else kern = qp == 32 ? scan_tc_kernel<32, true, false> : scan_tc_kernel<16, true, false>;
+  } else {
+    if (!multi) kern = qp == 64 ? scan_tc_kernel<64, false, true> : qp == 32 ? scan_tc_kernel<32, false, true> : scan_tc_kernel<16, false, true>;
+    else kern = qp == 32 ? scan_tc_kernel<32, true, true> : scan_tc_kernel<16, true, true>;
+  }
   if (qp != 16 && qp != 32 && !(qp == 64 && !multi)) {
     set_error("tcgen05 scan: unsupported queries-per-pass %d", qp);
     return DEVQA_E_INVALID;

@@ -102,7 +102,43 @@ def test_tc_is_deterministic_and_batch_independent():
 
 
 def test_tc_unsupported_configs_fail_loudly():
-    fb16 = FactBank.from_embeddings(_randn(100, 64, 1), dtype="bf16")
+    fb = FactBank.from_embeddings(_randn(100, 64, 1))
     with pytest.raises(L.DevqaError):
-        fb16.search(_randn(2, 64, 2).cuda(), 4, flags=L.FORCE_TENSOR)
-    fb16.close()
+        fb.search(_randn(2, 64, 2).cuda(), 200, flags=L.FORCE_TENSOR)      # top_k capacity > 128
+    fb.close()
+
+
+# ---- bf16-bank variant (kind::f16, queries split three ways) -------------------------------------------
+def _check_tc_bf16(bank_cpu, q_cpu, k, nb="eps", nq="eps"):
+    """The bf16 path is exact with respect to the bf16-ROUNDED bank (recall vs the fp32 bank is reported
+    separately, tests/test_gpu_parity.py)."""
+    fb = FactBank.from_embeddings(bank_cpu, dtype="bf16")
+    rounded = bank_cpu.to(torch.bfloat16).float()
+    s, i = fb.search(q_cpu.cuda(), k, normalize_bank=nb, normalize_query=nq, flags=L.FORCE_TENSOR)
+    kk = min(k, len(bank_cpu))
+    truth = ss.truth_scores_fp64(q_cpu, rounded, normalize_bank=bool(nb), normalize_query=bool(nq))
+    ss.compare_topk(s.cpu().numpy()[:, :kk], i.cpu().numpy()[:, :kk], truth, k, gap=GAP, rtol=RTOL, atol=ATOL)
+    s2, i2 = fb.search(q_cpu.cuda(), k, normalize_bank=nb, normalize_query=nq, flags=L.FORCE_STREAM)
+    ss.compare_topk(s2.cpu().numpy()[:, :kk], i2.cpu().numpy()[:, :kk], truth, k, gap=GAP, rtol=RTOL, atol=ATOL)
+    fb.close()
+
+
+@pytest.mark.parametrize("n,d,nq,k", [(128, 64, 16, 4), (1, 8, 3, 2), (129, 72, 9, 8), (4097, 768, 33, 32),
+                                       (3000, 4096, 40, 16), (5000, 384, 100, 16), (2000, 200, 17, 128)])
+def test_tc_bf16_bank(n, d, nq, k):
+    _check_tc_bf16(_randn(n, d, n + d, unit=False), _randn(nq, d, nq + k, unit=False), k)
+
+
+def test_tc_bf16_hidden_states_and_variants():
+    bank, q = _hidden_like(8174, 4096, 2234), _hidden_like(64, 4096, 6678)
+    _check_tc_bf16(bank, q, 16)
+    _check_tc_bf16(bank[:1000, :512].contiguous(), q[:, :512].contiguous(), 16, nb=None, nq=None)
+
+
+def test_tc_bf16_is_the_default_for_batches():
+    bank, q = _randn(50_000, 768, 5), _randn(64, 768, 6)
+    fb = FactBank.from_embeddings(bank, dtype="bf16")
+    a = fb.search(q.cuda(), 32)
+    b = fb.search(q.cuda(), 32, flags=L.FORCE_TENSOR)
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+    fb.close()
