@@ -8,11 +8,13 @@ The package holds only what that path needs:
   util.py               drop-in for the slice of sentence_transformers.util the reference calls
   retrieval.py          host-side mirror of the reference's retrieval glue (finds_sim, IKE/HICE lookups)
   dist.py               row-sharded bank over the GPUs of one box (one all-gather + fused merge)
+  pools.py              appended-pool top-1 / thresholded retrieval of the lifelong editors (LTE, SERAC, RECIPE)
 """
 from . import _lib
 from .bank import FactBank, hits_from_arrays, norm_flags, topk_merge
 from . import util
 from . import retrieval
 from . import dist
+from .pools import EditPool
 
-__all__ = ["FactBank", "util", "retrieval", "dist", "hits_from_arrays", "norm_flags", "topk_merge", "_lib"]
+__all__ = ["FactBank", "EditPool", "util", "retrieval", "dist", "hits_from_arrays", "norm_flags", "topk_merge", "_lib"]
