@@ -13,7 +13,8 @@ E_INVALID, E_CUDA, E_NOMEM, E_UNSUPPORTED, E_NCCL, E_STATE = -1, -2, -3, -4, -5,
 MAX_TOPK = 1024
 F32, BF16 = 0, 1
 NORMALIZE_BANK, NORMALIZE_QUERY, NOEPS = 1 << 0, 1 << 1, 1 << 2
-FORCE_STREAM, FORCE_TENSOR = 1 << 8, 1 << 9
+FORCE_STREAM, FORCE_TENSOR, FORCE_TF32X3 = 1 << 8, 1 << 9, 1 << 10
+DEBUG_FILTER_ONLY = 1 << 22
 
 _p, _i, _i64, _u, _u64 = C.c_void_p, C.c_int, C.c_int64, C.c_uint, C.c_uint64
 
@@ -23,6 +24,7 @@ SIGNATURES = {
     "devqa_last_error": (C.c_char_p, []),
     "devqa_launch_count": (_i64, []),
     "devqa_debug_tc_trace": (_i, [_p]),
+    "devqa_filter_fallbacks": (_i, [_i, C.POINTER(_i64)]),
     "devqa_profile_enable": (_i, [_i, _i]),
     "devqa_profile_collect": (_i, [_i, C.POINTER(C.c_double), C.POINTER(_i64), C.POINTER(_i64)]),
     "devqa_search_raw": (_i, [_p, _i, _i64, _i64, _i64, _p, _i64, _i64, _i, _u, _i64, _p, _p, _p]),

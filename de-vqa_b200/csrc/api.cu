@@ -38,6 +38,8 @@ struct Scratch {
   uint64_t* gathered = nullptr; size_t gathered_bytes = 0; // all-gather target (dist)
   void* tiny = nullptr;       size_t tiny_bytes = 0;       // padded copy of banks shorter than one row group
   float* qsplit = nullptr;    size_t qsplit_bytes = 0;     // TF32 hi / lo query planes of the tcgen05 scan
+  uint64_t* akeys = nullptr;  size_t akeys_bytes = 0;      // filter scan: merged approximate top-K' lists + per-query side arrays
+  uint32_t* fallbacks = nullptr;                           // device counter: queries the exact fallback had to redo
   cudaStream_t last_stream = nullptr;
   cudaEvent_t done = nullptr;
   // optional per-kernel timing (devqa_profile_*): event pairs around the scan passes of each search
@@ -46,8 +48,15 @@ struct Scratch {
   cudaEvent_t* prof_ev = nullptr;     // [2 * kProfSlots]
   int prof_used = 0;
   int64_t prof_scan_launches = 0;
+  int64_t prof_searches = 0;
 };
 static Scratch g_scratch[64];
+
+struct DeviceGuardLite {
+  int prev = -1;
+  explicit DeviceGuardLite(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); }
+  ~DeviceGuardLite() { if (prev >= 0) cudaSetDevice(prev); }
+};
 
 static int grow(void** p, size_t* have, size_t want, bool pinned) {
   if (*have >= want) return DEVQA_OK;
@@ -79,6 +88,11 @@ static int scratch_for(int device, Scratch** out) {
       return DEVQA_E_UNSUPPORTED;
     }
     DEVQA_CUDA(cudaEventCreateWithFlags(&s->done, cudaEventDisableTiming));
+    {
+      DeviceGuardLite guard(device);
+      DEVQA_CUDA(cudaMalloc(&s->fallbacks, 4));
+      DEVQA_CUDA(cudaMemset(s->fallbacks, 0, 4));
+    }
     s->sm_count = n;
   }
   *out = s;
@@ -104,6 +118,7 @@ struct SearchArgs {
   const float* queries; int64_t n_queries, query_ld;
   int top_k; unsigned flags; IdMap idmap;
   const float* row_sumsq = nullptr;
+  const uint32_t* max_sumsq = nullptr;   // library-owned banks: max ||row||^2 over every row ever appended (float bits)
 };
 
 static int validate(const SearchArgs& a) {
@@ -121,6 +136,98 @@ static int validate(const SearchArgs& a) {
   DEVQA_REQUIRE(a.idmap.base + a.n_rows * (a.idmap.chunk > 0 ? a.idmap.world : 1) <= 0xffffffffll,
                 "corpus ids beyond 2^32 are not supported");
   return DEVQA_OK;
+}
+
+// Side arrays of the filter scan (device), carved out of Scratch::akeys.
+struct FilterSide {
+  uint64_t* akeys = nullptr;     // [Q, K'] merged candidates (keys on the upper bound u)
+  uint32_t* need = nullptr;      // [Q] set by refine: the exact fallback has to redo this query
+  float* qinv = nullptr;         // [Q] scale applied by the query normalisation
+  float* qerr = nullptr;         // [Q] tc_filter_relerr(dim) * ||query as used||
+  uint32_t* seed_u = nullptr;    // [Q padded] k-th best upper bound of the prefix sample (score codes)
+  uint32_t* lostu = nullptr;     // [grid, Q] per-CTA bound on the rows its full list lost
+  int kp = 0;                    // K': capacity of the merged candidate list
+  int n_lists = 0;               // out: per-CTA lists per query
+};
+
+// One tcgen05 scan pipeline over all of a's queries: prepare the query operand, (seed thresholds on a prefix
+// sample,) scan every pass, merge the per-CTA lists.  side != nullptr: filter mode -- the per-CTA lists keep
+// kcap(top_k) candidates by upper bound, the merge keeps side->kp of them in side->akeys.  need != nullptr:
+// conditional run -- only flagged queries are recomputed and written.  Otherwise exactly one of out_keys /
+// (out_scores, out_ids): [Q, top_k].
+static int tc_pipeline(Scratch* s, const SearchArgs& a, int mode, FilterSide* side, const uint32_t* need,
+                       uint64_t* out_keys, float* out_scores, int64_t* out_ids, cudaStream_t stream) {
+  int rc;
+  const int kcap = topk_capacity(a.top_k);
+  const int list_k = side ? kcap : a.top_k;                 // entries a list keeps
+  const bool cached_norms = a.row_sumsq != nullptr;
+  int qp = 0, stages = 0;
+  if ((rc = scan_tc_plan(mode, int(a.n_queries), a.dim, kcap, cached_norms, &qp, &stages))) return rc;
+  const int q_pad = int((a.n_queries + qp - 1) / qp) * qp;
+  const size_t qcat_bytes = scan_tc_qcat_bytes(mode, a.dim, q_pad);
+  if ((rc = grow(reinterpret_cast<void**>(&s->qsplit), &s->qsplit_bytes, qcat_bytes + size_t(q_pad) * 4, false))) return rc;
+  uint32_t* gthr = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(s->qsplit) + qcat_bytes);   // shared per-query thresholds
+  const int64_t tiles = (a.n_rows + 127) / 128;
+  // Large banks: one pass per launch on every SM.  Small banks: several passes side by side so that
+  // tiles x passes still covers the SMs.
+  const int n_passes = q_pad / qp;
+  const int tiles_cap = int(tiles < s->sm_count ? tiles : s->sm_count);
+  int side_by = 1;
+  if (tiles < s->sm_count) side_by = n_passes < s->sm_count ? n_passes : s->sm_count;
+  int ctas_per_pass = s->sm_count / side_by;
+  if (ctas_per_pass > tiles_cap) ctas_per_pass = tiles_cap;
+  if (ctas_per_pass < 1) ctas_per_pass = 1;
+  const int grid = ctas_per_pass;                           // candidate lists per query
+  if ((rc = grow(reinterpret_cast<void**>(&s->cand), &s->cand_bytes, size_t(grid) * a.n_queries * kcap * 8, false))) return rc;
+
+  ScanParams p{};
+  p.n_rows = a.n_rows; p.dim = a.dim; p.bank_ld = a.bank_ld; p.bank = a.bank;
+  p.queries = a.queries; p.query_ld = a.query_ld; p.n_queries = int32_t(a.n_queries);
+  p.top_k = list_k; p.kcap = kcap; p.flags = a.flags; p.idmap = a.idmap; p.row_sumsq = a.row_sumsq;
+  p.cand = s->cand; p.need = need;
+  if (side) {
+    p.qerr = side->qerr; p.k_true = a.top_k; p.lostu = side->lostu; p.bank_max_sumsq = a.max_sumsq;
+    side->n_lists = grid;
+  }
+
+  const bool prof = s->profiling && !need && s->prof_used < Scratch::kProfSlots;
+  if (prof) DEVQA_CUDA(cudaEventRecord(s->prof_ev[2 * s->prof_used], stream));
+  if ((rc = scan_tc_prep_queries(mode, a.queries, a.query_ld, int(a.n_queries), qp, q_pad, a.dim, a.flags, s->qsplit, gthr,
+                                 side ? side->qinv : nullptr, side ? side->qerr : nullptr, side ? side->seed_u : nullptr, stream)))
+    return rc;
+  // Threshold seeding: scan a prefix sample of the bank (one tile per CTA) first; the k-th best score of a
+  // SUBSET is a lower bound of the k-th best of the whole bank, so the main scan starts with tight
+  // thresholds in every CTA instead of each CTA re-learning them (k ln(n/k) list insertions each).
+  const bool seed = tiles >= 8 * int64_t(ctas_per_pass) && !(a.flags & (1u << 21)) && !need;
+  if (seed) {
+    ScanParams pre = p;
+    pre.n_rows = int64_t(ctas_per_pass) * 128;
+    for (int pass = 0; pass < n_passes; pass += side_by) {
+      const int now = n_passes - pass < side_by ? n_passes - pass : side_by;
+      pre.q0 = int32_t(pass * qp);
+      pre.nq_pass = qp;
+      if ((rc = scan_tc_launch(pre, mode, s->qsplit, gthr, qp, stages, now, ctas_per_pass, stream))) return rc;
+    }
+    // exact modes: the sample's k-th best score IS a threshold; filter: its k-th best upper bound, from which the
+    // kernel derives one (minus 2E)
+    if ((rc = merge_lists_launch(s->cand, grid, a.n_queries, kcap, kcap, a.top_k, nullptr, nullptr, nullptr, stream,
+                                 side ? side->seed_u : gthr)))
+      return rc;
+    if (side) p.seed_u = side->seed_u;
+  }
+  for (int pass = 0; pass < n_passes; pass += side_by) {
+    const int now = n_passes - pass < side_by ? n_passes - pass : side_by;
+    p.q0 = int32_t(pass * qp);
+    p.nq_pass = qp;
+    if ((rc = scan_tc_launch(p, mode, s->qsplit, gthr, qp, stages, now, ctas_per_pass, stream))) return rc;
+    if (prof) s->prof_scan_launches++;
+  }
+  if (prof) {
+    DEVQA_CUDA(cudaEventRecord(s->prof_ev[2 * s->prof_used + 1], stream));
+    s->prof_used++;
+  }
+  if (side) return merge_lists_launch(s->cand, grid, a.n_queries, kcap, kcap, side->kp, side->akeys, nullptr, nullptr, stream);
+  return merge_lists_launch(s->cand, grid, a.n_queries, kcap, kcap, a.top_k, out_keys, out_scores, out_ids, stream, nullptr, need);
 }
 
 // Exactly one of out_keys / (out_scores,out_ids).
@@ -156,57 +263,55 @@ static int run_search(Scratch* s, const SearchArgs& a, uint64_t* out_keys, float
   int grid = 1;
 
   if (use_tc) {
-    int qp = 0, stages = 0;
-    if ((rc = scan_tc_plan(a.dtype, int(a.n_queries), a.dim, kcap, &qp, &stages))) return rc;
-    const int q_pad = int((a.n_queries + qp - 1) / qp) * qp;
-    const size_t qcat_bytes = scan_tc_qcat_bytes(a.dtype, a.dim, q_pad);
-    if ((rc = grow(reinterpret_cast<void**>(&s->qsplit), &s->qsplit_bytes, qcat_bytes + size_t(q_pad) * 4, false))) return rc;
-    uint32_t* gthr = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(s->qsplit) + qcat_bytes);   // shared per-query thresholds
-    const int64_t tiles = (a.n_rows + 127) / 128;
-    // Large banks: one pass per launch on every SM.  Small banks: several passes side by side so that
-    // tiles x passes still covers the SMs.
-    const int n_passes = q_pad / qp;
-    const int tiles_cap = int(tiles < s->sm_count ? tiles : s->sm_count);
-    int side = 1;
-    if (tiles < s->sm_count) side = n_passes < s->sm_count ? n_passes : s->sm_count;
-    int ctas_per_pass = s->sm_count / side;
-    if (ctas_per_pass > tiles_cap) ctas_per_pass = tiles_cap;
-    if (ctas_per_pass < 1) ctas_per_pass = 1;
-    grid = ctas_per_pass;                                   // candidate lists per query
-    if ((rc = grow(reinterpret_cast<void**>(&s->cand), &s->cand_bytes, size_t(grid) * a.n_queries * kcap * 8, false))) return rc;
-    p.bank = a.bank; p.cand = s->cand;
-    const bool prof = s->profiling && s->prof_used < Scratch::kProfSlots;
-    if (prof) DEVQA_CUDA(cudaEventRecord(s->prof_ev[2 * s->prof_used], stream));
-    if ((rc = scan_tc_prep_queries(a.dtype, a.queries, a.query_ld, int(a.n_queries), qp, q_pad, a.dim, a.flags, s->qsplit, gthr, stream)))
-      return rc;
-    // Threshold seeding: scan a prefix sample of the bank (one tile per CTA) first; the k-th best score of a
-    // SUBSET is a lower bound of the k-th best of the whole bank, so the main scan starts with tight
-    // thresholds in every CTA instead of each CTA re-learning them (k ln(n/k) list insertions each).
-    const bool seed = tiles >= 8 * int64_t(ctas_per_pass) && !(a.flags & (1u << 21));
-    if (seed) {
-      ScanParams pre = p;
-      pre.n_rows = int64_t(ctas_per_pass) * 128;
-      for (int pass = 0; pass < n_passes; pass += side) {
-        const int now = n_passes - pass < side ? n_passes - pass : side;
-        pre.q0 = int32_t(pass * qp);
-        pre.nq_pass = qp;
-        if ((rc = scan_tc_launch(pre, a.dtype, s->qsplit, gthr, qp, stages, now, ctas_per_pass, stream))) return rc;
+    // fp32 banks: the TF32 filter scan + exact re-scoring (refine.cu) + conditional exact fallback; the 3xTF32
+    // scan alone on request, for top_k > 64 (no room for the filter's surplus candidates) and for un-normalised
+    // scores over a caller-owned bank (the error bound needs max ||row||, which only library-owned banks cache).
+    const int kp = a.top_k <= 8 ? 32 : (a.top_k <= 16 ? 64 : 128);     // K': candidates kept per query after the merge
+    const bool filt = a.dtype == DEVQA_F32 && !(a.flags & DEVQA_FORCE_TF32X3) && a.top_k <= 64 && a.dim <= 16384 &&
+                      ((a.flags & DEVQA_NORMALIZE_BANK) || (a.row_sumsq && a.max_sumsq));
+    if (s->profiling) s->prof_searches++;
+    constexpr int64_t kChunkQ = 1024;                                  // bounds the candidate scratch (grid x Q x kcap keys)
+    for (int64_t c0 = 0; c0 < a.n_queries; c0 += kChunkQ) {
+      SearchArgs ac = a;
+      ac.queries = a.queries + c0 * a.query_ld;
+      ac.n_queries = a.n_queries - c0 < kChunkQ ? a.n_queries - c0 : kChunkQ;
+      uint64_t* ok = out_keys ? out_keys + c0 * a.top_k : nullptr;
+      float* os = out_scores ? out_scores + c0 * a.top_k : nullptr;
+      int64_t* oi = out_ids ? out_ids + c0 * a.top_k : nullptr;
+      if (!filt) {
+        if ((rc = tc_pipeline(s, ac, a.dtype == DEVQA_F32 ? kTcTf32x3 : kTcBf16x3, nullptr, nullptr, ok, os, oi, stream)))
+          return rc;
+        continue;
       }
-      if ((rc = merge_lists_launch(s->cand, grid, a.n_queries, kcap, kcap, a.top_k, nullptr, nullptr, nullptr, stream, gthr)))
+      const size_t nq = size_t(ac.n_queries), nq_pad = (nq + 127) / 128 * 128;
+      if ((rc = grow(reinterpret_cast<void**>(&s->akeys), &s->akeys_bytes,
+                     nq * kp * 8 + nq * 12 + nq_pad * 4 + size_t(s->sm_count) * nq * 4, false)))
         return rc;
+      FilterSide side;
+      side.kp = kp;
+      side.akeys = s->akeys;
+      side.need = reinterpret_cast<uint32_t*>(s->akeys + nq * kp);
+      side.qinv = reinterpret_cast<float*>(side.need + nq);
+      side.qerr = side.qinv + nq;
+      side.seed_u = reinterpret_cast<uint32_t*>(side.qerr + nq);
+      side.lostu = side.seed_u + nq_pad;
+      if ((rc = tc_pipeline(s, ac, kTcTf32x1, &side, nullptr, nullptr, nullptr, nullptr, stream))) return rc;
+      if (a.flags & DEVQA_DEBUG_FILTER_ONLY) {                           // tests: the filter's own upper bounds
+        if ((rc = merge_lists_launch(side.akeys, 1, ac.n_queries, kp, kp, a.top_k, ok, os, oi, stream))) return rc;
+        continue;
+      }
+      RefineParams rp{};
+      rp.bank = static_cast<const float*>(a.bank); rp.n_rows = a.n_rows; rp.dim = a.dim; rp.bank_ld = a.bank_ld;
+      rp.queries = ac.queries; rp.query_ld = a.query_ld; rp.n_queries = int32_t(ac.n_queries);
+      rp.qinv = side.qinv; rp.akeys = side.akeys; rp.lostu = side.lostu; rp.n_lists = side.n_lists;
+      rp.kp = kp; rp.top_k = a.top_k; rp.flags = a.flags; rp.idmap = a.idmap;
+      rp.need = side.need; rp.fallbacks = s->fallbacks; rp.out_keys = ok; rp.out_scores = os; rp.out_ids = oi;
+      if ((rc = refine_launch(rp, stream))) return rc;
+      // queries for which a lost row could still matter are redone exactly; for all others these launches
+      // exit at once (the flags live on the device: no host round trip, graph-capturable)
+      if ((rc = tc_pipeline(s, ac, kTcTf32x3, nullptr, side.need, ok, os, oi, stream))) return rc;
     }
-    for (int pass = 0; pass < n_passes; pass += side) {
-      const int now = n_passes - pass < side ? n_passes - pass : side;
-      p.q0 = int32_t(pass * qp);
-      p.nq_pass = qp;
-      if ((rc = scan_tc_launch(p, a.dtype, s->qsplit, gthr, qp, stages, now, ctas_per_pass, stream))) return rc;
-      if (prof) s->prof_scan_launches++;
-    }
-    if (prof) {
-      DEVQA_CUDA(cudaEventRecord(s->prof_ev[2 * s->prof_used + 1], stream));
-      s->prof_used++;
-    }
-    return merge_lists_launch(s->cand, grid, a.n_queries, kcap, kcap, a.top_k, out_keys, out_scores, out_ids, stream);
+    return DEVQA_OK;
   }
 
   // widest query tile whose shared-memory footprint fits
@@ -237,6 +342,7 @@ static int run_search(Scratch* s, const SearchArgs& a, uint64_t* out_keys, float
   }
   p.bank = bank_ptr; p.cand = s->cand;
   const bool prof = s->profiling && s->prof_used < Scratch::kProfSlots;
+  if (s->profiling) s->prof_searches++;
   if (prof) DEVQA_CUDA(cudaEventRecord(s->prof_ev[2 * s->prof_used], stream));
   for (int64_t q0 = 0; q0 < a.n_queries; q0 += qt) {
     p.q0 = int32_t(q0);
@@ -262,6 +368,7 @@ struct devqa_bank {
   int64_t size = 0, capacity = 0;
   void* data = nullptr;
   float* sumsq = nullptr;          // cached ||row||^2 per stored row (bf16 banks: of the rounded row)
+  uint32_t* max_sumsq = nullptr;   // device word: max of those over every row ever appended (float bits; never shrinks)
   devqa::IdMap idmap{0, 0, 0, 1};
   size_t esz() const { return dtype == DEVQA_F32 ? 4 : 2; }
 };
@@ -323,6 +430,7 @@ static SearchArgs bank_args(const devqa_bank* b, const float* q, int64_t nq, int
   a.bank = b->data; a.dtype = b->dtype; a.n_rows = b->size; a.dim = b->dim; a.bank_ld = b->ld;
   a.queries = q; a.n_queries = nq; a.query_ld = qld; a.top_k = k; a.flags = flags; a.idmap = b->idmap;
   a.row_sumsq = b->sumsq;
+  a.max_sumsq = b->max_sumsq;
   return a;
 }
 
@@ -373,6 +481,21 @@ int devqa_debug_tc_trace(int64_t* device_buf_16x256) {
   return DEVQA_OK;
 }
 
+int devqa_filter_fallbacks(int device, int64_t* count) {
+  DEVQA_REQUIRE(count != nullptr, "count is null");
+  Scratch* s = nullptr;
+  int rc = scratch_for(device, &s);
+  if (rc) return rc;
+  DEVQA_ON_DEVICE(device);
+  std::lock_guard<std::mutex> lock(s->mu);
+  uint32_t v = 0;
+  DEVQA_CUDA(cudaDeviceSynchronize());
+  DEVQA_CUDA(cudaMemcpy(&v, s->fallbacks, 4, cudaMemcpyDeviceToHost));
+  DEVQA_CUDA(cudaMemset(s->fallbacks, 0, 4));
+  *count = v;
+  return DEVQA_OK;
+}
+
 int devqa_profile_enable(int device, int enable) {
   Scratch* s = nullptr;
   int rc = scratch_for(device, &s);
@@ -387,6 +510,7 @@ int devqa_profile_enable(int device, int enable) {
   s->profiling = enable != 0;
   s->prof_used = 0;
   s->prof_scan_launches = 0;
+  s->prof_searches = 0;
   return DEVQA_OK;
 }
 
@@ -406,9 +530,10 @@ int devqa_profile_collect(int device, double* scan_ms_total, int64_t* scan_launc
   }
   *scan_ms_total = total;
   *scan_launches = s->prof_scan_launches;
-  *searches = s->prof_used;
+  *searches = s->prof_searches;
   s->prof_used = 0;
   s->prof_scan_launches = 0;
+  s->prof_searches = 0;
   return DEVQA_OK;
 }
 
@@ -453,7 +578,12 @@ int devqa_bank_create(devqa_bank** out, int device, int64_t dim, int64_t capacit
   b->device = device; b->dtype = dtype; b->dim = dim;
   const int64_t align = dtype == DEVQA_F32 ? 4 : 8;          // rows stay 16-byte aligned
   b->ld = (dim + align - 1) / align * align;
-  if (capacity_rows > 0 && (rc = bank_grow(b, capacity_rows, nullptr))) { delete b; return rc; }
+  if (cudaMalloc(&b->max_sumsq, 4) != cudaSuccess || cudaMemset(b->max_sumsq, 0, 4) != cudaSuccess) {
+    set_error("cudaMalloc for the bank header failed");
+    delete b;
+    return DEVQA_E_NOMEM;
+  }
+  if (capacity_rows > 0 && (rc = bank_grow(b, capacity_rows, nullptr))) { cudaFree(b->max_sumsq); delete b; return rc; }
   *out = b;
   return DEVQA_OK;
 }
@@ -462,6 +592,7 @@ int devqa_bank_destroy(devqa_bank* b) {
   if (!b) return DEVQA_OK;
   DEVQA_ON_DEVICE(b->device);
   if (b->data) { cudaDeviceSynchronize(); cudaFree(b->data); cudaFree(b->sumsq); }
+  if (b->max_sumsq) cudaFree(b->max_sumsq);
   delete b;
   return DEVQA_OK;
 }
@@ -513,7 +644,7 @@ int devqa_bank_append(devqa_bank* b, const float* rows, int64_t n, int64_t ld, i
       if ((rc = convert_rows_launch(rows, ld, dst, b->dtype, b->ld, n, b->dim, stream))) return rc;
     }
   }
-  if ((rc = row_sumsq_launch(dst, b->dtype, n, b->dim, b->ld, b->sumsq + b->size, stream))) return rc;
+  if ((rc = row_sumsq_launch(dst, b->dtype, n, b->dim, b->ld, b->sumsq + b->size, stream, b->max_sumsq))) return rc;
   b->size += n;
   return DEVQA_OK;
 }
@@ -728,7 +859,7 @@ int devqa_bank_append_synthetic(devqa_bank* b, int64_t n_rows, uint64_t seed, in
   if (rc) return rc;
   char* dst = static_cast<char*>(b->data) + size_t(b->size) * b->ld * b->esz();
   if ((rc = fill_synthetic_launch(dst, b->dtype, n_rows, b->dim, b->ld, seed, first_global_row, kind, stream))) return rc;
-  if ((rc = row_sumsq_launch(dst, b->dtype, n_rows, b->dim, b->ld, b->sumsq + b->size, stream))) return rc;
+  if ((rc = row_sumsq_launch(dst, b->dtype, n_rows, b->dim, b->ld, b->sumsq + b->size, stream, b->max_sumsq))) return rc;
   b->size += n_rows;
   return DEVQA_OK;
 }

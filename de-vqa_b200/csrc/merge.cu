@@ -39,10 +39,12 @@ __device__ __forceinline__ void emit(uint64_t key, int e, int top_k, int64_t q, 
 __global__ void __launch_bounds__(kMergeThreads) merge32_kernel(const uint64_t* __restrict__ lists, int n_lists,
                                                                int64_t n_queries, int list_stride, int list_len,
                                                                int top_k, uint64_t* out_keys, float* out_scores,
-                                                               int64_t* out_ids, uint32_t* kth_codes) {
+                                                               int64_t* out_ids, uint32_t* kth_codes,
+                                                               const uint32_t* __restrict__ need) {
   __shared__ uint64_t sacc[kMergeWarps][32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t q = blockIdx.x;
+  if (need && need[q] == 0u) return;
   uint64_t acc = kEmptyKey;
   const int rev = 31 - lane;
   for (int l = warp; l < n_lists; l += kMergeWarps) {
@@ -69,8 +71,10 @@ __global__ void __launch_bounds__(kMergeThreads) merge_generic_kernel(const uint
                                                                      int list_stride, int list_len, int kcap,
                                                                      int top_k, uint64_t* out_keys,
                                                                      float* out_scores, int64_t* out_ids,
-                                                                     uint32_t* kth_codes) {
+                                                                     uint32_t* kth_codes,
+                                                                     const uint32_t* __restrict__ need) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  if (need && need[blockIdx.x] == 0u) return;
   const int nwarps = blockDim.x >> 5;
   uint64_t* acc = reinterpret_cast<uint64_t*>(smem_raw);       // [warps][kcap]
   uint64_t* inc = acc + size_t(nwarps) * kcap;                  // [warps][kcap]
@@ -100,19 +104,19 @@ __global__ void __launch_bounds__(kMergeThreads) merge_generic_kernel(const uint
 
 int merge_lists_launch(const uint64_t* lists, int n_lists, int64_t n_queries, int list_stride,
                        int list_len, int top_k, uint64_t* out_keys, float* out_scores, int64_t* out_ids,
-                       cudaStream_t stream, uint32_t* kth_codes) {
+                       cudaStream_t stream, uint32_t* kth_codes, const uint32_t* need) {
   if (n_queries == 0) return DEVQA_OK;
   const int kcap = topk_capacity(top_k > list_len ? top_k : list_len);
   if (kcap == 32) {
     merge32_kernel<<<unsigned(n_queries), kMergeThreads, 0, stream>>>(lists, n_lists, n_queries, list_stride,
                                                                       list_len, top_k, out_keys, out_scores,
-                                                                      out_ids, kth_codes);
+                                                                      out_ids, kth_codes, need);
   } else {
     const int threads = kcap <= 512 ? kMergeThreads : kMergeThreads / 2;   // keep smem <= 128 KB
     const size_t smem = size_t(2) * (threads / 32) * kcap * 8;
     DEVQA_CUDA(cudaFuncSetAttribute(merge_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
     merge_generic_kernel<<<unsigned(n_queries), threads, smem, stream>>>(
-        lists, n_lists, n_queries, list_stride, list_len, kcap, top_k, out_keys, out_scores, out_ids, kth_codes);
+        lists, n_lists, n_queries, list_stride, list_len, kcap, top_k, out_keys, out_scores, out_ids, kth_codes, need);
   }
   DEVQA_CUDA(cudaGetLastError());
   count_launch();

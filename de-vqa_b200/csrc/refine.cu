@@ -1,0 +1,196 @@
+// Exact re-scoring of the tensor-core filter's candidates (scan_tc.cu, kTf32x1).
+//
+// The filter scan computes, per (row, query), an approximate score s~ (one TF32 product: bank words truncated
+// to 10 mantissa bits, queries rounded to TF32) and works on the upper bound  u = s~ + E >= s,
+// E = tc_filter_relerr(dim) * ||row|| * ||query||  (Cauchy-Schwarz on the per-element rounding errors).
+// What reaches this kernel, per query: the merged list of the K' candidates with the largest u, and the
+// per-CTA lists it was merged from.  Three facts make the result exact:
+//   * a row the scan dropped against a shared threshold had u < T <= exact k-th best score (T = some
+//     list's k-th best u minus 2E: those k rows all have s >= u - 2E);
+//   * a row that a FULL list pushed out or turned away has s <= u <= that list's last entry at the time; the
+//     scan records the largest such bound per (CTA, query) (lostu), and the merged list's last entry bounds
+//     what the merge dropped;
+//   * a candidate that is not re-scored here has u < the k-th best exact score found so far.
+// So after re-scoring, with s*_k = the k-th best exact score among the candidates: if every such bound
+// is < s*_k, no lost row can enter the top-k and the answer is exact.  Otherwise (heavily duplicated or
+// clustered rows, NaN) need[q] is raised and api.cu redoes the query with the fp32-exact 3xTF32 scan.
+// Similarity scores still never round-trip through HBM; only K' keys per query do.
+//
+// The exact score is computed the way scan_stream.cu computes it -- lane l owns columns 128c + 4l .. + 3 of
+// chunk c (32c + l for unaligned dims), sequential FMAs over chunks, xor-butterfly 16, 8, 4, 2, 1 across lanes,
+// then * 1/max(||row||, eps) with ||row||^2 accumulated in the same order -- so both kernels return
+// bit-identical scores and the kernel choice is invisible in results.
+//
+// One CTA per query: 8 warps re-score the candidates, then the CTA bitonic-sorts the exact keys.
+#include "scan.cuh"
+#include "topk.cuh"
+
+namespace devqa {
+namespace {
+
+constexpr int kRefineThreads = 256;
+constexpr int kMaxKp = 128;
+
+template <bool VEC>
+__device__ __forceinline__ float exact_score(const float* __restrict__ row, const float* sq, int dim, unsigned flags, int lane) {
+  constexpr int NV = VEC ? 4 : 1;
+  constexpr int CH = 32 * NV;
+  const int nchunks = (dim + CH - 1) / CH;
+  const bool norm = (flags & DEVQA_NORMALIZE_BANK) != 0;
+  float acc = 0.f, nr = 0.f;
+  for (int c = 0; c < nchunks; ++c) {
+    const int col = c * CH + lane * NV;
+    float b[NV], qv[NV];
+    if constexpr (VEC) {
+      float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (col < dim) t = __ldg(reinterpret_cast<const float4*>(row + col));
+      b[0] = t.x; b[1] = t.y; b[2] = t.z; b[3] = t.w;
+      const float4 u = *reinterpret_cast<const float4*>(sq + col);
+      qv[0] = u.x; qv[1] = u.y; qv[2] = u.z; qv[3] = u.w;
+    } else {
+      b[0] = col < dim ? __ldg(row + col) : 0.f;
+      qv[0] = sq[col];
+    }
+#pragma unroll
+    for (int e = 0; e < NV; ++e) acc = fmaf(b[e], qv[e], acc);
+    if (norm) {
+#pragma unroll
+      for (int e = 0; e < NV; ++e) nr = fmaf(b[e], b[e], nr);
+    }
+  }
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) acc = acc + __shfl_xor_sync(kFull, acc, off);
+  if (norm) {
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) nr = nr + __shfl_xor_sync(kFull, nr, off);
+    const float nrm = sqrtf(nr);
+    acc *= 1.0f / ((flags & DEVQA_NOEPS) ? nrm : fmaxf(nrm, kNormEps));
+  }
+  return acc;
+}
+
+template <bool VEC>
+__global__ void __launch_bounds__(kRefineThreads) refine_kernel(const RefineParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ uint64_t ex[kMaxKp];
+  __shared__ uint64_t ak[kMaxKp];
+  __shared__ float s_prelim;
+  __shared__ uint32_t s_lost;                                       // max score code of any full list's last entry
+  constexpr int CH = VEC ? 128 : 32;
+  const int dim = int(p.dim);
+  const int dpad = (dim + CH - 1) / CH * CH;
+  float* sq = reinterpret_cast<float*>(smem_raw);                  // the query exactly as the stream kernel stages it
+  const int q = blockIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float* src = p.queries + size_t(q) * p.query_ld;
+  const float inv = p.qinv[q];
+  for (int c = threadIdx.x; c < dpad; c += kRefineThreads) sq[c] = c < dim ? src[c] * inv : 0.f;
+  for (int c = threadIdx.x; c < kMaxKp; c += kRefineThreads) {
+    ak[c] = c < p.kp ? p.akeys[size_t(q) * p.kp + c] : kEmptyKey;
+    ex[c] = kEmptyKey;
+  }
+  if (threadIdx.x == 0) s_lost = 0u;
+  __syncthreads();
+
+  auto rescore = [&](int c) {                                       // whole warp
+    const uint64_t a = ak[c];
+    uint64_t key = kEmptyKey;
+    if (a != kEmptyKey) {                                           // warp-uniform
+      const int64_t gid = int64_t(key_id(a));
+      int64_t row = gid - p.idmap.base;
+      if (p.idmap.chunk > 0) row = ((row / p.idmap.chunk) / p.idmap.world) * p.idmap.chunk + row % p.idmap.chunk;
+      const float s = exact_score<VEC>(p.bank + row * p.bank_ld, sq, dim, p.flags, lane);
+      key = pack_key(s, uint32_t(gid));
+    }
+    if (lane == 0) ex[c] = key;
+  };
+  // phase 1: the k candidates with the largest upper bounds
+  const int k1 = p.top_k < p.kp ? p.top_k : p.kp;
+  for (int c = warp; c < k1; c += kRefineThreads / 32) rescore(c);
+  // meanwhile: the upper bound of everything the per-CTA lists lost while full
+  {
+    uint32_t lost = 0u;
+    for (int g = threadIdx.x; g < p.n_lists; g += kRefineThreads) {
+      const uint32_t code = p.lostu[size_t(g) * p.n_queries + q];
+      lost = code > lost ? code : lost;
+    }
+    if (lost != 0u) atomicMax(&s_lost, lost);
+  }
+  __syncthreads();
+  if (warp == 0) {                                                  // the k-th best exact score among those k (or -inf)
+    uint64_t m = ~0ull;
+    for (int c = lane; c < p.top_k; c += 32) {
+      const uint64_t key = c < k1 ? ex[c] : kEmptyKey;
+      m = key < m ? key : m;
+    }
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) { const uint64_t o = shfl_xor_u64(m, off); m = o < m ? o : m; }
+    if (lane == 0) s_prelim = m == kEmptyKey ? -INFINITY : key_score(m);
+  }
+  __syncthreads();
+  // phase 2: every further candidate that could still beat it
+  const float prelim = s_prelim;
+  for (int c = k1 + warp; c < p.kp; c += kRefineThreads / 32) {
+    const uint64_t a = ak[c];
+    if (a != kEmptyKey && !(key_score(a) < prelim)) rescore(c);    // warp-uniform; NaN upper bounds are re-scored
+  }
+  __syncthreads();
+  // bitonic sort of the 128 slots, descending (empty = 0 sinks to the end)
+  for (int k = 2; k <= kMaxKp; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      const int i = threadIdx.x;
+      if (i < kMaxKp) {
+        const int l = i ^ j;
+        if (l > i) {
+          const uint64_t a = ex[i], b = ex[l];
+          const bool desc = (i & k) == 0;
+          if (desc ? a < b : a > b) { ex[i] = b; ex[l] = a; }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  // nothing lost can enter the top-k?
+  if (threadIdx.x == 0) {
+    const uint64_t kth = ex[p.top_k - 1];
+    bool complete = true;
+    uint32_t lost = s_lost;                                         // full per-CTA lists
+    const uint64_t mlast = ak[p.kp - 1];                            // the merged list, when it is full
+    if (mlast != kEmptyKey && uint32_t(mlast >> 32) > lost) lost = uint32_t(mlast >> 32);
+    if (lost != 0u) {
+      // rows were pushed out somewhere: they all have exact score <= code_score(lost)
+      complete = kth != kEmptyKey && code_score(lost) < key_score(kth);    // false for NaN on either side
+    }
+    p.need[q] = complete ? 0u : 1u;
+    if (!complete && p.fallbacks) atomicAdd(p.fallbacks, 1u);
+  }
+  for (int e = threadIdx.x; e < p.top_k; e += kRefineThreads) {
+    const uint64_t key = ex[e];
+    const size_t o = size_t(q) * p.top_k + e;
+    if (p.out_keys) {
+      p.out_keys[o] = key;
+    } else {
+      const bool empty = key == kEmptyKey;
+      p.out_scores[o] = empty ? -INFINITY : key_score(key);
+      p.out_ids[o] = empty ? int64_t(-1) : int64_t(key_id(key));
+    }
+  }
+}
+
+}  // namespace
+
+int refine_launch(const RefineParams& p, cudaStream_t stream) {
+  if (p.n_queries == 0) return DEVQA_OK;
+  DEVQA_REQUIRE(p.kp <= kMaxKp && p.top_k <= p.kp, "refine: candidate list of %d for top_k %d unsupported", p.kp, p.top_k);
+  const bool vec = p.dim % 4 == 0 && p.bank_ld % 4 == 0 && reinterpret_cast<uintptr_t>(p.bank) % 16 == 0;   // scan_stream's rule
+  const int ch = vec ? 128 : 32;
+  const size_t smem = size_t((p.dim + ch - 1) / ch * ch) * 4;
+  auto kern = vec ? refine_kernel<true> : refine_kernel<false>;
+  if (smem > 48 * 1024) DEVQA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+  kern<<<unsigned(p.n_queries), kRefineThreads, smem, stream>>>(p);
+  DEVQA_CUDA(cudaGetLastError());
+  count_launch();
+  return DEVQA_OK;
+}
+
+}  // namespace devqa

@@ -57,6 +57,18 @@ namespace devqa {
 namespace {
 
 constexpr int kTcThreads = 384;
+// Arithmetic of the contraction (template parameter MODE):
+//   kTf32x3  fp32 bank, 3xTF32 split (fp32-exact scores straight from the tensor core)
+//   kBf16x3  bf16 bank, queries split three ways (exact w.r.t. the bf16-rounded bank)
+//   kTf32x1  fp32 bank, ONE TF32 product: an approximate score s~ with a rigorous error bound E (scan.cuh,
+//            tc_filter_relerr), used as a FILTER.  The epilogue works on the UPPER BOUND u = s~ + E >= s: lists
+//            are sorted by u; a CTA's k-th best u minus 2E is a lower bound T of the exact k-th best score, shared
+//            across CTAs exactly like the thresholds of the other modes; rows with u < T cannot be in the result
+//            and are dropped.  refine.cu re-scores the surviving candidates exactly in fp32 and proves that
+//            nothing was lost (every row a full list pushed out has u <= that list's last entry).  One mma group
+//            (N = queries), no split warps, no lo tile: 48 KB instead of 88 KB of shared-memory traffic per
+//            k-block at 64 queries, and 128 queries per pass fit.
+enum : int { kTf32x3 = 0, kBf16x3 = 1, kTf32x1 = 2 };
 constexpr int kTileRows = 128;
 constexpr int kBlockK = 32;                          // fp32 columns per k-block = one 128-byte swizzle row
 constexpr int kATileBytes = kTileRows * kBlockK * 4; // 16 KB
@@ -231,7 +243,15 @@ struct TcParams {
   uint32_t flags;
   const float* qcat;       // this pass's query operand: [n_kblocks][2*qp rows][32] fp32, rows 128B-swizzled
   uint64_t* cand;          // [grid, n_queries, kcap]
-  const float* row_sumsq;  // optional cached ||row||^2 (bf16 variant: replaces the in-kernel norm warps)
+  const float* row_sumsq;  // optional cached ||row||^2 (bf16 / filter variants: replaces the in-kernel norm warps)
+  uint32_t* max_sumsq;     // filter variant with in-kernel norms: atomicMax of the bit pattern of max ||row||^2
+  const uint32_t* need;    // optional [n_queries] flags: a CTA whose pass has none set exits at once (exact fallback)
+  // filter variant only
+  const float* qerr;       // [n_queries] relerr(dim) * ||query as used||: E = qerr * ||row|| (1 for normalised rows)
+  const uint32_t* seed_u;  // optional [n_queries] score codes of a prefix sample's k-th best u (0 = none)
+  const uint32_t* bank_max_sumsq;   // un-normalised scores: max ||row||^2 of the bank (float bits)
+  int32_t k_true;          // the caller's top_k (lists keep kcap entries; T comes from entry k_true - 1)
+  uint32_t* lostu;         // [grid, n_queries] out: score code bounding every row this CTA's full list lost (0 = none)
   uint32_t* gthr;          // [n_queries] shared lower bounds of the k-th score (monotone score codes, 0 = none)
   IdMap idmap;
   long long* trace;        // optional [16][256] clock64 samples of CTA 0's roles (devqa_debug_tc_trace)
@@ -269,8 +289,10 @@ __host__ __device__ inline SmemLayout tc_layout(int stages, int qp, int kcap, in
 // UMMA operand fetches, so every dependent LDS/STS costs hundreds of cycles): for the common capacity 32
 // the list is pulled into registers once (one key per lane), all inserts are shuffles, and it is written
 // back once.
-__device__ __noinline__ float epilogue_insert_query(uint64_t* list, int kcap, int top_k, const float* tile_row, float th,
-                                                    uint32_t rowmask, int64_t row0, IdMap idmap, int lane) {
+// Returns two floats packed into 64 bits: high = score of entry top_k - 1 (the list's admission threshold), low =
+// score of entry k_true - 1 (filter variant: the k-th best upper bound, from which T is derived; equal otherwise).
+__device__ __noinline__ uint64_t epilogue_insert_query(uint64_t* list, int kcap, int top_k, int k_true, const float* tile_row, float th,
+                                                       uint32_t rowmask, int64_t row0, IdMap idmap, int lane) {
   const float4 sc = *reinterpret_cast<const float4*>(tile_row + lane * 4);
   const uint32_t bits = ((!(sc.x < th) ? 1u : 0u) | (!(sc.y < th) ? 2u : 0u) | (!(sc.z < th) ? 4u : 0u) | (!(sc.w < th) ? 8u : 0u)) & rowmask;
   uint64_t mylist = kcap == 32 ? list[lane] : 0ull;
@@ -302,23 +324,31 @@ __device__ __noinline__ float epilogue_insert_query(uint64_t* list, int kcap, in
       }
     }
   }
-  uint64_t kth;
+  uint64_t kth, ktrue;
   if (kcap == 32) {
     list[lane] = mylist;
     kth = shfl_u64(mylist, top_k - 1);
+    ktrue = shfl_u64(mylist, k_true - 1);
   } else {
     __syncwarp();
     kth = list[top_k - 1];
+    ktrue = list[k_true - 1];
   }
-  return kth == kEmptyKey ? -INFINITY : key_score(kth);
+  const float a = kth == kEmptyKey ? -INFINITY : key_score(kth);
+  const float b = ktrue == kEmptyKey ? -INFINITY : key_score(ktrue);
+  return (uint64_t(__float_as_uint(a)) << 32) | uint64_t(__float_as_uint(b));
 }
 
-template <int QP, bool MULTI, bool BF>
+template <int QP, bool MULTI, int MODE>
 __global__ void __launch_bounds__(kTcThreads, 1)
 scan_tc_kernel(const __grid_constant__ CUtensorMap bank_map, const __grid_constant__ TcParams p) {
   extern __shared__ unsigned char smem_unaligned[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_unaligned) + 1023) & ~uintptr_t(1023));
-  constexpr int kParts = BF ? 3 : 2;                     // row groups of the query operand per k-block
+  constexpr bool BF = MODE == kBf16x3;
+  constexpr bool FILT = MODE == kTf32x1;
+  constexpr bool TWO_ISSUERS = MODE == kTf32x3;
+  static_assert(!(FILT && MULTI), "the filter variant accumulates the whole K chain in the tensor core");
+  constexpr int kParts = BF ? 3 : (FILT ? 1 : 2);        // row groups of the query operand per k-block
   constexpr int kElemsK = BF ? 64 : 32;                  // bank columns per k-block (always 128 bytes)
   const SmemLayout L = tc_layout(p.stages, p.qp, p.kcap, kParts);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -334,14 +364,25 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap bank_map, const __grid_consta
   uint64_t* tmem_empty = tmem_full + 2;            // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L.tmem_slot);
 
+  // this CTA's share of the work
+  const int pass_local = int(blockIdx.x) % p.passes;
+  const int tile0 = int(blockIdx.x) / p.passes, tile_step = int(gridDim.x) / p.passes;
+  const int q0 = p.q0 + pass_local * QP;
+  const int nq_pass = min(QP, p.n_queries - q0);
+  if (p.need) {                                          // conditional (fallback) launch: nothing to do for most passes
+    int any = 0;
+    for (int i = threadIdx.x; i < nq_pass; i += kTcThreads) any |= int(p.need[q0 + i] != 0u);
+    if (!__syncthreads_or(any)) return;
+  }
+
   // ---- one-time setup ------------------------------------------------------------------------
   for (int i = threadIdx.x; i < QP * p.kcap; i += kTcThreads) lists[i] = kEmptyKey;
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&bank_map);
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < S; ++s) { mbar_init(&full_tma[s], 1); mbar_init(&full_split[s], 128); mbar_init(&empty[s], BF ? 1 : 2); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], BF ? 1 : 2); mbar_init(&tmem_empty[a], 128); }
+    for (int s = 0; s < S; ++s) { mbar_init(&full_tma[s], 1); mbar_init(&full_split[s], 128); mbar_init(&empty[s], TWO_ISSUERS ? 2 : 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], TWO_ISSUERS ? 2 : 1); mbar_init(&tmem_empty[a], 128); }
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, 512);
@@ -349,19 +390,17 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap bank_map, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  // this CTA's share of the work
-  const int pass_local = int(blockIdx.x) % p.passes;
-  const int tile0 = int(blockIdx.x) / p.passes, tile_step = int(gridDim.x) / p.passes;
-  const int q0 = p.q0 + pass_local * QP;
-  const int nq_pass = min(QP, p.n_queries - q0);
   const float* const qcat = p.qcat + size_t(pass_local) * size_t(p.n_kblocks) * (kParts * QP * 32);   // 32 words per 128-byte row
-  // TMEM columns: two accumulator buffers of 3*QP columns, then one 32-column lo tile per ring stage
-  constexpr uint32_t kAccCols = 3 * QP;
+  // TMEM columns: two accumulator buffers of 3*QP (filter: QP) columns, then one 32-column lo tile per ring stage
+  constexpr uint32_t kAccCols = FILT ? QP : 3 * QP;
   const uint32_t tmem_alo = tmem_base + 2 * kAccCols;
   const int nkb = p.n_kblocks;
-  // bf16 banks with cached row norms need no pass over the tile by CUDA cores at all
-  const bool norm_warps = !(BF && (p.row_sumsq != nullptr || !(p.flags & DEVQA_NORMALIZE_BANK)));
-  const int nsets = (nkb + kSetKBlocks - 1) / kSetKBlocks;   // accumulation units per tile (1 unless MULTI)
+  // bf16 banks with cached row norms need no pass over the tile by CUDA cores at all; the filter variant
+  // needs ||row||^2 either way (normalised scores, or max ||row|| for the error bound of plain dot scores)
+  const bool norm_warps = FILT ? p.row_sumsq == nullptr
+                               : !(BF && (p.row_sumsq != nullptr || !(p.flags & DEVQA_NORMALIZE_BANK)));
+  const int set_kb = FILT ? nkb : kSetKBlocks;           // k-blocks accumulated inside the tensor core
+  const int nsets = (nkb + set_kb - 1) / set_kb;         // accumulation units per tile (1 unless MULTI)
 
   if (warp == 0) {
     // ===== TMA producer =====
@@ -397,7 +436,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap bank_map, const __grid_consta
   } else if (warp == 1) {
     // ===== MMA issuer 1: A (hi by truncation, from shared memory) x [Qhi ; Qlo] -> cols [0, 2QP) =====
     if (lane == 0) {
-      const uint32_t idesc_cat = BF ? idesc_bf16(3 * QP) : idesc_tf32(2 * QP);
+      const uint32_t idesc_cat = BF ? idesc_bf16(3 * QP) : idesc_tf32(kParts * QP);
       const uint32_t a_lo0 = (smem_u32(smem + L.a_raw) & 0x3ffffu) >> 4, b_lo0 = (smem_u32(smem + L.bq) & 0x3ffffu) >> 4;
       RingPos r;
       uint32_t unit = 0;
@@ -407,9 +446,9 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap bank_map, const __grid_consta
           mbar_wait(&tmem_empty[a], ((unit >> 1) & 1) ^ 1);
           tc_fence_after();
           const uint32_t d = tmem_base + uint32_t(a) * kAccCols;
-          const int kb_end = min(nkb, (set + 1) * kSetKBlocks);
-          for (int kb = set * kSetKBlocks; kb < kb_end; ++kb) {
-            const uint32_t first = kb == set * kSetKBlocks ? 0u : 1u;
+          const int kb_end = min(nkb, (set + 1) * set_kb);
+          for (int kb = set * set_kb; kb < kb_end; ++kb) {
+            const uint32_t first = kb == set * set_kb ? 0u : 1u;
             const uint32_t a_lo = a_lo0 + uint32_t(r.s) * (kATileBytes >> 4), b_lo = b_lo0 + uint32_t(r.s) * (b_stage_bytes >> 4);
             mbar_wait(&full_tma[r.s], r.phase);
             tc_fence_after();
@@ -418,7 +457,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap bank_map, const __grid_consta
               if constexpr (BF) mma_bf16(d, desc_from_lo(a_lo + kk * 2), desc_from_lo(b_lo + kk * 2), idesc_cat, first | uint32_t(kk));
               else mma_tf32(d, desc_from_lo(a_lo + kk * 2), desc_from_lo(b_lo + kk * 2), idesc_cat, first | uint32_t(kk));
             }
-            if (BF && norm_warps) mbar_wait(&full_split[r.s], r.phase);   // the norm warps are done reading the stage
+            if (!TWO_ISSUERS && norm_warps) mbar_wait(&full_split[r.s], r.phase);   // the norm warps are done reading the stage
             mma_commit(&empty[r.s]);                      // (one of) the arrival(s) that free the stage
             r.advance(S);
           }
@@ -428,7 +467,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap bank_map, const __grid_consta
     }
   } else if (warp == 2) {
     // ===== MMA issuer 2: Alo (from tensor memory) x Qhi -> cols [2QP, 3QP) =====
-    if (lane == 0 && !BF) {
+    if (lane == 0 && TWO_ISSUERS) {
       const uint32_t idesc_hi = idesc_tf32(QP);
       const uint32_t b_lo0 = (smem_u32(smem + L.bq) & 0x3ffffu) >> 4;
       const bool on = !(p.flags & kDbgNoMma2);
@@ -440,9 +479,9 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap bank_map, const __grid_consta
           mbar_wait(&tmem_empty[a], ((unit >> 1) & 1) ^ 1);
           tc_fence_after();
           const uint32_t d = tmem_base + uint32_t(a) * kAccCols + 2 * QP;
-          const int kb_end = min(nkb, (set + 1) * kSetKBlocks);
-          for (int kb = set * kSetKBlocks; kb < kb_end; ++kb) {
-            const uint32_t first = kb == set * kSetKBlocks ? 0u : 1u;
+          const int kb_end = min(nkb, (set + 1) * set_kb);
+          for (int kb = set * set_kb; kb < kb_end; ++kb) {
+            const uint32_t first = kb == set * set_kb ? 0u : 1u;
             const uint32_t b_lo = b_lo0 + uint32_t(r.s) * (b_stage_bytes >> 4);
             const uint32_t alo = tmem_alo + uint32_t(r.s) * kBlockK;
             mbar_wait(&full_split[r.s], r.phase);         // implies full_tma[s]: the split warps waited on it
@@ -465,6 +504,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap bank_map, const __grid_consta
     const uint32_t row_off = uint32_t(row) * 128;
     const uint32_t sw = uint32_t(row & 7);                // 16-byte chunk c of row r lives at chunk c ^ (r & 7)
     uint32_t lt = 0;
+    float max_ss = 0.f;
     RingPos rp;
     const uint32_t st_lane = uint32_t((warp & 3) * 32) << 16;     // warp w may only touch TMEM lanes 32*(w%4)..
     const uint32_t a_raw_s = smem_u32(smem + L.a_raw) + row_off;
@@ -491,8 +531,16 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap bank_map, const __grid_consta
             }
           }
         }
+        if constexpr (FILT) {
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {                   // order is irrelevant for a sum of squares
+            const float4 v = lds128(src + (uint32_t(c) << 4));
+            ss[c] = fmaf(v.x, v.x, ss[c]); ss[c] = fmaf(v.y, v.y, ss[c]);
+            ss[c] = fmaf(v.z, v.z, ss[c]); ss[c] = fmaf(v.w, v.w, ss[c]);
+          }
+        }
         uint32_t lo[32];
-        if (!BF && !(p.flags & kDbgNoSplit)) {
+        if (TWO_ISSUERS && !(p.flags & kDbgNoSplit)) {
 #pragma unroll
           for (int c = 0; c < 8; ++c) {                   // logical 16-byte chunk c of the row
             const float4 v = lds128(src + ((uint32_t(c) ^ sw) << 4));
@@ -507,11 +555,21 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap bank_map, const __grid_consta
           tmem_st32(tmem_alo + uint32_t(s) * kBlockK + st_lane, lo);
           tmem_st_wait();
         }
-        if (kb == nkb - 1)
-          norms[(lt % kNormRing) * kTileRows + row] = ((ss[0] + ss[1]) + (ss[2] + ss[3])) + ((ss[4] + ss[5]) + (ss[6] + ss[7]));
+        if (kb == nkb - 1) {
+          const float tot = ((ss[0] + ss[1]) + (ss[2] + ss[3])) + ((ss[4] + ss[5]) + (ss[6] + ss[7]));
+          norms[(lt % kNormRing) * kTileRows + row] = tot;
+          if constexpr (FILT) max_ss = fmaxf(max_ss, tot);  // NaN rows are caught by the refine step, not here
+        }
         tc_fence_before();                                // TMEM writes ordered before the MMA issuer's reads
         mbar_arrive(&full_split[s]);
         rp.advance(S);
+      }
+    }
+    if constexpr (FILT) {                                 // max ||row||^2: the error bound of un-normalised scores
+      if (p.max_sumsq) {
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) max_ss = fmaxf(max_ss, __shfl_xor_sync(kFull, max_ss, off));
+        if (lane == 0) atomicMax(p.max_sumsq, __float_as_uint(max_ss));   // non-negative floats order like their bits
       }
     }
   } else if (warp >= 8) {
@@ -535,6 +593,24 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap bank_map, const __grid_consta
     const int own_j = (lane / NQW_) * HQ + e * NQW_ + lane % NQW_;
     const bool own_live = lane < QP / 4 && own_j < nq_pass;
     uint32_t* const own_gthr = p.gthr + q0 + (own_live ? own_j : 0);
+    // filter variant: per-query error scale in shared memory (phase A) and for the owned query (thresholds)
+    float* const eqs = reinterpret_cast<float*>(smem + L.thr);        // [QP]
+    float eq_own = 0.f, maxn = 1.f;
+    float lost_reg = -INFINITY;                          // upper bound of every row the owned query's full list turned away
+    const bool dot_mode = FILT && !(p.flags & DEVQA_NORMALIZE_BANK);  // E scales with ||row||
+    if constexpr (FILT) {
+      for (int j = threadIdx.x - 256; j < QP; j += 128) eqs[j] = j < nq_pass ? p.qerr[q0 + j] : 0.f;
+      if (dot_mode) maxn = sqrtf(__uint_as_float(*p.bank_max_sumsq));
+      if (own_live) {
+        eq_own = p.qerr[q0 + own_j];
+        const uint32_t code = p.seed_u ? p.seed_u[q0 + own_j] : 0u;
+        if (code != 0u) {
+          const float t = code_score(code) - 2.f * eq_own * maxn;     // lower bound of the exact k-th best score
+          if (t > thr_reg) thr_reg = t;
+        }
+      }
+      epilogue_barrier();
+    }
     for (int tile = tile0; tile < p.n_tiles; tile += tile_step, ++lt) {
       // pick up the bounds other CTAs have published (one relaxed load per owned query per tile)
       if (own_live) {
@@ -549,13 +625,14 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap bank_map, const __grid_consta
         mbar_wait(&tmem_full[a], (unit >> 1) & 1);
         tc_fence_after();
         if (e == 0 && lane == 0) trace_at(p, 6, unit);
-        float inv = 1.f;
-        if (last && (p.flags & DEVQA_NORMALIZE_BANK)) {
+        float inv = 1.f, rowfac = 1.f;                      // rowfac: ||row|| when E scales with it
+        if (last && ((p.flags & DEVQA_NORMALIZE_BANK) || dot_mode)) {
           const int64_t grow = int64_t(tile) * kTileRows + row_in_tile;
           const float ssq = norm_warps ? norms[(lt % kNormRing) * kTileRows + row_in_tile]
                                        : (grow < p.n_rows ? p.row_sumsq[grow] : 1.f);
           const float nrm = sqrtf(ssq);
-          inv = 1.0f / ((p.flags & DEVQA_NOEPS) ? nrm : fmaxf(nrm, kNormEps));
+          if (dot_mode) rowfac = nrm;
+          else inv = 1.0f / ((p.flags & DEVQA_NOEPS) ? nrm : fmaxf(nrm, kNormEps));
         }
         const uint32_t taddr = tmem_base + uint32_t(a) * kAccCols + (uint32_t(e * 32) << 16);
 #pragma unroll (MULTI ? HALVES : 1)
@@ -564,19 +641,27 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap bank_map, const __grid_consta
 #pragma unroll
           for (int c = 0; c < HQ / 16; ++c) {
             const int j0 = h * HQ + c * 16;
-            uint32_t d1[16], d2[16], d3[16];
+            uint32_t d1[16], d2[FILT ? 1 : 16], d3[FILT ? 1 : 16];
             tmem_ld<16>(taddr + uint32_t(j0), d1);
-            tmem_ld<16>(taddr + uint32_t(QP + j0), d2);
-            tmem_ld<16>(taddr + uint32_t(2 * QP + j0), d3);
+            if constexpr (!FILT) {
+              tmem_ld<16>(taddr + uint32_t(QP + j0), d2);
+              tmem_ld<16>(taddr + uint32_t(2 * QP + j0), d3);
+            }
             tmem_ld_wait();
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
-              float v = (__uint_as_float(d2[i]) + __uint_as_float(d3[i])) + __uint_as_float(d1[i]);
+              float v;
+              if constexpr (FILT) v = __uint_as_float(d1[i]);
+              else v = (__uint_as_float(d2[i]) + __uint_as_float(d3[i])) + __uint_as_float(d1[i]);
               if constexpr (MULTI) {
                 v = set == 0 ? v : acc[j0 + i] + v;
                 acc[j0 + i] = v;
               }
-              if (last) stile[(c * 16 + i) * kTileRows + row_in_tile] = v * inv;
+              if constexpr (FILT) {                         // upper bound of the exact score
+                if (last) stile[(c * 16 + i) * kTileRows + row_in_tile] = fmaf(v, inv, eqs[j0 + i] * rowfac);
+              } else {
+                if (last) stile[(c * 16 + i) * kTileRows + row_in_tile] = v * inv;
+              }
             }
           }
           if (h == HALVES - 1) {                          // every TMEM read of this buffer has completed
@@ -612,9 +697,19 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap bank_map, const __grid_consta
             if (j >= nq_pass) break;
             const int oi = h * NQW + i;                   // index among the queries this warp owns
             const float th = __shfl_sync(kFull, thr_reg, oi);
-            const float nt = epilogue_insert_query(lists + size_t(j) * p.kcap, p.kcap, p.top_k,
-                                                   stile + (e * NQW + i) * kTileRows, th, rowmask, row0, p.idmap, lane);
-            if (lane == oi && nt > thr_reg) {               // publish: a lower bound of the global k-th score
+            const uint64_t nt2 = epilogue_insert_query(lists + size_t(j) * p.kcap, p.kcap, p.top_k, FILT ? p.k_true : p.top_k,
+                                                       stile + (e * NQW + i) * kTileRows, th, rowmask, row0, p.idmap, lane);
+            const float nt = __uint_as_float(uint32_t(nt2 >> 32));
+            if constexpr (FILT) {
+              if (lane == oi) {
+                // k-th best upper bound - 2E  <=  k-th best exact score of these rows  <=  that of the bank
+                const float t = __uint_as_float(uint32_t(nt2)) - 2.f * eq_own * maxn;
+                if (t > thr_reg) { thr_reg = t; atomicMax(own_gthr, score_code(t)); }
+                // A full list admits nothing below its last entry.  Rows it turns away while that entry is the
+                // binding threshold (above T) are LOST, not proven irrelevant: remember their upper bound.
+                if (nt > thr_reg) { thr_reg = nt; lost_reg = nt; }
+              }
+            } else if (lane == oi && nt > thr_reg) {        // publish: a lower bound of the global k-th score
               thr_reg = nt;
               atomicMax(own_gthr, score_code(nt));
             }
@@ -626,6 +721,9 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap bank_map, const __grid_consta
         if (e == 0 && lane == 0 && p.trace && blockIdx.x == 0 && unit < 256) { p.trace[8 * 256 + unit] = slow_calls; slow_calls = 0; }
 #endif
       }
+    }
+    if constexpr (FILT) {
+      if (own_live) p.lostu[size_t(tile0) * p.n_queries + q0 + own_j] = lost_reg == -INFINITY ? 0u : score_code(lost_reg);
     }
   }
 
@@ -680,6 +778,49 @@ __global__ void __launch_bounds__(256) prep_queries_kernel(const float* __restri
       blk[hi_row * kBlockK + (((w >> 2) ^ (hi_row & 7)) << 2) + (w & 3)] = hi;
       blk[lo_row * kBlockK + (((w >> 2) ^ (lo_row & 7)) << 2) + (w & 3)] = __uint_as_float(lb);
     }
+  }
+}
+
+// Filter variant (kTf32x1): one TF32 plane (rounded to nearest), [n_kblocks][qp rows][32 cols] per pass, plus the
+// per-query scale and norm that refine.cu needs to re-create the exact fp32 query and the error bound.
+__global__ void __launch_bounds__(256) prep_queries_filt_kernel(const float* __restrict__ q, int64_t q_ld, int n_queries, int dim,
+                                                                int qp, int n_kblocks, int q_pad, unsigned flags,
+                                                                float* __restrict__ qcat, uint32_t* __restrict__ gthr,
+                                                                float* __restrict__ qinv, float* __restrict__ qerr,
+                                                                uint32_t* __restrict__ seed_u) {
+  if (blockIdx.x == 0)
+    for (int i = threadIdx.x; i < q_pad; i += blockDim.x) { gthr[i] = 0u; seed_u[i] = 0u; }
+  const int lane = threadIdx.x & 31;
+  const int warps = gridDim.x * (blockDim.x >> 5);
+  const int d_pad = n_kblocks * kBlockK;
+  for (int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < q_pad; r += warps) {
+    float inv = 0.f;
+    const float* src = q + size_t(r < n_queries ? r : 0) * q_ld;
+    if (r < n_queries) {
+      inv = 1.f;
+      if (flags & DEVQA_NORMALIZE_QUERY) {
+        float ss = 0.f;
+        for (int c = lane; c < dim; c += 32) { const float x = src[c]; ss = fmaf(x, x, ss); }
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) ss += __shfl_xor_sync(kFull, ss, off);
+        const float nrm = sqrtf(ss);
+        inv = 1.0f / ((flags & DEVQA_NOEPS) ? nrm : fmaxf(nrm, kNormEps));
+      }
+    }
+    const int pass = r / qp, rp = r % qp;
+    float* base = qcat + size_t(pass) * n_kblocks * (qp * kBlockK);
+    float nn = 0.f;
+    for (int c = lane; c < d_pad; c += 32) {
+      const float x = (r < n_queries && c < dim) ? src[c] * inv : 0.f;
+      nn = fmaf(x, x, nn);
+      uint32_t hb;
+      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(x));
+      const int kb = c / kBlockK, w = c % kBlockK;
+      base[size_t(kb) * (qp * kBlockK) + rp * kBlockK + (((w >> 2) ^ (rp & 7)) << 2) + (w & 3)] = __uint_as_float(hb);
+    }
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) nn += __shfl_xor_sync(kFull, nn, off);
+    if (lane == 0 && r < n_queries) { qinv[r] = inv; qerr[r] = tc_filter_relerr(dim) * sqrtf(nn); }
   }
 }
 
@@ -766,26 +907,28 @@ bool scan_tc_supported(int bank_dtype, const void* bank, int64_t dim, int64_t ba
 }
 
 // bank columns per 128-byte k-block row, and the padded k-block count
-static int elems_per_kblock(int bank_dtype) { return bank_dtype == DEVQA_F32 ? 32 : 64; }
-int scan_tc_kblocks(int bank_dtype, int64_t dim) { return int((dim + elems_per_kblock(bank_dtype) - 1) / elems_per_kblock(bank_dtype)); }
+static int elems_per_kblock(int mode) { return mode == kTcBf16x3 ? 64 : 32; }
+static int mode_parts(int mode) { return mode == kTcBf16x3 ? 3 : (mode == kTcTf32x1 ? 1 : 2); }
+int scan_tc_kblocks(int mode, int64_t dim) { return int((dim + elems_per_kblock(mode) - 1) / elems_per_kblock(mode)); }
 // bytes of the prepared query operand for q_pad queries
-size_t scan_tc_qcat_bytes(int bank_dtype, int64_t dim, int q_pad) {
-  return size_t(q_pad) * scan_tc_kblocks(bank_dtype, dim) * 128 * (bank_dtype == DEVQA_F32 ? 2 : 3);
+size_t scan_tc_qcat_bytes(int mode, int64_t dim, int q_pad) {
+  return size_t(q_pad) * scan_tc_kblocks(mode, dim) * 128 * mode_parts(mode);
 }
 
-// Queries per pass + pipeline depth that fit in shared memory / tensor memory for this k.
-int scan_tc_plan(int bank_dtype, int n_queries, int64_t dim, int kcap, int* qp_out, int* stages_out) {
-  const bool bf = bank_dtype != DEVQA_F32;
+// Queries per pass + pipeline depth that fit in shared memory / tensor memory for this list capacity.
+int scan_tc_plan(int mode, int n_queries, int64_t dim, int kcap, bool cached_norms, int* qp_out, int* stages_out) {
+  const bool bf = mode == kTcBf16x3, filt = mode == kTcTf32x1;
   // more than one K-set (1024 fp32 / 2048 bf16 columns) sums K-sets in the epilogue's registers (MULTI):
-  // 32 queries per pass at most
-  int qp = scan_tc_kblocks(bank_dtype, dim) > kSetKBlocks ? 32 : 64;
+  // 32 queries per pass at most.  The filter keeps the whole K chain in the tensor core (its error bound
+  // covers the drift) and, with cached row norms (no CUDA-core pass over the tile), takes 128 queries per pass.
+  int qp = filt ? (cached_norms ? 128 : 64) : (scan_tc_kblocks(mode, dim) > kSetKBlocks ? 32 : 64);
   const int q16 = (n_queries + 15) / 16 * 16;
   while (qp > 16 && qp / 2 >= q16) qp >>= 1;
   for (; qp >= 16; qp >>= 1) {
     for (int stages = kMaxStages; stages >= 3; --stages) {
-      // TMEM: 2 accumulator buffers of 3*qp columns (+ one 32-column lo tile per stage for fp32 banks)
-      if (6 * qp + (bf ? 0 : stages * kBlockK) > 512) continue;
-      if (tc_layout(stages, qp, kcap, bf ? 3 : 2).total + 1024 <= 225 * 1024) {
+      // TMEM: 2 accumulator buffers of 3*qp (filter: qp) columns (+ one 32-column lo tile per stage for 3xTF32)
+      if ((filt ? 2 : 6) * qp + (mode == kTcTf32x3 ? stages * kBlockK : 0) > 512) continue;
+      if (tc_layout(stages, qp, kcap, mode_parts(mode)).total + 1024 <= 225 * 1024) {
         *qp_out = qp; *stages_out = stages;
         return DEVQA_OK;
       }
@@ -796,16 +939,20 @@ int scan_tc_plan(int bank_dtype, int n_queries, int64_t dim, int kcap, int* qp_o
 }
 
 // qcat must hold scan_tc_qcat_bytes(); q_pad is a multiple of qp; gthr [q_pad] is zeroed here.
-int scan_tc_prep_queries(int bank_dtype, const float* queries, int64_t query_ld, int n_queries, int qp, int q_pad,
-                         int64_t dim, unsigned flags, void* qcat, uint32_t* gthr, cudaStream_t stream) {
-  const int n_kblocks = scan_tc_kblocks(bank_dtype, dim);
+int scan_tc_prep_queries(int mode, const float* queries, int64_t query_ld, int n_queries, int qp, int q_pad,
+                         int64_t dim, unsigned flags, void* qcat, uint32_t* gthr, float* qinv, float* qerr,
+                         uint32_t* seed_u, cudaStream_t stream) {
+  const int n_kblocks = scan_tc_kblocks(mode, dim);
   const int grid = (q_pad + 7) / 8;
-  if (bank_dtype == DEVQA_F32)
+  if (mode == kTcTf32x3)
     prep_queries_kernel<<<grid, 256, 0, stream>>>(queries, query_ld, n_queries, int(dim), qp, n_kblocks, q_pad, flags,
                                                   static_cast<float*>(qcat), gthr);
-  else
+  else if (mode == kTcBf16x3)
     prep_queries_bf16_kernel<<<grid, 256, 0, stream>>>(queries, query_ld, n_queries, int(dim), qp, n_kblocks, q_pad, flags,
                                                        static_cast<__nv_bfloat16*>(qcat), gthr);
+  else
+    prep_queries_filt_kernel<<<grid, 256, 0, stream>>>(queries, query_ld, n_queries, int(dim), qp, n_kblocks, q_pad, flags,
+                                                       static_cast<float*>(qcat), gthr, qinv, qerr, seed_u);
   DEVQA_CUDA(cudaGetLastError());
   count_launch();
   return DEVQA_OK;
@@ -814,11 +961,12 @@ int scan_tc_prep_queries(int bank_dtype, const float* queries, int64_t query_ld,
 static long long* g_tc_trace = nullptr;
 void scan_tc_set_trace(long long* buf) { g_tc_trace = buf; }
 
-int scan_tc_launch(const ScanParams& sp, int bank_dtype, const void* qcat, uint32_t* gthr, int qp, int stages, int passes,
+int scan_tc_launch(const ScanParams& sp, int mode, const void* qcat, uint32_t* gthr, int qp, int stages, int passes,
                    int ctas_per_pass, cudaStream_t stream) {
   const int grid = passes * ctas_per_pass;
-  const bool bf = bank_dtype != DEVQA_F32;
-  const int n_kblocks = scan_tc_kblocks(bank_dtype, sp.dim);
+  const bool bf = mode == kTcBf16x3;
+  const int parts = mode_parts(mode);
+  const int n_kblocks = scan_tc_kblocks(mode, sp.dim);
   CUtensorMap bank_map;
   int rc = make_map(&bank_map, sp.bank, bf, uint64_t(sp.dim), uint64_t(sp.n_rows), uint64_t(sp.bank_ld) * (bf ? 2 : 4), kTileRows);
   if (rc) return rc;
@@ -828,20 +976,26 @@ int scan_tc_launch(const ScanParams& sp, int bank_dtype, const void* qcat, uint3
   p.qp = qp; p.nq_pass = sp.nq_pass; p.q0 = sp.q0; p.n_queries = sp.n_queries;
   p.top_k = sp.top_k; p.kcap = sp.kcap; p.stages = stages; p.passes = passes; p.flags = sp.flags;
   p.cand = sp.cand; p.gthr = gthr; p.idmap = sp.idmap; p.row_sumsq = sp.row_sumsq;
+  p.max_sumsq = sp.max_sumsq; p.need = sp.need;
+  p.lostu = sp.lostu; p.qerr = sp.qerr; p.seed_u = sp.seed_u; p.bank_max_sumsq = sp.bank_max_sumsq; p.k_true = sp.k_true > 0 ? sp.k_true : sp.top_k;
   // pass index = q0 / qp; one pass = n_kblocks * parts * qp rows of 128 bytes (32 words)
-  p.qcat = static_cast<const float*>(qcat) + size_t(sp.q0 / qp) * size_t(n_kblocks) * (bf ? 3 : 2) * qp * 32;
+  p.qcat = static_cast<const float*>(qcat) + size_t(sp.q0 / qp) * size_t(n_kblocks) * parts * qp * 32;
   p.trace = g_tc_trace;
-  const size_t smem = tc_layout(stages, qp, sp.kcap, bf ? 3 : 2).total + 1024;
-  const bool multi = p.n_kblocks > kSetKBlocks;
+  const size_t smem = tc_layout(stages, qp, sp.kcap, parts).total + 1024;
+  const bool multi = mode != kTcTf32x1 && p.n_kblocks > kSetKBlocks;
   void (*kern)(CUtensorMap, TcParams) = nullptr;
-  if (!bf) {
-    if (!multi) kern = qp == 64 ? scan_tc_kernel<64, false, false> : qp == 32 ? scan_tc_kernel<32, false, false> : scan_tc_kernel<16, false, false>;
-    else kern = qp == 32 ? scan_tc_kernel<32, true, false> : scan_tc_kernel<16, true, false>;
+  if (mode == kTcTf32x3) {
+    if (!multi) kern = qp == 64 ? scan_tc_kernel<64, false, kTf32x3> : qp == 32 ? scan_tc_kernel<32, false, kTf32x3> : scan_tc_kernel<16, false, kTf32x3>;
+    else kern = qp == 32 ? scan_tc_kernel<32, true, kTf32x3> : scan_tc_kernel<16, true, kTf32x3>;
+  } else if (mode == kTcBf16x3) {
+    if (!multi) kern = qp == 64 ? scan_tc_kernel<64, false, kBf16x3> : qp == 32 ? scan_tc_kernel<32, false, kBf16x3> : scan_tc_kernel<16, false, kBf16x3>;
+    else kern = qp == 32 ? scan_tc_kernel<32, true, kBf16x3> : scan_tc_kernel<16, true, kBf16x3>;
   } else {
-    if (!multi) kern = qp == 64 ? scan_tc_kernel<64, false, true> : qp == 32 ? scan_tc_kernel<32, false, true> : scan_tc_kernel<16, false, true>;
-    else kern = qp == 32 ? scan_tc_kernel<32, true, true> : scan_tc_kernel<16, true, true>;
+    kern = qp == 128 ? scan_tc_kernel<128, false, kTf32x1> : qp == 64 ? scan_tc_kernel<64, false, kTf32x1>
+         : qp == 32 ? scan_tc_kernel<32, false, kTf32x1> : scan_tc_kernel<16, false, kTf32x1>;
   }
-  if (qp != 16 && qp != 32 && !(qp == 64 && !multi)) {
+  const bool qp_ok = qp == 16 || qp == 32 || (qp == 64 && !multi) || (qp == 128 && mode == kTcTf32x1);
+  if (!qp_ok) {
     set_error("tcgen05 scan: unsupported queries-per-pass %d", qp);
     return DEVQA_E_INVALID;
   }

@@ -75,6 +75,11 @@ extern "C" {
                                            and NaN ranks above every number, as torch.topk does        */
 #define DEVQA_FORCE_STREAM (1u << 8)    /* testing/benchmark: force the bank-streaming (CUDA-core) kernel */
 #define DEVQA_FORCE_TENSOR (1u << 9)    /* testing/benchmark: force the tcgen05 contraction kernel       */
+#define DEVQA_FORCE_TF32X3 (1u << 10)   /* testing/benchmark: tcgen05 path without the TF32 filter + exact
+                                           re-scoring stage (every score straight from the 3xTF32 split)  */
+
+#define DEVQA_DEBUG_FILTER_ONLY (1u << 22) /* tests: return the TF32 filter's approximate top-k as is (no exact
+                                              re-scoring) so that its error bound can be checked            */
 
 typedef struct devqa_bank devqa_bank; /* opaque, library-owned fact bank */
 typedef struct devqa_comm devqa_comm; /* opaque, one NCCL communicator + staging */
@@ -91,6 +96,12 @@ DEVQA_API int64_t devqa_launch_count(void);
 DEVQA_API int devqa_profile_enable(int device, int enable);
 DEVQA_API int devqa_profile_collect(int device, double* scan_ms_total, int64_t* scan_launches,
                                     int64_t* searches);
+
+/* fp32 banks, batches > 4 queries: the tensor-core scan filters with ONE TF32 product, re-scores its
+ * candidates exactly in fp32 and proves per query that the exact top-k is among them; queries for which the
+ * proof fails (heavily duplicated / clustered rows, NaN) are redone by the fp32-exact 3xTF32 scan in the same
+ * call.  Returns (and resets) how many queries took that fallback on `device`; synchronises the device. */
+DEVQA_API int devqa_filter_fallbacks(int device, int64_t* count);
 
 /* Debugging aid: when set to a device buffer of 16 x 256 int64, CTA 0 of the tcgen05 scan records
  * clock64() samples of its warp roles (producer, split, MMA, epilogue) into it.  NULL disables. */

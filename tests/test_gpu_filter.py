@@ -1,0 +1,209 @@
+"""The TF32 filter + exact re-scoring stage of the tcgen05 scan (fp32 banks, batches > 4 queries):
+its error bound, its bit-identity with the CUDA-core stream kernel, and the exact fallback for queries
+whose candidate list is not provably complete.  GPU only."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+import devqa_b200
+from devqa_b200 import FactBank
+from oracle import semantic_search as ss
+
+pytestmark = pytest.mark.gpu
+L = devqa_b200._lib
+GAP, RTOL, ATOL = 1e-5, 1e-5, 1e-6
+
+
+def _randn(n, d, seed, unit=True):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(n, d, generator=g)
+    return torch.nn.functional.normalize(x, dim=1) if unit else x
+
+
+def _hidden_like(n, d, seed):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(n, d, generator=g) * torch.exp(0.5 * torch.randn(n, 1, generator=g))
+    x[:, [1, d // 3, d // 2, d - 2]] *= 50.0
+    return x
+
+
+def _fallbacks(device=0):
+    n = C.c_int64()
+    L.check(L.lib().devqa_filter_fallbacks(device, C.byref(n)))
+    return n.value
+
+
+def _record(name, value):
+    """Keep measured error / bound pairs next to the test log (gpurun_out/ travels back from the GPU box)."""
+    import json, os
+    out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    if os.path.isdir(out):
+        path = os.path.join(out, "filter_error_bound.json")
+        data = json.load(open(path)) if os.path.exists(path) else {}
+        data[name] = value
+        json.dump(data, open(path, "w"), indent=1)
+
+
+def relerr(d):
+    """csrc/scan.cuh tc_filter_relerr"""
+    return 1.5 * 2.0 ** -10 + d * 2.0 ** -24
+
+
+@pytest.mark.parametrize("n,d,nq,k,nb,nq_mode", [
+    (5000, 768, 64, 32, "eps", "eps"), (5000, 768, 128, 32, "eps", "eps"), (3000, 384, 20, 16, "eps", "eps"),
+    (4097, 100, 9, 5, None, None), (2000, 4096, 40, 4, "eps", "eps"), (300, 36, 7, 8, "eps", None),
+    (6000, 1000, 130, 64, "noeps", "noeps"), (129, 64, 200, 3, None, "eps")])
+def test_filter_matches_stream_kernel_bit_for_bit(n, d, nq, k, nb, nq_mode):
+    """Re-scoring repeats scan_stream's arithmetic, so the kernel choice is invisible in results."""
+    bank, q = _randn(n, d, n + d, unit=False), _randn(nq, d, nq + k, unit=False)
+    fb = FactBank.from_embeddings(bank)
+    _fallbacks()
+    a = fb.search(q.cuda(), k, normalize_bank=nb, normalize_query=nq_mode, flags=L.FORCE_TENSOR)
+    assert _fallbacks() == 0
+    b = fb.search(q.cuda(), k, normalize_bank=nb, normalize_query=nq_mode, flags=L.FORCE_STREAM)
+    assert torch.equal(a[1], b[1])
+    assert torch.equal(a[0], b[0])
+    truth = ss.truth_scores_fp64(q, bank, normalize_bank=bool(nb), normalize_query=bool(nq_mode))
+    kk = min(k, n)
+    ss.compare_topk(a[0].cpu().numpy()[:, :kk], a[1].cpu().numpy()[:, :kk], truth, k, gap=GAP, rtol=RTOL, atol=ATOL)
+    fb.close()
+
+
+def test_filter_on_caller_owned_tensor_without_cached_norms():
+    """devqa_search_raw has no cached ||row||^2: the norm warps supply them (and max ||row|| for dot scores)."""
+    bank, q = _hidden_like(3000, 512, 7), _hidden_like(33, 512, 8)
+    dev_bank, dev_q = bank.cuda(), q.cuda()
+    for normalise in (True, False):
+        score_fn = devqa_b200.util.cos_sim if normalise else devqa_b200.util.dot_score
+        hits = devqa_b200.util.semantic_search(dev_q, dev_bank, top_k=10, score_function=score_fn)
+        truth = ss.truth_scores_fp64(q, bank, normalize_bank=normalise, normalize_query=normalise)
+        s = np.array([[h["score"] for h in row] for row in hits], dtype=np.float32)
+        i = np.array([[h["corpus_id"] for h in row] for row in hits])
+        ss.compare_topk(s, i, truth, 10, gap=GAP, rtol=RTOL, atol=ATOL)
+
+
+@pytest.mark.parametrize("kind", ["randn", "positive", "hidden", "hidden4096"])
+def test_filter_error_bound_holds(kind):
+    """The filter ranks rows by u = approximate score + E and everything rests on  exact <= u <= exact + 2E,
+    E = relerr(D) * ||row|| * ||query||.  Checked on adversarial inputs: all-positive vectors make every TF32
+    truncation error point the same way; hidden-state rows have x50 outlier columns."""
+    g = torch.Generator().manual_seed(99)
+    if kind == "randn":
+        bank, q = _randn(4000, 768, 1, unit=False), _randn(48, 768, 2, unit=False)
+    elif kind == "positive":
+        bank, q = torch.rand(4000, 768, generator=g) + 0.5, torch.rand(48, 768, generator=g) + 0.5
+    elif kind == "hidden":
+        bank, q = _hidden_like(4000, 768, 3), _hidden_like(48, 768, 4)
+    else:
+        bank, q = _hidden_like(2000, 4096, 5), _hidden_like(32, 4096, 6)
+    d = bank.shape[1]
+    fb = FactBank.from_embeddings(bank)
+    for nb, nqm in (("eps", "eps"), (None, None)):
+        u, i = fb.search(q.cuda(), 32, normalize_bank=nb, normalize_query=nqm, flags=L.FORCE_TENSOR | L.DEBUG_FILTER_ONLY)
+        u, i = u.cpu().double().numpy(), i.cpu().numpy()
+        truth = ss.truth_scores_fp64(q, bank, normalize_bank=bool(nb), normalize_query=bool(nqm))
+        exact = np.take_along_axis(truth, i, axis=1)
+        bn = np.linalg.norm(bank.double().numpy(), axis=1)
+        qn = np.linalg.norm(q.double().numpy(), axis=1)
+        scale = np.ones_like(exact) if nb else bn[i] * qn[:, None]
+        e = relerr(d) * scale
+        err = np.abs(u - e - exact) / scale                     # |approximate - exact| per unit of ||row|| ||query||
+        _record(f"{kind}_{'cos' if nb else 'dot'}_d{d}", {"max_err": float(err.max()), "bound": relerr(d)})
+        assert (u >= exact).all(), (kind, nb, float((exact - u).max()))
+        assert (u <= exact + 2.0001 * e).all(), (kind, nb)
+        assert err.max() > 1e-6          # these really are approximate scores
+    fb.close()
+
+
+def test_duplicated_rows_take_the_exact_fallback():
+    """200 identical consecutive rows: one CTA's list fills up with ties, rows it turns away are not provably
+    irrelevant, and the 3xTF32 scan redoes that query; ties resolve to ascending ids either way."""
+    bank = _randn(5000, 256, 11)
+    bank[1000:1200] = bank[1000]
+    q = torch.cat([bank[1000:1001] + 0.01 * _randn(1, 256, 12), _randn(15, 256, 13)])
+    fb = FactBank.from_embeddings(bank)
+    _fallbacks()
+    s, i = fb.search(q.cuda(), 32, flags=L.FORCE_TENSOR)
+    n_fb = _fallbacks()
+    assert 1 <= n_fb <= 2
+    assert i[0].tolist() == list(range(1000, 1032))
+    truth = ss.truth_scores_fp64(q, bank)
+    ss.compare_topk(s.cpu().numpy(), i.cpu().numpy(), truth, 32, gap=GAP, rtol=RTOL, atol=ATOL)
+    # the other queries were answered by the filter + re-scoring: bit-identical to the stream kernel
+    s2, i2 = fb.search(q.cuda(), 32, flags=L.FORCE_STREAM)
+    assert torch.equal(i, i2) and torch.equal(s[1:], s2[1:])
+    fb.close()
+
+
+def test_clustered_scores_stay_exact():
+    """All-positive rows: cosine scores crowd into a narrow band, most queries fail the proof."""
+    g = torch.Generator().manual_seed(21)
+    bank, q = torch.rand(20000, 384, generator=g), torch.rand(24, 384, generator=g)
+    fb = FactBank.from_embeddings(bank)
+    s, i = fb.search(q.cuda(), 16, flags=L.FORCE_TENSOR)
+    truth = ss.truth_scores_fp64(q, bank)
+    ss.compare_topk(s.cpu().numpy(), i.cpu().numpy(), truth, 16, gap=GAP, rtol=RTOL, atol=ATOL)
+    fb.close()
+
+
+def test_nan_rows_and_zero_rows():
+    bank = _randn(3000, 128, 31, unit=False)
+    bank[17] = 0
+    bank[99, 5] = float("nan")
+    q = _randn(10, 128, 32, unit=False)
+    fb = FactBank.from_embeddings(bank)
+    s, i = fb.search(q.cuda(), 4, normalize_bank="noeps", normalize_query="noeps", flags=L.FORCE_TENSOR)
+    assert set(i[:, :2].flatten().tolist()) == {17, 99} and torch.isnan(s[:, :2]).all()
+    s, i = fb.search(q.cuda(), 4, flags=L.FORCE_TENSOR)               # eps clamp: the zero row scores 0, NaN row first
+    assert (i[:, 0] == 99).all() and torch.isnan(s[:, 0]).all()
+    fb.close()
+
+
+def test_large_batch_many_passes_and_chunks():
+    """Q = 2100: three scratch chunks of 1024 queries, 128-query passes, several launches."""
+    bank, q = _randn(20000, 128, 41), _randn(2100, 128, 42)
+    fb = FactBank.from_embeddings(bank)
+    s, i = fb.search(q.cuda(), 8)
+    truth = ss.truth_scores_fp64(q, bank)
+    ss.compare_topk(s.cpu().numpy(), i.cpu().numpy(), truth, 8, gap=GAP, rtol=RTOL, atol=ATOL)
+    keys = fb.search_packed(q.cuda(), 8)
+    s3, i3 = devqa_b200.bank.topk_merge(keys.unsqueeze(0).contiguous(), 8)
+    assert torch.equal(i3, i) and torch.equal(s3, s)
+    fb.close()
+
+
+def test_sharded_filter_equals_single_bank():
+    """Chunked round-robin id map: re-scoring inverts it to find the local row."""
+    bank, q = _randn(9000, 192, 51), _randn(40, 192, 52)
+    whole = FactBank.from_embeddings(bank)
+    ref = whole.search(q.cuda(), 16)
+    chunk, world = 500, 3
+    keys = []
+    for rank in range(world):
+        rows = torch.cat([bank[c * chunk:(c + 1) * chunk] for c in range(rank, 18, world)])
+        fb = FactBank.from_embeddings(rows)
+        fb.set_id_map(0, chunk, rank, world)
+        keys.append(fb.search_packed(q.cuda(), 16, flags=L.FORCE_TENSOR))
+        fb.close()
+    s, i = devqa_b200.bank.topk_merge(torch.stack(keys).contiguous(), 16)
+    assert torch.equal(i, ref[1]) and torch.equal(s, ref[0])
+    whole.close()
+
+
+def test_full_size_bank_has_no_fallbacks():
+    """1M x 768 unit rows, Q = 128, k = 32: the filter's candidate list (K' = 64) is provably complete for
+    every query, i.e. the fast path is the one that runs at the benchmark shapes."""
+    fb = FactBank(768, capacity=1_000_000)
+    fb.append_synthetic(1_000_000, 3234)
+    q = _randn(128, 768, 7678).cuda()
+    _fallbacks()
+    a = fb.search(q, 32)
+    assert _fallbacks() == 0
+    b = fb.search(q, 32, flags=L.FORCE_TENSOR | L.FORCE_TF32X3)
+    assert (a[1] == b[1]).float().mean() > 0.995       # the 3xTF32 scores differ in the last bits: near-ties may swap
+    torch.testing.assert_close(a[0], b[0], rtol=1e-5, atol=1e-6)
+    c = fb.search(q[:8], 32, flags=L.FORCE_STREAM)
+    assert torch.equal(a[1][:8], c[1]) and torch.equal(a[0][:8], c[0])
+    fb.close()

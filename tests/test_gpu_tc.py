@@ -27,13 +27,16 @@ def _hidden_like(n, d, seed):
 
 
 def _check_tc(bank_cpu, q_cpu, k, nb="eps", nq="eps"):
+    """Both arithmetic variants of the tcgen05 scan: the default (TF32 filter + exact re-scoring, with the
+    3xTF32 scan as its fallback) and the 3xTF32 scan alone."""
     fb = FactBank.from_embeddings(bank_cpu)
-    s, i = fb.search(q_cpu.cuda(), k, normalize_bank=nb, normalize_query=nq, flags=L.FORCE_TENSOR)
-    s, i = s.cpu().numpy(), i.cpu().numpy()
     kk = min(k, len(bank_cpu))
     truth = ss.truth_scores_fp64(q_cpu, bank_cpu, normalize_bank=bool(nb), normalize_query=bool(nq))
-    stats = ss.compare_topk(s[:, :kk], i[:, :kk], truth, k, gap=GAP, rtol=RTOL, atol=ATOL)
-    assert np.all(i[:, kk:] == -1)
+    for variant in (L.FORCE_TENSOR, L.FORCE_TENSOR | L.FORCE_TF32X3):
+        s, i = fb.search(q_cpu.cuda(), k, normalize_bank=nb, normalize_query=nq, flags=variant)
+        s, i = s.cpu().numpy(), i.cpu().numpy()
+        stats = ss.compare_topk(s[:, :kk], i[:, :kk], truth, k, gap=GAP, rtol=RTOL, atol=ATOL)
+        assert np.all(i[:, kk:] == -1)
     # the two kernels agree with each other under the same rule
     s2, i2 = fb.search(q_cpu.cuda(), k, normalize_bank=nb, normalize_query=nq, flags=L.FORCE_STREAM)
     ss.compare_topk(s2.cpu().numpy()[:, :kk], i2.cpu().numpy()[:, :kk], truth, k, gap=GAP, rtol=RTOL, atol=ATOL)
