@@ -138,6 +138,8 @@ static int validate(const SearchArgs& a) {
   return DEVQA_OK;
 }
 
+constexpr int kGmaxStride = 160;   // >= SM count, 16-byte multiple
+
 // Side arrays of the filter scan (device), carved out of Scratch::akeys.
 struct FilterSide {
   uint64_t* akeys = nullptr;     // [Q, K'] merged candidates (keys on the upper bound u)
@@ -146,6 +148,7 @@ struct FilterSide {
   float* qerr = nullptr;         // [Q] tc_filter_relerr(dim) * ||query as used||
   uint32_t* seed_u = nullptr;    // [Q padded] k-th best upper bound of the prefix sample (score codes)
   uint32_t* lostu = nullptr;     // [grid, Q] per-CTA bound on the rows its full list lost
+  uint32_t* gmax = nullptr;      // [Q padded, kGmaxStride] per-CTA best upper bound per query (threshold exchange)
   int kp = 0;                    // K': capacity of the merged candidate list
   int n_lists = 0;               // out: per-CTA lists per query
 };
@@ -187,7 +190,10 @@ static int tc_pipeline(Scratch* s, const SearchArgs& a, int mode, FilterSide* si
   p.cand = s->cand; p.need = need;
   if (side) {
     p.qerr = side->qerr; p.k_true = a.top_k; p.lostu = side->lostu; p.bank_max_sumsq = a.max_sumsq;
+    p.gmax = side->gmax; p.gmax_stride = kGmaxStride;
     side->n_lists = grid;
+    DEVQA_REQUIRE(grid <= kGmaxStride, "more CTAs per pass than the threshold exchange holds");
+    DEVQA_CUDA(cudaMemsetAsync(side->gmax, 0, size_t(q_pad) * kGmaxStride * 4, stream));
   }
 
   const bool prof = s->profiling && !need && s->prof_used < Scratch::kProfSlots;
@@ -198,10 +204,14 @@ static int tc_pipeline(Scratch* s, const SearchArgs& a, int mode, FilterSide* si
   // Threshold seeding: scan a prefix sample of the bank (one tile per CTA) first; the k-th best score of a
   // SUBSET is a lower bound of the k-th best of the whole bank, so the main scan starts with tight
   // thresholds in every CTA instead of each CTA re-learning them (k ln(n/k) list insertions each).
-  const bool seed = tiles >= 8 * int64_t(ctas_per_pass) && !(a.flags & (1u << 21)) && !need;
+  // (the filter variant exchanges thresholds between CTAs while it runs and needs no seeding)
+  const bool seed = tiles >= 8 * int64_t(ctas_per_pass) && !(a.flags & (1u << 21)) && !need && (!side || (a.flags >> 24) & 0xfu);
   if (seed) {
     ScanParams pre = p;
-    pre.n_rows = int64_t(ctas_per_pass) * 128;
+    int seed_tiles = int((a.flags >> 24) & 0xfu);           // undocumented: sample tiles per CTA (benchmark sweeps)
+    if (seed_tiles == 0) seed_tiles = 1;
+    pre.n_rows = int64_t(ctas_per_pass) * 128 * seed_tiles;
+    if (pre.n_rows > a.n_rows) pre.n_rows = a.n_rows;
     for (int pass = 0; pass < n_passes; pass += side_by) {
       const int now = n_passes - pass < side_by ? n_passes - pass : side_by;
       pre.q0 = int32_t(pass * qp);
@@ -285,7 +295,7 @@ static int run_search(Scratch* s, const SearchArgs& a, uint64_t* out_keys, float
       }
       const size_t nq = size_t(ac.n_queries), nq_pad = (nq + 127) / 128 * 128;
       if ((rc = grow(reinterpret_cast<void**>(&s->akeys), &s->akeys_bytes,
-                     nq * kp * 8 + nq * 12 + nq_pad * 4 + size_t(s->sm_count) * nq * 4, false)))
+                     nq * kp * 8 + nq * 12 + nq_pad * 4 + size_t(s->sm_count) * nq * 4 + nq_pad * kGmaxStride * 4, false)))
         return rc;
       FilterSide side;
       side.kp = kp;
@@ -295,6 +305,7 @@ static int run_search(Scratch* s, const SearchArgs& a, uint64_t* out_keys, float
       side.qerr = side.qinv + nq;
       side.seed_u = reinterpret_cast<uint32_t*>(side.qerr + nq);
       side.lostu = side.seed_u + nq_pad;
+      side.gmax = side.lostu + size_t(s->sm_count) * nq;
       if ((rc = tc_pipeline(s, ac, kTcTf32x1, &side, nullptr, nullptr, nullptr, nullptr, stream))) return rc;
       if (a.flags & DEVQA_DEBUG_FILTER_ONLY) {                           // tests: the filter's own upper bounds
         if ((rc = merge_lists_launch(side.akeys, 1, ac.n_queries, kp, kp, a.top_k, ok, os, oi, stream))) return rc;

@@ -30,6 +30,8 @@ struct ScanParams {
   const uint32_t* bank_max_sumsq;   // un-normalised scores: max ||row||^2 over the bank (float bits)
   int32_t k_true;          // caller's top_k (the lists keep kcap entries)
   uint32_t* lostu;         // [grid, n_queries] out: bound on the rows each CTA's full list lost (score code, 0 = none)
+  uint32_t* gmax;          // [q_pad, gmax_stride] zeroed scratch: each CTA's best upper bound per query (score codes)
+  int32_t gmax_stride;
 };
 
 size_t scan_stream_smem_bytes(int64_t dim, int nv, int qt, int kcap);

@@ -76,6 +76,7 @@ constexpr int kNormRing = 8;
 constexpr int kMaxStages = 8;
 constexpr int kPrefetchAhead = 12;                  // bank k-blocks pulled into L2 ahead of the smem ring
 constexpr int kSetKBlocks = 32;
+constexpr int kHitCap = 2048;                        // filter epilogue: hit queue entries (>= 128 rows x 16 queries)
 // undocumented debugging bits of `flags` (performance bisection only; results are wrong when set)
 constexpr unsigned kDbgNoInsert = 1u << 16, kDbgNoSplit = 1u << 17, kDbgNoMma2 = 1u << 18, kDbgNoQueryTma = 1u << 19, kDbgNoPrefetch = 1u << 20;                     // k-blocks (of 32 columns) accumulated inside the tensor core
 
@@ -252,6 +253,8 @@ struct TcParams {
   const uint32_t* bank_max_sumsq;   // un-normalised scores: max ||row||^2 of the bank (float bits)
   int32_t k_true;          // the caller's top_k (lists keep kcap entries; T comes from entry k_true - 1)
   uint32_t* lostu;         // [grid, n_queries] out: score code bounding every row this CTA's full list lost (0 = none)
+  uint32_t* gmax;          // [q_pad, gmax_stride] score code of each CTA's best upper bound per query (0 = none yet)
+  int32_t gmax_stride;
   uint32_t* gthr;          // [n_queries] shared lower bounds of the k-th score (monotone score codes, 0 = none)
   IdMap idmap;
   long long* trace;        // optional [16][256] clock64 samples of CTA 0's roles (devqa_debug_tc_trace)
@@ -273,8 +276,8 @@ __host__ __device__ inline SmemLayout tc_layout(int stages, int qp, int kcap, in
   L.a_raw = off; off += uint32_t(stages) * kATileBytes;
   L.bq = off;    off += uint32_t(stages) * uint32_t(b_parts * qp) * 128;     // [parts*qp rows x 128 B], 1024-aligned since qp % 16 == 0
   L.lists = off; off += uint32_t(qp) * kcap * 8;
-  L.thr = off;   off += uint32_t(qp) * 4;
-  L.scratch = off; off += uint32_t(qp < 32 ? qp : 32) * kTileRows * 4;   // score tile [HQ][128]
+  L.thr = off;   off += uint32_t(qp) * 16 + 16;                          // filter: eq / threshold / lost / service bound per query + counters
+  L.scratch = off; off += b_parts == 1 ? kHitCap * 8 : uint32_t(qp < 32 ? qp : 32) * kTileRows * 4;   // score tile [HQ][128] / hit queue
   L.norms = off; off += kNormRing * kTileRows * 4;
   off = (off + 7) & ~7u;
   L.bars = off;  off += (3 * kMaxStages + 4) * 8;
@@ -289,10 +292,8 @@ __host__ __device__ inline SmemLayout tc_layout(int stages, int qp, int kcap, in
 // UMMA operand fetches, so every dependent LDS/STS costs hundreds of cycles): for the common capacity 32
 // the list is pulled into registers once (one key per lane), all inserts are shuffles, and it is written
 // back once.
-// Returns two floats packed into 64 bits: high = score of entry top_k - 1 (the list's admission threshold), low =
-// score of entry k_true - 1 (filter variant: the k-th best upper bound, from which T is derived; equal otherwise).
-__device__ __noinline__ uint64_t epilogue_insert_query(uint64_t* list, int kcap, int top_k, int k_true, const float* tile_row, float th,
-                                                       uint32_t rowmask, int64_t row0, IdMap idmap, int lane) {
+__device__ __noinline__ float epilogue_insert_query(uint64_t* list, int kcap, int top_k, const float* tile_row, float th,
+                                                    uint32_t rowmask, int64_t row0, IdMap idmap, int lane) {
   const float4 sc = *reinterpret_cast<const float4*>(tile_row + lane * 4);
   const uint32_t bits = ((!(sc.x < th) ? 1u : 0u) | (!(sc.y < th) ? 2u : 0u) | (!(sc.z < th) ? 4u : 0u) | (!(sc.w < th) ? 8u : 0u)) & rowmask;
   uint64_t mylist = kcap == 32 ? list[lane] : 0ull;
@@ -324,19 +325,250 @@ __device__ __noinline__ uint64_t epilogue_insert_query(uint64_t* list, int kcap,
       }
     }
   }
-  uint64_t kth, ktrue;
+  uint64_t kth;
   if (kcap == 32) {
     list[lane] = mylist;
     kth = shfl_u64(mylist, top_k - 1);
-    ktrue = shfl_u64(mylist, k_true - 1);
   } else {
     __syncwarp();
     kth = list[top_k - 1];
-    ktrue = list[k_true - 1];
   }
-  const float a = kth == kEmptyKey ? -INFINITY : key_score(kth);
-  const float b = ktrue == kEmptyKey ? -INFINITY : key_score(ktrue);
-  return (uint64_t(__float_as_uint(a)) << 32) | uint64_t(__float_as_uint(b));
+  return kth == kEmptyKey ? -INFINITY : key_score(kth);
+}
+
+// ---- filter variant: epilogue ------------------------------------------------------------------------------
+// Thread <-> TMEM lane <-> bank row.  Each thread walks its row's QP accumulators (16 per tcgen05.ld), forms the
+// upper bound u = s~ + E and compares it with that query's threshold (shared memory, broadcast reads).  Nothing
+// is stored for the overwhelming majority that fail; the rare survivors are pushed into a shared-memory hit queue
+// and, after ONE 128-thread barrier per tile, inserted into the per-query lists by the warp that owns the query
+// (q % 4).  The previous epilogue wrote every score to shared memory and re-read it (64 KB per tile at 128
+// queries, on a shared-memory pipe that TMA and UMMA already keep ~90% busy): 93 cycles per query and tile
+// measured against ~35 here.  A tile that overflows the queue (cold start: no thresholds yet) is redone in
+// segments of 16 queries through a dense [16][128] score tile and the burst-capable list insertion of the
+// other modes.
+//
+// Thresholds.  A row can be dropped when u < T for any lower bound T of the exact k-th best score.  Locally,
+// T = (the list's k-th best u) - 2E.  Globally: every CTA publishes the score code of its best u per query
+// (gmax); if k CTAs each hold a row with u >= x then k rows have s >= x - 2E, so T = (k-th largest of the
+// CTAs' bests) - 2E.  Because the global top-k rows sit in (almost) distinct CTAs this is within a few rows of
+// the ideal "k-th best of everything seen so far", whereas the best LOCAL bound only knows 1/148 of the rows
+// (measured: 0.29 -> <0.01 list insertions per query and tile).  The otherwise idle warps 3-7 run this
+// selection continuously (service warps) and hand the result to the epilogue through shared memory.
+struct FiltState {            // per-query state in shared memory, [QP] each
+  float* eq;                  // tc_filter_relerr * ||query||
+  float* thr;                 // admission threshold on u: max(lower bounds T of the exact k-th best, full list's last entry)
+  float* lost;                // upper bound of every row a full list turned away while its last entry was binding
+  float* thr_ext;             // T from the service warps (written by them only)
+  uint32_t* qn;               // [2] hit counters (alternating per segment), [2] = scan finished
+  float* hit_u;               // [kHitCap]   (dense mode: score tile [16][128])
+  uint32_t* hit_id;           // [kHitCap] query << 8 | row in tile
+};
+
+// After the list of query j changed: derive the local bound, keep the lost-rows bound, publish the CTA's best.
+__device__ __forceinline__ void filt_after_insert(const TcParams& p, const FiltState& st, int j, int q0, int cta, float maxn,
+                                                  uint64_t best, uint64_t ktrue, uint64_t kth) {
+  float th = st.thr[j];
+  // k-th best upper bound - 2E  <=  k-th best exact score of these rows  <=  that of the bank
+  if (ktrue != kEmptyKey) {
+    const float t = key_score(ktrue) - 2.f * st.eq[j] * maxn;
+    if (t > th) th = t;
+  }
+  // A full list admits nothing below its last entry.  Rows it turns away while that entry is the binding
+  // threshold (at or above T) are LOST, not proven irrelevant: remember their upper bound for refine.cu.
+  if (kth != kEmptyKey) {
+    const float l = key_score(kth);
+    if (l >= th) { th = l; st.lost[j] = l; }
+  }
+  st.thr[j] = th;
+  if (p.gmax) p.gmax[size_t(q0 + j) * p.gmax_stride + cta] = uint32_t(best >> 32);   // single writer per slot
+}
+
+template <int QP>
+__device__ __forceinline__ void filt_epilogue(const TcParams& p, const FiltState st, uint64_t* lists, const float* norms,
+                                              bool norm_warps, uint32_t tmem_base, uint64_t* tmem_full, uint64_t* tmem_empty,
+                                              int tile0, int tile_step, int q0, int nq_pass, float maxn, int e, int lane) {
+  const int row_in_tile = e * 32 + lane;
+  const bool no_insert = (p.flags & kDbgNoInsert) != 0;
+  const bool dot_mode = !(p.flags & DEVQA_NORMALIZE_BANK);          // E scales with ||row||
+  uint32_t lt = 0, unit = 0, seg_idx = 0;
+  int slow_calls = 0;
+  for (int tile = tile0; tile < p.n_tiles; tile += tile_step, ++lt, ++unit) {
+    const int a = unit & 1;
+    mbar_wait(&tmem_full[a], (unit >> 1) & 1);
+    tc_fence_after();
+    if (e == 0 && lane == 0) trace_at(p, 6, unit);
+    const int64_t grow = int64_t(tile) * kTileRows + row_in_tile;
+    const bool row_live = grow < p.n_rows && !no_insert;
+    float inv = 1.f, rowfac = 1.f;
+    {
+      const float ssq = norm_warps ? norms[(lt % kNormRing) * kTileRows + row_in_tile] : (grow < p.n_rows ? p.row_sumsq[grow] : 1.f);
+      const float nrm = sqrtf(ssq);
+      if (dot_mode) rowfac = nrm;
+      else inv = 1.0f / ((p.flags & DEVQA_NOEPS) ? nrm : fmaxf(nrm, kNormEps));
+    }
+    const uint32_t taddr = tmem_base + uint32_t(a) * QP + (uint32_t(e * 32) << 16);
+    bool dense = false;                                               // after a queue overflow: 16 queries at a time
+    int seg = QP;
+    for (int jb = 0; jb < QP; jb += seg, ++seg_idx) {
+      uint32_t* const qn = st.qn + (seg_idx & 1);
+      // ---- scan ----
+#pragma unroll 1
+      for (int c = jb; c < jb + seg; c += 16) {
+        uint32_t d[16];
+        tmem_ld<16>(taddr + uint32_t(c), d);
+        tmem_ld_wait();
+        float u[16];
+        uint32_t mask = 0;
+#pragma unroll
+        for (int i4 = 0; i4 < 4; ++i4) {
+          const float4 eq4 = *reinterpret_cast<const float4*>(st.eq + c + 4 * i4);
+          const float4 th4 = *reinterpret_cast<const float4*>(st.thr + c + 4 * i4);
+          u[4 * i4 + 0] = fmaf(__uint_as_float(d[4 * i4 + 0]), inv, eq4.x * rowfac);
+          u[4 * i4 + 1] = fmaf(__uint_as_float(d[4 * i4 + 1]), inv, eq4.y * rowfac);
+          u[4 * i4 + 2] = fmaf(__uint_as_float(d[4 * i4 + 2]), inv, eq4.z * rowfac);
+          u[4 * i4 + 3] = fmaf(__uint_as_float(d[4 * i4 + 3]), inv, eq4.w * rowfac);
+          mask |= (!(u[4 * i4 + 0] < th4.x) ? 1u : 0u) << (4 * i4 + 0);   // NaN passes, like torch.topk ranks it first
+          mask |= (!(u[4 * i4 + 1] < th4.y) ? 1u : 0u) << (4 * i4 + 1);
+          mask |= (!(u[4 * i4 + 2] < th4.z) ? 1u : 0u) << (4 * i4 + 2);
+          mask |= (!(u[4 * i4 + 3] < th4.w) ? 1u : 0u) << (4 * i4 + 3);
+        }
+        if (!row_live) mask = 0u;
+        if (dense) {                                                    // the segment's scores as a [16][128] tile
+#pragma unroll
+          for (int i = 0; i < 16; ++i) st.hit_u[i * kTileRows + row_in_tile] = u[i];
+        } else if (__any_sync(kFull, mask != 0u)) {                     // rare
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            if ((mask >> i) & 1u) {
+              const uint32_t idx = atomicAdd(qn, 1u);
+              if (idx < uint32_t(kHitCap)) { st.hit_u[idx] = u[i]; st.hit_id[idx] = (uint32_t(c + i) << 8) | uint32_t(row_in_tile); }
+            }
+          }
+        }
+      }
+      const bool last_seg = jb + seg >= QP;
+      tc_fence_before();
+      epilogue_barrier();                                               // every hit of the segment is visible
+      const uint32_t n = dense ? 0u : *qn;
+      if (e == 0 && lane == 0) st.qn[(seg_idx & 1) ^ 1] = 0u;           // the other counter: idle until the next scan
+      if (n > uint32_t(kHitCap)) {                                      // overflow (cold start): redo the tile densely
+        dense = true;
+        seg = 16;
+        jb = -16;
+        epilogue_barrier();
+        continue;
+      }
+      if (last_seg) mbar_arrive(&tmem_empty[a]);                        // this thread's TMEM reads of the buffer are done
+      if (dense) {
+        // ---- dense segment: warp e owns queries jb + e, jb + 4 + e, ... ----
+        const int64_t row0 = int64_t(tile) * kTileRows + lane * 4;
+        uint32_t rowmask = 0;
+#pragma unroll
+        for (int t = 0; t < 4; ++t) rowmask |= (row0 + t < p.n_rows ? 1u : 0u) << t;
+        if (no_insert) rowmask = 0;
+#pragma unroll 1
+        for (int i = e; i < 16; i += 4) {
+          const int j = jb + i;
+          if (j >= nq_pass) break;
+          const float th = st.thr[j];
+          const float4 sc = *reinterpret_cast<const float4*>(st.hit_u + i * kTileRows + lane * 4);
+          const bool hit = (!(sc.x < th) && (rowmask & 1u)) || (!(sc.y < th) && (rowmask & 2u)) ||
+                           (!(sc.z < th) && (rowmask & 4u)) || (!(sc.w < th) && (rowmask & 8u));
+          if (!__any_sync(kFull, hit)) continue;
+          ++slow_calls;
+          uint64_t* list = lists + size_t(j) * p.kcap;
+          epilogue_insert_query(list, p.kcap, p.top_k, st.hit_u + i * kTileRows, th, rowmask, row0, p.idmap, lane);
+          __syncwarp();
+          if (lane == 0) filt_after_insert(p, st, j, q0, tile0, maxn, list[0], list[p.k_true - 1], list[p.top_k - 1]);
+          __syncwarp();
+        }
+      } else {
+        // ---- drain: warp e owns the queries with q % 4 == e ----
+        for (uint32_t h = 0; h < n; ++h) {
+          const uint32_t id = st.hit_id[h];
+          const int j = int(id >> 8);
+          if ((j & 3) != e) continue;                                   // warp-uniform
+          const float uu = st.hit_u[h];
+          if (uu < st.thr[j]) continue;                                 // the threshold has risen since the push
+          ++slow_calls;
+          const uint64_t key = pack_key(uu, uint32_t(p.idmap(int64_t(tile) * kTileRows + int64_t(id & 0xffu))));
+          uint64_t* list = lists + size_t(j) * p.kcap;
+          uint64_t best, kth, ktrue;
+          if (p.kcap == 32) {
+            uint64_t mine = list[lane];
+            const int pos = __popc(__ballot_sync(kFull, mine > key));
+            const uint64_t up = shfl_u64(mine, lane > 0 ? lane - 1 : 0);
+            if (pos < p.top_k) mine = lane > pos ? up : (lane == pos ? key : mine);
+            list[lane] = mine;
+            best = shfl_u64(mine, 0);
+            kth = shfl_u64(mine, p.top_k - 1);
+            ktrue = shfl_u64(mine, p.k_true - 1);
+          } else {
+            warp_list_insert(list, p.kcap, p.top_k, key, lane);
+            __syncwarp();
+            best = list[0];
+            kth = list[p.top_k - 1];
+            ktrue = list[p.k_true - 1];
+          }
+          if (lane == 0) filt_after_insert(p, st, j, q0, tile0, maxn, best, ktrue, kth);
+          __syncwarp();
+        }
+      }
+      // ---- pick up the service warps' bounds (own queries only: nobody else writes thr) ----
+      if (last_seg) {
+        const int j = 4 * lane + e;
+        if (j < nq_pass) st.thr[j] = fmaxf(st.thr[j], st.thr_ext[j]);
+      }
+      epilogue_barrier();                                               // thresholds visible, queue reusable
+    }
+    if (e == 0 && lane == 0) trace_at(p, 7, unit);
+#ifdef DEVQA_TC_TRACE
+    if (e == 0 && lane == 0 && p.trace && blockIdx.x == 0 && unit < 256) { p.trace[8 * 256 + unit] = slow_calls; slow_calls = 0; }
+#endif
+  }
+  if (e == 0 && lane == 0) *reinterpret_cast<volatile uint32_t*>(st.qn + 2) = 1u;   // service warps: stop
+  // what this CTA's lists lost, for the completeness proof
+  for (int j = e * 32 + lane; j < nq_pass; j += 128) {
+    const float l = st.lost[j];
+    p.lostu[size_t(tile0) * p.n_queries + q0 + j] = l == -INFINITY ? 0u : score_code(l);
+  }
+}
+
+// Service warp: for its share of the queries, T = (k-th largest of the CTAs' best upper bounds) - 2E, over and over.
+__device__ __forceinline__ void filt_service(const TcParams& p, const FiltState st, int q0, int nq_pass, int n_ctas, float maxn,
+                                             int sid, int nserv, int lane) {
+  volatile uint32_t* const done = st.qn + 2;
+  const int k = p.k_true;
+  if (n_ctas < k || !p.gmax) return;                                  // the bound needs k distinct CTAs
+  volatile float* const thr_ext = st.thr_ext;
+  while (!*done) {
+    for (int j = sid; j < nq_pass && !*done; j += nserv) {
+      const uint32_t* src = p.gmax + size_t(q0 + j) * p.gmax_stride;
+      uint32_t v[5];
+#pragma unroll
+      for (int i = 0; i < 5; ++i) {
+        const int c = lane + 32 * i;
+        v[i] = 0u;
+        if (c < n_ctas) asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v[i]) : "l"(src + c));
+      }
+      // largest x (to 22 bits) with at least k values >= x: a lower bound of the k-th largest
+      uint32_t x = 0u;
+#pragma unroll 1
+      for (int bit = 31; bit >= 10; --bit) {
+        const uint32_t cand = x | (1u << bit);
+        int cnt = 0;
+#pragma unroll
+        for (int i = 0; i < 5; ++i) cnt += v[i] >= cand ? 1 : 0;
+        cnt = __reduce_add_sync(kFull, cnt);
+        if (cnt >= k) x = cand;
+      }
+      if (lane == 0 && x != 0u) {
+        const float t = code_score(x) - 2.f * st.eq[j] * maxn;
+        if (t > thr_ext[j]) thr_ext[j] = t;
+      }
+    }
+    __nanosleep(2000);
+  }
 }
 
 template <int QP, bool MULTI, int MODE>
@@ -377,6 +609,28 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap bank_map, const __grid_consta
 
   // ---- one-time setup ------------------------------------------------------------------------
   for (int i = threadIdx.x; i < QP * p.kcap; i += kTcThreads) lists[i] = kEmptyKey;
+  FiltState st{};
+  float maxn = 1.f;                                      // un-normalised scores: E scales with ||row|| <= maxn
+  if constexpr (FILT) {
+    float* fs = reinterpret_cast<float*>(smem + L.thr);
+    st.eq = fs; st.thr = fs + QP; st.lost = fs + 2 * QP; st.thr_ext = fs + 3 * QP;
+    st.qn = reinterpret_cast<uint32_t*>(fs + 4 * QP);
+    st.hit_u = reinterpret_cast<float*>(smem + L.scratch);
+    st.hit_id = reinterpret_cast<uint32_t*>(smem + L.scratch) + kHitCap;
+    if (!(p.flags & DEVQA_NORMALIZE_BANK)) maxn = sqrtf(__uint_as_float(*p.bank_max_sumsq));
+    for (int j = threadIdx.x; j < QP; j += kTcThreads) {
+      const bool live = j < nq_pass;
+      const float eq = live ? p.qerr[q0 + j] : 0.f;
+      float t = live ? -INFINITY : INFINITY;                          // dead queries never hit
+      const uint32_t code = (live && p.seed_u) ? p.seed_u[q0 + j] : 0u;
+      if (code != 0u) {
+        const float ts = code_score(code) - 2.f * eq * maxn;          // lower bound of the exact k-th best score
+        if (ts > t) t = ts;
+      }
+      st.eq[j] = eq; st.thr[j] = t; st.lost[j] = -INFINITY; st.thr_ext[j] = -INFINITY;
+    }
+    if (threadIdx.x < 4) st.qn[threadIdx.x] = 0u;
+  }
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&bank_map);
   }
@@ -572,6 +826,14 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap bank_map, const __grid_consta
         if (lane == 0) atomicMax(p.max_sumsq, __float_as_uint(max_ss));   // non-negative floats order like their bits
       }
     }
+  } else if (FILT && (warp == 3 || (warp >= 4 && warp < 8))) {
+    // ===== service warps, filter variant (warps 4-7 only when they are not busy with row norms) =====
+    if (warp == 3) filt_service(p, st, q0, nq_pass, tile_step, maxn, 0, norm_warps ? 1 : 5, lane);
+    else filt_service(p, st, q0, nq_pass, tile_step, maxn, warp - 3, 5, lane);
+  } else if (warp >= 8 && FILT) {
+    // ===== epilogue warps, filter variant: scan + hit queue (filt_epilogue) =====
+    filt_epilogue<QP>(p, st, lists, norms, norm_warps, tmem_base, tmem_full, tmem_empty, tile0, tile_step, q0, nq_pass, maxn,
+                      warp - 8, lane);
   } else if (warp >= 8) {
     // ===== epilogue warps =====
     // Phase A: thread <-> TMEM lane <-> bank row: sum the three accumulator parts, scale by 1/||row||
@@ -593,24 +855,6 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap bank_map, const __grid_consta
     const int own_j = (lane / NQW_) * HQ + e * NQW_ + lane % NQW_;
     const bool own_live = lane < QP / 4 && own_j < nq_pass;
     uint32_t* const own_gthr = p.gthr + q0 + (own_live ? own_j : 0);
-    // filter variant: per-query error scale in shared memory (phase A) and for the owned query (thresholds)
-    float* const eqs = reinterpret_cast<float*>(smem + L.thr);        // [QP]
-    float eq_own = 0.f, maxn = 1.f;
-    float lost_reg = -INFINITY;                          // upper bound of every row the owned query's full list turned away
-    const bool dot_mode = FILT && !(p.flags & DEVQA_NORMALIZE_BANK);  // E scales with ||row||
-    if constexpr (FILT) {
-      for (int j = threadIdx.x - 256; j < QP; j += 128) eqs[j] = j < nq_pass ? p.qerr[q0 + j] : 0.f;
-      if (dot_mode) maxn = sqrtf(__uint_as_float(*p.bank_max_sumsq));
-      if (own_live) {
-        eq_own = p.qerr[q0 + own_j];
-        const uint32_t code = p.seed_u ? p.seed_u[q0 + own_j] : 0u;
-        if (code != 0u) {
-          const float t = code_score(code) - 2.f * eq_own * maxn;     // lower bound of the exact k-th best score
-          if (t > thr_reg) thr_reg = t;
-        }
-      }
-      epilogue_barrier();
-    }
     for (int tile = tile0; tile < p.n_tiles; tile += tile_step, ++lt) {
       // pick up the bounds other CTAs have published (one relaxed load per owned query per tile)
       if (own_live) {
@@ -625,14 +869,13 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap bank_map, const __grid_consta
         mbar_wait(&tmem_full[a], (unit >> 1) & 1);
         tc_fence_after();
         if (e == 0 && lane == 0) trace_at(p, 6, unit);
-        float inv = 1.f, rowfac = 1.f;                      // rowfac: ||row|| when E scales with it
-        if (last && ((p.flags & DEVQA_NORMALIZE_BANK) || dot_mode)) {
+        float inv = 1.f;
+        if (last && (p.flags & DEVQA_NORMALIZE_BANK)) {
           const int64_t grow = int64_t(tile) * kTileRows + row_in_tile;
           const float ssq = norm_warps ? norms[(lt % kNormRing) * kTileRows + row_in_tile]
                                        : (grow < p.n_rows ? p.row_sumsq[grow] : 1.f);
           const float nrm = sqrtf(ssq);
-          if (dot_mode) rowfac = nrm;
-          else inv = 1.0f / ((p.flags & DEVQA_NOEPS) ? nrm : fmaxf(nrm, kNormEps));
+          inv = 1.0f / ((p.flags & DEVQA_NOEPS) ? nrm : fmaxf(nrm, kNormEps));
         }
         const uint32_t taddr = tmem_base + uint32_t(a) * kAccCols + (uint32_t(e * 32) << 16);
 #pragma unroll (MULTI ? HALVES : 1)
@@ -641,27 +884,19 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap bank_map, const __grid_consta
 #pragma unroll
           for (int c = 0; c < HQ / 16; ++c) {
             const int j0 = h * HQ + c * 16;
-            uint32_t d1[16], d2[FILT ? 1 : 16], d3[FILT ? 1 : 16];
+            uint32_t d1[16], d2[16], d3[16];
             tmem_ld<16>(taddr + uint32_t(j0), d1);
-            if constexpr (!FILT) {
-              tmem_ld<16>(taddr + uint32_t(QP + j0), d2);
-              tmem_ld<16>(taddr + uint32_t(2 * QP + j0), d3);
-            }
+            tmem_ld<16>(taddr + uint32_t(QP + j0), d2);
+            tmem_ld<16>(taddr + uint32_t(2 * QP + j0), d3);
             tmem_ld_wait();
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
-              float v;
-              if constexpr (FILT) v = __uint_as_float(d1[i]);
-              else v = (__uint_as_float(d2[i]) + __uint_as_float(d3[i])) + __uint_as_float(d1[i]);
+              float v = (__uint_as_float(d2[i]) + __uint_as_float(d3[i])) + __uint_as_float(d1[i]);
               if constexpr (MULTI) {
                 v = set == 0 ? v : acc[j0 + i] + v;
                 acc[j0 + i] = v;
               }
-              if constexpr (FILT) {                         // upper bound of the exact score
-                if (last) stile[(c * 16 + i) * kTileRows + row_in_tile] = fmaf(v, inv, eqs[j0 + i] * rowfac);
-              } else {
-                if (last) stile[(c * 16 + i) * kTileRows + row_in_tile] = v * inv;
-              }
+              if (last) stile[(c * 16 + i) * kTileRows + row_in_tile] = v * inv;
             }
           }
           if (h == HALVES - 1) {                          // every TMEM read of this buffer has completed
@@ -697,19 +932,9 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap bank_map, const __grid_consta
             if (j >= nq_pass) break;
             const int oi = h * NQW + i;                   // index among the queries this warp owns
             const float th = __shfl_sync(kFull, thr_reg, oi);
-            const uint64_t nt2 = epilogue_insert_query(lists + size_t(j) * p.kcap, p.kcap, p.top_k, FILT ? p.k_true : p.top_k,
-                                                       stile + (e * NQW + i) * kTileRows, th, rowmask, row0, p.idmap, lane);
-            const float nt = __uint_as_float(uint32_t(nt2 >> 32));
-            if constexpr (FILT) {
-              if (lane == oi) {
-                // k-th best upper bound - 2E  <=  k-th best exact score of these rows  <=  that of the bank
-                const float t = __uint_as_float(uint32_t(nt2)) - 2.f * eq_own * maxn;
-                if (t > thr_reg) { thr_reg = t; atomicMax(own_gthr, score_code(t)); }
-                // A full list admits nothing below its last entry.  Rows it turns away while that entry is the
-                // binding threshold (above T) are LOST, not proven irrelevant: remember their upper bound.
-                if (nt > thr_reg) { thr_reg = nt; lost_reg = nt; }
-              }
-            } else if (lane == oi && nt > thr_reg) {        // publish: a lower bound of the global k-th score
+            const float nt = epilogue_insert_query(lists + size_t(j) * p.kcap, p.kcap, p.top_k,
+                                                   stile + (e * NQW + i) * kTileRows, th, rowmask, row0, p.idmap, lane);
+            if (lane == oi && nt > thr_reg) {               // publish: a lower bound of the global k-th score
               thr_reg = nt;
               atomicMax(own_gthr, score_code(nt));
             }
@@ -721,9 +946,6 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap bank_map, const __grid_consta
         if (e == 0 && lane == 0 && p.trace && blockIdx.x == 0 && unit < 256) { p.trace[8 * 256 + unit] = slow_calls; slow_calls = 0; }
 #endif
       }
-    }
-    if constexpr (FILT) {
-      if (own_live) p.lostu[size_t(tile0) * p.n_queries + q0 + own_j] = lost_reg == -INFINITY ? 0u : score_code(lost_reg);
     }
   }
 
@@ -977,7 +1199,7 @@ int scan_tc_launch(const ScanParams& sp, int mode, const void* qcat, uint32_t* g
   p.top_k = sp.top_k; p.kcap = sp.kcap; p.stages = stages; p.passes = passes; p.flags = sp.flags;
   p.cand = sp.cand; p.gthr = gthr; p.idmap = sp.idmap; p.row_sumsq = sp.row_sumsq;
   p.max_sumsq = sp.max_sumsq; p.need = sp.need;
-  p.lostu = sp.lostu; p.qerr = sp.qerr; p.seed_u = sp.seed_u; p.bank_max_sumsq = sp.bank_max_sumsq; p.k_true = sp.k_true > 0 ? sp.k_true : sp.top_k;
+  p.gmax = sp.gmax; p.gmax_stride = sp.gmax_stride; p.lostu = sp.lostu; p.qerr = sp.qerr; p.seed_u = sp.seed_u; p.bank_max_sumsq = sp.bank_max_sumsq; p.k_true = sp.k_true > 0 ? sp.k_true : sp.top_k;
   // pass index = q0 / qp; one pass = n_kblocks * parts * qp rows of 128 bytes (32 words)
   p.qcat = static_cast<const float*>(qcat) + size_t(sp.q0 / qp) * size_t(n_kblocks) * parts * qp * 32;
   p.trace = g_tc_trace;

@@ -26,3 +26,15 @@ for r in (6, 7):
 print("slow_calls_w0".ljust(14), " ".join(f"{int(x):7d}" for x in t[8, :24]))
 for r, nm in ((13, "s0_ld_done"), (14, "s0_bits_done"), (9, "step0_body"), (10, "step0_bar"), (11, "step1_bar"), (12, "step2_bar")):
     print(nm.ljust(14), " ".join(f"{int(x) - t0:7d}" if x else "      -" for x in t[r, :24]))
+# summary over all recorded tiles
+import numpy as np
+got, done, slow = t[6].numpy().astype(np.int64), t[7].numpy().astype(np.int64), t[8].numpy()
+m = (got > 0) & (done > 0)
+n_rec = int(m.sum())
+if n_rec > 8:
+    dur = (done - got)[m]
+    per = np.diff(got[m])
+    for lo, hi in ((0, 8), (8, 64), (64, 128), (128, 256)):
+        if lo < n_rec:
+            h = min(hi, n_rec)
+            print(f"tiles {lo:3d}-{h:3d}: epilogue cycles/tile {dur[lo:h].mean():8.0f}  tile period {per[lo:h - 1].mean() if h - 1 > lo else 0:8.0f}  slow calls (warp 0)/tile {slow[lo:h].mean():5.2f}")
