@@ -9,8 +9,8 @@ Workload (named in config.workload): the north-star configuration -- a 10M x 768
 k = 32, Q = 64 queries per search call (the top of config C3's batch range; tcgen05 kernel) --
 row-sharded over the N GPUs (STRONG scaling: the bank is fixed, each GPU scans 10M/N rows).  A
 "step" is one search call: fused normalise + contraction + top-k over the whole bank, (N>1: + one
-all-gather + merge).  "regimes" adds a short sweep over Q = 1, 4, 16, 64 on the same bank so that
-the HBM-bound small-batch kernels are reported next to the headline.
+all-gather + merge).  "regimes" adds a short sweep over Q = 1 ... 4096 on the same bank so that the
+HBM-bound small-batch kernels and the tensor-core large-batch regime (C4) are reported next to the headline.
 
 value  queries/s with queries and bank resident in HBM, CUDA-event timed, max over ranks.
 e2e    the same metric through the host-buffer C-ABI call (numpy queries in, numpy results
@@ -172,18 +172,33 @@ def measured_peak():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def ncu_traffic(a, rows_local):
+def ncu_traffic(a, rows_local, q_per_launch):
     """dram bytes per scan launch from a committed ncu --set full capture of the same shape, else None."""
     path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     try:
         with open(path) as f:
             for rec in json.load(f):
                 if (rec["rows"], rec["dim"], rec["queries"], rec["top_k"], rec["bank_dtype"]) == \
-                        (rows_local, a.dim, a.queries, a.topk, a.bank_dtype):
+                        (rows_local, a.dim, int(q_per_launch), a.topk, a.bank_dtype):
                     return rec["dram_bytes_per_launch"]
     except Exception:                   # noqa: BLE001
         pass
     return None
+
+
+def kernel_label(nq, bank_dtype, topk):
+    """Which scan kernel api.cu selects for this batch (csrc/api.cu run_search)."""
+    if nq <= 4:
+        return "scan_stream_kernel (CUDA cores, 128-bit streaming loads)"
+    if bank_dtype == "fp32" and topk <= 64:
+        return "scan_tc_kernel<TF32x1 filter> (tcgen05/TMEM/TMA) + refine_kernel (exact fp32 re-scoring)"
+    return "scan_tc_kernel<%s> (tcgen05/TMEM/TMA)" % ("3xTF32" if bank_dtype == "fp32" else "bf16x3")
+
+
+def filter_fallbacks(L, C, device):
+    n = C.c_int64()
+    L.check(L.lib().devqa_filter_fallbacks(device, C.byref(n)))
+    return int(n.value)
 
 
 # ---- our arm ------------------------------------------------------------------------------------------------
@@ -239,6 +254,7 @@ def run_ours(a):
     for _ in range(max(a.warmup, 3)):
         out = bank.search(q_dev, a.topk, flags=a.flags)
     barrier()
+    filter_fallbacks(L, C, local_rank)                     # reset the counter
     sampler = ClockSampler(local_rank)
     sampler.start()
     L.check(L.lib().devqa_profile_enable(local_rank, 1))
@@ -264,6 +280,7 @@ def run_ours(a):
     clocks = sampler.summary(t_wall0, t_wall1)
     ms_per_step = ms_total / a.steps
     value = a.queries / (ms_per_step * 1e-3)
+    fallbacks = filter_fallbacks(L, C, local_rank)         # queries the exact 3xTF32 fallback had to redo (timed region)
 
     # ---- end to end through the host-buffer entry point ---------------------------------------
     for _ in range(3):
@@ -284,9 +301,9 @@ def run_ours(a):
     scan_ms_per_launch = scan_ms.value / max(1, scan_launches.value)
     achieved = alg_bytes / (scan_ms_per_launch * 1e-3) / 1e9 if scan_ms_per_launch > 0 else 0.0
     peak, peak_src = measured_peak()
-    kernel_name = "scan_tc_kernel (tcgen05/TMEM/TMA)" if (a.queries > 4 and a.bank_dtype == "fp32") else "scan_stream_kernel (CUDA cores)"
+    kernel_name = kernel_label(a.queries, a.bank_dtype, a.topk)
     roofline = {"bound": "hbm", "kernel": kernel_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": ncu_traffic(a, rows_local), "peak_source": peak_src,
+                "frac": achieved / peak, "traffic": ncu_traffic(a, rows_local, q_per_launch), "peak_source": peak_src,
                 "frac_of_8TBs_nominal": achieved / 8000.0, "alg_bytes_per_launch": alg_bytes,
                 "launch_ms": scan_ms_per_launch, "launches_timed": scan_launches.value,
                 "scan_share_of_step": scan_ms.value / max(1e-9, ev0.elapsed_time(ev1))}
@@ -294,29 +311,37 @@ def run_ours(a):
     # ---- regimes: the same bank at other batch sizes (device-resident, 10 steps each) ----------
     regimes = []
     if not a.no_regimes:
-        for nq in (1, 4, 16, 64):
+        for nq in (1, 4, 16, 64, 128, 1024, 4096):
             gq = torch.Generator().manual_seed(9000 + nq)
             qd = torch.nn.functional.normalize(torch.randn(nq, a.dim, generator=gq), dim=1).to(dev)
-            for _ in range(3):
+            reps = 10 if nq <= 128 else (4 if nq <= 1024 else 2)
+            for _ in range(3 if nq <= 128 else 1):
                 bank.search(qd, a.topk)
             barrier()
+            filter_fallbacks(L, C, local_rank)
             L.check(L.lib().devqa_profile_enable(local_rank, 1))
             r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             r0.record()
-            for _ in range(10):
+            for _ in range(reps):
                 bank.search(qd, a.topk)
             r1.record()
             barrier()
-            ms = max_over_ranks(r0.elapsed_time(r1)) / 10
+            ms = max_over_ranks(r0.elapsed_time(r1)) / reps
             sm, sl, sr = C.c_double(), C.c_int64(), C.c_int64()
             L.check(L.lib().devqa_profile_collect(local_rank, C.byref(sm), C.byref(sl), C.byref(sr)))
             L.check(L.lib().devqa_profile_enable(local_rank, 0))
             scan_ms_call = sm.value / max(1, sr.value)
             gbs = (rows_local * a.dim * esz * (sl.value / max(1, sr.value))) / (scan_ms_call * 1e-3) / 1e9
+            passes = sl.value / max(1, sr.value)
+            # useful flops of the contraction (2*Q*N*D, split / filter overhead not counted), whole job
+            tflops = 2.0 * nq * a.rows * a.dim / (ms * 1e-3) / 1e12
             regimes.append({"queries_per_call": nq, "ms_per_call": ms, "queries_per_s": nq / (ms * 1e-3),
                             "scan_gbs_per_gpu": gbs, "frac_of_measured_hbm": gbs / peak,
-                            "kernel": "tcgen05" if (nq > 4 and a.bank_dtype == "fp32") else "stream",
-                            "bank_passes_per_call": sl.value / max(1, sr.value)})
+                            "useful_tflops": tflops,
+                            "kernel": ("stream" if nq <= 4 else ("tcgen05 TF32 filter + exact re-scoring"
+                                       if a.bank_dtype == "fp32" and a.topk <= 64 else "tcgen05")),
+                            "bank_passes_per_call": passes,
+                            "exact_fallback_queries": filter_fallbacks(L, C, local_rank)})
 
     if rank == 0:
         cpu = None
@@ -328,6 +353,7 @@ def run_ours(a):
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": a.queries * a.dim * 4,
                         "d2h_bytes_per_step": a.queries * a.topk * 12, "matches_device_path": same},
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
+                "exact_fallback_queries": fallbacks,
                 "aggregate_hbm_gbs": (a.rows * a.dim * esz) / (ms_per_step * 1e-3) / 1e9,
                 "aggregate_hbm_frac_of_measured": (a.rows * a.dim * esz) / (ms_per_step * 1e-3) / 1e9 / (peak * world)}
         if regimes:

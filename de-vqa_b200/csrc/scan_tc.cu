@@ -78,7 +78,7 @@ constexpr int kPrefetchAhead = 12;                  // bank k-blocks pulled into
 constexpr int kSetKBlocks = 32;
 constexpr int kHitCap = 2048;                        // filter epilogue: hit queue entries (>= 128 rows x 16 queries)
 // undocumented debugging bits of `flags` (performance bisection only; results are wrong when set)
-constexpr unsigned kDbgNoInsert = 1u << 16, kDbgNoSplit = 1u << 17, kDbgNoMma2 = 1u << 18, kDbgNoQueryTma = 1u << 19, kDbgNoPrefetch = 1u << 20;                     // k-blocks (of 32 columns) accumulated inside the tensor core
+constexpr unsigned kDbgNoInsert = 1u << 16, kDbgNoSplit = 1u << 17, kDbgNoMma2 = 1u << 18, kDbgNoQueryTma = 1u << 19, kDbgNoPrefetch = 1u << 20, kDbgNoBoot = 1u << 23;                     // k-blocks (of 32 columns) accumulated inside the tensor core
 
 // ---- PTX wrappers ---------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return uint32_t(__cvta_generic_to_shared(p)); }
@@ -386,13 +386,20 @@ __device__ __forceinline__ void filt_after_insert(const TcParams& p, const FiltS
 template <int QP>
 __device__ __forceinline__ void filt_epilogue(const TcParams& p, const FiltState st, uint64_t* lists, const float* norms,
                                               bool norm_warps, uint32_t tmem_base, uint64_t* tmem_full, uint64_t* tmem_empty,
-                                              int tile0, int tile_step, int q0, int nq_pass, float maxn, int e, int lane) {
+                                              int tile0, int tile_step, int n_my, int boot, int q0, int nq_pass, float maxn,
+                                              int e, int lane) {
   const int row_in_tile = e * 32 + lane;
   const bool no_insert = (p.flags & kDbgNoInsert) != 0;
   const bool dot_mode = !(p.flags & DEVQA_NORMALIZE_BANK);          // E scales with ||row||
   uint32_t lt = 0, unit = 0, seg_idx = 0;
   int slow_calls = 0;
-  for (int tile = tile0; tile < p.n_tiles; tile += tile_step, ++lt, ++unit) {
+  uint32_t* const best_s = st.hit_id;                                // bootstrap tiles: best score code per query
+  if (boot) {
+    for (int j = e * 32 + lane; j < QP; j += 128) best_s[j] = 0u;
+    epilogue_barrier();
+  }
+  for (int it = 0; it < n_my + boot; ++it, ++lt, ++unit) {
+    const int tile = tile0 + (it < n_my ? it : it - n_my) * tile_step;
     const int a = unit & 1;
     mbar_wait(&tmem_full[a], (unit >> 1) & 1);
     tc_fence_after();
@@ -407,6 +414,43 @@ __device__ __forceinline__ void filt_epilogue(const TcParams& p, const FiltState
       else inv = 1.0f / ((p.flags & DEVQA_NOEPS) ? nrm : fmaxf(nrm, kNormEps));
     }
     const uint32_t taddr = tmem_base + uint32_t(a) * QP + (uint32_t(e * 32) << 16);
+    if (it < boot) {
+      // ---- bootstrap visit: only each query's best upper bound in this tile, for the threshold exchange ----
+#pragma unroll 1
+      for (int c = 0; c < QP; c += 16) {
+        uint32_t d[16];
+        tmem_ld<16>(taddr + uint32_t(c), d);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i4 = 0; i4 < 4; ++i4) {
+          const float4 eq4 = *reinterpret_cast<const float4*>(st.eq + c + 4 * i4);
+          const float eqv[4] = {eq4.x, eq4.y, eq4.z, eq4.w};
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            const float uu = fmaf(__uint_as_float(d[4 * i4 + t]), inv, eqv[t] * rowfac);
+            const uint32_t m = __reduce_max_sync(kFull, row_live ? score_code(uu) : 0u);
+            if (lane == 0) atomicMax(best_s + c + 4 * i4 + t, m);
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tmem_empty[a]);
+      epilogue_barrier();
+      for (int j = e * 32 + lane; j < nq_pass; j += 128)
+        p.gmax[size_t(q0 + j) * p.gmax_stride + tile0] = best_s[j];
+      {                                                                // thresholds the service warps have derived so far
+        const int j = 4 * lane + e;
+        if (j < nq_pass) {
+          if (it == boot - 1) {                                        // last visit: give them a bounded moment to arrive --
+            const long long t0 = clock64();                            // a first ordinary tile without thresholds costs ~30 tiles
+            while (*reinterpret_cast<volatile float*>(st.thr_ext + j) == -INFINITY && clock64() - t0 < 100000) __nanosleep(200);
+          }
+          st.thr[j] = fmaxf(st.thr[j], *reinterpret_cast<volatile float*>(st.thr_ext + j));
+        }
+      }
+      epilogue_barrier();                                              // (also: best_s words go back to the hit queue)
+      continue;
+    }
     bool dense = false;                                               // after a queue overflow: 16 queries at a time
     int seg = QP;
     for (int jb = 0; jb < QP; jb += seg, ++seg_idx) {
@@ -541,33 +585,51 @@ __device__ __forceinline__ void filt_service(const TcParams& p, const FiltState 
   const int k = p.k_true;
   if (n_ctas < k || !p.gmax) return;                                  // the bound needs k distinct CTAs
   volatile float* const thr_ext = st.thr_ext;
+  constexpr int NQ = 4;                                               // queries selected side by side (hides the redux latency)
+  // The k-th best of everything seen grows like log(rows): refresh eagerly at first, then back off (a spinning
+  // warp costs issue slots and, on a power-capped part, clock).
+  unsigned pause_ns = 500;
   while (!*done) {
-    for (int j = sid; j < nq_pass && !*done; j += nserv) {
-      const uint32_t* src = p.gmax + size_t(q0 + j) * p.gmax_stride;
-      uint32_t v[5];
+    for (int jg = sid * NQ; jg < nq_pass && !*done; jg += nserv * NQ) {
+      uint32_t v[NQ][5];
 #pragma unroll
-      for (int i = 0; i < 5; ++i) {
-        const int c = lane + 32 * i;
-        v[i] = 0u;
-        if (c < n_ctas) asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v[i]) : "l"(src + c));
+      for (int t = 0; t < NQ; ++t) {
+        const int j = jg + t < nq_pass ? jg + t : jg;
+        const uint32_t* src = p.gmax + size_t(q0 + j) * p.gmax_stride;
+#pragma unroll
+        for (int i = 0; i < 5; ++i) {
+          const int c = lane + 32 * i;
+          v[t][i] = 0u;
+          if (c < n_ctas) asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v[t][i]) : "l"(src + c));
+        }
       }
-      // largest x (to 22 bits) with at least k values >= x: a lower bound of the k-th largest
-      uint32_t x = 0u;
+      // per query: the largest x (to 22 bits) with at least k values >= x, a lower bound of the k-th largest
+      uint32_t x[NQ];
+#pragma unroll
+      for (int t = 0; t < NQ; ++t) x[t] = 0u;
 #pragma unroll 1
       for (int bit = 31; bit >= 10; --bit) {
-        const uint32_t cand = x | (1u << bit);
-        int cnt = 0;
 #pragma unroll
-        for (int i = 0; i < 5; ++i) cnt += v[i] >= cand ? 1 : 0;
-        cnt = __reduce_add_sync(kFull, cnt);
-        if (cnt >= k) x = cand;
+        for (int t = 0; t < NQ; ++t) {
+          const uint32_t cand = x[t] | (1u << bit);
+          int cnt = 0;
+#pragma unroll
+          for (int i = 0; i < 5; ++i) cnt += v[t][i] >= cand ? 1 : 0;
+          cnt = __reduce_add_sync(kFull, cnt);
+          if (cnt >= k) x[t] = cand;
+        }
       }
-      if (lane == 0 && x != 0u) {
-        const float t = code_score(x) - 2.f * st.eq[j] * maxn;
-        if (t > thr_ext[j]) thr_ext[j] = t;
+#pragma unroll
+      for (int t = 0; t < NQ; ++t) {
+        const int j = jg + t;
+        if (lane == 0 && j < nq_pass && x[t] != 0u) {
+          const float tt = code_score(x[t]) - 2.f * st.eq[j] * maxn;
+          if (tt > thr_ext[j]) thr_ext[j] = tt;
+        }
       }
     }
-    __nanosleep(2000);
+    for (unsigned slept = 0; slept < pause_ns && !*done; slept += 1000) __nanosleep(pause_ns < 1000 ? pause_ns : 1000);
+    if (pause_ns < 64000) pause_ns *= 2;
   }
 }
 
@@ -653,6 +715,14 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap bank_map, const __grid_consta
   // needs ||row||^2 either way (normalised scores, or max ||row|| for the error bound of plain dot scores)
   const bool norm_warps = FILT ? p.row_sumsq == nullptr
                                : !(BF && (p.row_sumsq != nullptr || !(p.flags & DEVQA_NORMALIZE_BANK)));
+  // Tile sequence of this CTA: its strided tiles, then (filter variant, long scans) the first `boot` tiles AGAIN:
+  // on their first visit the epilogue only learns each query's best upper bound from them (thresholds for everyone
+  // through the service warps), on the second it treats them like any other tile -- with thresholds in place.
+  // Without this, the first two tiles of every CTA cost as much as ~40 ordinary ones (lists built from nothing).
+  const int n_my = (p.n_tiles - tile0 + tile_step - 1) / tile_step;
+  const int boot = (FILT && n_my >= 32 && tile_step >= p.k_true && p.gmax && !(p.flags & kDbgNoBoot)) ? 4 : 0;
+  const int n_iter = n_my + boot;
+  auto tile_at = [&](int it) { return tile0 + (it < n_my ? it : it - n_my) * tile_step; };
   const int set_kb = FILT ? nkb : kSetKBlocks;           // k-blocks accumulated inside the tensor core
   const int nsets = (nkb + set_kb - 1) / set_kb;         // accumulation units per tile (1 unless MULTI)
 
@@ -664,17 +734,18 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap bank_map, const __grid_consta
       const bool pf_on = !(p.flags & kDbgNoPrefetch);
       const bool qtma = !(p.flags & kDbgNoQueryTma);
       const uint32_t tx_bytes = kATileBytes + (qtma ? b_stage_bytes : 0u);
-      int pf_tile = tile0, pf_kb = 0;                     // next k-block to prefetch
+      int pf_it = 0, pf_kb = 0;                           // next k-block to prefetch
       auto prefetch_next = [&]() {
-        if (pf_tile < p.n_tiles) {
-          if (pf_on) tma_prefetch_l2_2d(&bank_map, pf_kb * kElemsK, pf_tile * kTileRows);
-          if (++pf_kb == nkb) { pf_kb = 0; pf_tile += tile_step; }
+        if (pf_it < n_iter) {
+          if (pf_on) tma_prefetch_l2_2d(&bank_map, pf_kb * kElemsK, tile_at(pf_it) * kTileRows);
+          if (++pf_kb == nkb) { pf_kb = 0; ++pf_it; }
         }
       };
       for (int i = 0; i < kPrefetchAhead; ++i) prefetch_next();
       RingPos r;
       uint32_t trace_it = 0;
-      for (int tile = tile0; tile < p.n_tiles; tile += tile_step) {
+      for (int it = 0; it < n_iter; ++it) {
+        const int tile = tile_at(it); (void)tile;
         for (int kb = 0; kb < nkb; ++kb) {
           prefetch_next();
           mbar_wait(&empty[r.s], r.phase ^ 1u);
@@ -694,7 +765,8 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap bank_map, const __grid_consta
       const uint32_t a_lo0 = (smem_u32(smem + L.a_raw) & 0x3ffffu) >> 4, b_lo0 = (smem_u32(smem + L.bq) & 0x3ffffu) >> 4;
       RingPos r;
       uint32_t unit = 0;
-      for (int tile = tile0; tile < p.n_tiles; tile += tile_step) {
+      for (int it = 0; it < n_iter; ++it) {
+        const int tile = tile_at(it); (void)tile;
         for (int set = 0; set < nsets; ++set, ++unit) {
           const int a = unit & 1;
           mbar_wait(&tmem_empty[a], ((unit >> 1) & 1) ^ 1);
@@ -727,7 +799,8 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap bank_map, const __grid_consta
       const bool on = !(p.flags & kDbgNoMma2);
       RingPos r;
       uint32_t unit = 0;
-      for (int tile = tile0; tile < p.n_tiles; tile += tile_step) {
+      for (int it = 0; it < n_iter; ++it) {
+        const int tile = tile_at(it); (void)tile;
         for (int set = 0; set < nsets; ++set, ++unit) {
           const int a = unit & 1;
           mbar_wait(&tmem_empty[a], ((unit >> 1) & 1) ^ 1);
@@ -762,7 +835,8 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap bank_map, const __grid_consta
     RingPos rp;
     const uint32_t st_lane = uint32_t((warp & 3) * 32) << 16;     // warp w may only touch TMEM lanes 32*(w%4)..
     const uint32_t a_raw_s = smem_u32(smem + L.a_raw) + row_off;
-    for (int tile = tile0; tile < p.n_tiles; tile += tile_step, ++lt) {
+    for (int it = 0; it < n_iter; ++it, ++lt) {
+      const int tile = tile_at(it); (void)tile;
       float ss[8];                                        // one partial sum per 16-byte chunk position
 #pragma unroll
       for (int c = 0; c < 8; ++c) ss[c] = 0.f;
@@ -832,8 +906,8 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap bank_map, const __grid_consta
     else filt_service(p, st, q0, nq_pass, tile_step, maxn, warp - 3, 5, lane);
   } else if (warp >= 8 && FILT) {
     // ===== epilogue warps, filter variant: scan + hit queue (filt_epilogue) =====
-    filt_epilogue<QP>(p, st, lists, norms, norm_warps, tmem_base, tmem_full, tmem_empty, tile0, tile_step, q0, nq_pass, maxn,
-                      warp - 8, lane);
+    filt_epilogue<QP>(p, st, lists, norms, norm_warps, tmem_base, tmem_full, tmem_empty, tile0, tile_step, n_my, boot, q0, nq_pass,
+                      maxn, warp - 8, lane);
   } else if (warp >= 8) {
     // ===== epilogue warps =====
     // Phase A: thread <-> TMEM lane <-> bank row: sum the three accumulator parts, scale by 1/||row||
@@ -855,7 +929,8 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap bank_map, const __grid_consta
     const int own_j = (lane / NQW_) * HQ + e * NQW_ + lane % NQW_;
     const bool own_live = lane < QP / 4 && own_j < nq_pass;
     uint32_t* const own_gthr = p.gthr + q0 + (own_live ? own_j : 0);
-    for (int tile = tile0; tile < p.n_tiles; tile += tile_step, ++lt) {
+    for (int it = 0; it < n_iter; ++it, ++lt) {
+      const int tile = tile_at(it); (void)tile;
       // pick up the bounds other CTAs have published (one relaxed load per owned query per tile)
       if (own_live) {
         uint32_t code;
