@@ -293,7 +293,7 @@ static int run_search(Scratch* s, const SearchArgs& a, uint64_t* out_keys, float
           return rc;
         continue;
       }
-      const size_t nq = size_t(ac.n_queries), nq_pad = (nq + 127) / 128 * 128;
+      const size_t nq = size_t(ac.n_queries), nq_pad = (nq + 255) / 256 * 256;   // >= q_pad of any plan
       if ((rc = grow(reinterpret_cast<void**>(&s->akeys), &s->akeys_bytes,
                      nq * kp * 8 + nq * 12 + nq_pad * 4 + size_t(s->sm_count) * nq * 4 + nq_pad * kGmaxStride * 4, false)))
         return rc;

@@ -76,7 +76,8 @@ constexpr int kNormRing = 8;
 constexpr int kMaxStages = 8;
 constexpr int kPrefetchAhead = 12;                  // bank k-blocks pulled into L2 ahead of the smem ring
 constexpr int kSetKBlocks = 32;
-constexpr int kHitCap = 2048;                        // filter epilogue: hit queue entries (>= 128 rows x 16 queries)
+// filter epilogue: hit queue entries; the same words hold the dense [16][128] score tile (8 KB), so >= 1024
+__host__ __device__ constexpr int hit_cap(int qp) { return qp > 128 ? 1024 : 2048; }
 // undocumented debugging bits of `flags` (performance bisection only; results are wrong when set)
 constexpr unsigned kDbgNoInsert = 1u << 16, kDbgNoSplit = 1u << 17, kDbgNoMma2 = 1u << 18, kDbgNoQueryTma = 1u << 19, kDbgNoPrefetch = 1u << 20, kDbgNoBoot = 1u << 23;                     // k-blocks (of 32 columns) accumulated inside the tensor core
 
@@ -277,8 +278,8 @@ __host__ __device__ inline SmemLayout tc_layout(int stages, int qp, int kcap, in
   L.bq = off;    off += uint32_t(stages) * uint32_t(b_parts * qp) * 128;     // [parts*qp rows x 128 B], 1024-aligned since qp % 16 == 0
   L.lists = off; off += uint32_t(qp) * kcap * 8;
   L.thr = off;   off += uint32_t(qp) * 16 + 16;                          // filter: eq / threshold / lost / service bound per query + counters
-  L.scratch = off; off += b_parts == 1 ? kHitCap * 8 : uint32_t(qp < 32 ? qp : 32) * kTileRows * 4;   // score tile [HQ][128] / hit queue
-  L.norms = off; off += kNormRing * kTileRows * 4;
+  L.scratch = off; off += b_parts == 1 ? hit_cap(qp) * 8 : uint32_t(qp < 32 ? qp : 32) * kTileRows * 4;   // score tile [HQ][128] / hit queue
+  L.norms = off; off += qp > 128 ? 0 : kNormRing * kTileRows * 4;         // (256 queries per pass: cached row norms only)
   off = (off + 7) & ~7u;
   L.bars = off;  off += (3 * kMaxStages + 4) * 8;
   L.tmem_slot = off; off += 16;
@@ -360,8 +361,8 @@ struct FiltState {            // per-query state in shared memory, [QP] each
   float* lost;                // upper bound of every row a full list turned away while its last entry was binding
   float* thr_ext;             // T from the service warps (written by them only)
   uint32_t* qn;               // [2] hit counters (alternating per segment), [2] = scan finished
-  float* hit_u;               // [kHitCap]   (dense mode: score tile [16][128])
-  uint32_t* hit_id;           // [kHitCap] query << 8 | row in tile
+  float* hit_u;               // [hit_cap(QP)]   (dense mode: score tile [16][128], running into hit_id)
+  uint32_t* hit_id;           // [hit_cap(QP)] query << 8 | row in tile
 };
 
 // After the list of query j changed: derive the local bound, keep the lost-rows bound, publish the CTA's best.
@@ -438,9 +439,8 @@ __device__ __forceinline__ void filt_epilogue(const TcParams& p, const FiltState
       epilogue_barrier();
       for (int j = e * 32 + lane; j < nq_pass; j += 128)
         p.gmax[size_t(q0 + j) * p.gmax_stride + tile0] = best_s[j];
-      {                                                                // thresholds the service warps have derived so far
-        const int j = 4 * lane + e;
-        if (j < nq_pass) {
+      for (int j = 4 * lane + e; j < nq_pass; j += 128) {              // thresholds the service warps have derived so far
+        {
           if (it == boot - 1) {                                        // last visit: give them a bounded moment to arrive --
             const long long t0 = clock64();                            // a first ordinary tile without thresholds costs ~30 tiles
             while (*reinterpret_cast<volatile float*>(st.thr_ext + j) == -INFINITY && clock64() - t0 < 100000) __nanosleep(200);
@@ -485,7 +485,7 @@ __device__ __forceinline__ void filt_epilogue(const TcParams& p, const FiltState
           for (int i = 0; i < 16; ++i) {
             if ((mask >> i) & 1u) {
               const uint32_t idx = atomicAdd(qn, 1u);
-              if (idx < uint32_t(kHitCap)) { st.hit_u[idx] = u[i]; st.hit_id[idx] = (uint32_t(c + i) << 8) | uint32_t(row_in_tile); }
+              if (idx < uint32_t(hit_cap(QP))) { st.hit_u[idx] = u[i]; st.hit_id[idx] = (uint32_t(c + i) << 8) | uint32_t(row_in_tile); }
             }
           }
         }
@@ -495,7 +495,7 @@ __device__ __forceinline__ void filt_epilogue(const TcParams& p, const FiltState
       epilogue_barrier();                                               // every hit of the segment is visible
       const uint32_t n = dense ? 0u : *qn;
       if (e == 0 && lane == 0) st.qn[(seg_idx & 1) ^ 1] = 0u;           // the other counter: idle until the next scan
-      if (n > uint32_t(kHitCap)) {                                      // overflow (cold start): redo the tile densely
+      if (n > uint32_t(hit_cap(QP))) {                                  // overflow (cold start): redo the tile densely
         dense = true;
         seg = 16;
         jb = -16;
@@ -559,10 +559,8 @@ __device__ __forceinline__ void filt_epilogue(const TcParams& p, const FiltState
         }
       }
       // ---- pick up the service warps' bounds (own queries only: nobody else writes thr) ----
-      if (last_seg) {
-        const int j = 4 * lane + e;
-        if (j < nq_pass) st.thr[j] = fmaxf(st.thr[j], st.thr_ext[j]);
-      }
+      if (last_seg)
+        for (int j = 4 * lane + e; j < nq_pass; j += 128) st.thr[j] = fmaxf(st.thr[j], st.thr_ext[j]);
       epilogue_barrier();                                               // thresholds visible, queue reusable
     }
     if (e == 0 && lane == 0) trace_at(p, 7, unit);
@@ -678,7 +676,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap bank_map, const __grid_consta
     st.eq = fs; st.thr = fs + QP; st.lost = fs + 2 * QP; st.thr_ext = fs + 3 * QP;
     st.qn = reinterpret_cast<uint32_t*>(fs + 4 * QP);
     st.hit_u = reinterpret_cast<float*>(smem + L.scratch);
-    st.hit_id = reinterpret_cast<uint32_t*>(smem + L.scratch) + kHitCap;
+    st.hit_id = reinterpret_cast<uint32_t*>(smem + L.scratch) + hit_cap(QP);
     if (!(p.flags & DEVQA_NORMALIZE_BANK)) maxn = sqrtf(__uint_as_float(*p.bank_max_sumsq));
     for (int j = threadIdx.x; j < QP; j += kTcThreads) {
       const bool live = j < nq_pass;
@@ -1218,9 +1216,11 @@ int scan_tc_plan(int mode, int n_queries, int64_t dim, int kcap, bool cached_nor
   // more than one K-set (1024 fp32 / 2048 bf16 columns) sums K-sets in the epilogue's registers (MULTI):
   // 32 queries per pass at most.  The filter keeps the whole K chain in the tensor core (its error bound
   // covers the drift) and, with cached row norms (no CUDA-core pass over the tile), takes 128 queries per pass.
-  int qp = filt ? (cached_norms ? 128 : 64) : (scan_tc_kblocks(mode, dim) > kSetKBlocks ? 32 : 64);
+  int qp = filt ? (cached_norms ? 256 : 64) : (scan_tc_kblocks(mode, dim) > kSetKBlocks ? 32 : 64);
   const int q16 = (n_queries + 15) / 16 * 16;
   while (qp > 16 && qp / 2 >= q16) qp >>= 1;
+  // 129..192 queries: two passes of 128 at the HBM-bound rate beat one shared-memory-bound pass of 256
+  if (qp == 256 && n_queries <= 192) qp = 128;
   for (; qp >= 16; qp >>= 1) {
     for (int stages = kMaxStages; stages >= 3; --stages) {
       // TMEM: 2 accumulator buffers of 3*qp (filter: qp) columns (+ one 32-column lo tile per stage for 3xTF32)
@@ -1288,10 +1288,10 @@ int scan_tc_launch(const ScanParams& sp, int mode, const void* qcat, uint32_t* g
     if (!multi) kern = qp == 64 ? scan_tc_kernel<64, false, kBf16x3> : qp == 32 ? scan_tc_kernel<32, false, kBf16x3> : scan_tc_kernel<16, false, kBf16x3>;
     else kern = qp == 32 ? scan_tc_kernel<32, true, kBf16x3> : scan_tc_kernel<16, true, kBf16x3>;
   } else {
-    kern = qp == 128 ? scan_tc_kernel<128, false, kTf32x1> : qp == 64 ? scan_tc_kernel<64, false, kTf32x1>
+    kern = qp == 256 ? scan_tc_kernel<256, false, kTf32x1> : qp == 128 ? scan_tc_kernel<128, false, kTf32x1> : qp == 64 ? scan_tc_kernel<64, false, kTf32x1>
          : qp == 32 ? scan_tc_kernel<32, false, kTf32x1> : scan_tc_kernel<16, false, kTf32x1>;
   }
-  const bool qp_ok = qp == 16 || qp == 32 || (qp == 64 && !multi) || (qp == 128 && mode == kTcTf32x1);
+  const bool qp_ok = qp == 16 || qp == 32 || (qp == 64 && !multi) || ((qp == 128 || qp == 256) && mode == kTcTf32x1);
   if (!qp_ok) {
     set_error("tcgen05 scan: unsupported queries-per-pass %d", qp);
     return DEVQA_E_INVALID;
