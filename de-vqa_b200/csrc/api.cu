@@ -150,7 +150,9 @@ struct FilterSide {
   uint32_t* lostu = nullptr;     // [grid, Q] per-CTA bound on the rows its full list lost
   uint32_t* gmax = nullptr;      // [Q padded, kGmaxStride] per-CTA best upper bound per query (threshold exchange)
   int kp = 0;                    // K': capacity of the merged candidate list
+  bool merge = true;             // in: merge the per-CTA lists into akeys (false: refine reads the lists themselves)
   int n_lists = 0;               // out: per-CTA lists per query
+  int kcap = 0;                  // out: capacity of each
 };
 
 // One tcgen05 scan pipeline over all of a's queries: prepare the query operand, (seed thresholds on a prefix
@@ -165,7 +167,8 @@ static int tc_pipeline(Scratch* s, const SearchArgs& a, int mode, FilterSide* si
   const int list_k = side ? kcap : a.top_k;                 // entries a list keeps
   const bool cached_norms = a.row_sumsq != nullptr;
   int qp = 0, stages = 0;
-  if ((rc = scan_tc_plan(mode, int(a.n_queries), a.dim, kcap, cached_norms, &qp, &stages))) return rc;
+  if ((rc = scan_tc_plan(mode, int(a.n_queries), a.dim, kcap, cached_norms, (a.n_rows + 127) / 128, s->sm_count, &qp, &stages)))
+    return rc;
   const int q_pad = int((a.n_queries + qp - 1) / qp) * qp;
   const size_t qcat_bytes = scan_tc_qcat_bytes(mode, a.dim, q_pad);
   if ((rc = grow(reinterpret_cast<void**>(&s->qsplit), &s->qsplit_bytes, qcat_bytes + size_t(q_pad) * 4, false))) return rc;
@@ -193,13 +196,13 @@ static int tc_pipeline(Scratch* s, const SearchArgs& a, int mode, FilterSide* si
     p.gmax = side->gmax; p.gmax_stride = kGmaxStride;
     side->n_lists = grid;
     DEVQA_REQUIRE(grid <= kGmaxStride, "more CTAs per pass than the threshold exchange holds");
-    DEVQA_CUDA(cudaMemsetAsync(side->gmax, 0, size_t(q_pad) * kGmaxStride * 4, stream));
   }
 
   const bool prof = s->profiling && !need && s->prof_used < Scratch::kProfSlots;
   if (prof) DEVQA_CUDA(cudaEventRecord(s->prof_ev[2 * s->prof_used], stream));
   if ((rc = scan_tc_prep_queries(mode, a.queries, a.query_ld, int(a.n_queries), qp, q_pad, a.dim, a.flags, s->qsplit, gthr,
-                                 side ? side->qinv : nullptr, side ? side->qerr : nullptr, side ? side->seed_u : nullptr, stream)))
+                                 side ? side->qinv : nullptr, side ? side->qerr : nullptr, side ? side->seed_u : nullptr,
+                                 side ? side->gmax : nullptr, kGmaxStride, need, stream)))
     return rc;
   // Threshold seeding: scan a prefix sample of the bank (one tile per CTA) first; the k-th best score of a
   // SUBSET is a lower bound of the k-th best of the whole bank, so the main scan starts with tight
@@ -236,7 +239,11 @@ static int tc_pipeline(Scratch* s, const SearchArgs& a, int mode, FilterSide* si
     DEVQA_CUDA(cudaEventRecord(s->prof_ev[2 * s->prof_used + 1], stream));
     s->prof_used++;
   }
-  if (side) return merge_lists_launch(s->cand, grid, a.n_queries, kcap, kcap, side->kp, side->akeys, nullptr, nullptr, stream);
+  if (side) {
+    side->kcap = kcap;
+    if (!side->merge) return DEVQA_OK;
+    return merge_lists_launch(s->cand, grid, a.n_queries, kcap, kcap, side->kp, side->akeys, nullptr, nullptr, stream);
+  }
   return merge_lists_launch(s->cand, grid, a.n_queries, kcap, kcap, a.top_k, out_keys, out_scores, out_ids, stream, nullptr, need);
 }
 
@@ -277,6 +284,8 @@ static int run_search(Scratch* s, const SearchArgs& a, uint64_t* out_keys, float
     // scan alone on request, for top_k > 64 (no room for the filter's surplus candidates) and for un-normalised
     // scores over a caller-owned bank (the error bound needs max ||row||, which only library-owned banks cache).
     const int kp = a.top_k <= 8 ? 32 : (a.top_k <= 16 ? 64 : 128);     // K': candidates kept per query after the merge
+    // (Nothing here may depend on the number of rows: every shard of a sharded bank has to take the same path, or
+    // G-GPU results would differ from 1-GPU results in the last bits of the scores.)
     const bool filt = a.dtype == DEVQA_F32 && !(a.flags & DEVQA_FORCE_TF32X3) && a.top_k <= 64 && a.dim <= 16384 &&
                       ((a.flags & DEVQA_NORMALIZE_BANK) || (a.row_sumsq && a.max_sumsq));
     if (s->profiling) s->prof_searches++;
@@ -306,6 +315,10 @@ static int run_search(Scratch* s, const SearchArgs& a, uint64_t* out_keys, float
       side.seed_u = reinterpret_cast<uint32_t*>(side.qerr + nq);
       side.lostu = side.seed_u + nq_pad;
       side.gmax = side.lostu + size_t(s->sm_count) * nq;
+      // With at least top_k CTAs per pass the scan's CTAs exchange their bests, and refine can pick the candidates
+      // straight out of the per-CTA lists (one kernel instead of merge + refine).
+      const int64_t tiles = (a.n_rows + 127) / 128;
+      side.merge = (a.flags & DEVQA_DEBUG_FILTER_ONLY) || tiles < s->sm_count || s->sm_count < a.top_k;
       if ((rc = tc_pipeline(s, ac, kTcTf32x1, &side, nullptr, nullptr, nullptr, nullptr, stream))) return rc;
       if (a.flags & DEVQA_DEBUG_FILTER_ONLY) {                           // tests: the filter's own upper bounds
         if ((rc = merge_lists_launch(side.akeys, 1, ac.n_queries, kp, kp, a.top_k, ok, os, oi, stream))) return rc;
@@ -317,7 +330,9 @@ static int run_search(Scratch* s, const SearchArgs& a, uint64_t* out_keys, float
       rp.qinv = side.qinv; rp.akeys = side.akeys; rp.lostu = side.lostu; rp.n_lists = side.n_lists;
       rp.kp = kp; rp.top_k = a.top_k; rp.flags = a.flags; rp.idmap = a.idmap;
       rp.need = side.need; rp.fallbacks = s->fallbacks; rp.out_keys = ok; rp.out_scores = os; rp.out_ids = oi;
-      if ((rc = refine_launch(rp, stream))) return rc;
+      rp.cand = s->cand; rp.cand_kcap = side.kcap; rp.gmax = side.gmax; rp.gmax_stride = kGmaxStride;
+      rp.qerr = side.qerr; rp.bank_max_sumsq = a.max_sumsq;
+      if ((rc = side.merge ? refine_launch(rp, stream) : refine_lists_launch(rp, stream))) return rc;
       // queries for which a lost row could still matter are redone exactly; for all others these launches
       // exit at once (the flags live on the device: no host round trip, graph-capturable)
       if ((rc = tc_pipeline(s, ac, kTcTf32x3, nullptr, side.need, ok, os, oi, stream))) return rc;

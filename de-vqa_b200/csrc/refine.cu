@@ -177,7 +177,135 @@ __global__ void __launch_bounds__(kRefineThreads) refine_kernel(const RefinePara
   }
 }
 
+// The same, straight from the per-CTA lists (no merge kernel in between), for scans whose CTAs exchanged bests
+// (n_lists >= top_k).  T = (top_k-th largest of the CTAs' best upper bounds) - 2E is a lower bound of the exact
+// k-th best score, so only keys with u >= T can matter: typically top_k plus a handful out of n_lists x kcap.
+// They are compacted into shared memory, ALL re-scored, sorted.  More than 128 of them: the query is flagged.
+constexpr int kRefineListThreads = 512;
+
+template <bool VEC>
+__global__ void __launch_bounds__(kRefineListThreads) refine_lists_kernel(const RefineParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ uint64_t ex[kMaxKp];
+  __shared__ uint64_t ak[kMaxKp];
+  __shared__ uint32_t s_count, s_lost, s_tcode;
+  constexpr int CH = VEC ? 128 : 32;
+  const int dim = int(p.dim);
+  const int dpad = (dim + CH - 1) / CH * CH;
+  float* sq = reinterpret_cast<float*>(smem_raw);
+  const int q = blockIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float* src = p.queries + size_t(q) * p.query_ld;
+  const float inv = p.qinv[q];
+  for (int c = threadIdx.x; c < dpad; c += kRefineListThreads) sq[c] = c < dim ? src[c] * inv : 0.f;
+  for (int c = threadIdx.x; c < kMaxKp; c += kRefineListThreads) ex[c] = kEmptyKey;
+  if (threadIdx.x == 0) { s_count = 0u; s_lost = 0u; s_tcode = 0u; }
+  // ---- T from the CTAs' bests (warp 0), lost-row bounds (warp 1) ----
+  if (warp == 0) {
+    const uint32_t* g = p.gmax + size_t(q) * p.gmax_stride;
+    uint32_t v[5];
+#pragma unroll
+    for (int i = 0; i < 5; ++i) { const int c = lane + 32 * i; v[i] = c < p.n_lists ? g[c] : 0u; }
+    uint32_t x = 0u;
+    for (int bit = 31; bit >= 0; --bit) {                              // exact top_k-th largest
+      const uint32_t cand = x | (1u << bit);
+      int cnt = 0;
+#pragma unroll
+      for (int i = 0; i < 5; ++i) cnt += v[i] >= cand ? 1 : 0;
+      cnt = __reduce_add_sync(kFull, cnt);
+      if (cnt >= p.top_k) x = cand;
+    }
+    if (lane == 0 && x != 0u) {
+      float maxn = 1.f;
+      if (!(p.flags & DEVQA_NORMALIZE_BANK)) maxn = sqrtf(__uint_as_float(*p.bank_max_sumsq));
+      const float t = code_score(x) - 2.0001f * p.qerr[q] * maxn;
+      if (t == t) s_tcode = score_code(t);                              // NaN: no usable bound, keep everything
+    }
+  } else if (warp == 1) {
+    uint32_t lost = 0u;
+    for (int g = lane; g < p.n_lists; g += 32) {
+      const uint32_t code = p.lostu[size_t(g) * p.n_queries + q];
+      lost = code > lost ? code : lost;
+    }
+    lost = __reduce_max_sync(kFull, lost);
+    if (lane == 0) s_lost = lost;
+  }
+  __syncthreads();
+  // ---- compact the keys that can still matter ----
+  const uint32_t tcode = s_tcode;
+  const int total = p.n_lists * p.cand_kcap;
+  for (int i = threadIdx.x; i < total; i += kRefineListThreads) {
+    const int g = i / p.cand_kcap, e = i - g * p.cand_kcap;
+    const uint64_t key = p.cand[(size_t(g) * p.n_queries + q) * p.cand_kcap + e];
+    if (key != kEmptyKey && uint32_t(key >> 32) >= tcode) {
+      const uint32_t slot = atomicAdd(&s_count, 1u);
+      if (slot < uint32_t(kMaxKp)) ak[slot] = key;
+    }
+  }
+  __syncthreads();
+  const uint32_t n_raw = s_count;
+  const int n = n_raw < uint32_t(kMaxKp) ? int(n_raw) : kMaxKp;
+  // ---- exact re-scoring ----
+  for (int c = warp; c < n; c += kRefineListThreads / 32) {
+    const uint64_t a = ak[c];
+    const int64_t gid = int64_t(key_id(a));
+    int64_t row = gid - p.idmap.base;
+    if (p.idmap.chunk > 0) row = ((row / p.idmap.chunk) / p.idmap.world) * p.idmap.chunk + row % p.idmap.chunk;
+    const float s = exact_score<VEC>(p.bank + row * p.bank_ld, sq, dim, p.flags, lane);
+    if (lane == 0) ex[c] = pack_key(s, uint32_t(gid));
+  }
+  __syncthreads();
+  for (int k = 2; k <= kMaxKp; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      const int i = threadIdx.x;
+      if (i < kMaxKp) {
+        const int l = i ^ j;
+        if (l > i) {
+          const uint64_t a = ex[i], b = ex[l];
+          const bool desc = (i & k) == 0;
+          if (desc ? a < b : a > b) { ex[i] = b; ex[l] = a; }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  if (threadIdx.x == 0) {
+    const uint64_t kth = ex[p.top_k - 1];
+    bool complete = n_raw <= uint32_t(kMaxKp);                        // otherwise candidates were cut off
+    const uint32_t lost = s_lost;
+    if (complete && lost != 0u)
+      complete = kth != kEmptyKey && code_score(lost) < key_score(kth);   // false for NaN on either side
+    p.need[q] = complete ? 0u : 1u;
+    if (!complete && p.fallbacks) atomicAdd(p.fallbacks, 1u);
+  }
+  for (int e = threadIdx.x; e < p.top_k; e += kRefineListThreads) {
+    const uint64_t key = ex[e];
+    const size_t o = size_t(q) * p.top_k + e;
+    if (p.out_keys) {
+      p.out_keys[o] = key;
+    } else {
+      const bool empty = key == kEmptyKey;
+      p.out_scores[o] = empty ? -INFINITY : key_score(key);
+      p.out_ids[o] = empty ? int64_t(-1) : int64_t(key_id(key));
+    }
+  }
+}
+
 }  // namespace
+
+int refine_lists_launch(const RefineParams& p, cudaStream_t stream) {
+  if (p.n_queries == 0) return DEVQA_OK;
+  DEVQA_REQUIRE(p.top_k <= kMaxKp && p.n_lists <= 160 && p.n_lists >= p.top_k, "refine: unsupported list geometry");
+  const bool vec = p.dim % 4 == 0 && p.bank_ld % 4 == 0 && reinterpret_cast<uintptr_t>(p.bank) % 16 == 0;   // scan_stream's rule
+  const int ch = vec ? 128 : 32;
+  const size_t smem = size_t((p.dim + ch - 1) / ch * ch) * 4;
+  auto kern = vec ? refine_lists_kernel<true> : refine_lists_kernel<false>;
+  if (smem > 40 * 1024) DEVQA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+  kern<<<unsigned(p.n_queries), kRefineListThreads, smem, stream>>>(p);
+  DEVQA_CUDA(cudaGetLastError());
+  count_launch();
+  return DEVQA_OK;
+}
 
 int refine_launch(const RefineParams& p, cudaStream_t stream) {
   if (p.n_queries == 0) return DEVQA_OK;

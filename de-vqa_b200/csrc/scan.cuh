@@ -52,15 +52,16 @@ constexpr int kTcTf32x3 = 0, kTcBf16x3 = 1, kTcTf32x1 = 2;
 //   (dim/32 + 5) times to nearest.  tests/test_gpu_filter.py measures the actual error against this bound.
 __host__ __device__ inline float tc_filter_relerr(int64_t dim) { return 1.5f * 0.0009765625f + float(dim) * 5.9604644775390625e-08f; }
 bool scan_tc_supported(int bank_dtype, const void* bank, int64_t dim, int64_t bank_ld, int top_k);
-int scan_tc_plan(int mode, int n_queries, int64_t dim, int kcap, bool cached_norms, int* qp_out, int* stages_out);
+int scan_tc_plan(int mode, int n_queries, int64_t dim, int kcap, bool cached_norms, int64_t n_tiles, int sm_count,
+                 int* qp_out, int* stages_out);
 size_t scan_tc_qcat_bytes(int mode, int64_t dim, int q_pad);
 // queries -> normalised, split (hi/lo TF32; hi/mid/lo bf16; hi TF32 only for the filter), laid out per pass as the
 // MMA B operand (see scan_tc.cu); also zeroes the shared threshold array gthr [q_pad].  Filter mode also writes,
 // per query, the scale the normalisation applied (qinv) and the error scale qerr = tc_filter_relerr(dim) *
-// ||query as used||, and zeroes seed_u [q_pad].
+// ||query as used||, and zeroes seed_u [q_pad] and the threshold exchange table gmax [q_pad, gmax_stride].
 int scan_tc_prep_queries(int mode, const float* queries, int64_t query_ld, int n_queries, int qp, int q_pad,
                          int64_t dim, unsigned flags, void* qcat, uint32_t* gthr, float* qinv, float* qerr,
-                         uint32_t* seed_u, cudaStream_t stream);
+                         uint32_t* seed_u, uint32_t* gmax, int gmax_stride, const uint32_t* need, cudaStream_t stream);
 // one launch = `passes` consecutive query passes starting at p.q0, each on ctas_per_pass CTAs
 int scan_tc_launch(const ScanParams& p, int mode, const void* qcat, uint32_t* gthr, int qp, int stages, int passes,
                    int ctas_per_pass, cudaStream_t stream);
@@ -74,6 +75,13 @@ struct RefineParams {
   const uint64_t* akeys;      // [n_queries, kp] merged candidates: keys on the upper bound u, sorted descending, 0 = empty
   const uint32_t* lostu;      // [n_lists, n_queries] per-CTA bound on the rows its full list lost (score code, 0 = none)
   int32_t n_lists;
+  // refine_lists_launch only: the per-CTA lists themselves and what the CTAs exchanged
+  const uint64_t* cand;       // [n_lists, n_queries, cand_kcap]
+  int32_t cand_kcap;
+  const uint32_t* gmax;       // [n_queries (padded), gmax_stride] each CTA's best upper bound per query (score codes)
+  int32_t gmax_stride;
+  const float* qerr;          // [n_queries] tc_filter_relerr(dim) * ||query as used||
+  const uint32_t* bank_max_sumsq;   // un-normalised scores: max ||row||^2 (float bits)
   int32_t kp, top_k;
   uint32_t flags;
   IdMap idmap;
@@ -81,7 +89,8 @@ struct RefineParams {
   uint32_t* fallbacks;        // device counter of such queries (devqa_filter_fallbacks)
   uint64_t* out_keys; float* out_scores; int64_t* out_ids;   // exactly one of keys / (scores, ids): [n_queries, top_k]
 };
-int refine_launch(const RefineParams& p, cudaStream_t stream);
+int refine_launch(const RefineParams& p, cudaStream_t stream);          // from the merged list akeys
+int refine_lists_launch(const RefineParams& p, cudaStream_t stream);    // from the per-CTA lists (n_lists >= top_k)
 
 // merge.cu: reduce `n_lists` sorted lists per query ([n_lists, n_queries, list_stride], the first
 // list_len entries of each valid) to the final top_k.  Exactly one of (out_keys) or

@@ -451,8 +451,10 @@ __device__ __forceinline__ void filt_epilogue(const TcParams& p, const FiltState
       epilogue_barrier();                                              // (also: best_s words go back to the hit queue)
       continue;
     }
-    bool dense = false;                                               // after a queue overflow: 16 queries at a time
-    int seg = QP;
+    // dense = 16 queries at a time through a score tile: after a queue overflow, and for a first tile without
+    // thresholds (short scans: every row is a candidate)
+    bool dense = it == 0 && boot == 0;
+    int seg = dense ? 16 : QP;
     for (int jb = 0; jb < QP; jb += seg, ++seg_idx) {
       uint32_t* const qn = st.qn + (seg_idx & 1);
       // ---- scan ----
@@ -495,7 +497,9 @@ __device__ __forceinline__ void filt_epilogue(const TcParams& p, const FiltState
       epilogue_barrier();                                               // every hit of the segment is visible
       const uint32_t n = dense ? 0u : *qn;
       if (e == 0 && lane == 0) st.qn[(seg_idx & 1) ^ 1] = 0u;           // the other counter: idle until the next scan
-      if (n > uint32_t(hit_cap(QP))) {                                  // overflow (cold start): redo the tile densely
+      // Many hits (cold lists, short scans): one-by-one insertion costs ~1000 cycles each per warp, the dense path a
+      // fixed ~9k cycles per 16 queries -- redo the tile densely beyond the break-even (and always on overflow).
+      if (n > uint32_t(2 * QP + 32 < hit_cap(QP) ? 2 * QP + 32 : hit_cap(QP))) {   // (cold start): redo the tile densely
         dense = true;
         seg = 16;
         jb = -16;
@@ -576,9 +580,12 @@ __device__ __forceinline__ void filt_epilogue(const TcParams& p, const FiltState
   }
 }
 
-// Service warp: for its share of the queries, T = (k-th largest of the CTAs' best upper bounds) - 2E, over and over.
-__device__ __forceinline__ void filt_service(const TcParams& p, const FiltState st, int q0, int nq_pass, int n_ctas, float maxn,
-                                             int sid, int nserv, int lane) {
+// Service warp (warp 3).  The selection is shared out: CTA c derives T for the queries j = c, c + n_ctas, ... from
+// all CTAs' bests and publishes it (gthr, one word per query); every CTA then picks up all of its pass's
+// thresholds with one coalesced read.  (Each CTA selecting for every query cost 148x the work and 16-32 us per
+// round at 128-256 queries; this way a round is a few microseconds.)
+__device__ __forceinline__ void filt_service(const TcParams& p, const FiltState st, int q0, int nq_pass, int n_ctas, int cta,
+                                             float maxn, int lane) {
   volatile uint32_t* const done = st.qn + 2;
   const int k = p.k_true;
   if (n_ctas < k || !p.gmax) return;                                  // the bound needs k distinct CTAs
@@ -588,11 +595,11 @@ __device__ __forceinline__ void filt_service(const TcParams& p, const FiltState 
   // warp costs issue slots and, on a power-capped part, clock).
   unsigned pause_ns = 500;
   while (!*done) {
-    for (int jg = sid * NQ; jg < nq_pass && !*done; jg += nserv * NQ) {
+    for (int jg = cta; jg < nq_pass; jg += n_ctas * NQ) {
       uint32_t v[NQ][5];
 #pragma unroll
       for (int t = 0; t < NQ; ++t) {
-        const int j = jg + t < nq_pass ? jg + t : jg;
+        const int j = jg + t * n_ctas < nq_pass ? jg + t * n_ctas : jg;
         const uint32_t* src = p.gmax + size_t(q0 + j) * p.gmax_stride;
 #pragma unroll
         for (int i = 0; i < 5; ++i) {
@@ -601,12 +608,12 @@ __device__ __forceinline__ void filt_service(const TcParams& p, const FiltState 
           if (c < n_ctas) asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v[t][i]) : "l"(src + c));
         }
       }
-      // per query: the largest x (to 22 bits) with at least k values >= x, a lower bound of the k-th largest
+      // per query: the largest x (to 20 bits) with at least k values >= x, a lower bound of the k-th largest
       uint32_t x[NQ];
 #pragma unroll
       for (int t = 0; t < NQ; ++t) x[t] = 0u;
 #pragma unroll 1
-      for (int bit = 31; bit >= 10; --bit) {
+      for (int bit = 31; bit >= 12; --bit) {
 #pragma unroll
         for (int t = 0; t < NQ; ++t) {
           const uint32_t cand = x[t] | (1u << bit);
@@ -619,11 +626,19 @@ __device__ __forceinline__ void filt_service(const TcParams& p, const FiltState 
       }
 #pragma unroll
       for (int t = 0; t < NQ; ++t) {
-        const int j = jg + t;
+        const int j = jg + t * n_ctas;
         if (lane == 0 && j < nq_pass && x[t] != 0u) {
-          const float tt = code_score(x[t]) - 2.f * st.eq[j] * maxn;
-          if (tt > thr_ext[j]) thr_ext[j] = tt;
+          const float tt = code_score(x[t]) - 2.f * st.eq[j] * maxn;   // NaN (k CTAs hold NaN rows) maps to the top code:
+          if (tt == tt) atomicMax(p.gthr + q0 + j, score_code(tt));   // not a usable bound, skip it
         }
+      }
+    }
+    for (int j = lane; j < nq_pass; j += 32) {
+      uint32_t code;
+      asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(code) : "l"(p.gthr + q0 + j));
+      if (code != 0u) {
+        const float tt = code_score(code);
+        if (tt > thr_ext[j]) thr_ext[j] = tt;
       }
     }
     for (unsigned slept = 0; slept < pause_ns && !*done; slept += 1000) __nanosleep(pause_ns < 1000 ? pause_ns : 1000);
@@ -713,12 +728,13 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap bank_map, const __grid_consta
   // needs ||row||^2 either way (normalised scores, or max ||row|| for the error bound of plain dot scores)
   const bool norm_warps = FILT ? p.row_sumsq == nullptr
                                : !(BF && (p.row_sumsq != nullptr || !(p.flags & DEVQA_NORMALIZE_BANK)));
-  // Tile sequence of this CTA: its strided tiles, then (filter variant, long scans) the first `boot` tiles AGAIN:
-  // on their first visit the epilogue only learns each query's best upper bound from them (thresholds for everyone
-  // through the service warps), on the second it treats them like any other tile -- with thresholds in place.
-  // Without this, the first two tiles of every CTA cost as much as ~40 ordinary ones (lists built from nothing).
+  // Tile sequence of this CTA: its strided tiles, then (filter variant, 8+ tiles) the first tile AGAIN: on its
+  // first visit the epilogue only learns each query's best upper bound from it (thresholds for everyone through
+  // the service warps) and waits a bounded moment for them; on the second visit it is a tile like any other --
+  // with thresholds in place.  Without this, the first two tiles of every CTA cost as much as ~40 ordinary ones
+  // (lists built from nothing, one insertion at a time).
   const int n_my = (p.n_tiles - tile0 + tile_step - 1) / tile_step;
-  const int boot = (FILT && n_my >= 32 && tile_step >= p.k_true && p.gmax && !(p.flags & kDbgNoBoot)) ? 4 : 0;
+  const int boot = (FILT && n_my >= 8 && tile_step >= p.k_true && p.gmax && !(p.flags & kDbgNoBoot)) ? 1 : 0;
   const int n_iter = n_my + boot;
   auto tile_at = [&](int it) { return tile0 + (it < n_my ? it : it - n_my) * tile_step; };
   const int set_kb = FILT ? nkb : kSetKBlocks;           // k-blocks accumulated inside the tensor core
@@ -898,10 +914,9 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap bank_map, const __grid_consta
         if (lane == 0) atomicMax(p.max_sumsq, __float_as_uint(max_ss));   // non-negative floats order like their bits
       }
     }
-  } else if (FILT && (warp == 3 || (warp >= 4 && warp < 8))) {
-    // ===== service warps, filter variant (warps 4-7 only when they are not busy with row norms) =====
-    if (warp == 3) filt_service(p, st, q0, nq_pass, tile_step, maxn, 0, norm_warps ? 1 : 5, lane);
-    else filt_service(p, st, q0, nq_pass, tile_step, maxn, warp - 3, 5, lane);
+  } else if (FILT && warp == 3) {
+    // ===== service warp, filter variant: threshold exchange between CTAs =====
+    filt_service(p, st, q0, nq_pass, tile_step, tile0, maxn, lane);
   } else if (warp >= 8 && FILT) {
     // ===== epilogue warps, filter variant: scan + hit queue (filt_epilogue) =====
     filt_epilogue<QP>(p, st, lists, norms, norm_warps, tmem_base, tmem_full, tmem_empty, tile0, tile_step, n_my, boot, q0, nq_pass,
@@ -1039,13 +1054,20 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap bank_map, const __grid_consta
 // is one contiguous, shared-memory-ready copy.  One warp per query.
 __global__ void __launch_bounds__(256) prep_queries_kernel(const float* __restrict__ q, int64_t q_ld, int n_queries, int dim,
                                                            int qp, int n_kblocks, int q_pad, unsigned flags,
-                                                           float* __restrict__ qcat, uint32_t* __restrict__ gthr) {
+                                                           float* __restrict__ qcat, uint32_t* __restrict__ gthr,
+                                                           const uint32_t* __restrict__ need) {
   if (blockIdx.x == 0)
     for (int i = threadIdx.x; i < q_pad; i += blockDim.x) gthr[i] = 0u;
   const int lane = threadIdx.x & 31;
   const int warps = gridDim.x * (blockDim.x >> 5);
   const int d_pad = n_kblocks * kBlockK;
   for (int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < q_pad; r += warps) {
+    if (need) {                                          // conditional (fallback) run: only passes with a flagged query
+      const int p0 = r / qp * qp;
+      bool any = false;
+      for (int i = p0 + lane; i < p0 + qp && i < n_queries; i += 32) any |= need[i] != 0u;
+      if (!__any_sync(kFull, any)) continue;
+    }
     float inv = 0.f;
     const float* src = q + size_t(r < n_queries ? r : 0) * q_ld;
     if (r < n_queries) {
@@ -1082,9 +1104,12 @@ __global__ void __launch_bounds__(256) prep_queries_filt_kernel(const float* __r
                                                                 int qp, int n_kblocks, int q_pad, unsigned flags,
                                                                 float* __restrict__ qcat, uint32_t* __restrict__ gthr,
                                                                 float* __restrict__ qinv, float* __restrict__ qerr,
-                                                                uint32_t* __restrict__ seed_u) {
+                                                                uint32_t* __restrict__ seed_u, uint32_t* __restrict__ gmax,
+                                                                int gmax_stride) {
   if (blockIdx.x == 0)
     for (int i = threadIdx.x; i < q_pad; i += blockDim.x) { gthr[i] = 0u; seed_u[i] = 0u; }
+  if (gmax)                                              // threshold exchange: no CTA has published anything yet
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < q_pad * gmax_stride; i += gridDim.x * blockDim.x) gmax[i] = 0u;
   const int lane = threadIdx.x & 31;
   const int warps = gridDim.x * (blockDim.x >> 5);
   const int d_pad = n_kblocks * kBlockK;
@@ -1211,7 +1236,8 @@ size_t scan_tc_qcat_bytes(int mode, int64_t dim, int q_pad) {
 }
 
 // Queries per pass + pipeline depth that fit in shared memory / tensor memory for this list capacity.
-int scan_tc_plan(int mode, int n_queries, int64_t dim, int kcap, bool cached_norms, int* qp_out, int* stages_out) {
+int scan_tc_plan(int mode, int n_queries, int64_t dim, int kcap, bool cached_norms, int64_t n_tiles, int sm_count,
+                 int* qp_out, int* stages_out) {
   const bool bf = mode == kTcBf16x3, filt = mode == kTcTf32x1;
   // more than one K-set (1024 fp32 / 2048 bf16 columns) sums K-sets in the epilogue's registers (MULTI):
   // 32 queries per pass at most.  The filter keeps the whole K chain in the tensor core (its error bound
@@ -1221,6 +1247,9 @@ int scan_tc_plan(int mode, int n_queries, int64_t dim, int kcap, bool cached_nor
   while (qp > 16 && qp / 2 >= q16) qp >>= 1;
   // 129..192 queries: two passes of 128 at the HBM-bound rate beat one shared-memory-bound pass of 256
   if (qp == 256 && n_queries <= 192) qp = 128;
+  // banks of fewer tiles than SMs: narrower passes run side by side, so that tiles x passes covers the machine
+  if (filt)
+    while (qp > 32 && n_tiles * ((n_queries + qp - 1) / qp) < sm_count) qp >>= 1;
   for (; qp >= 16; qp >>= 1) {
     for (int stages = kMaxStages; stages >= 3; --stages) {
       // TMEM: 2 accumulator buffers of 3*qp (filter: qp) columns (+ one 32-column lo tile per stage for 3xTF32)
@@ -1238,18 +1267,18 @@ int scan_tc_plan(int mode, int n_queries, int64_t dim, int kcap, bool cached_nor
 // qcat must hold scan_tc_qcat_bytes(); q_pad is a multiple of qp; gthr [q_pad] is zeroed here.
 int scan_tc_prep_queries(int mode, const float* queries, int64_t query_ld, int n_queries, int qp, int q_pad,
                          int64_t dim, unsigned flags, void* qcat, uint32_t* gthr, float* qinv, float* qerr,
-                         uint32_t* seed_u, cudaStream_t stream) {
+                         uint32_t* seed_u, uint32_t* gmax, int gmax_stride, const uint32_t* need, cudaStream_t stream) {
   const int n_kblocks = scan_tc_kblocks(mode, dim);
   const int grid = (q_pad + 7) / 8;
   if (mode == kTcTf32x3)
     prep_queries_kernel<<<grid, 256, 0, stream>>>(queries, query_ld, n_queries, int(dim), qp, n_kblocks, q_pad, flags,
-                                                  static_cast<float*>(qcat), gthr);
+                                                  static_cast<float*>(qcat), gthr, need);
   else if (mode == kTcBf16x3)
     prep_queries_bf16_kernel<<<grid, 256, 0, stream>>>(queries, query_ld, n_queries, int(dim), qp, n_kblocks, q_pad, flags,
                                                        static_cast<__nv_bfloat16*>(qcat), gthr);
   else
     prep_queries_filt_kernel<<<grid, 256, 0, stream>>>(queries, query_ld, n_queries, int(dim), qp, n_kblocks, q_pad, flags,
-                                                       static_cast<float*>(qcat), gthr, qinv, qerr, seed_u);
+                                                       static_cast<float*>(qcat), gthr, qinv, qerr, seed_u, gmax, gmax_stride);
   DEVQA_CUDA(cudaGetLastError());
   count_launch();
   return DEVQA_OK;

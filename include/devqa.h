@@ -78,6 +78,8 @@ extern "C" {
 #define DEVQA_FORCE_TF32X3 (1u << 10)   /* testing/benchmark: tcgen05 path without the TF32 filter + exact
                                            re-scoring stage (every score straight from the 3xTF32 split)  */
 
+#define DEVQA_FORCE_FILTER (1u << 11)   /* testing/benchmark: TF32 filter + exact re-scoring also on banks the
+                                           library would scan with 3xTF32 alone (fewer than 8 tiles per SM)     */
 #define DEVQA_DEBUG_FILTER_ONLY (1u << 22) /* tests: return the TF32 filter's approximate top-k as is (no exact
                                               re-scoring) so that its error bound can be checked            */
 

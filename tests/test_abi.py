@@ -48,7 +48,9 @@ def test_header_constants_match_binding(built_lib):
     for cname, pyname in [("DEVQA_MAX_TOPK", "MAX_TOPK"), ("DEVQA_F32", "F32"), ("DEVQA_BF16", "BF16"),
                           ("DEVQA_NORMALIZE_BANK", "NORMALIZE_BANK"), ("DEVQA_NORMALIZE_QUERY", "NORMALIZE_QUERY"),
                           ("DEVQA_NOEPS", "NOEPS"), ("DEVQA_E_INVALID", "E_INVALID"), ("DEVQA_E_UNSUPPORTED", "E_UNSUPPORTED"),
-                          ("DEVQA_E_NCCL", "E_NCCL"), ("DEVQA_FORCE_STREAM", "FORCE_STREAM"), ("DEVQA_FORCE_TENSOR", "FORCE_TENSOR")]:
+                          ("DEVQA_E_NCCL", "E_NCCL"), ("DEVQA_FORCE_STREAM", "FORCE_STREAM"), ("DEVQA_FORCE_TENSOR", "FORCE_TENSOR"),
+                          ("DEVQA_FORCE_TF32X3", "FORCE_TF32X3"), ("DEVQA_FORCE_FILTER", "FORCE_FILTER"),
+                          ("DEVQA_DEBUG_FILTER_ONLY", "DEBUG_FILTER_ONLY")]:
         assert const(cname) == getattr(L, pyname), cname
 
 

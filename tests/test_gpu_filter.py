@@ -14,6 +14,7 @@ from oracle import semantic_search as ss
 pytestmark = pytest.mark.gpu
 L = devqa_b200._lib
 GAP, RTOL, ATOL = 1e-5, 1e-5, 1e-6
+FILTER = L.FORCE_TENSOR | L.FORCE_FILTER     # small banks would otherwise be scanned with 3xTF32 alone
 
 
 def _randn(n, d, seed, unit=True):
@@ -60,7 +61,7 @@ def test_filter_matches_stream_kernel_bit_for_bit(n, d, nq, k, nb, nq_mode):
     bank, q = _randn(n, d, n + d, unit=False), _randn(nq, d, nq + k, unit=False)
     fb = FactBank.from_embeddings(bank)
     _fallbacks()
-    a = fb.search(q.cuda(), k, normalize_bank=nb, normalize_query=nq_mode, flags=L.FORCE_TENSOR)
+    a = fb.search(q.cuda(), k, normalize_bank=nb, normalize_query=nq_mode, flags=FILTER)
     assert _fallbacks() == 0
     b = fb.search(q.cuda(), k, normalize_bank=nb, normalize_query=nq_mode, flags=L.FORCE_STREAM)
     assert torch.equal(a[1], b[1])
@@ -77,11 +78,12 @@ def test_filter_on_caller_owned_tensor_without_cached_norms():
     dev_bank, dev_q = bank.cuda(), q.cuda()
     for normalise in (True, False):
         score_fn = devqa_b200.util.cos_sim if normalise else devqa_b200.util.dot_score
-        hits = devqa_b200.util.semantic_search(dev_q, dev_bank, top_k=10, score_function=score_fn)
+        s, i = devqa_b200.util.semantic_search_arrays(dev_q, dev_bank, top_k=10, score_function=score_fn, flags=FILTER)
         truth = ss.truth_scores_fp64(q, bank, normalize_bank=normalise, normalize_query=normalise)
-        s = np.array([[h["score"] for h in row] for row in hits], dtype=np.float32)
-        i = np.array([[h["corpus_id"] for h in row] for row in hits])
-        ss.compare_topk(s, i, truth, 10, gap=GAP, rtol=RTOL, atol=ATOL)
+        ss.compare_topk(s.cpu().numpy(), i.cpu().numpy(), truth, 10, gap=GAP, rtol=RTOL, atol=ATOL)
+        s2, i2 = devqa_b200.util.semantic_search_arrays(dev_q, dev_bank, top_k=10, score_function=score_fn, flags=L.FORCE_STREAM)
+        if normalise:                                        # the filter ran (cos_sim): bit-identical to the stream kernel
+            assert torch.equal(i, i2) and torch.equal(s, s2)
 
 
 @pytest.mark.parametrize("kind", ["randn", "positive", "hidden", "hidden4096"])
@@ -101,7 +103,7 @@ def test_filter_error_bound_holds(kind):
     d = bank.shape[1]
     fb = FactBank.from_embeddings(bank)
     for nb, nqm in (("eps", "eps"), (None, None)):
-        u, i = fb.search(q.cuda(), 32, normalize_bank=nb, normalize_query=nqm, flags=L.FORCE_TENSOR | L.DEBUG_FILTER_ONLY)
+        u, i = fb.search(q.cuda(), 32, normalize_bank=nb, normalize_query=nqm, flags=FILTER | L.DEBUG_FILTER_ONLY)
         u, i = u.cpu().double().numpy(), i.cpu().numpy()
         truth = ss.truth_scores_fp64(q, bank, normalize_bank=bool(nb), normalize_query=bool(nqm))
         exact = np.take_along_axis(truth, i, axis=1)
@@ -125,7 +127,7 @@ def test_duplicated_rows_take_the_exact_fallback():
     q = torch.cat([bank[1000:1001] + 0.01 * _randn(1, 256, 12), _randn(15, 256, 13)])
     fb = FactBank.from_embeddings(bank)
     _fallbacks()
-    s, i = fb.search(q.cuda(), 32, flags=L.FORCE_TENSOR)
+    s, i = fb.search(q.cuda(), 32, flags=FILTER)
     n_fb = _fallbacks()
     assert 1 <= n_fb <= 2
     assert i[0].tolist() == list(range(1000, 1032))
@@ -137,12 +139,42 @@ def test_duplicated_rows_take_the_exact_fallback():
     fb.close()
 
 
+@pytest.mark.parametrize("n,d,nq,k", [(40000, 128, 70, 32), (25000, 384, 130, 5), (60000, 64, 300, 16), (19000, 768, 64, 64)])
+def test_filter_midsize_banks_refine_from_the_per_cta_lists(n, d, nq, k):
+    """>= 148 tiles: the CTAs exchange their bests and refine picks its candidates out of the per-CTA lists."""
+    bank, q = _randn(n, d, n + 1, unit=False), _randn(nq, d, nq + 2, unit=False)
+    fb = FactBank.from_embeddings(bank)
+    _fallbacks()
+    a = fb.search(q.cuda(), k, flags=FILTER)
+    nfb = _fallbacks()
+    b = fb.search(q.cuda(), k, flags=L.FORCE_STREAM)
+    truth = ss.truth_scores_fp64(q, bank)
+    ss.compare_topk(a[0].cpu().numpy(), a[1].cpu().numpy(), truth, k, gap=GAP, rtol=RTOL, atol=ATOL)
+    if nfb == 0:
+        assert torch.equal(a[1], b[1]) and torch.equal(a[0], b[0])
+    assert nfb <= nq // 8
+    fb.close()
+
+
+def test_duplicated_rows_midsize_take_the_exact_fallback():
+    bank = _randn(30000, 128, 61)
+    bank[5000:5400] = bank[5000]
+    q = torch.cat([bank[5000:5001] + 0.01 * _randn(1, 128, 62), _randn(31, 128, 63)])
+    fb = FactBank.from_embeddings(bank)
+    _fallbacks()
+    s, i = fb.search(q.cuda(), 32, flags=FILTER)
+    assert _fallbacks() >= 1
+    assert i[0].tolist() == list(range(5000, 5032))
+    ss.compare_topk(s.cpu().numpy(), i.cpu().numpy(), ss.truth_scores_fp64(q, bank), 32, gap=GAP, rtol=RTOL, atol=ATOL)
+    fb.close()
+
+
 def test_clustered_scores_stay_exact():
     """All-positive rows: cosine scores crowd into a narrow band, most queries fail the proof."""
     g = torch.Generator().manual_seed(21)
     bank, q = torch.rand(20000, 384, generator=g), torch.rand(24, 384, generator=g)
     fb = FactBank.from_embeddings(bank)
-    s, i = fb.search(q.cuda(), 16, flags=L.FORCE_TENSOR)
+    s, i = fb.search(q.cuda(), 16, flags=FILTER)
     truth = ss.truth_scores_fp64(q, bank)
     ss.compare_topk(s.cpu().numpy(), i.cpu().numpy(), truth, 16, gap=GAP, rtol=RTOL, atol=ATOL)
     fb.close()
@@ -154,9 +186,9 @@ def test_nan_rows_and_zero_rows():
     bank[99, 5] = float("nan")
     q = _randn(10, 128, 32, unit=False)
     fb = FactBank.from_embeddings(bank)
-    s, i = fb.search(q.cuda(), 4, normalize_bank="noeps", normalize_query="noeps", flags=L.FORCE_TENSOR)
+    s, i = fb.search(q.cuda(), 4, normalize_bank="noeps", normalize_query="noeps", flags=FILTER)
     assert set(i[:, :2].flatten().tolist()) == {17, 99} and torch.isnan(s[:, :2]).all()
-    s, i = fb.search(q.cuda(), 4, flags=L.FORCE_TENSOR)               # eps clamp: the zero row scores 0, NaN row first
+    s, i = fb.search(q.cuda(), 4, flags=FILTER)               # eps clamp: the zero row scores 0, NaN row first
     assert (i[:, 0] == 99).all() and torch.isnan(s[:, 0]).all()
     fb.close()
 
@@ -178,14 +210,14 @@ def test_sharded_filter_equals_single_bank():
     """Chunked round-robin id map: re-scoring inverts it to find the local row."""
     bank, q = _randn(9000, 192, 51), _randn(40, 192, 52)
     whole = FactBank.from_embeddings(bank)
-    ref = whole.search(q.cuda(), 16)
+    ref = whole.search(q.cuda(), 16, flags=L.FORCE_STREAM)
     chunk, world = 500, 3
     keys = []
     for rank in range(world):
         rows = torch.cat([bank[c * chunk:(c + 1) * chunk] for c in range(rank, 18, world)])
         fb = FactBank.from_embeddings(rows)
         fb.set_id_map(0, chunk, rank, world)
-        keys.append(fb.search_packed(q.cuda(), 16, flags=L.FORCE_TENSOR))
+        keys.append(fb.search_packed(q.cuda(), 16, flags=FILTER))
         fb.close()
     s, i = devqa_b200.bank.topk_merge(torch.stack(keys).contiguous(), 16)
     assert torch.equal(i, ref[1]) and torch.equal(s, ref[0])

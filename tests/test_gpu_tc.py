@@ -32,7 +32,7 @@ def _check_tc(bank_cpu, q_cpu, k, nb="eps", nq="eps"):
     fb = FactBank.from_embeddings(bank_cpu)
     kk = min(k, len(bank_cpu))
     truth = ss.truth_scores_fp64(q_cpu, bank_cpu, normalize_bank=bool(nb), normalize_query=bool(nq))
-    for variant in (L.FORCE_TENSOR, L.FORCE_TENSOR | L.FORCE_TF32X3):
+    for variant in (L.FORCE_TENSOR | L.FORCE_FILTER, L.FORCE_TENSOR | L.FORCE_TF32X3):
         s, i = fb.search(q_cpu.cuda(), k, normalize_bank=nb, normalize_query=nq, flags=variant)
         s, i = s.cpu().numpy(), i.cpu().numpy()
         stats = ss.compare_topk(s[:, :kk], i[:, :kk], truth, k, gap=GAP, rtol=RTOL, atol=ATOL)
