@@ -78,3 +78,100 @@ class EditPool:
         mask = sims > proto
         ids = torch.masked_select(order, mask)
         return list(torch.split(ids, mask.sum(1).tolist())), (sims, order)
+
+
+class VocabBank:
+    """N2: ``BaseVLLMForEdit.find_closest_tokens`` (editor/vllms_for_edit/base.py:187-196) --
+    cosine top-k of hidden states against the vocabulary embedding matrix ``[V, d]`` -- with the matrix
+    resident in a FactBank instead of being re-normalised (a full ``[V, d]`` temporary) on every call.
+
+    The reference normalises the *queries* over ``dim=1`` of a ``[b, l, d]`` tensor, i.e. across the sequence
+    axis, not the feature axis; parity means reproducing exactly that (it is a tiny ``[b, l, d]`` pre-scale
+    done in torch), while the matrix rows get the fused ``x / ||x||`` (no eps) of the scan kernels."""
+
+    def __init__(self, embedding_matrix, device=0, dtype: str = "fp32"):
+        m = torch.as_tensor(embedding_matrix)
+        self.bank = FactBank.from_embeddings(m.detach().to(torch.float32), device=device, dtype=dtype)
+        self.dim = m.shape[1]
+
+    def __len__(self) -> int:
+        return len(self.bank)
+
+    def close(self) -> None:
+        self.bank.close()
+
+    def find_closest_tokens(self, embeddings: torch.Tensor, top_k: int = 1) -> Tuple[torch.Tensor, torch.Tensor]:
+        """embeddings ``[b, l, d]`` -> ``(toks [b, l, top_k] int64, sim [b, l, top_k] fp32)`` on the bank's device,
+        ordered like ``torch.topk`` (descending)."""
+        if embeddings.dim() != 3 or embeddings.shape[2] != self.dim:
+            raise ValueError(f"embeddings must be [b, l, {self.dim}]")
+        e = embeddings.detach().to(device=self.bank.device, dtype=torch.float32)
+        e = e / e.norm(dim=1, keepdim=True)                     # base.py:190 (sic: the sequence axis)
+        b, l, d = e.shape
+        s, i = self.bank.search(e.reshape(b * l, d), int(top_k), normalize_bank="noeps", normalize_query=None)
+        return i.view(b, l, top_k), s.view(b, l, top_k)
+
+
+class LiveEditPool:
+    """N3: the hard-routing similarity of LiveEdit's ``retrieve_moes``
+    (editor/vllm_editors/liveedit/liveedit.py:132-153): ``einsum('bed,med->bme', ivr, evr_pool).mean(2) *
+    sim_scale`` against a pool ``[m, eqe_n, module_dim]`` that grows by ``torch.cat`` per edit (:223-226),
+    compared with the similarity to a prototype; every pool entry ABOVE it is routed to (a boolean mask, no
+    top-k).  The mean over the ``eqe_n`` slots of per-slot dot products is one dot product over the flattened
+    ``eqe_n * module_dim`` vector divided by ``eqe_n``, so the pool is a FactBank of that width, appended in
+    place, and the mask comes out of the same streaming scan (all rows above the threshold, ascending ids --
+    the order ``pool[retrieval_map]`` yields)."""
+
+    def __init__(self, eqe_n: int, module_dim: int, device=0, capacity: int = 1024):
+        self.eqe_n, self.module_dim = int(eqe_n), int(module_dim)
+        self.dim = self.eqe_n * self.module_dim
+        self.bank = FactBank(self.dim, device=device, capacity=capacity)
+
+    def __len__(self) -> int:
+        return len(self.bank)
+
+    def append(self, evr) -> None:
+        """``edit_one_piece`` (:223-226): ``evr`` is ``[n, eqe_n, module_dim]``."""
+        t = torch.as_tensor(evr)
+        self.bank.append(t.reshape(-1, self.dim))
+
+    def restore(self, n_rows: int = 0) -> None:
+        """``restore_to_original_model`` (:209-214)."""
+        self.bank.truncate(n_rows)
+
+    def similarities(self, ivr, sim_scale: float, top: int) -> Tuple[torch.Tensor, torch.Tensor]:
+        """The ``top`` largest ``vis_sim`` values and their pool ids (descending), device tensors."""
+        q = torch.as_tensor(ivr).reshape(1, self.dim)
+        s, i = self.bank.search(q, top, normalize_bank=None, normalize_query=None)
+        return s[0] * (float(sim_scale) / self.eqe_n), i[0]
+
+    def retrieve(self, ivr, vis_sim_prot, sim_scale: float) -> Tuple[torch.Tensor, torch.Tensor]:
+        """``retrieval_map = vis_sim > vis_sim_prot`` as the ascending id list of the selected pool entries, plus
+        their similarities.  ``ivr``: ``[1, eqe_n, module_dim]``; ``vis_sim_prot``: the ``[1, 1]`` prototype
+        similarity the caller computed (:140-141)."""
+        m = len(self.bank)
+        dev = self.bank.device
+        if m == 0:
+            return torch.empty(0, dtype=torch.int64, device=dev), torch.empty(0, device=dev)
+        thr = float(torch.as_tensor(vis_sim_prot).reshape(-1)[0])
+        step = L.MAX_TOPK
+        s, i = self.similarities(ivr, sim_scale, min(m, step))
+        if m > step and float(s[-1]) > thr:
+            # more than MAX_TOPK entries may pass: enumerate the pool in row ranges (each a search over a slice of
+            # the same resident buffer, ids offset by the range start)
+            q = self.bank._prep_queries(torch.as_tensor(ivr).reshape(1, self.dim))
+            parts_s, parts_i = [], []
+            row_bytes = ((self.dim + 3) // 4 * 4) * 4
+            for start in range(0, m, step):
+                n = min(step, m - start)
+                ps = torch.empty((1, n), dtype=torch.float32, device=dev)
+                pi = torch.empty((1, n), dtype=torch.int64, device=dev)
+                L.check(L.lib().devqa_search_raw(self.bank.data_ptr + start * row_bytes, self.bank.dtype, n, self.dim,
+                                                 row_bytes // 4, q.data_ptr(), 1, self.dim, n, 0, start,
+                                                 ps.data_ptr(), pi.data_ptr(), _stream_ptr(self.bank.device_index)))
+                parts_s.append(ps[0] * (float(sim_scale) / self.eqe_n))
+                parts_i.append(pi[0])
+            s, i = torch.cat(parts_s), torch.cat(parts_i)
+        keep = s > thr
+        ids, order = torch.sort(i[keep])
+        return ids, s[keep][order]

@@ -71,3 +71,51 @@ def test_recipe_topk_above_prototype():
     assert [w.tolist() for w in want] == [x.cpu().tolist() for x in got]
     assert set(got[0].cpu().tolist()[:2]) == {5, 9}
     torch.testing.assert_close(gs.cpu(), sorted_sim[:, :k], rtol=1e-5, atol=1e-5)
+
+
+def test_find_closest_tokens_matches_reference_composition():
+    """N2, editor/vllms_for_edit/base.py:187-196 -- including its normalisation of the queries over dim=1 of
+    [b, l, d] (the sequence axis)."""
+    from devqa_b200 import VocabBank
+    g = _g(4)
+    v, d, b, l, k = 3000, 512, 2, 7, 5
+    matrix = torch.randn(v, d, generator=g)
+    emb = matrix[torch.randint(0, v, (b, l), generator=g)] + 0.3 * torch.randn(b, l, d, generator=g)
+    e_n = emb / emb.norm(dim=1, keepdim=True)
+    m_n = matrix / matrix.norm(dim=1, keepdim=True)
+    ref = torch.topk(torch.matmul(e_n, m_n.T), k, dim=-1)
+    vb = VocabBank(matrix)
+    toks, sim = vb.find_closest_tokens(emb, top_k=k)
+    assert toks.shape == (b, l, k) and toks.cpu().tolist() == ref.indices.tolist()
+    torch.testing.assert_close(sim.cpu(), ref.values, rtol=1e-5, atol=1e-6)
+    vb.close()
+
+
+@pytest.mark.parametrize("m", [0, 1, 37, 1500])
+def test_liveedit_hard_routing_mask(m):
+    """N3, liveedit.py:132-143: vis_sim = einsum('bed,med->bme').mean(2) * scale; map = vis_sim > prototype sim."""
+    from devqa_b200 import LiveEditPool
+    g = _g(5 + m)
+    eqe_n, md, scale = 4, 256, 10.0
+    pool_ref = torch.zeros(0, eqe_n, md)
+    pool = LiveEditPool(eqe_n, md, capacity=2)
+    for start in range(0, m, 100):                               # grown edit by edit (here: in small batches)
+        new = torch.randn(min(100, m - start), eqe_n, md, generator=g) / md ** 0.5
+        pool_ref = torch.cat([pool_ref, new], 0)
+        pool.append(new)
+    ivr = torch.randn(1, eqe_n, md, generator=g)
+    prot = torch.randn(1, eqe_n, md, generator=g) * (0.0 if m == 1500 else 0.05)   # m = 1500: about half pass (> MAX_TOPK)
+    vis_sim = torch.einsum('bed,med->bme', ivr, pool_ref).mean(2) * scale
+    vis_sim_prot = torch.einsum('bed,bed->be', ivr, prot).mean(1, True) * scale
+    safe = (vis_sim - vis_sim_prot).abs()[0] > 1e-5                 # entries whose verdict does not hinge on the last bits
+    want = (vis_sim > vis_sim_prot)[0]
+    ids, sims = pool.retrieve(ivr, vis_sim_prot, scale)
+    got = torch.zeros(m, dtype=torch.bool)
+    got[ids.cpu()] = True
+    assert torch.equal(got[safe], want[safe])
+    assert ids.cpu().tolist() == sorted(ids.cpu().tolist())
+    torch.testing.assert_close(sims.cpu(), vis_sim[0][ids.cpu()], rtol=1e-5, atol=1e-5)
+    if m == 1500:
+        assert len(ids) > 600
+        pool.restore(10)
+        assert len(pool) == 10 and bool((pool.retrieve(ivr, vis_sim_prot, scale)[0] < 10).all())
