@@ -172,6 +172,17 @@ def measured_peak():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def measured_tf32_peak():
+    """Dense TF32 tensor throughput to hold the large-batch regimes against: half of the measured SUSTAINED bf16
+    cuBLAS figure (TF32 runs at half the bf16 rate; sustained because these are long, power-capped steps)."""
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["bf16_tflops_sustained"]) / 2.0, "MEASURED_PEAKS.json bf16_tflops_sustained / 2"
+    except Exception:                   # noqa: BLE001
+        return 1125.0 * 0.62, "fallback: nominal 1125 TF32 TFLOP/s x 0.62 (sustained / nominal bf16 in B200_PROFILING.md)"
+
+
 def ncu_traffic(a, rows_local, q_per_launch):
     """dram bytes per scan launch from a committed ncu --set full capture of the same shape, else None."""
     path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
@@ -335,9 +346,11 @@ def run_ours(a):
             passes = sl.value / max(1, sr.value)
             # useful flops of the contraction (2*Q*N*D, split / filter overhead not counted), whole job
             tflops = 2.0 * nq * a.rows * a.dim / (ms * 1e-3) / 1e12
+            tf32_peak, tf32_src = measured_tf32_peak()
             regimes.append({"queries_per_call": nq, "ms_per_call": ms, "queries_per_s": nq / (ms * 1e-3),
                             "scan_gbs_per_gpu": gbs, "frac_of_measured_hbm": gbs / peak,
                             "useful_tflops": tflops,
+                            "frac_of_tf32_tensor_peak": tflops / (tf32_peak * world), "tf32_peak_source": tf32_src,
                             "kernel": ("stream" if nq <= 4 else ("tcgen05 TF32 filter + exact re-scoring"
                                        if a.bank_dtype == "fp32" and a.topk <= 64 else "tcgen05")),
                             "bank_passes_per_call": passes,

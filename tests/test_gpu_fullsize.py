@@ -137,3 +137,36 @@ def test_chunked_id_map_on_device():
     assert torch.equal(i, ref_i) and torch.equal(s, ref_s)
     assert i[:, 0].cpu().tolist() == [3, 300, 5000, 9999]
     full.close()
+
+
+def test_c4_shape_large_batch_equals_the_stream_kernel():
+    """BASELINE C4 on one GPU: 10M x 768 fp32 bank, 4096 queries, k = 32 -- 16 tensor-core filter passes of 256
+    queries.  Checked through properties that do not need an oracle at this size: (i) a sample of the queries
+    re-run through the CUDA-core stream kernel (4 at a time) returns bit-identical scores and ids; (ii) planted
+    queries find their own row first with score 1; (iii) every returned list is sorted and duplicate-free;
+    (iv) no query needed the exact fallback."""
+    import ctypes as C
+    L = devqa_b200._lib
+    n, nq = 10_000_000, 4096
+    fb = FactBank(D, capacity=n)
+    for r0 in range(0, n, 1 << 20):
+        fb.append_synthetic(min(1 << 20, n - r0), seed=4234, first_global_row=r0)
+    q = _queries(nq, 8678)
+    planted = torch.tensor([0, 127, 128, 4_999_999, 9_999_999])
+    for slot, row in enumerate(planted.tolist()):
+        q[slot * 7] = fb.rows(row, row + 1)[0]
+    cnt = C.c_int64()
+    L.check(L.lib().devqa_filter_fallbacks(0, C.byref(cnt)))
+    s, i = fb.search(q, K)
+    L.check(L.lib().devqa_filter_fallbacks(0, C.byref(cnt)))
+    assert cnt.value == 0
+    assert i[torch.arange(len(planted)) * 7, 0].cpu().tolist() == planted.tolist()
+    torch.testing.assert_close(s[torch.arange(len(planted)) * 7, 0], torch.ones(len(planted), device="cuda"), rtol=1e-5, atol=1e-5)
+    assert bool((s[:, 1:] <= s[:, :-1]).all())
+    assert all(len(set(row)) == K for row in i[::97].cpu().tolist())
+    sample = torch.cat([torch.arange(0, 32, 7), torch.tensor([255, 256, 1023, 1024, 2047, 4095])])
+    for lo in range(0, len(sample), 4):
+        sel = sample[lo:lo + 4]
+        s2, i2 = fb.search(q[sel], K, flags=L.FORCE_STREAM)
+        assert torch.equal(i2, i[sel]) and torch.equal(s2, s[sel])
+    fb.close()
