@@ -171,8 +171,12 @@ static int tc_pipeline(Scratch* s, const SearchArgs& a, int mode, FilterSide* si
     return rc;
   const int q_pad = int((a.n_queries + qp - 1) / qp) * qp;
   const size_t qcat_bytes = scan_tc_qcat_bytes(mode, a.dim, q_pad);
-  if ((rc = grow(reinterpret_cast<void**>(&s->qsplit), &s->qsplit_bytes, qcat_bytes + size_t(q_pad) * 4, false))) return rc;
+  const bool exchange = scan_tc_exchanges_thresholds(mode, a.dim);
+  if ((rc = grow(reinterpret_cast<void**>(&s->qsplit), &s->qsplit_bytes,
+                 qcat_bytes + size_t(q_pad) * 4 + (exchange && !side ? size_t(q_pad) * kGmaxStride * 4 : 0), false)))
+    return rc;
   uint32_t* gthr = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(s->qsplit) + qcat_bytes);   // shared per-query thresholds
+  uint32_t* gmax = side ? side->gmax : (exchange ? gthr + q_pad : nullptr);
   const int64_t tiles = (a.n_rows + 127) / 128;
   // Large banks: one pass per launch on every SM.  Small banks: several passes side by side so that
   // tiles x passes still covers the SMs.
@@ -193,22 +197,22 @@ static int tc_pipeline(Scratch* s, const SearchArgs& a, int mode, FilterSide* si
   p.cand = s->cand; p.need = need;
   if (side) {
     p.qerr = side->qerr; p.k_true = a.top_k; p.lostu = side->lostu; p.bank_max_sumsq = a.max_sumsq;
-    p.gmax = side->gmax; p.gmax_stride = kGmaxStride;
     side->n_lists = grid;
-    DEVQA_REQUIRE(grid <= kGmaxStride, "more CTAs per pass than the threshold exchange holds");
   }
+  p.gmax = gmax; p.gmax_stride = kGmaxStride;
+  DEVQA_REQUIRE(grid <= kGmaxStride, "more CTAs per pass than the threshold exchange holds");
 
   const bool prof = s->profiling && !need && s->prof_used < Scratch::kProfSlots;
   if (prof) DEVQA_CUDA(cudaEventRecord(s->prof_ev[2 * s->prof_used], stream));
   if ((rc = scan_tc_prep_queries(mode, a.queries, a.query_ld, int(a.n_queries), qp, q_pad, a.dim, a.flags, s->qsplit, gthr,
                                  side ? side->qinv : nullptr, side ? side->qerr : nullptr, side ? side->seed_u : nullptr,
-                                 side ? side->gmax : nullptr, kGmaxStride, need, stream)))
+                                 gmax, kGmaxStride, need, stream)))
     return rc;
   // Threshold seeding: scan a prefix sample of the bank (one tile per CTA) first; the k-th best score of a
   // SUBSET is a lower bound of the k-th best of the whole bank, so the main scan starts with tight
   // thresholds in every CTA instead of each CTA re-learning them (k ln(n/k) list insertions each).
   // (the filter variant exchanges thresholds between CTAs while it runs and needs no seeding)
-  const bool seed = tiles >= 8 * int64_t(ctas_per_pass) && !(a.flags & (1u << 21)) && !need && (!side || (a.flags >> 24) & 0xfu);
+  const bool seed = tiles >= 8 * int64_t(ctas_per_pass) && !(a.flags & (1u << 21)) && !need && (!exchange || (a.flags >> 24) & 0xfu);
   if (seed) {
     ScanParams pre = p;
     int seed_tiles = int((a.flags >> 24) & 0xfu);           // undocumented: sample tiles per CTA (benchmark sweeps)

@@ -55,6 +55,7 @@ bool scan_tc_supported(int bank_dtype, const void* bank, int64_t dim, int64_t ba
 int scan_tc_plan(int mode, int n_queries, int64_t dim, int kcap, bool cached_norms, int64_t n_tiles, int sm_count,
                  int* qp_out, int* stages_out);
 size_t scan_tc_qcat_bytes(int mode, int64_t dim, int q_pad);
+bool scan_tc_exchanges_thresholds(int mode, int64_t dim);   // scan-and-queue epilogue + gmax exchange (else: seeded score-tile epilogue)
 // queries -> normalised, split (hi/lo TF32; hi/mid/lo bf16; hi TF32 only for the filter), laid out per pass as the
 // MMA B operand (see scan_tc.cu); also zeroes the shared threshold array gthr [q_pad].  Filter mode also writes,
 // per query, the scale the normalisation applied (qinv) and the error scale qerr = tc_filter_relerr(dim) *

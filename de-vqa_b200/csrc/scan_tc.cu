@@ -77,7 +77,7 @@ constexpr int kMaxStages = 8;
 constexpr int kPrefetchAhead = 12;                  // bank k-blocks pulled into L2 ahead of the smem ring
 constexpr int kSetKBlocks = 32;
 // filter epilogue: hit queue entries; the same words hold the dense [16][128] score tile (8 KB), so >= 1024
-__host__ __device__ constexpr int hit_cap(int qp) { return qp > 128 ? 1024 : 2048; }
+__host__ __device__ constexpr int hit_cap(int qp) { return (qp > 128 || qp < 32) ? 1024 : 2048; }
 // undocumented debugging bits of `flags` (performance bisection only; results are wrong when set)
 constexpr unsigned kDbgNoInsert = 1u << 16, kDbgNoSplit = 1u << 17, kDbgNoMma2 = 1u << 18, kDbgNoQueryTma = 1u << 19, kDbgNoPrefetch = 1u << 20, kDbgNoBoot = 1u << 23;                     // k-blocks (of 32 columns) accumulated inside the tensor core
 
@@ -278,7 +278,7 @@ __host__ __device__ inline SmemLayout tc_layout(int stages, int qp, int kcap, in
   L.bq = off;    off += uint32_t(stages) * uint32_t(b_parts * qp) * 128;     // [parts*qp rows x 128 B], 1024-aligned since qp % 16 == 0
   L.lists = off; off += uint32_t(qp) * kcap * 8;
   L.thr = off;   off += uint32_t(qp) * 16 + 16;                          // filter: eq / threshold / lost / service bound per query + counters
-  L.scratch = off; off += b_parts == 1 ? hit_cap(qp) * 8 : uint32_t(qp < 32 ? qp : 32) * kTileRows * 4;   // score tile [HQ][128] / hit queue
+  L.scratch = off; off += hit_cap(qp) * 8;               // hit queue / dense [16][128] score tile (MULTI: score tile [HQ][128], same size)
   L.norms = off; off += qp > 128 ? 0 : kNormRing * kTileRows * 4;         // (256 queries per pass: cached row norms only)
   off = (off + 7) & ~7u;
   L.bars = off;  off += (3 * kMaxStages + 4) * 8;
@@ -384,7 +384,9 @@ __device__ __forceinline__ void filt_after_insert(const TcParams& p, const FiltS
   if (p.gmax) p.gmax[size_t(q0 + j) * p.gmax_stride + cta] = uint32_t(best >> 32);   // single writer per slot
 }
 
-template <int QP>
+// PARTS = 1: the filter variant (u = s~ + E).  PARTS = 3: the exact variants (3xTF32 / bf16x3; the score is the sum of
+// three accumulator column groups, E = 0, so u IS the score and T the k-th best itself): same scan, queue and exchange.
+template <int QP, int PARTS>
 __device__ __forceinline__ void filt_epilogue(const TcParams& p, const FiltState st, uint64_t* lists, const float* norms,
                                               bool norm_warps, uint32_t tmem_base, uint64_t* tmem_full, uint64_t* tmem_empty,
                                               int tile0, int tile_step, int n_my, int boot, int q0, int nq_pass, float maxn,
@@ -408,30 +410,47 @@ __device__ __forceinline__ void filt_epilogue(const TcParams& p, const FiltState
     const int64_t grow = int64_t(tile) * kTileRows + row_in_tile;
     const bool row_live = grow < p.n_rows && !no_insert;
     float inv = 1.f, rowfac = 1.f;
-    {
+    if (!dot_mode || PARTS == 1) {
       const float ssq = norm_warps ? norms[(lt % kNormRing) * kTileRows + row_in_tile] : (grow < p.n_rows ? p.row_sumsq[grow] : 1.f);
       const float nrm = sqrtf(ssq);
       if (dot_mode) rowfac = nrm;
       else inv = 1.0f / ((p.flags & DEVQA_NOEPS) ? nrm : fmaxf(nrm, kNormEps));
     }
-    const uint32_t taddr = tmem_base + uint32_t(a) * QP + (uint32_t(e * 32) << 16);
-    if (it < boot) {
-      // ---- bootstrap visit: only each query's best upper bound in this tile, for the threshold exchange ----
-#pragma unroll 1
-      for (int c = 0; c < QP; c += 16) {
-        uint32_t d[16];
-        tmem_ld<16>(taddr + uint32_t(c), d);
+    const uint32_t taddr = tmem_base + uint32_t(a) * (PARTS * QP) + (uint32_t(e * 32) << 16);
+    // 16 accumulators of this row -> 16 upper bounds (filter) / scores (exact variants)
+    auto load_u = [&](int c, float (&u)[16]) {
+      uint32_t d[16];
+      tmem_ld<16>(taddr + uint32_t(c), d);
+      if constexpr (PARTS == 3) {
+        uint32_t d2[16], d3[16];
+        tmem_ld<16>(taddr + uint32_t(QP + c), d2);
+        tmem_ld<16>(taddr + uint32_t(2 * QP + c), d3);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          u[i] = ((__uint_as_float(d2[i]) + __uint_as_float(d3[i])) + __uint_as_float(d[i])) * inv;
+      } else {
         tmem_ld_wait();
 #pragma unroll
         for (int i4 = 0; i4 < 4; ++i4) {
           const float4 eq4 = *reinterpret_cast<const float4*>(st.eq + c + 4 * i4);
-          const float eqv[4] = {eq4.x, eq4.y, eq4.z, eq4.w};
+          u[4 * i4 + 0] = fmaf(__uint_as_float(d[4 * i4 + 0]), inv, eq4.x * rowfac);
+          u[4 * i4 + 1] = fmaf(__uint_as_float(d[4 * i4 + 1]), inv, eq4.y * rowfac);
+          u[4 * i4 + 2] = fmaf(__uint_as_float(d[4 * i4 + 2]), inv, eq4.z * rowfac);
+          u[4 * i4 + 3] = fmaf(__uint_as_float(d[4 * i4 + 3]), inv, eq4.w * rowfac);
+        }
+      }
+    };
+    if (it < boot) {
+      // ---- bootstrap visit: only each query's best upper bound in this tile, for the threshold exchange ----
+#pragma unroll 1
+      for (int c = 0; c < QP; c += 16) {
+        float u[16];
+        load_u(c, u);
 #pragma unroll
-          for (int t = 0; t < 4; ++t) {
-            const float uu = fmaf(__uint_as_float(d[4 * i4 + t]), inv, eqv[t] * rowfac);
-            const uint32_t m = __reduce_max_sync(kFull, row_live ? score_code(uu) : 0u);
-            if (lane == 0) atomicMax(best_s + c + 4 * i4 + t, m);
-          }
+        for (int i = 0; i < 16; ++i) {
+          const uint32_t m = __reduce_max_sync(kFull, row_live ? score_code(u[i]) : 0u);
+          if (lane == 0) atomicMax(best_s + c + i, m);
         }
       }
       tc_fence_before();
@@ -460,19 +479,12 @@ __device__ __forceinline__ void filt_epilogue(const TcParams& p, const FiltState
       // ---- scan ----
 #pragma unroll 1
       for (int c = jb; c < jb + seg; c += 16) {
-        uint32_t d[16];
-        tmem_ld<16>(taddr + uint32_t(c), d);
-        tmem_ld_wait();
         float u[16];
+        load_u(c, u);
         uint32_t mask = 0;
 #pragma unroll
         for (int i4 = 0; i4 < 4; ++i4) {
-          const float4 eq4 = *reinterpret_cast<const float4*>(st.eq + c + 4 * i4);
           const float4 th4 = *reinterpret_cast<const float4*>(st.thr + c + 4 * i4);
-          u[4 * i4 + 0] = fmaf(__uint_as_float(d[4 * i4 + 0]), inv, eq4.x * rowfac);
-          u[4 * i4 + 1] = fmaf(__uint_as_float(d[4 * i4 + 1]), inv, eq4.y * rowfac);
-          u[4 * i4 + 2] = fmaf(__uint_as_float(d[4 * i4 + 2]), inv, eq4.z * rowfac);
-          u[4 * i4 + 3] = fmaf(__uint_as_float(d[4 * i4 + 3]), inv, eq4.w * rowfac);
           mask |= (!(u[4 * i4 + 0] < th4.x) ? 1u : 0u) << (4 * i4 + 0);   // NaN passes, like torch.topk ranks it first
           mask |= (!(u[4 * i4 + 1] < th4.y) ? 1u : 0u) << (4 * i4 + 1);
           mask |= (!(u[4 * i4 + 2] < th4.z) ? 1u : 0u) << (4 * i4 + 2);
@@ -574,10 +586,11 @@ __device__ __forceinline__ void filt_epilogue(const TcParams& p, const FiltState
   }
   if (e == 0 && lane == 0) *reinterpret_cast<volatile uint32_t*>(st.qn + 2) = 1u;   // service warps: stop
   // what this CTA's lists lost, for the completeness proof
-  for (int j = e * 32 + lane; j < nq_pass; j += 128) {
-    const float l = st.lost[j];
-    p.lostu[size_t(tile0) * p.n_queries + q0 + j] = l == -INFINITY ? 0u : score_code(l);
-  }
+  if (p.lostu)
+    for (int j = e * 32 + lane; j < nq_pass; j += 128) {
+      const float l = st.lost[j];
+      p.lostu[size_t(tile0) * p.n_queries + q0 + j] = l == -INFINITY ? 0u : score_code(l);
+    }
 }
 
 // Service warp (warp 3).  The selection is shared out: CTA c derives T for the queries j = c, c + n_ctas, ... from
@@ -655,6 +668,9 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap bank_map, const __grid_consta
   constexpr bool FILT = MODE == kTf32x1;
   constexpr bool TWO_ISSUERS = MODE == kTf32x3;
   static_assert(!(FILT && MULTI), "the filter variant accumulates the whole K chain in the tensor core");
+  // scan-and-queue epilogue + threshold exchange (filt_epilogue / filt_service): every variant whose tile is one
+  // accumulation unit; MULTI (K-sets summed in registers) keeps the score-tile epilogue below
+  constexpr bool SCANEPI = !MULTI;
   constexpr int kParts = BF ? 3 : (FILT ? 1 : 2);        // row groups of the query operand per k-block
   constexpr int kElemsK = BF ? 64 : 32;                  // bank columns per k-block (always 128 bytes)
   const SmemLayout L = tc_layout(p.stages, p.qp, p.kcap, kParts);
@@ -686,16 +702,16 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap bank_map, const __grid_consta
   for (int i = threadIdx.x; i < QP * p.kcap; i += kTcThreads) lists[i] = kEmptyKey;
   FiltState st{};
   float maxn = 1.f;                                      // un-normalised scores: E scales with ||row|| <= maxn
-  if constexpr (FILT) {
+  if constexpr (SCANEPI) {
     float* fs = reinterpret_cast<float*>(smem + L.thr);
     st.eq = fs; st.thr = fs + QP; st.lost = fs + 2 * QP; st.thr_ext = fs + 3 * QP;
     st.qn = reinterpret_cast<uint32_t*>(fs + 4 * QP);
     st.hit_u = reinterpret_cast<float*>(smem + L.scratch);
     st.hit_id = reinterpret_cast<uint32_t*>(smem + L.scratch) + hit_cap(QP);
-    if (!(p.flags & DEVQA_NORMALIZE_BANK)) maxn = sqrtf(__uint_as_float(*p.bank_max_sumsq));
+    if (FILT && !(p.flags & DEVQA_NORMALIZE_BANK)) maxn = sqrtf(__uint_as_float(*p.bank_max_sumsq));
     for (int j = threadIdx.x; j < QP; j += kTcThreads) {
       const bool live = j < nq_pass;
-      const float eq = live ? p.qerr[q0 + j] : 0.f;
+      const float eq = (FILT && live) ? p.qerr[q0 + j] : 0.f;
       float t = live ? -INFINITY : INFINITY;                          // dead queries never hit
       const uint32_t code = (live && p.seed_u) ? p.seed_u[q0 + j] : 0u;
       if (code != 0u) {
@@ -734,7 +750,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap bank_map, const __grid_consta
   // with thresholds in place.  Without this, the first two tiles of every CTA cost as much as ~40 ordinary ones
   // (lists built from nothing, one insertion at a time).
   const int n_my = (p.n_tiles - tile0 + tile_step - 1) / tile_step;
-  const int boot = (FILT && n_my >= 8 && tile_step >= p.k_true && p.gmax && !(p.flags & kDbgNoBoot)) ? 1 : 0;
+  const int boot = (SCANEPI && n_my >= 8 && tile_step >= p.k_true && p.gmax && !(p.flags & kDbgNoBoot)) ? 1 : 0;
   const int n_iter = n_my + boot;
   auto tile_at = [&](int it) { return tile0 + (it < n_my ? it : it - n_my) * tile_step; };
   const int set_kb = FILT ? nkb : kSetKBlocks;           // k-blocks accumulated inside the tensor core
@@ -914,13 +930,13 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap bank_map, const __grid_consta
         if (lane == 0) atomicMax(p.max_sumsq, __float_as_uint(max_ss));   // non-negative floats order like their bits
       }
     }
-  } else if (FILT && warp == 3) {
-    // ===== service warp, filter variant: threshold exchange between CTAs =====
+  } else if (SCANEPI && warp == 3) {
+    // ===== service warp: threshold exchange between CTAs =====
     filt_service(p, st, q0, nq_pass, tile_step, tile0, maxn, lane);
-  } else if (warp >= 8 && FILT) {
-    // ===== epilogue warps, filter variant: scan + hit queue (filt_epilogue) =====
-    filt_epilogue<QP>(p, st, lists, norms, norm_warps, tmem_base, tmem_full, tmem_empty, tile0, tile_step, n_my, boot, q0, nq_pass,
-                      maxn, warp - 8, lane);
+  } else if (warp >= 8 && SCANEPI) {
+    // ===== epilogue warps: scan + hit queue (filt_epilogue) =====
+    filt_epilogue<QP, FILT ? 1 : 3>(p, st, lists, norms, norm_warps, tmem_base, tmem_full, tmem_empty, tile0, tile_step, n_my, boot,
+                                    q0, nq_pass, maxn, warp - 8, lane);
   } else if (warp >= 8) {
     // ===== epilogue warps =====
     // Phase A: thread <-> TMEM lane <-> bank row: sum the three accumulator parts, scale by 1/||row||
@@ -1055,9 +1071,12 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap bank_map, const __grid_consta
 __global__ void __launch_bounds__(256) prep_queries_kernel(const float* __restrict__ q, int64_t q_ld, int n_queries, int dim,
                                                            int qp, int n_kblocks, int q_pad, unsigned flags,
                                                            float* __restrict__ qcat, uint32_t* __restrict__ gthr,
-                                                           const uint32_t* __restrict__ need) {
+                                                           const uint32_t* __restrict__ need, uint32_t* __restrict__ gmax,
+                                                           int gmax_stride) {
   if (blockIdx.x == 0)
     for (int i = threadIdx.x; i < q_pad; i += blockDim.x) gthr[i] = 0u;
+  if (gmax)                                              // threshold exchange: no CTA has published anything yet
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < q_pad * gmax_stride; i += gridDim.x * blockDim.x) gmax[i] = 0u;
   const int lane = threadIdx.x & 31;
   const int warps = gridDim.x * (blockDim.x >> 5);
   const int d_pad = n_kblocks * kBlockK;
@@ -1148,9 +1167,12 @@ __global__ void __launch_bounds__(256) prep_queries_filt_kernel(const float* __r
 // Output per pass: [n_kblocks][3*qp rows][64 bf16], rows 0..qp-1 = hi, qp.. = mid, 2qp.. = lo, 128B-swizzled.
 __global__ void __launch_bounds__(256) prep_queries_bf16_kernel(const float* __restrict__ q, int64_t q_ld, int n_queries, int dim,
                                                                 int qp, int n_kblocks, int q_pad, unsigned flags,
-                                                                __nv_bfloat16* __restrict__ qcat, uint32_t* __restrict__ gthr) {
+                                                                __nv_bfloat16* __restrict__ qcat, uint32_t* __restrict__ gthr,
+                                                                uint32_t* __restrict__ gmax, int gmax_stride) {
   if (blockIdx.x == 0)
     for (int i = threadIdx.x; i < q_pad; i += blockDim.x) gthr[i] = 0u;
+  if (gmax)
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < q_pad * gmax_stride; i += gridDim.x * blockDim.x) gmax[i] = 0u;
   const int lane = threadIdx.x & 31;
   const int warps = gridDim.x * (blockDim.x >> 5);
   const int d_pad = n_kblocks * 64;
@@ -1272,10 +1294,10 @@ int scan_tc_prep_queries(int mode, const float* queries, int64_t query_ld, int n
   const int grid = (q_pad + 7) / 8;
   if (mode == kTcTf32x3)
     prep_queries_kernel<<<grid, 256, 0, stream>>>(queries, query_ld, n_queries, int(dim), qp, n_kblocks, q_pad, flags,
-                                                  static_cast<float*>(qcat), gthr, need);
+                                                  static_cast<float*>(qcat), gthr, need, gmax, gmax_stride);
   else if (mode == kTcBf16x3)
     prep_queries_bf16_kernel<<<grid, 256, 0, stream>>>(queries, query_ld, n_queries, int(dim), qp, n_kblocks, q_pad, flags,
-                                                       static_cast<__nv_bfloat16*>(qcat), gthr);
+                                                       static_cast<__nv_bfloat16*>(qcat), gthr, gmax, gmax_stride);
   else
     prep_queries_filt_kernel<<<grid, 256, 0, stream>>>(queries, query_ld, n_queries, int(dim), qp, n_kblocks, q_pad, flags,
                                                        static_cast<float*>(qcat), gthr, qinv, qerr, seed_u, gmax, gmax_stride);
@@ -1283,6 +1305,9 @@ int scan_tc_prep_queries(int mode, const float* queries, int64_t query_ld, int n
   count_launch();
   return DEVQA_OK;
 }
+
+// Does this mode/dim run the scan-and-queue epilogue with the cross-CTA threshold exchange (needs gmax, no seeding)?
+bool scan_tc_exchanges_thresholds(int mode, int64_t dim) { return mode == kTcTf32x1 || scan_tc_kblocks(mode, dim) <= kSetKBlocks; }
 
 static long long* g_tc_trace = nullptr;
 void scan_tc_set_trace(long long* buf) { g_tc_trace = buf; }
