@@ -167,7 +167,9 @@ static int tc_pipeline(Scratch* s, const SearchArgs& a, int mode, FilterSide* si
   const int list_k = side ? kcap : a.top_k;                 // entries a list keeps
   const bool cached_norms = a.row_sumsq != nullptr;
   int qp = 0, stages = 0;
-  if ((rc = scan_tc_plan(mode, int(a.n_queries), a.dim, kcap, cached_norms, (a.n_rows + 127) / 128, s->sm_count, &qp, &stages)))
+  bool pair = false;
+  if ((rc = scan_tc_plan(mode, int(a.n_queries), a.dim, kcap, cached_norms, (a.n_rows + 127) / 128, s->sm_count, a.flags,
+                         &qp, &stages, &pair)))
     return rc;
   const int q_pad = int((a.n_queries + qp - 1) / qp) * qp;
   const size_t qcat_bytes = scan_tc_qcat_bytes(mode, a.dim, q_pad);
@@ -223,7 +225,7 @@ static int tc_pipeline(Scratch* s, const SearchArgs& a, int mode, FilterSide* si
       const int now = n_passes - pass < side_by ? n_passes - pass : side_by;
       pre.q0 = int32_t(pass * qp);
       pre.nq_pass = qp;
-      if ((rc = scan_tc_launch(pre, mode, s->qsplit, gthr, qp, stages, now, ctas_per_pass, stream))) return rc;
+      if ((rc = scan_tc_launch(pre, mode, s->qsplit, gthr, qp, stages, now, ctas_per_pass, false, stream))) return rc;
     }
     // exact modes: the sample's k-th best score IS a threshold; filter: its k-th best upper bound, from which the
     // kernel derives one (minus 2E)
@@ -236,7 +238,7 @@ static int tc_pipeline(Scratch* s, const SearchArgs& a, int mode, FilterSide* si
     const int now = n_passes - pass < side_by ? n_passes - pass : side_by;
     p.q0 = int32_t(pass * qp);
     p.nq_pass = qp;
-    if ((rc = scan_tc_launch(p, mode, s->qsplit, gthr, qp, stages, now, ctas_per_pass, stream))) return rc;
+    if ((rc = scan_tc_launch(p, mode, s->qsplit, gthr, qp, stages, now, ctas_per_pass, pair && now == 1, stream))) return rc;
     if (prof) s->prof_scan_launches++;
   }
   if (prof) {

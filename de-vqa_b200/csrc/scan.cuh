@@ -53,7 +53,7 @@ constexpr int kTcTf32x3 = 0, kTcBf16x3 = 1, kTcTf32x1 = 2;
 __host__ __device__ inline float tc_filter_relerr(int64_t dim) { return 1.5f * 0.0009765625f + float(dim) * 5.9604644775390625e-08f; }
 bool scan_tc_supported(int bank_dtype, const void* bank, int64_t dim, int64_t bank_ld, int top_k);
 int scan_tc_plan(int mode, int n_queries, int64_t dim, int kcap, bool cached_norms, int64_t n_tiles, int sm_count,
-                 int* qp_out, int* stages_out);
+                 unsigned flags, int* qp_out, int* stages_out, bool* pair_out);
 size_t scan_tc_qcat_bytes(int mode, int64_t dim, int q_pad);
 bool scan_tc_exchanges_thresholds(int mode, int64_t dim);   // scan-and-queue epilogue + gmax exchange (else: seeded score-tile epilogue)
 // queries -> normalised, split (hi/lo TF32; hi/mid/lo bf16; hi TF32 only for the filter), laid out per pass as the
@@ -64,8 +64,9 @@ int scan_tc_prep_queries(int mode, const float* queries, int64_t query_ld, int n
                          int64_t dim, unsigned flags, void* qcat, uint32_t* gthr, float* qinv, float* qerr,
                          uint32_t* seed_u, uint32_t* gmax, int gmax_stride, const uint32_t* need, cudaStream_t stream);
 // one launch = `passes` consecutive query passes starting at p.q0, each on ctas_per_pass CTAs
+// (pair: clusters of two CTAs sharing the query operand, see scan_tc.cu)
 int scan_tc_launch(const ScanParams& p, int mode, const void* qcat, uint32_t* gthr, int qp, int stages, int passes,
-                   int ctas_per_pass, cudaStream_t stream);
+                   int ctas_per_pass, bool pair, cudaStream_t stream);
 void scan_tc_set_trace(long long* buf);
 
 // refine.cu: exact fp32 re-scoring of the filter's candidates (bit-identical to scan_stream.cu's arithmetic).

@@ -79,7 +79,7 @@ constexpr int kSetKBlocks = 32;
 // filter epilogue: hit queue entries; the same words hold the dense [16][128] score tile (8 KB), so >= 1024
 __host__ __device__ constexpr int hit_cap(int qp) { return (qp > 128 || qp < 32) ? 1024 : 2048; }
 // undocumented debugging bits of `flags` (performance bisection only; results are wrong when set)
-constexpr unsigned kDbgNoInsert = 1u << 16, kDbgNoSplit = 1u << 17, kDbgNoMma2 = 1u << 18, kDbgNoQueryTma = 1u << 19, kDbgNoPrefetch = 1u << 20, kDbgNoBoot = 1u << 23;                     // k-blocks (of 32 columns) accumulated inside the tensor core
+constexpr unsigned kDbgNoInsert = 1u << 16, kDbgNoSplit = 1u << 17, kDbgNoMma2 = 1u << 18, kDbgNoQueryTma = 1u << 19, kDbgNoPrefetch = 1u << 20, kDbgNoBoot = 1u << 23, kDbgNoPair = 1u << 28;                     // k-blocks (of 32 columns) accumulated inside the tensor core
 
 // ---- PTX wrappers ---------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return uint32_t(__cvta_generic_to_shared(p)); }
@@ -204,6 +204,64 @@ __device__ __forceinline__ void tmem_ld<16>(uint32_t addr, uint32_t (&r)[16]) {
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void epilogue_barrier() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
+// ---- CTA-pair (cta_group::2) helpers ------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of the same shared-memory location in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t local_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// Pure signal, no ordering of this thread's own writes: used to forward a TMA completion (the data was written by
+// the async proxy and is consumed by the tensor core, exactly as when TMA signals the leader's barrier itself).
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// wait on a LOCAL barrier that a peer CTA arrives on (cluster-scope acquire)
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAITC_%=:\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONEC_%=;\n\t"
+      "bra WAITC_%=;\n\t"
+      "DONEC_%=:\n\t"
+      "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t addr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+// D[tmem of both CTAs] (+)= A[smem of each CTA: its 128 rows] . B[smem: N/2 rows in each CTA]^T; the leader issues
+__device__ __forceinline__ void mma_tf32_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// completion of all prior MMAs of the pair -> one arrival on the barrier at this offset in BOTH CTAs
+__device__ __forceinline__ void mma_commit_pair(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"(uint16_t(3)) : "memory");
+}
+// instruction descriptor of the pair MMA: M = 256 (128 rows per CTA)
+__host__ __device__ constexpr uint32_t idesc_tf32_pair(int n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | (uint32_t(n >> 3) << 17) | (uint32_t(256 >> 4) << 24);
+}
+
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (rows of 128 bytes, 8-row atoms of 1024 bytes):
 // start address >> 4 | SBO = 1024 >> 4 at bit 32 | descriptor version 1 at bit 46 | layout 2 at bit 61.
 __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t smem_addr) {
@@ -271,17 +329,18 @@ __device__ __forceinline__ void trace_at(const TcParams& p, int role, uint32_t i
 struct SmemLayout {        // byte offsets from the 1024-aligned base
   uint32_t a_raw, bq, lists, thr, scratch, norms, bars, tmem_slot, total;
 };
-__host__ __device__ inline SmemLayout tc_layout(int stages, int qp, int kcap, int b_parts = 2) {
+__host__ __device__ inline SmemLayout tc_layout(int stages, int qp, int kcap, int b_parts = 2, bool pair = false) {
   SmemLayout L;
   uint32_t off = 0;
   L.a_raw = off; off += uint32_t(stages) * kATileBytes;
-  L.bq = off;    off += uint32_t(stages) * uint32_t(b_parts * qp) * 128;     // [parts*qp rows x 128 B], 1024-aligned since qp % 16 == 0
+  // [parts*qp rows x 128 B], 1024-aligned since qp % 16 == 0; a CTA pair holds half of the query rows each
+  L.bq = off;    off += uint32_t(stages) * uint32_t(b_parts * (pair ? qp / 2 : qp)) * 128;
   L.lists = off; off += uint32_t(qp) * kcap * 8;
   L.thr = off;   off += uint32_t(qp) * 16 + 16;                          // filter: eq / threshold / lost / service bound per query + counters
   L.scratch = off; off += hit_cap(qp) * 8;               // hit queue / dense [16][128] score tile (MULTI: score tile [HQ][128], same size)
   L.norms = off; off += qp > 128 ? 0 : kNormRing * kTileRows * 4;         // (256 queries per pass: cached row norms only)
   off = (off + 7) & ~7u;
-  L.bars = off;  off += (3 * kMaxStages + 4) * 8;
+  L.bars = off;  off += (4 * kMaxStages + 4) * 8;        // full_tma, full_split, empty, peer_full (pairs), tmem_full/empty
   L.tmem_slot = off; off += 16;
   L.total = off;
   return L;
@@ -390,7 +449,12 @@ template <int QP, int PARTS>
 __device__ __forceinline__ void filt_epilogue(const TcParams& p, const FiltState st, uint64_t* lists, const float* norms,
                                               bool norm_warps, uint32_t tmem_base, uint64_t* tmem_full, uint64_t* tmem_empty,
                                               int tile0, int tile_step, int n_my, int boot, int q0, int nq_pass, float maxn,
-                                              int e, int lane) {
+                                              int e, int lane, uint32_t tmem_empty_remote = 0u) {
+  // accumulator buffer a may be overwritten (pairs: the peer CTA tells the leader, who issues the MMAs)
+  auto release_tmem = [&](int a) {
+    if (tmem_empty_remote) mbar_arrive_cluster(tmem_empty_remote + uint32_t(a) * 8u);
+    else mbar_arrive(&tmem_empty[a]);
+  };
   const int row_in_tile = e * 32 + lane;
   const bool no_insert = (p.flags & kDbgNoInsert) != 0;
   const bool dot_mode = !(p.flags & DEVQA_NORMALIZE_BANK);          // E scales with ||row||
@@ -454,7 +518,7 @@ __device__ __forceinline__ void filt_epilogue(const TcParams& p, const FiltState
         }
       }
       tc_fence_before();
-      mbar_arrive(&tmem_empty[a]);
+      release_tmem(a);
       epilogue_barrier();
       for (int j = e * 32 + lane; j < nq_pass; j += 128)
         p.gmax[size_t(q0 + j) * p.gmax_stride + tile0] = best_s[j];
@@ -518,7 +582,7 @@ __device__ __forceinline__ void filt_epilogue(const TcParams& p, const FiltState
         epilogue_barrier();
         continue;
       }
-      if (last_seg) mbar_arrive(&tmem_empty[a]);                        // this thread's TMEM reads of the buffer are done
+      if (last_seg) release_tmem(a);                                    // this thread's TMEM reads of the buffer are done
       if (dense) {
         // ---- dense segment: warp e owns queries jb + e, jb + 4 + e, ... ----
         const int64_t row0 = int64_t(tile) * kTileRows + lane * 4;
@@ -659,7 +723,12 @@ __device__ __forceinline__ void filt_service(const TcParams& p, const FiltState 
   }
 }
 
-template <int QP, bool MULTI, int MODE>
+// PAIR: two CTAs of one TPC (cluster of 2) run ONE MMA of M = 256 per instruction (cta_group::2): each CTA streams
+// its own 128 bank rows and holds HALF of the query operand, which the tensor cores of both read -- 64 instead of
+// 96 KB of shared-memory traffic per k-block at 256 queries.  The leader (cluster rank 0) issues the MMAs; the peer's
+// warp 1 forwards "my stage is loaded" to the leader's barrier; commits are multicast to both CTAs' barriers; both
+// epilogues release the accumulator on the leader's barrier.  Everything else (lists, thresholds, exchange) is per CTA.
+template <int QP, bool MULTI, int MODE, bool PAIR = false>
 __global__ void __launch_bounds__(kTcThreads, 1)
 scan_tc_kernel(const __grid_constant__ CUtensorMap bank_map, const __grid_constant__ TcParams p) {
   extern __shared__ unsigned char smem_unaligned[];
@@ -673,17 +742,22 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap bank_map, const __grid_consta
   constexpr bool SCANEPI = !MULTI;
   constexpr int kParts = BF ? 3 : (FILT ? 1 : 2);        // row groups of the query operand per k-block
   constexpr int kElemsK = BF ? 64 : 32;                  // bank columns per k-block (always 128 bytes)
-  const SmemLayout L = tc_layout(p.stages, p.qp, p.kcap, kParts);
+  static_assert(!PAIR || (FILT && QP == 256), "CTA pairs: filter variant, 256 queries per pass");
+  const SmemLayout L = tc_layout(p.stages, p.qp, p.kcap, kParts, PAIR);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int S = p.stages;
-  const uint32_t b_stage_bytes = uint32_t(kParts * QP) * 128;
+  constexpr int kBRows = PAIR ? QP / 2 : QP;             // query rows of the operand in THIS CTA's shared memory
+  const uint32_t b_stage_bytes = uint32_t(kParts * kBRows) * 128;
+  const uint32_t pair_rank = PAIR ? cluster_ctarank() : 0u;
+  const bool leader = pair_rank == 0u;
 
   uint64_t* lists = reinterpret_cast<uint64_t*>(smem + L.lists);
   float* norms = reinterpret_cast<float*>(smem + L.norms);
   uint64_t* full_tma = reinterpret_cast<uint64_t*>(smem + L.bars);
   uint64_t* full_split = full_tma + kMaxStages;
   uint64_t* empty = full_split + kMaxStages;
-  uint64_t* tmem_full = empty + kMaxStages;        // [2]
+  uint64_t* peer_full = empty + kMaxStages;        // pairs, leader only: the peer's stage s is loaded
+  uint64_t* tmem_full = peer_full + kMaxStages;    // [2]
   uint64_t* tmem_empty = tmem_full + 2;            // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L.tmem_slot);
 
@@ -726,13 +800,16 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap bank_map, const __grid_consta
     tma_prefetch_desc(&bank_map);
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < S; ++s) { mbar_init(&full_tma[s], 1); mbar_init(&full_split[s], 128); mbar_init(&empty[s], TWO_ISSUERS ? 2 : 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], TWO_ISSUERS ? 2 : 1); mbar_init(&tmem_empty[a], 128); }
+    for (int s = 0; s < S; ++s) {
+      mbar_init(&full_tma[s], 1); mbar_init(&full_split[s], 128); mbar_init(&empty[s], TWO_ISSUERS ? 2 : 1);
+      mbar_init(&peer_full[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], TWO_ISSUERS ? 2 : 1); mbar_init(&tmem_empty[a], PAIR ? 256 : 128); }
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc(tmem_slot, 512);
+  if (warp == 2) { if constexpr (PAIR) tmem_alloc_pair(tmem_slot, 512); else tmem_alloc(tmem_slot, 512); }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (PAIR) cluster_sync_all(); else __syncthreads();   // (pairs: the peer's barriers are initialised too)
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const float* const qcat = p.qcat + size_t(pass_local) * size_t(p.n_kblocks) * (kParts * QP * 32);   // 32 words per 128-byte row
@@ -749,7 +826,8 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap bank_map, const __grid_consta
   // the service warps) and waits a bounded moment for them; on the second visit it is a tile like any other --
   // with thresholds in place.  Without this, the first two tiles of every CTA cost as much as ~40 ordinary ones
   // (lists built from nothing, one insertion at a time).
-  const int n_my = (p.n_tiles - tile0 + tile_step - 1) / tile_step;
+  // (pairs: both CTAs run the leader's count; a missing last tile of the peer is all out-of-bounds rows)
+  const int n_my = (p.n_tiles - (PAIR ? (tile0 & ~1) : tile0) + tile_step - 1) / tile_step;
   const int boot = (SCANEPI && n_my >= 8 && tile_step >= p.k_true && p.gmax && !(p.flags & kDbgNoBoot)) ? 1 : 0;
   const int n_iter = n_my + boot;
   auto tile_at = [&](int it) { return tile0 + (it < n_my ? it : it - n_my) * tile_step; };
@@ -779,10 +857,12 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap bank_map, const __grid_consta
         for (int kb = 0; kb < nkb; ++kb) {
           prefetch_next();
           mbar_wait(&empty[r.s], r.phase ^ 1u);
+          trace_at(p, 1, trace_it);
           mbar_expect_tx(&full_tma[r.s], tx_bytes);
           tma_load_2d(smem + L.a_raw + r.s * kATileBytes, &bank_map, &full_tma[r.s], kb * kElemsK, tile * kTileRows);
           if (qtma)     // the whole [2QP x 32] query k-block is contiguous (and pre-swizzled) in global memory
-            bulk_load(smem + L.bq + r.s * b_stage_bytes, qcat + size_t(kb) * (kParts * QP * 32), b_stage_bytes, &full_tma[r.s]);
+            bulk_load(smem + L.bq + r.s * b_stage_bytes, qcat + size_t(kb) * (kParts * QP * 32) + size_t(pair_rank) * (kBRows * 32),
+                      b_stage_bytes, &full_tma[r.s]);               // (pairs: this CTA's half of the rows)
           trace_at(p, 0, trace_it++);
           r.advance(S);
         }
@@ -790,8 +870,10 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap bank_map, const __grid_consta
     }
   } else if (warp == 1) {
     // ===== MMA issuer 1: A (hi by truncation, from shared memory) x [Qhi ; Qlo] -> cols [0, 2QP) =====
-    if (lane == 0) {
-      const uint32_t idesc_cat = BF ? idesc_bf16(3 * QP) : idesc_tf32(kParts * QP);
+    if (PAIR && !leader) {
+      // pair, peer CTA: no MMA issue (warps 4-7 forward "stage s is loaded" to the leader, below)
+    } else if (lane == 0) {
+      const uint32_t idesc_cat = BF ? idesc_bf16(3 * QP) : (PAIR ? idesc_tf32_pair(QP) : idesc_tf32(kParts * QP));
       const uint32_t a_lo0 = (smem_u32(smem + L.a_raw) & 0x3ffffu) >> 4, b_lo0 = (smem_u32(smem + L.bq) & 0x3ffffu) >> 4;
       RingPos r;
       uint32_t unit = 0;
@@ -799,7 +881,8 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap bank_map, const __grid_consta
         const int tile = tile_at(it); (void)tile;
         for (int set = 0; set < nsets; ++set, ++unit) {
           const int a = unit & 1;
-          mbar_wait(&tmem_empty[a], ((unit >> 1) & 1) ^ 1);
+          if constexpr (PAIR) mbar_wait_cluster(&tmem_empty[a], ((unit >> 1) & 1) ^ 1);   // both CTAs' epilogues
+          else mbar_wait(&tmem_empty[a], ((unit >> 1) & 1) ^ 1);
           tc_fence_after();
           const uint32_t d = tmem_base + uint32_t(a) * kAccCols;
           const int kb_end = min(nkb, (set + 1) * set_kb);
@@ -807,17 +890,22 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap bank_map, const __grid_consta
             const uint32_t first = kb == set * set_kb ? 0u : 1u;
             const uint32_t a_lo = a_lo0 + uint32_t(r.s) * (kATileBytes >> 4), b_lo = b_lo0 + uint32_t(r.s) * (b_stage_bytes >> 4);
             mbar_wait(&full_tma[r.s], r.phase);
+            trace_at(p, 3, unit * uint32_t(nkb) + uint32_t(kb));
+            if constexpr (PAIR) mbar_wait_cluster(&peer_full[r.s], r.phase);     // ... and the peer's half
+            trace_at(p, 4, unit * uint32_t(nkb) + uint32_t(kb));
             tc_fence_after();
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk) {              // four 32-byte K slices of the 128-byte rows
               if constexpr (BF) mma_bf16(d, desc_from_lo(a_lo + kk * 2), desc_from_lo(b_lo + kk * 2), idesc_cat, first | uint32_t(kk));
+              else if constexpr (PAIR) mma_tf32_pair(d, desc_from_lo(a_lo + kk * 2), desc_from_lo(b_lo + kk * 2), idesc_cat, first | uint32_t(kk));
               else mma_tf32(d, desc_from_lo(a_lo + kk * 2), desc_from_lo(b_lo + kk * 2), idesc_cat, first | uint32_t(kk));
             }
             if (!TWO_ISSUERS && norm_warps) mbar_wait(&full_split[r.s], r.phase);   // the norm warps are done reading the stage
-            mma_commit(&empty[r.s]);                      // (one of) the arrival(s) that free the stage
+            if constexpr (PAIR) mma_commit_pair(&empty[r.s]);      // frees the stage in both CTAs
+            else mma_commit(&empty[r.s]);                 // (one of) the arrival(s) that free the stage
             r.advance(S);
           }
-          mma_commit(&tmem_full[a]);
+          if constexpr (PAIR) mma_commit_pair(&tmem_full[a]); else mma_commit(&tmem_full[a]);
         }
       }
     }
@@ -853,6 +941,21 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap bank_map, const __grid_consta
           }
           mma_commit(&tmem_full[a]);
         }
+      }
+    }
+  } else if (PAIR && !leader && warp >= 4 && warp < 8) {
+    // ===== pair, peer CTA: forward "stage s of my shared memory is loaded" to the leader's peer_full[s] =====
+    // One thread per stage residue: a cluster-scope release-arrive takes ~1500 cycles, a single forwarder would
+    // cap the ring at one k-block per that time (measured); four in flight keep up.
+    if (lane == 0) {
+      const uint32_t remote0 = mapa_u32(smem_u32(&peer_full[0]), 0u);
+      const int w = warp - 4;
+      const long long total = (long long)n_iter * nkb;
+      for (long long i = 0; i < total; ++i) {
+        const int st_i = int(i % S);
+        if ((st_i & 3) != w) continue;
+        mbar_wait(&full_tma[st_i], uint32_t((i / S) & 1));
+        mbar_arrive_cluster_relaxed(remote0 + uint32_t(st_i) * 8u);
       }
     }
   } else if (warp >= 4 && warp < 8 && norm_warps) {
@@ -936,7 +1039,8 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap bank_map, const __grid_consta
   } else if (warp >= 8 && SCANEPI) {
     // ===== epilogue warps: scan + hit queue (filt_epilogue) =====
     filt_epilogue<QP, FILT ? 1 : 3>(p, st, lists, norms, norm_warps, tmem_base, tmem_full, tmem_empty, tile0, tile_step, n_my, boot,
-                                    q0, nq_pass, maxn, warp - 8, lane);
+                                    q0, nq_pass, maxn, warp - 8, lane,
+                                    (PAIR && !leader) ? mapa_u32(smem_u32(&tmem_empty[0]), 0u) : 0u);
   } else if (warp >= 8) {
     // ===== epilogue warps =====
     // Phase A: thread <-> TMEM lane <-> bank row: sum the three accumulator parts, scale by 1/||row||
@@ -1061,7 +1165,12 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap bank_map, const __grid_consta
     const uint64_t* src = lists + size_t(q) * p.kcap;
     for (int i = lane; i < p.kcap; i += 32) out[i] = src[i];
   }
-  if (warp == 2) tmem_dealloc(tmem_base, 512);
+  if constexpr (PAIR) {
+    cluster_sync_all();                                  // nobody leaves (or frees TMEM) while the other still computes
+    if (warp == 2) tmem_dealloc_pair(tmem_base, 512);
+  } else {
+    if (warp == 2) tmem_dealloc(tmem_base, 512);
+  }
 }
 
 // ---- query preparation: normalise, pad, split into TF32 hi / lo, lay out as the MMA B operand -------------
@@ -1259,7 +1368,8 @@ size_t scan_tc_qcat_bytes(int mode, int64_t dim, int q_pad) {
 
 // Queries per pass + pipeline depth that fit in shared memory / tensor memory for this list capacity.
 int scan_tc_plan(int mode, int n_queries, int64_t dim, int kcap, bool cached_norms, int64_t n_tiles, int sm_count,
-                 int* qp_out, int* stages_out) {
+                 unsigned flags, int* qp_out, int* stages_out, bool* pair_out) {
+  *pair_out = false;
   const bool bf = mode == kTcBf16x3, filt = mode == kTcTf32x1;
   // more than one K-set (1024 fp32 / 2048 bf16 columns) sums K-sets in the epilogue's registers (MULTI):
   // 32 queries per pass at most.  The filter keeps the whole K chain in the tensor core (its error bound
@@ -1273,11 +1383,13 @@ int scan_tc_plan(int mode, int n_queries, int64_t dim, int kcap, bool cached_nor
   if (filt)
     while (qp > 32 && n_tiles * ((n_queries + qp - 1) / qp) < sm_count) qp >>= 1;
   for (; qp >= 16; qp >>= 1) {
+    // 256 queries per pass on a long scan: CTA pairs (each CTA holds half of the query operand)
+    const bool pair = filt && qp == 256 && n_tiles >= 2 * int64_t(sm_count) && sm_count % 2 == 0 && !(flags & kDbgNoPair);
     for (int stages = kMaxStages; stages >= 3; --stages) {
       // TMEM: 2 accumulator buffers of 3*qp (filter: qp) columns (+ one 32-column lo tile per stage for 3xTF32)
       if ((filt ? 2 : 6) * qp + (mode == kTcTf32x3 ? stages * kBlockK : 0) > 512) continue;
-      if (tc_layout(stages, qp, kcap, mode_parts(mode)).total + 1024 <= 225 * 1024) {
-        *qp_out = qp; *stages_out = stages;
+      if (tc_layout(stages, qp, kcap, mode_parts(mode), pair).total + 1024 <= 225 * 1024) {
+        *qp_out = qp; *stages_out = stages; *pair_out = pair;
         return DEVQA_OK;
       }
     }
@@ -1313,7 +1425,7 @@ static long long* g_tc_trace = nullptr;
 void scan_tc_set_trace(long long* buf) { g_tc_trace = buf; }
 
 int scan_tc_launch(const ScanParams& sp, int mode, const void* qcat, uint32_t* gthr, int qp, int stages, int passes,
-                   int ctas_per_pass, cudaStream_t stream) {
+                   int ctas_per_pass, bool pair, cudaStream_t stream) {
   const int grid = passes * ctas_per_pass;
   const bool bf = mode == kTcBf16x3;
   const int parts = mode_parts(mode);
@@ -1332,7 +1444,7 @@ int scan_tc_launch(const ScanParams& sp, int mode, const void* qcat, uint32_t* g
   // pass index = q0 / qp; one pass = n_kblocks * parts * qp rows of 128 bytes (32 words)
   p.qcat = static_cast<const float*>(qcat) + size_t(sp.q0 / qp) * size_t(n_kblocks) * parts * qp * 32;
   p.trace = g_tc_trace;
-  const size_t smem = tc_layout(stages, qp, sp.kcap, parts).total + 1024;
+  const size_t smem = tc_layout(stages, qp, sp.kcap, parts, pair).total + 1024;
   const bool multi = mode != kTcTf32x1 && p.n_kblocks > kSetKBlocks;
   void (*kern)(CUtensorMap, TcParams) = nullptr;
   if (mode == kTcTf32x3) {
@@ -1350,8 +1462,22 @@ int scan_tc_launch(const ScanParams& sp, int mode, const void* qcat, uint32_t* g
     set_error("tcgen05 scan: unsupported queries-per-pass %d", qp);
     return DEVQA_E_INVALID;
   }
+  if (pair) {
+    DEVQA_REQUIRE(mode == kTcTf32x1 && qp == 256 && passes == 1 && grid % 2 == 0, "tcgen05 scan: bad CTA-pair launch");
+    kern = scan_tc_kernel<256, false, kTf32x1, true>;
+  }
   DEVQA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-  kern<<<grid, kTcThreads, smem, stream>>>(bank_map, p);
+  if (pair) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(unsigned(grid)); cfg.blockDim = dim3(kTcThreads); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    DEVQA_CUDA(cudaLaunchKernelEx(&cfg, kern, bank_map, p));
+  } else {
+    kern<<<grid, kTcThreads, smem, stream>>>(bank_map, p);
+  }
   DEVQA_CUDA(cudaGetLastError());
   count_launch();
   return DEVQA_OK;

@@ -17,7 +17,7 @@ torch.cuda.synchronize()
 L.lib().devqa_debug_tc_trace(None)
 t = buf.cpu().view(16, 256)
 t0 = int(t[0, 0])
-names = ["tma_issue", "split_got", "split_done", "mma_got_tma", "mma_got_split", "mma_commit", "epi_got", "epi_done"]
+names = ["tma_issue", "got_empty", "split_done", "mma_got_tma", "mma_got_peer", "mma_commit", "epi_got", "epi_done"]
 n = 60
 for r in range(6):
     print(names[r].ljust(14), " ".join(f"{int(x) - t0:7d}" if x else "      -" for x in t[r, :n]))
