@@ -79,7 +79,7 @@ constexpr int kSetKBlocks = 32;
 // filter epilogue: hit queue entries; the same words hold the dense [16][128] score tile (8 KB), so >= 1024
 __host__ __device__ constexpr int hit_cap(int qp) { return (qp > 128 || qp < 32) ? 1024 : 2048; }
 // undocumented debugging bits of `flags` (performance bisection only; results are wrong when set)
-constexpr unsigned kDbgNoInsert = 1u << 16, kDbgNoSplit = 1u << 17, kDbgNoMma2 = 1u << 18, kDbgNoQueryTma = 1u << 19, kDbgNoPrefetch = 1u << 20, kDbgNoBoot = 1u << 23, kDbgNoPair = 1u << 28;                     // k-blocks (of 32 columns) accumulated inside the tensor core
+constexpr unsigned kDbgNoInsert = 1u << 16, kDbgNoSplit = 1u << 17, kDbgNoMma2 = 1u << 18, kDbgNoQueryTma = 1u << 19, kDbgNoPrefetch = 1u << 20, kDbgNoBoot = 1u << 23, kDbgNoPair = 1u << 28, kDbgPairAll = 1u << 29;                     // k-blocks (of 32 columns) accumulated inside the tensor core
 
 // ---- PTX wrappers ---------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return uint32_t(__cvta_generic_to_shared(p)); }
@@ -742,7 +742,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap bank_map, const __grid_consta
   constexpr bool SCANEPI = !MULTI;
   constexpr int kParts = BF ? 3 : (FILT ? 1 : 2);        // row groups of the query operand per k-block
   constexpr int kElemsK = BF ? 64 : 32;                  // bank columns per k-block (always 128 bytes)
-  static_assert(!PAIR || (FILT && QP == 256), "CTA pairs: filter variant, 256 queries per pass");
+  static_assert(!PAIR || (FILT && QP >= 64), "CTA pairs: filter variant, 64+ queries per pass");
   const SmemLayout L = tc_layout(p.stages, p.qp, p.kcap, kParts, PAIR);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int S = p.stages;
@@ -1384,7 +1384,8 @@ int scan_tc_plan(int mode, int n_queries, int64_t dim, int kcap, bool cached_nor
     while (qp > 32 && n_tiles * ((n_queries + qp - 1) / qp) < sm_count) qp >>= 1;
   for (; qp >= 16; qp >>= 1) {
     // 256 queries per pass on a long scan: CTA pairs (each CTA holds half of the query operand)
-    const bool pair = filt && qp == 256 && n_tiles >= 2 * int64_t(sm_count) && sm_count % 2 == 0 && !(flags & kDbgNoPair);
+    const bool pair = filt && cached_norms && (qp == 256 || (qp >= 64 && (flags & kDbgPairAll))) &&
+                      n_tiles >= 2 * int64_t(sm_count) && sm_count % 2 == 0 && !(flags & kDbgNoPair);
     for (int stages = kMaxStages; stages >= 3; --stages) {
       // TMEM: 2 accumulator buffers of 3*qp (filter: qp) columns (+ one 32-column lo tile per stage for 3xTF32)
       if ((filt ? 2 : 6) * qp + (mode == kTcTf32x3 ? stages * kBlockK : 0) > 512) continue;
@@ -1463,8 +1464,9 @@ int scan_tc_launch(const ScanParams& sp, int mode, const void* qcat, uint32_t* g
     return DEVQA_E_INVALID;
   }
   if (pair) {
-    DEVQA_REQUIRE(mode == kTcTf32x1 && qp == 256 && passes == 1 && grid % 2 == 0, "tcgen05 scan: bad CTA-pair launch");
-    kern = scan_tc_kernel<256, false, kTf32x1, true>;
+    DEVQA_REQUIRE(mode == kTcTf32x1 && qp >= 64 && passes == 1 && grid % 2 == 0, "tcgen05 scan: bad CTA-pair launch");
+    kern = qp == 256 ? scan_tc_kernel<256, false, kTf32x1, true> : qp == 128 ? scan_tc_kernel<128, false, kTf32x1, true>
+                                                                              : scan_tc_kernel<64, false, kTf32x1, true>;
   }
   DEVQA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
   if (pair) {
