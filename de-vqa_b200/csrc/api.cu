@@ -101,7 +101,13 @@ static int scratch_for(int device, Scratch** out) {
 
 // order this call behind the previous user of the scratch when the stream changed
 static int scratch_enter(Scratch* s, cudaStream_t stream) {
-  if (s->last_stream != stream && s->done) DEVQA_CUDA(cudaStreamWaitEvent(stream, s->done, 0));
+  if (s->last_stream != stream && s->done) {
+    // (a capturing stream must not wait on an event from outside its capture; whoever captures a search has
+    // synchronised with earlier work already, as CUDA graph capture requires)
+    cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(stream, &st);
+    if (st == cudaStreamCaptureStatusNone) DEVQA_CUDA(cudaStreamWaitEvent(stream, s->done, 0));
+  }
   return DEVQA_OK;
 }
 static int scratch_leave(Scratch* s, cudaStream_t stream) {

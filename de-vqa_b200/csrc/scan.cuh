@@ -22,7 +22,6 @@ struct ScanParams {
   uint64_t* cand;          // [grid, n_queries, kcap] sorted candidate lists (output)
   IdMap idmap;
   const float* row_sumsq;  // optional cached ||row||^2 of library-owned banks (nullptr: computed in-kernel)
-  uint32_t* max_sumsq;     // tcgen05 filter variant without cached norms: receives max ||row||^2 (float bits, atomicMax)
   const uint32_t* need;    // tcgen05 scan as a conditional fallback: [n_queries] flags, passes with none set exit at once
   // tcgen05 filter variant
   const float* qerr;       // [n_queries] tc_filter_relerr(dim) * ||query as used||

@@ -304,7 +304,6 @@ struct TcParams {
   const float* qcat;       // this pass's query operand: [n_kblocks][2*qp rows][32] fp32, rows 128B-swizzled
   uint64_t* cand;          // [grid, n_queries, kcap]
   const float* row_sumsq;  // optional cached ||row||^2 (bf16 / filter variants: replaces the in-kernel norm warps)
-  uint32_t* max_sumsq;     // filter variant with in-kernel norms: atomicMax of the bit pattern of max ||row||^2
   const uint32_t* need;    // optional [n_queries] flags: a CTA whose pass has none set exits at once (exact fallback)
   // filter variant only
   const float* qerr;       // [n_queries] relerr(dim) * ||query as used||: E = qerr * ||row|| (1 for normalised rows)
@@ -964,7 +963,6 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap bank_map, const __grid_consta
     const uint32_t row_off = uint32_t(row) * 128;
     const uint32_t sw = uint32_t(row & 7);                // 16-byte chunk c of row r lives at chunk c ^ (r & 7)
     uint32_t lt = 0;
-    float max_ss = 0.f;
     RingPos rp;
     const uint32_t st_lane = uint32_t((warp & 3) * 32) << 16;     // warp w may only touch TMEM lanes 32*(w%4)..
     const uint32_t a_raw_s = smem_u32(smem + L.a_raw) + row_off;
@@ -1019,18 +1017,10 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap bank_map, const __grid_consta
         if (kb == nkb - 1) {
           const float tot = ((ss[0] + ss[1]) + (ss[2] + ss[3])) + ((ss[4] + ss[5]) + (ss[6] + ss[7]));
           norms[(lt % kNormRing) * kTileRows + row] = tot;
-          if constexpr (FILT) max_ss = fmaxf(max_ss, tot);  // NaN rows are caught by the refine step, not here
         }
         tc_fence_before();                                // TMEM writes ordered before the MMA issuer's reads
         mbar_arrive(&full_split[s]);
         rp.advance(S);
-      }
-    }
-    if constexpr (FILT) {                                 // max ||row||^2: the error bound of un-normalised scores
-      if (p.max_sumsq) {
-#pragma unroll
-        for (int off = 16; off >= 1; off >>= 1) max_ss = fmaxf(max_ss, __shfl_xor_sync(kFull, max_ss, off));
-        if (lane == 0) atomicMax(p.max_sumsq, __float_as_uint(max_ss));   // non-negative floats order like their bits
       }
     }
   } else if (SCANEPI && warp == 3) {
@@ -1440,7 +1430,7 @@ int scan_tc_launch(const ScanParams& sp, int mode, const void* qcat, uint32_t* g
   p.qp = qp; p.nq_pass = sp.nq_pass; p.q0 = sp.q0; p.n_queries = sp.n_queries;
   p.top_k = sp.top_k; p.kcap = sp.kcap; p.stages = stages; p.passes = passes; p.flags = sp.flags;
   p.cand = sp.cand; p.gthr = gthr; p.idmap = sp.idmap; p.row_sumsq = sp.row_sumsq;
-  p.max_sumsq = sp.max_sumsq; p.need = sp.need;
+  p.need = sp.need;
   p.gmax = sp.gmax; p.gmax_stride = sp.gmax_stride; p.lostu = sp.lostu; p.qerr = sp.qerr; p.seed_u = sp.seed_u; p.bank_max_sumsq = sp.bank_max_sumsq; p.k_true = sp.k_true > 0 ? sp.k_true : sp.top_k;
   // pass index = q0 / qp; one pass = n_kblocks * parts * qp rows of 128 bytes (32 words)
   p.qcat = static_cast<const float*>(qcat) + size_t(sp.q0 / qp) * size_t(n_kblocks) * parts * qp * 32;

@@ -301,3 +301,34 @@ def test_launch_counter_moves():
     torch.cuda.synchronize()
     assert L.lib().devqa_launch_count() >= before + 2           # scan + merge
     fb.close()
+
+
+def test_search_is_capturable_in_a_cuda_graph():
+    """The tensor API enqueues kernels only (no host synchronisation, the exact-fallback decision is taken on the
+    device), so a search can be captured once and replayed: stream kernel (Q = 1) and tensor-core filter path (Q = 40)."""
+    import devqa_b200
+    from devqa_b200 import FactBank
+    g = torch.Generator().manual_seed(77)
+    bank = torch.nn.functional.normalize(torch.randn(60_000, 256, generator=g), dim=1)
+    fb = FactBank.from_embeddings(bank)
+    for nq in (1, 40):
+        q = torch.nn.functional.normalize(torch.randn(nq, 256, generator=g), dim=1).cuda()
+        q2 = torch.nn.functional.normalize(torch.randn(nq, 256, generator=g), dim=1).cuda()
+        want1, want2 = fb.search(q, 16), fb.search(q2, 16)          # also sizes every scratch buffer
+        static_q = q.clone()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            fb.search(static_q, 16)
+        torch.cuda.current_stream().wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            out = fb.search(static_q, 16)
+        graph.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(out[0], want1[0]) and torch.equal(out[1], want1[1])
+        static_q.copy_(q2)
+        graph.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(out[0], want2[0]) and torch.equal(out[1], want2[1])
+    fb.close()
