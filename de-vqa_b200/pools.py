@@ -9,6 +9,7 @@ sort at every forward:
           append :104
   RECIPE  editor/vllm_editors/recipe_vl/recipe_vl.py:86-95 (dot / sqrt(d), top-``retr_top_k`` entries that beat
           the prototype in row 0), append :163-164
+  HICE    easyeditor/trainer/algs/HICE.py:238-250 (m-loc memory gate: no-eps cosine max > 0.81; part of N4)
 
 ``EditPool`` keeps the pool in a FactBank (in-place append, amortised O(1); ``restore`` = truncate) and serves
 the three lookups with the same fused scan kernels as the IKE path.  Same decision rules as the reference;
@@ -50,6 +51,18 @@ class EditPool:
         s, i = self.bank.search(text_embds, 1, normalize_bank="eps", normalize_query="eps")
         s, i = s[:, 0].cpu(), i[:, 0].cpu()
         return [int(ix) if float(v) > sim_threshold else None for v, ix in zip(s, i)], s
+
+    # ---- HICE memory gate (N4) ------------------------------------------------------------------------
+    def hice_memory_gate(self, query_embedding, threshold: float = 0.81) -> Tuple[bool, float]:
+        """``HICE.run_classifier2`` (easyeditor/trainer/algs/HICE.py:238-250): ``sim = q/||q|| @ (mem/||mem||).T``
+        over the m-loc memory, in scope iff ``sim.max() > threshold``.  The reference re-concatenates and
+        re-normalises the whole memory on every call; here it is a resident pool (``append`` per remembered
+        embedding) and the gate is one fused no-eps cosine top-1.  Returns (gate, max similarity)."""
+        if len(self.bank) == 0:
+            return False, float("-inf")
+        s, _ = self.bank.search(query_embedding, 1, normalize_bank="noeps", normalize_query="noeps")
+        best = float(s.max())
+        return best > threshold, best
 
     # ---- SERAC -------------------------------------------------------------------------------------
     def serac_retrieve(self, rep1) -> Tuple[torch.Tensor, torch.Tensor]:

@@ -119,3 +119,23 @@ def test_liveedit_hard_routing_mask(m):
         assert len(ids) > 600
         pool.restore(10)
         assert len(pool) == 10 and bool((pool.retrieve(ivr, vis_sim_prot, scale)[0] < 10).all())
+
+
+def test_hice_memory_gate():
+    """HICE.py:238-250: sim = q/||q|| @ (mem/||mem||).T; in scope iff sim.max() > 0.81."""
+    g = _g(9)
+    d = 384
+    mem = [torch.randn(1, d, generator=g) for _ in range(40)]
+    pool = EditPool(d)
+    assert pool.hice_memory_gate(torch.randn(1, d, generator=g)) == (False, float("-inf"))
+    for m in mem:
+        pool.append(m)
+    memory_fea = torch.cat(mem, dim=0)
+    memory_fea = memory_fea / torch.norm(memory_fea, p=2, dim=-1).unsqueeze(-1)
+    for q in (mem[17] + 0.3 * torch.randn(1, d, generator=g), torch.randn(1, d, generator=g)):
+        q_fea = q / torch.norm(q, p=2, dim=-1)
+        sim = q_fea @ memory_fea.T
+        gate, best = pool.hice_memory_gate(q)
+        assert gate == bool(sim.max() > 0.81)
+        assert abs(best - float(sim.max())) < 1e-5
+    assert pool.hice_memory_gate(mem[17])[0] is True
