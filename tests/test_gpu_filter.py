@@ -239,3 +239,32 @@ def test_full_size_bank_has_no_fallbacks():
     c = fb.search(q[:8], 32, flags=L.FORCE_STREAM)
     assert torch.equal(a[1][:8], c[1]) and torch.equal(a[0][:8], c[0])
     fb.close()
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_filter_random_shapes_against_the_stream_kernel(seed):
+    """Randomised shapes / modes: the tensor-core filter path returns what the CUDA-core stream kernel returns, bit
+    for bit (queries that took the 3xTF32 fallback: within the fp32 contract)."""
+    import random
+    rnd = random.Random(1000 + seed)
+    n = rnd.choice([1, 7, 127, 129, 1000, 4097, 20000, 50001])
+    d = 4 * rnd.randint(1, 256)
+    nq = rnd.choice([5, 16, 17, 63, 64, 65, 130, 257, 300])
+    k = rnd.choice([1, 2, 5, 16, 31, 32, 33, 64])
+    nb, nqm = rnd.choice([("eps", "eps"), ("noeps", "noeps"), (None, None), ("eps", None), (None, "eps")])
+    unit = rnd.random() < 0.5
+    bank, q = _randn(n, d, 7 * seed + 1, unit=unit), _randn(nq, d, 7 * seed + 2, unit=unit)
+    if not unit and rnd.random() < 0.5:
+        bank = bank * torch.exp(torch.randn(n, 1, generator=torch.Generator().manual_seed(seed)))
+    fb = FactBank.from_embeddings(bank)
+    _fallbacks()
+    a = fb.search(q.cuda(), k, normalize_bank=nb, normalize_query=nqm, flags=FILTER)
+    nfb = _fallbacks()
+    b = fb.search(q.cuda(), k, normalize_bank=nb, normalize_query=nqm, flags=L.FORCE_STREAM)
+    kk = min(k, n)
+    truth = ss.truth_scores_fp64(q, bank, normalize_bank=bool(nb), normalize_query=bool(nqm))
+    ss.compare_topk(a[0].cpu().numpy()[:, :kk], a[1].cpu().numpy()[:, :kk], truth, k, gap=GAP, rtol=RTOL, atol=ATOL)
+    assert bool((a[1][:, kk:] == -1).all())
+    if nfb == 0:
+        assert torch.equal(a[1], b[1]) and torch.equal(a[0], b[0]), (n, d, nq, k, nb, nqm)
+    fb.close()
