@@ -346,8 +346,14 @@ static int run_search(Scratch* s, const SearchArgs& a, uint64_t* out_keys, float
       rp.qerr = side.qerr; rp.bank_max_sumsq = a.max_sumsq;
       if ((rc = side.merge ? refine_launch(rp, stream) : refine_lists_launch(rp, stream))) return rc;
       // queries for which a lost row could still matter are redone exactly; for all others these launches
-      // exit at once (the flags live on the device: no host round trip, graph-capturable)
-      if ((rc = tc_pipeline(s, ac, kTcTf32x3, nullptr, side.need, ok, os, oi, stream))) return rc;
+      // exit at once (the flags live on the device: no host round trip, graph-capturable).  The fallback's top-k
+      // (3xTF32 scores) is then re-scored in the stream kernel's arithmetic like every other result, so scores
+      // stay bit-identical across kernels, batch sizes and shardings even for flagged queries.
+      uint64_t* fkeys = side.akeys;                                      // [Q, top_k] keys; akeys is free again
+      if ((rc = tc_pipeline(s, ac, kTcTf32x3, nullptr, side.need, fkeys, nullptr, nullptr, stream))) return rc;
+      RefineParams fr = rp;
+      fr.akeys = fkeys; fr.kp = a.top_k; fr.only_if = side.need; fr.lostu = nullptr; fr.n_lists = 0;
+      if ((rc = refine_launch(fr, stream))) return rc;
     }
     return DEVQA_OK;
   }

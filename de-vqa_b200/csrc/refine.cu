@@ -81,6 +81,7 @@ __global__ void __launch_bounds__(kRefineThreads) refine_kernel(const RefinePara
   const int dpad = (dim + CH - 1) / CH * CH;
   float* sq = reinterpret_cast<float*>(smem_raw);                  // the query exactly as the stream kernel stages it
   const int q = blockIdx.x;
+  if (p.only_if && p.only_if[q] == 0u) return;                     // conditional run (after the exact fallback)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const float* src = p.queries + size_t(q) * p.query_ld;
   const float inv = p.qinv[q];
@@ -150,8 +151,9 @@ __global__ void __launch_bounds__(kRefineThreads) refine_kernel(const RefinePara
       __syncthreads();
     }
   }
-  // nothing lost can enter the top-k?
-  if (threadIdx.x == 0) {
+  // nothing lost can enter the top-k?  (not asked when this run only re-expresses an exact result in the stream
+  // kernel's arithmetic)
+  if (threadIdx.x == 0 && !p.only_if) {
     const uint64_t kth = ex[p.top_k - 1];
     bool complete = true;
     uint32_t lost = s_lost;                                         // full per-CTA lists

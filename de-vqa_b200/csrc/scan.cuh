@@ -86,6 +86,8 @@ struct RefineParams {
   int32_t kp, top_k;
   uint32_t flags;
   IdMap idmap;
+  const uint32_t* only_if;    // refine_launch only: when set, re-score (and re-sort) akeys of the flagged queries and
+                              // nothing else -- no completeness verdict (used on the exact fallback's result)
   uint32_t* need;             // [n_queries] out: 1 when a lost row could still belong to the exact top-k
   uint32_t* fallbacks;        // device counter of such queries (devqa_filter_fallbacks)
   uint64_t* out_keys; float* out_scores; int64_t* out_ids;   // exactly one of keys / (scores, ids): [n_queries, top_k]
