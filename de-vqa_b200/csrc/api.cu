@@ -302,10 +302,15 @@ static int run_search(Scratch* s, const SearchArgs& a, uint64_t* out_keys, float
                       ((a.flags & DEVQA_NORMALIZE_BANK) || (a.row_sumsq && a.max_sumsq));
     if (s->profiling) s->prof_searches++;
     constexpr int64_t kChunkQ = 1024;                                  // bounds the candidate scratch (grid x Q x kcap keys)
-    for (int64_t c0 = 0; c0 < a.n_queries; c0 += kChunkQ) {
+    for (int64_t c0 = 0, clen = 0; c0 < a.n_queries; c0 += clen) {
       SearchArgs ac = a;
       ac.queries = a.queries + c0 * a.query_ld;
       ac.n_queries = a.n_queries - c0 < kChunkQ ? a.n_queries - c0 : kChunkQ;
+      // 256-query passes: a ragged tail (e.g. 300 = 256 + 44) goes into its own chunk, which then plans a narrower,
+      // faster pass for itself instead of a second 256-wide one that is mostly padding
+      if (filt && a.row_sumsq && ac.n_queries > 256 && ac.n_queries % 256 != 0 && ac.n_queries % 256 <= 192)
+        ac.n_queries -= ac.n_queries % 256;
+      clen = ac.n_queries;
       uint64_t* ok = out_keys ? out_keys + c0 * a.top_k : nullptr;
       float* os = out_scores ? out_scores + c0 * a.top_k : nullptr;
       int64_t* oi = out_ids ? out_ids + c0 * a.top_k : nullptr;

@@ -115,6 +115,25 @@ def test_sharded_merge_equals_unsharded_bit_for_bit(big_bank):
         assert torch.equal(i, ref_i) and torch.equal(s, ref_s)
 
 
+def test_sharded_large_batch_equals_unsharded_bit_for_bit(big_bank):
+    """The same emulation with a large batch: 300 queries run the 256-query CTA-pair kernel plus a 64-query pass on the
+    whole bank and on each of 8 shards (different tile counts, thresholds and candidate sets per shard) -- the merged
+    result must not differ in a single bit."""
+    q = _queries(300, 1001)
+    ref_s, ref_i = big_bank.search(q, K)
+    bounds = devqa_b200.dist.shard_bounds(N, 8)
+    packed = []
+    for r in range(8):
+        lo, hi = bounds[r], bounds[r + 1]
+        shard = FactBank(D, capacity=hi - lo)
+        shard.append_synthetic(hi - lo, seed=3234, first_global_row=lo)
+        shard.set_id_map(lo)
+        packed.append(shard.search_packed(q, K))
+        shard.close()
+    s, i = topk_merge(torch.stack(packed), K)
+    assert torch.equal(i, ref_i) and torch.equal(s, ref_s)
+
+
 def test_chunked_id_map_on_device():
     """Round-robin chunk ownership (appendable sharded bank): ids returned are global ids."""
     n, d, chunk, world = 10_000, 64, 256, 4
