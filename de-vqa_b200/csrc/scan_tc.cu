@@ -79,7 +79,7 @@ constexpr int kSetKBlocks = 32;
 // filter epilogue: hit queue entries; the same words hold the dense [16][128] score tile (8 KB), so >= 1024
 __host__ __device__ constexpr int hit_cap(int qp) { return (qp > 128 || qp < 32) ? 1024 : 2048; }
 // undocumented debugging bits of `flags` (performance bisection only; results are wrong when set)
-constexpr unsigned kDbgNoInsert = 1u << 16, kDbgNoSplit = 1u << 17, kDbgNoMma2 = 1u << 18, kDbgNoQueryTma = 1u << 19, kDbgNoPrefetch = 1u << 20, kDbgNoBoot = 1u << 23, kDbgNoPair = 1u << 28, kDbgPairAll = 1u << 29, kDbgNoMma1 = 1u << 30;                     // k-blocks (of 32 columns) accumulated inside the tensor core
+constexpr unsigned kDbgNoInsert = 1u << 16, kDbgNoSplit = 1u << 17, kDbgNoMma2 = 1u << 18, kDbgNoQueryTma = 1u << 19, kDbgL2Prefetch = 1u << 20, kDbgNoBoot = 1u << 23, kDbgNoPair = 1u << 28, kDbgPairAll = 1u << 29, kDbgNoMma1 = 1u << 30;                     // k-blocks (of 32 columns) accumulated inside the tensor core
 
 // ---- PTX wrappers ---------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return uint32_t(__cvta_generic_to_shared(p)); }
@@ -836,9 +836,10 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap bank_map, const __grid_consta
   if (warp == 0) {
     // ===== TMA producer =====
     if (lane == 0) {
-      // The smem ring holds a few k-blocks only, so HBM latency is also hidden one level up: bank
-      // k-blocks are prefetched into L2 kPrefetchAhead k-blocks ahead of the ring loads.
-      const bool pf_on = !(p.flags & kDbgNoPrefetch);
+      // (An L2 prefetch of the tiles a dozen k-blocks ahead of the ring used to run here.  With 4-8 ring stages in
+      // flight it only cost: every byte touched L2 twice.  Measured at 10M x 768, sustained: Q = 16 5.29 -> 4.40 ms,
+      // Q = 64 5.19 -> 4.90 ms, Q = 1024 31.8 -> 28.5 ms, 1M rows Q = 64 0.594 -> 0.524 ms.  Opt-in for experiments.)
+      const bool pf_on = (p.flags & kDbgL2Prefetch) != 0;
       const bool qtma = !(p.flags & kDbgNoQueryTma);
       const uint32_t tx_bytes = kATileBytes + (qtma ? b_stage_bytes : 0u);
       int pf_it = 0, pf_kb = 0;                           // next k-block to prefetch

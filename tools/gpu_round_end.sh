@@ -18,5 +18,5 @@ python tools/bench_configs.py --cpu > gpurun_out/configs_r01c.jsonl 2> gpurun_ou
 tail -3 gpurun_out/configs_r01c.err
 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/launches_filt_r01.csv python bench.py --steps 4 --warmup 3 --no-cpu-baseline --no-regimes > gpurun_out/ncu_launch_filt.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:scan_tc_kernel -s 2 -c 1 -o gpurun_out/filt_r01 -f python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-regimes > gpurun_out/ncu_full_filt.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:scan_tc_kernel -s 2 -c 1 -o gpurun_out/filt_pair_r01 -f python bench.py --queries 256 --steps 2 --warmup 3 --no-cpu-baseline --no-regimes > gpurun_out/ncu_full_pair.log 2>&1
+ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k 'regex:scan_tc_kernel<.int.256' -s 2 -c 1 -o gpurun_out/filt_pair_r01 -f python bench.py --queries 256 --steps 2 --warmup 3 --no-cpu-baseline --no-regimes > gpurun_out/ncu_full_pair.log 2>&1
 tail -1 gpurun_out/ncu_full_pair.log
