@@ -271,11 +271,11 @@ static int run_search(Scratch* s, const SearchArgs& a, uint64_t* out_keys, float
   const int nv = vectorised ? nv_vec : 1;
   int rc;
   // ---- kernel selection (by batch size only, so that every shard of a sharded bank picks the same one) ----
-  // Q <= 4: one pass of the CUDA-core stream (measured 6.6-7.0 TB/s on 10M x 768).  Larger batches: the
-  // tcgen05 contraction (fp32 banks), which holds ~6.3 TB/s up to 16 queries per pass where the CUDA-core
-  // kernel turns issue-bound (5.4 TB/s at 8 queries, two passes beyond).
+  // Q <= 2: one pass of the CUDA-core stream (7.0 TB/s on 10M x 768, two launches).  Larger batches: the tcgen05
+  // contraction, which streams at the same rate up to 64 queries per pass (the CUDA-core kernel is issue-bound
+  // from 4 queries per pass on: 4.87 ms against 4.40 ms sustained on 10M rows).
   const bool tc_ok = scan_tc_supported(a.dtype, a.bank, a.dim, a.bank_ld, a.top_k) && a.n_rows > 0;
-  bool use_tc = tc_ok && a.n_queries > 4;
+  bool use_tc = tc_ok && a.n_queries > 2;
   if (a.flags & DEVQA_FORCE_STREAM) use_tc = false;
   if (a.flags & DEVQA_FORCE_TENSOR) {
     if (!tc_ok) {

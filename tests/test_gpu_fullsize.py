@@ -69,7 +69,7 @@ def test_prefix_idempotence_sortedness(big_bank):
         assert (s32[:, :-1] >= s32[:, 1:]).all()
         assert all(len(set(r)) == 32 for r in i32.cpu().tolist())
         # a query's result does not depend on what else is in the batch, nor on the kernel that serves the batch
-        # (<= 4 queries: CUDA-core stream, more: tcgen05 filter + exact re-scoring in the stream kernel's arithmetic)
+        # (<= 2 queries: CUDA-core stream, more: tcgen05 filter + exact re-scoring in the stream kernel's arithmetic)
         s1, i1 = big_bank.search(q[:1], 32)
         assert torch.equal(i1, i32[:1]) and torch.equal(s1, s32[:1])
         if nq >= 8:

@@ -146,7 +146,7 @@ def main():
             best, med = time_search(lambda: fb.search(qd, 32), 50, False)
             emit(config="C3", n=1_000_000, d=768, q=nq, k=32, ms_best=best, ms_median=med, qps=nq * 1e3 / med,
                  gbs=3.072 / (med * 1e-3), frac_of_measured=3.072 / (med * 1e-3) / PEAK,
-                 kernel="tcgen05" if nq > 4 else "stream")
+                 kernel="tcgen05" if nq > 2 else "stream")
         if a.cpu:
             bank = fb.rows().cpu()
             for nq in (1, 8, 64):
