@@ -188,8 +188,10 @@ constexpr int kRefineListThreads = 512;
 template <bool VEC>
 __global__ void __launch_bounds__(kRefineListThreads) refine_lists_kernel(const RefineParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int kWide = 512;                                         // first-cut capacity (= threads: one key each)
+  static_assert(kWide == kRefineListThreads, "one key per thread in the second cut");
   __shared__ uint64_t ex[kMaxKp];
-  __shared__ uint64_t ak[kMaxKp];
+  __shared__ uint64_t ak[kWide];
   __shared__ uint32_t s_count, s_lost, s_tcode;
   constexpr int CH = VEC ? 128 : 32;
   const int dim = int(p.dim);
@@ -241,11 +243,44 @@ __global__ void __launch_bounds__(kRefineListThreads) refine_lists_kernel(const 
     const uint64_t key = p.cand[(size_t(g) * p.n_queries + q) * p.cand_kcap + e];
     if (key != kEmptyKey && uint32_t(key >> 32) >= tcode) {
       const uint32_t slot = atomicAdd(&s_count, 1u);
-      if (slot < uint32_t(kMaxKp)) ak[slot] = key;
+      if (slot < uint32_t(kWide)) ak[slot] = key;
     }
   }
   __syncthreads();
-  const uint32_t n_raw = s_count;
+  uint32_t n_raw = s_count;
+  // Second cut.  T from the CTAs' bests is loose when top_k is not small against the number of CTAs (k = 64 of 148:
+  // ~30% more rows above it than the true k-th best has).  With the first cut in shared memory the exact k-th
+  // best upper bound of everything kept is one bitonic sort away: keep what is >= that - 2E.
+  if (n_raw > uint32_t(kMaxKp) && n_raw <= uint32_t(kWide)) {
+    uint64_t mine = threadIdx.x < int(n_raw) ? ak[threadIdx.x] : kEmptyKey;
+    __syncthreads();
+    ak[threadIdx.x] = mine;
+    __syncthreads();
+    for (int k = 2; k <= kWide; k <<= 1) {
+      for (int j = k >> 1; j > 0; j >>= 1) {
+        const int i = threadIdx.x, l = i ^ j;
+        if (l > i) {
+          const uint64_t a = ak[i], b = ak[l];
+          const bool desc = (i & k) == 0;
+          if (desc ? a < b : a > b) { ak[i] = b; ak[l] = a; }
+        }
+        __syncthreads();
+      }
+    }
+    // ak is sorted by upper bound, descending; the k-th entry bounds the exact k-th best from below (minus 2E)
+    if (threadIdx.x == 0) {
+      float maxn = 1.f;
+      if (!(p.flags & DEVQA_NORMALIZE_BANK)) maxn = sqrtf(__uint_as_float(*p.bank_max_sumsq));
+      const float t = key_score(ak[p.top_k - 1]) - 2.0001f * p.qerr[q] * maxn;
+      s_tcode = t == t ? score_code(t) : 0u;
+      s_count = 0u;
+    }
+    __syncthreads();
+    const uint32_t t2 = s_tcode;
+    if (threadIdx.x < int(n_raw) && uint32_t(ak[threadIdx.x] >> 32) >= t2) atomicAdd(&s_count, 1u);   // a prefix: ak is sorted
+    __syncthreads();
+    n_raw = s_count;
+  }
   const int n = n_raw < uint32_t(kMaxKp) ? int(n_raw) : kMaxKp;
   // ---- exact re-scoring ----
   for (int c = warp; c < n; c += kRefineListThreads / 32) {
