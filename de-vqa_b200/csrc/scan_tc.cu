@@ -1369,8 +1369,6 @@ int scan_tc_plan(int mode, int n_queries, int64_t dim, int kcap, bool cached_nor
   int qp = filt ? (cached_norms ? 256 : 64) : (scan_tc_kblocks(mode, dim) > kSetKBlocks ? 32 : 64);
   const int q16 = (n_queries + 15) / 16 * 16;
   while (qp > 16 && qp / 2 >= q16) qp >>= 1;
-  // 129..192 queries: two passes of 128 at the HBM-bound rate beat one shared-memory-bound pass of 256
-  if (qp == 256 && n_queries <= 192) qp = 128;
   // banks of fewer tiles than SMs: narrower passes run side by side, so that tiles x passes covers the machine
   if (filt)
     while (qp > 32 && n_tiles * ((n_queries + qp - 1) / qp) < sm_count) qp >>= 1;
