@@ -1,6 +1,7 @@
 // C ABI of libdevqa (include/devqa.h): bank object, workspace, kernel selection, NCCL plumbing.
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <atomic>
 #include <mutex>
@@ -40,6 +41,7 @@ struct Scratch {
   float* qsplit = nullptr;    size_t qsplit_bytes = 0;     // TF32 hi / lo query planes of the tcgen05 scan
   uint64_t* akeys = nullptr;  size_t akeys_bytes = 0;      // filter scan: merged approximate top-K' lists + per-query side arrays
   uint32_t* fallbacks = nullptr;                           // device counter: queries the exact fallback had to redo
+  uint32_t* ticket = nullptr;                              // device word: arrival counter of the stream kernel's fused merge
   cudaStream_t last_stream = nullptr;
   cudaEvent_t done = nullptr;
   // optional per-kernel timing (devqa_profile_*): event pairs around the scan passes of each search
@@ -90,8 +92,9 @@ static int scratch_for(int device, Scratch** out) {
     DEVQA_CUDA(cudaEventCreateWithFlags(&s->done, cudaEventDisableTiming));
     {
       DeviceGuardLite guard(device);
-      DEVQA_CUDA(cudaMalloc(&s->fallbacks, 4));
-      DEVQA_CUDA(cudaMemset(s->fallbacks, 0, 4));
+      DEVQA_CUDA(cudaMalloc(&s->fallbacks, 8));
+      DEVQA_CUDA(cudaMemset(s->fallbacks, 0, 8));
+      s->ticket = s->fallbacks + 1;
     }
     s->sm_count = n;
   }
@@ -391,6 +394,10 @@ static int run_search(Scratch* s, const SearchArgs& a, uint64_t* out_keys, float
     bank_ptr = s->tiny;
   }
   p.bank = bank_ptr; p.cand = s->cand;
+  // the last CTA of each pass merges: no merge launch (opt-in via DEVQA_FUSED_MERGE=1 until verified on hardware)
+  static const bool fused_ok = getenv("DEVQA_FUSED_MERGE") != nullptr && atoi(getenv("DEVQA_FUSED_MERGE")) != 0;
+  const bool fused_merge = fused_ok && kcap == 32;
+  if (fused_merge) { p.ticket = s->ticket; p.out_keys = out_keys; p.out_scores = out_scores; p.out_ids = out_ids; }
   const bool prof = s->profiling && s->prof_used < Scratch::kProfSlots;
   if (s->profiling) s->prof_searches++;
   if (prof) DEVQA_CUDA(cudaEventRecord(s->prof_ev[2 * s->prof_used], stream));
@@ -405,6 +412,7 @@ static int run_search(Scratch* s, const SearchArgs& a, uint64_t* out_keys, float
     DEVQA_CUDA(cudaEventRecord(s->prof_ev[2 * s->prof_used + 1], stream));
     s->prof_used++;
   }
+  if (fused_merge) return DEVQA_OK;
   return merge_lists_launch(s->cand, grid, a.n_queries, kcap, kcap, a.top_k, out_keys, out_scores, out_ids, stream);
 }
 
@@ -485,6 +493,8 @@ static SearchArgs bank_args(const devqa_bank* b, const float* q, int64_t nq, int
 }
 
 // H2D of queries into scratch; returns device pointer
+static bool small_io(size_t qbytes, size_t obytes) { return qbytes <= 16 * 1024 && obytes <= 16 * 1024; }
+
 static int stage_queries(Scratch* s, const float* qh, int64_t nq, int64_t dim, int64_t qld, int top_k,
                          float** dq, float** d_scores, int64_t** d_ids, cudaStream_t stream) {
   const size_t qbytes = size_t(nq) * dim * 4;
@@ -496,8 +506,13 @@ static int stage_queries(Scratch* s, const float* qh, int64_t nq, int64_t dim, i
   if (rc) return rc;
   float* pq = static_cast<float*>(s->pin_io);
   for (int64_t i = 0; i < nq; ++i) memcpy(pq + i * dim, qh + i * qld, size_t(dim) * 4);
+  // Small calls (the reference's one query at a time): the merge kernel writes the few result bytes straight into
+  // the pinned staging buffer (device-accessible under unified addressing) -- one copy command less per search.
+  // (Reading the QUERIES from host memory was tried too: every CTA fetching them across the bus doubled the
+  // end-to-end latency, 50 -> 104 us at 6345 x 384.)
   *dq = static_cast<float*>(s->dev_io);
-  char* outs = static_cast<char*>(s->dev_io) + ((qbytes + 255) / 256) * 256;
+  char* base = small_io(qbytes, obytes) ? static_cast<char*>(s->pin_io) : static_cast<char*>(s->dev_io);
+  char* outs = base + ((qbytes + 255) / 256) * 256;
   *d_ids = reinterpret_cast<int64_t*>(outs);
   *d_scores = reinterpret_cast<float*>(outs + size_t(nq) * top_k * 8);
   DEVQA_CUDA(cudaMemcpyAsync(*dq, pq, qbytes, cudaMemcpyHostToDevice, stream));
@@ -509,7 +524,8 @@ static int unstage_results(Scratch* s, int64_t nq, int64_t dim, int top_k, float
   const size_t off = ((qbytes + 255) / 256) * 256;
   const size_t obytes = size_t(nq) * top_k * 12;
   char* pin_out = static_cast<char*>(s->pin_io) + off;
-  DEVQA_CUDA(cudaMemcpyAsync(pin_out, static_cast<char*>(s->dev_io) + off, obytes, cudaMemcpyDeviceToHost, stream));
+  if (!small_io(qbytes, obytes))
+    DEVQA_CUDA(cudaMemcpyAsync(pin_out, static_cast<char*>(s->dev_io) + off, obytes, cudaMemcpyDeviceToHost, stream));
   DEVQA_CUDA(cudaStreamSynchronize(stream));
   memcpy(ids_h, pin_out, size_t(nq) * top_k * 8);
   memcpy(scores_h, pin_out + size_t(nq) * top_k * 8, size_t(nq) * top_k * 4);

@@ -28,6 +28,9 @@ struct ScanParams {
   const uint32_t* seed_u;  // optional [n_queries] score codes of a prefix sample's k-th best upper bound
   const uint32_t* bank_max_sumsq;   // un-normalised scores: max ||row||^2 over the bank (float bits)
   int32_t k_true;          // caller's top_k (the lists keep kcap entries)
+  // stream kernel, capacity 32: the last CTA to finish merges the per-CTA lists itself (no merge launch)
+  uint32_t* ticket;        // zeroed device word (re-zeroed by the kernel); nullptr: separate merge kernel
+  uint64_t* out_keys; float* out_scores; int64_t* out_ids;   // final [n_queries, top_k] (exactly one form)
   uint32_t* lostu;         // [grid, n_queries] out: bound on the rows each CTA's full list lost (score code, 0 = none)
   uint32_t* gmax;          // [q_pad, gmax_stride] zeroed scratch: each CTA's best upper bound per query (score codes)
   int32_t gmax_stride;

@@ -343,6 +343,38 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_stream_kernel(const Scan
     const uint64_t* src = lists + size_t(q) * kcap;
     for (int e = lane; e < kcap; e += 32) out[e] = src[e];
   }
+  // ---- fused cross-CTA merge (capacity 32): the last CTA to get here folds every CTA's list ---------------
+  // One launch instead of two: on the reference's one-query-at-a-time banks (6-19k rows) the second launch and
+  // its ramp were a third of the device time.
+  if (p.ticket != nullptr) {
+    __shared__ unsigned s_ticket;
+    __threadfence();                                   // this CTA's lists are visible device-wide
+    __syncthreads();
+    if (threadIdx.x == 0) s_ticket = atomicAdd(p.ticket, 1u);
+    __syncthreads();
+    if (s_ticket != gridDim.x - 1) return;
+    __threadfence();
+    uint64_t* sacc = lists;                            // [kScanWarps][32], the lists are dead now
+    const int rev = 31 - lane;
+    for (int q = 0; q < p.nq_pass; ++q) {
+      uint64_t acc = kEmptyKey;
+      for (int l = warp; l < int(gridDim.x); l += kScanWarps) {
+        const uint64_t* src = p.cand + (size_t(l) * p.n_queries + (p.q0 + q)) * 32;
+        acc = warp_merge32(acc, __ldcg(src + rev), lane);
+      }
+      __syncthreads();
+      sacc[warp * 32 + lane] = acc;
+      __syncthreads();
+      for (int s2 = 1; s2 < kScanWarps; s2 <<= 1) {
+        if ((warp % (2 * s2)) == 0 && warp + s2 < kScanWarps) acc = warp_merge32(acc, sacc[(warp + s2) * 32 + rev], lane);
+        __syncthreads();
+        if ((warp % (2 * s2)) == 0) sacc[warp * 32 + lane] = acc;
+        __syncthreads();
+      }
+      if (warp == 0) emit_result(acc, lane, p.top_k, p.q0 + q, p.out_keys, p.out_scores, p.out_ids);
+    }
+    if (threadIdx.x == 0) *p.ticket = 0u;              // ready for the next launch (stream-ordered)
+  }
 }
 
 template <typename T, int NV, int QT, int R>

@@ -75,4 +75,18 @@ __device__ __forceinline__ uint64_t warp_sort32_desc(uint64_t v, int lane) {
   return v;
 }
 
+// Final result slot e of query q: packed key, or (score, id) with -inf / -1 for an empty slot.
+__device__ __forceinline__ void emit_result(uint64_t key, int e, int top_k, int64_t q, uint64_t* out_keys, float* out_scores,
+                                            int64_t* out_ids) {
+  if (e >= top_k) return;
+  const size_t o = size_t(q) * top_k + e;
+  if (out_keys) {
+    out_keys[o] = key;
+  } else {
+    const bool empty = key == kEmptyKey;
+    out_scores[o] = empty ? -INFINITY : key_score(key);
+    out_ids[o] = empty ? int64_t(-1) : int64_t(key_id(key));
+  }
+}
+
 }  // namespace devqa
