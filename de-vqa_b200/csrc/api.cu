@@ -394,8 +394,8 @@ static int run_search(Scratch* s, const SearchArgs& a, uint64_t* out_keys, float
     bank_ptr = s->tiny;
   }
   p.bank = bank_ptr; p.cand = s->cand;
-  // the last CTA of each pass merges: no merge launch (opt-in via DEVQA_FUSED_MERGE=1 until verified on hardware)
-  static const bool fused_ok = getenv("DEVQA_FUSED_MERGE") != nullptr && atoi(getenv("DEVQA_FUSED_MERGE")) != 0;
+  // the last CTA of each pass merges: no merge launch (DEVQA_FUSED_MERGE=0 restores the separate merge kernel)
+  static const bool fused_ok = getenv("DEVQA_FUSED_MERGE") == nullptr || atoi(getenv("DEVQA_FUSED_MERGE")) != 0;
   const bool fused_merge = fused_ok && kcap == 32;
   if (fused_merge) { p.ticket = s->ticket; p.out_keys = out_keys; p.out_scores = out_scores; p.out_ids = out_ids; }
   const bool prof = s->profiling && s->prof_used < Scratch::kProfSlots;
