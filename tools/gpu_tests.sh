@@ -5,3 +5,9 @@ timeout 1500 python -m pytest tests -x -q -m gpu > gpurun_out/pytest_gpu_all.log
 echo "pytest exit $?" >> gpurun_out/pytest_gpu_all.log
 tail -12 gpurun_out/pytest_gpu_all.log
 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; tail -1 gpurun_out/smoke.log
+python bench.py --steps 30 --warmup 3 --no-cpu-baseline --no-regimes | python -c "
+import sys,json
+for ln in sys.stdin:
+    if ln.startswith('{'):
+        d=json.loads(ln); print('bench Q64 x30', 'ms', round(d['ms_per_step'],3), 'q/s', round(d['value']), 'e2e', round(d['e2e']['value']), 'frac', round(d['roofline']['frac'],3), 'launches/step', d['gpu_launches']/d['steps'], d['e2e']['matches_device_path'])
+"
