@@ -271,3 +271,18 @@ def test_filter_random_shapes_against_the_stream_kernel(seed):
     if nfb == 0:
         assert torch.equal(a[1], b[1]) and torch.equal(a[0], b[0]), (n, d, nq, k, nb, nqm)
     fb.close()
+
+
+@pytest.mark.parametrize("n,d,nq,k", [(3000, 37, 9, 5), (20000, 101, 70, 16), (2500, 385, 33, 32), (129, 3, 6, 2)])
+def test_filter_dims_not_multiple_of_four(n, d, nq, k):
+    """Rows of a FactBank are padded to 16 bytes, so the tensor path still applies; the exact re-scoring then has to
+    follow the stream kernel's SCALAR column order (one column per lane and chunk) to stay bit-identical."""
+    bank, q = _randn(n, d, 5 * n + d, unit=False), _randn(nq, d, 3 * nq + d, unit=False)
+    fb = FactBank.from_embeddings(bank)
+    a = fb.search(q.cuda(), k, flags=FILTER)
+    b = fb.search(q.cuda(), k, flags=L.FORCE_STREAM)
+    truth = ss.truth_scores_fp64(q, bank)
+    kk = min(k, n)
+    ss.compare_topk(a[0].cpu().numpy()[:, :kk], a[1].cpu().numpy()[:, :kk], truth, k, gap=GAP, rtol=RTOL, atol=ATOL)
+    assert torch.equal(a[1], b[1]) and torch.equal(a[0], b[0])
+    fb.close()
