@@ -83,6 +83,9 @@ extern "C" {
 #define DEVQA_DEBUG_FILTER_ONLY (1u << 22) /* tests: return the TF32 filter's approximate top-k as is (no exact
                                               re-scoring) so that its error bound can be checked            */
 
+/* Environment knob (read once): DEVQA_FUSED_MERGE=0 makes the small-batch stream kernel launch a separate merge
+ * kernel instead of letting its last CTA merge the per-CTA lists (the default since it saves a launch per search). */
+
 typedef struct devqa_bank devqa_bank; /* opaque, library-owned fact bank */
 typedef struct devqa_comm devqa_comm; /* opaque, one NCCL communicator + staging */
 
