@@ -95,9 +95,13 @@ def encode_ike_facts(sentence_model, ds, hparams) -> Dict:
     return stored
 
 
-def encode_ike_facts_multimodal(sentence_model, ds, hparams) -> Dict:
+def encode_ike_facts_multimodal(sentence_model, ds, hparams, device=None) -> Dict:
     """Multimodal bank in the frozen four-column layout (util.py:54-86): three rows per record
-    (edit, rephrase, locality), pickled to ``{results_dir}/embedding/{task_name}_embeddings_llava.pkl``."""
+    (edit, rephrase, locality), pickled to ``{results_dir}/embedding/{task_name}_embeddings_llava.pkl``.
+
+    ``device`` (extension): also leave the bank RESIDENT on that GPU and register it under the file
+    just written, so that the first ``apply_ike_to_multimodal_model`` / ``bank_from_file`` after the build does
+    not go pickle -> numpy -> torch.tensor -> .to(device) again (ike_main.py:187-194 does that on every request)."""
     sentences, images, prompts = [], [], []
     for rec in ds:
         images += [rec['image_path'], rec['rephrase_image_path'], rec['locality_image_path']]
@@ -108,8 +112,11 @@ def encode_ike_facts_multimodal(sentence_model, ds, hparams) -> Dict:
               'images': images, 'prompts': prompts}
     base_path = f'{hparams.results_dir}/embedding'
     os.makedirs(base_path, exist_ok=True)
-    with open(f'{base_path}/{hparams.task_name}_embeddings_llava.pkl', "wb") as f:
+    path = f'{base_path}/{hparams.task_name}_embeddings_llava.pkl'
+    with open(path, "wb") as f:
         pickle.dump(stored, f, protocol=pickle.HIGHEST_PROTOCOL)
+    if device is not None:
+        register_bank_for_file(path, FactBank.from_stored_data(stored, device=_device_index(device)), device)
     return stored
 
 
@@ -123,6 +130,12 @@ def clear_bank_cache() -> None:
         b.close()
     _file_banks.clear()
     _object_banks.clear()
+
+
+def register_bank_for_file(path: str, bank: FactBank, device=0) -> None:
+    """Make ``bank`` the resident copy of the bank file at ``path`` (as it is on disk right now)."""
+    st = os.stat(path)
+    _file_banks[(os.path.abspath(path), st.st_size, st.st_mtime, _device_index(device))] = bank
 
 
 def bank_from_file(path: str, device=0) -> FactBank:

@@ -332,3 +332,31 @@ def test_search_is_capturable_in_a_cuda_graph():
         torch.cuda.synchronize()
         assert torch.equal(out[0], want2[0]) and torch.equal(out[1], want2[1])
     fb.close()
+
+
+def test_bank_producer_can_leave_the_bank_resident(tmp_path):
+    """N4: encode_ike_facts_multimodal(..., device=0) writes the frozen pickle AND registers the resident bank for it,
+    so the first lookup after the build does not re-read and re-upload the file (ike_main.py:187-194)."""
+    import pickle
+    import types
+    from devqa_b200 import retrieval
+    retrieval.clear_bank_cache()
+    enc = StubEncoder()
+    ds = [{"prompt": f"what is item {i}?", "target": f"thing {i}", "rephrase_prompt": f"item {i} is what?",
+           "locality_prompt": f"where is place {i}?", "locality_ground_truth": f"city {i}", "image_path": f"a{i}.jpg",
+           "rephrase_image_path": f"b{i}.jpg", "locality_image_path": f"c{i}.jpg"} for i in range(50)]
+    hp = types.SimpleNamespace(results_dir=str(tmp_path), task_name="vqa", sentence_model_name="x/stub", k=4, device=0,
+                               alg_name="IKE")
+    stored = retrieval.encode_ike_facts_multimodal(enc, ds, hp, device=0)
+    path = tmp_path / "embedding" / "vqa_embeddings_llava.pkl"
+    with open(path, "rb") as f:
+        on_disk = pickle.load(f)
+    assert list(on_disk) == ["sentences", "embeddings", "images", "prompts"] and len(on_disk["sentences"]) == 150
+    assert on_disk["embeddings"].dtype == np.float32 and np.array_equal(on_disk["embeddings"], stored["embeddings"])
+    bank = retrieval.bank_from_file(str(path), device=0)          # the registered, already resident bank
+    assert len(bank) == 150 and bank.sentences == stored["sentences"]
+    assert retrieval.bank_from_file(str(path), device=0) is bank
+    q = torch.tensor(enc.encode(stored["sentences"][7]))
+    s, i = bank.search(q.cuda(), 1)
+    assert int(i[0, 0]) == 7
+    retrieval.clear_bank_cache()
