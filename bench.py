@@ -201,8 +201,9 @@ def kernel_label(nq, bank_dtype, topk):
     """Which scan kernel api.cu selects for this batch (csrc/api.cu run_search)."""
     if nq <= 2:
         return "scan_stream_kernel (CUDA cores, 128-bit streaming loads)"
-    if bank_dtype == "fp32" and topk <= 64:
-        return "scan_tc_kernel<TF32x1 filter> (tcgen05/TMEM/TMA) + refine_kernel (exact fp32 re-scoring)"
+    if topk <= 64:
+        return "scan_tc_kernel<%s filter> (tcgen05/TMEM/TMA) + refine_kernel (exact fp32 re-scoring)" % (
+            "TF32x1" if bank_dtype == "fp32" else "bf16x1")
     return "scan_tc_kernel<%s> (tcgen05/TMEM/TMA)" % ("3xTF32" if bank_dtype == "fp32" else "bf16x3")
 
 
@@ -351,8 +352,7 @@ def run_ours(a):
                             "scan_gbs_per_gpu": gbs, "frac_of_measured_hbm": gbs / peak,
                             "useful_tflops": tflops,
                             "frac_of_tf32_tensor_peak": tflops / (tf32_peak * world), "tf32_peak_source": tf32_src,
-                            "kernel": ("stream" if nq <= 2 else ("tcgen05 TF32 filter + exact re-scoring"
-                                       if a.bank_dtype == "fp32" and a.topk <= 64 else "tcgen05")),
+                            "kernel": ("stream" if nq <= 2 else ("tcgen05 filter + exact re-scoring" if a.topk <= 64 else "tcgen05")),
                             "bank_passes_per_call": passes,
                             "exact_fallback_queries": filter_fallbacks(L, C, local_rank)})
 

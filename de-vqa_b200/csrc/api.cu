@@ -301,8 +301,12 @@ static int run_search(Scratch* s, const SearchArgs& a, uint64_t* out_keys, float
     const int kp = a.top_k <= 8 ? 32 : (a.top_k <= 16 ? 64 : 128);     // K': candidates kept per query after the merge
     // (Nothing here may depend on the number of rows: every shard of a sharded bank has to take the same path, or
     // G-GPU results would differ from 1-GPU results in the last bits of the scores.)
-    const bool filt = a.dtype == DEVQA_F32 && !(a.flags & DEVQA_FORCE_TF32X3) && a.top_k <= 64 && a.dim <= 16384 &&
-                      ((a.flags & DEVQA_NORMALIZE_BANK) || (a.row_sumsq && a.max_sumsq));
+    // bf16 banks: the same filter with queries rounded to bf16 (library-owned banks: cached row norms), bf16x3 as fallback.
+    const bool filt = !(a.flags & DEVQA_FORCE_TF32X3) && a.top_k <= 64 && a.dim <= 16384 &&
+                      (a.dtype == DEVQA_F32 ? ((a.flags & DEVQA_NORMALIZE_BANK) || (a.row_sumsq && a.max_sumsq))
+                                            : (a.row_sumsq != nullptr && a.max_sumsq != nullptr));
+    const int filt_mode = a.dtype == DEVQA_F32 ? kTcTf32x1 : kTcBf16x1;
+    const int exact_mode = a.dtype == DEVQA_F32 ? kTcTf32x3 : kTcBf16x3;
     if (s->profiling) s->prof_searches++;
     constexpr int64_t kChunkQ = 1024;                                  // bounds the candidate scratch (grid x Q x kcap keys)
     for (int64_t c0 = 0, clen = 0; c0 < a.n_queries; c0 += clen) {
@@ -340,13 +344,13 @@ static int run_search(Scratch* s, const SearchArgs& a, uint64_t* out_keys, float
       // straight out of the per-CTA lists (one kernel instead of merge + refine).
       const int64_t tiles = (a.n_rows + 127) / 128;
       side.merge = (a.flags & DEVQA_DEBUG_FILTER_ONLY) || tiles < s->sm_count || s->sm_count < a.top_k;
-      if ((rc = tc_pipeline(s, ac, kTcTf32x1, &side, nullptr, nullptr, nullptr, nullptr, stream))) return rc;
+      if ((rc = tc_pipeline(s, ac, filt_mode, &side, nullptr, nullptr, nullptr, nullptr, stream))) return rc;
       if (a.flags & DEVQA_DEBUG_FILTER_ONLY) {                           // tests: the filter's own upper bounds
         if ((rc = merge_lists_launch(side.akeys, 1, ac.n_queries, kp, kp, a.top_k, ok, os, oi, stream))) return rc;
         continue;
       }
       RefineParams rp{};
-      rp.bank = static_cast<const float*>(a.bank); rp.n_rows = a.n_rows; rp.dim = a.dim; rp.bank_ld = a.bank_ld;
+      rp.bank = a.bank; rp.bank_dtype = a.dtype; rp.n_rows = a.n_rows; rp.dim = a.dim; rp.bank_ld = a.bank_ld;
       rp.queries = ac.queries; rp.query_ld = a.query_ld; rp.n_queries = int32_t(ac.n_queries);
       rp.qinv = side.qinv; rp.akeys = side.akeys; rp.lostu = side.lostu; rp.n_lists = side.n_lists;
       rp.kp = kp; rp.top_k = a.top_k; rp.flags = a.flags; rp.idmap = a.idmap;
@@ -359,7 +363,7 @@ static int run_search(Scratch* s, const SearchArgs& a, uint64_t* out_keys, float
       // (3xTF32 scores) is then re-scored in the stream kernel's arithmetic like every other result, so scores
       // stay bit-identical across kernels, batch sizes and shardings even for flagged queries.
       uint64_t* fkeys = side.akeys;                                      // [Q, top_k] keys; akeys is free again
-      if ((rc = tc_pipeline(s, ac, kTcTf32x3, nullptr, side.need, fkeys, nullptr, nullptr, stream))) return rc;
+      if ((rc = tc_pipeline(s, ac, exact_mode, nullptr, side.need, fkeys, nullptr, nullptr, stream))) return rc;
       RefineParams fr = rp;
       fr.akeys = fkeys; fr.kp = a.top_k; fr.only_if = side.need; fr.lostu = nullptr; fr.n_lists = 0;
       if ((rc = refine_launch(fr, stream))) return rc;

@@ -31,9 +31,12 @@ namespace {
 constexpr int kRefineThreads = 256;
 constexpr int kMaxKp = 128;
 
-template <bool VEC>
-__device__ __forceinline__ float exact_score(const float* __restrict__ row, const float* sq, int dim, unsigned flags, int lane) {
-  constexpr int NV = VEC ? 4 : 1;
+// T = float: VEC = 4 columns per lane and chunk (128-bit loads), else 1.  T = __nv_bfloat16: VEC = 8 columns per lane
+// and chunk, unpacked low half first -- scan_stream.cu's Loader<T, NV> orders.
+template <typename T, bool VEC>
+__device__ __forceinline__ float exact_score(const T* __restrict__ row, const float* sq, int dim, unsigned flags, int lane) {
+  constexpr bool BF = sizeof(T) == 2;
+  constexpr int NV = VEC ? (BF ? 8 : 4) : 1;
   constexpr int CH = 32 * NV;
   const int nchunks = (dim + CH - 1) / CH;
   const bool norm = (flags & DEVQA_NORMALIZE_BANK) != 0;
@@ -41,14 +44,24 @@ __device__ __forceinline__ float exact_score(const float* __restrict__ row, cons
   for (int c = 0; c < nchunks; ++c) {
     const int col = c * CH + lane * NV;
     float b[NV], qv[NV];
-    if constexpr (VEC) {
+    if constexpr (VEC && BF) {
+      uint4 t = make_uint4(0u, 0u, 0u, 0u);
+      if (col < dim) t = __ldg(reinterpret_cast<const uint4*>(row + col));
+      b[0] = __uint_as_float(t.x << 16); b[1] = __uint_as_float(t.x & 0xffff0000u);
+      b[2] = __uint_as_float(t.y << 16); b[3] = __uint_as_float(t.y & 0xffff0000u);
+      b[4] = __uint_as_float(t.z << 16); b[5] = __uint_as_float(t.z & 0xffff0000u);
+      b[6] = __uint_as_float(t.w << 16); b[7] = __uint_as_float(t.w & 0xffff0000u);
+      const float4 u0 = *reinterpret_cast<const float4*>(sq + col), u1 = *reinterpret_cast<const float4*>(sq + col + 4);
+      qv[0] = u0.x; qv[1] = u0.y; qv[2] = u0.z; qv[3] = u0.w; qv[4] = u1.x; qv[5] = u1.y; qv[6] = u1.z; qv[7] = u1.w;
+    } else if constexpr (VEC) {
       float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
       if (col < dim) t = __ldg(reinterpret_cast<const float4*>(row + col));
       b[0] = t.x; b[1] = t.y; b[2] = t.z; b[3] = t.w;
       const float4 u = *reinterpret_cast<const float4*>(sq + col);
       qv[0] = u.x; qv[1] = u.y; qv[2] = u.z; qv[3] = u.w;
     } else {
-      b[0] = col < dim ? __ldg(row + col) : 0.f;
+      if constexpr (BF) b[0] = col < dim ? __bfloat162float(row[col]) : 0.f;
+      else b[0] = col < dim ? __ldg(row + col) : 0.f;
       qv[0] = sq[col];
     }
 #pragma unroll
@@ -69,14 +82,14 @@ __device__ __forceinline__ float exact_score(const float* __restrict__ row, cons
   return acc;
 }
 
-template <bool VEC>
+template <typename T, bool VEC>
 __global__ void __launch_bounds__(kRefineThreads) refine_kernel(const RefineParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ uint64_t ex[kMaxKp];
   __shared__ uint64_t ak[kMaxKp];
   __shared__ float s_prelim;
   __shared__ uint32_t s_lost;                                       // max score code of any full list's last entry
-  constexpr int CH = VEC ? 128 : 32;
+  constexpr int CH = VEC ? (sizeof(T) == 2 ? 256 : 128) : 32;
   const int dim = int(p.dim);
   const int dpad = (dim + CH - 1) / CH * CH;
   float* sq = reinterpret_cast<float*>(smem_raw);                  // the query exactly as the stream kernel stages it
@@ -100,7 +113,7 @@ __global__ void __launch_bounds__(kRefineThreads) refine_kernel(const RefinePara
       const int64_t gid = int64_t(key_id(a));
       int64_t row = gid - p.idmap.base;
       if (p.idmap.chunk > 0) row = ((row / p.idmap.chunk) / p.idmap.world) * p.idmap.chunk + row % p.idmap.chunk;
-      const float s = exact_score<VEC>(p.bank + row * p.bank_ld, sq, dim, p.flags, lane);
+      const float s = exact_score<T, VEC>(static_cast<const T*>(p.bank) + row * p.bank_ld, sq, dim, p.flags, lane);
       key = pack_key(s, uint32_t(gid));
     }
     if (lane == 0) ex[c] = key;
@@ -185,7 +198,7 @@ __global__ void __launch_bounds__(kRefineThreads) refine_kernel(const RefinePara
 // They are compacted into shared memory, ALL re-scored, sorted.  More than 128 of them: the query is flagged.
 constexpr int kRefineListThreads = 512;
 
-template <bool VEC>
+template <typename T, bool VEC>
 __global__ void __launch_bounds__(kRefineListThreads) refine_lists_kernel(const RefineParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int kWide = 512;                                         // first-cut capacity (= threads: one key each)
@@ -193,7 +206,7 @@ __global__ void __launch_bounds__(kRefineListThreads) refine_lists_kernel(const 
   __shared__ uint64_t ex[kMaxKp];
   __shared__ uint64_t ak[kWide];
   __shared__ uint32_t s_count, s_lost, s_tcode;
-  constexpr int CH = VEC ? 128 : 32;
+  constexpr int CH = VEC ? (sizeof(T) == 2 ? 256 : 128) : 32;
   const int dim = int(p.dim);
   const int dpad = (dim + CH - 1) / CH * CH;
   float* sq = reinterpret_cast<float*>(smem_raw);
@@ -288,7 +301,7 @@ __global__ void __launch_bounds__(kRefineListThreads) refine_lists_kernel(const 
     const int64_t gid = int64_t(key_id(a));
     int64_t row = gid - p.idmap.base;
     if (p.idmap.chunk > 0) row = ((row / p.idmap.chunk) / p.idmap.world) * p.idmap.chunk + row % p.idmap.chunk;
-    const float s = exact_score<VEC>(p.bank + row * p.bank_ld, sq, dim, p.flags, lane);
+    const float s = exact_score<T, VEC>(static_cast<const T*>(p.bank) + row * p.bank_ld, sq, dim, p.flags, lane);
     if (lane == 0) ex[c] = pack_key(s, uint32_t(gid));
   }
   __syncthreads();
@@ -330,13 +343,24 @@ __global__ void __launch_bounds__(kRefineListThreads) refine_lists_kernel(const 
 
 }  // namespace
 
+// scan_stream's rule for the vectorised column order (4 fp32 / 8 bf16 columns per lane and chunk)
+static bool refine_vectorised(const RefineParams& p) {
+  const int nv = p.bank_dtype == DEVQA_F32 ? 4 : 8;
+  return p.dim % nv == 0 && p.bank_ld % nv == 0 && reinterpret_cast<uintptr_t>(p.bank) % 16 == 0;
+}
+static size_t refine_query_smem(const RefineParams& p, bool vec) {
+  const int ch = vec ? (p.bank_dtype == DEVQA_F32 ? 128 : 256) : 32;
+  return size_t((p.dim + ch - 1) / ch * ch) * 4;
+}
+
 int refine_lists_launch(const RefineParams& p, cudaStream_t stream) {
   if (p.n_queries == 0) return DEVQA_OK;
   DEVQA_REQUIRE(p.top_k <= kMaxKp && p.n_lists <= 160 && p.n_lists >= p.top_k, "refine: unsupported list geometry");
-  const bool vec = p.dim % 4 == 0 && p.bank_ld % 4 == 0 && reinterpret_cast<uintptr_t>(p.bank) % 16 == 0;   // scan_stream's rule
-  const int ch = vec ? 128 : 32;
-  const size_t smem = size_t((p.dim + ch - 1) / ch * ch) * 4;
-  auto kern = vec ? refine_lists_kernel<true> : refine_lists_kernel<false>;
+  const bool vec = refine_vectorised(p);
+  const size_t smem = refine_query_smem(p, vec);
+  void (*kern)(RefineParams) = p.bank_dtype == DEVQA_F32
+      ? (vec ? refine_lists_kernel<float, true> : refine_lists_kernel<float, false>)
+      : (vec ? refine_lists_kernel<__nv_bfloat16, true> : refine_lists_kernel<__nv_bfloat16, false>);
   if (smem > 40 * 1024) DEVQA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
   kern<<<unsigned(p.n_queries), kRefineListThreads, smem, stream>>>(p);
   DEVQA_CUDA(cudaGetLastError());
@@ -347,10 +371,11 @@ int refine_lists_launch(const RefineParams& p, cudaStream_t stream) {
 int refine_launch(const RefineParams& p, cudaStream_t stream) {
   if (p.n_queries == 0) return DEVQA_OK;
   DEVQA_REQUIRE(p.kp <= kMaxKp && p.top_k <= p.kp, "refine: candidate list of %d for top_k %d unsupported", p.kp, p.top_k);
-  const bool vec = p.dim % 4 == 0 && p.bank_ld % 4 == 0 && reinterpret_cast<uintptr_t>(p.bank) % 16 == 0;   // scan_stream's rule
-  const int ch = vec ? 128 : 32;
-  const size_t smem = size_t((p.dim + ch - 1) / ch * ch) * 4;
-  auto kern = vec ? refine_kernel<true> : refine_kernel<false>;
+  const bool vec = refine_vectorised(p);
+  const size_t smem = refine_query_smem(p, vec);
+  void (*kern)(RefineParams) = p.bank_dtype == DEVQA_F32
+      ? (vec ? refine_kernel<float, true> : refine_kernel<float, false>)
+      : (vec ? refine_kernel<__nv_bfloat16, true> : refine_kernel<__nv_bfloat16, false>);
   if (smem > 48 * 1024) DEVQA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
   kern<<<unsigned(p.n_queries), kRefineThreads, smem, stream>>>(p);
   DEVQA_CUDA(cudaGetLastError());

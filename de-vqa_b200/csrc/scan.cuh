@@ -46,13 +46,16 @@ int scan_stream_launch(const ScanParams& p, int bank_dtype, bool vectorised, int
 //   kTcBf16x3 (= DEVQA_BF16) bf16 bank, exact w.r.t. the rounded bank
 //   kTcTf32x1                fp32 bank, approximate scores with a proven error bound: a FILTER whose top-K'
 //                            lists are rescored exactly by refine.cu
-constexpr int kTcTf32x3 = 0, kTcBf16x3 = 1, kTcTf32x1 = 2;
+constexpr int kTcTf32x3 = 0, kTcBf16x3 = 1, kTcTf32x1 = 2, kTcBf16x1 = 3;   // kTcBf16x1: the filter on a bf16 bank
 // |approximate - exact| <= tc_filter_relerr(dim) * ||row|| * ||query||  for the kTcTf32x1 scores:
 //   2^-10 (bank words truncated to TF32) + 2^-11 (queries rounded to TF32) + their product, by Cauchy-Schwarz;
 //   dim * 2^-24 for the accumulation: the tensor core adds dim/8 times into an fp32 accumulator with truncation
 //   (<= 2 ulp of the running magnitude each: dim * 2^-25) and the fp32 re-scoring it is compared with rounds
 //   (dim/32 + 5) times to nearest.  tests/test_gpu_filter.py measures the actual error against this bound.
-__host__ __device__ inline float tc_filter_relerr(int64_t dim) { return 1.5f * 0.0009765625f + float(dim) * 5.9604644775390625e-08f; }
+// bf16 banks (kTcBf16x1): the bank is exact, queries are rounded to bf16 (<= 2^-9): 1.01 * 2^-9 + dim * 2^-24.
+__host__ __device__ inline float tc_filter_relerr(int64_t dim, bool bf16_bank = false) {
+  return (bf16_bank ? 1.01f * 0.001953125f : 1.5f * 0.0009765625f) + float(dim) * 5.9604644775390625e-08f;
+}
 bool scan_tc_supported(int bank_dtype, const void* bank, int64_t dim, int64_t bank_ld, int top_k);
 int scan_tc_plan(int mode, int n_queries, int64_t dim, int kcap, bool cached_norms, int64_t n_tiles, int sm_count,
                  unsigned flags, int* qp_out, int* stages_out, bool* pair_out);
@@ -73,7 +76,7 @@ void scan_tc_set_trace(long long* buf);
 
 // refine.cu: exact fp32 re-scoring of the filter's candidates (bit-identical to scan_stream.cu's arithmetic).
 struct RefineParams {
-  const float* bank; int64_t n_rows, dim, bank_ld;
+  const void* bank; int bank_dtype; int64_t n_rows, dim, bank_ld;   // fp32 or bf16 rows (DEVQA_F32 / DEVQA_BF16)
   const float* queries; int64_t query_ld; int32_t n_queries;
   const float* qinv;          // [n_queries] query scale applied by the normalisation (1 when off)
   const uint64_t* akeys;      // [n_queries, kp] merged candidates: keys on the upper bound u, sorted descending, 0 = empty

@@ -68,7 +68,7 @@ constexpr int kTcThreads = 384;
 //            nothing was lost (every row a full list pushed out has u <= that list's last entry).  One mma group
 //            (N = queries), no split warps, no lo tile: 48 KB instead of 88 KB of shared-memory traffic per
 //            k-block at 64 queries, and 128 queries per pass fit.
-enum : int { kTf32x3 = 0, kBf16x3 = 1, kTf32x1 = 2 };
+enum : int { kTf32x3 = 0, kBf16x3 = 1, kTf32x1 = 2, kBf16x1 = 3 };   // kBf16x1: the filter on a bf16 bank (queries rounded to bf16)
 constexpr int kTileRows = 128;
 constexpr int kBlockK = 32;                          // fp32 columns per k-block = one 128-byte swizzle row
 constexpr int kATileBytes = kTileRows * kBlockK * 4; // 16 KB
@@ -252,6 +252,14 @@ __device__ __forceinline__ void mma_tf32_pair(uint32_t tmem_d, uint64_t adesc, u
       "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t"
       "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
+__device__ __forceinline__ void mma_bf16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
 // completion of all prior MMAs of the pair -> one arrival on the barrier at this offset in BOTH CTAs
 __device__ __forceinline__ void mma_commit_pair(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
@@ -260,6 +268,10 @@ __device__ __forceinline__ void mma_commit_pair(uint64_t* bar) {
 // instruction descriptor of the pair MMA: M = 256 (128 rows per CTA)
 __host__ __device__ constexpr uint32_t idesc_tf32_pair(int n) {
   return (1u << 4) | (2u << 7) | (2u << 10) | (uint32_t(n >> 3) << 17) | (uint32_t(256 >> 4) << 24);
+}
+
+__host__ __device__ constexpr uint32_t idesc_bf16_pair(int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(n >> 3) << 17) | (uint32_t(256 >> 4) << 24);
 }
 
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (rows of 128 bytes, 8-row atoms of 1024 bytes):
@@ -732,15 +744,16 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 scan_tc_kernel(const __grid_constant__ CUtensorMap bank_map, const __grid_constant__ TcParams p) {
   extern __shared__ unsigned char smem_unaligned[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_unaligned) + 1023) & ~uintptr_t(1023));
-  constexpr bool BF = MODE == kBf16x3;
-  constexpr bool FILT = MODE == kTf32x1;
+  constexpr bool BF = MODE == kBf16x3;                   // three bf16 query planes, exact
+  constexpr bool BFD = MODE == kBf16x3 || MODE == kBf16x1;   // the bank (and the MMA) is bf16
+  constexpr bool FILT = MODE == kTf32x1 || MODE == kBf16x1;
   constexpr bool TWO_ISSUERS = MODE == kTf32x3;
   static_assert(!(FILT && MULTI), "the filter variant accumulates the whole K chain in the tensor core");
   // scan-and-queue epilogue + threshold exchange (filt_epilogue / filt_service): every variant whose tile is one
   // accumulation unit; MULTI (K-sets summed in registers) keeps the score-tile epilogue below
   constexpr bool SCANEPI = !MULTI;
   constexpr int kParts = BF ? 3 : (FILT ? 1 : 2);        // row groups of the query operand per k-block
-  constexpr int kElemsK = BF ? 64 : 32;                  // bank columns per k-block (always 128 bytes)
+  constexpr int kElemsK = BFD ? 64 : 32;                 // bank columns per k-block (always 128 bytes)
   static_assert(!PAIR || (FILT && QP >= 64), "CTA pairs: filter variant, 64+ queries per pass");
   const SmemLayout L = tc_layout(p.stages, p.qp, p.kcap, kParts, PAIR);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -873,7 +886,8 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap bank_map, const __grid_consta
     if (PAIR && !leader) {
       // pair, peer CTA: no MMA issue (warps 4-7 forward "stage s is loaded" to the leader, below)
     } else if (lane == 0) {
-      const uint32_t idesc_cat = BF ? idesc_bf16(3 * QP) : (PAIR ? idesc_tf32_pair(QP) : idesc_tf32(kParts * QP));
+      const uint32_t idesc_cat = BFD ? (PAIR ? idesc_bf16_pair(QP) : idesc_bf16(kParts * QP))
+                                     : (PAIR ? idesc_tf32_pair(QP) : idesc_tf32(kParts * QP));
       const uint32_t a_lo0 = (smem_u32(smem + L.a_raw) & 0x3ffffu) >> 4, b_lo0 = (smem_u32(smem + L.bq) & 0x3ffffu) >> 4;
       RingPos r;
       uint32_t unit = 0;
@@ -897,7 +911,8 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap bank_map, const __grid_consta
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk) {              // four 32-byte K slices of the 128-byte rows
               if (p.flags & kDbgNoMma1) break;            // (bisection: stream the tiles only)
-              if constexpr (BF) mma_bf16(d, desc_from_lo(a_lo + kk * 2), desc_from_lo(b_lo + kk * 2), idesc_cat, first | uint32_t(kk));
+              if constexpr (BFD && PAIR) mma_bf16_pair(d, desc_from_lo(a_lo + kk * 2), desc_from_lo(b_lo + kk * 2), idesc_cat, first | uint32_t(kk));
+              else if constexpr (BFD) mma_bf16(d, desc_from_lo(a_lo + kk * 2), desc_from_lo(b_lo + kk * 2), idesc_cat, first | uint32_t(kk));
               else if constexpr (PAIR) mma_tf32_pair(d, desc_from_lo(a_lo + kk * 2), desc_from_lo(b_lo + kk * 2), idesc_cat, first | uint32_t(kk));
               else mma_tf32(d, desc_from_lo(a_lo + kk * 2), desc_from_lo(b_lo + kk * 2), idesc_cat, first | uint32_t(kk));
             }
@@ -992,7 +1007,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap bank_map, const __grid_consta
             }
           }
         }
-        if constexpr (FILT) {
+        if constexpr (FILT && !BFD) {                     // (the bf16 filter runs on banks with cached norms only)
 #pragma unroll
           for (int c = 0; c < 8; ++c) {                   // order is irrelevant for a sum of squares
             const float4 v = lds128(src + (uint32_t(c) << 4));
@@ -1264,6 +1279,49 @@ __global__ void __launch_bounds__(256) prep_queries_filt_kernel(const float* __r
   }
 }
 
+// Filter on a bf16 bank (kBf16x1): one bf16 plane (rounded to nearest), [n_kblocks][qp rows][64 cols] per pass.
+__global__ void __launch_bounds__(256) prep_queries_filt_bf16_kernel(const float* __restrict__ q, int64_t q_ld, int n_queries, int dim,
+                                                                     int qp, int n_kblocks, int q_pad, unsigned flags,
+                                                                     __nv_bfloat16* __restrict__ qcat, uint32_t* __restrict__ gthr,
+                                                                     float* __restrict__ qinv, float* __restrict__ qerr,
+                                                                     uint32_t* __restrict__ seed_u, uint32_t* __restrict__ gmax,
+                                                                     int gmax_stride) {
+  if (blockIdx.x == 0)
+    for (int i = threadIdx.x; i < q_pad; i += blockDim.x) { gthr[i] = 0u; seed_u[i] = 0u; }
+  if (gmax)
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < q_pad * gmax_stride; i += gridDim.x * blockDim.x) gmax[i] = 0u;
+  const int lane = threadIdx.x & 31;
+  const int warps = gridDim.x * (blockDim.x >> 5);
+  const int d_pad = n_kblocks * 64;
+  for (int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < q_pad; r += warps) {
+    float inv = 0.f;
+    const float* src = q + size_t(r < n_queries ? r : 0) * q_ld;
+    if (r < n_queries) {
+      inv = 1.f;
+      if (flags & DEVQA_NORMALIZE_QUERY) {
+        float ss = 0.f;
+        for (int c = lane; c < dim; c += 32) { const float x = src[c]; ss = fmaf(x, x, ss); }
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) ss += __shfl_xor_sync(kFull, ss, off);
+        const float nrm = sqrtf(ss);
+        inv = 1.0f / ((flags & DEVQA_NOEPS) ? nrm : fmaxf(nrm, kNormEps));
+      }
+    }
+    const int pass = r / qp, rp = r % qp;
+    __nv_bfloat16* base = qcat + size_t(pass) * n_kblocks * (qp * 64);
+    float nn = 0.f;
+    for (int c = lane; c < d_pad; c += 32) {
+      const float x = (r < n_queries && c < dim) ? src[c] * inv : 0.f;
+      nn = fmaf(x, x, nn);
+      const int kb = c / 64, w = c % 64;
+      base[size_t(kb) * (qp * 64) + rp * 64 + (((w >> 3) ^ (rp & 7)) << 3) + (w & 7)] = __float2bfloat16_rn(x);
+    }
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) nn += __shfl_xor_sync(kFull, nn, off);
+    if (lane == 0 && r < n_queries) { qinv[r] = inv; qerr[r] = tc_filter_relerr(dim, true) * sqrtf(nn); }
+  }
+}
+
 // bf16-bank variant: three bf16 planes hi + mid + lo (24 mantissa bits together), k-blocks of 64 columns.
 // Output per pass: [n_kblocks][3*qp rows][64 bf16], rows 0..qp-1 = hi, qp.. = mid, 2qp.. = lo, 128B-swizzled.
 __global__ void __launch_bounds__(256) prep_queries_bf16_kernel(const float* __restrict__ q, int64_t q_ld, int n_queries, int dim,
@@ -1350,8 +1408,8 @@ bool scan_tc_supported(int bank_dtype, const void* bank, int64_t dim, int64_t ba
 }
 
 // bank columns per 128-byte k-block row, and the padded k-block count
-static int elems_per_kblock(int mode) { return mode == kTcBf16x3 ? 64 : 32; }
-static int mode_parts(int mode) { return mode == kTcBf16x3 ? 3 : (mode == kTcTf32x1 ? 1 : 2); }
+static int elems_per_kblock(int mode) { return (mode == kTcBf16x3 || mode == kTcBf16x1) ? 64 : 32; }
+static int mode_parts(int mode) { return mode == kTcBf16x3 ? 3 : ((mode == kTcTf32x1 || mode == kTcBf16x1) ? 1 : 2); }
 int scan_tc_kblocks(int mode, int64_t dim) { return int((dim + elems_per_kblock(mode) - 1) / elems_per_kblock(mode)); }
 // bytes of the prepared query operand for q_pad queries
 size_t scan_tc_qcat_bytes(int mode, int64_t dim, int q_pad) {
@@ -1362,7 +1420,7 @@ size_t scan_tc_qcat_bytes(int mode, int64_t dim, int q_pad) {
 int scan_tc_plan(int mode, int n_queries, int64_t dim, int kcap, bool cached_norms, int64_t n_tiles, int sm_count,
                  unsigned flags, int* qp_out, int* stages_out, bool* pair_out) {
   *pair_out = false;
-  const bool bf = mode == kTcBf16x3, filt = mode == kTcTf32x1;
+  const bool filt = mode == kTcTf32x1 || mode == kTcBf16x1;
   // more than one K-set (1024 fp32 / 2048 bf16 columns) sums K-sets in the epilogue's registers (MULTI):
   // 32 queries per pass at most.  The filter keeps the whole K chain in the tensor core (its error bound
   // covers the drift) and, with cached row norms (no CUDA-core pass over the tile), takes 128 queries per pass.
@@ -1374,7 +1432,7 @@ int scan_tc_plan(int mode, int n_queries, int64_t dim, int kcap, bool cached_nor
     while (qp > 32 && n_tiles * ((n_queries + qp - 1) / qp) < sm_count) qp >>= 1;
   for (; qp >= 16; qp >>= 1) {
     // 256 queries per pass on a long scan: CTA pairs (each CTA holds half of the query operand)
-    const bool pair = filt && cached_norms && (qp == 256 || (qp >= 64 && (flags & kDbgPairAll))) &&
+    const bool pair = filt && cached_norms && (qp == 256 || (qp >= 64 && mode == kTcTf32x1 && (flags & kDbgPairAll))) &&
                       n_tiles >= 2 * int64_t(sm_count) && sm_count % 2 == 0 && !(flags & kDbgNoPair);
     for (int stages = kMaxStages; stages >= 3; --stages) {
       // TMEM: 2 accumulator buffers of 3*qp (filter: qp) columns (+ one 32-column lo tile per stage for 3xTF32)
@@ -1401,6 +1459,9 @@ int scan_tc_prep_queries(int mode, const float* queries, int64_t query_ld, int n
   else if (mode == kTcBf16x3)
     prep_queries_bf16_kernel<<<grid, 256, 0, stream>>>(queries, query_ld, n_queries, int(dim), qp, n_kblocks, q_pad, flags,
                                                        static_cast<__nv_bfloat16*>(qcat), gthr, gmax, gmax_stride);
+  else if (mode == kTcBf16x1)
+    prep_queries_filt_bf16_kernel<<<grid, 256, 0, stream>>>(queries, query_ld, n_queries, int(dim), qp, n_kblocks, q_pad, flags,
+                                                            static_cast<__nv_bfloat16*>(qcat), gthr, qinv, qerr, seed_u, gmax, gmax_stride);
   else
     prep_queries_filt_kernel<<<grid, 256, 0, stream>>>(queries, query_ld, n_queries, int(dim), qp, n_kblocks, q_pad, flags,
                                                        static_cast<float*>(qcat), gthr, qinv, qerr, seed_u, gmax, gmax_stride);
@@ -1410,7 +1471,7 @@ int scan_tc_prep_queries(int mode, const float* queries, int64_t query_ld, int n
 }
 
 // Does this mode/dim run the scan-and-queue epilogue with the cross-CTA threshold exchange (needs gmax, no seeding)?
-bool scan_tc_exchanges_thresholds(int mode, int64_t dim) { return mode == kTcTf32x1 || scan_tc_kblocks(mode, dim) <= kSetKBlocks; }
+bool scan_tc_exchanges_thresholds(int mode, int64_t dim) { return mode == kTcTf32x1 || mode == kTcBf16x1 || scan_tc_kblocks(mode, dim) <= kSetKBlocks; }
 
 static long long* g_tc_trace = nullptr;
 void scan_tc_set_trace(long long* buf) { g_tc_trace = buf; }
@@ -1418,7 +1479,8 @@ void scan_tc_set_trace(long long* buf) { g_tc_trace = buf; }
 int scan_tc_launch(const ScanParams& sp, int mode, const void* qcat, uint32_t* gthr, int qp, int stages, int passes,
                    int ctas_per_pass, bool pair, cudaStream_t stream) {
   const int grid = passes * ctas_per_pass;
-  const bool bf = mode == kTcBf16x3;
+  const bool bf = mode == kTcBf16x3 || mode == kTcBf16x1;
+  const bool filt = mode == kTcTf32x1 || mode == kTcBf16x1;
   const int parts = mode_parts(mode);
   const int n_kblocks = scan_tc_kblocks(mode, sp.dim);
   CUtensorMap bank_map;
@@ -1436,7 +1498,7 @@ int scan_tc_launch(const ScanParams& sp, int mode, const void* qcat, uint32_t* g
   p.qcat = static_cast<const float*>(qcat) + size_t(sp.q0 / qp) * size_t(n_kblocks) * parts * qp * 32;
   p.trace = g_tc_trace;
   const size_t smem = tc_layout(stages, qp, sp.kcap, parts, pair).total + 1024;
-  const bool multi = mode != kTcTf32x1 && p.n_kblocks > kSetKBlocks;
+  const bool multi = !filt && p.n_kblocks > kSetKBlocks;
   void (*kern)(CUtensorMap, TcParams) = nullptr;
   if (mode == kTcTf32x3) {
     if (!multi) kern = qp == 64 ? scan_tc_kernel<64, false, kTf32x3> : qp == 32 ? scan_tc_kernel<32, false, kTf32x3> : scan_tc_kernel<16, false, kTf32x3>;
@@ -1444,19 +1506,27 @@ int scan_tc_launch(const ScanParams& sp, int mode, const void* qcat, uint32_t* g
   } else if (mode == kTcBf16x3) {
     if (!multi) kern = qp == 64 ? scan_tc_kernel<64, false, kBf16x3> : qp == 32 ? scan_tc_kernel<32, false, kBf16x3> : scan_tc_kernel<16, false, kBf16x3>;
     else kern = qp == 32 ? scan_tc_kernel<32, true, kBf16x3> : scan_tc_kernel<16, true, kBf16x3>;
+  } else if (mode == kTcBf16x1) {
+    kern = qp == 256 ? scan_tc_kernel<256, false, kBf16x1> : qp == 128 ? scan_tc_kernel<128, false, kBf16x1> : qp == 64 ? scan_tc_kernel<64, false, kBf16x1>
+         : qp == 32 ? scan_tc_kernel<32, false, kBf16x1> : scan_tc_kernel<16, false, kBf16x1>;
   } else {
     kern = qp == 256 ? scan_tc_kernel<256, false, kTf32x1> : qp == 128 ? scan_tc_kernel<128, false, kTf32x1> : qp == 64 ? scan_tc_kernel<64, false, kTf32x1>
          : qp == 32 ? scan_tc_kernel<32, false, kTf32x1> : scan_tc_kernel<16, false, kTf32x1>;
   }
-  const bool qp_ok = qp == 16 || qp == 32 || (qp == 64 && !multi) || ((qp == 128 || qp == 256) && mode == kTcTf32x1);
+  const bool qp_ok = qp == 16 || qp == 32 || (qp == 64 && !multi) || ((qp == 128 || qp == 256) && filt);
   if (!qp_ok) {
     set_error("tcgen05 scan: unsupported queries-per-pass %d", qp);
     return DEVQA_E_INVALID;
   }
   if (pair) {
-    DEVQA_REQUIRE(mode == kTcTf32x1 && qp >= 64 && passes == 1 && grid % 2 == 0, "tcgen05 scan: bad CTA-pair launch");
-    kern = qp == 256 ? scan_tc_kernel<256, false, kTf32x1, true> : qp == 128 ? scan_tc_kernel<128, false, kTf32x1, true>
-                                                                              : scan_tc_kernel<64, false, kTf32x1, true>;
+    DEVQA_REQUIRE(filt && qp >= 64 && passes == 1 && grid % 2 == 0, "tcgen05 scan: bad CTA-pair launch");
+    if (mode == kTcBf16x1) {
+      DEVQA_REQUIRE(qp == 256, "tcgen05 scan: bf16 CTA pairs run 256 queries per pass");
+      kern = scan_tc_kernel<256, false, kBf16x1, true>;
+    } else {
+      kern = qp == 256 ? scan_tc_kernel<256, false, kTf32x1, true> : qp == 128 ? scan_tc_kernel<128, false, kTf32x1, true>
+                                                                                : scan_tc_kernel<64, false, kTf32x1, true>;
+    }
   }
   DEVQA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
   if (pair) {

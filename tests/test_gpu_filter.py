@@ -286,3 +286,24 @@ def test_filter_dims_not_multiple_of_four(n, d, nq, k):
     ss.compare_topk(a[0].cpu().numpy()[:, :kk], a[1].cpu().numpy()[:, :kk], truth, k, gap=GAP, rtol=RTOL, atol=ATOL)
     assert torch.equal(a[1], b[1]) and torch.equal(a[0], b[0])
     fb.close()
+
+
+@pytest.mark.parametrize("n,d,nq,k,nb,nqm", [(5000, 768, 64, 32, "eps", "eps"), (40000, 256, 300, 16, "eps", "eps"),
+                                               (3000, 384, 20, 5, None, None), (20000, 100, 70, 64, "noeps", "noeps"),
+                                               (60000, 512, 130, 32, "eps", None), (129, 72, 9, 8, "eps", "eps")])
+def test_bf16_bank_filter_matches_the_stream_kernel_bit_for_bit(n, d, nq, k, nb, nqm):
+    """bf16 banks take the same filter (queries rounded to bf16 on the tensor core, exact re-scoring against the
+    bf16 rows in the stream kernel's arithmetic): identical results, exact w.r.t. the bf16-rounded bank."""
+    bank, q = _randn(n, d, 11 * n + d, unit=False), _randn(nq, d, 13 * nq + k, unit=False)
+    fb = FactBank.from_embeddings(bank, dtype="bf16")
+    _fallbacks()
+    a = fb.search(q.cuda(), k, normalize_bank=nb, normalize_query=nqm, flags=FILTER)
+    nfb = _fallbacks()
+    b = fb.search(q.cuda(), k, normalize_bank=nb, normalize_query=nqm, flags=L.FORCE_STREAM)
+    rounded = bank.to(torch.bfloat16).float()
+    truth = ss.truth_scores_fp64(q, rounded, normalize_bank=bool(nb), normalize_query=bool(nqm))
+    kk = min(k, n)
+    ss.compare_topk(a[0].cpu().numpy()[:, :kk], a[1].cpu().numpy()[:, :kk], truth, k, gap=GAP, rtol=RTOL, atol=ATOL)
+    assert torch.equal(a[1], b[1]) and torch.equal(a[0], b[0])
+    assert nfb <= max(1, nq // 8)
+    fb.close()
