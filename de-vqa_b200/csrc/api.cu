@@ -279,6 +279,18 @@ static int run_search(Scratch* s, const SearchArgs& a, uint64_t* out_keys, float
   // from 4 queries per pass on: 4.87 ms against 4.40 ms sustained on 10M rows).
   const bool tc_ok = scan_tc_supported(a.dtype, a.bank, a.dim, a.bank_ld, a.top_k) && a.n_rows > 0;
   bool use_tc = tc_ok && a.n_queries > 2;
+  // Where the tensor path is the filter (see below), it returns bit for bit what the stream kernel returns, so
+  // the choice between the two may also look at the bank size without breaking "G shards == one bank":
+  const bool filter_path = !(a.flags & DEVQA_FORCE_TF32X3) && a.top_k <= 64 && a.dim <= 16384 &&
+                           (a.dtype == DEVQA_F32 ? ((a.flags & DEVQA_NORMALIZE_BANK) || (a.row_sumsq && a.max_sumsq))
+                                                 : (a.row_sumsq != nullptr && a.max_sumsq != nullptr));
+  if (tc_ok && filter_path) {
+    const int64_t tiles = (a.n_rows + 127) / 128;
+    // tiny banks (fewer tiles than SMs), up to 8 queries: ONE stream launch (~15 us) beats the seven-launch pipeline
+    if (a.n_queries <= 8 && tiles < s->sm_count) use_tc = false;
+    // large bf16 banks: the bf16 stream kernel manages 5.1 TB/s, the tensor path 6.9 -- also for one or two queries
+    if (a.dtype == DEVQA_BF16 && a.n_queries <= 2 && tiles >= 8 * int64_t(s->sm_count)) use_tc = true;
+  }
   if (a.flags & DEVQA_FORCE_STREAM) use_tc = false;
   if (a.flags & DEVQA_FORCE_TENSOR) {
     if (!tc_ok) {
@@ -302,9 +314,7 @@ static int run_search(Scratch* s, const SearchArgs& a, uint64_t* out_keys, float
     // (Nothing here may depend on the number of rows: every shard of a sharded bank has to take the same path, or
     // G-GPU results would differ from 1-GPU results in the last bits of the scores.)
     // bf16 banks: the same filter with queries rounded to bf16 (library-owned banks: cached row norms), bf16x3 as fallback.
-    const bool filt = !(a.flags & DEVQA_FORCE_TF32X3) && a.top_k <= 64 && a.dim <= 16384 &&
-                      (a.dtype == DEVQA_F32 ? ((a.flags & DEVQA_NORMALIZE_BANK) || (a.row_sumsq && a.max_sumsq))
-                                            : (a.row_sumsq != nullptr && a.max_sumsq != nullptr));
+    const bool filt = filter_path;
     const int filt_mode = a.dtype == DEVQA_F32 ? kTcTf32x1 : kTcBf16x1;
     const int exact_mode = a.dtype == DEVQA_F32 ? kTcTf32x3 : kTcBf16x3;
     if (s->profiling) s->prof_searches++;
