@@ -14,6 +14,7 @@ MAX_TOPK = 1024
 F32, BF16 = 0, 1
 NORMALIZE_BANK, NORMALIZE_QUERY, NOEPS = 1 << 0, 1 << 1, 1 << 2
 FORCE_STREAM, FORCE_TENSOR, FORCE_TF32X3, FORCE_FILTER = 1 << 8, 1 << 9, 1 << 10, 1 << 11
+DEBUG_TIGHT_BOUND = 1 << 12
 DEBUG_FILTER_ONLY = 1 << 22
 
 _p, _i, _i64, _u, _u64 = C.c_void_p, C.c_int, C.c_int64, C.c_uint, C.c_uint64
@@ -25,6 +26,8 @@ SIGNATURES = {
     "devqa_launch_count": (_i64, []),
     "devqa_debug_tc_trace": (_i, [_p]),
     "devqa_filter_fallbacks": (_i, [_i, C.POINTER(_i64)]),
+    "devqa_filter_bound_violations": (_i, [_i, C.POINTER(_i64)]),
+    "devqa_filter_relerr": (C.c_double, [_i64, _i]),
     "devqa_profile_enable": (_i, [_i, _i]),
     "devqa_profile_collect": (_i, [_i, C.POINTER(C.c_double), C.POINTER(_i64), C.POINTER(_i64)]),
     "devqa_search_raw": (_i, [_p, _i, _i64, _i64, _i64, _p, _i64, _i64, _i, _u, _i64, _p, _p, _p]),
@@ -45,6 +48,10 @@ SIGNATURES = {
     "devqa_bank_search": (_i, [_p, _p, _i64, _i64, _i, _u, _p, _p, _p]),
     "devqa_bank_search_host": (_i, [_p, _p, _i64, _i64, _i, _u, _p, _p, _p]),
     "devqa_bank_search_packed": (_i, [_p, _p, _i64, _i64, _i, _u, _p, _p]),
+    "devqa_bank_select_above": (_i, [_p, _p, _i64, _i64, _p, C.c_float, _u, _p, _p, _p, _i64, _p, _p]),
+    "devqa_scope_gate": (_i, [_p, _i64, _i64, _i64, _p, _i64, _i64, _p, _i64, _i, _u, _p, C.c_float, _p, _p, _p]),
+    "devqa_bank_hice_probe": (_i, [_p, _p, _p, _p, _i64, _i64, _p, _i64, _i64, _p, _i64, _i, C.c_float, _i, _u,
+                                   _p, _p, _p, _p, _p, _p]),
     "devqa_topk_merge": (_i, [_p, _i, _i64, _i, _p, _p, _p]),
     "devqa_dist_unique_id": (_i, [_p]),
     "devqa_dist_init": (_i, [C.POINTER(_p), _p, _i, _i, _i]),

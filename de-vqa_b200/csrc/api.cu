@@ -38,10 +38,14 @@ struct Scratch {
   uint64_t* keys = nullptr;   size_t keys_bytes = 0;       // packed local top-k (dist)
   uint64_t* gathered = nullptr; size_t gathered_bytes = 0; // all-gather target (dist)
   void* tiny = nullptr;       size_t tiny_bytes = 0;       // padded copy of banks shorter than one row group
+  uint8_t* selmask = nullptr; size_t selmask_bytes = 0;    // threshold-select: [Q, N] mask when the caller wants none
   float* qsplit = nullptr;    size_t qsplit_bytes = 0;     // TF32 hi / lo query planes of the tcgen05 scan
   uint64_t* akeys = nullptr;  size_t akeys_bytes = 0;      // filter scan: merged approximate top-K' lists + per-query side arrays
   uint32_t* fallbacks = nullptr;                           // device counter: queries the exact fallback had to redo
   uint32_t* ticket = nullptr;                              // device word: arrival counter of the stream kernel's fused merge
+  uint32_t* violations = nullptr;                          // device counter: re-scored candidates outside [u - 2E, u] (refine.cu canary)
+  uint32_t* gate_ticket = nullptr;                         // device word: arrival counter of the scope-gate kernel
+  float* gate = nullptr;      size_t gate_bytes = 0;       // scope gate: per-CTA partial logits + memory-search results
   cudaStream_t last_stream = nullptr;
   cudaEvent_t done = nullptr;
   // optional per-kernel timing (devqa_profile_*): event pairs around the scan passes of each search
@@ -60,8 +64,21 @@ struct DeviceGuardLite {
   ~DeviceGuardLite() { if (prev >= 0) cudaSetDevice(prev); }
 };
 
+static thread_local cudaStream_t tl_stream = nullptr;   // the stream of the entry point this thread is inside (scratch_enter)
+
 static int grow(void** p, size_t* have, size_t want, bool pinned) {
   if (*have >= want) return DEVQA_OK;
+  {
+    // (re)allocation synchronises the device, which is illegal while the call's stream is being captured: say so
+    // instead of failing inside cudaDeviceSynchronize and invalidating the capture.  A search is capturable once an
+    // identical (or larger) call has run eagerly and sized the scratch -- the warm-up graph capture needs anyway.
+    cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(tl_stream, &st);
+    if (st != cudaStreamCaptureStatusNone) {
+      set_error("scratch of %zu bytes must grow during stream capture: run the same call once eagerly before capturing", want);
+      return DEVQA_E_STATE;
+    }
+  }
   if (*p) {
     DEVQA_CUDA(cudaDeviceSynchronize());
     if (pinned) cudaFreeHost(*p); else cudaFree(*p);
@@ -77,9 +94,12 @@ static int grow(void** p, size_t* have, size_t want, bool pinned) {
   return DEVQA_OK;
 }
 
+static std::mutex g_scratch_init_mu;
+
 static int scratch_for(int device, Scratch** out) {
   DEVQA_REQUIRE(device >= 0 && device < 64, "device %d out of range", device);
   Scratch* s = &g_scratch[device];
+  std::lock_guard<std::mutex> init_lock(g_scratch_init_mu);   // lazy init from any host thread
   if (s->sm_count == 0) {
     int n = 0;
     DEVQA_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, device));
@@ -89,12 +109,16 @@ static int scratch_for(int device, Scratch** out) {
       set_error("libdevqa is built for sm_100a only; device %d has compute capability %d.x", device, major);
       return DEVQA_E_UNSUPPORTED;
     }
-    DEVQA_CUDA(cudaEventCreateWithFlags(&s->done, cudaEventDisableTiming));
     {
+      // everything below belongs to `device`, whichever device the calling thread has current (an event created on
+      // another device cannot be recorded on this device's streams)
       DeviceGuardLite guard(device);
-      DEVQA_CUDA(cudaMalloc(&s->fallbacks, 8));
-      DEVQA_CUDA(cudaMemset(s->fallbacks, 0, 8));
+      DEVQA_CUDA(cudaEventCreateWithFlags(&s->done, cudaEventDisableTiming));
+      DEVQA_CUDA(cudaMalloc(&s->fallbacks, 16));
+      DEVQA_CUDA(cudaMemset(s->fallbacks, 0, 16));
       s->ticket = s->fallbacks + 1;
+      s->violations = s->fallbacks + 2;
+      s->gate_ticket = s->fallbacks + 3;
     }
     s->sm_count = n;
   }
@@ -104,6 +128,7 @@ static int scratch_for(int device, Scratch** out) {
 
 // order this call behind the previous user of the scratch when the stream changed
 static int scratch_enter(Scratch* s, cudaStream_t stream) {
+  tl_stream = stream;
   if (s->last_stream != stream && s->done) {
     // (a capturing stream must not wait on an event from outside its capture; whoever captures a search has
     // synchronised with earlier work already, as CUDA graph capture requires)
@@ -364,7 +389,7 @@ static int run_search(Scratch* s, const SearchArgs& a, uint64_t* out_keys, float
       rp.queries = ac.queries; rp.query_ld = a.query_ld; rp.n_queries = int32_t(ac.n_queries);
       rp.qinv = side.qinv; rp.akeys = side.akeys; rp.lostu = side.lostu; rp.n_lists = side.n_lists;
       rp.kp = kp; rp.top_k = a.top_k; rp.flags = a.flags; rp.idmap = a.idmap;
-      rp.need = side.need; rp.fallbacks = s->fallbacks; rp.out_keys = ok; rp.out_scores = os; rp.out_ids = oi;
+      rp.need = side.need; rp.fallbacks = s->fallbacks; rp.violations = s->violations; rp.out_keys = ok; rp.out_scores = os; rp.out_ids = oi;
       rp.cand = s->cand; rp.cand_kcap = side.kcap; rp.gmax = side.gmax; rp.gmax_stride = kGmaxStride;
       rp.qerr = side.qerr; rp.bank_max_sumsq = a.max_sumsq;
       if ((rc = side.merge ? refine_launch(rp, stream) : refine_lists_launch(rp, stream))) return rc;
@@ -575,6 +600,23 @@ int devqa_filter_fallbacks(int device, int64_t* count) {
   *count = v;
   return DEVQA_OK;
 }
+
+int devqa_filter_bound_violations(int device, int64_t* count) {
+  DEVQA_REQUIRE(count != nullptr, "count is null");
+  Scratch* s = nullptr;
+  int rc = scratch_for(device, &s);
+  if (rc) return rc;
+  DEVQA_ON_DEVICE(device);
+  std::lock_guard<std::mutex> lock(s->mu);
+  uint32_t v = 0;
+  DEVQA_CUDA(cudaDeviceSynchronize());
+  DEVQA_CUDA(cudaMemcpy(&v, s->violations, 4, cudaMemcpyDeviceToHost));
+  DEVQA_CUDA(cudaMemset(s->violations, 0, 4));
+  *count = v;
+  return DEVQA_OK;
+}
+
+double devqa_filter_relerr(int64_t dim, int bank_dtype) { return double(tc_filter_relerr(dim, bank_dtype == DEVQA_BF16)); }
 
 int devqa_profile_enable(int device, int enable) {
   Scratch* s = nullptr;
@@ -808,6 +850,156 @@ int devqa_bank_search_host(devqa_bank* b, const float* qh, int64_t nq, int64_t q
   a.queries = dq; a.query_ld = b->dim;
   if ((rc = run_search(s, a, nullptr, ds, di, stream))) return rc;
   if ((rc = unstage_results(s, nq, b->dim, top_k, scores_h, ids_h, stream))) return rc;
+  return scratch_leave(s, stream);
+}
+
+int devqa_bank_select_above(devqa_bank* b, const float* queries, int64_t nq, int64_t qld, const float* thresholds,
+                            float scale, unsigned flags, uint8_t* out_mask, int64_t* out_ids, float* out_scores,
+                            int64_t cap, int64_t* out_counts, void* stream_) {
+  DEVQA_REQUIRE(b != nullptr, "bank is null");
+  DEVQA_REQUIRE(nq >= 0 && cap >= 0 && qld >= b->dim, "bad select shape");
+  if (nq == 0) return DEVQA_OK;
+  DEVQA_REQUIRE(queries && thresholds && out_counts, "null queries / thresholds / out_counts");
+  DEVQA_REQUIRE(cap == 0 || (out_ids && out_scores), "out_ids / out_scores are null");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  DEVQA_ON_DEVICE(b->device);
+  Scratch* s = nullptr;
+  int rc = scratch_for(b->device, &s);
+  if (rc) return rc;
+  std::lock_guard<std::mutex> lock(s->mu);
+  if ((rc = scratch_enter(s, stream))) return rc;
+  const int64_t n = b->size;
+  uint8_t* mask = out_mask;
+  if (!mask && n > 0) {
+    if ((rc = grow(reinterpret_cast<void**>(&s->selmask), &s->selmask_bytes, size_t(nq) * size_t(n), false))) return rc;
+    mask = s->selmask;
+  }
+  if (n > 0) {
+    const int nv_vec = b->dtype == DEVQA_F32 ? 4 : 8;
+    const bool vectorised = (b->dim % nv_vec == 0) && (b->ld % nv_vec == 0) && (reinterpret_cast<uintptr_t>(b->data) % 16 == 0);
+    const int nv = vectorised ? nv_vec : 1;
+    int qt = nq > 1 ? 4 : 1;
+    if (scan_stream_smem_bytes(b->dim, nv, qt, 0) > 200 * 1024) qt = 1;
+    if (scan_stream_smem_bytes(b->dim, nv, qt, 0) > 220 * 1024) {
+      set_error("dim %lld does not fit the scan kernel's shared memory", (long long)b->dim);
+      return DEVQA_E_UNSUPPORTED;
+    }
+    const void* bank_ptr = b->data;
+    if (n < 8) {                                           // whole row groups only: zero-padded copy (see run_search)
+      const size_t row_bytes = size_t(b->ld) * b->esz();
+      if ((rc = grow(&s->tiny, &s->tiny_bytes, 8 * row_bytes, false))) return rc;
+      DEVQA_CUDA(cudaMemsetAsync(s->tiny, 0, 8 * row_bytes, stream));
+      DEVQA_CUDA(cudaMemcpyAsync(s->tiny, b->data, size_t(n - 1) * row_bytes + size_t(b->dim) * b->esz(),
+                                 cudaMemcpyDeviceToDevice, stream));
+      bank_ptr = s->tiny;
+    }
+    const int R = scan_stream_rows_per_group(qt);
+    const int64_t groups = (n + R - 1) / R;
+    const int64_t want_ctas = (groups + (kScanThreads / 32) - 1) / (kScanThreads / 32);
+    const int grid = int(want_ctas < s->sm_count ? (want_ctas < 1 ? 1 : want_ctas) : s->sm_count);
+    ScanParams p{};
+    p.bank = bank_ptr; p.n_rows = n; p.dim = b->dim; p.bank_ld = b->ld;
+    p.queries = queries; p.query_ld = qld; p.n_queries = int32_t(nq);
+    p.top_k = 1; p.kcap = 32; p.flags = flags; p.idmap = b->idmap;
+    p.sel_thr = thresholds; p.sel_scale = scale; p.sel_mask = mask; p.sel_mask_ld = n;
+    for (int64_t q0 = 0; q0 < nq; q0 += qt) {
+      p.q0 = int32_t(q0);
+      p.nq_pass = int32_t(nq - q0 < qt ? nq - q0 : qt);
+      if ((rc = scan_stream_launch(p, b->dtype, vectorised, qt, grid, stream))) return rc;
+    }
+  }
+  SelectParams sp{};
+  sp.bank = b->data; sp.bank_dtype = b->dtype; sp.n_rows = n; sp.dim = b->dim; sp.bank_ld = b->ld;
+  sp.queries = queries; sp.query_ld = qld; sp.n_queries = int32_t(nq);
+  sp.flags = flags; sp.scale = scale; sp.idmap = b->idmap;
+  sp.mask = mask; sp.mask_ld = n; sp.out_ids = out_ids; sp.out_scores = out_scores; sp.cap = cap; sp.out_counts = out_counts;
+  if ((rc = select_compact_launch(sp, stream))) return rc;
+  return scratch_leave(s, stream);
+}
+
+// gate (+ optional memory check) on an entered scratch; mem_scores: device [nq] or nullptr
+static int gate_common(Scratch* s, const float* queries, int64_t nq, int64_t qld, int64_t dim, const float* w_rand,
+                       int64_t w_ld, int64_t m, const float* wo, int64_t wo_ld, int n_classes, unsigned flags,
+                       const float* mem_scores, float mem_threshold, float* out_logits, int32_t* out_preds,
+                       float* partial, cudaStream_t stream) {
+  GateParams g{};
+  g.queries = queries; g.query_ld = qld; g.n_queries = int32_t(nq); g.dim = int32_t(dim);
+  g.w_rand = w_rand; g.w_ld = w_ld; g.m = int32_t(m); g.wo = wo; g.wo_ld = wo_ld; g.n_classes = n_classes;
+  g.flags = flags; g.partial = partial; g.ticket = s->gate_ticket; g.logits = out_logits; g.preds = out_preds;
+  g.mem_scores = mem_scores; g.mem_stride = 1; g.mem_threshold = mem_threshold;
+  return scope_gate_launch(g, stream);
+}
+
+static int gate_validate(const float* queries, int64_t nq, int64_t qld, int64_t dim, const float* w_rand, int64_t w_ld,
+                         int64_t m, const float* wo, int64_t wo_ld, int n_classes, const float* out_logits,
+                         const int32_t* out_preds) {
+  DEVQA_REQUIRE(nq >= 0 && dim > 0 && qld >= dim, "scope gate: bad query shape");
+  DEVQA_REQUIRE(m > 0 && m <= (1 << 24) && w_ld >= m && wo_ld >= m, "scope gate: bad W_rand / Wo shape");
+  DEVQA_REQUIRE(n_classes >= 1 && n_classes <= 64, "scope gate: n_classes %d unsupported", n_classes);
+  DEVQA_REQUIRE(nq == 0 || (queries && w_rand && wo && out_logits && out_preds), "scope gate: null pointers");
+  return DEVQA_OK;
+}
+
+int devqa_scope_gate(const float* queries, int64_t nq, int64_t qld, int64_t dim, const float* w_rand, int64_t w_ld,
+                     int64_t m, const float* wo, int64_t wo_ld, int n_classes, unsigned flags, const float* mem_scores,
+                     float mem_threshold, float* out_logits, int32_t* out_preds, void* stream_) {
+  int rc = gate_validate(queries, nq, qld, dim, w_rand, w_ld, m, wo, wo_ld, n_classes, out_logits, out_preds);
+  if (rc) return rc;
+  if (nq == 0) return DEVQA_OK;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  int device = 0;
+  DEVQA_CUDA(cudaGetDevice(&device));
+  Scratch* s = nullptr;
+  if ((rc = scratch_for(device, &s))) return rc;
+  std::lock_guard<std::mutex> lock(s->mu);
+  if ((rc = scratch_enter(s, stream))) return rc;
+  GateParams shape{}; shape.m = int32_t(m); shape.n_queries = int32_t(nq); shape.n_classes = n_classes;
+  if ((rc = grow(reinterpret_cast<void**>(&s->gate), &s->gate_bytes, scope_gate_partial_floats(shape) * 4, false))) return rc;
+  if ((rc = gate_common(s, queries, nq, qld, dim, w_rand, w_ld, m, wo, wo_ld, n_classes, flags, mem_scores, mem_threshold,
+                        out_logits, out_preds, s->gate, stream)))
+    return rc;
+  return scratch_leave(s, stream);
+}
+
+int devqa_bank_hice_probe(devqa_bank* b, devqa_bank* memory, const float* queries, const float* mem_queries, int64_t nq,
+                          int64_t qld, const float* w_rand, int64_t w_ld, int64_t m, const float* wo, int64_t wo_ld,
+                          int n_classes, float mem_threshold, int top_k, unsigned flags, float* out_logits,
+                          int32_t* out_preds, float* out_mem_sim, float* out_scores, int64_t* out_ids, void* stream_) {
+  DEVQA_REQUIRE(b != nullptr, "bank is null");
+  int rc = gate_validate(queries, nq, qld, b->dim, w_rand, w_ld, m, wo, wo_ld, n_classes, out_logits, out_preds);
+  if (rc) return rc;
+  DEVQA_REQUIRE(!memory || (memory->device == b->device && memory->dim == b->dim), "memory bank: other device or width");
+  if (nq == 0) return DEVQA_OK;
+  DEVQA_REQUIRE(out_scores && out_ids, "output pointers are null");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  SearchArgs a = bank_args(b, queries, nq, qld, top_k, flags);
+  if ((rc = validate(a))) return rc;
+  DEVQA_ON_DEVICE(b->device);
+  Scratch* s = nullptr;
+  if ((rc = scratch_for(b->device, &s))) return rc;
+  std::lock_guard<std::mutex> lock(s->mu);
+  if ((rc = scratch_enter(s, stream))) return rc;
+  GateParams shape{}; shape.m = int32_t(m); shape.n_queries = int32_t(nq); shape.n_classes = n_classes;
+  const size_t part = scope_gate_partial_floats(shape);
+  // scratch: [partial logits | best memory similarity per probe | its row id (int64, 8-byte aligned)]
+  const size_t mem_off = (part + 1) / 2 * 2;
+  if ((rc = grow(reinterpret_cast<void**>(&s->gate), &s->gate_bytes, (mem_off + size_t(nq) * 4) * 4, false))) return rc;
+  float* mem_sim = nullptr;
+  if (memory && memory->size > 0) {
+    // HICE.py:243-248: probe/||probe|| @ (memory/||memory||)^T, max over the memory = a fused no-eps cosine top-1
+    mem_sim = out_mem_sim ? out_mem_sim : s->gate + mem_off;
+    int64_t* mem_ids = reinterpret_cast<int64_t*>(s->gate + mem_off + size_t(nq) + (size_t(nq) & 1));
+    SearchArgs am = bank_args(memory, mem_queries ? mem_queries : queries, nq, qld, 1,
+                              DEVQA_NORMALIZE_BANK | DEVQA_NORMALIZE_QUERY | DEVQA_NOEPS);
+    if ((rc = validate(am))) return rc;
+    if ((rc = run_search(s, am, nullptr, mem_sim, mem_ids, stream))) return rc;
+  } else if (out_mem_sim) {
+    DEVQA_CUDA(cudaMemsetAsync(out_mem_sim, 0xff, size_t(nq) * 4, stream));   // NaN: "no memory"
+  }
+  if ((rc = gate_common(s, queries, nq, qld, b->dim, w_rand, w_ld, m, wo, wo_ld, n_classes,
+                        DEVQA_NORMALIZE_QUERY | DEVQA_NOEPS, mem_sim, mem_threshold, out_logits, out_preds, s->gate, stream)))
+    return rc;
+  if ((rc = run_search(s, a, nullptr, out_scores, out_ids, stream))) return rc;
   return scratch_leave(s, stream);
 }
 

@@ -24,6 +24,7 @@
 // One CTA per query: 8 warps re-score the candidates, then the CTA bitonic-sorts the exact keys.
 #include "scan.cuh"
 #include "topk.cuh"
+#include "exact.cuh"
 
 namespace devqa {
 namespace {
@@ -31,55 +32,15 @@ namespace {
 constexpr int kRefineThreads = 256;
 constexpr int kMaxKp = 128;
 
-// T = float: VEC = 4 columns per lane and chunk (128-bit loads), else 1.  T = __nv_bfloat16: VEC = 8 columns per lane
-// and chunk, unpacked low half first -- scan_stream.cu's Loader<T, NV> orders.
-template <typename T, bool VEC>
-__device__ __forceinline__ float exact_score(const T* __restrict__ row, const float* sq, int dim, unsigned flags, int lane) {
-  constexpr bool BF = sizeof(T) == 2;
-  constexpr int NV = VEC ? (BF ? 8 : 4) : 1;
-  constexpr int CH = 32 * NV;
-  const int nchunks = (dim + CH - 1) / CH;
-  const bool norm = (flags & DEVQA_NORMALIZE_BANK) != 0;
-  float acc = 0.f, nr = 0.f;
-  for (int c = 0; c < nchunks; ++c) {
-    const int col = c * CH + lane * NV;
-    float b[NV], qv[NV];
-    if constexpr (VEC && BF) {
-      uint4 t = make_uint4(0u, 0u, 0u, 0u);
-      if (col < dim) t = __ldg(reinterpret_cast<const uint4*>(row + col));
-      b[0] = __uint_as_float(t.x << 16); b[1] = __uint_as_float(t.x & 0xffff0000u);
-      b[2] = __uint_as_float(t.y << 16); b[3] = __uint_as_float(t.y & 0xffff0000u);
-      b[4] = __uint_as_float(t.z << 16); b[5] = __uint_as_float(t.z & 0xffff0000u);
-      b[6] = __uint_as_float(t.w << 16); b[7] = __uint_as_float(t.w & 0xffff0000u);
-      const float4 u0 = *reinterpret_cast<const float4*>(sq + col), u1 = *reinterpret_cast<const float4*>(sq + col + 4);
-      qv[0] = u0.x; qv[1] = u0.y; qv[2] = u0.z; qv[3] = u0.w; qv[4] = u1.x; qv[5] = u1.y; qv[6] = u1.z; qv[7] = u1.w;
-    } else if constexpr (VEC) {
-      float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (col < dim) t = __ldg(reinterpret_cast<const float4*>(row + col));
-      b[0] = t.x; b[1] = t.y; b[2] = t.z; b[3] = t.w;
-      const float4 u = *reinterpret_cast<const float4*>(sq + col);
-      qv[0] = u.x; qv[1] = u.y; qv[2] = u.z; qv[3] = u.w;
-    } else {
-      if constexpr (BF) b[0] = col < dim ? __bfloat162float(row[col]) : 0.f;
-      else b[0] = col < dim ? __ldg(row + col) : 0.f;
-      qv[0] = sq[col];
-    }
-#pragma unroll
-    for (int e = 0; e < NV; ++e) acc = fmaf(b[e], qv[e], acc);
-    if (norm) {
-#pragma unroll
-      for (int e = 0; e < NV; ++e) nr = fmaf(b[e], b[e], nr);
-    }
-  }
-#pragma unroll
-  for (int off = 16; off >= 1; off >>= 1) acc = acc + __shfl_xor_sync(kFull, acc, off);
-  if (norm) {
-#pragma unroll
-    for (int off = 16; off >= 1; off >>= 1) nr = nr + __shfl_xor_sync(kFull, nr, off);
-    const float nrm = sqrtf(nr);
-    acc *= 1.0f / ((flags & DEVQA_NOEPS) ? nrm : fmaxf(nrm, kNormEps));
-  }
-  return acc;
+// Canary of the filter's error bound.  Every candidate that is re-scored has both its upper bound u (the score field of
+// the key the scan produced: u = s~ + E) and its exact score s.  The whole completeness proof rests on
+//     u - 2E <= s <= u,      E = qerr * (||row|| for un-normalised scores, 1 otherwise);
+// the bound's accumulation term models undocumented tensor-core behaviour (scan.cuh), so it is CHECKED here instead of
+// trusted: a violation flags the query for the exact fallback and is counted (devqa_filter_bound_violations).
+// Non-finite values carry no information about the bound and are skipped.
+__device__ __forceinline__ bool bound_violated(float u, float s, float e) {
+  if (!(fabsf(u) <= 3.0e38f) || !(fabsf(s) <= 3.0e38f) || !(e <= 3.0e38f)) return false;
+  return s > u || (u - s) > 2.0001f * e + 1e-30f;
 }
 
 template <typename T, bool VEC>
@@ -89,6 +50,7 @@ __global__ void __launch_bounds__(kRefineThreads) refine_kernel(const RefinePara
   __shared__ uint64_t ak[kMaxKp];
   __shared__ float s_prelim;
   __shared__ uint32_t s_lost;                                       // max score code of any full list's last entry
+  __shared__ uint32_t s_viol;                                       // candidates whose exact score left [u - 2E, u]
   constexpr int CH = VEC ? (sizeof(T) == 2 ? 256 : 128) : 32;
   const int dim = int(p.dim);
   const int dpad = (dim + CH - 1) / CH * CH;
@@ -103,8 +65,11 @@ __global__ void __launch_bounds__(kRefineThreads) refine_kernel(const RefinePara
     ak[c] = c < p.kp ? p.akeys[size_t(q) * p.kp + c] : kEmptyKey;
     ex[c] = kEmptyKey;
   }
-  if (threadIdx.x == 0) s_lost = 0u;
+  if (threadIdx.x == 0) { s_lost = 0u; s_viol = 0u; }
   __syncthreads();
+  const bool canary = !p.only_if && p.qerr != nullptr;              // the keys carry upper bounds of the filter scan
+  const bool dot_mode = !(p.flags & DEVQA_NORMALIZE_BANK);
+  const float eq = canary ? p.qerr[q] : 0.f;
 
   auto rescore = [&](int c) {                                       // whole warp
     const uint64_t a = ak[c];
@@ -113,8 +78,11 @@ __global__ void __launch_bounds__(kRefineThreads) refine_kernel(const RefinePara
       const int64_t gid = int64_t(key_id(a));
       int64_t row = gid - p.idmap.base;
       if (p.idmap.chunk > 0) row = ((row / p.idmap.chunk) / p.idmap.world) * p.idmap.chunk + row % p.idmap.chunk;
-      const float s = exact_score<T, VEC>(static_cast<const T*>(p.bank) + row * p.bank_ld, sq, dim, p.flags, lane);
+      float nrm = 1.f;
+      const float s = exact_score<T, VEC>(static_cast<const T*>(p.bank) + row * p.bank_ld, sq, dim, p.flags, lane,
+                                          (canary && dot_mode) ? &nrm : nullptr);
       key = pack_key(s, uint32_t(gid));
+      if (canary && lane == 0 && bound_violated(key_score(a), s, eq * nrm)) atomicAdd(&s_viol, 1u);
     }
     if (lane == 0) ex[c] = key;
   };
@@ -176,6 +144,10 @@ __global__ void __launch_bounds__(kRefineThreads) refine_kernel(const RefinePara
       // rows were pushed out somewhere: they all have exact score <= code_score(lost)
       complete = kth != kEmptyKey && code_score(lost) < key_score(kth);    // false for NaN on either side
     }
+    if (s_viol != 0u) {                                             // the error bound did not hold: nothing is proven
+      complete = false;
+      if (p.violations) atomicAdd(p.violations, s_viol);
+    }
     p.need[q] = complete ? 0u : 1u;
     if (!complete && p.fallbacks) atomicAdd(p.fallbacks, 1u);
   }
@@ -205,18 +177,20 @@ __global__ void __launch_bounds__(kRefineListThreads) refine_lists_kernel(const 
   static_assert(kWide == kRefineListThreads, "one key per thread in the second cut");
   __shared__ uint64_t ex[kMaxKp];
   __shared__ uint64_t ak[kWide];
-  __shared__ uint32_t s_count, s_lost, s_tcode;
+  __shared__ uint32_t s_count, s_lost, s_tcode, s_viol;
   constexpr int CH = VEC ? (sizeof(T) == 2 ? 256 : 128) : 32;
   const int dim = int(p.dim);
   const int dpad = (dim + CH - 1) / CH * CH;
   float* sq = reinterpret_cast<float*>(smem_raw);
   const int q = blockIdx.x;
+  const bool dot_mode = !(p.flags & DEVQA_NORMALIZE_BANK);
+  const float eq = p.qerr[q];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const float* src = p.queries + size_t(q) * p.query_ld;
   const float inv = p.qinv[q];
   for (int c = threadIdx.x; c < dpad; c += kRefineListThreads) sq[c] = c < dim ? src[c] * inv : 0.f;
   for (int c = threadIdx.x; c < kMaxKp; c += kRefineListThreads) ex[c] = kEmptyKey;
-  if (threadIdx.x == 0) { s_count = 0u; s_lost = 0u; s_tcode = 0u; }
+  if (threadIdx.x == 0) { s_count = 0u; s_lost = 0u; s_tcode = 0u; s_viol = 0u; }
   // ---- T from the CTAs' bests (warp 0), lost-row bounds (warp 1) ----
   if (warp == 0) {
     const uint32_t* g = p.gmax + size_t(q) * p.gmax_stride;
@@ -301,8 +275,13 @@ __global__ void __launch_bounds__(kRefineListThreads) refine_lists_kernel(const 
     const int64_t gid = int64_t(key_id(a));
     int64_t row = gid - p.idmap.base;
     if (p.idmap.chunk > 0) row = ((row / p.idmap.chunk) / p.idmap.world) * p.idmap.chunk + row % p.idmap.chunk;
-    const float s = exact_score<T, VEC>(static_cast<const T*>(p.bank) + row * p.bank_ld, sq, dim, p.flags, lane);
-    if (lane == 0) ex[c] = pack_key(s, uint32_t(gid));
+    float nrm = 1.f;
+    const float s = exact_score<T, VEC>(static_cast<const T*>(p.bank) + row * p.bank_ld, sq, dim, p.flags, lane,
+                                        dot_mode ? &nrm : nullptr);
+    if (lane == 0) {
+      ex[c] = pack_key(s, uint32_t(gid));
+      if (bound_violated(key_score(a), s, eq * nrm)) atomicAdd(&s_viol, 1u);   // canary, see bound_violated()
+    }
   }
   __syncthreads();
   for (int k = 2; k <= kMaxKp; k <<= 1) {
@@ -325,6 +304,10 @@ __global__ void __launch_bounds__(kRefineListThreads) refine_lists_kernel(const 
     const uint32_t lost = s_lost;
     if (complete && lost != 0u)
       complete = kth != kEmptyKey && code_score(lost) < key_score(kth);   // false for NaN on either side
+    if (s_viol != 0u) {                                                // the error bound did not hold: nothing is proven
+      complete = false;
+      if (p.violations) atomicAdd(p.violations, s_viol);
+    }
     p.need[q] = complete ? 0u : 1u;
     if (!complete && p.fallbacks) atomicAdd(p.fallbacks, 1u);
   }

@@ -31,6 +31,11 @@ struct ScanParams {
   // stream kernel, capacity 32: the last CTA to finish merges the per-CTA lists itself (no merge launch)
   uint32_t* ticket;        // zeroed device word (re-zeroed by the kernel); nullptr: separate merge kernel
   uint64_t* out_keys; float* out_scores; int64_t* out_ids;   // final [n_queries, top_k] (exactly one form)
+  // stream kernel, threshold-select mode (select.cu): mask[q][row] = score * sel_scale > sel_thr[q]
+  const float* sel_thr;    // [n_queries] device thresholds
+  float sel_scale;
+  uint8_t* sel_mask;       // [n_queries, sel_mask_ld] out; nullptr = ordinary top-k scan
+  int64_t sel_mask_ld;
   uint32_t* lostu;         // [grid, n_queries] out: bound on the rows each CTA's full list lost (score code, 0 = none)
   uint32_t* gmax;          // [q_pad, gmax_stride] zeroed scratch: each CTA's best upper bound per query (score codes)
   int32_t gmax_stride;
@@ -47,14 +52,24 @@ int scan_stream_launch(const ScanParams& p, int bank_dtype, bool vectorised, int
 //   kTcTf32x1                fp32 bank, approximate scores with a proven error bound: a FILTER whose top-K'
 //                            lists are rescored exactly by refine.cu
 constexpr int kTcTf32x3 = 0, kTcBf16x3 = 1, kTcTf32x1 = 2, kTcBf16x1 = 3;   // kTcBf16x1: the filter on a bf16 bank
-// |approximate - exact| <= tc_filter_relerr(dim) * ||row|| * ||query||  for the kTcTf32x1 scores:
-//   2^-10 (bank words truncated to TF32) + 2^-11 (queries rounded to TF32) + their product, by Cauchy-Schwarz;
-//   dim * 2^-24 for the accumulation: the tensor core adds dim/8 times into an fp32 accumulator with truncation
-//   (<= 2 ulp of the running magnitude each: dim * 2^-25) and the fp32 re-scoring it is compared with rounds
-//   (dim/32 + 5) times to nearest.  tests/test_gpu_filter.py measures the actual error against this bound.
-// bf16 banks (kTcBf16x1): the bank is exact, queries are rounded to bf16 (<= 2^-9): 1.01 * 2^-9 + dim * 2^-24.
+// |approximate - fp32-exact| <= tc_filter_relerr(dim) * ||row|| * ||query||  for the filter scores.  Terms:
+//   inputs   fp32 bank (kTcTf32x1): the tensor core truncates bank words to TF32 (relative error < 2^-10), queries are
+//            rounded to nearest TF32 (<= 2^-11); by Cauchy-Schwarz the sum of the per-element errors is at most
+//            (2^-10 + 2^-11 + 2^-21) * ||row|| * ||query||.  bf16 bank (kTcBf16x1): the bank is exact, queries are
+//            rounded to nearest bf16 -- 8 significand bits, i.e. <= 2^-8 (NOT 2^-9).
+//   2^-19    the product term above, and the fp32 roundings inside ||query|| and the cached ||row||^2 that E is built from.
+//   dim*2^-22  everything that grows with the length of the sum: the tensor core adds dim/8 (dim/16) times into an fp32
+//            accumulator with truncation -- modelled as <= 1 ulp per MMA (dim * 2^-26), but the hardware's internal
+//            alignment of the 8 products is undocumented, so up to 9 ulp per MMA (2.25 * dim * 2^-24) are budgeted; the
+//            fp32 re-scoring the bound is compared with rounds (dim/32 + 5) times to nearest, and so does each of the
+//            two ||row||^2 sums (filter side / exact side) the normalised scores are divided by.
+// The bound is deliberately not tight in its length term: E only widens the band of candidates refine.cu re-scores
+// (a few rows per query), while a violated bound would silently lose a row.  refine.cu checks  u - 2E <= s <= u  for
+// every candidate it re-scores (devqa_filter_bound_violations), tests/test_gpu_filter.py measures the actual error
+// on constructed worst cases against this bound.
 __host__ __device__ inline float tc_filter_relerr(int64_t dim, bool bf16_bank = false) {
-  return (bf16_bank ? 1.01f * 0.001953125f : 1.5f * 0.0009765625f) + float(dim) * 5.9604644775390625e-08f;
+  const float inputs = bf16_bank ? 0.00390625f : 1.5f * 0.0009765625f;       // 2^-8 | 2^-10 + 2^-11
+  return inputs + 1.9073486328125e-06f + float(dim) * 2.384185791015625e-07f;  // + 2^-19 + dim * 2^-22
 }
 bool scan_tc_supported(int bank_dtype, const void* bank, int64_t dim, int64_t bank_ld, int top_k);
 int scan_tc_plan(int mode, int n_queries, int64_t dim, int kcap, bool cached_norms, int64_t n_tiles, int sm_count,
@@ -96,6 +111,7 @@ struct RefineParams {
                               // nothing else -- no completeness verdict (used on the exact fallback's result)
   uint32_t* need;             // [n_queries] out: 1 when a lost row could still belong to the exact top-k
   uint32_t* fallbacks;        // device counter of such queries (devqa_filter_fallbacks)
+  uint32_t* violations;       // device counter: re-scored candidates whose exact score lay outside [u - 2E, u]
   uint64_t* out_keys; float* out_scores; int64_t* out_ids;   // exactly one of keys / (scores, ids): [n_queries, top_k]
 };
 int refine_launch(const RefineParams& p, cudaStream_t stream);          // from the merged list akeys
@@ -110,6 +126,32 @@ int merge_lists_launch(const uint64_t* lists, int n_lists, int64_t n_queries, in
                        int list_len, int top_k, uint64_t* out_keys, float* out_scores,
                        int64_t* out_ids, cudaStream_t stream, uint32_t* kth_codes = nullptr,
                        const uint32_t* need = nullptr);
+
+// select.cu: threshold-select (LiveEdit retrieve_moes): ordered compaction of the mask the stream kernel wrote.
+struct SelectParams {
+  const void* bank; int bank_dtype; int64_t n_rows, dim, bank_ld;
+  const float* queries; int64_t query_ld; int32_t n_queries;
+  unsigned flags; float scale; IdMap idmap;
+  const uint8_t* mask; int64_t mask_ld;       // [n_queries, mask_ld]
+  int64_t* out_ids; float* out_scores;        // [n_queries, cap]: selected rows in ascending row order (-1 / -inf beyond)
+  int64_t cap;
+  int64_t* out_counts;                        // [n_queries] number of selected rows (may exceed cap)
+};
+int select_compact_launch(const SelectParams& p, cudaStream_t stream);
+
+// gate.cu: HICE scope gate -- logits = relu(q/||q|| @ W_rand) @ Wo^T, argmax, m-loc memory override.
+struct GateParams {
+  const float* queries; int64_t query_ld; int32_t n_queries; int32_t dim;
+  const float* w_rand; int64_t w_ld; int32_t m;        // [dim, m]
+  const float* wo; int64_t wo_ld; int32_t n_classes;   // [n_classes, m]
+  unsigned flags;                                      // DEVQA_NORMALIZE_QUERY / DEVQA_NOEPS
+  float* partial;                                      // scratch [scope_gate_partial_floats()]
+  uint32_t* ticket;                                    // zeroed device word (re-zeroed by the kernel)
+  float* logits; int32_t* preds;                       // out [n_queries, n_classes], [n_queries]
+  const float* mem_scores; int64_t mem_stride; float mem_threshold;   // optional: best memory similarity per probe
+};
+size_t scope_gate_partial_floats(const GateParams& p);
+int scope_gate_launch(const GateParams& p, cudaStream_t stream);
 
 // synth.cu
 int fill_synthetic_launch(void* dst, int dtype, int64_t n_rows, int64_t dim, int64_t ld, uint64_t seed,

@@ -175,7 +175,9 @@ __device__ __forceinline__ void prefetch_l2(const void* p) {
   asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 }
 
-template <typename T, int NV, int QT, int R, bool NORM>
+// SELECT: threshold-select epilogue (LiveEdit's hard routing, liveedit.py:132-143): instead of a top-k, every row gets a
+// byte  mask[q][row] = (score * sel_scale > sel_thr[q])  -- no lists, no k cap, rows in bank order by construction.
+template <typename T, int NV, int QT, int R, bool NORM, bool SELECT = false>
 __global__ void __launch_bounds__(kScanThreads, 1) scan_stream_kernel(const ScanParams p) {
   constexpr int V = QT * R;
   constexpr int CH = 32 * NV;                       // columns one warp covers per chunk
@@ -212,7 +214,8 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_stream_kernel(const Scan
     for (int c = lane; c < dpad; c += 32)
       dst[query_slot<NV, QT>(c)] = (c < dim && q < p.nq_pass) ? src[c] * inv : 0.f;
   }
-  for (int i = threadIdx.x; i < kScanWarps * QT * kcap; i += kScanThreads) lists[i] = kEmptyKey;
+  if constexpr (!SELECT)
+    for (int i = threadIdx.x; i < kScanWarps * QT * kcap; i += kScanThreads) lists[i] = kEmptyKey;
   __syncthreads();
 
   uint64_t* my_lists = lists + size_t(warp) * QT * kcap;
@@ -222,6 +225,14 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_stream_kernel(const Scan
   // when V < 32 several lanes end up with the same total: only the one with clear low bits reports it
   const bool q_live = my_q < p.nq_pass && (lane & ((32 >> Log2<V>::value) - 1)) == 0;
   uint64_t thr = kEmptyKey;                          // k-th key of my_q's list
+  float sel_thr = 0.f;                               // SELECT: this lane's query's threshold
+  uint8_t* sel_row = nullptr;                        //         and its mask row
+  if constexpr (SELECT) {
+    if (q_live) {
+      sel_thr = p.sel_thr[p.q0 + my_q];
+      sel_row = p.sel_mask + size_t(p.q0 + my_q) * p.sel_mask_ld;
+    }
+  }
 
   const int64_t n_groups = (p.n_rows + R - 1) / R;
   const int64_t warp_stride = int64_t(gridDim.x) * kScanWarps;
@@ -309,6 +320,12 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_stream_kernel(const Scan
     }
     const int64_t row = base + my_r;
     const bool live = q_live && row >= g * R && row < p.n_rows;
+    if constexpr (SELECT) {
+      if (live) sel_row[row] = (score * p.sel_scale > sel_thr) ? uint8_t(1) : uint8_t(0);   // NaN: not selected, like torch's >
+      base = base_n;
+      g = gn;
+      continue;
+    }
     const uint64_t key = live ? pack_key(score, uint32_t(p.idmap(row))) : kEmptyKey;
     unsigned hit = __ballot_sync(kFull, key > thr);
     if (hit) {
@@ -325,6 +342,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_stream_kernel(const Scan
     g = gn;
   }
 
+  if constexpr (SELECT) return;
   // ---- epilogue: tree-merge the warps' lists, one sorted candidate list per (CTA, query) ------
   __syncthreads();
   for (int s = 1; s < kScanWarps; s <<= 1) {
@@ -390,8 +408,23 @@ int launch_variant(const ScanParams& p, int grid, cudaStream_t stream) {
   return DEVQA_OK;
 }
 
+template <typename T, int NV, int QT, int R>
+int launch_select_variant(const ScanParams& p, int grid, cudaStream_t stream) {
+  const int nchunks = (int(p.dim) + 32 * NV - 1) / (32 * NV);
+  const size_t smem = size_t(QT) * nchunks * 32 * NV * 4;
+  const bool norm = (p.flags & DEVQA_NORMALIZE_BANK) != 0;
+  auto kern = norm ? scan_stream_kernel<T, NV, QT, R, true, true> : scan_stream_kernel<T, NV, QT, R, false, true>;
+  DEVQA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+  kern<<<grid, kScanThreads, smem, stream>>>(p);
+  DEVQA_CUDA(cudaGetLastError());
+  count_launch();
+  return DEVQA_OK;
+}
+
 template <typename T, int NV>
 int launch_qt(const ScanParams& p, int qt, int grid, cudaStream_t stream) {
+  if (p.sel_mask != nullptr)
+    return qt == 4 ? launch_select_variant<T, NV, 4, 4>(p, grid, stream) : launch_select_variant<T, NV, 1, 4>(p, grid, stream);
   switch (qt) {
     case 8: return launch_variant<T, NV, 8, 4>(p, grid, stream);
     case 4: return launch_variant<T, NV, 4, 4>(p, grid, stream);
@@ -409,7 +442,8 @@ size_t scan_stream_smem_bytes(int64_t dim, int nv, int qt, int kcap) {
 
 int scan_stream_rows_per_group(int qt) { return 4; }
 
-// One pass: queries [q0, q0 + nq_pass) against the whole bank.  `qt` in {1,2,4,8} >= nq_pass.
+// One pass: queries [q0, q0 + nq_pass) against the whole bank.  `qt` in {1,2,4,8} >= nq_pass
+// (threshold-select mode, p.sel_mask != nullptr: qt in {1,4}).
 int scan_stream_launch(const ScanParams& p, int bank_dtype, bool vectorised, int qt, int grid,
                        cudaStream_t stream) {
   if (bank_dtype == DEVQA_F32) {

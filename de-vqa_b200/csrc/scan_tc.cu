@@ -1275,7 +1275,10 @@ __global__ void __launch_bounds__(256) prep_queries_filt_kernel(const float* __r
     }
 #pragma unroll
     for (int off = 16; off >= 1; off >>= 1) nn += __shfl_xor_sync(kFull, nn, off);
-    if (lane == 0 && r < n_queries) { qinv[r] = inv; qerr[r] = tc_filter_relerr(dim) * sqrtf(nn); }
+    if (lane == 0 && r < n_queries) {
+      qinv[r] = inv;
+      qerr[r] = tc_filter_relerr(dim) * sqrtf(nn) * ((flags & DEVQA_DEBUG_TIGHT_BOUND) ? 0.015625f : 1.f);
+    }
   }
 }
 
@@ -1318,7 +1321,10 @@ __global__ void __launch_bounds__(256) prep_queries_filt_bf16_kernel(const float
     }
 #pragma unroll
     for (int off = 16; off >= 1; off >>= 1) nn += __shfl_xor_sync(kFull, nn, off);
-    if (lane == 0 && r < n_queries) { qinv[r] = inv; qerr[r] = tc_filter_relerr(dim, true) * sqrtf(nn); }
+    if (lane == 0 && r < n_queries) {
+      qinv[r] = inv;
+      qerr[r] = tc_filter_relerr(dim, true) * sqrtf(nn) * ((flags & DEVQA_DEBUG_TIGHT_BOUND) ? 0.015625f : 1.f);
+    }
   }
 }
 

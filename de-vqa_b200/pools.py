@@ -84,13 +84,106 @@ class EditPool:
         proto_id = torch.empty((q.shape[0], 1), dtype=torch.int64, device=self.bank.device)
         bank_ld = (self.dim + 3) // 4 * 4                      # FactBank pads fp32 rows to 16 bytes
         # similarity with the prototype = a one-row search over row 0 of the same resident buffer
-        L.check(L.lib().devqa_search_raw(self.bank.data_ptr, self.bank.dtype, 1, self.dim, bank_ld,
-                                         q.data_ptr(), q.shape[0], q.stride(0) if q.shape[0] > 1 else self.dim, 1, 0, 0,
-                                         proto.data_ptr(), proto_id.data_ptr(), _stream_ptr(self.bank.device_index)))
+        # (devqa_search_raw works on the CURRENT device: make that the bank's)
+        with torch.cuda.device(self.bank.device):
+            L.check(L.lib().devqa_search_raw(self.bank.data_ptr, self.bank.dtype, 1, self.dim, bank_ld,
+                                             q.data_ptr(), q.shape[0], q.stride(0) if q.shape[0] > 1 else self.dim, 1, 0, 0,
+                                             proto.data_ptr(), proto_id.data_ptr(), _stream_ptr(self.bank.device_index)))
         proto = proto / (self.dim ** 0.5)
         mask = sims > proto
         ids = torch.masked_select(order, mask)
         return list(torch.split(ids, mask.sum(1).tolist())), (sims, order)
+
+
+class ScopeGate:
+    """N4: HICE's scope decision for the probes of one edit request, resident on the device.
+
+    Reference: ``our_predict_domain`` (easyeditor/evaluate/multimodal_evaluate.py:382-392) --
+    ``relu(q/||q|| @ W_rand) @ Wo.T`` + argmax -- and the m-loc memory check of ``HICE.run_classifier2``
+    (easyeditor/trainer/algs/HICE.py:238-250).  ``W_rand`` ``[dim, M]`` and ``Wo`` ``[n_classes, M]`` are uploaded once
+    (the reference re-sends them per call as arguments of a Python function); ``mloc_memory`` (a list of ``[1, dim]``
+    tensors, a ``[n, dim]`` tensor, or the reference's ``{'embeddings': [...]}`` dict) becomes a resident pool.
+    ``predict`` is the gate alone; ``probe`` is gate + memory check + in-context lookup for ALL probes of a request in
+    one C call (``devqa_bank_hice_probe``), replacing up to ~11 Python round trips of gate -> ``select_icl_samples``."""
+
+    def __init__(self, Wo, W_rand, device=0, mloc_memory=None, threshold: float = 0.81):
+        self.device = torch.device(device if not isinstance(device, int) else f"cuda:{device}")
+        self.W_rand = torch.as_tensor(W_rand).detach().to(device=self.device, dtype=torch.float32).contiguous()
+        self.Wo = torch.as_tensor(Wo).detach().to(device=self.device, dtype=torch.float32).contiguous()
+        if self.W_rand.dim() != 2 or self.Wo.dim() != 2 or self.Wo.shape[1] != self.W_rand.shape[1]:
+            raise ValueError("W_rand must be [dim, M] and Wo [n_classes, M]")
+        self.dim, self.m = self.W_rand.shape
+        self.n_classes = self.Wo.shape[0]
+        self.threshold = float(threshold)
+        self.memory: Optional[EditPool] = None
+        if mloc_memory is not None:
+            self.set_memory(mloc_memory)
+
+    def set_memory(self, mloc_memory) -> None:
+        if isinstance(mloc_memory, dict):
+            mloc_memory = mloc_memory['embeddings']
+        if isinstance(mloc_memory, (list, tuple)):
+            mloc_memory = torch.cat([torch.as_tensor(e).reshape(-1, self.dim) for e in mloc_memory], 0) \
+                if len(mloc_memory) else torch.zeros(0, self.dim)
+        mem = torch.as_tensor(mloc_memory).reshape(-1, self.dim)
+        self.memory = EditPool(self.dim, device=self.device, capacity=max(1, len(mem)))
+        if len(mem):
+            self.memory.append(mem)
+
+    def remember(self, embedding) -> None:
+        """``mloc_memory['embeddings'].append(...)``: one more remembered m-loc sample, in place."""
+        if self.memory is None:
+            self.memory = EditPool(self.dim, device=self.device)
+        self.memory.append(torch.as_tensor(embedding).reshape(-1, self.dim))
+
+    def _q(self, x) -> torch.Tensor:
+        q = torch.as_tensor(x).detach().to(device=self.device, dtype=torch.float32)
+        q = q.reshape(-1, self.dim)
+        return q if q.is_contiguous() else q.contiguous()
+
+    def predict(self, query_embeddings) -> Tuple[torch.Tensor, torch.Tensor]:
+        """``our_predict_domain``'s arithmetic for ``[n, dim]`` (or ``[dim]``) probe embeddings:
+        ``(logits [n, n_classes] fp32, preds [n] int64)`` on the device.  No memory check (the reference's
+        ``our_predict_domain`` accepts ``mloc_memory`` but never reads it)."""
+        q = self._q(query_embeddings)
+        n = q.shape[0]
+        logits = torch.empty((n, self.n_classes), dtype=torch.float32, device=self.device)
+        preds = torch.empty((n,), dtype=torch.int32, device=self.device)
+        with torch.cuda.device(self.device):
+            L.check(L.lib().devqa_scope_gate(q.data_ptr(), n, self.dim, self.dim, self.W_rand.data_ptr(), self.m, self.m,
+                                             self.Wo.data_ptr(), self.m, self.n_classes, L.NORMALIZE_QUERY | L.NOEPS,
+                                             None, 0.0, logits.data_ptr(), preds.data_ptr(),
+                                             _stream_ptr(self.device.index)))
+        return logits, preds.long()
+
+    def probe(self, bank: FactBank, query_embeddings, top_k: int, mem_query_embeddings=None,
+              normalize_bank="noeps", normalize_query="noeps"):
+        """All probes of a request at once: memory check (``run_classifier2``: the probe's "Prompt: ..." embedding
+        ``mem_query_embeddings``, default the gate's own) -> scope gate -> top-k lookup over ``bank``
+        (``select_icl_samples``'s no-eps cosine by default).  Returns device tensors
+        ``(logits [n, C], preds [n] int64, mem_sim [n] (NaN without memory), scores [n, k], ids [n, k])``; the lookup
+        of a probe matters only where ``preds != 0`` (multimodal_evaluate.py:498-505)."""
+        from .bank import norm_flags
+        q = self._q(query_embeddings)
+        n = q.shape[0]
+        mq = self._q(mem_query_embeddings) if mem_query_embeddings is not None else None
+        if mq is not None and mq.shape != q.shape:
+            raise ValueError("mem_query_embeddings must match query_embeddings in shape")
+        if bank.device != self.device or bank.dim != self.dim:
+            raise ValueError("bank lives on another device or has another width")
+        logits = torch.empty((n, self.n_classes), dtype=torch.float32, device=self.device)
+        preds = torch.empty((n,), dtype=torch.int32, device=self.device)
+        mem_sim = torch.empty((n,), dtype=torch.float32, device=self.device)
+        scores = torch.empty((n, top_k), dtype=torch.float32, device=self.device)
+        ids = torch.empty((n, top_k), dtype=torch.int64, device=self.device)
+        mem_h = self.memory.bank._h if self.memory is not None else None
+        L.check(L.lib().devqa_bank_hice_probe(bank._h, mem_h, q.data_ptr(), mq.data_ptr() if mq is not None else None,
+                                              n, self.dim, self.W_rand.data_ptr(), self.m, self.m, self.Wo.data_ptr(),
+                                              self.m, self.n_classes, self.threshold, int(top_k),
+                                              norm_flags(normalize_bank, normalize_query), logits.data_ptr(),
+                                              preds.data_ptr(), mem_sim.data_ptr(), scores.data_ptr(), ids.data_ptr(),
+                                              _stream_ptr(self.device.index)))
+        return logits, preds.long(), mem_sim, scores, ids
 
 
 class VocabBank:
@@ -158,33 +251,41 @@ class LiveEditPool:
         s, i = self.bank.search(q, top, normalize_bank=None, normalize_query=None)
         return s[0] * (float(sim_scale) / self.eqe_n), i[0]
 
+    def select(self, ivr, vis_sim_prot, sim_scale: float, cap: Optional[int] = None, want_mask: bool = True):
+        """One ``devqa_bank_select_above`` call -- the bank-streaming kernel's threshold-select epilogue plus the
+        ordered compaction (csrc/select.cu).  No host synchronisation: ``vis_sim_prot`` may be a device tensor (the
+        prototype similarity the caller computed on the device, liveedit.py:140-141).  Returns device tensors
+        ``(mask [m] bool | None, ids [cap] int64 ascending / -1, sims [cap] fp32, count [1] int64)``."""
+        m = len(self.bank)
+        dev = self.bank.device
+        cap = m if cap is None else int(cap)
+        q = self.bank._prep_queries(torch.as_tensor(ivr).reshape(1, self.dim))
+        thr = torch.as_tensor(vis_sim_prot, dtype=torch.float32).reshape(-1)[:1].to(dev).contiguous()
+        mask = torch.empty((1, m), dtype=torch.uint8, device=dev) if want_mask else None
+        ids = torch.empty((1, max(cap, 1)), dtype=torch.int64, device=dev)
+        sims = torch.empty((1, max(cap, 1)), dtype=torch.float32, device=dev)
+        count = torch.empty((1,), dtype=torch.int64, device=dev)
+        with torch.cuda.device(dev):
+            L.check(L.lib().devqa_bank_select_above(self.bank._h, q.data_ptr(), 1, self.dim, thr.data_ptr(),
+                                                    float(sim_scale) / self.eqe_n, 0,
+                                                    mask.data_ptr() if mask is not None and m > 0 else None,
+                                                    ids.data_ptr(), sims.data_ptr(), cap, count.data_ptr(),
+                                                    _stream_ptr(self.bank.device_index)))
+        return (mask[0].bool() if mask is not None else None), ids[0, :cap], sims[0, :cap], count
+
+    def retrieval_map(self, ivr, vis_sim_prot, sim_scale: float) -> torch.Tensor:
+        """``retrieval_map = vis_sim > vis_sim_prot`` (liveedit.py:142) as a ``[m]`` bool device tensor; no host sync."""
+        return self.select(ivr, vis_sim_prot, sim_scale, cap=0)[0]
+
     def retrieve(self, ivr, vis_sim_prot, sim_scale: float) -> Tuple[torch.Tensor, torch.Tensor]:
-        """``retrieval_map = vis_sim > vis_sim_prot`` as the ascending id list of the selected pool entries, plus
-        their similarities.  ``ivr``: ``[1, eqe_n, module_dim]``; ``vis_sim_prot``: the ``[1, 1]`` prototype
-        similarity the caller computed (:140-141)."""
+        """The ascending id list of the selected pool entries (the order ``pool[retrieval_map]`` yields) plus their
+        similarities.  ``ivr``: ``[1, eqe_n, module_dim]``; ``vis_sim_prot``: the ``[1, 1]`` prototype similarity the
+        caller computed (:140-141).  Any number of entries may pass (no top-k cap); the one host sync is reading the
+        count to size the result, which ``pool[retrieval_map]`` also pays."""
         m = len(self.bank)
         dev = self.bank.device
         if m == 0:
             return torch.empty(0, dtype=torch.int64, device=dev), torch.empty(0, device=dev)
-        thr = float(torch.as_tensor(vis_sim_prot).reshape(-1)[0])
-        step = L.MAX_TOPK
-        s, i = self.similarities(ivr, sim_scale, min(m, step))
-        if m > step and float(s[-1]) > thr:
-            # more than MAX_TOPK entries may pass: enumerate the pool in row ranges (each a search over a slice of
-            # the same resident buffer, ids offset by the range start)
-            q = self.bank._prep_queries(torch.as_tensor(ivr).reshape(1, self.dim))
-            parts_s, parts_i = [], []
-            row_bytes = ((self.dim + 3) // 4 * 4) * 4
-            for start in range(0, m, step):
-                n = min(step, m - start)
-                ps = torch.empty((1, n), dtype=torch.float32, device=dev)
-                pi = torch.empty((1, n), dtype=torch.int64, device=dev)
-                L.check(L.lib().devqa_search_raw(self.bank.data_ptr + start * row_bytes, self.bank.dtype, n, self.dim,
-                                                 row_bytes // 4, q.data_ptr(), 1, self.dim, n, 0, start,
-                                                 ps.data_ptr(), pi.data_ptr(), _stream_ptr(self.bank.device_index)))
-                parts_s.append(ps[0] * (float(sim_scale) / self.eqe_n))
-                parts_i.append(pi[0])
-            s, i = torch.cat(parts_s), torch.cat(parts_i)
-        keep = s > thr
-        ids, order = torch.sort(i[keep])
-        return ids, s[keep][order]
+        _, ids, sims, count = self.select(ivr, vis_sim_prot, sim_scale, want_mask=False)
+        n = int(count.item())
+        return ids[:n], sims[:n]

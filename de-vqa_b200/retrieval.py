@@ -141,7 +141,7 @@ def register_bank_for_file(path: str, bank: FactBank, device=0) -> None:
 def bank_from_file(path: str, device=0) -> FactBank:
     """Pickle/.pth -> resident FactBank, uploaded once per (file version, device)."""
     st = os.stat(path)
-    dev = device if isinstance(device, int) else getattr(device, "index", None) or 0
+    dev = _device_index(device)
     key = (os.path.abspath(path), st.st_size, st.st_mtime, dev)
     bank = _file_banks.get(key)
     if bank is None:
@@ -151,19 +151,41 @@ def bank_from_file(path: str, device=0) -> FactBank:
 
 def bank_from_stored_data(stored_data: Dict, device=0) -> FactBank:
     """``stored_data = {'sentences', 'embeddings'}`` (multimodal_editor.py:1129-1130) -> resident
-    FactBank, re-uploaded only when the embeddings object is replaced or modified in place."""
+    FactBank.  torch tensors carry a version counter that every in-place op bumps, so their resident copy is
+    re-uploaded exactly when the object is replaced or modified.  ndarrays / lists have no such counter: an in-place
+    edit of equal length would be invisible, so they are uploaded on every call (one H2D copy -- still without the
+    reference's per-call renormalisation) unless the caller registered the bank with ``pin_stored_data``."""
     emb = stored_data['embeddings']
     version = getattr(emb, "_version", None)
-    hit = _object_banks.get(id(emb))
-    if hit is not None and hit[0]() is emb and hit[1] == version and len(hit[2]) == len(emb):
+    dev = _device_index(device)
+    for key in [k for k, v in _object_banks.items() if v[0]() is None]:       # owners that died: free their banks
+        _object_banks.pop(key)[2].close()
+    hit = _object_banks.get((id(emb), dev))
+    pinned = hit is not None and hit[1] == "pinned"
+    if hit is not None and hit[0]() is emb and (pinned or (version is not None and hit[1] == version)) \
+            and len(hit[2]) == len(emb):
         bank = hit[2]
     else:
-        dev = device if isinstance(device, int) else getattr(device, "index", None) or 0
         bank = FactBank.from_embeddings(emb, device=dev)
-        try:
-            _object_banks[id(emb)] = (weakref.ref(emb), version, bank)
-        except TypeError:
-            pass
+        if version is not None:
+            try:
+                _object_banks[(id(emb), dev)] = (weakref.ref(emb), version, bank)
+            except TypeError:
+                pass
+    bank.sentences = stored_data['sentences']
+    return bank
+
+
+def pin_stored_data(stored_data: Dict, device=0) -> FactBank:
+    """Declare that ``stored_data['embeddings']`` (an ndarray: no version counter) will not be modified in place,
+    so that its resident copy may be reused across calls.  Call again after editing it."""
+    emb = stored_data['embeddings']
+    dev = _device_index(device)
+    old = _object_banks.pop((id(emb), dev), None)
+    if old is not None:
+        old[2].close()
+    bank = FactBank.from_embeddings(emb, device=dev)
+    _object_banks[(id(emb), dev)] = (weakref.ref(emb), "pinned", bank)
     bank.sentences = stored_data['sentences']
     return bank
 
@@ -318,3 +340,73 @@ def select_icl_samples(prompt, target, stored_data, sentence_model, device, hpar
     while len(''.join(icl_examples)) > DEMO_CHAR_CAP:
         del icl_examples[-1]
     return icl_examples
+
+
+# ---- HICE scope gate (multimodal_evaluate.py:382-392, 498-573; HICE.py:238-263) ------------------------------------
+_gates: Dict[Tuple[int, int, int], Any] = {}
+
+
+def _scope_gate(Wo, W_rand, device):
+    """Resident ``ScopeGate`` for this (Wo, W_rand) pair: the reference passes both tensors to every call."""
+    from .pools import ScopeGate
+    dev = _device_index(device)
+    for key in [k for k, v in _gates.items() if v[0]() is None or v[1]() is None]:
+        _gates.pop(key)
+    key = (id(Wo), id(W_rand), dev)
+    hit = _gates.get(key)
+    versions = (getattr(Wo, "_version", None), getattr(W_rand, "_version", None))
+    if hit is not None and hit[0]() is Wo and hit[1]() is W_rand and hit[2] == versions and None not in versions:
+        return hit[3]
+    gate = ScopeGate(Wo, W_rand, device=dev)
+    try:
+        _gates[key] = (weakref.ref(Wo), weakref.ref(W_rand), versions, gate)
+    except TypeError:
+        pass
+    return gate
+
+
+def our_predict_domain(prompt, target, sentence_model, Wo, W_rand, device, mloc_memory=None, threshold=0.81):
+    """multimodal_evaluate.py:382-392, same signature and return value ``(logits [n_classes], preds 0-d)``:
+    ``relu(q/||q|| @ W_rand) @ Wo.T`` and its argmax, computed by ``scope_gate_kernel``.  Like the reference,
+    ``mloc_memory`` / ``threshold`` are accepted and not used here (the memory check lives in ``run_classifier2``)."""
+    new_fact = prompt + ' ' + target
+    q = _encode_query(sentence_model, _query_sentence(new_fact, new_fact), device=device)
+    logits, preds = _scope_gate(Wo, W_rand, device).predict(q)
+    return logits[0], preds[0]
+
+
+def hice_probe_batch(probes: Sequence[Tuple[str, str]], stored_data, sentence_model, device, hparams, Wo, W_rand,
+                     mloc_memory=None, threshold: float = 0.81, mem_prompts: Optional[Sequence[str]] = None):
+    """The retrieval of ``compute_hice_multimodal_edit_quality`` (multimodal_evaluate.py:498-573) for ALL probes of a
+    request -- rephrase, locality, m-loc and the seven dynamic t*i* probes -- in one device call: scope gate
+    (``our_predict_domain``) and, for the probes it lets through, ``select_icl_samples``.
+    ``probes``: ``(prompt, target)`` pairs.  ``mem_prompts`` (optional): per probe the text of ``run_classifier2``'s
+    memory check (``"Prompt: {prompt} \n\n"`` sentence is built here); needs ``mloc_memory``.
+    Returns ``[(pred, icl_examples or None), ...]``: ``icl_examples`` as ``select_icl_samples`` returns them (2500-char
+    cap applied) where ``pred != 0``, else ``None`` (the reference then evaluates with ``['']``)."""
+    sentences = [_query_sentence(p + ' ' + t, p + ' ' + t) for p, t in probes]
+    q = np.stack([_encode_query(sentence_model, s, device=device)[0] for s in sentences])
+    gate = _scope_gate(Wo, W_rand, device)
+    mq = None
+    if mloc_memory is not None:
+        gate.threshold = float(threshold)
+        if gate.memory is None or getattr(gate, "_memory_src", None) is not mloc_memory:
+            gate.set_memory(mloc_memory)
+            gate._memory_src = mloc_memory
+        if mem_prompts is not None:
+            mq = np.stack([_encode_query(sentence_model, f"Prompt: {p} \n\n", device=device)[0] for p in mem_prompts])
+    else:
+        gate.memory = None
+    bank = bank_from_stored_data(stored_data, device=_device_index(device))
+    _, preds, _, scores, ids = gate.probe(bank, q, hparams.k, mem_query_embeddings=mq)
+    preds, ids = preds.cpu().tolist(), ids.cpu().tolist()
+    out = []
+    for pred, row in zip(preds, ids):
+        if pred == 0:
+            out.append((0, None))
+            continue
+        icl = [stored_data['sentences'][i] for i in row if i >= 0]
+        while len(''.join(icl)) > DEMO_CHAR_CAP:
+            del icl[-1]
+        out.append((pred, icl))
+    return out

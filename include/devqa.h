@@ -80,6 +80,8 @@ extern "C" {
 
 #define DEVQA_FORCE_FILTER (1u << 11)   /* testing/benchmark: TF32 filter + exact re-scoring also on banks the
                                            library would scan with 3xTF32 alone (fewer than 8 tiles per SM)     */
+#define DEVQA_DEBUG_TIGHT_BOUND (1u << 12) /* tests: run the filter with 1/64 of its error bound, so that the bound IS
+                                              violated and the canary (devqa_filter_bound_violations) has to catch it */
 #define DEVQA_DEBUG_FILTER_ONLY (1u << 22) /* tests: return the TF32 filter's approximate top-k as is (no exact
                                               re-scoring) so that its error bound can be checked            */
 
@@ -107,6 +109,13 @@ DEVQA_API int devqa_profile_collect(int device, double* scan_ms_total, int64_t* 
  * proof fails (heavily duplicated / clustered rows, NaN) are redone by the fp32-exact 3xTF32 scan in the same
  * call.  Returns (and resets) how many queries took that fallback on `device`; synchronises the device. */
 DEVQA_API int devqa_filter_fallbacks(int device, int64_t* count);
+/* The filter's proof rests on  u - 2E <= s <= u  (u: the scan's upper bound of a row's score, s: its exact fp32 score,
+ * E = devqa_filter_relerr(dim) * ||row|| * ||query||).  The re-scoring kernels check it for every candidate they
+ * re-score; a violation sends the query to the exact fallback and is counted here.  Returns (and resets) that counter;
+ * synchronises the device.  Expected value: 0, always. */
+DEVQA_API int devqa_filter_bound_violations(int device, int64_t* count);
+/* The relative error bound the filter uses for `dim` columns on an fp32 (DEVQA_F32) or bf16 (DEVQA_BF16) bank. */
+DEVQA_API double devqa_filter_relerr(int64_t dim, int bank_dtype);
 
 /* Debugging aid: when set to a device buffer of 16 x 256 int64, CTA 0 of the tcgen05 scan records
  * clock64() samples of its warp roles (producer, split, MMA, epilogue) into it.  NULL disables. */
@@ -167,6 +176,42 @@ DEVQA_API int devqa_bank_search_host(devqa_bank* bank, const float* queries_host
 DEVQA_API int devqa_bank_search_packed(devqa_bank* bank, const float* queries, int64_t n_queries,
                              int64_t query_ld, int top_k, unsigned flags, uint64_t* out_keys,
                              void* stream);
+
+/* Threshold-select instead of top-k (LiveEdit's hard routing, editor/vllm_editors/liveedit/liveedit.py:132-143:
+ * retrieval_map = vis_sim > vis_sim_prot over the whole pool): every row whose  score * scale > thresholds[q].
+ * One pass of the bank-streaming kernel writes the boolean mask (out_mask [n_queries, size] bytes, optional), a second
+ * small kernel compacts it: out_ids / out_scores [n_queries, cap] receive the selected rows in ASCENDING id order with
+ * their scaled scores (-1 / -inf beyond the count; rows beyond `cap` are only in the mask), out_counts [n_queries] the
+ * number of selected rows (may exceed cap).  `thresholds` is a DEVICE array: no host synchronisation, no k cap.
+ * NaN scores are not selected (torch's > is false for NaN).  Scores are bit-identical to devqa_bank_search's. */
+DEVQA_API int devqa_bank_select_above(devqa_bank* bank, const float* queries, int64_t n_queries, int64_t query_ld,
+                                      const float* thresholds, float scale, unsigned flags, uint8_t* out_mask,
+                                      int64_t* out_ids, float* out_scores, int64_t cap, int64_t* out_counts,
+                                      void* stream);
+
+/* ---- HICE scope gate (easyeditor/evaluate/multimodal_evaluate.py:382-392; easyeditor/trainer/algs/HICE.py:238-263) ----
+ * logits = relu(q/||q|| @ W_rand) @ Wo^T, preds = argmax(logits); W_rand [dim, m] (row stride w_ld), Wo [n_classes, m]
+ * (row stride wo_ld), all DEVICE fp32.  `flags`: DEVQA_NORMALIZE_QUERY | DEVQA_NOEPS reproduces the reference's
+ * q / torch.norm(q).  mem_scores (optional, device [n_queries]): best cosine similarity of each probe against the m-loc
+ * memory; a probe with mem_scores > mem_threshold is out of scope (preds = 0), as in run_classifier2.
+ * One kernel for all probes; deterministic (fixed-order reductions).  Works on the current device. */
+DEVQA_API int devqa_scope_gate(const float* queries, int64_t n_queries, int64_t query_ld, int64_t dim,
+                               const float* w_rand, int64_t w_ld, int64_t m, const float* wo, int64_t wo_ld,
+                               int n_classes, unsigned flags, const float* mem_scores, float mem_threshold,
+                               float* out_logits, int32_t* out_preds, void* stream);
+/* The whole per-probe retrieval of compute_hice_multimodal_edit_quality (multimodal_evaluate.py:503-573) for all
+ * probes of a request in ONE call on one stream: (1) the m-loc memory check -- no-eps cosine top-1 of mem_queries
+ * (NULL: of `queries`) against `memory` (NULL or empty: skipped); (2) the RanPAC scope gate on `queries` with the
+ * memory override; (3) the in-context lookup -- top_k search of `queries` over `bank` with `flags` (the reference uses
+ * DEVQA_NORMALIZE_BANK | DEVQA_NORMALIZE_QUERY | DEVQA_NOEPS, select_icl_samples :404-412).  out_mem_sim (optional)
+ * [n_queries]; out_logits [n_queries, n_classes]; out_preds [n_queries]; out_scores / out_ids [n_queries, top_k]
+ * (returned for every probe; callers use the in-scope ones, preds != 0).  No host synchronisation. */
+DEVQA_API int devqa_bank_hice_probe(devqa_bank* bank, devqa_bank* memory, const float* queries,
+                                    const float* mem_queries, int64_t n_queries, int64_t query_ld,
+                                    const float* w_rand, int64_t w_ld, int64_t m, const float* wo, int64_t wo_ld,
+                                    int n_classes, float mem_threshold, int top_k, unsigned flags,
+                                    float* out_logits, int32_t* out_preds, float* out_mem_sim,
+                                    float* out_scores, int64_t* out_ids, void* stream);
 
 /* ---- multi-GPU merge ---------------------------------------------------------------------
  * gathered: [n_lists, n_queries, top_k] packed keys, each [top_k] run sorted descending. */

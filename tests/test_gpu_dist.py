@@ -62,3 +62,37 @@ def test_two_gpu_sharded_search(tmp_path):
     import torch.multiprocessing as mp
     mp.spawn(_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
     assert all(os.path.exists(tmp_path / f"ok{r}") for r in range(2))
+
+
+def test_bank_on_device_1_while_device_0_is_current():
+    """the per-device scratch (its event in particular) must be created on the bank's device, whichever
+    device the calling thread has current -- bank_from_file(device=hparams.device) is called exactly like that."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import subprocess, sys, textwrap
+    code = textwrap.dedent(f"""
+        import sys; sys.path.insert(0, {ROOT!r})
+        import torch, devqa_b200
+        from devqa_b200 import FactBank, EditPool, LiveEditPool
+        torch.cuda.set_device(0)
+        g = torch.Generator().manual_seed(1)
+        bank = torch.randn(5000, 128, generator=g)
+        q = torch.randn(9, 128, generator=g)
+        fb1 = FactBank.from_embeddings(bank, device=1)          # first touch of device 1's scratch, device 0 current
+        s1, i1 = fb1.search(q, 8)
+        side = torch.cuda.Stream(device=1)
+        with torch.cuda.stream(side):                           # stream change -> the scratch's event is waited on
+            s1b, i1b = fb1.search(q, 8)
+        fb0 = FactBank.from_embeddings(bank, device=0)
+        s0, i0 = fb0.search(q, 8)
+        torch.cuda.synchronize(0); torch.cuda.synchronize(1)
+        assert s1.device.index == 1 and torch.equal(i1.cpu(), i0.cpu()) and torch.equal(s1.cpu(), s0.cpu())
+        assert torch.equal(i1b.cpu(), i0.cpu())
+        pool = EditPool(128, device=1); pool.append(bank[:100])
+        ids, (sims, order) = pool.recipe_retrieve(q, 4)
+        lp = LiveEditPool(4, 32, device=1); lp.append(bank[:50].reshape(50, 4, 32))
+        lp.retrieve(q[:1].reshape(1, 4, 32), torch.tensor([[0.0]]), 10.0)
+        print("ok")
+    """)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-2000:]

@@ -47,9 +47,23 @@ def _record(name, value):
         json.dump(data, open(path, "w"), indent=1)
 
 
-def relerr(d):
-    """csrc/scan.cuh tc_filter_relerr"""
-    return 1.5 * 2.0 ** -10 + d * 2.0 ** -24
+def _violations(device=0):
+    n = C.c_int64()
+    L.check(L.lib().devqa_filter_bound_violations(device, C.byref(n)))
+    return n.value
+
+
+def relerr(d, bf16=False):
+    """csrc/scan.cuh tc_filter_relerr, as the library itself reports it"""
+    return float(L.lib().devqa_filter_relerr(int(d), L.BF16 if bf16 else L.F32))
+
+
+def test_relerr_is_what_the_header_documents():
+    assert relerr(768) == pytest.approx(1.5 * 2.0 ** -10 + 2.0 ** -19 + 768 * 2.0 ** -22, rel=1e-6)
+    # bf16 has 8 significand bits: round-to-nearest is off by up to 2^-8 relative (ADVICE r1: not 2^-9)
+    assert relerr(768, bf16=True) == pytest.approx(2.0 ** -8 + 2.0 ** -19 + 768 * 2.0 ** -22, rel=1e-6)
+    x = torch.tensor([1.0 + 2.0 ** -8 + 2.0 ** -12])
+    assert abs(float(x.to(torch.bfloat16).float() - x) / float(x)) > 1.01 * 2.0 ** -9
 
 
 @pytest.mark.parametrize("n,d,nq,k,nb,nq_mode", [
@@ -116,6 +130,163 @@ def test_filter_error_bound_holds(kind):
         assert (u >= exact).all(), (kind, nb, float((exact - u).max()))
         assert (u <= exact + 2.0001 * e).all(), (kind, nb)
         assert err.max() > 1e-6          # these really are approximate scores
+    fb.close()
+
+
+# ---- the bound on constructed worst cases -----------------------------------------------------------------------
+def _bits_to_f32(bits):
+    return torch.from_numpy(np.asarray(bits, dtype=np.uint32).view(np.float32).copy())
+
+
+def _worst_case(n, nq, d, seed, bf16):
+    """Rows and queries whose per-element rounding errors all point the same way and for which Cauchy-Schwarz is
+    tight (query j is parallel to row j): every element is a power of two times a fixed mantissa,
+      fp32 bank:  row mantissa  = low 13 bits all ones (TF32 truncation loses 2^-10 relative, the maximum),
+                  query mantissa = one below the TF32 rounding midpoint (rounds DOWN by 2^-11, the maximum);
+      bf16 bank:  row = the power of two itself (exact in bf16), query mantissa = one below the bf16 midpoint
+                  (rounds down by 2^-8).
+    Exponents vary per column (8 values), so the tensor core's truncating accumulation has work to do as well."""
+    rng = np.random.default_rng(seed)
+    e = rng.integers(120, 128, size=(n, d), dtype=np.uint32)            # 2^-7 .. 2^0
+    row_m = np.uint32(0) if bf16 else np.uint32(0x1FFF)
+    q_m = np.uint32(0x7FFF) if bf16 else np.uint32(0x0FFF)
+    rows = _bits_to_f32((e << np.uint32(23)) | row_m)
+    eq = e[rng.integers(0, n, size=nq)] if nq > n else e[:nq]
+    queries = _bits_to_f32((eq << np.uint32(23)) | q_m)
+    return rows, queries
+
+
+@pytest.mark.parametrize("d", [768, 4096, 16384])
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+def test_filter_error_bound_on_the_constructed_worst_case(d, dtype):
+    """positive rows with low-13-bits-all-ones mantissas x positive queries just below the TF32
+    midpoints push the per-element error to 2^-10 + 2^-11 with Cauchy-Schwarz tight; what is left of the bound has to
+    cover the tensor core's accumulation.  Measured error / bound is recorded per case (gpurun_out/filter_error_bound.json)."""
+    bf = dtype == "bf16"
+    n, nq, k = 64, 32, 64                               # k = n: the bound of EVERY pair comes back, the parallel ones included
+    bank, q = _worst_case(n, nq, d, 1000 + d, bf)
+    fb = FactBank.from_embeddings(bank, dtype=dtype)
+    b64, q64 = bank.double().numpy(), q.double().numpy()
+    bn, qn = np.linalg.norm(b64, axis=1), np.linalg.norm(q64, axis=1)
+    for nb, nqm in ((None, None), ("eps", None)):
+        u, i = fb.search(q.cuda(), k, normalize_bank=nb, normalize_query=nqm, flags=FILTER | L.DEBUG_FILTER_ONLY)
+        u, i = u.cpu().double().numpy(), i.cpu().numpy()
+        exact = np.take_along_axis(q64 @ b64.T / (bn[None, :] if nb else 1.0), i, axis=1)
+        scale = qn[:, None] * (np.ones_like(exact) if nb else bn[i])
+        e = relerr(d, bf) * scale
+        err = np.abs(u - e - exact) / scale
+        inputs_only = (2.0 ** -8) if bf else (2.0 ** -10 + 2.0 ** -11)
+        _record(f"worstcase_{dtype}_{'cos' if nb else 'dot'}_d{d}",
+                {"max_err": float(err.max()), "bound": relerr(d, bf), "input_rounding_alone": inputs_only})
+        assert (u >= exact).all(), (d, dtype, nb, float(((exact - u) / scale).max()))
+        assert (u <= exact + 2.0001 * e).all(), (d, dtype, nb)
+        assert err.max() > 0.9 * inputs_only, "the construction is supposed to come close to the input-rounding bound"
+        assert err.max() < relerr(d, bf)
+    # and the real thing: filter + exact re-scoring equals the stream kernel, canary silent
+    _fallbacks(); _violations()
+    a = fb.search(q.cuda(), 32, normalize_bank=None, normalize_query=None, flags=FILTER)
+    assert _violations() == 0
+    _fallbacks()
+    b = fb.search(q.cuda(), 32, normalize_bank=None, normalize_query=None, flags=L.FORCE_STREAM)
+    # (row j and query j are parallel, scores of other pairs are close: the fallback may run; results must agree in ids
+    # wherever the stream kernel's scores differ)
+    sa, sb = a[0].cpu().numpy(), b[0].cpu().numpy()
+    np.testing.assert_allclose(sa, sb, rtol=1e-5)
+    fb.close()
+
+
+@pytest.mark.parametrize("kind", ["randn", "positive", "hidden", "worst"])
+@pytest.mark.parametrize("d", [36, 768, 4096])
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+def test_filter_bound_exhaustively_on_tiny_banks(kind, d, dtype):
+    """test_filter_error_bound_holds only sees rows that were RETURNED.  With N = 64 rows and
+    k = 64 the filter returns its upper bound for EVERY (row, query) pair, so every pair is held against fp64 and
+    against the stream kernel's own fp32 score (the quantity the proof is really about)."""
+    bf = dtype == "bf16"
+    n, nq = 64, 48
+    g = torch.Generator().manual_seed(7 * d + len(kind))
+    if kind == "randn":
+        bank, q = _randn(n, d, d + 1, unit=False), _randn(nq, d, d + 2, unit=False)
+    elif kind == "positive":
+        bank, q = torch.rand(n, d, generator=g) + 0.5, torch.rand(nq, d, generator=g) + 0.5
+    elif kind == "hidden":
+        bank, q = _hidden_like(n, d, d + 3), _hidden_like(nq, d, d + 4)
+    else:
+        bank, q = _worst_case(n, nq, d, d + 5, bf)
+    fb = FactBank.from_embeddings(bank, dtype=dtype)
+    stored = bank.to(torch.bfloat16).float() if bf else bank
+    b64, q64 = stored.double().numpy(), q.double().numpy()
+    bn, qn = np.linalg.norm(b64, axis=1), np.linalg.norm(q64, axis=1)
+    worst = 0.0
+    for nb, nqm in ((None, None), ("eps", "eps"), ("eps", None)):
+        u, i = fb.search(q.cuda(), n, normalize_bank=nb, normalize_query=nqm, flags=FILTER | L.DEBUG_FILTER_ONLY)
+        s, j = fb.search(q.cuda(), n, normalize_bank=nb, normalize_query=nqm, flags=L.FORCE_STREAM)
+        u, i, s, j = u.cpu().double().numpy(), i.cpu().numpy(), s.cpu().double().numpy(), j.cpu().numpy()
+        assert (np.sort(i, axis=1) == np.arange(n)[None, :]).all(), "every row must come back"
+        u_by_row = np.empty_like(u); np.put_along_axis(u_by_row, i, u, axis=1)
+        s_by_row = np.empty_like(s); np.put_along_axis(s_by_row, j, s, axis=1)
+        truth = ss.truth_scores_fp64(q, stored, normalize_bank=bool(nb), normalize_query=bool(nqm))
+        qscale = np.ones(nq) if nqm else qn
+        scale = qscale[:, None] * (np.ones((nq, n)) if nb else bn[None, :])
+        e = relerr(d, bf) * scale
+        assert (u_by_row >= truth).all(), (kind, d, dtype, nb, float(((truth - u_by_row) / scale).max()))
+        assert (u_by_row >= s_by_row).all(), (kind, d, dtype, nb)
+        assert (u_by_row <= truth + 2.0001 * e).all() and (u_by_row <= s_by_row + 2.0001 * e).all(), (kind, d, dtype, nb)
+        worst = max(worst, float((np.abs(u_by_row - e - truth) / scale).max()))
+    _record(f"exhaustive_{kind}_{dtype}_d{d}", {"max_err": worst, "bound": relerr(d, bf), "pairs": 3 * n * nq})
+    fb.close()
+
+
+def test_canary_catches_a_violated_bound():
+    """DEVQA_DEBUG_TIGHT_BOUND runs the filter with 1/64 of its error bound: exact scores then do fall outside
+    [u - 2E, u], the re-scoring kernels must notice, count it, and send the query to the exact fallback."""
+    g = torch.Generator().manual_seed(5)
+    bank, q = torch.rand(30000, 768, generator=g) + 0.5, torch.rand(40, 768, generator=g) + 0.5
+    fb = FactBank.from_embeddings(bank)
+    for n_rows in (30000, 3000):                       # refine from the per-CTA lists / from the merged list
+        fb.truncate(n_rows)
+        _fallbacks(); _violations()
+        s, i = fb.search(q.cuda(), 16, flags=FILTER | L.DEBUG_TIGHT_BOUND)
+        assert _violations() > 0
+        assert _fallbacks() > 0
+        fb.search(q.cuda(), 16, flags=FILTER)
+        assert _violations() == 0
+    fb.close()
+
+
+@pytest.mark.parametrize("kind", ["positive", "hidden", "constant_offset"])
+def test_bf16_filter_error_bound_holds(kind):
+    """the bf16 filter's bound was 2x too small; adversarial inputs for it are queries whose
+    components carry aligned rounding errors (constant / offset hidden states) against all-positive rows."""
+    g = torch.Generator().manual_seed(77)
+    d = 768
+    if kind == "positive":
+        bank, q = torch.rand(4000, d, generator=g) + 0.5, torch.rand(48, d, generator=g) + 0.5
+    elif kind == "hidden":
+        bank, q = _hidden_like(4000, d, 13).abs(), _hidden_like(48, d, 14).abs()
+    else:
+        bank = torch.rand(4000, d, generator=g) + 0.5
+        q = (1.0 + 2.0 ** -8 + 2.0 ** -12) * torch.ones(48, d) * torch.exp2(torch.randint(-3, 1, (48, 1), generator=g).float())
+    fb = FactBank.from_embeddings(bank, dtype="bf16")
+    stored = bank.to(torch.bfloat16).float()
+    for nb, nqm in (("eps", "eps"), (None, None)):
+        u, i = fb.search(q.cuda(), 32, normalize_bank=nb, normalize_query=nqm, flags=FILTER | L.DEBUG_FILTER_ONLY)
+        u, i = u.cpu().double().numpy(), i.cpu().numpy()
+        truth = ss.truth_scores_fp64(q, stored, normalize_bank=bool(nb), normalize_query=bool(nqm))
+        exact = np.take_along_axis(truth, i, axis=1)
+        bn = np.linalg.norm(stored.double().numpy(), axis=1)
+        qn = np.linalg.norm(q.double().numpy(), axis=1)
+        scale = np.ones_like(exact) if nb else bn[i] * qn[:, None]
+        e = relerr(d, True) * scale
+        err = np.abs(u - e - exact) / scale
+        _record(f"bf16_{kind}_{'cos' if nb else 'dot'}_d{d}", {"max_err": float(err.max()), "bound": relerr(d, True)})
+        assert (u >= exact).all(), (kind, nb, float(((exact - u) / scale).max()))
+        assert (u <= exact + 2.0001 * e).all(), (kind, nb)
+    _violations()
+    a = fb.search(q.cuda(), 32, flags=FILTER)
+    assert _violations() == 0
+    b = fb.search(q.cuda(), 32, flags=L.FORCE_STREAM)
+    assert torch.equal(a[1], b[1]) and torch.equal(a[0], b[0])
     fb.close()
 
 

@@ -3,6 +3,7 @@ import pytest
 import torch
 import torch.nn.functional as F
 
+import devqa_b200
 from devqa_b200 import EditPool
 
 pytestmark = pytest.mark.gpu
@@ -121,6 +122,69 @@ def test_liveedit_hard_routing_mask(m):
         assert len(pool) == 10 and bool((pool.retrieve(ivr, vis_sim_prot, scale)[0] < 10).all())
 
 
+def test_liveedit_retrieval_map_without_host_sync():
+    """The mask itself (retrieval_map) from a DEVICE threshold; whole pool passing (no k cap)."""
+    from devqa_b200 import LiveEditPool
+    g = _g(77)
+    eqe_n, md, scale, m = 4, 256, 10.0, 5000
+    pool_ref = torch.randn(m, eqe_n, md, generator=g) / md ** 0.5
+    pool = LiveEditPool(eqe_n, md)
+    pool.append(pool_ref)
+    ivr = torch.randn(1, eqe_n, md, generator=g)
+    vis_sim = torch.einsum('bed,med->bme', ivr, pool_ref).mean(2) * scale
+    for thr in (0.0, float(vis_sim.min()) - 1.0, float(vis_sim.max()) + 1.0):
+        prot = torch.tensor([[thr]], device="cuda")
+        got = pool.retrieval_map(ivr, prot, scale).cpu()
+        want = (vis_sim > thr)[0]
+        safe = (vis_sim[0] - thr).abs() > 1e-5
+        assert got.dtype == torch.bool and got.shape == (m,)
+        assert torch.equal(got[safe], want[safe])
+        ids, sims = pool.retrieve(ivr, prot, scale)
+        assert torch.equal(torch.nonzero(got)[:, 0], ids.cpu())           # ascending ids == pool[retrieval_map] order
+    assert len(pool.retrieve(ivr, torch.tensor([[float(vis_sim.min()) - 1.0]]), scale)[0]) == m
+
+
+@pytest.mark.parametrize("n,d,nq,dtype,nb", [(1, 64, 1, "fp32", None), (7, 36, 3, "fp32", "eps"), (3001, 384, 5, "fp32", "eps"),
+                                            (20000, 768, 9, "bf16", "noeps"), (70000, 101, 2, "fp32", None)])
+def test_select_above_matches_the_search_scores_bit_for_bit(n, d, nq, dtype, nb):
+    """devqa_bank_select_above: per-query device thresholds, cap smaller than the count, scores identical to
+    devqa_bank_search's (the stream kernel's arithmetic), NaN rows never selected."""
+    import ctypes as C
+    from devqa_b200 import FactBank, norm_flags
+    L = devqa_b200._lib
+    g = _g(n + d)
+    bank = torch.randn(n, d, generator=g)
+    if n > 100:
+        bank[5, 0] = float("nan")
+    q = torch.randn(nq, d, generator=g)
+    fb = FactBank.from_embeddings(bank, dtype=dtype)
+    k = min(n, 64)
+    s_ref, i_ref = fb.search(q.cuda(), k, normalize_bank=nb, normalize_query=nb, flags=L.FORCE_STREAM)
+    finite = torch.where(torch.isnan(s_ref), torch.full_like(s_ref, float("inf")), s_ref)
+    # threshold = midway between the 10th and 11th best finite score -> exactly the finite part of the top-10 passes
+    fin_sorted = torch.sort(torch.where(torch.isnan(s_ref), torch.full_like(s_ref, -float("inf")), s_ref), dim=1, descending=True)[0]
+    cut = min(10, k - 1)
+    thr = ((fin_sorted[:, cut - 1] + fin_sorted[:, cut]) / 2 if k > 1 else fin_sorted[:, 0] - 1.0).contiguous()
+    cap = 6
+    mask = torch.empty((nq, n), dtype=torch.uint8, device="cuda")
+    ids = torch.empty((nq, cap), dtype=torch.int64, device="cuda")
+    sims = torch.empty((nq, cap), dtype=torch.float32, device="cuda")
+    cnt = torch.empty((nq,), dtype=torch.int64, device="cuda")
+    qd = q.cuda().contiguous()
+    L.check(L.lib().devqa_bank_select_above(fb._h, qd.data_ptr(), nq, d, thr.data_ptr(), 1.0, norm_flags(nb, nb),
+                                            mask.data_ptr(), ids.data_ptr(), sims.data_ptr(), cap, cnt.data_ptr(),
+                                            torch.cuda.current_stream().cuda_stream))
+    for j in range(nq):
+        want = sorted(int(i) for s, i in zip(s_ref[j].tolist(), i_ref[j].tolist()) if s == s and s > float(thr[j]))
+        assert int(cnt[j]) == len(want) == int(mask[j].sum())
+        assert torch.nonzero(mask[j])[:, 0].tolist() == want
+        assert ids[j].tolist() == (want + [-1] * cap)[:cap]
+        lookup = dict(zip(i_ref[j].tolist(), s_ref[j].tolist()))
+        for c in range(min(cap, len(want))):
+            assert float(sims[j, c]) == lookup[want[c]]                  # bit-identical to the search's score
+    fb.close()
+
+
 def test_hice_memory_gate():
     """HICE.py:238-250: sim = q/||q|| @ (mem/||mem||).T; in scope iff sim.max() > 0.81."""
     g = _g(9)
@@ -139,3 +203,104 @@ def test_hice_memory_gate():
         assert gate == bool(sim.max() > 0.81)
         assert abs(best - float(sim.max())) < 1e-5
     assert pool.hice_memory_gate(mem[17])[0] is True
+
+
+# ---- N4: HICE scope gate + memory check + lookup in one call -------------------------------------------------------
+def _ranpac_reference(q, W_rand, Wo):
+    """multimodal_evaluate.py:387-391"""
+    query_fea = q / torch.norm(q, p=2, dim=-1, keepdim=True)
+    query_fea_h = torch.nn.functional.relu(query_fea @ W_rand)
+    logits = query_fea_h @ Wo.T
+    return logits, torch.max(logits, dim=-1)[1]
+
+
+@pytest.mark.parametrize("d,M,C,n", [(384, 10000, 2, 11), (384, 1000, 2, 1), (100, 777, 3, 40), (768, 4096, 2, 17)])
+def test_scope_gate_matches_the_torch_composition(d, M, C, n):
+    from devqa_b200 import ScopeGate
+    g = _g(d + M)
+    W_rand = torch.randn(d, M, generator=g)
+    Wo = torch.randn(C, M, generator=g) / M ** 0.5
+    q = torch.randn(n, d, generator=g) * 3.0
+    gate = ScopeGate(Wo, W_rand)
+    logits, preds = gate.predict(q)
+    ref_logits, ref_preds = _ranpac_reference(q.double(), W_rand.double(), Wo.double())
+    torch.testing.assert_close(logits.cpu().double(), ref_logits, rtol=1e-5, atol=1e-5 * float(ref_logits.abs().max()))
+    top2 = torch.topk(ref_logits, 2, dim=1)[0] if C > 1 else None
+    safe = (top2[:, 0] - top2[:, 1]) > 1e-4 * ref_logits.abs().max()
+    assert torch.equal(preds.cpu()[safe], ref_preds[safe])
+    again = gate.predict(q)
+    assert torch.equal(again[0], logits) and torch.equal(again[1], preds)        # deterministic
+
+
+def test_our_predict_domain_mirror():
+    """Same signature / return value as multimodal_evaluate.py:382."""
+    from devqa_b200 import retrieval
+    from oracle.st_shim import StubEncoder
+    g = _g(3)
+    enc = StubEncoder()
+    W_rand = torch.randn(384, 2000, generator=g)
+    Wo = torch.randn(2, 2000, generator=g)
+    logits, preds = retrieval.our_predict_domain("what is on the table", "a cat", enc, Wo, W_rand, "cuda:0")
+    q = torch.tensor(enc.encode("New Fact: what is on the table a cat\nPrompt: what is on the table a cat\n\n"))
+    ref_logits, ref_preds = _ranpac_reference(q[None].double(), W_rand.double(), Wo.double())
+    torch.testing.assert_close(logits.cpu().double(), ref_logits[0], rtol=1e-5, atol=1e-4)
+    assert int(preds) == int(ref_preds[0]) and logits.shape == (2,)
+
+
+def test_hice_probe_fuses_gate_memory_and_lookup():
+    """devqa_bank_hice_probe == gate (torch) + run_classifier2's memory override + select_icl_samples' search."""
+    from devqa_b200 import FactBank, ScopeGate
+    L = devqa_b200._lib
+    g = _g(11)
+    d, M, n, k = 384, 5000, 11, 16
+    W_rand = torch.randn(d, M, generator=g)
+    Wo = torch.randn(2, M, generator=g) / M ** 0.5
+    bank = torch.randn(20000, d, generator=g)
+    mem = [torch.randn(1, d, generator=g) for _ in range(60)]
+    q = torch.randn(n, d, generator=g)
+    mq = torch.randn(n, d, generator=g)
+    mq[3] = mem[7][0] + 0.05 * torch.randn(d, generator=g)              # probe 3 is a remembered m-loc sample
+    fb = FactBank.from_embeddings(bank)
+    gate = ScopeGate(Wo, W_rand, mloc_memory={'embeddings': mem}, threshold=0.81)
+    logits, preds, mem_sim, scores, ids = gate.probe(fb, q, k, mem_query_embeddings=mq)
+    ref_logits, ref_preds = _ranpac_reference(q.double(), W_rand.double(), Wo.double())
+    memory_fea = torch.cat(mem, 0)
+    memory_fea = memory_fea / torch.norm(memory_fea, p=2, dim=-1).unsqueeze(-1)
+    sim = (mq / torch.norm(mq, p=2, dim=-1, keepdim=True)) @ memory_fea.T
+    want = ref_preds.clone()
+    want[sim.max(1)[0] > 0.81] = 0
+    assert float(sim[3].max()) > 0.81 and int(preds[3]) == 0
+    assert torch.equal(preds.cpu(), want)
+    torch.testing.assert_close(mem_sim.cpu(), sim.max(1)[0], rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(logits.cpu().double(), ref_logits, rtol=1e-5, atol=1e-5)
+    s2, i2 = fb.search(q.cuda(), k, normalize_bank="noeps", normalize_query="noeps")
+    assert torch.equal(ids, i2) and torch.equal(scores, s2)
+    # no memory: NaN similarities, classifier decides alone
+    gate2 = ScopeGate(Wo, W_rand)
+    _, p2, ms2, _, _ = gate2.probe(fb, q, k)
+    assert torch.isnan(ms2).all() and torch.equal(p2.cpu(), ref_preds)
+    fb.close()
+
+
+def test_hice_probe_batch_mirror():
+    from devqa_b200 import retrieval
+    from oracle.st_shim import StubEncoder
+    import types
+    g = _g(21)
+    enc = StubEncoder()
+    sents = [f"fact number {i} " + "x" * 300 for i in range(500)]
+    emb = torch.tensor(enc.encode(sents))
+    stored = {"sentences": sents, "embeddings": emb}
+    W_rand = torch.randn(384, 3000, generator=g)
+    Wo = torch.randn(2, 3000, generator=g)
+    hp = types.SimpleNamespace(k=16, device=0)
+    probes = [(f"fact number {i}", "x") for i in (3, 77, 123, 400)]
+    got = retrieval.hice_probe_batch(probes, stored, enc, "cuda:0", hp, Wo, W_rand)
+    for (prompt, target), (pred, icl) in zip(probes, got):
+        _, ref_pred = retrieval.our_predict_domain(prompt, target, enc, Wo, W_rand, "cuda:0")
+        assert pred == int(ref_pred)
+        if pred != 0:
+            assert icl == retrieval.select_icl_samples(prompt, target, stored, enc, "cuda:0", hp)
+            assert len(''.join(icl)) <= 2500
+        else:
+            assert icl is None

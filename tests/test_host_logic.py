@@ -163,6 +163,37 @@ def test_bank_cache_reuses_and_invalidates(golden, oracle_backed):
     assert retrieval.bank_from_stored_data(stored) is not b1
 
 
+def test_bank_cache_never_serves_a_stale_ndarray(golden, oracle_backed):
+    """ndarrays have no version counter, so an equal-length in-place edit must not be served from a stale
+    resident bank; pin_stored_data opts in to reuse."""
+    emb = np.array(golden["embeddings"], copy=True)
+    stored = {"sentences": golden["bank"]["sentences"], "embeddings": emb}
+    b1 = retrieval.bank_from_stored_data(stored)
+    emb[0] *= -1.0
+    b2 = retrieval.bank_from_stored_data(stored)
+    assert b2 is not b1 and float(b2.emb[0, 0]) == float(emb[0, 0])
+    p1 = retrieval.pin_stored_data(stored)
+    assert retrieval.bank_from_stored_data(stored) is p1
+    assert retrieval.pin_stored_data(stored) is not p1
+
+
+def test_device_spellings_agree():
+    """'cuda:1'.index is a bound method (truthy); every cache key goes through _device_index."""
+    import torch as _t
+    assert retrieval._device_index("cuda:1") == 1 and retrieval._device_index(1) == 1
+    assert retrieval._device_index(_t.device("cuda", 1)) == 1 and retrieval._device_index("cuda") == 0
+
+
+def test_dead_owners_are_evicted(golden, oracle_backed):
+    emb = torch.tensor(golden["embeddings"])
+    retrieval.bank_from_stored_data({"sentences": golden["bank"]["sentences"], "embeddings": emb})
+    assert len(retrieval._object_banks) == 1
+    del emb
+    import gc; gc.collect()
+    retrieval.bank_from_stored_data({"sentences": golden["bank"]["sentences"], "embeddings": torch.tensor(golden["embeddings"])})
+    assert len(retrieval._object_banks) == 1
+
+
 def test_apply_ike_requires_train_ds(golden):
     with pytest.raises(AssertionError):
         retrieval.apply_ike_to_multimodal_model(None, None, {"prompt": "a", "target": "b"}, types.SimpleNamespace())
