@@ -659,12 +659,16 @@ int devqa_profile_collect(int device, double* scan_ms_total, int64_t* scan_launc
   return DEVQA_OK;
 }
 
-int devqa_search_raw(const void* bank, int bank_dtype, int64_t n_rows, int64_t dim, int64_t bank_ld,
-                     const float* queries, int64_t n_queries, int64_t query_ld, int top_k, unsigned flags,
-                     int64_t id_base, float* out_scores, int64_t* out_ids, void* stream_) {
+static int search_raw_common(const void* bank, int bank_dtype, int64_t n_rows, int64_t dim, int64_t bank_ld,
+                             const float* queries, int64_t n_queries, int64_t query_ld, int top_k, unsigned flags,
+                             int64_t id_base, const float* row_sumsq, const uint32_t* max_sumsq_bits,
+                             float* out_scores, int64_t* out_ids, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   SearchArgs a{bank, bank_dtype, n_rows, dim, bank_ld, queries, n_queries, query_ld, top_k, flags,
                IdMap{id_base, 0, 0, 1}};
+  // fp32 banks only: for bf16 banks cached norms also enter the exact variants' final scores, and the stream
+  // kernel would not use them -- results must not depend on which kernel served the call
+  if (row_sumsq && max_sumsq_bits && bank_dtype == DEVQA_F32) { a.row_sumsq = row_sumsq; a.max_sumsq = max_sumsq_bits; }
   int rc = validate(a);
   if (rc) return rc;
   DEVQA_REQUIRE(n_queries == 0 || (out_scores && out_ids), "output pointers are null");
@@ -677,6 +681,29 @@ int devqa_search_raw(const void* bank, int bank_dtype, int64_t n_rows, int64_t d
   if ((rc = scratch_enter(s, stream))) return rc;
   if ((rc = run_search(s, a, nullptr, out_scores, out_ids, stream))) return rc;
   return scratch_leave(s, stream);
+}
+
+int devqa_search_raw(const void* bank, int bank_dtype, int64_t n_rows, int64_t dim, int64_t bank_ld,
+                     const float* queries, int64_t n_queries, int64_t query_ld, int top_k, unsigned flags,
+                     int64_t id_base, float* out_scores, int64_t* out_ids, void* stream_) {
+  return search_raw_common(bank, bank_dtype, n_rows, dim, bank_ld, queries, n_queries, query_ld, top_k, flags, id_base,
+                           nullptr, nullptr, out_scores, out_ids, stream_);
+}
+
+int devqa_search_raw_ex(const void* bank, int bank_dtype, int64_t n_rows, int64_t dim, int64_t bank_ld,
+                        const float* queries, int64_t n_queries, int64_t query_ld, int top_k, unsigned flags,
+                        int64_t id_base, const float* row_sumsq, const uint32_t* max_sumsq_bits, float* out_scores,
+                        int64_t* out_ids, void* stream_) {
+  return search_raw_common(bank, bank_dtype, n_rows, dim, bank_ld, queries, n_queries, query_ld, top_k, flags, id_base,
+                           row_sumsq, max_sumsq_bits, out_scores, out_ids, stream_);
+}
+
+int devqa_row_sumsq(const void* bank, int bank_dtype, int64_t n_rows, int64_t dim, int64_t bank_ld, float* out_sumsq,
+                    uint32_t* out_max_bits, void* stream_) {
+  DEVQA_REQUIRE(n_rows >= 0 && dim > 0 && bank_ld >= dim, "bad shape");
+  DEVQA_REQUIRE(bank_dtype == DEVQA_F32 || bank_dtype == DEVQA_BF16, "unknown bank dtype %d", bank_dtype);
+  DEVQA_REQUIRE(n_rows == 0 || (bank && out_sumsq), "null pointers");
+  return row_sumsq_launch(bank, bank_dtype, n_rows, dim, bank_ld, out_sumsq, static_cast<cudaStream_t>(stream_), out_max_bits);
 }
 
 int devqa_normalize_rows(const float* src, int64_t src_ld, float* dst, int64_t dst_ld, int64_t n_rows, int64_t dim,

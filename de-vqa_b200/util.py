@@ -17,6 +17,7 @@ accepted and ignored (the scan never materialises a score matrix).
 """
 from __future__ import annotations
 
+import weakref
 from typing import Callable, List
 
 import numpy as np
@@ -54,6 +55,43 @@ def _cuda_f32(t: torch.Tensor, device=None) -> torch.Tensor:
 
 def _ld(t: torch.Tensor) -> int:
     return t.stride(0) if t.shape[0] > 1 else t.shape[1]
+
+
+# ---- side information about caller-owned banks ----------------------------------------------------------------------
+# The TF32 filter needs ||row||^2 per row (and their maximum) to bound its error.  A FactBank caches them on append;
+# for a caller-owned tensor they are computed once per (storage, view, version) by one extra pass over the bank and
+# kept for as long as the storage lives.  torch bumps a tensor's version counter on every in-place op (views share
+# it), which is what invalidates an entry; a storage that dies takes its entries with it (weakref).
+_NORM_CACHE_MIN_BYTES = 32 << 20          # below this the whole search is launch-latency bound anyway
+_norm_cache: dict = {}
+
+
+def _cached_row_norms(corpus: torch.Tensor):
+    """(row_sumsq device pointer, max-bits device pointer) for an fp32 CUDA corpus, or (None, None)."""
+    if corpus.dtype != torch.float32 or corpus.numel() * 4 < _NORM_CACHE_MIN_BYTES:
+        return None, None
+    storage = corpus.untyped_storage()
+    sid = storage._cdata
+    view = (corpus.data_ptr(), tuple(corpus.shape), tuple(corpus.stride()))
+    entry = _norm_cache.get(sid)
+    if entry is None or entry[0]() is not storage:
+        def _drop(_ref, sid=sid):
+            _norm_cache.pop(sid, None)
+        try:
+            entry = _norm_cache[sid] = (weakref.ref(storage, _drop), {})
+        except TypeError:
+            return None, None
+    hit = entry[1].get(view)
+    if hit is None or hit[0] != corpus._version:
+        n = corpus.shape[0]
+        side = torch.zeros(n + 2, dtype=torch.float32, device=corpus.device)     # [n] sums, then the max word
+        L.check(L.lib().devqa_row_sumsq(corpus.data_ptr(), L.F32, n, corpus.shape[1], _ld(corpus), side.data_ptr(),
+                                        side.data_ptr() + 4 * n, _stream_ptr(corpus.device.index)))
+        if len(entry[1]) >= 8:
+            entry[1].clear()
+        hit = entry[1][view] = (corpus._version, side)
+    side = hit[1]
+    return side.data_ptr(), side.data_ptr() + 4 * corpus.shape[0]
 
 
 def normalize_embeddings(embeddings: torch.Tensor) -> torch.Tensor:
@@ -107,9 +145,12 @@ def semantic_search_arrays(query_embeddings, corpus_embeddings, top_k: int = 10,
     scores = torch.empty((nq, kk), dtype=torch.float32, device=corpus.device)
     ids = torch.empty((nq, kk), dtype=torch.int64, device=corpus.device)
     with torch.cuda.device(corpus.device):
-        L.check(L.lib().devqa_search_raw(corpus.data_ptr(), L.F32, n, corpus.shape[1], _ld(corpus),
-                                         queries.data_ptr(), nq, _ld(queries), kk, nflags | flags, 0,
-                                         scores.data_ptr(), ids.data_ptr(), _stream_ptr(corpus.device.index)))
+        # batches the tensor-core path serves: hand it ||row||^2 so that it can filter (see _cached_row_norms)
+        ss_ptr, max_ptr = _cached_row_norms(corpus) if (nq > 2 and kk <= 64) else (None, None)
+        L.check(L.lib().devqa_search_raw_ex(corpus.data_ptr(), L.F32, n, corpus.shape[1], _ld(corpus),
+                                            queries.data_ptr(), nq, _ld(queries), kk, nflags | flags, 0,
+                                            ss_ptr, max_ptr, scores.data_ptr(), ids.data_ptr(),
+                                            _stream_ptr(corpus.device.index)))
     return scores, ids
 
 

@@ -131,6 +131,21 @@ DEVQA_API int devqa_search_raw(const void* bank, int bank_dtype, int64_t n_rows,
                      unsigned flags, int64_t id_base, float* out_scores, int64_t* out_ids,
                      void* stream);
 
+/* The same with side information about the caller-owned bank: row_sumsq [n_rows] = ||row||^2 per row and
+ * max_sumsq_bits = the bit pattern of their maximum (both DEVICE memory, e.g. from devqa_row_sumsq, NULL = none).
+ * With it an fp32 bank is searched exactly like a library-owned one -- the TF32 filter + exact re-scoring also for
+ * un-normalised dot scores (the reference's  normalise first, then semantic_search(q, bank, dot_score)  pattern,
+ * dataset/vllm.py:66-68,104).  Results are bit-identical to devqa_search_raw's; the side information only decides
+ * how fast they arrive, but it MUST describe the bank as it is now (a stale array can lose rows). */
+DEVQA_API int devqa_search_raw_ex(const void* bank, int bank_dtype, int64_t n_rows, int64_t dim, int64_t bank_ld,
+                        const float* queries, int64_t n_queries, int64_t query_ld, int top_k,
+                        unsigned flags, int64_t id_base, const float* row_sumsq,
+                        const uint32_t* max_sumsq_bits, float* out_scores, int64_t* out_ids, void* stream);
+/* ||row||^2 of every row of a caller-owned bank (one warp per row): out_sumsq [n_rows]; out_max_bits (optional) is a
+ * device word the caller zeroed, which receives the bit pattern of the largest sum (atomicMax). */
+DEVQA_API int devqa_row_sumsq(const void* bank, int bank_dtype, int64_t n_rows, int64_t dim, int64_t bank_ld,
+                              float* out_sumsq, uint32_t* out_max_bits, void* stream);
+
 /* Stand-alone row normalisation, dst = src / max(||src||_2, 1e-12) (or / ||src|| with
  * DEVQA_NOEPS): util.normalize_embeddings (dataset/vllm.py:66,104,117).  dst may equal src.
  * The search entry points fuse normalisation and do not need this.                        */

@@ -24,6 +24,12 @@ executes them in a namespace where
 
 Outputs: ``evqa_bank.npz`` (bank embeddings) and ``evqa_golden.json`` (bank text
 columns, queries, and the reference functions' outputs).
+
+Level-0 call trace (``evqa_trace.json`` + ``evqa_trace.npz``): while the reference bodies run, every call they make
+into ``util.*`` is recorded -- which reference function made it, the exact tensors it passed (query, bank, kwargs)
+and the value it got back.  ``tests/test_gpu_parity.py::test_level0_call_trace_replay`` replays those calls
+against ``devqa_b200.util`` on the GPU: the drop-in boundary exercised with the reference's own arguments, without
+any reference source in the repo.  Distinct arrays are stored once (keyed by sha256).
 """
 import ast
 import builtins
@@ -87,7 +93,46 @@ class _TorchProxy(types.ModuleType):
         return torch.device("cpu")
 
 
+class TraceUtil:
+    """``util`` as the reference bodies see it: the oracle, with every call recorded."""
+
+    def __init__(self, inner):
+        self.inner = inner
+        self.site = "?"
+        self.calls = []
+        self.arrays = {}
+        self.dot_score = inner.dot_score
+        self.cos_sim = inner.cos_sim
+
+    def _key(self, t):
+        import hashlib
+        a = np.ascontiguousarray(torch.as_tensor(t).detach().cpu().numpy().astype(np.float32))
+        k = "a" + hashlib.sha256(a.tobytes() + str(a.shape).encode()).hexdigest()[:16]
+        self.arrays.setdefault(k, a)
+        return k
+
+    def normalize_embeddings(self, x):
+        out = self.inner.normalize_embeddings(x)
+        self.calls.append({"site": self.site, "fn": "normalize_embeddings", "input": self._key(x), "output": self._key(out)})
+        return out
+
+    def semantic_search(self, query_embeddings, corpus_embeddings, query_chunk_size=100, corpus_chunk_size=500000,
+                        top_k=10, score_function=None):
+        kw = {} if score_function is None else {"score_function": score_function}
+        hits = self.inner.semantic_search(query_embeddings, corpus_embeddings, query_chunk_size, corpus_chunk_size,
+                                          top_k, **kw)
+        name = "cos_sim" if score_function is None else getattr(score_function, "__name__", "?")
+        self.calls.append({"site": self.site, "fn": "semantic_search", "query": self._key(query_embeddings),
+                           "corpus": self._key(corpus_embeddings), "top_k": int(top_k), "score_function": name,
+                           "query_ndim": int(torch.as_tensor(query_embeddings).dim()),
+                           "result": [[[h["corpus_id"], h["score"]] for h in row] for row in hits]})
+        return hits
+
+
 def main():
+    global oracle_util
+    plain_oracle = oracle_util
+    tracer = oracle_util = TraceUtil(plain_oracle)          # every namespace below hands the reference THIS util
     shim = st_shim.install(oracle_util)
     tproxy = _TorchProxy()
     tmp = tempfile.mkdtemp(prefix="devqa_golden_")
@@ -132,14 +177,16 @@ def main():
     exec(load_def("dataset/vllm.py", "init_retrieval", cls="BaseVLLMEditData"), ns_ds)
     exec(load_def("dataset/vllm.py", "finds_sim", cls="BaseVLLMEditData"), ns_ds)
     self_obj = types.SimpleNamespace()
+    tracer.site = "dataset/vllm.py:89 init_retrieval"
     ns_ds["init_retrieval"](self_obj, types="vqa")
     finds = []
     for r in evalq:
         for trg in (r['pred'], r['alt']):
+            tracer.site = "dataset/vllm.py:65 finds_sim"
             ex, img = ns_ds["finds_sim"](self_obj, r['src'], trg)
-            q = oracle_util.normalize_embeddings(torch.tensor(encoder.encode(r['src'])).unsqueeze(0))
-            hits = oracle_util.semantic_search(q, torch.as_tensor(self_obj.stored_embeddings),
-                                               score_function=oracle_util.dot_score, top_k=5)[0]
+            q = plain_oracle.normalize_embeddings(torch.tensor(encoder.encode(r['src'])).unsqueeze(0))
+            hits = plain_oracle.semantic_search(q, torch.as_tensor(self_obj.stored_embeddings),
+                                                score_function=plain_oracle.dot_score, top_k=5)[0]
             finds.append({"src": r['src'], "trg": trg, "example": list(ex), "image": img,
                           "hit_ids": [h["corpus_id"] for h in hits],
                           "hit_scores": [h["score"] for h in hits]})
@@ -158,9 +205,12 @@ def main():
     lookups = []
     for r in evalq[:12]:
         req = {"prompt": r['src'], "target": r['alt']}
+        tracer.site = "easyeditor/models/ike/ike_main.py:171 apply_ike_to_multimodal_model"
         ike = ns_ike["apply_ike_to_multimodal_model"](None, None, req, hparams, train_ds=records)
+        tracer.site = "easyeditor/models/ike/ike_main.py:210 apply_hice_to_multimodal_model"
         hice = ns_ike["apply_hice_to_multimodal_model"](None, None, req, hparams, train_ds=records,
                                                         sentence_model=encoder, stored_data=stored)
+        tracer.site = "easyeditor/evaluate/multimodal_evaluate.py:395 select_icl_samples"
         sel = ns_ev["select_icl_samples"](r['src'], r['alt'], stored, encoder, "cpu", hparams)
         hp40 = types.SimpleNamespace(**{**vars(hparams), "k": 40})   # long enough to hit the 2500-char cap
         sel40 = ns_ev["select_icl_samples"](r['src'], r['alt'], stored, encoder, "cpu", hp40)
@@ -185,6 +235,13 @@ def main():
                    "k": K_DEMOS, "records": records,
                    "bank": {"sentences": bank["sentences"], "images": bank["images"], "prompts": bank["prompts"]},
                    "finds_sim": finds, "lookups": lookups}, f, indent=1, ensure_ascii=False)
+    np.savez_compressed(os.path.join(HERE, "evqa_trace.npz"), **tracer.arrays)
+    with open(os.path.join(HERE, "evqa_trace.json"), "w") as f:
+        json.dump({"generator": "tests/golden/make_golden.py (TraceUtil)",
+                   "what": "every util.* call the reference's own function bodies made while the golden file was "
+                           "generated: arguments (arrays in evqa_trace.npz, keyed by sha256) and returned value",
+                   "calls": tracer.calls}, f, indent=0)
+    print("trace:", len(tracer.calls), "util calls,", len(tracer.arrays), "distinct arrays")
     st_shim.uninstall()
     print("wrote", len(bank["sentences"]), "bank rows,", len(finds), "finds_sim cases,", len(lookups), "lookups")
 
