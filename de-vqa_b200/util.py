@@ -136,7 +136,10 @@ def semantic_search_arrays(query_embeddings, corpus_embeddings, top_k: int = 10,
     queries = _matrix(query_embeddings)
     if corpus.dim() != 2 or queries.dim() != 2 or corpus.shape[1] != queries.shape[1]:
         raise ValueError(f"shape mismatch: queries {tuple(queries.shape)} vs corpus {tuple(corpus.shape)}")
+    given = corpus
     corpus = _cuda_f32(corpus)
+    # norms are cached only for the caller's own resident tensor (an uploaded / re-laid-out temporary dies with this call)
+    resident = given.is_cuda and corpus.data_ptr() == given.data_ptr()
     queries = _cuda_f32(queries, device=corpus.device)      # upstream moves the query to the corpus device
     n, nq = corpus.shape[0], queries.shape[0]
     if n == 0:
@@ -146,7 +149,7 @@ def semantic_search_arrays(query_embeddings, corpus_embeddings, top_k: int = 10,
     ids = torch.empty((nq, kk), dtype=torch.int64, device=corpus.device)
     with torch.cuda.device(corpus.device):
         # batches the tensor-core path serves: hand it ||row||^2 so that it can filter (see _cached_row_norms)
-        ss_ptr, max_ptr = _cached_row_norms(corpus) if (nq > 2 and kk <= 64) else (None, None)
+        ss_ptr, max_ptr = _cached_row_norms(corpus) if (resident and nq > 2 and kk <= 64) else (None, None)
         L.check(L.lib().devqa_search_raw_ex(corpus.data_ptr(), L.F32, n, corpus.shape[1], _ld(corpus),
                                             queries.data_ptr(), nq, _ld(queries), kk, nflags | flags, 0,
                                             ss_ptr, max_ptr, scores.data_ptr(), ids.data_ptr(),
