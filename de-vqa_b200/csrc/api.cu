@@ -24,6 +24,10 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+bool pdl_enabled() {
+  static const bool on = getenv("DEVQA_PDL") == nullptr || atoi(getenv("DEVQA_PDL")) != 0;
+  return on;
+}
 
 // ---- per-device scratch ---------------------------------------------------------------------------
 // Candidate lists of the scan kernels, pinned staging for the _host entry points.  One search runs
@@ -185,6 +189,11 @@ struct FilterSide {
   uint32_t* gmax = nullptr;      // [Q padded, kGmaxStride] per-CTA best upper bound per query (threshold exchange)
   int kp = 0;                    // K': capacity of the merged candidate list
   bool merge = true;             // in: merge the per-CTA lists into akeys (false: refine reads the lists themselves)
+  // one-shot mode (short scans, one tile per CTA): the scan emits its candidates straight into ocand
+  uint32_t* gbar = nullptr;      // [2 * 64] arrival counters  } zeroed together by the query-prep kernel
+  uint32_t* ocount = nullptr;    // [Q] candidates per query   }
+  uint64_t* ocand = nullptr;     // [Q, kOneshotCap]
+  bool oneshot = false;          // out: the scan ran in one-shot mode (refine reads ocand / ocount)
   int n_lists = 0;               // out: per-CTA lists per query
   int kcap = 0;                  // out: capacity of each
 };
@@ -202,8 +211,14 @@ static int tc_pipeline(Scratch* s, const SearchArgs& a, int mode, FilterSide* si
   const bool cached_norms = a.row_sumsq != nullptr;
   int qp = 0, stages = 0;
   bool pair = false;
-  if ((rc = scan_tc_plan(mode, int(a.n_queries), a.dim, kcap, cached_norms, (a.n_rows + 127) / 128, s->sm_count, a.flags,
-                         &qp, &stages, &pair)))
+  // Short scans on the filter path: every CTA owns ONE tile, thresholds come from a grid-wide exchange of the tiles'
+  // bests, candidates go straight to a global array (scan_tc.cu, oneshot_epilogue).  Needs at least top_k tiles (T is the
+  // top_k-th largest of the tiles' bests) and all of them resident at once.
+  const int64_t n_tiles_all = (a.n_rows + 127) / 128;
+  const bool oneshot = side != nullptr && side->ocand != nullptr && !need && n_tiles_all <= s->sm_count &&
+                       n_tiles_all >= a.top_k && !(a.flags & (DEVQA_DEBUG_FILTER_ONLY | DEVQA_DEBUG_NO_ONESHOT));
+  if ((rc = scan_tc_plan(mode, int(a.n_queries), a.dim, kcap, cached_norms, n_tiles_all, s->sm_count, a.flags,
+                         &qp, &stages, &pair, oneshot)))
     return rc;
   const int q_pad = int((a.n_queries + qp - 1) / qp) * qp;
   const size_t qcat_bytes = scan_tc_qcat_bytes(mode, a.dim, q_pad);
@@ -223,6 +238,12 @@ static int tc_pipeline(Scratch* s, const SearchArgs& a, int mode, FilterSide* si
   int ctas_per_pass = s->sm_count / side_by;
   if (ctas_per_pass > tiles_cap) ctas_per_pass = tiles_cap;
   if (ctas_per_pass < 1) ctas_per_pass = 1;
+  if (oneshot) {                                             // one CTA per tile; as many passes per launch as fit
+    ctas_per_pass = int(tiles);
+    side_by = s->sm_count / ctas_per_pass;
+    if (side_by > n_passes) side_by = n_passes;
+    DEVQA_REQUIRE(n_passes <= 64, "one-shot scan: too many passes for the arrival counters");
+  }
   const int grid = ctas_per_pass;                           // candidate lists per query
   if ((rc = grow(reinterpret_cast<void**>(&s->cand), &s->cand_bytes, size_t(grid) * a.n_queries * kcap * 8, false))) return rc;
 
@@ -234,6 +255,8 @@ static int tc_pipeline(Scratch* s, const SearchArgs& a, int mode, FilterSide* si
   if (side) {
     p.qerr = side->qerr; p.k_true = a.top_k; p.lostu = side->lostu; p.bank_max_sumsq = a.max_sumsq;
     side->n_lists = grid;
+    side->oneshot = oneshot;
+    if (oneshot) { p.oneshot = 1; p.gbar = side->gbar; p.ocount = side->ocount; p.ocand = side->ocand; p.ocap = kOneshotCap; }
   }
   p.gmax = gmax; p.gmax_stride = kGmaxStride;
   DEVQA_REQUIRE(grid <= kGmaxStride, "more CTAs per pass than the threshold exchange holds");
@@ -242,7 +265,8 @@ static int tc_pipeline(Scratch* s, const SearchArgs& a, int mode, FilterSide* si
   if (prof) DEVQA_CUDA(cudaEventRecord(s->prof_ev[2 * s->prof_used], stream));
   if ((rc = scan_tc_prep_queries(mode, a.queries, a.query_ld, int(a.n_queries), qp, q_pad, a.dim, a.flags, s->qsplit, gthr,
                                  side ? side->qinv : nullptr, side ? side->qerr : nullptr, side ? side->seed_u : nullptr,
-                                 gmax, kGmaxStride, need, stream)))
+                                 gmax, kGmaxStride, need, stream, oneshot ? side->gbar : nullptr,
+                                 oneshot ? 128 + int(a.n_queries) : 0)))
     return rc;
   // Threshold seeding: scan a prefix sample of the bank (one tile per CTA) first; the k-th best score of a
   // SUBSET is a lower bound of the k-th best of the whole bank, so the main scan starts with tight
@@ -281,7 +305,7 @@ static int tc_pipeline(Scratch* s, const SearchArgs& a, int mode, FilterSide* si
   }
   if (side) {
     side->kcap = kcap;
-    if (!side->merge) return DEVQA_OK;
+    if (!side->merge || oneshot) return DEVQA_OK;
     return merge_lists_launch(s->cand, grid, a.n_queries, kcap, kcap, side->kp, side->akeys, nullptr, nullptr, stream);
   }
   return merge_lists_launch(s->cand, grid, a.n_queries, kcap, kcap, a.top_k, out_keys, out_scores, out_ids, stream, nullptr, need);
@@ -364,7 +388,8 @@ static int run_search(Scratch* s, const SearchArgs& a, uint64_t* out_keys, float
       }
       const size_t nq = size_t(ac.n_queries), nq_pad = (nq + 255) / 256 * 256;   // >= q_pad of any plan
       if ((rc = grow(reinterpret_cast<void**>(&s->akeys), &s->akeys_bytes,
-                     nq * kp * 8 + nq * 12 + nq_pad * 4 + size_t(s->sm_count) * nq * 4 + nq_pad * kGmaxStride * 4, false)))
+                     nq * kp * 8 + nq * 12 + nq_pad * 4 + size_t(s->sm_count) * nq * 4 + nq_pad * kGmaxStride * 4 +
+                         (128 + nq_pad) * 4 + 8 + nq * kOneshotCap * 8, false)))
         return rc;
       FilterSide side;
       side.kp = kp;
@@ -375,6 +400,9 @@ static int run_search(Scratch* s, const SearchArgs& a, uint64_t* out_keys, float
       side.seed_u = reinterpret_cast<uint32_t*>(side.qerr + nq);
       side.lostu = side.seed_u + nq_pad;
       side.gmax = side.lostu + size_t(s->sm_count) * nq;
+      side.gbar = side.gmax + nq_pad * kGmaxStride;                     // [128] counters, then [nq] candidate counts,
+      side.ocount = side.gbar + 128;                                    // zeroed as ONE region by the prep kernel
+      side.ocand = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(side.ocount + nq_pad) + 7) & ~uintptr_t(7));
       // With at least top_k CTAs per pass the scan's CTAs exchange their bests, and refine can pick the candidates
       // straight out of the per-CTA lists (one kernel instead of merge + refine).
       const int64_t tiles = (a.n_rows + 127) / 128;
@@ -392,7 +420,8 @@ static int run_search(Scratch* s, const SearchArgs& a, uint64_t* out_keys, float
       rp.need = side.need; rp.fallbacks = s->fallbacks; rp.violations = s->violations; rp.out_keys = ok; rp.out_scores = os; rp.out_ids = oi;
       rp.cand = s->cand; rp.cand_kcap = side.kcap; rp.gmax = side.gmax; rp.gmax_stride = kGmaxStride;
       rp.qerr = side.qerr; rp.bank_max_sumsq = a.max_sumsq;
-      if ((rc = side.merge ? refine_launch(rp, stream) : refine_lists_launch(rp, stream))) return rc;
+      if (side.oneshot) { rp.dcount = side.ocount; rp.dcand = side.ocand; rp.dcap = kOneshotCap; }
+      if ((rc = (side.merge && !side.oneshot) ? refine_launch(rp, stream) : refine_lists_launch(rp, stream))) return rc;
       // queries for which a lost row could still matter are redone exactly; for all others these launches
       // exit at once (the flags live on the device: no host round trip, graph-capturable).  The fallback's top-k
       // (3xTF32 scores) is then re-scored in the stream kernel's arithmetic like every other result, so scores

@@ -77,6 +77,25 @@ struct IdMap {
 };
 
 #ifdef __CUDACC__
+// ---- programmatic dependent launch ---------------------------------------------------------------------------------
+// A search is a chain of small kernels (query prep -> scan -> re-scoring -> conditional fallback -> merge); between two
+// kernels of a stream the GPU idles for the ~3-5 us it takes to drain one grid and launch the next -- 40 of C2's 150 us.
+// Kernels of the chain are launched with the programmatic-stream-serialization attribute: the next grid is set up
+// while the previous one still runs, and every kernel starts with pdl_wait(), which blocks until the previous grid has
+// completed and its memory is visible.  (Without the attribute pdl_wait() is a no-op.)  DEVQA_PDL=0 disables it.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 // 128-bit streaming load: read-only path, do not allocate in L1 (the bank is touched once).
 __device__ __forceinline__ float4 ld_stream_f4(const float4* p) {
   float4 v;

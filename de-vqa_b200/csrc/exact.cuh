@@ -18,38 +18,52 @@ __device__ __forceinline__ float exact_score(const T* __restrict__ row, const fl
   constexpr bool BF = sizeof(T) == 2;
   constexpr int NV = VEC ? (BF ? 8 : 4) : 1;
   constexpr int CH = 32 * NV;
+  constexpr int U = 8;                       // chunks whose loads are issued together (memory-level parallelism: the
+                                             // row comes from HBM, one round trip per batch instead of one per chunk)
   const int nchunks = (dim + CH - 1) / CH;
   const bool norm = (flags & DEVQA_NORMALIZE_BANK) != 0;
   const bool want_nr = norm || row_norm != nullptr;
   float acc = 0.f, nr = 0.f;
-  for (int c = 0; c < nchunks; ++c) {
-    const int col = c * CH + lane * NV;
-    float b[NV], qv[NV];
-    if constexpr (VEC && BF) {
-      uint4 t = make_uint4(0u, 0u, 0u, 0u);
-      if (col < dim) t = __ldg(reinterpret_cast<const uint4*>(row + col));
-      b[0] = __uint_as_float(t.x << 16); b[1] = __uint_as_float(t.x & 0xffff0000u);
-      b[2] = __uint_as_float(t.y << 16); b[3] = __uint_as_float(t.y & 0xffff0000u);
-      b[4] = __uint_as_float(t.z << 16); b[5] = __uint_as_float(t.z & 0xffff0000u);
-      b[6] = __uint_as_float(t.w << 16); b[7] = __uint_as_float(t.w & 0xffff0000u);
-      const float4 u0 = *reinterpret_cast<const float4*>(sq + col), u1 = *reinterpret_cast<const float4*>(sq + col + 4);
-      qv[0] = u0.x; qv[1] = u0.y; qv[2] = u0.z; qv[3] = u0.w; qv[4] = u1.x; qv[5] = u1.y; qv[6] = u1.z; qv[7] = u1.w;
-    } else if constexpr (VEC) {
-      float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (col < dim) t = __ldg(reinterpret_cast<const float4*>(row + col));
-      b[0] = t.x; b[1] = t.y; b[2] = t.z; b[3] = t.w;
-      const float4 u = *reinterpret_cast<const float4*>(sq + col);
-      qv[0] = u.x; qv[1] = u.y; qv[2] = u.z; qv[3] = u.w;
-    } else {
-      if constexpr (BF) b[0] = col < dim ? __bfloat162float(row[col]) : 0.f;
-      else b[0] = col < dim ? __ldg(row + col) : 0.f;
-      qv[0] = sq[col];
+  for (int c0 = 0; c0 < nchunks; c0 += U) {
+    uint4 raw[U];                            // VEC: 16 bytes per chunk; scalar: .x holds the element's fp32 bits
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int col = (c0 + u) * CH + lane * NV;
+      raw[u] = make_uint4(0u, 0u, 0u, 0u);
+      if (c0 + u < nchunks && col < dim) {
+        if constexpr (VEC) raw[u] = __ldg(reinterpret_cast<const uint4*>(row + col));
+        else if constexpr (BF) raw[u].x = __float_as_uint(__bfloat162float(row[col]));
+        else raw[u].x = __float_as_uint(__ldg(row + col));
+      }
     }
 #pragma unroll
-    for (int e = 0; e < NV; ++e) acc = fmaf(b[e], qv[e], acc);
-    if (want_nr) {
+    for (int u = 0; u < U; ++u) {            // the FMAs in chunk order, exactly as the stream kernel chains them
+      if (c0 + u >= nchunks) break;
+      const int col = (c0 + u) * CH + lane * NV;
+      float b[NV], qv[NV];
+      if constexpr (VEC && BF) {
+        const uint4 t = raw[u];
+        b[0] = __uint_as_float(t.x << 16); b[1] = __uint_as_float(t.x & 0xffff0000u);
+        b[2] = __uint_as_float(t.y << 16); b[3] = __uint_as_float(t.y & 0xffff0000u);
+        b[4] = __uint_as_float(t.z << 16); b[5] = __uint_as_float(t.z & 0xffff0000u);
+        b[6] = __uint_as_float(t.w << 16); b[7] = __uint_as_float(t.w & 0xffff0000u);
+        const float4 u0 = *reinterpret_cast<const float4*>(sq + col), u1 = *reinterpret_cast<const float4*>(sq + col + 4);
+        qv[0] = u0.x; qv[1] = u0.y; qv[2] = u0.z; qv[3] = u0.w; qv[4] = u1.x; qv[5] = u1.y; qv[6] = u1.z; qv[7] = u1.w;
+      } else if constexpr (VEC) {
+        const uint4 t = raw[u];
+        b[0] = __uint_as_float(t.x); b[1] = __uint_as_float(t.y); b[2] = __uint_as_float(t.z); b[3] = __uint_as_float(t.w);
+        const float4 qq = *reinterpret_cast<const float4*>(sq + col);
+        qv[0] = qq.x; qv[1] = qq.y; qv[2] = qq.z; qv[3] = qq.w;
+      } else {
+        b[0] = __uint_as_float(raw[u].x);
+        qv[0] = sq[col];
+      }
 #pragma unroll
-      for (int e = 0; e < NV; ++e) nr = fmaf(b[e], b[e], nr);
+      for (int e = 0; e < NV; ++e) acc = fmaf(b[e], qv[e], acc);
+      if (want_nr) {
+#pragma unroll
+        for (int e = 0; e < NV; ++e) nr = fmaf(b[e], b[e], nr);
+      }
     }
   }
 #pragma unroll
@@ -64,5 +78,12 @@ __device__ __forceinline__ float exact_score(const T* __restrict__ row, const fl
   return acc;
 }
 
+// pull a row towards L2 ahead of its re-scoring (one 128-byte line per lane and step)
+template <typename T>
+__device__ __forceinline__ void prefetch_row_l2(const T* row, int dim, int lane) {
+  const char* p = reinterpret_cast<const char*>(row);
+  for (int off = lane * 128; off < dim * int(sizeof(T)); off += 32 * 128)
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p + off));
+}
 
 }  // namespace devqa

@@ -34,6 +34,7 @@ __global__ void __launch_bounds__(kGateThreads) scope_gate_kernel(const GatePara
   const int dim = p.dim;
   const int m = blockIdx.x * kGateThreads + threadIdx.x;
   const bool m_live = m < p.m;
+  pdl_wait();
   for (int q0 = 0; q0 < p.n_queries; q0 += kGateQ) {
     const int nq = min(kGateQ, p.n_queries - q0);
     __syncthreads();
@@ -129,7 +130,7 @@ int scope_gate_launch(const GateParams& p, cudaStream_t stream) {
   }
   if (smem > 40 * 1024) DEVQA_CUDA(cudaFuncSetAttribute(scope_gate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
   const int grid = (p.m + kGateThreads - 1) / kGateThreads;
-  scope_gate_kernel<<<grid, kGateThreads, smem, stream>>>(p);
+  DEVQA_CUDA(launch_pdl(scope_gate_kernel, dim3(grid), dim3(kGateThreads), smem, stream, p));
   DEVQA_CUDA(cudaGetLastError());
   count_launch();
   return DEVQA_OK;

@@ -44,6 +44,7 @@ __global__ void __launch_bounds__(kMergeThreads) merge32_kernel(const uint64_t* 
   __shared__ uint64_t sacc[kMergeWarps][32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t q = blockIdx.x;
+  pdl_wait();
   if (need && need[q] == 0u) return;
   uint64_t acc = kEmptyKey;
   const int rev = 31 - lane;
@@ -74,6 +75,7 @@ __global__ void __launch_bounds__(kMergeThreads) merge_generic_kernel(const uint
                                                                      uint32_t* kth_codes,
                                                                      const uint32_t* __restrict__ need) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  pdl_wait();
   if (need && need[blockIdx.x] == 0u) return;
   const int nwarps = blockDim.x >> 5;
   uint64_t* acc = reinterpret_cast<uint64_t*>(smem_raw);       // [warps][kcap]
@@ -108,15 +110,14 @@ int merge_lists_launch(const uint64_t* lists, int n_lists, int64_t n_queries, in
   if (n_queries == 0) return DEVQA_OK;
   const int kcap = topk_capacity(top_k > list_len ? top_k : list_len);
   if (kcap == 32) {
-    merge32_kernel<<<unsigned(n_queries), kMergeThreads, 0, stream>>>(lists, n_lists, n_queries, list_stride,
-                                                                      list_len, top_k, out_keys, out_scores,
-                                                                      out_ids, kth_codes, need);
+    DEVQA_CUDA(launch_pdl(merge32_kernel, dim3(unsigned(n_queries)), dim3(kMergeThreads), 0, stream, lists, n_lists, n_queries,
+                          list_stride, list_len, top_k, out_keys, out_scores, out_ids, kth_codes, need));
   } else {
     const int threads = kcap <= 512 ? kMergeThreads : kMergeThreads / 2;   // keep smem <= 128 KB
     const size_t smem = size_t(2) * (threads / 32) * kcap * 8;
     DEVQA_CUDA(cudaFuncSetAttribute(merge_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-    merge_generic_kernel<<<unsigned(n_queries), threads, smem, stream>>>(
-        lists, n_lists, n_queries, list_stride, list_len, kcap, top_k, out_keys, out_scores, out_ids, kth_codes, need);
+    DEVQA_CUDA(launch_pdl(merge_generic_kernel, dim3(unsigned(n_queries)), dim3(threads), smem, stream, lists, n_lists, n_queries,
+                          list_stride, list_len, kcap, top_k, out_keys, out_scores, out_ids, kth_codes, need));
   }
   DEVQA_CUDA(cudaGetLastError());
   count_launch();

@@ -43,11 +43,31 @@ __device__ __forceinline__ bool bound_violated(float u, float s, float e) {
   return s > u || (u - s) > 2.0001f * e + 1e-30f;
 }
 
+// ex[0 .. kMaxKp): exact keys, unique or empty (0)  ->  srt[0 .. kMaxKp) descending, empties last.  Rank sort: thread i
+// counts the keys above its own (128 broadcast reads, no barrier in between) -- ~1/10 of the 28-phase bitonic network
+// this replaced, which was a third of the kernel's time.  All threads call; srt must not alias ex.
+__device__ __forceinline__ void rank_sort(const uint64_t* ex, uint64_t* srt) {
+  const int i = threadIdx.x;
+  if (i < kMaxKp) srt[i] = kEmptyKey;
+  __syncthreads();
+  if (i < kMaxKp) {
+    const uint64_t key = ex[i];
+    if (key != kEmptyKey) {
+      int rank = 0;
+#pragma unroll 8
+      for (int j = 0; j < kMaxKp; ++j) rank += ex[j] > key ? 1 : 0;
+      srt[rank] = key;
+    }
+  }
+  __syncthreads();
+}
+
 template <typename T, bool VEC>
 __global__ void __launch_bounds__(kRefineThreads) refine_kernel(const RefineParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ uint64_t ex[kMaxKp];
   __shared__ uint64_t ak[kMaxKp];
+  __shared__ uint64_t srt[kMaxKp];
   __shared__ float s_prelim;
   __shared__ uint32_t s_lost;                                       // max score code of any full list's last entry
   __shared__ uint32_t s_viol;                                       // candidates whose exact score left [u - 2E, u]
@@ -56,6 +76,7 @@ __global__ void __launch_bounds__(kRefineThreads) refine_kernel(const RefinePara
   const int dpad = (dim + CH - 1) / CH * CH;
   float* sq = reinterpret_cast<float*>(smem_raw);                  // the query exactly as the stream kernel stages it
   const int q = blockIdx.x;
+  pdl_wait();
   if (p.only_if && p.only_if[q] == 0u) return;                     // conditional run (after the exact fallback)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const float* src = p.queries + size_t(q) * p.query_ld;
@@ -117,25 +138,11 @@ __global__ void __launch_bounds__(kRefineThreads) refine_kernel(const RefinePara
     if (a != kEmptyKey && !(key_score(a) < prelim)) rescore(c);    // warp-uniform; NaN upper bounds are re-scored
   }
   __syncthreads();
-  // bitonic sort of the 128 slots, descending (empty = 0 sinks to the end)
-  for (int k = 2; k <= kMaxKp; k <<= 1) {
-    for (int j = k >> 1; j > 0; j >>= 1) {
-      const int i = threadIdx.x;
-      if (i < kMaxKp) {
-        const int l = i ^ j;
-        if (l > i) {
-          const uint64_t a = ex[i], b = ex[l];
-          const bool desc = (i & k) == 0;
-          if (desc ? a < b : a > b) { ex[i] = b; ex[l] = a; }
-        }
-      }
-      __syncthreads();
-    }
-  }
+  rank_sort(ex, srt);                                               // descending, empties last
   // nothing lost can enter the top-k?  (not asked when this run only re-expresses an exact result in the stream
   // kernel's arithmetic)
   if (threadIdx.x == 0 && !p.only_if) {
-    const uint64_t kth = ex[p.top_k - 1];
+    const uint64_t kth = srt[p.top_k - 1];
     bool complete = true;
     uint32_t lost = s_lost;                                         // full per-CTA lists
     const uint64_t mlast = ak[p.kp - 1];                            // the merged list, when it is full
@@ -152,7 +159,7 @@ __global__ void __launch_bounds__(kRefineThreads) refine_kernel(const RefinePara
     if (!complete && p.fallbacks) atomicAdd(p.fallbacks, 1u);
   }
   for (int e = threadIdx.x; e < p.top_k; e += kRefineThreads) {
-    const uint64_t key = ex[e];
+    const uint64_t key = srt[e];
     const size_t o = size_t(q) * p.top_k + e;
     if (p.out_keys) {
       p.out_keys[o] = key;
@@ -183,6 +190,7 @@ __global__ void __launch_bounds__(kRefineListThreads) refine_lists_kernel(const 
   const int dpad = (dim + CH - 1) / CH * CH;
   float* sq = reinterpret_cast<float*>(smem_raw);
   const int q = blockIdx.x;
+  pdl_wait();
   const bool dot_mode = !(p.flags & DEVQA_NORMALIZE_BANK);
   const float eq = p.qerr[q];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -191,8 +199,11 @@ __global__ void __launch_bounds__(kRefineListThreads) refine_lists_kernel(const 
   for (int c = threadIdx.x; c < dpad; c += kRefineListThreads) sq[c] = c < dim ? src[c] * inv : 0.f;
   for (int c = threadIdx.x; c < kMaxKp; c += kRefineListThreads) ex[c] = kEmptyKey;
   if (threadIdx.x == 0) { s_count = 0u; s_lost = 0u; s_tcode = 0u; s_viol = 0u; }
+  const bool direct = p.dcount != nullptr;                             // one-shot scan: candidates are one array already
   // ---- T from the CTAs' bests (warp 0), lost-row bounds (warp 1) ----
-  if (warp == 0) {
+  if (direct) {
+    // nothing to derive: the scan emitted every row with u >= T itself, and lost none
+  } else if (warp == 0) {
     const uint32_t* g = p.gmax + size_t(q) * p.gmax_stride;
     uint32_t v[5];
 #pragma unroll
@@ -224,7 +235,13 @@ __global__ void __launch_bounds__(kRefineListThreads) refine_lists_kernel(const 
   __syncthreads();
   // ---- compact the keys that can still matter ----
   const uint32_t tcode = s_tcode;
-  const int total = p.n_lists * p.cand_kcap;
+  const int total = direct ? 0 : p.n_lists * p.cand_kcap;
+  if (direct) {
+    const uint32_t cnt = p.dcount[q];
+    const uint32_t have = cnt < uint32_t(p.dcap) ? cnt : uint32_t(p.dcap);
+    for (uint32_t i = threadIdx.x; i < have && i < uint32_t(kWide); i += kRefineListThreads) ak[i] = p.dcand[size_t(q) * p.dcap + i];
+    if (threadIdx.x == 0) s_count = cnt > uint32_t(p.dcap) ? uint32_t(kWide) + 1u : have;   // overflow: candidates are missing
+  }
   for (int i = threadIdx.x; i < total; i += kRefineListThreads) {
     const int g = i / p.cand_kcap, e = i - g * p.cand_kcap;
     const uint64_t key = p.cand[(size_t(g) * p.n_queries + q) * p.cand_kcap + e];
@@ -269,37 +286,57 @@ __global__ void __launch_bounds__(kRefineListThreads) refine_lists_kernel(const 
     n_raw = s_count;
   }
   const int n = n_raw < uint32_t(kMaxKp) ? int(n_raw) : kMaxKp;
-  // ---- exact re-scoring ----
-  for (int c = warp; c < n; c += kRefineListThreads / 32) {
-    const uint64_t a = ak[c];
-    const int64_t gid = int64_t(key_id(a));
-    int64_t row = gid - p.idmap.base;
+  // ---- exact re-scoring, two phases (like refine_kernel): the top_k candidates by upper bound first; then only those
+  // whose upper bound can still beat the k-th best exact score found.  Re-scoring is the kernel's whole cost (one
+  // HBM/L2 round trip of dim * 4 bytes per candidate), and typically a third of the candidates fall in phase 2. ----
+  __shared__ float s_prelim;
+  uint64_t* const byu = ak + 2 * kMaxKp;                               // candidates sorted by upper bound (ak[256..384))
+  __syncthreads();
+  if (threadIdx.x >= n && threadIdx.x < kMaxKp) ak[threadIdx.x] = kEmptyKey;
+  __syncthreads();
+  rank_sort(ak, byu);
+  auto row_of = [&](int c) {
+    int64_t row = int64_t(key_id(byu[c])) - p.idmap.base;
     if (p.idmap.chunk > 0) row = ((row / p.idmap.chunk) / p.idmap.world) * p.idmap.chunk + row % p.idmap.chunk;
+    return static_cast<const T*>(p.bank) + row * p.bank_ld;
+  };
+  auto rescore = [&](int c) {                                          // whole warp
+    const uint64_t a = byu[c];
     float nrm = 1.f;
-    const float s = exact_score<T, VEC>(static_cast<const T*>(p.bank) + row * p.bank_ld, sq, dim, p.flags, lane,
-                                        dot_mode ? &nrm : nullptr);
+    const float s = exact_score<T, VEC>(row_of(c), sq, dim, p.flags, lane, dot_mode ? &nrm : nullptr);
     if (lane == 0) {
-      ex[c] = pack_key(s, uint32_t(gid));
+      ex[c] = pack_key(s, key_id(a));
       if (bound_violated(key_score(a), s, eq * nrm)) atomicAdd(&s_viol, 1u);   // canary, see bound_violated()
     }
+  };
+  constexpr int kWarps = kRefineListThreads / 32;
+  const int k1 = p.top_k < n ? p.top_k : n;
+  for (int c = warp; c < k1; c += kWarps) {
+    // the candidates' rows left L2 long ago (the scan has streamed gigabytes since): pull the warp's NEXT row in
+    // while this one is scored -- the kernel is a chain of memory round trips, not of flops
+    if (c + kWarps < k1) prefetch_row_l2(row_of(c + kWarps), dim, lane);
+    rescore(c);
   }
   __syncthreads();
-  for (int k = 2; k <= kMaxKp; k <<= 1) {
-    for (int j = k >> 1; j > 0; j >>= 1) {
-      const int i = threadIdx.x;
-      if (i < kMaxKp) {
-        const int l = i ^ j;
-        if (l > i) {
-          const uint64_t a = ex[i], b = ex[l];
-          const bool desc = (i & k) == 0;
-          if (desc ? a < b : a > b) { ex[i] = b; ex[l] = a; }
-        }
-      }
-      __syncthreads();
+  if (warp == 0) {                                                     // the k-th best exact score among those (or -inf)
+    uint64_t m = ~0ull;
+    for (int c = lane; c < p.top_k; c += 32) {
+      const uint64_t key = c < k1 ? ex[c] : kEmptyKey;
+      m = key < m ? key : m;
     }
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) { const uint64_t o = shfl_xor_u64(m, off); m = o < m ? o : m; }
+    if (lane == 0) s_prelim = m == kEmptyKey ? -INFINITY : key_score(m);
   }
+  __syncthreads();
+  const float prelim = s_prelim;
+  for (int c = k1 + warp; c < n; c += kWarps)
+    if (!(key_score(byu[c]) < prelim)) rescore(c);                     // warp-uniform; NaN upper bounds are re-scored
+  __syncthreads();
+  uint64_t* const srt = ak;                                            // (the compacted keys are dead now)
+  rank_sort(ex, srt);
   if (threadIdx.x == 0) {
-    const uint64_t kth = ex[p.top_k - 1];
+    const uint64_t kth = srt[p.top_k - 1];
     bool complete = n_raw <= uint32_t(kMaxKp);                        // otherwise candidates were cut off
     const uint32_t lost = s_lost;
     if (complete && lost != 0u)
@@ -312,7 +349,7 @@ __global__ void __launch_bounds__(kRefineListThreads) refine_lists_kernel(const 
     if (!complete && p.fallbacks) atomicAdd(p.fallbacks, 1u);
   }
   for (int e = threadIdx.x; e < p.top_k; e += kRefineListThreads) {
-    const uint64_t key = ex[e];
+    const uint64_t key = srt[e];
     const size_t o = size_t(q) * p.top_k + e;
     if (p.out_keys) {
       p.out_keys[o] = key;
@@ -338,14 +375,15 @@ static size_t refine_query_smem(const RefineParams& p, bool vec) {
 
 int refine_lists_launch(const RefineParams& p, cudaStream_t stream) {
   if (p.n_queries == 0) return DEVQA_OK;
-  DEVQA_REQUIRE(p.top_k <= kMaxKp && p.n_lists <= 160 && p.n_lists >= p.top_k, "refine: unsupported list geometry");
+  if (p.dcount) DEVQA_REQUIRE(p.top_k <= kMaxKp && p.dcap <= 512 && p.dcand, "refine: unsupported direct candidate geometry");
+  else DEVQA_REQUIRE(p.top_k <= kMaxKp && p.n_lists <= 160 && p.n_lists >= p.top_k, "refine: unsupported list geometry");
   const bool vec = refine_vectorised(p);
   const size_t smem = refine_query_smem(p, vec);
   void (*kern)(RefineParams) = p.bank_dtype == DEVQA_F32
       ? (vec ? refine_lists_kernel<float, true> : refine_lists_kernel<float, false>)
       : (vec ? refine_lists_kernel<__nv_bfloat16, true> : refine_lists_kernel<__nv_bfloat16, false>);
   if (smem > 40 * 1024) DEVQA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-  kern<<<unsigned(p.n_queries), kRefineListThreads, smem, stream>>>(p);
+  DEVQA_CUDA(launch_pdl(kern, dim3(unsigned(p.n_queries)), dim3(kRefineListThreads), smem, stream, p));
   DEVQA_CUDA(cudaGetLastError());
   count_launch();
   return DEVQA_OK;
@@ -360,7 +398,7 @@ int refine_launch(const RefineParams& p, cudaStream_t stream) {
       ? (vec ? refine_kernel<float, true> : refine_kernel<float, false>)
       : (vec ? refine_kernel<__nv_bfloat16, true> : refine_kernel<__nv_bfloat16, false>);
   if (smem > 48 * 1024) DEVQA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-  kern<<<unsigned(p.n_queries), kRefineThreads, smem, stream>>>(p);
+  DEVQA_CUDA(launch_pdl(kern, dim3(unsigned(p.n_queries)), dim3(kRefineThreads), smem, stream, p));
   DEVQA_CUDA(cudaGetLastError());
   count_launch();
   return DEVQA_OK;

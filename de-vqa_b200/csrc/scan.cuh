@@ -39,6 +39,12 @@ struct ScanParams {
   uint32_t* lostu;         // [grid, n_queries] out: bound on the rows each CTA's full list lost (score code, 0 = none)
   uint32_t* gmax;          // [q_pad, gmax_stride] zeroed scratch: each CTA's best upper bound per query (score codes)
   int32_t gmax_stride;
+  // tcgen05 filter, one-shot mode (every CTA owns one tile; scan_tc.cu oneshot_epilogue)
+  int32_t oneshot;
+  uint32_t* gbar;          // [2 * passes] zeroed arrival counters
+  uint32_t* ocount;        // [n_queries] zeroed candidate counts
+  uint64_t* ocand;         // [n_queries, ocap] candidates
+  int32_t ocap;
 };
 
 size_t scan_stream_smem_bytes(int64_t dim, int nv, int qt, int kcap);
@@ -73,7 +79,8 @@ __host__ __device__ inline float tc_filter_relerr(int64_t dim, bool bf16_bank = 
 }
 bool scan_tc_supported(int bank_dtype, const void* bank, int64_t dim, int64_t bank_ld, int top_k);
 int scan_tc_plan(int mode, int n_queries, int64_t dim, int kcap, bool cached_norms, int64_t n_tiles, int sm_count,
-                 unsigned flags, int* qp_out, int* stages_out, bool* pair_out);
+                 unsigned flags, int* qp_out, int* stages_out, bool* pair_out, bool oneshot = false);
+constexpr int kOneshotCap = 512;       // candidates per query the one-shot scan can emit (refine's first-cut capacity)
 size_t scan_tc_qcat_bytes(int mode, int64_t dim, int q_pad);
 bool scan_tc_exchanges_thresholds(int mode, int64_t dim);   // scan-and-queue epilogue + gmax exchange (else: seeded score-tile epilogue)
 // queries -> normalised, split (hi/lo TF32; hi/mid/lo bf16; hi TF32 only for the filter), laid out per pass as the
@@ -82,7 +89,8 @@ bool scan_tc_exchanges_thresholds(int mode, int64_t dim);   // scan-and-queue ep
 // ||query as used||, and zeroes seed_u [q_pad] and the threshold exchange table gmax [q_pad, gmax_stride].
 int scan_tc_prep_queries(int mode, const float* queries, int64_t query_ld, int n_queries, int qp, int q_pad,
                          int64_t dim, unsigned flags, void* qcat, uint32_t* gthr, float* qinv, float* qerr,
-                         uint32_t* seed_u, uint32_t* gmax, int gmax_stride, const uint32_t* need, cudaStream_t stream);
+                         uint32_t* seed_u, uint32_t* gmax, int gmax_stride, const uint32_t* need, cudaStream_t stream,
+                         uint32_t* zero_words = nullptr, int n_zero = 0);   // filter modes: further words to zero
 // one launch = `passes` consecutive query passes starting at p.q0, each on ctas_per_pass CTAs
 // (pair: clusters of two CTAs sharing the query operand, see scan_tc.cu)
 int scan_tc_launch(const ScanParams& p, int mode, const void* qcat, uint32_t* gthr, int qp, int stages, int passes,
@@ -104,6 +112,10 @@ struct RefineParams {
   int32_t gmax_stride;
   const float* qerr;          // [n_queries] tc_filter_relerr(dim) * ||query as used||
   const uint32_t* bank_max_sumsq;   // un-normalised scores: max ||row||^2 (float bits)
+  // refine_lists_launch, direct mode (one-shot scans): the candidates are already one unordered array per query
+  const uint32_t* dcount;     // [n_queries] candidates emitted (may exceed dcap: then the query is flagged)
+  const uint64_t* dcand;      // [n_queries, dcap]
+  int32_t dcap;
   int32_t kp, top_k;
   uint32_t flags;
   IdMap idmap;

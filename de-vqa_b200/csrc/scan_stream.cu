@@ -190,6 +190,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_stream_kernel(const Scan
   const int nchunks = (dim + CH - 1) / CH;
   const int dpad = nchunks * CH;
   const int kcap = p.kcap;
+  pdl_wait();
 
   float* sq = reinterpret_cast<float*>(smem_raw);                                   // [nchunks][QT][NV/4][32] x4
   uint64_t* lists = reinterpret_cast<uint64_t*>(smem_raw + size_t(QT) * dpad * 4);  // [warps][QT][kcap]
@@ -402,7 +403,7 @@ int launch_variant(const ScanParams& p, int grid, cudaStream_t stream) {
   const bool norm = (p.flags & DEVQA_NORMALIZE_BANK) != 0;
   auto kern = norm ? scan_stream_kernel<T, NV, QT, R, true> : scan_stream_kernel<T, NV, QT, R, false>;
   DEVQA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-  kern<<<grid, kScanThreads, smem, stream>>>(p);
+  DEVQA_CUDA(launch_pdl(kern, dim3(grid), dim3(kScanThreads), smem, stream, p));
   DEVQA_CUDA(cudaGetLastError());
   count_launch();
   return DEVQA_OK;
@@ -415,7 +416,7 @@ int launch_select_variant(const ScanParams& p, int grid, cudaStream_t stream) {
   const bool norm = (p.flags & DEVQA_NORMALIZE_BANK) != 0;
   auto kern = norm ? scan_stream_kernel<T, NV, QT, R, true, true> : scan_stream_kernel<T, NV, QT, R, false, true>;
   DEVQA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-  kern<<<grid, kScanThreads, smem, stream>>>(p);
+  DEVQA_CUDA(launch_pdl(kern, dim3(grid), dim3(kScanThreads), smem, stream, p));
   DEVQA_CUDA(cudaGetLastError());
   count_launch();
   return DEVQA_OK;

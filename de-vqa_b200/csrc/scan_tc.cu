@@ -326,6 +326,12 @@ struct TcParams {
   uint32_t* gmax;          // [q_pad, gmax_stride] score code of each CTA's best upper bound per query (0 = none yet)
   int32_t gmax_stride;
   uint32_t* gthr;          // [n_queries] shared lower bounds of the k-th score (monotone score codes, 0 = none)
+  // one-shot mode (short scans: every CTA owns exactly ONE tile, all CTAs co-resident): see oneshot_epilogue
+  int32_t oneshot;
+  uint32_t* gbar;          // [2 * passes of the call] zeroed arrival counters: bests published / thresholds published
+  uint32_t* ocount;        // [n_queries] zeroed: candidates emitted per query
+  uint64_t* ocand;         // [n_queries, ocap] candidate keys (on the upper bound u), unordered
+  int32_t ocap;
   IdMap idmap;
   long long* trace;        // optional [16][256] clock64 samples of CTA 0's roles (devqa_debug_tc_trace)
 };
@@ -668,6 +674,51 @@ __device__ __forceinline__ void filt_epilogue(const TcParams& p, const FiltState
     }
 }
 
+// One round of the shared-out threshold selection: CTA `cta` derives T for the queries j = cta, cta + n_ctas, ... of
+// its pass from every CTA's best upper bound (gmax) and publishes it in gthr (atomicMax on the score code).
+__device__ __forceinline__ void service_select_round(const TcParams& p, const FiltState& st, int q0, int nq_pass, int n_ctas,
+                                                     int cta, float maxn, int lane, int k) {
+  constexpr int NQ = 4;                                               // queries selected side by side (hides the redux latency)
+  for (int jg = cta; jg < nq_pass; jg += n_ctas * NQ) {
+    uint32_t v[NQ][5];
+#pragma unroll
+    for (int t = 0; t < NQ; ++t) {
+      const int j = jg + t * n_ctas < nq_pass ? jg + t * n_ctas : jg;
+      const uint32_t* src = p.gmax + size_t(q0 + j) * p.gmax_stride;
+#pragma unroll
+      for (int i = 0; i < 5; ++i) {
+        const int c = lane + 32 * i;
+        v[t][i] = 0u;
+        if (c < n_ctas) asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v[t][i]) : "l"(src + c));
+      }
+    }
+    // per query: the largest x (to 20 bits) with at least k values >= x, a lower bound of the k-th largest
+    uint32_t x[NQ];
+#pragma unroll
+    for (int t = 0; t < NQ; ++t) x[t] = 0u;
+#pragma unroll 1
+    for (int bit = 31; bit >= 12; --bit) {
+#pragma unroll
+      for (int t = 0; t < NQ; ++t) {
+        const uint32_t cand = x[t] | (1u << bit);
+        int cnt = 0;
+#pragma unroll
+        for (int i = 0; i < 5; ++i) cnt += v[t][i] >= cand ? 1 : 0;
+        cnt = __reduce_add_sync(kFull, cnt);
+        if (cnt >= k) x[t] = cand;
+      }
+    }
+#pragma unroll
+    for (int t = 0; t < NQ; ++t) {
+      const int j = jg + t * n_ctas;
+      if (lane == 0 && j < nq_pass && x[t] != 0u) {
+        const float tt = code_score(x[t]) - 2.f * st.eq[j] * maxn;   // NaN (k CTAs hold NaN rows) maps to the top code:
+        if (tt == tt) atomicMax(p.gthr + q0 + j, score_code(tt));   // not a usable bound, skip it
+      }
+    }
+  }
+}
+
 // Service warp (warp 3).  The selection is shared out: CTA c derives T for the queries j = c, c + n_ctas, ... from
 // all CTAs' bests and publishes it (gthr, one word per query); every CTA then picks up all of its pass's
 // thresholds with one coalesced read.  (Each CTA selecting for every query cost 148x the work and 16-32 us per
@@ -678,49 +729,11 @@ __device__ __forceinline__ void filt_service(const TcParams& p, const FiltState 
   const int k = p.k_true;
   if (n_ctas < k || !p.gmax) return;                                  // the bound needs k distinct CTAs
   volatile float* const thr_ext = st.thr_ext;
-  constexpr int NQ = 4;                                               // queries selected side by side (hides the redux latency)
   // The k-th best of everything seen grows like log(rows): refresh eagerly at first, then back off (a spinning
   // warp costs issue slots and, on a power-capped part, clock).
   unsigned pause_ns = 500;
   while (!*done) {
-    for (int jg = cta; jg < nq_pass; jg += n_ctas * NQ) {
-      uint32_t v[NQ][5];
-#pragma unroll
-      for (int t = 0; t < NQ; ++t) {
-        const int j = jg + t * n_ctas < nq_pass ? jg + t * n_ctas : jg;
-        const uint32_t* src = p.gmax + size_t(q0 + j) * p.gmax_stride;
-#pragma unroll
-        for (int i = 0; i < 5; ++i) {
-          const int c = lane + 32 * i;
-          v[t][i] = 0u;
-          if (c < n_ctas) asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v[t][i]) : "l"(src + c));
-        }
-      }
-      // per query: the largest x (to 20 bits) with at least k values >= x, a lower bound of the k-th largest
-      uint32_t x[NQ];
-#pragma unroll
-      for (int t = 0; t < NQ; ++t) x[t] = 0u;
-#pragma unroll 1
-      for (int bit = 31; bit >= 12; --bit) {
-#pragma unroll
-        for (int t = 0; t < NQ; ++t) {
-          const uint32_t cand = x[t] | (1u << bit);
-          int cnt = 0;
-#pragma unroll
-          for (int i = 0; i < 5; ++i) cnt += v[t][i] >= cand ? 1 : 0;
-          cnt = __reduce_add_sync(kFull, cnt);
-          if (cnt >= k) x[t] = cand;
-        }
-      }
-#pragma unroll
-      for (int t = 0; t < NQ; ++t) {
-        const int j = jg + t * n_ctas;
-        if (lane == 0 && j < nq_pass && x[t] != 0u) {
-          const float tt = code_score(x[t]) - 2.f * st.eq[j] * maxn;   // NaN (k CTAs hold NaN rows) maps to the top code:
-          if (tt == tt) atomicMax(p.gthr + q0 + j, score_code(tt));   // not a usable bound, skip it
-        }
-      }
-    }
+    service_select_round(p, st, q0, nq_pass, n_ctas, cta, maxn, lane, k);
     for (int j = lane; j < nq_pass; j += 32) {
       uint32_t code;
       asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(code) : "l"(p.gthr + q0 + j));
@@ -732,6 +745,132 @@ __device__ __forceinline__ void filt_service(const TcParams& p, const FiltState 
     for (unsigned slept = 0; slept < pause_ns && !*done; slept += 1000) __nanosleep(pause_ns < 1000 ? pause_ns : 1000);
     if (pause_ns < 64000) pause_ns *= 2;
   }
+}
+
+// ---- one-shot mode: short scans (the whole bank is at most one tile per SM) -------------------------------------------
+// C2's shape -- 8174 rows x 4096 columns, 256 queries -- is 64 tiles: every CTA owns exactly ONE tile and all CTAs are
+// co-resident.  The persistent kernel's epilogue is built for long scans (thresholds learnt over many tiles, per-CTA
+// lists, ~1000 cycles per list insertion): on a CTA's first tile there are no thresholds, so every row is a candidate
+// and list building cost 75 us of a 134 us scan.  Here instead, with the tile's accumulators staying in tensor memory:
+//   pass A   each query's best upper bound u in this tile (one redux.max per query and warp) -> gmax[q][tile];
+//   barrier  all CTAs of the pass have published (arrival counter in global memory, spin -- co-residency is guaranteed
+//            by the cooperative launch);
+//   select   CTA c derives T = (k-th largest of the tiles' bests) - 2E for queries c, c + n_ctas, ... (service warp) and
+//            publishes it; second barrier;
+//   pass B   the SAME accumulators are scanned again against T: the few rows with u >= T (about k + 10 per query over the
+//            whole bank) are appended to a global candidate array by atomic counter -- no lists, nothing is ever "lost".
+// refine.cu then re-scores the candidates exactly (refine_lists_kernel, direct mode).  A query whose candidates overflow
+// the array (no usable T: NaN, fewer than k tiles) is flagged there and redone by the exact pipeline.
+__device__ __forceinline__ void grid_arrive(uint32_t* ctr) {
+  __threadfence();
+  atomicAdd(ctr, 1u);
+}
+__device__ __forceinline__ void grid_wait(const uint32_t* ctr, uint32_t want) {
+  const long long t0 = clock64();
+  uint32_t v;
+  do {
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+    if (v >= want) break;
+    __nanosleep(100);
+  } while (clock64() - t0 < 2000000000ll);      // ~1 s: give up (thresholds stay open, the queries overflow and are redone exactly)
+}
+
+template <int QP>
+__device__ __forceinline__ void oneshot_epilogue(const TcParams& p, const FiltState st, const float* norms, bool norm_warps,
+                                                 uint32_t tmem_base, uint64_t* tmem_full, int tile, int n_ctas, int pass_global,
+                                                 int q0, int nq_pass, int e, int lane) {
+  const int row_in_tile = e * 32 + lane;
+  const bool dot_mode = !(p.flags & DEVQA_NORMALIZE_BANK);
+  mbar_wait(&tmem_full[0], 0);
+  tc_fence_after();
+  const int64_t grow = int64_t(tile) * kTileRows + row_in_tile;
+  const bool row_live = grow < p.n_rows && !(p.flags & kDbgNoInsert);
+  float inv = 1.f, rowfac = 1.f;
+  {
+    const float ssq = norm_warps ? norms[row_in_tile] : (grow < p.n_rows ? p.row_sumsq[grow] : 1.f);
+    const float nrm = sqrtf(ssq);
+    if (dot_mode) rowfac = nrm;
+    else inv = 1.0f / ((p.flags & DEVQA_NOEPS) ? nrm : fmaxf(nrm, kNormEps));
+  }
+  const uint32_t taddr = tmem_base + (uint32_t(e * 32) << 16);
+  auto load_u = [&](int c, float (&u)[16]) {
+    uint32_t d[16];
+    tmem_ld<16>(taddr + uint32_t(c), d);
+    tmem_ld_wait();
+#pragma unroll
+    for (int i4 = 0; i4 < 4; ++i4) {
+      const float4 eq4 = *reinterpret_cast<const float4*>(st.eq + c + 4 * i4);
+      u[4 * i4 + 0] = fmaf(__uint_as_float(d[4 * i4 + 0]), inv, eq4.x * rowfac);
+      u[4 * i4 + 1] = fmaf(__uint_as_float(d[4 * i4 + 1]), inv, eq4.y * rowfac);
+      u[4 * i4 + 2] = fmaf(__uint_as_float(d[4 * i4 + 2]), inv, eq4.z * rowfac);
+      u[4 * i4 + 3] = fmaf(__uint_as_float(d[4 * i4 + 3]), inv, eq4.w * rowfac);
+    }
+  };
+  uint32_t* const best_s = st.hit_id;
+  for (int j = e * 32 + lane; j < QP; j += 128) best_s[j] = 0u;
+  epilogue_barrier();
+  // ---- pass A: the tile's best upper bound per query ----
+#pragma unroll 1
+  for (int c = 0; c < QP; c += 16) {
+    float u[16];
+    load_u(c, u);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const uint32_t m = __reduce_max_sync(kFull, row_live ? score_code(u[i]) : 0u);
+      if (lane == 0) atomicMax(best_s + c + i, m);
+    }
+  }
+  epilogue_barrier();
+  for (int j = e * 32 + lane; j < nq_pass; j += 128) p.gmax[size_t(q0 + j) * p.gmax_stride + tile] = best_s[j];
+  epilogue_barrier();
+  if (e == 0 && lane == 0) {
+    grid_arrive(p.gbar + 2 * pass_global);                            // this CTA's bests are published
+    grid_wait(p.gbar + 2 * pass_global + 1, uint32_t(n_ctas));        // every CTA's share of the thresholds is
+  }
+  epilogue_barrier();
+  for (int j = e * 32 + lane; j < nq_pass; j += 128) {
+    uint32_t code;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(code) : "l"(p.gthr + q0 + j));
+    st.thr[j] = code != 0u ? code_score(code) : -INFINITY;            // (dead queries keep +inf)
+  }
+  epilogue_barrier();
+  // ---- pass B: the same accumulators against the thresholds; survivors go straight to the candidate array ----
+#pragma unroll 1
+  for (int c = 0; c < QP; c += 16) {
+    float u[16];
+    load_u(c, u);
+    uint32_t mask = 0;
+#pragma unroll
+    for (int i4 = 0; i4 < 4; ++i4) {
+      const float4 th4 = *reinterpret_cast<const float4*>(st.thr + c + 4 * i4);
+      mask |= (!(u[4 * i4 + 0] < th4.x) ? 1u : 0u) << (4 * i4 + 0);     // NaN passes, like torch.topk ranks it first
+      mask |= (!(u[4 * i4 + 1] < th4.y) ? 1u : 0u) << (4 * i4 + 1);
+      mask |= (!(u[4 * i4 + 2] < th4.z) ? 1u : 0u) << (4 * i4 + 2);
+      mask |= (!(u[4 * i4 + 3] < th4.w) ? 1u : 0u) << (4 * i4 + 3);
+    }
+    if (!row_live) mask = 0u;
+    if (mask != 0u) {                                                  // rare
+      const uint32_t id = uint32_t(p.idmap(grow));
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        if ((mask >> i) & 1u) {
+          const int q = q0 + c + i;
+          const uint32_t idx = atomicAdd(p.ocount + q, 1u);
+          if (idx < uint32_t(p.ocap)) p.ocand[size_t(q) * p.ocap + idx] = pack_key(u[i], id);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+}
+
+__device__ __forceinline__ void oneshot_service(const TcParams& p, const FiltState st, int q0, int nq_pass, int n_ctas, int cta,
+                                                int pass_global, float maxn, int lane) {
+  if (lane == 0) grid_wait(p.gbar + 2 * pass_global, uint32_t(n_ctas));   // every tile's bests are in gmax
+  __syncwarp();
+  service_select_round(p, st, q0, nq_pass, n_ctas, cta, maxn, lane, p.k_true);
+  __syncwarp();
+  if (lane == 0) grid_arrive(p.gbar + 2 * pass_global + 1);
 }
 
 // PAIR: two CTAs of one TPC (cluster of 2) run ONE MMA of M = 256 per instruction (cta_group::2): each CTA streams
@@ -778,6 +917,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap bank_map, const __grid_consta
   const int tile0 = int(blockIdx.x) / p.passes, tile_step = int(gridDim.x) / p.passes;
   const int q0 = p.q0 + pass_local * QP;
   const int nq_pass = min(QP, p.n_queries - q0);
+  pdl_wait();                                            // (programmatic dependent launch: the previous kernel's results)
   if (p.need) {                                          // conditional (fallback) launch: nothing to do for most passes
     int any = 0;
     for (int i = threadIdx.x; i < nq_pass; i += kTcThreads) any |= int(p.need[q0 + i] != 0u);
@@ -1042,7 +1182,13 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap bank_map, const __grid_consta
     }
   } else if (SCANEPI && warp == 3) {
     // ===== service warp: threshold exchange between CTAs =====
-    filt_service(p, st, q0, nq_pass, tile_step, tile0, maxn, lane);
+    if (FILT && p.oneshot) oneshot_service(p, st, q0, nq_pass, tile_step, tile0, p.q0 / QP + pass_local, maxn, lane);
+    else filt_service(p, st, q0, nq_pass, tile_step, tile0, maxn, lane);
+  } else if (warp >= 8 && FILT && p.oneshot) {
+    // ===== epilogue warps, one tile per CTA: two passes over the accumulators, candidates straight to global memory =====
+    if constexpr (FILT)
+      oneshot_epilogue<QP>(p, st, norms, norm_warps, tmem_base, tmem_full, tile0, tile_step, p.q0 / QP + pass_local, q0, nq_pass,
+                           warp - 8, lane);
   } else if (warp >= 8 && SCANEPI) {
     // ===== epilogue warps: scan + hit queue (filt_epilogue) =====
     filt_epilogue<QP, FILT ? 1 : 3>(p, st, lists, norms, norm_warps, tmem_base, tmem_full, tmem_empty, tile0, tile_step, n_my, boot,
@@ -1167,7 +1313,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap bank_map, const __grid_consta
   // ---- teardown: candidates out, TMEM back ------------------------------------------------------
   tc_fence_before();
   __syncthreads();
-  for (int q = warp; q < nq_pass; q += kTcThreads / 32) {
+  for (int q = warp; q < nq_pass && !p.oneshot; q += kTcThreads / 32) {
     uint64_t* out = p.cand + (size_t(tile0) * p.n_queries + (q0 + q)) * p.kcap;
     const uint64_t* src = lists + size_t(q) * p.kcap;
     for (int i = lane; i < p.kcap; i += 32) out[i] = src[i];
@@ -1189,6 +1335,7 @@ __global__ void __launch_bounds__(256) prep_queries_kernel(const float* __restri
                                                            float* __restrict__ qcat, uint32_t* __restrict__ gthr,
                                                            const uint32_t* __restrict__ need, uint32_t* __restrict__ gmax,
                                                            int gmax_stride) {
+  pdl_wait();
   if (blockIdx.x == 0)
     for (int i = threadIdx.x; i < q_pad; i += blockDim.x) gthr[i] = 0u;
   if (gmax)                                              // threshold exchange: no CTA has published anything yet
@@ -1233,97 +1380,94 @@ __global__ void __launch_bounds__(256) prep_queries_kernel(const float* __restri
   }
 }
 
-// Filter variant (kTf32x1): one TF32 plane (rounded to nearest), [n_kblocks][qp rows][32 cols] per pass, plus the
-// per-query scale and norm that refine.cu needs to re-create the exact fp32 query and the error bound.
-__global__ void __launch_bounds__(256) prep_queries_filt_kernel(const float* __restrict__ q, int64_t q_ld, int n_queries, int dim,
+// Filter variants (kTf32x1 / kBf16x1): ONE plane, rounded to nearest -- TF32 words [n_kblocks][qp rows][32 cols] or bf16
+// [n_kblocks][qp rows][64 cols] per pass -- plus the per-query scale and norm that refine.cu needs to re-create the exact
+// fp32 query and the error bound.  One CTA per (padded) query: the row is staged in shared memory by all threads
+// (full memory-level parallelism; one warp walking a 4096-column query was 13.5 us of C2's 240), warp 0 then forms the
+// norms from shared memory in EXACTLY the stream kernel's order (lane-strided FMAs, xor butterfly: the scale has to be
+// bit-identical to scan_stream.cu's for the re-scored results to be), and all threads write the operand.
+// Also zeroes, grid-wide: gthr / seed_u [q_pad], the threshold exchange table gmax, and `zero_words` (one-shot
+// mode: arrival counters + candidate counts).
+template <bool BF16>
+__global__ void __launch_bounds__(128) prep_queries_filt_kernel(const float* __restrict__ q, int64_t q_ld, int n_queries, int dim,
                                                                 int qp, int n_kblocks, int q_pad, unsigned flags,
-                                                                float* __restrict__ qcat, uint32_t* __restrict__ gthr,
+                                                                void* __restrict__ qcat_, uint32_t* __restrict__ gthr,
                                                                 float* __restrict__ qinv, float* __restrict__ qerr,
                                                                 uint32_t* __restrict__ seed_u, uint32_t* __restrict__ gmax,
-                                                                int gmax_stride) {
-  if (blockIdx.x == 0)
-    for (int i = threadIdx.x; i < q_pad; i += blockDim.x) { gthr[i] = 0u; seed_u[i] = 0u; }
+                                                                int gmax_stride, uint32_t* __restrict__ zero_words, int n_zero) {
+  extern __shared__ __align__(16) float srow[];          // [d_pad]
+  __shared__ float s_inv;
+  constexpr int EK = BF16 ? 64 : 32;                     // columns per 128-byte k-block row
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  pdl_wait();
+  for (int i = blockIdx.x * nthr + tid; i < q_pad; i += gridDim.x * nthr) { gthr[i] = 0u; seed_u[i] = 0u; }
   if (gmax)                                              // threshold exchange: no CTA has published anything yet
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < q_pad * gmax_stride; i += gridDim.x * blockDim.x) gmax[i] = 0u;
-  const int lane = threadIdx.x & 31;
-  const int warps = gridDim.x * (blockDim.x >> 5);
-  const int d_pad = n_kblocks * kBlockK;
-  for (int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < q_pad; r += warps) {
-    float inv = 0.f;
-    const float* src = q + size_t(r < n_queries ? r : 0) * q_ld;
-    if (r < n_queries) {
-      inv = 1.f;
-      if (flags & DEVQA_NORMALIZE_QUERY) {
-        float ss = 0.f;
-        for (int c = lane; c < dim; c += 32) { const float x = src[c]; ss = fmaf(x, x, ss); }
+    for (int i = blockIdx.x * nthr + tid; i < q_pad * gmax_stride; i += gridDim.x * nthr) gmax[i] = 0u;
+  for (int i = blockIdx.x * nthr + tid; i < n_zero; i += gridDim.x * nthr) zero_words[i] = 0u;
+  const int lane = tid & 31, warp = tid >> 5;
+  const int d_pad = n_kblocks * EK;
+  for (int r = blockIdx.x; r < q_pad; r += gridDim.x) {
+    const bool live = r < n_queries;
+    const float* src = q + size_t(live ? r : 0) * q_ld;
+    __syncthreads();
+    if (live && (dim & 3) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {   // 128-bit loads, 8 in flight per thread
+      const float4* src4 = reinterpret_cast<const float4*>(src);
+      float4* dst4 = reinterpret_cast<float4*>(srow);
+#pragma unroll 8
+      for (int c = tid; c < dim / 4; c += nthr) dst4[c] = __ldg(src4 + c);
+      for (int c = dim + tid; c < d_pad; c += nthr) srow[c] = 0.f;
+    } else {
+#pragma unroll 8
+      for (int c = tid; c < d_pad; c += nthr) srow[c] = (live && c < dim) ? src[c] : 0.f;
+    }
+    __syncthreads();
+    if (warp == 0) {
+      float inv = 0.f;
+      if (live) {
+        inv = 1.f;
+        if (flags & DEVQA_NORMALIZE_QUERY) {
+          float ss = 0.f;
+          for (int c = lane; c < dim; c += 32) { const float x = srow[c]; ss = fmaf(x, x, ss); }
 #pragma unroll
-        for (int off = 16; off >= 1; off >>= 1) ss += __shfl_xor_sync(kFull, ss, off);
-        const float nrm = sqrtf(ss);
-        inv = 1.0f / ((flags & DEVQA_NOEPS) ? nrm : fmaxf(nrm, kNormEps));
+          for (int off = 16; off >= 1; off >>= 1) ss += __shfl_xor_sync(kFull, ss, off);
+          const float nrm = sqrtf(ss);
+          inv = 1.0f / ((flags & DEVQA_NOEPS) ? nrm : fmaxf(nrm, kNormEps));
+        }
+      }
+      float nn = 0.f;                                    // ||query as used||^2
+      for (int c = lane; c < d_pad; c += 32) { const float x = srow[c] * inv; nn = fmaf(x, x, nn); }
+#pragma unroll
+      for (int off = 16; off >= 1; off >>= 1) nn += __shfl_xor_sync(kFull, nn, off);
+      if (lane == 0) {
+        s_inv = inv;
+        if (live) {
+          qinv[r] = inv;
+          qerr[r] = tc_filter_relerr(dim, BF16) * sqrtf(nn) * ((flags & DEVQA_DEBUG_TIGHT_BOUND) ? 0.015625f : 1.f);
+        }
       }
     }
+    __syncthreads();
+    const float inv = s_inv;
     const int pass = r / qp, rp = r % qp;
-    float* base = qcat + size_t(pass) * n_kblocks * (qp * kBlockK);
-    float nn = 0.f;
-    for (int c = lane; c < d_pad; c += 32) {
-      const float x = (r < n_queries && c < dim) ? src[c] * inv : 0.f;
-      nn = fmaf(x, x, nn);
-      uint32_t hb;
-      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(x));
-      const int kb = c / kBlockK, w = c % kBlockK;
-      base[size_t(kb) * (qp * kBlockK) + rp * kBlockK + (((w >> 2) ^ (rp & 7)) << 2) + (w & 3)] = __uint_as_float(hb);
-    }
-#pragma unroll
-    for (int off = 16; off >= 1; off >>= 1) nn += __shfl_xor_sync(kFull, nn, off);
-    if (lane == 0 && r < n_queries) {
-      qinv[r] = inv;
-      qerr[r] = tc_filter_relerr(dim) * sqrtf(nn) * ((flags & DEVQA_DEBUG_TIGHT_BOUND) ? 0.015625f : 1.f);
-    }
-  }
-}
-
-// Filter on a bf16 bank (kBf16x1): one bf16 plane (rounded to nearest), [n_kblocks][qp rows][64 cols] per pass.
-__global__ void __launch_bounds__(256) prep_queries_filt_bf16_kernel(const float* __restrict__ q, int64_t q_ld, int n_queries, int dim,
-                                                                     int qp, int n_kblocks, int q_pad, unsigned flags,
-                                                                     __nv_bfloat16* __restrict__ qcat, uint32_t* __restrict__ gthr,
-                                                                     float* __restrict__ qinv, float* __restrict__ qerr,
-                                                                     uint32_t* __restrict__ seed_u, uint32_t* __restrict__ gmax,
-                                                                     int gmax_stride) {
-  if (blockIdx.x == 0)
-    for (int i = threadIdx.x; i < q_pad; i += blockDim.x) { gthr[i] = 0u; seed_u[i] = 0u; }
-  if (gmax)
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < q_pad * gmax_stride; i += gridDim.x * blockDim.x) gmax[i] = 0u;
-  const int lane = threadIdx.x & 31;
-  const int warps = gridDim.x * (blockDim.x >> 5);
-  const int d_pad = n_kblocks * 64;
-  for (int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < q_pad; r += warps) {
-    float inv = 0.f;
-    const float* src = q + size_t(r < n_queries ? r : 0) * q_ld;
-    if (r < n_queries) {
-      inv = 1.f;
-      if (flags & DEVQA_NORMALIZE_QUERY) {
-        float ss = 0.f;
-        for (int c = lane; c < dim; c += 32) { const float x = src[c]; ss = fmaf(x, x, ss); }
-#pragma unroll
-        for (int off = 16; off >= 1; off >>= 1) ss += __shfl_xor_sync(kFull, ss, off);
-        const float nrm = sqrtf(ss);
-        inv = 1.0f / ((flags & DEVQA_NOEPS) ? nrm : fmaxf(nrm, kNormEps));
+    if constexpr (BF16) {
+      __nv_bfloat16* base = static_cast<__nv_bfloat16*>(qcat_) + size_t(pass) * n_kblocks * (qp * 64);
+      for (int c = tid; c < d_pad; c += nthr) {
+        const int kb = c / 64, w = c % 64;
+        base[size_t(kb) * (qp * 64) + rp * 64 + (((w >> 3) ^ (rp & 7)) << 3) + (w & 7)] = __float2bfloat16_rn(srow[c] * inv);
       }
-    }
-    const int pass = r / qp, rp = r % qp;
-    __nv_bfloat16* base = qcat + size_t(pass) * n_kblocks * (qp * 64);
-    float nn = 0.f;
-    for (int c = lane; c < d_pad; c += 32) {
-      const float x = (r < n_queries && c < dim) ? src[c] * inv : 0.f;
-      nn = fmaf(x, x, nn);
-      const int kb = c / 64, w = c % 64;
-      base[size_t(kb) * (qp * 64) + rp * 64 + (((w >> 3) ^ (rp & 7)) << 3) + (w & 7)] = __float2bfloat16_rn(x);
-    }
-#pragma unroll
-    for (int off = 16; off >= 1; off >>= 1) nn += __shfl_xor_sync(kFull, nn, off);
-    if (lane == 0 && r < n_queries) {
-      qinv[r] = inv;
-      qerr[r] = tc_filter_relerr(dim, true) * sqrtf(nn) * ((flags & DEVQA_DEBUG_TIGHT_BOUND) ? 0.015625f : 1.f);
+    } else {
+      float* base = static_cast<float*>(qcat_) + size_t(pass) * n_kblocks * (qp * kBlockK);
+      for (int c4 = tid; c4 < d_pad / 4; c4 += nthr) {                  // one 16-byte chunk of the swizzled row per store
+        const float4 v = reinterpret_cast<const float4*>(srow)[c4];
+        uint32_t h0, h1, h2, h3;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h0) : "f"(v.x * inv));
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h1) : "f"(v.y * inv));
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h2) : "f"(v.z * inv));
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h3) : "f"(v.w * inv));
+        const int kb = c4 / (kBlockK / 4), w4 = c4 % (kBlockK / 4);
+        float4* dst = reinterpret_cast<float4*>(base + size_t(kb) * (qp * kBlockK) + rp * kBlockK) + (w4 ^ (rp & 7));
+        *dst = make_float4(__uint_as_float(h0), __uint_as_float(h1), __uint_as_float(h2), __uint_as_float(h3));
+      }
     }
   }
 }
@@ -1334,6 +1478,7 @@ __global__ void __launch_bounds__(256) prep_queries_bf16_kernel(const float* __r
                                                                 int qp, int n_kblocks, int q_pad, unsigned flags,
                                                                 __nv_bfloat16* __restrict__ qcat, uint32_t* __restrict__ gthr,
                                                                 uint32_t* __restrict__ gmax, int gmax_stride) {
+  pdl_wait();
   if (blockIdx.x == 0)
     for (int i = threadIdx.x; i < q_pad; i += blockDim.x) gthr[i] = 0u;
   if (gmax)
@@ -1424,7 +1569,7 @@ size_t scan_tc_qcat_bytes(int mode, int64_t dim, int q_pad) {
 
 // Queries per pass + pipeline depth that fit in shared memory / tensor memory for this list capacity.
 int scan_tc_plan(int mode, int n_queries, int64_t dim, int kcap, bool cached_norms, int64_t n_tiles, int sm_count,
-                 unsigned flags, int* qp_out, int* stages_out, bool* pair_out) {
+                 unsigned flags, int* qp_out, int* stages_out, bool* pair_out, bool oneshot) {
   *pair_out = false;
   const bool filt = mode == kTcTf32x1 || mode == kTcBf16x1;
   // more than one K-set (1024 fp32 / 2048 bf16 columns) sums K-sets in the epilogue's registers (MULTI):
@@ -1434,8 +1579,15 @@ int scan_tc_plan(int mode, int n_queries, int64_t dim, int kcap, bool cached_nor
   const int q16 = (n_queries + 15) / 16 * 16;
   while (qp > 16 && qp / 2 >= q16) qp >>= 1;
   // banks of fewer tiles than SMs: narrower passes run side by side, so that tiles x passes covers the machine
-  if (filt)
+  if (filt && oneshot) {
+    // (tried: ONE 256-query pass on CTA pairs, half of the query operand per CTA -- 185 us against 150 at C2: 64 SMs
+    // cannot pull the operands out of L2 as fast as 128 can)
+    // one tile per CTA, every CTA of the launch co-resident: halve the pass width only while one launch still holds
+    // all passes (C2: 64 tiles, 256 queries -> two 128-query passes = 128 CTAs; four 64-query passes would not fit)
+    while (qp > 32 && n_tiles * ((n_queries + qp / 2 - 1) / (qp / 2)) <= sm_count) qp >>= 1;
+  } else if (filt) {
     while (qp > 32 && n_tiles * ((n_queries + qp - 1) / qp) < sm_count) qp >>= 1;
+  }
   for (; qp >= 16; qp >>= 1) {
     // 256 queries per pass on a long scan: CTA pairs (each CTA holds half of the query operand)
     const bool pair = filt && cached_norms && (qp == 256 || (qp >= 64 && mode == kTcTf32x1 && (flags & kDbgPairAll))) &&
@@ -1456,21 +1608,25 @@ int scan_tc_plan(int mode, int n_queries, int64_t dim, int kcap, bool cached_nor
 // qcat must hold scan_tc_qcat_bytes(); q_pad is a multiple of qp; gthr [q_pad] is zeroed here.
 int scan_tc_prep_queries(int mode, const float* queries, int64_t query_ld, int n_queries, int qp, int q_pad,
                          int64_t dim, unsigned flags, void* qcat, uint32_t* gthr, float* qinv, float* qerr,
-                         uint32_t* seed_u, uint32_t* gmax, int gmax_stride, const uint32_t* need, cudaStream_t stream) {
+                         uint32_t* seed_u, uint32_t* gmax, int gmax_stride, const uint32_t* need, cudaStream_t stream,
+                         uint32_t* zero_words, int n_zero) {
   const int n_kblocks = scan_tc_kblocks(mode, dim);
   const int grid = (q_pad + 7) / 8;
   if (mode == kTcTf32x3)
-    prep_queries_kernel<<<grid, 256, 0, stream>>>(queries, query_ld, n_queries, int(dim), qp, n_kblocks, q_pad, flags,
-                                                  static_cast<float*>(qcat), gthr, need, gmax, gmax_stride);
+    DEVQA_CUDA(launch_pdl(prep_queries_kernel, dim3(grid), dim3(256), 0, stream, queries, query_ld, n_queries, int(dim), qp,
+                          n_kblocks, q_pad, flags, static_cast<float*>(qcat), gthr, need, gmax, gmax_stride));
   else if (mode == kTcBf16x3)
-    prep_queries_bf16_kernel<<<grid, 256, 0, stream>>>(queries, query_ld, n_queries, int(dim), qp, n_kblocks, q_pad, flags,
-                                                       static_cast<__nv_bfloat16*>(qcat), gthr, gmax, gmax_stride);
-  else if (mode == kTcBf16x1)
-    prep_queries_filt_bf16_kernel<<<grid, 256, 0, stream>>>(queries, query_ld, n_queries, int(dim), qp, n_kblocks, q_pad, flags,
-                                                            static_cast<__nv_bfloat16*>(qcat), gthr, qinv, qerr, seed_u, gmax, gmax_stride);
-  else
-    prep_queries_filt_kernel<<<grid, 256, 0, stream>>>(queries, query_ld, n_queries, int(dim), qp, n_kblocks, q_pad, flags,
-                                                       static_cast<float*>(qcat), gthr, qinv, qerr, seed_u, gmax, gmax_stride);
+    DEVQA_CUDA(launch_pdl(prep_queries_bf16_kernel, dim3(grid), dim3(256), 0, stream, queries, query_ld, n_queries, int(dim),
+                          qp, n_kblocks, q_pad, flags, static_cast<__nv_bfloat16*>(qcat), gthr, gmax, gmax_stride));
+  else {
+    const int ek = mode == kTcBf16x1 ? 64 : 32;
+    const size_t smem = size_t(n_kblocks) * ek * 4;
+    const int fgrid = q_pad < 1184 ? q_pad : 1184;          // one CTA per query (8 per SM at most)
+    auto kern = mode == kTcBf16x1 ? prep_queries_filt_kernel<true> : prep_queries_filt_kernel<false>;
+    if (smem > 40 * 1024) DEVQA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    DEVQA_CUDA(launch_pdl(kern, dim3(fgrid), dim3(128), smem, stream, queries, query_ld, n_queries, int(dim), qp, n_kblocks,
+                          q_pad, flags, qcat, gthr, qinv, qerr, seed_u, gmax, gmax_stride, zero_words, n_zero));
+  }
   DEVQA_CUDA(cudaGetLastError());
   count_launch();
   return DEVQA_OK;
@@ -1499,6 +1655,7 @@ int scan_tc_launch(const ScanParams& sp, int mode, const void* qcat, uint32_t* g
   p.top_k = sp.top_k; p.kcap = sp.kcap; p.stages = stages; p.passes = passes; p.flags = sp.flags;
   p.cand = sp.cand; p.gthr = gthr; p.idmap = sp.idmap; p.row_sumsq = sp.row_sumsq;
   p.need = sp.need;
+  p.oneshot = sp.oneshot; p.gbar = sp.gbar; p.ocount = sp.ocount; p.ocand = sp.ocand; p.ocap = sp.ocap;
   p.gmax = sp.gmax; p.gmax_stride = sp.gmax_stride; p.lostu = sp.lostu; p.qerr = sp.qerr; p.seed_u = sp.seed_u; p.bank_max_sumsq = sp.bank_max_sumsq; p.k_true = sp.k_true > 0 ? sp.k_true : sp.top_k;
   // pass index = q0 / qp; one pass = n_kblocks * parts * qp rows of 128 bytes (32 words)
   p.qcat = static_cast<const float*>(qcat) + size_t(sp.q0 / qp) * size_t(n_kblocks) * parts * qp * 32;
@@ -1538,13 +1695,25 @@ int scan_tc_launch(const ScanParams& sp, int mode, const void* qcat, uint32_t* g
   if (pair) {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(unsigned(grid)); cfg.blockDim = dim3(kTcThreads); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 2 : 1;
+    DEVQA_CUDA(cudaLaunchKernelEx(&cfg, kern, bank_map, p));
+  } else if (p.oneshot) {
+    // the CTAs wait for each other (oneshot_epilogue): a cooperative launch guarantees they are all resident
+    DEVQA_REQUIRE(filt && ctas_per_pass == p.n_tiles, "tcgen05 scan: one-shot mode needs one CTA per tile");
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(unsigned(grid)); cfg.blockDim = dim3(kTcThreads); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeCooperative;
+    attr[0].val.cooperative = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
     DEVQA_CUDA(cudaLaunchKernelEx(&cfg, kern, bank_map, p));
   } else {
-    kern<<<grid, kTcThreads, smem, stream>>>(bank_map, p);
+    DEVQA_CUDA(launch_pdl(kern, dim3(unsigned(grid)), dim3(kTcThreads), smem, stream, bank_map, p));
   }
   DEVQA_CUDA(cudaGetLastError());
   count_launch();

@@ -32,6 +32,7 @@ __global__ void __launch_bounds__(kSelThreads) select_compact_kernel(const Selec
   const int q = blockIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const float* src = p.queries + size_t(q) * p.query_ld;
+  pdl_wait();
   if (warp == 0) {                                                   // scan_stream.cu's prologue arithmetic
     float inv = 1.f;
     if (p.flags & DEVQA_NORMALIZE_QUERY) {
@@ -109,7 +110,7 @@ int select_compact_launch(const SelectParams& p, cudaStream_t stream) {
       ? (vec ? select_compact_kernel<float, true> : select_compact_kernel<float, false>)
       : (vec ? select_compact_kernel<__nv_bfloat16, true> : select_compact_kernel<__nv_bfloat16, false>);
   if (smem > 40 * 1024) DEVQA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-  kern<<<unsigned(p.n_queries), kSelThreads, smem, stream>>>(p);
+  DEVQA_CUDA(launch_pdl(kern, dim3(unsigned(p.n_queries)), dim3(kSelThreads), smem, stream, p));
   DEVQA_CUDA(cudaGetLastError());
   count_launch();
   return DEVQA_OK;

@@ -82,6 +82,8 @@ extern "C" {
                                            library would scan with 3xTF32 alone (fewer than 8 tiles per SM)     */
 #define DEVQA_DEBUG_TIGHT_BOUND (1u << 12) /* tests: run the filter with 1/64 of its error bound, so that the bound IS
                                               violated and the canary (devqa_filter_bound_violations) has to catch it */
+#define DEVQA_DEBUG_NO_ONESHOT (1u << 13)  /* tests/benchmarks: short scans through the persistent kernel's list epilogue
+                                              instead of the one-shot mode (one tile per CTA, grid-wide threshold exchange) */
 #define DEVQA_DEBUG_FILTER_ONLY (1u << 22) /* tests: return the TF32 filter's approximate top-k as is (no exact
                                               re-scoring) so that its error bound can be checked            */
 

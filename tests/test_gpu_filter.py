@@ -478,3 +478,44 @@ def test_bf16_bank_filter_matches_the_stream_kernel_bit_for_bit(n, d, nq, k, nb,
     assert torch.equal(a[1], b[1]) and torch.equal(a[0], b[0])
     assert nfb <= max(1, nq // 8)
     fb.close()
+
+
+@pytest.mark.parametrize("n,d,nq,k,nb", [(8174, 4096, 256, 16, "eps"), (2100, 768, 300, 16, "eps"), (18900, 384, 64, 32, None),
+                                         (18944, 128, 1100, 5, "eps"), (4100, 256, 33, 32, "noeps"), (6345, 384, 16, 16, "eps")])
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+def test_one_shot_mode_for_short_scans(n, d, nq, k, nb, dtype):
+    """Banks of at most one tile per SM (and at least top_k tiles): one tile per CTA, grid-wide threshold exchange,
+    candidates straight to a global array (scan_tc.cu oneshot_epilogue).  Bit-identical to the stream kernel and to
+    the persistent kernel's list epilogue (DEVQA_DEBUG_NO_ONESHOT), C2's shape included."""
+    bank = _hidden_like(n, d, n + d) if d == 4096 else _randn(n, d, n + d, unit=False)
+    q = _hidden_like(nq, d, nq + 1) if d == 4096 else _randn(nq, d, nq + 1, unit=False)
+    fb = FactBank.from_embeddings(bank, dtype=dtype)
+    _fallbacks(); _violations()
+    a = fb.search(q.cuda(), k, normalize_bank=nb, normalize_query=nb, flags=FILTER)
+    nfb, nv = _fallbacks(), _violations()
+    b = fb.search(q.cuda(), k, normalize_bank=nb, normalize_query=nb, flags=FILTER | L.DEBUG_NO_ONESHOT)
+    _fallbacks()
+    if d <= 1024:
+        c = fb.search(q.cuda(), k, normalize_bank=nb, normalize_query=nb, flags=L.FORCE_STREAM)
+        assert torch.equal(a[1], c[1]) and torch.equal(a[0], c[0])
+    assert torch.equal(a[1], b[1]) and torch.equal(a[0], b[0])
+    assert nv == 0 and nfb <= max(1, nq // 16)
+    stored = bank.to(torch.bfloat16).float() if dtype == "bf16" else bank
+    truth = ss.truth_scores_fp64(q, stored, normalize_bank=bool(nb), normalize_query=bool(nb))
+    ss.compare_topk(a[0].cpu().numpy(), a[1].cpu().numpy(), truth, k, gap=GAP, rtol=RTOL, atol=ATOL)
+    fb.close()
+
+
+def test_one_shot_mode_overflow_takes_the_fallback():
+    """NaN rows in >= k tiles leave no usable threshold: every row is a candidate, the array overflows, the query is
+    flagged and the exact pipeline answers it."""
+    bank = _randn(5000, 128, 3, unit=False)
+    bank[::100, 7] = float("nan")                      # 50 NaN rows spread over all 40 tiles
+    q = _randn(12, 128, 4, unit=False)
+    fb = FactBank.from_embeddings(bank)
+    _fallbacks()
+    s, i = fb.search(q.cuda(), 8, flags=FILTER)
+    assert _fallbacks() >= 1
+    s2, i2 = fb.search(q.cuda(), 8, flags=L.FORCE_STREAM)
+    assert torch.isnan(s).all() and torch.equal(i, i2)
+    fb.close()
