@@ -59,6 +59,11 @@ SIGNATURES = {
     "devqa_dist_unique_id": (_i, [_p]),
     "devqa_dist_init": (_i, [C.POINTER(_p), _p, _i, _i, _i]),
     "devqa_dist_destroy": (_i, [_p]),
+    "devqa_dist_p2p_export": (_i, [_p, _p]),
+    "devqa_dist_p2p_connect": (_i, [_p, _p]),
+    "devqa_dist_p2p_set": (_i, [_p, _i]),
+    "devqa_dist_p2p_enabled": (_i, [_p]),
+    "devqa_dist_p2p_timeouts": (_i, [_p, C.POINTER(_i64)]),
     "devqa_dist_rank": (_i, [_p]),
     "devqa_dist_world": (_i, [_p]),
     "devqa_bank_search_dist": (_i, [_p, _p, _p, _i64, _i64, _i, _u, _p, _p, _p]),

@@ -502,6 +502,16 @@ struct devqa_bank {
 struct devqa_comm {
   int rank = 0, world = 1, device = 0;
   void* nccl = nullptr;   // ncclComm_t
+  // Peer-to-peer exchange of the local top-k (scan.cuh, P2pExchange).  Mailbox of a rank, in its own memory:
+  //   [0, 256)                      header (word 0: waits that timed out)
+  //   flags  [2 slots][world][kP2pMaxQ]  u32    sequence number of the call whose keys have arrived
+  //   data   [2 slots][world][kP2pMaxKeys] u64  the keys, per slot laid out [source rank][n_queries][top_k]
+  unsigned char* mbox = nullptr;                             // this rank's mailbox (cudaMalloc, exported by IPC handle)
+  unsigned char* peer_mbox[devqa::kP2pMaxWorld] = {};        // every rank's mailbox as mapped into this process
+  bool p2p = false;
+  size_t flags_off() const { return 256; }
+  size_t data_off() const { return 256 + size_t(2) * world * devqa::kP2pMaxQ * 4; }
+  size_t mbox_bytes() const { return data_off() + size_t(2) * world * devqa::kP2pMaxKeys * 8; }
 };
 
 namespace devqa {
@@ -1104,8 +1114,75 @@ int devqa_dist_init(devqa_comm** out, const void* id_bytes, int rank, int world,
 int devqa_dist_destroy(devqa_comm* c) {
   if (!c) return DEVQA_OK;
   const NcclApi* api = nccl_api();
+  if (c->mbox) {
+    DeviceGuardLite guard(c->device);
+    cudaDeviceSynchronize();
+    for (int r = 0; r < c->world; ++r)
+      if (r != c->rank && c->peer_mbox[r]) cudaIpcCloseMemHandle(c->peer_mbox[r]);
+    cudaFree(c->mbox);
+  }
   if (api && c->nccl) api->CommDestroy(c->nccl);
   delete c;
+  return DEVQA_OK;
+}
+
+// ---- peer-to-peer mailboxes: export -> (handles travel over any host channel) -> connect -------------------------
+int devqa_dist_p2p_export(devqa_comm* c, void* out_handle_64_bytes) {
+  DEVQA_REQUIRE(c && out_handle_64_bytes, "null argument");
+  DEVQA_REQUIRE(c->world <= kP2pMaxWorld, "world %d exceeds the mailbox layout", c->world);
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  DEVQA_ON_DEVICE(c->device);
+  if (!c->mbox) {
+    DEVQA_CUDA(cudaMalloc(reinterpret_cast<void**>(&c->mbox), c->mbox_bytes()));
+    DEVQA_CUDA(cudaMemset(c->mbox, 0, c->data_off()));      // flags start at 0; sequence numbers start at 1
+    DEVQA_CUDA(cudaDeviceSynchronize());
+  }
+  cudaIpcMemHandle_t h;
+  DEVQA_CUDA(cudaIpcGetMemHandle(&h, c->mbox));
+  memcpy(out_handle_64_bytes, &h, 64);
+  return DEVQA_OK;
+}
+
+int devqa_dist_p2p_connect(devqa_comm* c, const void* handles_world_x_64_bytes) {
+  DEVQA_REQUIRE(c && handles_world_x_64_bytes, "null argument");
+  DEVQA_REQUIRE(c->mbox != nullptr, "call devqa_dist_p2p_export first");
+  DEVQA_ON_DEVICE(c->device);
+  for (int r = 0; r < c->world; ++r) {
+    if (r == c->rank) { c->peer_mbox[r] = c->mbox; continue; }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, static_cast<const char*>(handles_world_x_64_bytes) + size_t(r) * 64, 64);
+    void* ptr = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      for (int k = 0; k < r; ++k)
+        if (k != c->rank && c->peer_mbox[k]) { cudaIpcCloseMemHandle(c->peer_mbox[k]); c->peer_mbox[k] = nullptr; }
+      set_error("cudaIpcOpenMemHandle for rank %d failed: %s (staying on ncclAllGather)", r, cudaGetErrorString(e));
+      return DEVQA_E_UNSUPPORTED;
+    }
+    c->peer_mbox[r] = static_cast<unsigned char*>(ptr);
+  }
+  c->p2p = true;
+  return DEVQA_OK;
+}
+
+int devqa_dist_p2p_set(devqa_comm* c, int enable) {
+  DEVQA_REQUIRE(c != nullptr, "comm is null");
+  DEVQA_REQUIRE(!enable || c->peer_mbox[c->rank] != nullptr, "mailboxes are not connected");
+  c->p2p = enable != 0;
+  return DEVQA_OK;
+}
+int devqa_dist_p2p_enabled(const devqa_comm* c) { return c && c->p2p ? 1 : 0; }
+
+int devqa_dist_p2p_timeouts(devqa_comm* c, int64_t* count) {
+  DEVQA_REQUIRE(c && count, "null argument");
+  *count = 0;
+  if (!c->mbox) return DEVQA_OK;
+  DEVQA_ON_DEVICE(c->device);
+  uint32_t v = 0;
+  DEVQA_CUDA(cudaDeviceSynchronize());
+  DEVQA_CUDA(cudaMemcpy(&v, c->mbox, 4, cudaMemcpyDeviceToHost));
+  *count = v;
   return DEVQA_OK;
 }
 int devqa_dist_rank(const devqa_comm* c) { return c ? c->rank : DEVQA_E_INVALID; }
@@ -1118,6 +1195,21 @@ static int dist_search(devqa_bank* b, devqa_comm* c, SearchArgs a, Scratch* s, f
   const size_t per_rank = size_t(a.n_queries) * a.top_k;
   int rc = grow(reinterpret_cast<void**>(&s->keys), &s->keys_bytes, per_rank * 8, false);
   if (rc) return rc;
+  if (c->p2p && a.n_queries <= kP2pMaxQ && int64_t(per_rank) <= kP2pMaxKeys) {
+    // small batches (the latency-bound regime): each rank's merge kernel pushes its keys into the peers' mailboxes
+    // and waits for theirs -- no collective launch (the decision depends on the call's shape only: every rank takes
+    // the same branch, and the sequence numbers stay in lockstep)
+    if ((rc = run_search(s, a, s->keys, nullptr, nullptr, stream))) return rc;
+    P2pExchange x{};
+    x.local_keys = s->keys; x.rank = c->rank; x.world = c->world;
+    x.header = reinterpret_cast<uint32_t*>(c->mbox);
+    for (int r = 0; r < c->world; ++r) {
+      x.peer_flags[r] = reinterpret_cast<uint32_t*>(c->peer_mbox[r] + c->flags_off());
+      x.peer_data[r] = reinterpret_cast<uint64_t*>(c->peer_mbox[r] + c->data_off());
+    }
+    return merge_lists_launch(x.peer_data[c->rank], c->world, a.n_queries, a.top_k, a.top_k, a.top_k, nullptr, out_scores,
+                              out_ids, stream, nullptr, nullptr, &x);
+  }
   if ((rc = grow(reinterpret_cast<void**>(&s->gathered), &s->gathered_bytes, per_rank * 8 * c->world, false))) return rc;
   if ((rc = run_search(s, a, s->keys, nullptr, nullptr, stream))) return rc;
   int r = api->AllGather(s->keys, s->gathered, per_rank, /*ncclUint64*/ 5, c->nccl, stream);

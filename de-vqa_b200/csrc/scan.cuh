@@ -134,10 +134,28 @@ int refine_lists_launch(const RefineParams& p, cudaStream_t stream);    // from 
 // (out_scores, out_ids) is written: [n_queries, top_k].  With kth_codes != nullptr nothing else is written:
 // kth_codes[q] receives the monotone score code of the k-th best key (0 when fewer than k exist).
 // With need != nullptr only queries whose flag is set are touched.
+//
+// Peer-to-peer exchange fused into the merge (multi-GPU search): with `xchg` set, the CTA of query q first
+// WRITES this rank's sorted top-k of q straight into every peer's mailbox over NVLink (plain stores into IPC-mapped
+// memory, a system-scope fence, then a release-store of the call's sequence number into the peer's flag word), waits
+// until all `world` flags of q in its own mailbox carry that sequence number, and then merges the `world` lists lying
+// there -- ONE kernel instead of ncclAllGather + merge, no collective launch on the critical path.
+constexpr int kP2pMaxWorld = 16;
+constexpr int kP2pMaxQ = 512;                 // queries per call through the mailbox (all CTAs must be co-resident)
+constexpr int64_t kP2pMaxKeys = 65536;        // keys per (slot, source rank): n_queries * top_k of a call
+// The sequence number lives in DEVICE memory (header word 1 of the local mailbox; the kernel's last CTA advances it), so
+// a search captured in a CUDA graph exchanges correctly on every replay; calls alternate between two slots.
+struct P2pExchange {
+  const uint64_t* local_keys;                 // [n_queries, list_stride] this rank's sorted top-k
+  uint64_t* peer_data[kP2pMaxWorld];          // per rank: slot 0 of its data, a slot = [source rank][kP2pMaxKeys], used as [n_queries][list_stride]
+  uint32_t* peer_flags[kP2pMaxWorld];         // per rank: slot 0 of its flags, a slot = [source rank][kP2pMaxQ]
+  uint32_t* header;                           // local mailbox header: [0] timeouts, [1] exchanges completed, [2] arrival ticket
+  int32_t rank, world;
+};
 int merge_lists_launch(const uint64_t* lists, int n_lists, int64_t n_queries, int list_stride,
                        int list_len, int top_k, uint64_t* out_keys, float* out_scores,
                        int64_t* out_ids, cudaStream_t stream, uint32_t* kth_codes = nullptr,
-                       const uint32_t* need = nullptr);
+                       const uint32_t* need = nullptr, const P2pExchange* xchg = nullptr);
 
 // select.cu: threshold-select (LiveEdit retrieve_moes): ordered compaction of the mask the stream kernel wrote.
 struct SelectParams {

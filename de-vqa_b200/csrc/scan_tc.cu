@@ -49,6 +49,9 @@
 // launch, so a launch runs several query passes side by side: CTA c works on pass c % passes and on
 // tiles c / passes, c / passes + ctas_per_pass, ...
 #include <cuda.h>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
 
 #include "scan.cuh"
 #include "topk.cuh"
@@ -1705,13 +1708,27 @@ int scan_tc_launch(const ScanParams& sp, int mode, const void* qcat, uint32_t* g
   } else if (p.oneshot) {
     // the CTAs wait for each other (oneshot_epilogue): a cooperative launch guarantees they are all resident
     DEVQA_REQUIRE(filt && ctas_per_pass == p.n_tiles, "tcgen05 scan: one-shot mode needs one CTA per tile");
+    // DEVQA_ONESHOT_LAUNCH (experiments): "coop" = cooperative only, "pdl" = programmatic dependent launch only (grid <=
+    // SM count and one CTA per SM: resident in practice, and grid_wait gives up after a second), default = both.
+    static const char* how = getenv("DEVQA_ONESHOT_LAUNCH");
+    const bool want_coop = !how || strcmp(how, "pdl") != 0;
+    const bool want_pdl = pdl_enabled() && (!how || strcmp(how, "coop") != 0);
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(unsigned(grid)); cfg.blockDim = dim3(kTcThreads); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeCooperative;
-    attr[0].val.cooperative = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
-    DEVQA_CUDA(cudaLaunchKernelEx(&cfg, kern, bank_map, p));
+    cudaLaunchAttribute attr[2];
+    int na = 0;
+    if (want_coop) { attr[na].id = cudaLaunchAttributeCooperative; attr[na].val.cooperative = 1; ++na; }
+    if (want_pdl) { attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization; attr[na].val.programmaticStreamSerializationAllowed = 1; ++na; }
+    cfg.attrs = attr; cfg.numAttrs = na;
+    cudaError_t le = cudaLaunchKernelEx(&cfg, kern, bank_map, p);
+    if (le != cudaSuccess && na == 2) {                      // the combination is not accepted: cooperative alone
+      cudaGetLastError();
+      cfg.numAttrs = 1;
+      le = cudaLaunchKernelEx(&cfg, kern, bank_map, p);
+      static bool told = false;
+      if (!told && getenv("DEVQA_VERBOSE")) { told = true; fprintf(stderr, "libdevqa: cooperative + PDL launch rejected, using cooperative\n"); }
+    }
+    DEVQA_CUDA(le);
   } else {
     DEVQA_CUDA(launch_pdl(kern, dim3(unsigned(grid)), dim3(kTcThreads), smem, stream, bank_map, p));
   }

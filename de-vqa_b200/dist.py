@@ -68,7 +68,7 @@ class Communicator:
     """libdevqa's own NCCL communicator (``devqa_dist_init``).  The 128-byte unique id is
     created on rank 0 and shipped through ``torch.distributed`` (any backend)."""
 
-    def __init__(self, device: Optional[int] = None):
+    def __init__(self, device: Optional[int] = None, p2p: bool = True):
         import torch.distributed as dist
         if not dist.is_initialized():
             raise RuntimeError("torch.distributed is not initialised")
@@ -82,6 +82,34 @@ class Communicator:
         self._h = C.c_void_p()
         idbuf = C.create_string_buffer(box[0], 128)
         L.check(L.lib().devqa_dist_init(C.byref(self._h), idbuf, self.rank, self.world, self.device))
+        self.p2p = self._connect_mailboxes(dist) if p2p and self.world > 1 else False
+
+    def _connect_mailboxes(self, dist) -> bool:
+        """Peer-to-peer exchange of the local top-k (devqa_dist_p2p_*): export this rank's mailbox, gather every
+        rank's IPC handle over torch.distributed, map them.  Every rank ends up with the same setting: if any rank
+        cannot map a peer (no NVLink/P2P, IPC blocked by the container), all stay on ncclAllGather."""
+        import os
+        if os.environ.get("DEVQA_P2P", "1") == "0" or self.world > 16:
+            return False
+        handle = C.create_string_buffer(64)
+        ok = L.lib().devqa_dist_p2p_export(self._h, handle) == L.OK
+        handles = [None] * self.world
+        dist.all_gather_object(handles, bytes(handle.raw) if ok else None)
+        if ok and all(h is not None for h in handles):
+            ok = L.lib().devqa_dist_p2p_connect(self._h, C.create_string_buffer(b"".join(handles), 64 * self.world)) == L.OK
+        else:
+            ok = False
+        verdict = [None] * self.world
+        dist.all_gather_object(verdict, bool(ok))
+        everyone = all(verdict)
+        if ok and not everyone:
+            L.lib().devqa_dist_p2p_set(self._h, 0)
+        return everyone
+
+    def p2p_timeouts(self) -> int:
+        n = C.c_int64()
+        L.check(L.lib().devqa_dist_p2p_timeouts(self._h, C.byref(n)))
+        return int(n.value)
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._h.value:

@@ -241,6 +241,18 @@ DEVQA_API int devqa_topk_merge(const uint64_t* gathered, int n_lists, int64_t n_
 DEVQA_API int devqa_dist_unique_id(void* out_id_128_bytes);
 DEVQA_API int devqa_dist_init(devqa_comm** out, const void* id_128_bytes, int rank, int world, int device);
 DEVQA_API int devqa_dist_destroy(devqa_comm* comm);
+/* Peer-to-peer mailboxes (optional, one box): every rank exports a 64-byte IPC handle of its mailbox, the handles travel
+ * over the same host channel as the NCCL id, and every rank connects with the `world` handles in rank order.  After
+ * that, searches of up to 512 queries (n_queries * top_k <= 65536) exchange their local top-k by writing straight into
+ * the peers' mailboxes over NVLink from inside the merge kernel -- scan -> re-scoring -> ONE push/wait/merge kernel, no
+ * collective launch.  Larger batches keep the ncclAllGather.  connect() returns DEVQA_E_UNSUPPORTED when a peer's
+ * memory cannot be mapped (the communicator then simply stays on NCCL); all ranks must end up with the same setting
+ * (devqa_dist_p2p_set).  devqa_dist_p2p_timeouts: waits that gave up after ~10 s (a peer died); expected 0. */
+DEVQA_API int devqa_dist_p2p_export(devqa_comm* comm, void* out_handle_64_bytes);
+DEVQA_API int devqa_dist_p2p_connect(devqa_comm* comm, const void* handles_world_x_64_bytes);
+DEVQA_API int devqa_dist_p2p_set(devqa_comm* comm, int enable);
+DEVQA_API int devqa_dist_p2p_enabled(const devqa_comm* comm);
+DEVQA_API int devqa_dist_p2p_timeouts(devqa_comm* comm, int64_t* count);
 DEVQA_API int devqa_dist_rank(const devqa_comm* comm);
 DEVQA_API int devqa_dist_world(const devqa_comm* comm);
 /* scan of the local shard -> ONE ncclAllGather of [n_queries, top_k] packed keys ->

@@ -49,7 +49,72 @@ def _worker(rank, world, port, out_dir):
         small = FactBank.from_embeddings(rows, device=rank)
         ss_, si_ = small.search(q.cuda(), k)
         assert torch.equal(ci, si_) and torch.equal(cs, ss_)
+        # ---- the exchange: peer-to-peer mailboxes (default) vs ncclAllGather, bit for bit; batches beyond the mailbox
+        # (Q > 512) take the NCCL path by themselves
+        L = devqa_b200._lib
+        assert comm.p2p == bool(L.lib().devqa_dist_p2p_enabled(comm._h))
+        report = {"p2p": comm.p2p}
+        big_q = torch.nn.functional.normalize(torch.randn(600, d, generator=g), dim=1).cuda()
+        for nq, kk in ((1, 5), (9, 32), (64, 32), (300, 100), (512, 128)):
+            qq = big_q[:nq]
+            a = sb.search(qq, kk)
+            if comm.p2p:
+                L.check(L.lib().devqa_dist_p2p_set(comm._h, 0))
+                b = sb.search(qq, kk)
+                L.check(L.lib().devqa_dist_p2p_set(comm._h, 1))
+                assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]), (nq, kk)
+            r = full.search(qq, kk)
+            assert torch.equal(a[1], r[1]) and torch.equal(a[0], r[0]), (nq, kk)
+        a = sb.search(big_q, 8)
+        r = full.search(big_q, 8)
+        assert torch.equal(a[1], r[1]) and torch.equal(a[0], r[0])
+        # ---- the whole distributed step (scan -> re-scoring -> exchange -> merge) captured in ONE CUDA graph and
+        # replayed with new queries: no host involvement per step (missing #5)
+        qbuf = big_q[:64].clone()
+        out_s = torch.empty((64, k), dtype=torch.float32, device="cuda")
+        out_i = torch.empty((64, k), dtype=torch.int64, device="cuda")
+        from devqa_b200.bank import norm_flags, _stream_ptr
+
+        def enqueue():
+            L.check(L.lib().devqa_bank_search_dist(sb.local._h, comm._h, qbuf.data_ptr(), 64, d, k, norm_flags("eps", "eps"),
+                                                   out_s.data_ptr(), out_i.data_ptr(), _stream_ptr(rank)))
+        enqueue(); enqueue()                                        # warm-up: sizes every scratch buffer
         torch.cuda.synchronize()
+        dist.barrier()
+        graph = torch.cuda.CUDAGraph()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.graph(graph, stream=side):
+            enqueue()
+        for rep in range(4):
+            qbuf.copy_(big_q[rep * 100: rep * 100 + 64])
+            graph.replay()
+            torch.cuda.synchronize()
+            want = full.search(qbuf, k)
+            assert torch.equal(out_i, want[1]) and torch.equal(out_s, want[0]), rep
+        # timing of the eager step, both exchanges (reported, not asserted)
+        for name, on in (("p2p", 1), ("nccl", 0)):
+            if not comm.p2p and on:
+                continue
+            if comm.p2p:
+                L.check(L.lib().devqa_dist_p2p_set(comm._h, on))
+            for _ in range(5):
+                sb.search(qbuf, k)
+            dist.barrier(); torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(100):
+                sb.search(qbuf, k)
+            e1.record(); torch.cuda.synchronize()
+            report[name + "_us_per_step"] = e0.elapsed_time(e1) * 10.0
+        if comm.p2p:
+            L.check(L.lib().devqa_dist_p2p_set(comm._h, 1))
+        assert comm.p2p_timeouts() == 0
+        torch.cuda.synchronize()
+        import json
+        gp = os.path.join(ROOT, "gpurun_out")
+        if rank == 0 and os.path.isdir(gp):
+            json.dump(report, open(os.path.join(gp, "dist_exchange_2gpu.json"), "w"))
         open(os.path.join(out_dir, f"ok{rank}"), "w").write("ok")
     finally:
         dist.destroy_process_group()
