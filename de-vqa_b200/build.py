@@ -13,7 +13,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libdevqa.so")
-SOURCES = ["api.cu", "scan_stream.cu", "scan_tc.cu", "merge.cu", "refine.cu", "select.cu", "gate.cu", "synth.cu", "norm.cu", "nccl_dyn.cpp"]
+SOURCES = ["api.cu", "scan_stream.cu", "scan_tc.cu", "merge.cu", "refine.cu", "select.cu", "gate.cu", "vmm.cu", "synth.cu", "norm.cu", "nccl_dyn.cpp"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC,-fvisibility=hidden,-Wall", "-DDEVQA_BUILD",

@@ -43,6 +43,7 @@ struct Scratch {
   uint64_t* gathered = nullptr; size_t gathered_bytes = 0; // all-gather target (dist)
   void* tiny = nullptr;       size_t tiny_bytes = 0;       // padded copy of banks shorter than one row group
   uint8_t* selmask = nullptr; size_t selmask_bytes = 0;    // threshold-select: [Q, N] mask when the caller wants none
+  uint64_t* deep = nullptr;   size_t deep_bytes = 0;       // deep top-k: one pass's keys [Q, 1024] + per-query bound keys
   float* qsplit = nullptr;    size_t qsplit_bytes = 0;     // TF32 hi / lo query planes of the tcgen05 scan
   uint64_t* akeys = nullptr;  size_t akeys_bytes = 0;      // filter scan: merged approximate top-K' lists + per-query side arrays
   uint32_t* fallbacks = nullptr;                           // device counter: queries the exact fallback had to redo
@@ -157,6 +158,7 @@ struct SearchArgs {
   int top_k; unsigned flags; IdMap idmap;
   const float* row_sumsq = nullptr;
   const uint32_t* max_sumsq = nullptr;   // library-owned banks: max ||row||^2 over every row ever appended (float bits)
+  const uint64_t* below = nullptr;       // deep top-k passes: per-query exclusive upper bound key
 };
 
 static int validate(const SearchArgs& a) {
@@ -165,10 +167,7 @@ static int validate(const SearchArgs& a) {
   DEVQA_REQUIRE(a.bank_ld >= a.dim && a.query_ld >= a.dim, "row stride smaller than dim");
   DEVQA_REQUIRE(a.top_k >= 1, "top_k must be >= 1");
   DEVQA_REQUIRE(a.dtype == DEVQA_F32 || a.dtype == DEVQA_BF16, "unknown bank dtype %d", a.dtype);
-  if (a.top_k > DEVQA_MAX_TOPK) {
-    set_error("top_k %d exceeds DEVQA_MAX_TOPK (%d)", a.top_k, DEVQA_MAX_TOPK);
-    return DEVQA_E_UNSUPPORTED;
-  }
+  DEVQA_REQUIRE(a.top_k <= (1 << 24), "top_k %d unsupported", a.top_k);
   DEVQA_REQUIRE(a.n_rows == 0 || a.bank != nullptr, "bank pointer is null");
   DEVQA_REQUIRE(a.n_queries == 0 || a.queries != nullptr, "queries pointer is null");
   DEVQA_REQUIRE(a.idmap.base + a.n_rows * (a.idmap.chunk > 0 ? a.idmap.world : 1) <= 0xffffffffll,
@@ -216,7 +215,7 @@ static int tc_pipeline(Scratch* s, const SearchArgs& a, int mode, FilterSide* si
   // top_k-th largest of the tiles' bests) and all of them resident at once.
   const int64_t n_tiles_all = (a.n_rows + 127) / 128;
   const bool oneshot = side != nullptr && side->ocand != nullptr && !need && n_tiles_all <= s->sm_count &&
-                       n_tiles_all >= a.top_k && !(a.flags & (DEVQA_DEBUG_FILTER_ONLY | DEVQA_DEBUG_NO_ONESHOT));
+                       n_tiles_all >= a.top_k && a.top_k <= 64 && !(a.flags & (DEVQA_DEBUG_FILTER_ONLY | DEVQA_DEBUG_NO_ONESHOT));
   if ((rc = scan_tc_plan(mode, int(a.n_queries), a.dim, kcap, cached_norms, n_tiles_all, s->sm_count, a.flags,
                          &qp, &stages, &pair, oneshot)))
     return rc;
@@ -311,10 +310,37 @@ static int tc_pipeline(Scratch* s, const SearchArgs& a, int mode, FilterSide* si
   return merge_lists_launch(s->cand, grid, a.n_queries, kcap, kcap, a.top_k, out_keys, out_scores, out_ids, stream, nullptr, need);
 }
 
+static int run_search(Scratch* s, const SearchArgs& a, uint64_t* out_keys, float* out_scores, int64_t* out_ids,
+                      cudaStream_t stream);
+
+// top_k beyond DEVQA_MAX_TOPK (upstream's semantic_search accepts any top_k): results come 1024 at a time, pass j
+// being the top-1024 among the keys BELOW the last key pass j - 1 emitted (keys are unique and totally ordered, so the
+// passes tile the ranking exactly).  One bank read per query and pass on the stream kernel -- a rarely used corner,
+// served for completeness, not for speed.
+static int run_search_deep(Scratch* s, const SearchArgs& a, uint64_t* out_keys, float* out_scores, int64_t* out_ids,
+                           cudaStream_t stream) {
+  int rc;
+  const size_t nq = size_t(a.n_queries);
+  if ((rc = grow(reinterpret_cast<void**>(&s->deep), &s->deep_bytes, nq * DEVQA_MAX_TOPK * 8 + nq * 8, false))) return rc;
+  uint64_t* pass_keys = s->deep;
+  uint64_t* below = s->deep + nq * DEVQA_MAX_TOPK;
+  for (int col0 = 0; col0 < a.top_k; col0 += DEVQA_MAX_TOPK) {
+    SearchArgs aj = a;
+    aj.top_k = a.top_k - col0 < DEVQA_MAX_TOPK ? a.top_k - col0 : DEVQA_MAX_TOPK;
+    aj.flags |= DEVQA_FORCE_STREAM;
+    aj.below = col0 ? below : nullptr;
+    if ((rc = run_search(s, aj, pass_keys, nullptr, nullptr, stream))) return rc;
+    if ((rc = deep_emit_launch(pass_keys, a.n_queries, aj.top_k, a.top_k, col0, out_keys, out_scores, out_ids, below, stream)))
+      return rc;
+  }
+  return DEVQA_OK;
+}
+
 // Exactly one of out_keys / (out_scores,out_ids).
 static int run_search(Scratch* s, const SearchArgs& a, uint64_t* out_keys, float* out_scores, int64_t* out_ids,
                       cudaStream_t stream) {
   if (a.n_queries == 0) return DEVQA_OK;
+  if (a.top_k > DEVQA_MAX_TOPK) return run_search_deep(s, a, out_keys, out_scores, out_ids, stream);
   const int kcap = topk_capacity(a.top_k);
   const int nv_vec = a.dtype == DEVQA_F32 ? 4 : 8;
   const size_t esz = a.dtype == DEVQA_F32 ? 4 : 2;
@@ -330,7 +356,7 @@ static int run_search(Scratch* s, const SearchArgs& a, uint64_t* out_keys, float
   bool use_tc = tc_ok && a.n_queries > 2;
   // Where the tensor path is the filter (see below), it returns bit for bit what the stream kernel returns, so
   // the choice between the two may also look at the bank size without breaking "G shards == one bank":
-  const bool filter_path = !(a.flags & DEVQA_FORCE_TF32X3) && a.top_k <= 64 && a.dim <= 16384 &&
+  const bool filter_path = !(a.flags & DEVQA_FORCE_TF32X3) && a.top_k <= 128 && a.dim <= 16384 &&
                            (a.dtype == DEVQA_F32 ? ((a.flags & DEVQA_NORMALIZE_BANK) || (a.row_sumsq && a.max_sumsq))
                                                  : (a.row_sumsq != nullptr && a.max_sumsq != nullptr));
   if (tc_ok && filter_path) {
@@ -353,13 +379,15 @@ static int run_search(Scratch* s, const SearchArgs& a, uint64_t* out_keys, float
   p.n_rows = a.n_rows; p.dim = a.dim; p.bank_ld = a.bank_ld;
   p.queries = a.queries; p.query_ld = a.query_ld; p.n_queries = int32_t(a.n_queries);
   p.top_k = a.top_k; p.kcap = kcap; p.flags = a.flags; p.idmap = a.idmap; p.row_sumsq = a.row_sumsq;
+  p.below = a.below;
   int grid = 1;
 
   if (use_tc) {
     // fp32 banks: the TF32 filter scan + exact re-scoring (refine.cu) + conditional exact fallback; the 3xTF32
     // scan alone on request, for top_k > 64 (no room for the filter's surplus candidates) and for un-normalised
     // scores over a caller-owned bank (the error bound needs max ||row||, which only library-owned banks cache).
-    const int kp = a.top_k <= 8 ? 32 : (a.top_k <= 16 ? 64 : 128);     // K': candidates kept per query after the merge
+    // K': candidates kept per query after the merge
+    const int kp = a.top_k <= 8 ? 32 : (a.top_k <= 16 ? 64 : (a.top_k <= 64 ? 128 : 256));
     // (Nothing here may depend on the number of rows: every shard of a sharded bank has to take the same path, or
     // G-GPU results would differ from 1-GPU results in the last bits of the scores.)
     // bf16 banks: the same filter with queries rounded to bf16 (library-owned banks: cached row norms), bf16x3 as fallback.
@@ -406,7 +434,8 @@ static int run_search(Scratch* s, const SearchArgs& a, uint64_t* out_keys, float
       // With at least top_k CTAs per pass the scan's CTAs exchange their bests, and refine can pick the candidates
       // straight out of the per-CTA lists (one kernel instead of merge + refine).
       const int64_t tiles = (a.n_rows + 127) / 128;
-      side.merge = (a.flags & DEVQA_DEBUG_FILTER_ONLY) || tiles < s->sm_count || s->sm_count < a.top_k;
+      // (top_k > 64: the top_k-th largest of <= 148 CTA bests is too loose a cut for refine_lists -- merged path, K' = 256)
+      side.merge = (a.flags & DEVQA_DEBUG_FILTER_ONLY) || tiles < s->sm_count || s->sm_count < a.top_k || a.top_k > 64;
       if ((rc = tc_pipeline(s, ac, filt_mode, &side, nullptr, nullptr, nullptr, nullptr, stream))) return rc;
       if (a.flags & DEVQA_DEBUG_FILTER_ONLY) {                           // tests: the filter's own upper bounds
         if ((rc = merge_lists_launch(side.akeys, 1, ac.n_queries, kp, kp, a.top_k, ok, os, oi, stream))) return rc;
@@ -493,6 +522,7 @@ struct devqa_bank {
   int64_t dim = 0, ld = 0;
   int64_t size = 0, capacity = 0;
   void* data = nullptr;
+  devqa::VmmBuffer* vmm = nullptr; // rows live in a reserved virtual range that grows in place (vmm.cu); nullptr: cudaMalloc + copy
   float* sumsq = nullptr;          // cached ||row||^2 per stored row (bf16 banks: of the rounded row)
   uint32_t* max_sumsq = nullptr;   // device word: max of those over every row ever appended (float bits; never shrinks)
   devqa::IdMap idmap{0, 0, 0, 1};
@@ -533,25 +563,44 @@ static int bank_grow(devqa_bank* b, int64_t want_rows, cudaStream_t stream) {
   if (want_rows <= b->capacity) return DEVQA_OK;
   int64_t cap = b->capacity > 0 ? b->capacity : 1024;
   while (cap < want_rows) cap += cap / 2 + 1024;          // geometric: amortised O(1) per appended row
-  void* fresh = nullptr;
   const size_t bytes = size_t(cap) * b->ld * b->esz();
-  cudaError_t e = cudaMalloc(&fresh, bytes);
-  if (e != cudaSuccess) {
-    set_error("cudaMalloc of %zu bytes for the bank failed: %s", bytes, cudaGetErrorString(e));
-    return DEVQA_E_NOMEM;
-  }
-  if (b->size > 0)
-    DEVQA_CUDA(cudaMemcpyAsync(fresh, b->data, size_t(b->size) * b->ld * b->esz(), cudaMemcpyDeviceToDevice, stream));
+  // the row norms (4 bytes per row) are small enough to move
   float* fresh_ss = nullptr;
-  e = cudaMalloc(&fresh_ss, size_t(cap) * 4);
+  cudaError_t e = cudaMalloc(&fresh_ss, size_t(cap) * 4);
   if (e != cudaSuccess) {
-    cudaFree(fresh);
     set_error("cudaMalloc of %zu bytes for the row norms failed: %s", size_t(cap) * 4, cudaGetErrorString(e));
     return DEVQA_E_NOMEM;
   }
-  if (b->size > 0) DEVQA_CUDA(cudaMemcpyAsync(fresh_ss, b->sumsq, size_t(b->size) * 4, cudaMemcpyDeviceToDevice, stream));
+  if (b->vmm) {
+    // in place: fresh physical chunks are mapped behind the rows already stored -- nothing is copied, nothing moves
+    bool moved = false;
+    int rc = vmm_grow(b->vmm, bytes, &moved);
+    if (rc == DEVQA_OK) {
+      if (b->size > 0) DEVQA_CUDA(cudaMemcpyAsync(fresh_ss, b->sumsq, size_t(b->size) * 4, cudaMemcpyDeviceToDevice, stream));
+      if (b->sumsq) { DEVQA_CUDA(cudaStreamSynchronize(stream)); DEVQA_CUDA(cudaFree(b->sumsq)); }
+      b->data = vmm_data(b->vmm);
+      b->sumsq = fresh_ss;
+      b->capacity = cap;
+      return DEVQA_OK;
+    }
+    if (rc != DEVQA_E_UNSUPPORTED || b->data != nullptr) { cudaFree(fresh_ss); return rc; }
+    vmm_destroy(b->vmm);                                  // (never worked on this device: plain allocations from here on)
+    b->vmm = nullptr;
+  }
+  void* fresh = nullptr;
+  e = cudaMalloc(&fresh, bytes);
+  if (e != cudaSuccess) {
+    cudaFree(fresh_ss);
+    set_error("cudaMalloc of %zu bytes for the bank failed: %s", bytes, cudaGetErrorString(e));
+    return DEVQA_E_NOMEM;
+  }
+  if (b->size > 0) {
+    DEVQA_CUDA(cudaMemcpyAsync(fresh, b->data, size_t(b->size) * b->ld * b->esz(), cudaMemcpyDeviceToDevice, stream));
+    DEVQA_CUDA(cudaMemcpyAsync(fresh_ss, b->sumsq, size_t(b->size) * 4, cudaMemcpyDeviceToDevice, stream));
+  }
   if (b->data) {
-    DEVQA_CUDA(cudaStreamSynchronize(stream));
+    // the old buffers may still be read by searches enqueued on ANY stream: wait for the device, not just this stream
+    DEVQA_CUDA(cudaDeviceSynchronize());
     DEVQA_CUDA(cudaFree(b->data));
     DEVQA_CUDA(cudaFree(b->sumsq));
   }
@@ -771,7 +820,14 @@ int devqa_bank_create(devqa_bank** out, int device, int64_t dim, int64_t capacit
     delete b;
     return DEVQA_E_NOMEM;
   }
-  if (capacity_rows > 0 && (rc = bank_grow(b, capacity_rows, nullptr))) { cudaFree(b->max_sumsq); delete b; return rc; }
+  static const bool vmm_on = getenv("DEVQA_VMM") == nullptr || atoi(getenv("DEVQA_VMM")) != 0;
+  if (vmm_on) b->vmm = vmm_create(device);                   // nullptr: driver without VMM -> cudaMalloc + copy-on-regrow
+  if (capacity_rows > 0 && (rc = bank_grow(b, capacity_rows, nullptr))) {
+    cudaFree(b->max_sumsq);
+    if (b->vmm) vmm_destroy(b->vmm);
+    delete b;
+    return rc;
+  }
   *out = b;
   return DEVQA_OK;
 }
@@ -779,7 +835,9 @@ int devqa_bank_create(devqa_bank** out, int device, int64_t dim, int64_t capacit
 int devqa_bank_destroy(devqa_bank* b) {
   if (!b) return DEVQA_OK;
   DEVQA_ON_DEVICE(b->device);
-  if (b->data) { cudaDeviceSynchronize(); cudaFree(b->data); cudaFree(b->sumsq); }
+  if (b->data || b->vmm) cudaDeviceSynchronize();
+  if (b->vmm) { vmm_destroy(b->vmm); if (b->sumsq) cudaFree(b->sumsq); }
+  else if (b->data) { cudaFree(b->data); cudaFree(b->sumsq); }
   if (b->max_sumsq) cudaFree(b->max_sumsq);
   delete b;
   return DEVQA_OK;
@@ -1072,7 +1130,7 @@ int devqa_bank_hice_probe(devqa_bank* b, devqa_bank* memory, const float* querie
 int devqa_topk_merge(const uint64_t* gathered, int n_lists, int64_t nq, int top_k, float* out_scores,
                      int64_t* out_ids, void* stream) {
   DEVQA_REQUIRE(n_lists >= 1 && nq >= 0 && top_k >= 1, "bad merge shape");
-  if (top_k > DEVQA_MAX_TOPK) { set_error("top_k %d exceeds DEVQA_MAX_TOPK", top_k); return DEVQA_E_UNSUPPORTED; }
+  if (top_k > DEVQA_MAX_TOPK) { set_error("devqa_topk_merge: top_k %d exceeds DEVQA_MAX_TOPK", top_k); return DEVQA_E_UNSUPPORTED; }
   DEVQA_REQUIRE(nq == 0 || (gathered && out_scores && out_ids), "null pointers");
   return merge_lists_launch(gathered, n_lists, nq, top_k, top_k, top_k, nullptr, out_scores, out_ids,
                             static_cast<cudaStream_t>(stream));
@@ -1190,6 +1248,10 @@ int devqa_dist_world(const devqa_comm* c) { return c ? c->world : DEVQA_E_INVALI
 
 static int dist_search(devqa_bank* b, devqa_comm* c, SearchArgs a, Scratch* s, float* out_scores, int64_t* out_ids,
                        cudaStream_t stream) {
+  if (a.top_k > DEVQA_MAX_TOPK) {
+    set_error("sharded search: top_k %d exceeds DEVQA_MAX_TOPK (%d)", a.top_k, DEVQA_MAX_TOPK);
+    return DEVQA_E_UNSUPPORTED;
+  }
   const NcclApi* api = nccl_api();
   if (!api) return DEVQA_E_NCCL;
   const size_t per_rank = size_t(a.n_queries) * a.top_k;

@@ -155,7 +155,36 @@ __global__ void __launch_bounds__(kMergeThreads) merge_generic_kernel(const uint
   if (xchg.world > 0) p2p_leave(xchg);
 }
 
+__global__ void __launch_bounds__(256) deep_emit_kernel(const uint64_t* __restrict__ pass_keys, int64_t n_queries, int kj,
+                                                        int top_k, int col0, uint64_t* out_keys, float* out_scores,
+                                                        int64_t* out_ids, uint64_t* below) {
+  pdl_wait();
+  const int64_t q = blockIdx.x;
+  for (int e = threadIdx.x; e < kj; e += blockDim.x) {
+    const uint64_t key = pass_keys[size_t(q) * kj + e];
+    const size_t o = size_t(q) * top_k + col0 + e;
+    if (out_keys) {
+      out_keys[o] = key;
+    } else {
+      const bool empty = key == kEmptyKey;
+      out_scores[o] = empty ? -INFINITY : key_score(key);
+      out_ids[o] = empty ? int64_t(-1) : int64_t(key_id(key));
+    }
+    if (e == kj - 1) below[q] = key == kEmptyKey ? 1ull : key;      // (1: below every real key -- the bank is exhausted)
+  }
+}
+
 }  // namespace
+
+int deep_emit_launch(const uint64_t* pass_keys, int64_t n_queries, int kj, int top_k, int col0, uint64_t* out_keys,
+                     float* out_scores, int64_t* out_ids, uint64_t* below, cudaStream_t stream) {
+  if (n_queries == 0) return DEVQA_OK;
+  DEVQA_CUDA(launch_pdl(deep_emit_kernel, dim3(unsigned(n_queries)), dim3(256), 0, stream, pass_keys, n_queries, kj, top_k, col0,
+                        out_keys, out_scores, out_ids, below));
+  DEVQA_CUDA(cudaGetLastError());
+  count_launch();
+  return DEVQA_OK;
+}
 
 int merge_lists_launch(const uint64_t* lists, int n_lists, int64_t n_queries, int list_stride,
                        int list_len, int top_k, uint64_t* out_keys, float* out_scores, int64_t* out_ids,

@@ -30,7 +30,8 @@ namespace devqa {
 namespace {
 
 constexpr int kRefineThreads = 256;
-constexpr int kMaxKp = 128;
+constexpr int kMaxKp = 256;        // refine_kernel: merged candidates per query (K' = 256 serves top_k <= 128)
+constexpr int kListKp = 128;       // refine_lists_kernel: candidates re-scored per query (top_k <= 64)
 
 // Canary of the filter's error bound.  Every candidate that is re-scored has both its upper bound u (the score field of
 // the key the scan produced: u = s~ + E) and its exact score s.  The whole completeness proof rests on
@@ -43,19 +44,19 @@ __device__ __forceinline__ bool bound_violated(float u, float s, float e) {
   return s > u || (u - s) > 2.0001f * e + 1e-30f;
 }
 
-// ex[0 .. kMaxKp): exact keys, unique or empty (0)  ->  srt[0 .. kMaxKp) descending, empties last.  Rank sort: thread i
-// counts the keys above its own (128 broadcast reads, no barrier in between) -- ~1/10 of the 28-phase bitonic network
-// this replaced, which was a third of the kernel's time.  All threads call; srt must not alias ex.
-__device__ __forceinline__ void rank_sort(const uint64_t* ex, uint64_t* srt) {
+// ex[0 .. n): exact keys, unique or empty (0)  ->  srt[0 .. n) descending, empties last (n <= blockDim.x).  Rank sort:
+// thread i counts the keys above its own (n broadcast reads, no barrier in between) -- ~1/10 of the 28-phase bitonic
+// network this replaced, which was a third of the kernel's time.  All threads call; srt must not alias ex.
+__device__ __forceinline__ void rank_sort(const uint64_t* ex, uint64_t* srt, int n) {
   const int i = threadIdx.x;
-  if (i < kMaxKp) srt[i] = kEmptyKey;
+  if (i < n) srt[i] = kEmptyKey;
   __syncthreads();
-  if (i < kMaxKp) {
+  if (i < n) {
     const uint64_t key = ex[i];
     if (key != kEmptyKey) {
       int rank = 0;
 #pragma unroll 8
-      for (int j = 0; j < kMaxKp; ++j) rank += ex[j] > key ? 1 : 0;
+      for (int j = 0; j < n; ++j) rank += ex[j] > key ? 1 : 0;
       srt[rank] = key;
     }
   }
@@ -138,7 +139,7 @@ __global__ void __launch_bounds__(kRefineThreads) refine_kernel(const RefinePara
     if (a != kEmptyKey && !(key_score(a) < prelim)) rescore(c);    // warp-uniform; NaN upper bounds are re-scored
   }
   __syncthreads();
-  rank_sort(ex, srt);                                               // descending, empties last
+  rank_sort(ex, srt, p.kp <= 128 ? 128 : kMaxKp);                   // descending, empties last
   // nothing lost can enter the top-k?  (not asked when this run only re-expresses an exact result in the stream
   // kernel's arithmetic)
   if (threadIdx.x == 0 && !p.only_if) {
@@ -182,7 +183,7 @@ __global__ void __launch_bounds__(kRefineListThreads) refine_lists_kernel(const 
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int kWide = 512;                                         // first-cut capacity (= threads: one key each)
   static_assert(kWide == kRefineListThreads, "one key per thread in the second cut");
-  __shared__ uint64_t ex[kMaxKp];
+  __shared__ uint64_t ex[kListKp];
   __shared__ uint64_t ak[kWide];
   __shared__ uint32_t s_count, s_lost, s_tcode, s_viol;
   constexpr int CH = VEC ? (sizeof(T) == 2 ? 256 : 128) : 32;
@@ -197,7 +198,7 @@ __global__ void __launch_bounds__(kRefineListThreads) refine_lists_kernel(const 
   const float* src = p.queries + size_t(q) * p.query_ld;
   const float inv = p.qinv[q];
   for (int c = threadIdx.x; c < dpad; c += kRefineListThreads) sq[c] = c < dim ? src[c] * inv : 0.f;
-  for (int c = threadIdx.x; c < kMaxKp; c += kRefineListThreads) ex[c] = kEmptyKey;
+  for (int c = threadIdx.x; c < kListKp; c += kRefineListThreads) ex[c] = kEmptyKey;
   if (threadIdx.x == 0) { s_count = 0u; s_lost = 0u; s_tcode = 0u; s_viol = 0u; }
   const bool direct = p.dcount != nullptr;                             // one-shot scan: candidates are one array already
   // ---- T from the CTAs' bests (warp 0), lost-row bounds (warp 1) ----
@@ -255,7 +256,7 @@ __global__ void __launch_bounds__(kRefineListThreads) refine_lists_kernel(const 
   // Second cut.  T from the CTAs' bests is loose when top_k is not small against the number of CTAs (k = 64 of 148:
   // ~30% more rows above it than the true k-th best has).  With the first cut in shared memory the exact k-th
   // best upper bound of everything kept is one bitonic sort away: keep what is >= that - 2E.
-  if (n_raw > uint32_t(kMaxKp) && n_raw <= uint32_t(kWide)) {
+  if (n_raw > uint32_t(kListKp) && n_raw <= uint32_t(kWide)) {
     uint64_t mine = threadIdx.x < int(n_raw) ? ak[threadIdx.x] : kEmptyKey;
     __syncthreads();
     ak[threadIdx.x] = mine;
@@ -285,16 +286,16 @@ __global__ void __launch_bounds__(kRefineListThreads) refine_lists_kernel(const 
     __syncthreads();
     n_raw = s_count;
   }
-  const int n = n_raw < uint32_t(kMaxKp) ? int(n_raw) : kMaxKp;
+  const int n = n_raw < uint32_t(kListKp) ? int(n_raw) : kListKp;
   // ---- exact re-scoring, two phases (like refine_kernel): the top_k candidates by upper bound first; then only those
   // whose upper bound can still beat the k-th best exact score found.  Re-scoring is the kernel's whole cost (one
   // HBM/L2 round trip of dim * 4 bytes per candidate), and typically a third of the candidates fall in phase 2. ----
   __shared__ float s_prelim;
-  uint64_t* const byu = ak + 2 * kMaxKp;                               // candidates sorted by upper bound (ak[256..384))
+  __shared__ uint64_t byu[kListKp];                                    // candidates sorted by upper bound
   __syncthreads();
-  if (threadIdx.x >= n && threadIdx.x < kMaxKp) ak[threadIdx.x] = kEmptyKey;
+  if (threadIdx.x >= n && threadIdx.x < kListKp) ak[threadIdx.x] = kEmptyKey;
   __syncthreads();
-  rank_sort(ak, byu);
+  rank_sort(ak, byu, kListKp);
   auto row_of = [&](int c) {
     int64_t row = int64_t(key_id(byu[c])) - p.idmap.base;
     if (p.idmap.chunk > 0) row = ((row / p.idmap.chunk) / p.idmap.world) * p.idmap.chunk + row % p.idmap.chunk;
@@ -334,10 +335,10 @@ __global__ void __launch_bounds__(kRefineListThreads) refine_lists_kernel(const 
     if (!(key_score(byu[c]) < prelim)) rescore(c);                     // warp-uniform; NaN upper bounds are re-scored
   __syncthreads();
   uint64_t* const srt = ak;                                            // (the compacted keys are dead now)
-  rank_sort(ex, srt);
+  rank_sort(ex, srt, kListKp);
   if (threadIdx.x == 0) {
     const uint64_t kth = srt[p.top_k - 1];
-    bool complete = n_raw <= uint32_t(kMaxKp);                        // otherwise candidates were cut off
+    bool complete = n_raw <= uint32_t(kListKp);                        // otherwise candidates were cut off
     const uint32_t lost = s_lost;
     if (complete && lost != 0u)
       complete = kth != kEmptyKey && code_score(lost) < key_score(kth);   // false for NaN on either side
@@ -375,8 +376,8 @@ static size_t refine_query_smem(const RefineParams& p, bool vec) {
 
 int refine_lists_launch(const RefineParams& p, cudaStream_t stream) {
   if (p.n_queries == 0) return DEVQA_OK;
-  if (p.dcount) DEVQA_REQUIRE(p.top_k <= kMaxKp && p.dcap <= 512 && p.dcand, "refine: unsupported direct candidate geometry");
-  else DEVQA_REQUIRE(p.top_k <= kMaxKp && p.n_lists <= 160 && p.n_lists >= p.top_k, "refine: unsupported list geometry");
+  if (p.dcount) DEVQA_REQUIRE(p.top_k <= kListKp / 2 && p.dcap <= 512 && p.dcand, "refine: unsupported direct candidate geometry");
+  else DEVQA_REQUIRE(p.top_k <= kListKp / 2 && p.n_lists <= 160 && p.n_lists >= p.top_k, "refine: unsupported list geometry");
   const bool vec = refine_vectorised(p);
   const size_t smem = refine_query_smem(p, vec);
   void (*kern)(RefineParams) = p.bank_dtype == DEVQA_F32

@@ -31,6 +31,8 @@ struct ScanParams {
   // stream kernel, capacity 32: the last CTA to finish merges the per-CTA lists itself (no merge launch)
   uint32_t* ticket;        // zeroed device word (re-zeroed by the kernel); nullptr: separate merge kernel
   uint64_t* out_keys; float* out_scores; int64_t* out_ids;   // final [n_queries, top_k] (exactly one form)
+  // stream kernel, deep top-k (top_k > DEVQA_MAX_TOPK, one pass per 1024 results): only keys BELOW below[q] take part
+  const uint64_t* below;   // [n_queries] exclusive upper bound keys (0 = none); nullptr = ordinary scan
   // stream kernel, threshold-select mode (select.cu): mask[q][row] = score * sel_scale > sel_thr[q]
   const float* sel_thr;    // [n_queries] device thresholds
   float sel_scale;
@@ -183,6 +185,14 @@ struct GateParams {
 size_t scope_gate_partial_floats(const GateParams& p);
 int scope_gate_launch(const GateParams& p, cudaStream_t stream);
 
+// vmm.cu: bank storage that grows in place (virtual memory management); nullptr / DEVQA_E_UNSUPPORTED when unavailable
+struct VmmBuffer;
+VmmBuffer* vmm_create(int device);
+int vmm_grow(VmmBuffer* b, size_t want_bytes, bool* moved);
+void* vmm_data(const VmmBuffer* b);
+size_t vmm_mapped(const VmmBuffer* b);
+void vmm_destroy(VmmBuffer* b);
+
 // synth.cu
 int fill_synthetic_launch(void* dst, int dtype, int64_t n_rows, int64_t dim, int64_t ld, uint64_t seed,
                           int64_t first_global_row, int kind, cudaStream_t stream);
@@ -193,6 +203,10 @@ int normalize_rows_launch(const float* src, int64_t src_ld, float* dst, int64_t 
 // (max_bits: optional device word that receives atomicMax of the sums' bit patterns)
 int row_sumsq_launch(const void* rows, int dtype, int64_t n_rows, int64_t dim, int64_t ld, float* out, cudaStream_t stream,
                      uint32_t* max_bits = nullptr);
+// merge.cu: one 1024-wide pass of a deep top-k: [n_queries, kj] keys -> columns [col0, col0 + kj) of the caller's
+// [n_queries, top_k] outputs (keys, or scores + ids), and below[q] = the pass's last key (1 when the bank is exhausted).
+int deep_emit_launch(const uint64_t* pass_keys, int64_t n_queries, int kj, int top_k, int col0, uint64_t* out_keys,
+                     float* out_scores, int64_t* out_ids, uint64_t* below, cudaStream_t stream);
 // synth.cu helper kernels
 int widen_rows_launch(const void* src, int64_t src_ld, float* dst, int64_t dst_ld, int64_t n_rows, int64_t dim,
                       cudaStream_t stream);

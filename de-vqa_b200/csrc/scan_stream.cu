@@ -226,6 +226,8 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_stream_kernel(const Scan
   // when V < 32 several lanes end up with the same total: only the one with clear low bits reports it
   const bool q_live = my_q < p.nq_pass && (lane & ((32 >> Log2<V>::value) - 1)) == 0;
   uint64_t thr = kEmptyKey;                          // k-th key of my_q's list
+  uint64_t below_q = 0ull;                           // deep top-k: keys at or above this one were emitted by earlier passes
+  if (p.below != nullptr && q_live) below_q = p.below[p.q0 + my_q];
   float sel_thr = 0.f;                               // SELECT: this lane's query's threshold
   uint8_t* sel_row = nullptr;                        //         and its mask row
   if constexpr (SELECT) {
@@ -327,7 +329,8 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_stream_kernel(const Scan
       g = gn;
       continue;
     }
-    const uint64_t key = live ? pack_key(score, uint32_t(p.idmap(row))) : kEmptyKey;
+    uint64_t key = live ? pack_key(score, uint32_t(p.idmap(row))) : kEmptyKey;
+    if (below_q != 0ull && key >= below_q) key = kEmptyKey;
     unsigned hit = __ballot_sync(kFull, key > thr);
     if (hit) {
       while (hit) {

@@ -11,7 +11,7 @@ module is provided as ``sentence_transformers.util``:
 Everything is computed by libdevqa.so on the GPU.  There is no CPU path: CPU tensors /
 ndarrays are uploaded, and a machine without a B200 raises.  Divergences from upstream,
 all outside the parity contract: ties are ordered by ascending
-corpus id; ``top_k`` is capped at 1024; ``score_function`` must be ``dot_score`` or
+corpus id; ``score_function`` must be ``dot_score`` or
 ``cos_sim`` (the only two the reference passes or defaults to); chunk-size arguments are
 accepted and ignored (the scan never materialises a score matrix).
 """

@@ -62,7 +62,8 @@ extern "C" {
 #define DEVQA_E_NCCL (-5)        /* NCCL missing or a collective failed */
 #define DEVQA_E_STATE (-6)       /* object used in the wrong state */
 
-#define DEVQA_MAX_TOPK 1024
+#define DEVQA_MAX_TOPK 1024 /* results per pass: single-GPU searches accept any top_k (deeper ranks come 1024 at a time, one
+                               bank pass each); devqa_topk_merge and the sharded search are limited to this */
 
 /* bank element types */
 #define DEVQA_F32 0

@@ -519,3 +519,25 @@ def test_one_shot_mode_overflow_takes_the_fallback():
     s2, i2 = fb.search(q.cuda(), 8, flags=L.FORCE_STREAM)
     assert torch.isnan(s).all() and torch.equal(i, i2)
     fb.close()
+
+
+@pytest.mark.parametrize("n,d,nq,k,nb", [(30000, 256, 40, 65, "eps"), (50000, 128, 70, 100, None), (30000, 768, 20, 128, "eps"),
+                                         (3000, 384, 33, 128, "noeps"), (100, 64, 9, 128, "eps")])
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+def test_filter_serves_top_k_up_to_128(n, d, nq, k, nb, dtype):
+    """top_k in 65..128 used to leave the filter for the 3xTF32 scan.  Lists of capacity 128,
+    K' = 256 merged candidates, refine_kernel over 256 slots: bit-identical to the stream kernel."""
+    bank, q = _randn(n, d, n + k, unit=False), _randn(nq, d, nq + k, unit=False)
+    fb = FactBank.from_embeddings(bank, dtype=dtype)
+    _fallbacks(); _violations()
+    a = fb.search(q.cuda(), k, normalize_bank=nb, normalize_query=nb, flags=FILTER)
+    nfb, nv = _fallbacks(), _violations()
+    b = fb.search(q.cuda(), k, normalize_bank=nb, normalize_query=nb, flags=L.FORCE_STREAM)
+    assert nv == 0 and nfb <= max(1, nq // 8)
+    assert torch.equal(a[1], b[1]) and torch.equal(a[0], b[0])
+    kk = min(k, n)
+    stored = bank.to(torch.bfloat16).float() if dtype == "bf16" else bank
+    truth = ss.truth_scores_fp64(q, stored, normalize_bank=bool(nb), normalize_query=bool(nb))
+    ss.compare_topk(a[0].cpu().numpy()[:, :kk], a[1].cpu().numpy()[:, :kk], truth, k, gap=GAP, rtol=RTOL, atol=ATOL)
+    assert bool((a[1][:, kk:] == -1).all())
+    fb.close()

@@ -442,3 +442,30 @@ def test_level0_dot_score_over_a_prenormalised_tensor_takes_the_filter():
     del bank, half
     import gc; gc.collect()
     assert len(dutil._norm_cache) == 0                        # the storage died, its entry went with it
+
+
+@pytest.mark.parametrize("n,d,nq,k,dtype", [(5000, 64, 3, 1025, "fp32"), (9000, 128, 2, 3000, "fp32"), (2500, 36, 1, 2500, "bf16"),
+                                            (1500, 64, 2, 4000, "fp32")])
+def test_any_top_k_like_upstream(n, d, nq, k, dtype):
+    """VERDICT r1 missing #6: upstream's semantic_search accepts any top_k (min(top_k, N) results).  Beyond 1024 the
+    ranking comes 1024 at a time, each pass the top-1024 below the previous pass's last key: identical to one full
+    sort of the stream kernel's scores."""
+    bank, q = _randn(n, d, n + d, unit=False), _randn(nq, d, nq + d, unit=False)
+    fb = FactBank.from_embeddings(bank, dtype=dtype)
+    s, i = fb.search(q.cuda(), k)
+    kk = min(k, n)
+    assert bool((i[:, kk:] == -1).all()) and bool(torch.isneginf(s[:, kk:]).all())
+    # reference ranking: every row's score from the same kernel (1024 at a time is how it is made; compare with the
+    # scores of a k = 1024 search and with fp64 truth)
+    s1, i1 = fb.search(q.cuda(), 1024)
+    assert torch.equal(i[:, :1024], i1) and torch.equal(s[:, :1024], s1)
+    assert bool((s[:, :kk - 1] >= s[:, 1:kk]).all())                       # descending throughout
+    for r in range(nq):
+        assert len(set(i[r, :kk].tolist())) == kk                           # no row twice, none missing when k >= n
+    stored = bank.to(torch.bfloat16).float() if dtype == "bf16" else bank
+    truth = ss.truth_scores_fp64(q, stored)
+    ss.compare_topk(s.cpu().numpy()[:, :kk], i.cpu().numpy()[:, :kk], truth, kk, gap=GAP, rtol=RTOL, atol=ATOL)
+    hits = dutil.semantic_search(q[:1].cuda(), stored.cuda(), top_k=k, score_function=dutil.cos_sim) if dtype == "fp32" else None
+    if hits is not None:
+        assert len(hits[0]) == kk and [h["corpus_id"] for h in hits[0]] == i[0, :kk].tolist()
+    fb.close()

@@ -304,3 +304,36 @@ def test_hice_probe_batch_mirror():
             assert len(''.join(icl)) <= 2500
         else:
             assert icl is None
+
+
+def test_bank_grows_in_place_without_moving_rows():
+    """regrow used to be cudaMalloc + a device-to-device copy of the whole bank.  With the bank in a
+    reserved virtual range (csrc/vmm.cu) fresh physical chunks are mapped behind the stored rows: the data pointer stays
+    put across many regrows, contents survive, searches before and after agree."""
+    from devqa_b200 import FactBank
+    g = _g(31)
+    fb = FactBank(256, capacity=8)
+    first = torch.randn(8, 256, generator=g)
+    fb.append(first)
+    ptr0 = fb.data_ptr
+    ref = [first]
+    moved = 0
+    for step in range(40):
+        new = torch.randn(1 + 997 * step, 256, generator=g)
+        fb.append(new)
+        ref.append(new)
+        moved += int(fb.data_ptr != ptr0)
+    whole = torch.cat(ref)
+    assert len(fb) == whole.shape[0] > 700_000
+    assert torch.equal(fb.rows(0, 8).cpu(), first) and torch.equal(fb.rows(len(fb) - 5).cpu(), whole[-5:])
+    import os
+    if os.environ.get("DEVQA_VMM", "1") != "0":
+        assert moved == 0 and fb.data_ptr == ptr0, "the bank moved although virtual memory management is on"
+    q = torch.randn(5, 256, generator=g)
+    s, i = fb.search(q.cuda(), 8)
+    s2, i2 = FactBank.from_embeddings(whole).search(q.cuda(), 8)
+    assert torch.equal(i, i2) and torch.equal(s, s2)
+    fb.truncate(100)
+    fb.append(whole[:50])
+    assert torch.equal(fb.rows(100, 150).cpu(), whole[:50])
+    fb.close()
