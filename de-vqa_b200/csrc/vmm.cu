@@ -5,7 +5,7 @@
 // copy of everything stored so far: amortised O(1), but every regrow moved up to 30 GB and needed ~2.5x the bank in
 // free memory for a moment.  Here the bank lives in one reserved virtual address range and growing it maps fresh
 // physical chunks BEHIND the rows already there: no copy, no move, no transient second buffer; the data pointer
-// only changes if the reservation itself (4x the first request, at least 1 GiB) is outgrown, and even then the
+// only changes if the reservation itself (4x the first request, at least 4 GiB of address space) is outgrown, and even then the
 // physical chunks are re-mapped, not copied.
 //
 // The driver entry points are fetched with cudaGetDriverEntryPoint (the library does not link libcuda); if they are
@@ -117,7 +117,7 @@ int vmm_grow(VmmBuffer* b, size_t want_bytes, bool* moved) {
   if (add < geometric) add = geometric;
   const size_t need = b->mapped + add;
   if (need > b->reserved) {
-    size_t res = b->reserved ? b->reserved : size_t(1) << 30;
+    size_t res = b->reserved ? b->reserved : size_t(4) << 30;
     while (res < need * (b->reserved ? 2 : 4) && res < (size_t(1) << 40)) res <<= 1;
     if (res < need) res = round_up(need);
     CUdeviceptr fresh = 0;
