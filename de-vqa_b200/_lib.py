@@ -14,6 +14,7 @@ MAX_TOPK = 1024
 F32, BF16 = 0, 1
 NORMALIZE_BANK, NORMALIZE_QUERY, NOEPS = 1 << 0, 1 << 1, 1 << 2
 FORCE_STREAM, FORCE_TENSOR, FORCE_TF32X3, FORCE_FILTER = 1 << 8, 1 << 9, 1 << 10, 1 << 11
+NO_SHADOW = 1 << 15
 DEBUG_TIGHT_BOUND = 1 << 12
 DEBUG_NO_ONESHOT = 1 << 13
 DEBUG_FILTER_ONLY = 1 << 22
@@ -45,6 +46,8 @@ SIGNATURES = {
     "devqa_bank_data": (_p, [_p]),
     "devqa_bank_reserve": (_i, [_p, _i64, _p]),
     "devqa_bank_append": (_i, [_p, _p, _i64, _i64, _i, _p]),
+    "devqa_bank_set_shadow": (_i, [_p, _i, _p]),
+    "devqa_bank_has_shadow": (_i, [_p]),
     "devqa_bank_read_rows": (_i, [_p, _i64, _i64, _p, _i64, _p]),
     "devqa_bank_truncate": (_i, [_p, _i64]),
     "devqa_bank_set_id_map": (_i, [_p, _i64, _i64, _i, _i]),

@@ -74,7 +74,7 @@ class FactBank:
     """
 
     def __init__(self, dim: int, device: Union[int, str, torch.device] = 0, dtype: str = "fp32",
-                 capacity: int = 0):
+                 capacity: int = 0, shadow: bool = False):
         dev = torch.device(device if not isinstance(device, int) else f"cuda:{device}")
         if dev.type != "cuda":
             raise ValueError("FactBank lives on a CUDA device; there is no CPU path")
@@ -85,6 +85,8 @@ class FactBank:
         self._h = C.c_void_p()
         torch.cuda.init()
         L.check(L.lib().devqa_bank_create(C.byref(self._h), self.device_index, self.dim, int(capacity), self.dtype))
+        if shadow:
+            self.set_shadow(True)
         # text columns of the pickle layout (util.py:84-86); optional
         self.sentences: List[str] = []
         self.images: List[str] = []
@@ -92,11 +94,11 @@ class FactBank:
 
     # ---- construction from the reference's on-disk layouts --------------------------------------
     @classmethod
-    def from_embeddings(cls, embeddings, device=0, dtype: str = "fp32", capacity: int = 0) -> "FactBank":
+    def from_embeddings(cls, embeddings, device=0, dtype: str = "fp32", capacity: int = 0, shadow: bool = False) -> "FactBank":
         emb = embeddings if isinstance(embeddings, torch.Tensor) else torch.as_tensor(np.asarray(embeddings))
         if emb.dim() != 2:
             raise ValueError("embeddings must be [N, D]")
-        bank = cls(emb.shape[1], device=device, dtype=dtype, capacity=max(capacity, emb.shape[0]))
+        bank = cls(emb.shape[1], device=device, dtype=dtype, capacity=max(capacity, emb.shape[0]), shadow=shadow)
         bank.append(emb)
         return bank
 
@@ -143,6 +145,15 @@ class FactBank:
             self.close()
         except Exception:
             pass
+
+    def set_shadow(self, enable: bool = True) -> None:
+        """Keep (or drop) a bf16 shadow of this fp32 bank: large scans stream 2 bytes per element instead of 4 and
+        re-score their candidates against the fp32 rows -- results stay the exact fp32 results, bit for bit."""
+        L.check(L.lib().devqa_bank_set_shadow(self._h, 1 if enable else 0, _stream_ptr(self.device_index)))
+
+    @property
+    def has_shadow(self) -> bool:
+        return bool(L.lib().devqa_bank_has_shadow(self._h))
 
     def set_id_map(self, id_base: int = 0, chunk_rows: int = 0, rank: int = 0, world: int = 1) -> None:
         L.check(L.lib().devqa_bank_set_id_map(self._h, int(id_base), int(chunk_rows), int(rank), int(world)))

@@ -159,6 +159,8 @@ struct SearchArgs {
   const float* row_sumsq = nullptr;
   const uint32_t* max_sumsq = nullptr;   // library-owned banks: max ||row||^2 over every row ever appended (float bits)
   const uint64_t* below = nullptr;       // deep top-k passes: per-query exclusive upper bound key
+  const void* shadow = nullptr;          // fp32 library banks: optional bf16 copy of the rows (the filter scans IT)
+  int64_t shadow_ld = 0;
 };
 
 static int validate(const SearchArgs& a) {
@@ -359,12 +361,16 @@ static int run_search(Scratch* s, const SearchArgs& a, uint64_t* out_keys, float
   const bool filter_path = !(a.flags & DEVQA_FORCE_TF32X3) && a.top_k <= 128 && a.dim <= 16384 &&
                            (a.dtype == DEVQA_F32 ? ((a.flags & DEVQA_NORMALIZE_BANK) || (a.row_sumsq && a.max_sumsq))
                                                  : (a.row_sumsq != nullptr && a.max_sumsq != nullptr));
+  // bf16 shadow: only where refine reads the per-CTA lists (its 512-candidate capacity takes the shadow's wide error band)
+  const bool shadow_scan = filter_path && a.shadow != nullptr && a.dtype == DEVQA_F32 && a.top_k <= 64 &&
+                           (a.n_rows + 127) / 128 >= s->sm_count && s->sm_count >= a.top_k &&
+                           !(a.flags & (DEVQA_DEBUG_FILTER_ONLY | DEVQA_NO_SHADOW));
   if (tc_ok && filter_path) {
     const int64_t tiles = (a.n_rows + 127) / 128;
     // tiny banks (fewer tiles than SMs), up to 8 queries: ONE stream launch (~15 us) beats the seven-launch pipeline
     if (a.n_queries <= 8 && tiles < s->sm_count) use_tc = false;
     // large bf16 banks: the bf16 stream kernel manages 5.1 TB/s, the tensor path 6.9 -- also for one or two queries
-    if (a.dtype == DEVQA_BF16 && a.n_queries <= 2 && tiles >= 8 * int64_t(s->sm_count)) use_tc = true;
+    if ((a.dtype == DEVQA_BF16 || shadow_scan) && a.n_queries <= 2 && tiles >= 8 * int64_t(s->sm_count)) use_tc = true;
   }
   if (a.flags & DEVQA_FORCE_STREAM) use_tc = false;
   if (a.flags & DEVQA_FORCE_TENSOR) {
@@ -392,7 +398,7 @@ static int run_search(Scratch* s, const SearchArgs& a, uint64_t* out_keys, float
     // G-GPU results would differ from 1-GPU results in the last bits of the scores.)
     // bf16 banks: the same filter with queries rounded to bf16 (library-owned banks: cached row norms), bf16x3 as fallback.
     const bool filt = filter_path;
-    const int filt_mode = a.dtype == DEVQA_F32 ? kTcTf32x1 : kTcBf16x1;
+    const int filt_mode = (a.dtype == DEVQA_F32 && !shadow_scan) ? kTcTf32x1 : kTcBf16x1;
     const int exact_mode = a.dtype == DEVQA_F32 ? kTcTf32x3 : kTcBf16x3;
     if (s->profiling) s->prof_searches++;
     constexpr int64_t kChunkQ = 1024;                                  // bounds the candidate scratch (grid x Q x kcap keys)
@@ -436,7 +442,11 @@ static int run_search(Scratch* s, const SearchArgs& a, uint64_t* out_keys, float
       const int64_t tiles = (a.n_rows + 127) / 128;
       // (top_k > 64: the top_k-th largest of <= 148 CTA bests is too loose a cut for refine_lists -- merged path, K' = 256)
       side.merge = (a.flags & DEVQA_DEBUG_FILTER_ONLY) || tiles < s->sm_count || s->sm_count < a.top_k || a.top_k > 64;
-      if ((rc = tc_pipeline(s, ac, filt_mode, &side, nullptr, nullptr, nullptr, nullptr, stream))) return rc;
+      {
+        SearchArgs as = ac;                                              // what the filter SCANS
+        if (shadow_scan) { as.bank = a.shadow; as.bank_ld = a.shadow_ld; as.dtype = DEVQA_BF16; as.flags |= kFlagShadowScan; }
+        if ((rc = tc_pipeline(s, as, filt_mode, &side, nullptr, nullptr, nullptr, nullptr, stream))) return rc;
+      }
       if (a.flags & DEVQA_DEBUG_FILTER_ONLY) {                           // tests: the filter's own upper bounds
         if ((rc = merge_lists_launch(side.akeys, 1, ac.n_queries, kp, kp, a.top_k, ok, os, oi, stream))) return rc;
         continue;
@@ -523,6 +533,11 @@ struct devqa_bank {
   int64_t size = 0, capacity = 0;
   void* data = nullptr;
   devqa::VmmBuffer* vmm = nullptr; // rows live in a reserved virtual range that grows in place (vmm.cu); nullptr: cudaMalloc + copy
+  // Optional bf16 SHADOW of an fp32 bank (devqa_bank_set_shadow): the tensor-core filter streams these 2 bytes per
+  // element instead of 4, candidates are re-scored against the fp32 rows -- exact fp32 results from half the bytes.
+  void* shadow = nullptr;
+  devqa::VmmBuffer* shadow_vmm = nullptr;
+  int64_t shadow_ld = 0, shadow_capacity = 0;
   float* sumsq = nullptr;          // cached ||row||^2 per stored row (bf16 banks: of the rounded row)
   uint32_t* max_sumsq = nullptr;   // device word: max of those over every row ever appended (float bits; never shrinks)
   devqa::IdMap idmap{0, 0, 0, 1};
@@ -610,12 +625,52 @@ static int bank_grow(devqa_bank* b, int64_t want_rows, cudaStream_t stream) {
   return DEVQA_OK;
 }
 
+// keep the bf16 shadow's storage in step with the bank's capacity
+static int shadow_grow(devqa_bank* b, int64_t cap, cudaStream_t stream) {
+  if (!b->shadow_ld || cap <= b->shadow_capacity) return DEVQA_OK;
+  const size_t bytes = size_t(cap) * b->shadow_ld * 2;
+  if (b->shadow_vmm) {
+    bool moved = false;
+    int rc = vmm_grow(b->shadow_vmm, bytes, &moved);
+    if (rc == DEVQA_OK) { b->shadow = vmm_data(b->shadow_vmm); b->shadow_capacity = cap; return DEVQA_OK; }
+    if (rc != DEVQA_E_UNSUPPORTED || b->shadow != nullptr) return rc;
+    vmm_destroy(b->shadow_vmm);
+    b->shadow_vmm = nullptr;
+  }
+  void* fresh = nullptr;
+  cudaError_t e = cudaMalloc(&fresh, bytes);
+  if (e != cudaSuccess) {
+    set_error("cudaMalloc of %zu bytes for the bf16 shadow failed: %s", bytes, cudaGetErrorString(e));
+    return DEVQA_E_NOMEM;
+  }
+  if (b->shadow) {
+    if (b->size > 0)
+      DEVQA_CUDA(cudaMemcpyAsync(fresh, b->shadow, size_t(b->size) * b->shadow_ld * 2, cudaMemcpyDeviceToDevice, stream));
+    DEVQA_CUDA(cudaDeviceSynchronize());
+    DEVQA_CUDA(cudaFree(b->shadow));
+  }
+  b->shadow = fresh;
+  b->shadow_capacity = cap;
+  return DEVQA_OK;
+}
+
+// rows [first, first + n) were just written to the fp32 bank: round them into the shadow
+static int shadow_update(devqa_bank* b, int64_t first, int64_t n, cudaStream_t stream) {
+  if (!b->shadow_ld || n == 0) return DEVQA_OK;
+  int rc = shadow_grow(b, b->capacity, stream);
+  if (rc) return rc;
+  const float* src = static_cast<const float*>(b->data) + size_t(first) * b->ld;
+  char* dst = static_cast<char*>(b->shadow) + size_t(first) * b->shadow_ld * 2;
+  return convert_rows_launch(src, b->ld, dst, DEVQA_BF16, b->shadow_ld, n, b->dim, stream);
+}
+
 static SearchArgs bank_args(const devqa_bank* b, const float* q, int64_t nq, int64_t qld, int k, unsigned flags) {
   SearchArgs a{};
   a.bank = b->data; a.dtype = b->dtype; a.n_rows = b->size; a.dim = b->dim; a.bank_ld = b->ld;
   a.queries = q; a.n_queries = nq; a.query_ld = qld; a.top_k = k; a.flags = flags; a.idmap = b->idmap;
   a.row_sumsq = b->sumsq;
   a.max_sumsq = b->max_sumsq;
+  a.shadow = b->shadow; a.shadow_ld = b->shadow_ld;
   return a;
 }
 
@@ -836,6 +891,7 @@ int devqa_bank_destroy(devqa_bank* b) {
   if (!b) return DEVQA_OK;
   DEVQA_ON_DEVICE(b->device);
   if (b->data || b->vmm) cudaDeviceSynchronize();
+  if (b->shadow_vmm) vmm_destroy(b->shadow_vmm); else if (b->shadow) cudaFree(b->shadow);
   if (b->vmm) { vmm_destroy(b->vmm); if (b->sumsq) cudaFree(b->sumsq); }
   else if (b->data) { cudaFree(b->data); cudaFree(b->sumsq); }
   if (b->max_sumsq) cudaFree(b->max_sumsq);
@@ -891,9 +947,36 @@ int devqa_bank_append(devqa_bank* b, const float* rows, int64_t n, int64_t ld, i
     }
   }
   if ((rc = row_sumsq_launch(dst, b->dtype, n, b->dim, b->ld, b->sumsq + b->size, stream, b->max_sumsq))) return rc;
+  if ((rc = shadow_update(b, b->size, n, stream))) return rc;
   b->size += n;
   return DEVQA_OK;
 }
+
+int devqa_bank_set_shadow(devqa_bank* b, int enable, void* stream_) {
+  DEVQA_REQUIRE(b != nullptr, "bank is null");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  DEVQA_ON_DEVICE(b->device);
+  if (!enable) {
+    if (b->shadow_ld) {
+      DEVQA_CUDA(cudaDeviceSynchronize());
+      if (b->shadow_vmm) vmm_destroy(b->shadow_vmm); else if (b->shadow) cudaFree(b->shadow);
+      b->shadow = nullptr; b->shadow_vmm = nullptr; b->shadow_ld = 0; b->shadow_capacity = 0;
+    }
+    return DEVQA_OK;
+  }
+  if (b->dtype != DEVQA_F32) { set_error("a bf16 shadow only makes sense for an fp32 bank"); return DEVQA_E_UNSUPPORTED; }
+  if (b->shadow_ld) return DEVQA_OK;
+  static const bool vmm_on = getenv("DEVQA_VMM") == nullptr || atoi(getenv("DEVQA_VMM")) != 0;
+  b->shadow_ld = (b->dim + 7) / 8 * 8;                       // rows stay 16-byte aligned
+  b->shadow_vmm = vmm_on ? vmm_create(b->device) : nullptr;
+  int rc = shadow_update(b, 0, b->size, stream);
+  if (rc) {
+    if (b->shadow_vmm) vmm_destroy(b->shadow_vmm); else if (b->shadow) cudaFree(b->shadow);
+    b->shadow = nullptr; b->shadow_vmm = nullptr; b->shadow_ld = 0; b->shadow_capacity = 0;
+  }
+  return rc;
+}
+int devqa_bank_has_shadow(const devqa_bank* b) { return b && b->shadow_ld ? 1 : 0; }
 
 int devqa_bank_read_rows(const devqa_bank* b, int64_t first_row, int64_t n, float* dst, int64_t dst_ld, void* stream_) {
   DEVQA_REQUIRE(b != nullptr, "bank is null");
@@ -1342,6 +1425,7 @@ int devqa_bank_append_synthetic(devqa_bank* b, int64_t n_rows, uint64_t seed, in
   char* dst = static_cast<char*>(b->data) + size_t(b->size) * b->ld * b->esz();
   if ((rc = fill_synthetic_launch(dst, b->dtype, n_rows, b->dim, b->ld, seed, first_global_row, kind, stream))) return rc;
   if ((rc = row_sumsq_launch(dst, b->dtype, n_rows, b->dim, b->ld, b->sumsq + b->size, stream, b->max_sumsq))) return rc;
+  if ((rc = shadow_update(b, b->size, n_rows, stream))) return rc;
   b->size += n_rows;
   return DEVQA_OK;
 }

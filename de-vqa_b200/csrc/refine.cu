@@ -31,7 +31,8 @@ namespace {
 
 constexpr int kRefineThreads = 256;
 constexpr int kMaxKp = 256;        // refine_kernel: merged candidates per query (K' = 256 serves top_k <= 128)
-constexpr int kListKp = 128;       // refine_lists_kernel: candidates re-scored per query (top_k <= 64)
+constexpr int kListKp = 512;       // refine_lists_kernel: candidates per query (top_k <= 64; the bf16-shadow filter's
+                                   // wide error band leaves ~200 of them on a 10M-row bank)
 
 // Canary of the filter's error bound.  Every candidate that is re-scored has both its upper bound u (the score field of
 // the key the scan produced: u = s~ + E) and its exact score s.  The whole completeness proof rests on
@@ -253,39 +254,8 @@ __global__ void __launch_bounds__(kRefineListThreads) refine_lists_kernel(const 
   }
   __syncthreads();
   uint32_t n_raw = s_count;
-  // Second cut.  T from the CTAs' bests is loose when top_k is not small against the number of CTAs (k = 64 of 148:
-  // ~30% more rows above it than the true k-th best has).  With the first cut in shared memory the exact k-th
-  // best upper bound of everything kept is one bitonic sort away: keep what is >= that - 2E.
-  if (n_raw > uint32_t(kListKp) && n_raw <= uint32_t(kWide)) {
-    uint64_t mine = threadIdx.x < int(n_raw) ? ak[threadIdx.x] : kEmptyKey;
-    __syncthreads();
-    ak[threadIdx.x] = mine;
-    __syncthreads();
-    for (int k = 2; k <= kWide; k <<= 1) {
-      for (int j = k >> 1; j > 0; j >>= 1) {
-        const int i = threadIdx.x, l = i ^ j;
-        if (l > i) {
-          const uint64_t a = ak[i], b = ak[l];
-          const bool desc = (i & k) == 0;
-          if (desc ? a < b : a > b) { ak[i] = b; ak[l] = a; }
-        }
-        __syncthreads();
-      }
-    }
-    // ak is sorted by upper bound, descending; the k-th entry bounds the exact k-th best from below (minus 2E)
-    if (threadIdx.x == 0) {
-      float maxn = 1.f;
-      if (!(p.flags & DEVQA_NORMALIZE_BANK)) maxn = sqrtf(__uint_as_float(*p.bank_max_sumsq));
-      const float t = key_score(ak[p.top_k - 1]) - 2.0001f * p.qerr[q] * maxn;
-      s_tcode = t == t ? score_code(t) : 0u;
-      s_count = 0u;
-    }
-    __syncthreads();
-    const uint32_t t2 = s_tcode;
-    if (threadIdx.x < int(n_raw) && uint32_t(ak[threadIdx.x] >> 32) >= t2) atomicAdd(&s_count, 1u);   // a prefix: ak is sorted
-    __syncthreads();
-    n_raw = s_count;
-  }
+  // (A second cut on the exact k-th best upper bound of the kept keys used to follow here.  The two-phase re-scoring
+  // below supersedes it: phase 2 only touches candidates whose upper bound reaches the k-th best EXACT score.)
   const int n = n_raw < uint32_t(kListKp) ? int(n_raw) : kListKp;
   // ---- exact re-scoring, two phases (like refine_kernel): the top_k candidates by upper bound first; then only those
   // whose upper bound can still beat the k-th best exact score found.  Re-scoring is the kernel's whole cost (one
@@ -293,9 +263,10 @@ __global__ void __launch_bounds__(kRefineListThreads) refine_lists_kernel(const 
   __shared__ float s_prelim;
   __shared__ uint64_t byu[kListKp];                                    // candidates sorted by upper bound
   __syncthreads();
+  const int n_sort = (n + 31) & ~31;                                   // rank sorts walk n_sort slots, not 512
   if (threadIdx.x >= n && threadIdx.x < kListKp) ak[threadIdx.x] = kEmptyKey;
   __syncthreads();
-  rank_sort(ak, byu, kListKp);
+  rank_sort(ak, byu, n_sort);
   auto row_of = [&](int c) {
     int64_t row = int64_t(key_id(byu[c])) - p.idmap.base;
     if (p.idmap.chunk > 0) row = ((row / p.idmap.chunk) / p.idmap.world) * p.idmap.chunk + row % p.idmap.chunk;
@@ -335,7 +306,7 @@ __global__ void __launch_bounds__(kRefineListThreads) refine_lists_kernel(const 
     if (!(key_score(byu[c]) < prelim)) rescore(c);                     // warp-uniform; NaN upper bounds are re-scored
   __syncthreads();
   uint64_t* const srt = ak;                                            // (the compacted keys are dead now)
-  rank_sort(ex, srt, kListKp);
+  rank_sort(ex, srt, n_sort);
   if (threadIdx.x == 0) {
     const uint64_t kth = srt[p.top_k - 1];
     bool complete = n_raw <= uint32_t(kListKp);                        // otherwise candidates were cut off
@@ -376,8 +347,8 @@ static size_t refine_query_smem(const RefineParams& p, bool vec) {
 
 int refine_lists_launch(const RefineParams& p, cudaStream_t stream) {
   if (p.n_queries == 0) return DEVQA_OK;
-  if (p.dcount) DEVQA_REQUIRE(p.top_k <= kListKp / 2 && p.dcap <= 512 && p.dcand, "refine: unsupported direct candidate geometry");
-  else DEVQA_REQUIRE(p.top_k <= kListKp / 2 && p.n_lists <= 160 && p.n_lists >= p.top_k, "refine: unsupported list geometry");
+  if (p.dcount) DEVQA_REQUIRE(p.top_k <= 64 && p.dcap <= 512 && p.dcand, "refine: unsupported direct candidate geometry");
+  else DEVQA_REQUIRE(p.top_k <= 64 && p.n_lists <= 160 && p.n_lists >= p.top_k, "refine: unsupported list geometry");
   const bool vec = refine_vectorised(p);
   const size_t smem = refine_query_smem(p, vec);
   void (*kern)(RefineParams) = p.bank_dtype == DEVQA_F32

@@ -75,10 +75,15 @@ constexpr int kTcTf32x3 = 0, kTcBf16x3 = 1, kTcTf32x1 = 2, kTcBf16x1 = 3;   // k
 // (a few rows per query), while a violated bound would silently lose a row.  refine.cu checks  u - 2E <= s <= u  for
 // every candidate it re-scores (devqa_filter_bound_violations), tests/test_gpu_filter.py measures the actual error
 // on constructed worst cases against this bound.
-__host__ __device__ inline float tc_filter_relerr(int64_t dim, bool bf16_bank = false) {
-  const float inputs = bf16_bank ? 0.00390625f : 1.5f * 0.0009765625f;       // 2^-8 | 2^-10 + 2^-11
+// bf16 SHADOW of an fp32 bank (shadow = true): the bank words were rounded to nearest bf16 as well (<= 2^-8 each), so
+// inputs = (1 + 2^-8)^2 - 1 = 2^-7 + 2^-16 relative to the ORIGINAL fp32 row's norm.
+__host__ __device__ inline float tc_filter_relerr(int64_t dim, bool bf16_bank = false, bool shadow = false) {
+  const float inputs = shadow ? 0.0078125f + 1.52587890625e-05f                // 2^-7 + 2^-16
+                              : (bf16_bank ? 0.00390625f : 1.5f * 0.0009765625f);   // 2^-8 | 2^-10 + 2^-11
   return inputs + 1.9073486328125e-06f + float(dim) * 2.384185791015625e-07f;  // + 2^-19 + dim * 2^-22
 }
+// internal flag bit (never set by callers): the bf16 bank being scanned is the shadow of an fp32 bank
+constexpr unsigned kFlagShadowScan = 1u << 14;
 bool scan_tc_supported(int bank_dtype, const void* bank, int64_t dim, int64_t bank_ld, int top_k);
 int scan_tc_plan(int mode, int n_queries, int64_t dim, int kcap, bool cached_norms, int64_t n_tiles, int sm_count,
                  unsigned flags, int* qp_out, int* stages_out, bool* pair_out, bool oneshot = false);

@@ -379,11 +379,19 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_stream_kernel(const Scan
     uint64_t* sacc = lists;                            // [kScanWarps][32], the lists are dead now
     const int rev = 31 - lane;
     for (int q = 0; q < p.nq_pass; ++q) {
-      uint64_t acc = kEmptyKey;
-      for (int l = warp; l < int(gridDim.x); l += kScanWarps) {
-        const uint64_t* src = p.cand + (size_t(l) * p.n_queries + (p.q0 + q)) * 32;
-        acc = warp_merge32(acc, __ldcg(src + rev), lane);
+      // all of this warp's lists are requested before the first merge: ONE L2 round trip instead of ten dependent
+      // ones (the serial chain was half of the device time of a 6345-row search)
+      constexpr int kMaxLists = (160 + kScanWarps - 1) / kScanWarps;
+      uint64_t v[kMaxLists];
+#pragma unroll
+      for (int i = 0; i < kMaxLists; ++i) {
+        const int l = warp + i * kScanWarps;
+        v[i] = l < int(gridDim.x) ? __ldcg(p.cand + (size_t(l) * p.n_queries + (p.q0 + q)) * 32 + rev) : kEmptyKey;
       }
+      uint64_t acc = kEmptyKey;
+#pragma unroll
+      for (int i = 0; i < kMaxLists; ++i)
+        if (warp + i * kScanWarps < int(gridDim.x)) acc = warp_merge32(acc, v[i], lane);   // warp-uniform
       __syncthreads();
       sacc[warp * 32 + lane] = acc;
       __syncthreads();

@@ -1445,7 +1445,8 @@ __global__ void __launch_bounds__(128) prep_queries_filt_kernel(const float* __r
         s_inv = inv;
         if (live) {
           qinv[r] = inv;
-          qerr[r] = tc_filter_relerr(dim, BF16) * sqrtf(nn) * ((flags & DEVQA_DEBUG_TIGHT_BOUND) ? 0.015625f : 1.f);
+          qerr[r] = tc_filter_relerr(dim, BF16, BF16 && (flags & kFlagShadowScan)) * sqrtf(nn) *
+                    ((flags & DEVQA_DEBUG_TIGHT_BOUND) ? 0.015625f : 1.f);
         }
       }
     }

@@ -126,12 +126,13 @@ class Communicator:
 class ShardedFactBank:
     """This rank's shard of a row-sharded bank + the collective search."""
 
-    def __init__(self, dim: int, comm: Communicator, dtype: str = "fp32", chunk_rows: int = 0, capacity: int = 0):
+    def __init__(self, dim: int, comm: Communicator, dtype: str = "fp32", chunk_rows: int = 0, capacity: int = 0,
+                 shadow: bool = False):
         self.comm = comm
         self.rank, self.world = comm.rank, comm.world
         self.dim = dim
         self.chunk_rows = int(chunk_rows)
-        self.local = FactBank(dim, device=comm.device, dtype=dtype, capacity=capacity)
+        self.local = FactBank(dim, device=comm.device, dtype=dtype, capacity=capacity, shadow=shadow)
         self.total_rows = 0
         if self.chunk_rows > 0:
             self.local.set_id_map(0, self.chunk_rows, self.rank, self.world)
@@ -152,12 +153,12 @@ class ShardedFactBank:
 
     @classmethod
     def synthetic(cls, n_rows: int, dim: int, comm: Communicator, seed: int, kind: int = 0, dtype: str = "fp32",
-                  batch_rows: int = 1 << 20) -> "ShardedFactBank":
+                  batch_rows: int = 1 << 20, shadow: bool = False) -> "ShardedFactBank":
         """Contiguous shards of the counter-based synthetic bank (any world size reproduces the
         same global bank)."""
         bounds = shard_bounds(n_rows, comm.world)
         lo, hi = bounds[comm.rank], bounds[comm.rank + 1]
-        sb = cls(dim, comm, dtype=dtype, capacity=hi - lo)
+        sb = cls(dim, comm, dtype=dtype, capacity=hi - lo, shadow=shadow)
         sb.local.set_id_map(lo, 0, 0, 1)
         for r0 in range(lo, hi, batch_rows):
             sb.local.append_synthetic(min(batch_rows, hi - r0), seed, first_global_row=r0, kind=kind)

@@ -541,3 +541,69 @@ def test_filter_serves_top_k_up_to_128(n, d, nq, k, nb, dtype):
     ss.compare_topk(a[0].cpu().numpy()[:, :kk], a[1].cpu().numpy()[:, :kk], truth, k, gap=GAP, rtol=RTOL, atol=ATOL)
     assert bool((a[1][:, kk:] == -1).all())
     fb.close()
+
+
+# ---- bf16 shadow of an fp32 bank: exact fp32 results from half the bytes --------------------------------------------
+@pytest.mark.parametrize("n,d,nq,k,nb,unit", [(40000, 768, 64, 32, "eps", True), (25000, 384, 5, 16, "eps", False),
+                                              (60000, 128, 130, 5, None, False), (19000, 100, 70, 64, "noeps", False),
+                                              (300000, 64, 1, 32, "eps", True), (20000, 768, 300, 32, None, True)])
+def test_shadow_bank_returns_the_exact_fp32_results(n, d, nq, k, nb, unit):
+    """The filter scans a bf16 SHADOW of the fp32 bank (2 bytes per element), candidates are re-scored against the
+    fp32 rows: bit-identical to the stream kernel on the fp32 bank, canary silent."""
+    bank, q = _randn(n, d, n + d, unit=unit), _randn(nq, d, nq + k, unit=unit)
+    if not unit:
+        bank = bank * torch.exp(0.5 * torch.randn(n, 1, generator=torch.Generator().manual_seed(n)))
+    fb = FactBank.from_embeddings(bank, shadow=True)
+    assert fb.has_shadow
+    _fallbacks(); _violations()
+    a = fb.search(q.cuda(), k, normalize_bank=nb, normalize_query=nb, flags=L.FORCE_TENSOR)
+    nfb, nv = _fallbacks(), _violations()
+    b = fb.search(q.cuda(), k, normalize_bank=nb, normalize_query=nb, flags=L.FORCE_STREAM)
+    c = fb.search(q.cuda(), k, normalize_bank=nb, normalize_query=nb, flags=L.FORCE_TENSOR | L.NO_SHADOW)
+    assert nv == 0 and nfb <= max(1, nq // 8), (nfb, nv)
+    assert torch.equal(a[1], b[1]) and torch.equal(a[0], b[0])
+    assert torch.equal(a[1], c[1]) and torch.equal(a[0], c[0])
+    truth = ss.truth_scores_fp64(q, bank, normalize_bank=bool(nb), normalize_query=bool(nb))
+    ss.compare_topk(a[0].cpu().numpy(), a[1].cpu().numpy(), truth, k, gap=GAP, rtol=RTOL, atol=ATOL)
+    # appended rows reach the shadow too; dropping the shadow changes nothing
+    extra = _randn(1000, d, 5, unit=unit) * 3.0
+    fb.append(extra)
+    a2 = fb.search(q.cuda(), k, normalize_bank=nb, normalize_query=nb, flags=L.FORCE_TENSOR)
+    b2 = fb.search(q.cuda(), k, normalize_bank=nb, normalize_query=nb, flags=L.FORCE_STREAM)
+    assert torch.equal(a2[1], b2[1]) and torch.equal(a2[0], b2[0])
+    assert bool((a2[1] >= n).any()) or nb is not None                # (tripled rows show up in un-normalised searches)
+    fb.set_shadow(False)
+    assert not fb.has_shadow
+    a3 = fb.search(q.cuda(), k, normalize_bank=nb, normalize_query=nb, flags=L.FORCE_TENSOR)
+    assert torch.equal(a3[1], b2[1]) and torch.equal(a3[0], b2[0])
+    fb.close()
+
+
+@pytest.mark.parametrize("d", [768, 4096])
+def test_shadow_error_bound_on_the_constructed_worst_case(d):
+    """Rows AND queries one below the bf16 rounding midpoint, parallel, all positive: the per-element error reaches
+    2^-7 of ||row|| ||query||; the shadow's bound (2^-7 + 2^-16 + 2^-19 + D 2^-22) must hold for every pair, and the
+    real search must come back exact with the canary silent."""
+    rng = np.random.default_rng(d)
+    n, nq = 25000, 16                                         # >= 148 tiles: the shadow path is taken
+    e = rng.integers(120, 128, size=(n, d), dtype=np.uint32)
+    rows = _bits_to_f32((e << np.uint32(23)) | np.uint32(0x7FFF))
+    queries = _bits_to_f32((e[:nq] << np.uint32(23)) | np.uint32(0x7FFF))
+    fb = FactBank.from_embeddings(rows, shadow=True)
+    rel = 2.0 ** -7 + 2.0 ** -16 + 2.0 ** -19 + d * 2.0 ** -22
+    _fallbacks(); _violations()
+    a = fb.search(queries.cuda(), 8, normalize_bank="eps", normalize_query=None, flags=L.FORCE_TENSOR)
+    nfb, nv = _fallbacks(), _violations()
+    b = fb.search(queries.cuda(), 8, normalize_bank="eps", normalize_query=None, flags=L.FORCE_STREAM)
+    assert nv == 0
+    assert torch.equal(a[1], b[1]) and torch.equal(a[0], b[0])
+    assert a[1][:, 0].cpu().tolist() == list(range(nq))        # query j is parallel to row j: cosine 1
+    # the measured error of the shadow product for the parallel pairs, against the bound
+    r16, q16 = rows[:nq].to(torch.bfloat16).double(), queries.to(torch.bfloat16).double()
+    exact = (rows[:nq].double() * queries.double()).sum(1)
+    approx = (r16 * q16).sum(1)
+    scale = rows[:nq].double().norm(dim=1) * queries.double().norm(dim=1)
+    err = float(((exact - approx).abs() / scale).max())
+    _record(f"shadow_worstcase_d{d}", {"max_err": err, "bound": rel, "fallbacks": nfb})
+    assert 0.9 * 2.0 ** -7 < err < rel
+    fb.close()
