@@ -291,17 +291,21 @@ def test_bf16_filter_error_bound_holds(kind):
 
 
 def test_duplicated_rows_take_the_exact_fallback():
-    """200 identical consecutive rows: one CTA's list fills up with ties, rows it turns away are not provably
-    irrelevant, and the 3xTF32 scan redoes that query; ties resolve to ascending ids either way."""
+    """200 identical consecutive rows.  Persistent list epilogue (DEVQA_DEBUG_NO_ONESHOT): one CTA's list fills up with
+    ties, rows it turns away are not provably irrelevant, and the 3xTF32 scan redoes that query.  One-shot mode (the
+    default at this size): all 200 ties are emitted as candidates and re-scored, no fallback needed.  Ties resolve to
+    ascending ids either way."""
     bank = _randn(5000, 256, 11)
     bank[1000:1200] = bank[1000]
     q = torch.cat([bank[1000:1001] + 0.01 * _randn(1, 256, 12), _randn(15, 256, 13)])
     fb = FactBank.from_embeddings(bank)
     _fallbacks()
-    s, i = fb.search(q.cuda(), 32, flags=FILTER)
+    s, i = fb.search(q.cuda(), 32, flags=FILTER | L.DEBUG_NO_ONESHOT)
     n_fb = _fallbacks()
     assert 1 <= n_fb <= 2
     assert i[0].tolist() == list(range(1000, 1032))
+    s1, i1 = fb.search(q.cuda(), 32, flags=FILTER)
+    assert _fallbacks() == 0 and torch.equal(i1, i) and torch.equal(s1, s)
     truth = ss.truth_scores_fp64(q, bank)
     ss.compare_topk(s.cpu().numpy(), i.cpu().numpy(), truth, 32, gap=GAP, rtol=RTOL, atol=ATOL)
     # every query -- answered by the filter + re-scoring, or by the fallback and then re-scored in the same
