@@ -17,6 +17,7 @@ FORCE_STREAM, FORCE_TENSOR, FORCE_TF32X3, FORCE_FILTER = 1 << 8, 1 << 9, 1 << 10
 NO_SHADOW = 1 << 15
 DEBUG_TIGHT_BOUND = 1 << 12
 DEBUG_NO_ONESHOT = 1 << 13
+DEBUG_NO_EMIT = 1 << 3
 DEBUG_FILTER_ONLY = 1 << 22
 
 _p, _i, _i64, _u, _u64 = C.c_void_p, C.c_int, C.c_int64, C.c_uint, C.c_uint64

@@ -195,6 +195,8 @@ struct FilterSide {
   uint32_t* ocount = nullptr;    // [Q] candidates per query   }
   uint64_t* ocand = nullptr;     // [Q, kOneshotCap]
   bool oneshot = false;          // out: the scan ran in one-shot mode (refine reads ocand / ocount)
+  bool emit = false;             // out: the long scan emitted its candidates into ocand (no per-CTA lists)
+  int ocap = 0;                  // capacity of ocand per query (kOneshotCap / kEmitCap)
   int n_lists = 0;               // out: per-CTA lists per query
   int kcap = 0;                  // out: capacity of each
 };
@@ -239,6 +241,10 @@ static int tc_pipeline(Scratch* s, const SearchArgs& a, int mode, FilterSide* si
   int ctas_per_pass = s->sm_count / side_by;
   if (ctas_per_pass > tiles_cap) ctas_per_pass = tiles_cap;
   if (ctas_per_pass < 1) ctas_per_pass = 1;
+  // Long scans whose candidates refine would otherwise pick out of the per-CTA lists: no lists at all, survivors go
+  // straight to the flat candidate array (scan_tc.cu emit_epilogue).  Needs the threshold exchange (>= top_k CTAs).
+  const bool emit = side != nullptr && side->ocand != nullptr && !oneshot && !need && !side->merge &&
+                    ctas_per_pass >= a.top_k && tiles >= s->sm_count && !(a.flags & (DEVQA_DEBUG_FILTER_ONLY | DEVQA_DEBUG_NO_EMIT));
   if (oneshot) {                                             // one CTA per tile; as many passes per launch as fit
     ctas_per_pass = int(tiles);
     side_by = s->sm_count / ctas_per_pass;
@@ -257,7 +263,10 @@ static int tc_pipeline(Scratch* s, const SearchArgs& a, int mode, FilterSide* si
     p.qerr = side->qerr; p.k_true = a.top_k; p.lostu = side->lostu; p.bank_max_sumsq = a.max_sumsq;
     side->n_lists = grid;
     side->oneshot = oneshot;
+    side->emit = emit;
+    side->ocap = oneshot ? kOneshotCap : kEmitCap;
     if (oneshot) { p.oneshot = 1; p.gbar = side->gbar; p.ocount = side->ocount; p.ocand = side->ocand; p.ocap = kOneshotCap; }
+    if (emit) { p.emit = 1; p.ocount = side->ocount; p.ocand = side->ocand; p.ocap = kEmitCap; }   // [grid][Q] / [grid][Q][cap]
   }
   p.gmax = gmax; p.gmax_stride = kGmaxStride;
   DEVQA_REQUIRE(grid <= kGmaxStride, "more CTAs per pass than the threshold exchange holds");
@@ -306,7 +315,7 @@ static int tc_pipeline(Scratch* s, const SearchArgs& a, int mode, FilterSide* si
   }
   if (side) {
     side->kcap = kcap;
-    if (!side->merge || oneshot) return DEVQA_OK;
+    if (!side->merge || oneshot || emit) return DEVQA_OK;
     return merge_lists_launch(s->cand, grid, a.n_queries, kcap, kcap, side->kp, side->akeys, nullptr, nullptr, stream);
   }
   return merge_lists_launch(s->cand, grid, a.n_queries, kcap, kcap, a.top_k, out_keys, out_scores, out_ids, stream, nullptr, need);
@@ -423,7 +432,9 @@ static int run_search(Scratch* s, const SearchArgs& a, uint64_t* out_keys, float
       const size_t nq = size_t(ac.n_queries), nq_pad = (nq + 255) / 256 * 256;   // >= q_pad of any plan
       if ((rc = grow(reinterpret_cast<void**>(&s->akeys), &s->akeys_bytes,
                      nq * kp * 8 + nq * 12 + nq_pad * 4 + size_t(s->sm_count) * nq * 4 + nq_pad * kGmaxStride * 4 +
-                         (128 + nq_pad) * 4 + 8 + nq * kOneshotCap * 8, false)))
+                         (128 + size_t(s->sm_count) * nq_pad) * 4 + 8 +
+                         nq * (size_t(kOneshotCap) > size_t(s->sm_count) * kEmitCap ? size_t(kOneshotCap) : size_t(s->sm_count) * kEmitCap) * 8,
+                     false)))
         return rc;
       FilterSide side;
       side.kp = kp;
@@ -436,7 +447,7 @@ static int run_search(Scratch* s, const SearchArgs& a, uint64_t* out_keys, float
       side.gmax = side.lostu + size_t(s->sm_count) * nq;
       side.gbar = side.gmax + nq_pad * kGmaxStride;                     // [128] counters, then [nq] candidate counts,
       side.ocount = side.gbar + 128;                                    // zeroed as ONE region by the prep kernel
-      side.ocand = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(side.ocount + nq_pad) + 7) & ~uintptr_t(7));
+      side.ocand = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(side.ocount + size_t(s->sm_count) * nq_pad) + 7) & ~uintptr_t(7));
       // With at least top_k CTAs per pass the scan's CTAs exchange their bests, and refine can pick the candidates
       // straight out of the per-CTA lists (one kernel instead of merge + refine).
       const int64_t tiles = (a.n_rows + 127) / 128;
@@ -459,7 +470,8 @@ static int run_search(Scratch* s, const SearchArgs& a, uint64_t* out_keys, float
       rp.need = side.need; rp.fallbacks = s->fallbacks; rp.violations = s->violations; rp.out_keys = ok; rp.out_scores = os; rp.out_ids = oi;
       rp.cand = s->cand; rp.cand_kcap = side.kcap; rp.gmax = side.gmax; rp.gmax_stride = kGmaxStride;
       rp.qerr = side.qerr; rp.bank_max_sumsq = a.max_sumsq;
-      if (side.oneshot) { rp.dcount = side.ocount; rp.dcand = side.ocand; rp.dcap = kOneshotCap; }
+      if (side.oneshot) { rp.dcount = side.ocount; rp.dcand = side.ocand; rp.dcap = side.ocap; }
+      if (side.emit) { rp.cand = side.ocand; rp.cand_kcap = kEmitCap; rp.cand_count = side.ocount; }   // per-CTA regions
       if ((rc = (side.merge && !side.oneshot) ? refine_launch(rp, stream) : refine_lists_launch(rp, stream))) return rc;
       // queries for which a lost row could still matter are redone exactly; for all others these launches
       // exit at once (the flags live on the device: no host round trip, graph-capturable).  The fallback's top-k

@@ -186,7 +186,7 @@ __global__ void __launch_bounds__(kRefineListThreads) refine_lists_kernel(const 
   static_assert(kWide == kRefineListThreads, "one key per thread in the second cut");
   __shared__ uint64_t ex[kListKp];
   __shared__ uint64_t ak[kWide];
-  __shared__ uint32_t s_count, s_lost, s_tcode, s_viol;
+  __shared__ uint32_t s_count, s_lost, s_tcode, s_viol, s_over;
   constexpr int CH = VEC ? (sizeof(T) == 2 ? 256 : 128) : 32;
   const int dim = int(p.dim);
   const int dpad = (dim + CH - 1) / CH * CH;
@@ -200,12 +200,10 @@ __global__ void __launch_bounds__(kRefineListThreads) refine_lists_kernel(const 
   const float inv = p.qinv[q];
   for (int c = threadIdx.x; c < dpad; c += kRefineListThreads) sq[c] = c < dim ? src[c] * inv : 0.f;
   for (int c = threadIdx.x; c < kListKp; c += kRefineListThreads) ex[c] = kEmptyKey;
-  if (threadIdx.x == 0) { s_count = 0u; s_lost = 0u; s_tcode = 0u; s_viol = 0u; }
-  const bool direct = p.dcount != nullptr;                             // one-shot scan: candidates are one array already
-  // ---- T from the CTAs' bests (warp 0), lost-row bounds (warp 1) ----
-  if (direct) {
-    // nothing to derive: the scan emitted every row with u >= T itself, and lost none
-  } else if (warp == 0) {
+  if (threadIdx.x == 0) { s_count = 0u; s_lost = 0u; s_tcode = 0u; s_viol = 0u; s_over = 0u; }
+  const bool direct = p.dcount != nullptr;                             // one-shot / emit scans: candidates are one flat array
+  // ---- T from the CTAs' bests (warp 0), lost-row bounds (warp 1; direct mode: the scan lost nothing) ----
+  if (warp == 0 && p.gmax != nullptr && p.n_lists >= p.top_k) {
     const uint32_t* g = p.gmax + size_t(q) * p.gmax_stride;
     uint32_t v[5];
 #pragma unroll
@@ -225,7 +223,7 @@ __global__ void __launch_bounds__(kRefineListThreads) refine_lists_kernel(const 
       const float t = code_score(x) - 2.0001f * p.qerr[q] * maxn;
       if (t == t) s_tcode = score_code(t);                              // NaN: no usable bound, keep everything
     }
-  } else if (warp == 1) {
+  } else if (warp == 1 && !direct) {
     uint32_t lost = 0u;
     for (int g = lane; g < p.n_lists; g += 32) {
       const uint32_t code = p.lostu[size_t(g) * p.n_queries + q];
@@ -239,17 +237,44 @@ __global__ void __launch_bounds__(kRefineListThreads) refine_lists_kernel(const 
   const uint32_t tcode = s_tcode;
   const int total = direct ? 0 : p.n_lists * p.cand_kcap;
   if (direct) {
+    // the flat array holds every row that beat the threshold of ITS moment; only those at or above the final T matter
     const uint32_t cnt = p.dcount[q];
     const uint32_t have = cnt < uint32_t(p.dcap) ? cnt : uint32_t(p.dcap);
-    for (uint32_t i = threadIdx.x; i < have && i < uint32_t(kWide); i += kRefineListThreads) ak[i] = p.dcand[size_t(q) * p.dcap + i];
-    if (threadIdx.x == 0) s_count = cnt > uint32_t(p.dcap) ? uint32_t(kWide) + 1u : have;   // overflow: candidates are missing
+    for (uint32_t i = threadIdx.x; i < have; i += kRefineListThreads) {
+      const uint64_t key = p.dcand[size_t(q) * p.dcap + i];
+      if (uint32_t(key >> 32) >= tcode) {
+        const uint32_t slot = atomicAdd(&s_count, 1u);
+        if (slot < uint32_t(kWide)) ak[slot] = key;
+      }
+    }
+    if (cnt > uint32_t(p.dcap) && threadIdx.x == 0) s_over = 1u;       // overflow: candidates are missing
   }
-  for (int i = threadIdx.x; i < total; i += kRefineListThreads) {
-    const int g = i / p.cand_kcap, e = i - g * p.cand_kcap;
-    const uint64_t key = p.cand[(size_t(g) * p.n_queries + q) * p.cand_kcap + e];
-    if (key != kEmptyKey && uint32_t(key >> 32) >= tcode) {
-      const uint32_t slot = atomicAdd(&s_count, 1u);
-      if (slot < uint32_t(kWide)) ak[slot] = key;
+  if (!direct && p.cand_count) {
+    // emit mode: per-CTA regions filled from the front, counts beside them.  A warp takes every 16th region; its
+    // counts are requested together, then one (rarely two) coalesced reads per region.
+    constexpr int kW = kRefineListThreads / 32;
+    const int gi = warp + lane * kW;                                    // lane i holds the count of region warp + 16 i
+    const uint32_t my_cnt = (lane < (160 + kW - 1) / kW && gi < p.n_lists) ? p.cand_count[size_t(gi) * p.n_queries + q] : 0u;
+    for (int i = 0; warp + i * kW < p.n_lists; ++i) {
+      const int g = warp + i * kW;
+      const uint32_t cnt = __shfl_sync(kFull, my_cnt, i);
+      const uint64_t* base = p.cand + (size_t(g) * p.n_queries + q) * p.cand_kcap;
+      for (uint32_t e = lane; e < cnt; e += 32) {
+        const uint64_t key = base[e];
+        if (key != kEmptyKey && uint32_t(key >> 32) >= tcode) {
+          const uint32_t slot = atomicAdd(&s_count, 1u);
+          if (slot < uint32_t(kWide)) ak[slot] = key;
+        }
+      }
+    }
+  } else {
+    for (int i = threadIdx.x; i < total; i += kRefineListThreads) {
+      const int g = i / p.cand_kcap, e = i - g * p.cand_kcap;
+      const uint64_t key = p.cand[(size_t(g) * p.n_queries + q) * p.cand_kcap + e];
+      if (key != kEmptyKey && uint32_t(key >> 32) >= tcode) {
+        const uint32_t slot = atomicAdd(&s_count, 1u);
+        if (slot < uint32_t(kWide)) ak[slot] = key;
+      }
     }
   }
   __syncthreads();
@@ -309,7 +334,7 @@ __global__ void __launch_bounds__(kRefineListThreads) refine_lists_kernel(const 
   rank_sort(ex, srt, n_sort);
   if (threadIdx.x == 0) {
     const uint64_t kth = srt[p.top_k - 1];
-    bool complete = n_raw <= uint32_t(kListKp);                        // otherwise candidates were cut off
+    bool complete = n_raw <= uint32_t(kListKp) && s_over == 0u;        // otherwise candidates were cut off
     const uint32_t lost = s_lost;
     if (complete && lost != 0u)
       complete = kth != kEmptyKey && code_score(lost) < key_score(kth);   // false for NaN on either side
@@ -347,7 +372,7 @@ static size_t refine_query_smem(const RefineParams& p, bool vec) {
 
 int refine_lists_launch(const RefineParams& p, cudaStream_t stream) {
   if (p.n_queries == 0) return DEVQA_OK;
-  if (p.dcount) DEVQA_REQUIRE(p.top_k <= 64 && p.dcap <= 512 && p.dcand, "refine: unsupported direct candidate geometry");
+  if (p.dcount) DEVQA_REQUIRE(p.top_k <= 64 && p.dcand && p.n_lists <= 160, "refine: unsupported direct candidate geometry");
   else DEVQA_REQUIRE(p.top_k <= 64 && p.n_lists <= 160 && p.n_lists >= p.top_k, "refine: unsupported list geometry");
   const bool vec = refine_vectorised(p);
   const size_t smem = refine_query_smem(p, vec);

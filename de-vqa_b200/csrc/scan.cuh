@@ -43,6 +43,7 @@ struct ScanParams {
   int32_t gmax_stride;
   // tcgen05 filter, one-shot mode (every CTA owns one tile; scan_tc.cu oneshot_epilogue)
   int32_t oneshot;
+  int32_t emit;            // long scans: candidates to ocand instead of per-CTA lists (scan_tc.cu emit_epilogue)
   uint32_t* gbar;          // [2 * passes] zeroed arrival counters
   uint32_t* ocount;        // [n_queries] zeroed candidate counts
   uint64_t* ocand;         // [n_queries, ocap] candidates
@@ -88,6 +89,8 @@ bool scan_tc_supported(int bank_dtype, const void* bank, int64_t dim, int64_t ba
 int scan_tc_plan(int mode, int n_queries, int64_t dim, int kcap, bool cached_norms, int64_t n_tiles, int sm_count,
                  unsigned flags, int* qp_out, int* stages_out, bool* pair_out, bool oneshot = false);
 constexpr int kOneshotCap = 512;       // candidates per query the one-shot scan can emit (refine's first-cut capacity)
+constexpr int kEmitCap = 128;          // candidates per (CTA, query) a long scan can emit (everything that ever beat the running
+                                       // threshold: ~1500 per query over 148 CTAs with the bf16 shadow at top_k = 32)
 size_t scan_tc_qcat_bytes(int mode, int64_t dim, int q_pad);
 bool scan_tc_exchanges_thresholds(int mode, int64_t dim);   // scan-and-queue epilogue + gmax exchange (else: seeded score-tile epilogue)
 // queries -> normalised, split (hi/lo TF32; hi/mid/lo bf16; hi TF32 only for the filter), laid out per pass as the
@@ -115,6 +118,8 @@ struct RefineParams {
   // refine_lists_launch only: the per-CTA lists themselves and what the CTAs exchanged
   const uint64_t* cand;       // [n_lists, n_queries, cand_kcap]
   int32_t cand_kcap;
+  const uint32_t* cand_count; // optional [n_lists, n_queries]: valid entries per list (emit mode: lists are unsorted
+                              // regions filled from the front); nullptr: sorted lists, empty slots are 0
   const uint32_t* gmax;       // [n_queries (padded), gmax_stride] each CTA's best upper bound per query (score codes)
   int32_t gmax_stride;
   const float* qerr;          // [n_queries] tc_filter_relerr(dim) * ||query as used||

@@ -331,6 +331,7 @@ struct TcParams {
   uint32_t* gthr;          // [n_queries] shared lower bounds of the k-th score (monotone score codes, 0 = none)
   // one-shot mode (short scans: every CTA owns exactly ONE tile, all CTAs co-resident): see oneshot_epilogue
   int32_t oneshot;
+  int32_t emit;            // long scans: survivors appended to ocand instead of per-CTA lists (emit_epilogue)
   uint32_t* gbar;          // [2 * passes of the call] zeroed arrival counters: bests published / thresholds published
   uint32_t* ocount;        // [n_queries] zeroed: candidates emitted per query
   uint64_t* ocand;         // [n_queries, ocap] candidate keys (on the upper bound u), unordered
@@ -485,9 +486,20 @@ __device__ __forceinline__ void filt_epilogue(const TcParams& p, const FiltState
     for (int j = e * 32 + lane; j < QP; j += 128) best_s[j] = 0u;
     epilogue_barrier();
   }
+  // cached row norms: the NEXT tile's value is requested a whole tile ahead (a global load per tile at the point of
+  // use cost ~800 cycles of every 7000-cycle tile period on the shadow path)
+  const bool cached = !norm_warps && (!dot_mode || PARTS == 1);
+  auto tile_of = [&](int it) { return tile0 + (it < n_my ? it : it - n_my) * tile_step; };
+  auto ssq_of = [&](int it) {
+    const int64_t g = int64_t(tile_of(it)) * kTileRows + row_in_tile;
+    return (cached && it < n_my + boot && g < p.n_rows) ? __ldg(p.row_sumsq + g) : 1.f;
+  };
+  float ssq_next = ssq_of(0);
   for (int it = 0; it < n_my + boot; ++it, ++lt, ++unit) {
-    const int tile = tile0 + (it < n_my ? it : it - n_my) * tile_step;
+    const int tile = tile_of(it);
     const int a = unit & 1;
+    const float ssq_cached = ssq_next;
+    ssq_next = ssq_of(it + 1);
     mbar_wait(&tmem_full[a], (unit >> 1) & 1);
     tc_fence_after();
     if (e == 0 && lane == 0) trace_at(p, 6, unit);
@@ -495,7 +507,7 @@ __device__ __forceinline__ void filt_epilogue(const TcParams& p, const FiltState
     const bool row_live = grow < p.n_rows && !no_insert;
     float inv = 1.f, rowfac = 1.f;
     if (!dot_mode || PARTS == 1) {
-      const float ssq = norm_warps ? norms[(lt % kNormRing) * kTileRows + row_in_tile] : (grow < p.n_rows ? p.row_sumsq[grow] : 1.f);
+      const float ssq = norm_warps ? norms[(lt % kNormRing) * kTileRows + row_in_tile] : ssq_cached;
       const float nrm = sqrtf(ssq);
       if (dot_mode) rowfac = nrm;
       else inv = 1.0f / ((p.flags & DEVQA_NOEPS) ? nrm : fmaxf(nrm, kNormEps));
@@ -561,10 +573,8 @@ __device__ __forceinline__ void filt_epilogue(const TcParams& p, const FiltState
     for (int jb = 0; jb < QP; jb += seg, ++seg_idx) {
       uint32_t* const qn = st.qn + (seg_idx & 1);
       // ---- scan ----
-#pragma unroll 1
-      for (int c = jb; c < jb + seg; c += 16) {
-        float u[16];
-        load_u(c, u);
+      // 16 scores of this row against their thresholds; the few survivors go to the hit queue (or, dense: all 16 to the tile)
+      auto consume = [&](int c, const float (&u)[16]) {
         uint32_t mask = 0;
 #pragma unroll
         for (int i4 = 0; i4 < 4; ++i4) {
@@ -586,6 +596,44 @@ __device__ __forceinline__ void filt_epilogue(const TcParams& p, const FiltState
               if (idx < uint32_t(hit_cap(QP))) { st.hit_u[idx] = u[i]; st.hit_id[idx] = (uint32_t(c + i) << 8) | uint32_t(row_in_tile); }
             }
           }
+        }
+      };
+      if constexpr (PARTS == 1) {
+        // filter variants: the tensor-memory load of the NEXT 16 accumulators is in flight while these 16 are compared
+        // (tcgen05.wait::ld waits for everything outstanding, so: wait, issue the next, then work on the current)
+        auto to_u = [&](int c, const uint32_t (&d)[16], float (&u)[16]) {
+#pragma unroll
+          for (int i4 = 0; i4 < 4; ++i4) {
+            const float4 eq4 = *reinterpret_cast<const float4*>(st.eq + c + 4 * i4);
+            u[4 * i4 + 0] = fmaf(__uint_as_float(d[4 * i4 + 0]), inv, eq4.x * rowfac);
+            u[4 * i4 + 1] = fmaf(__uint_as_float(d[4 * i4 + 1]), inv, eq4.y * rowfac);
+            u[4 * i4 + 2] = fmaf(__uint_as_float(d[4 * i4 + 2]), inv, eq4.z * rowfac);
+            u[4 * i4 + 3] = fmaf(__uint_as_float(d[4 * i4 + 3]), inv, eq4.w * rowfac);
+          }
+        };
+        uint32_t da[16], db[16];
+        const int c_end = jb + seg;
+        tmem_ld<16>(taddr + uint32_t(jb), da);
+#pragma unroll 1
+        for (int c = jb; c < c_end; c += 32) {
+          float u[16];
+          tmem_ld_wait();
+          if (c + 16 < c_end) tmem_ld<16>(taddr + uint32_t(c + 16), db);
+          to_u(c, da, u);
+          consume(c, u);
+          if (c + 16 < c_end) {
+            tmem_ld_wait();
+            if (c + 32 < c_end) tmem_ld<16>(taddr + uint32_t(c + 32), da);
+            to_u(c + 16, db, u);
+            consume(c + 16, u);
+          }
+        }
+      } else {
+#pragma unroll 1
+        for (int c = jb; c < jb + seg; c += 16) {
+          float u[16];
+          load_u(c, u);
+          consume(c, u);
         }
       }
       const bool last_seg = jb + seg >= QP;
@@ -628,34 +676,61 @@ __device__ __forceinline__ void filt_epilogue(const TcParams& p, const FiltState
         }
       } else {
         // ---- drain: warp e owns the queries with q % 4 == e ----
-        for (uint32_t h = 0; h < n; ++h) {
-          const uint32_t id = st.hit_id[h];
-          const int j = int(id >> 8);
-          if ((j & 3) != e) continue;                                   // warp-uniform
-          const float uu = st.hit_u[h];
-          if (uu < st.thr[j]) continue;                                 // the threshold has risen since the push
-          ++slow_calls;
-          const uint64_t key = pack_key(uu, uint32_t(p.idmap(int64_t(tile) * kTileRows + int64_t(id & 0xffu))));
-          uint64_t* list = lists + size_t(j) * p.kcap;
-          uint64_t best, kth, ktrue;
-          if (p.kcap == 32) {
-            uint64_t mine = list[lane];
-            const int pos = __popc(__ballot_sync(kFull, mine > key));
-            const uint64_t up = shfl_u64(mine, lane > 0 ? lane - 1 : 0);
-            if (pos < p.top_k) mine = lane > pos ? up : (lane == pos ? key : mine);
-            list[lane] = mine;
-            best = shfl_u64(mine, 0);
-            kth = shfl_u64(mine, p.top_k - 1);
-            ktrue = shfl_u64(mine, p.k_true - 1);
-          } else {
-            warp_list_insert(list, p.kcap, p.top_k, key, lane);
+        // The queue is read 32 hits at a time, ONE load per lane; the warp then walks its own hits through shuffles
+        // and has every shared-memory word an insertion needs (the list, the threshold, the error scale) in flight
+        // together.  The previous form chained six dependent shared-memory round trips per hit on a pipe that TMA and
+        // UMMA keep ~90% busy -- ~1000 cycles per insertion, and with the bf16 shadow (tile period 7 k cycles instead
+        // of 14 k) the epilogue, not HBM, set the pace.
+        for (uint32_t h0 = 0; h0 < n; h0 += 32) {
+          const uint32_t h = h0 + uint32_t(lane);
+          uint32_t my_id = 0u;
+          float my_u = 0.f;
+          if (h < n) { my_id = st.hit_id[h]; my_u = st.hit_u[h]; }
+          unsigned todo = __ballot_sync(kFull, h < n && (int(my_id >> 8) & 3) == e);
+          while (todo) {                                                // warp-uniform
+            const int srcl = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const uint32_t id = __shfl_sync(kFull, my_id, srcl);
+            const float uu = __shfl_sync(kFull, my_u, srcl);
+            const int j = int(id >> 8);
+            uint64_t* list = lists + size_t(j) * p.kcap;
+            const float th_now = st.thr[j];                             // (three independent loads)
+            const float eq_j = st.eq[j];
+            uint64_t mine = p.kcap == 32 ? list[lane] : 0ull;
+            if (uu < th_now) continue;                                  // the threshold has risen since the push
+            ++slow_calls;
+            const uint64_t key = pack_key(uu, uint32_t(p.idmap(int64_t(tile) * kTileRows + int64_t(id & 0xffu))));
+            uint64_t best, kth, ktrue;
+            if (p.kcap == 32) {
+              const int pos = __popc(__ballot_sync(kFull, mine > key));
+              const uint64_t up = shfl_u64(mine, lane > 0 ? lane - 1 : 0);
+              if (pos < p.top_k) mine = lane > pos ? up : (lane == pos ? key : mine);
+              list[lane] = mine;
+              best = shfl_u64(mine, 0);
+              kth = shfl_u64(mine, p.top_k - 1);
+              ktrue = shfl_u64(mine, p.k_true - 1);
+            } else {
+              warp_list_insert(list, p.kcap, p.top_k, key, lane);
+              __syncwarp();
+              best = list[0];
+              kth = list[p.top_k - 1];
+              ktrue = list[p.k_true - 1];
+            }
+            if (lane == 0) {                                            // filt_after_insert, on values already in registers
+              float th = th_now;
+              if (ktrue != kEmptyKey) {
+                const float t = key_score(ktrue) - 2.f * eq_j * maxn;
+                if (t > th) th = t;
+              }
+              if (kth != kEmptyKey) {
+                const float l = key_score(kth);
+                if (l >= th) { th = l; st.lost[j] = l; }
+              }
+              st.thr[j] = th;
+              if (p.gmax) p.gmax[size_t(q0 + j) * p.gmax_stride + tile0] = uint32_t(best >> 32);   // single writer per slot
+            }
             __syncwarp();
-            best = list[0];
-            kth = list[p.top_k - 1];
-            ktrue = list[p.k_true - 1];
           }
-          if (lane == 0) filt_after_insert(p, st, j, q0, tile0, maxn, best, ktrue, kth);
-          __syncwarp();
         }
       }
       // ---- pick up the service warps' bounds (own queries only: nobody else writes thr) ----
@@ -746,7 +821,168 @@ __device__ __forceinline__ void filt_service(const TcParams& p, const FiltState 
       }
     }
     for (unsigned slept = 0; slept < pause_ns && !*done; slept += 1000) __nanosleep(pause_ns < 1000 ? pause_ns : 1000);
-    if (pause_ns < 64000) pause_ns *= 2;
+    // back off only once thresholds exist: the epilogue's first tile WAITS for them (a service warp that had already
+    // grown its pause to 8-16 us while the first tile was still being multiplied cost ~20 us per scan)
+    bool have = true;
+    for (int j = lane; j < nq_pass; j += 32) have = have && thr_ext[j] != -INFINITY;
+    if (__all_sync(kFull, have) && pause_ns < 64000) pause_ns *= 2;
+  }
+}
+
+// ---- emit mode: long scans on the filter path without per-CTA lists ----------------------------------------------------
+// The list epilogue inserts every row that beats the running threshold into a sorted per-CTA list (~900 cycles per
+// insertion on a shared-memory pipe that TMA and UMMA keep busy).  The number of such rows is set by the filter's error
+// band: ~200 per query and scan with the TF32 filter, ~1500 with the bf16 shadow (band 2E = 0.43 sigma of the score
+// distribution) -- there the epilogue, not HBM, set the tile period (traced: 7.1 k cycles of epilogue per 7.9 k-cycle
+// tile; the first eight tiles 17 k each).  But nothing downstream needs the lists SORTED: refine.cu only wants every
+// row with u >= T.  So, like the one-shot mode's pass B, a thread that finds a survivor appends it to a flat per-query
+// candidate array in global memory (one atomicAdd + one store, no queue, no drain, no CTA barrier per tile) and
+// raises the CTA's best-u word for the threshold exchange.  Thresholds come only from the exchange (service warp); the
+// first tile's accumulators stay in tensor memory while the CTA waits for the first thresholds and are then scanned
+// like any other tile (no second visit).  Nothing is ever pushed out of a list, so there are no lost-row bounds;
+// a candidate array that overflows flags its query for the exact fallback (refine.cu).
+template <int QP>
+__device__ __forceinline__ void emit_epilogue(const TcParams& p, const FiltState st, const float* norms, bool norm_warps,
+                                              uint32_t tmem_base, uint64_t* tmem_full, uint64_t* tmem_empty, int tile0,
+                                              int tile_step, int n_my, int q0, int nq_pass, int e, int lane,
+                                              uint32_t tmem_empty_remote = 0u) {
+  auto release_tmem = [&](int a) {
+    if (tmem_empty_remote) mbar_arrive_cluster(tmem_empty_remote + uint32_t(a) * 8u);
+    else mbar_arrive(&tmem_empty[a]);
+  };
+  const int row_in_tile = e * 32 + lane;
+  const int tid = e * 32 + lane;
+  const bool dot_mode = !(p.flags & DEVQA_NORMALIZE_BANK);
+  uint32_t* const best_s = st.hit_id;                                  // [QP] best upper bound this CTA has emitted, per query
+  uint32_t* const pub_s = st.hit_id + QP;                              // [QP] what gmax holds
+  uint32_t* const cnt_s = st.hit_id + 2 * QP;                          // [QP] candidates this CTA has emitted, per query
+  for (int j = tid; j < QP; j += 128) { best_s[j] = 0u; pub_s[j] = 0u; cnt_s[j] = 0u; }
+  // this CTA's own region of the candidate array: [n_queries][ocap] -- private counters in shared memory, plain global
+  // stores, nothing to wait for (a global atomicAdd per survivor stalled the finding thread for a full round trip)
+  uint64_t* const my_cand = p.ocand + size_t(tile0) * p.n_queries * p.ocap;
+  epilogue_barrier();
+  auto ssq_of = [&](int it) {
+    const int64_t g = int64_t(tile0 + it * tile_step) * kTileRows + row_in_tile;
+    return (!norm_warps && it < n_my && g < p.n_rows) ? __ldg(p.row_sumsq + g) : 1.f;
+  };
+  float ssq_next = ssq_of(0);
+  for (int it = 0; it < n_my; ++it) {
+    const int tile = tile0 + it * tile_step;
+    const int a = it & 1;
+    const float ssq_cached = ssq_next;
+    ssq_next = ssq_of(it + 1);
+    mbar_wait(&tmem_full[a], (it >> 1) & 1);
+    tc_fence_after();
+    if (e == 0 && lane == 0) trace_at(p, 6, it);
+    const int64_t grow = int64_t(tile) * kTileRows + row_in_tile;
+    const bool row_live = grow < p.n_rows && !(p.flags & kDbgNoInsert);
+    float inv = 1.f, rowfac = 1.f;
+    {
+      const float ssq = norm_warps ? norms[(it % kNormRing) * kTileRows + row_in_tile] : ssq_cached;
+      const float nrm = sqrtf(ssq);
+      if (dot_mode) rowfac = nrm;
+      else inv = 1.0f / ((p.flags & DEVQA_NOEPS) ? nrm : fmaxf(nrm, kNormEps));
+    }
+    const uint32_t taddr = tmem_base + uint32_t(a) * QP + (uint32_t(e * 32) << 16);
+    auto to_u = [&](int c, const uint32_t (&d)[16], float (&u)[16]) {
+#pragma unroll
+      for (int i4 = 0; i4 < 4; ++i4) {
+        const float4 eq4 = *reinterpret_cast<const float4*>(st.eq + c + 4 * i4);
+        u[4 * i4 + 0] = fmaf(__uint_as_float(d[4 * i4 + 0]), inv, eq4.x * rowfac);
+        u[4 * i4 + 1] = fmaf(__uint_as_float(d[4 * i4 + 1]), inv, eq4.y * rowfac);
+        u[4 * i4 + 2] = fmaf(__uint_as_float(d[4 * i4 + 2]), inv, eq4.z * rowfac);
+        u[4 * i4 + 3] = fmaf(__uint_as_float(d[4 * i4 + 3]), inv, eq4.w * rowfac);
+      }
+    };
+    if (it == 0) {
+      // ---- first tile, pass A: each query's best upper bound -> exchange; then a bounded wait for the thresholds ----
+#pragma unroll 1
+      for (int c = 0; c < QP; c += 16) {
+        uint32_t d[16];
+        float u[16];
+        tmem_ld<16>(taddr + uint32_t(c), d);
+        tmem_ld_wait();
+        to_u(c, d, u);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const uint32_t m = __reduce_max_sync(kFull, row_live ? score_code(u[i]) : 0u);
+          if (lane == 0) atomicMax(best_s + c + i, m);
+        }
+      }
+      epilogue_barrier();
+      for (int j = tid; j < nq_pass; j += 128) {
+        const uint32_t b = best_s[j];
+        pub_s[j] = b;
+        p.gmax[size_t(q0 + j) * p.gmax_stride + tile0] = b;
+      }
+      for (int j = tid; j < nq_pass; j += 128) {
+        const long long t0 = clock64();                                // (no thresholds: every row would be a candidate)
+        while (*reinterpret_cast<volatile float*>(st.thr_ext + j) == -INFINITY && clock64() - t0 < 400000) __nanosleep(200);
+        st.thr[j] = fmaxf(st.thr[j], *reinterpret_cast<volatile float*>(st.thr_ext + j));
+      }
+      epilogue_barrier();
+    }
+    // ---- scan: 16 accumulators at a time, the next tensor-memory load in flight while these are compared ----
+    auto consume = [&](int c, const float (&u)[16]) {
+      uint32_t mask = 0;
+#pragma unroll
+      for (int i4 = 0; i4 < 4; ++i4) {
+        const float4 th4 = *reinterpret_cast<const float4*>(st.thr + c + 4 * i4);
+        mask |= (!(u[4 * i4 + 0] < th4.x) ? 1u : 0u) << (4 * i4 + 0);     // NaN passes, like torch.topk ranks it first
+        mask |= (!(u[4 * i4 + 1] < th4.y) ? 1u : 0u) << (4 * i4 + 1);
+        mask |= (!(u[4 * i4 + 2] < th4.z) ? 1u : 0u) << (4 * i4 + 2);
+        mask |= (!(u[4 * i4 + 3] < th4.w) ? 1u : 0u) << (4 * i4 + 3);
+      }
+      if (!row_live) mask = 0u;
+      if (mask != 0u) {                                                // rare
+        const uint32_t id = uint32_t(p.idmap(grow));
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          if ((mask >> i) & 1u) {
+            atomicMax(best_s + c + i, score_code(u[i]));
+            const uint32_t idx = atomicAdd(cnt_s + c + i, 1u);
+            if (idx < uint32_t(p.ocap)) my_cand[size_t(q0 + c + i) * p.ocap + idx] = pack_key(u[i], id);
+          }
+        }
+      }
+    };
+    {
+      uint32_t da[16], db[16];
+      tmem_ld<16>(taddr, da);
+#pragma unroll 1
+      for (int c = 0; c < QP; c += 32) {
+        float u[16];
+        tmem_ld_wait();
+        if (c + 16 < QP) tmem_ld<16>(taddr + uint32_t(c + 16), db);
+        to_u(c, da, u);
+        consume(c, u);
+        if (c + 16 < QP) {
+          tmem_ld_wait();
+          if (c + 32 < QP) tmem_ld<16>(taddr + uint32_t(c + 32), da);
+          to_u(c + 16, db, u);
+          consume(c + 16, u);
+        }
+      }
+    }
+    tc_fence_before();
+    release_tmem(a);                                                   // this thread's reads of the buffer are done
+    // ---- thresholds from the service warp; this CTA's bests to the exchange.  No barrier: thr only ever rises, and a
+    // reader that still sees the old word merely emits a candidate more ----
+    for (int j = tid; j < nq_pass; j += 128) {
+      st.thr[j] = fmaxf(st.thr[j], st.thr_ext[j]);
+      const uint32_t b = best_s[j];
+      if (b != pub_s[j]) { pub_s[j] = b; p.gmax[size_t(q0 + j) * p.gmax_stride + tile0] = b; }
+    }
+    if (e == 0 && lane == 0) trace_at(p, 7, it);
+  }
+  epilogue_barrier();
+  if (e == 0 && lane == 0) *reinterpret_cast<volatile uint32_t*>(st.qn + 2) = 1u;   // service warp: stop
+  for (int j = tid; j < nq_pass; j += 128) {
+    const uint32_t cnt = cnt_s[j];
+    p.ocount[size_t(tile0) * p.n_queries + q0 + j] = cnt < uint32_t(p.ocap) ? cnt : uint32_t(p.ocap);
+    // nothing is ever lost -- unless this CTA's region overflowed: then "anything may be missing" (NaN code: refine
+    // flags the query for the exact fallback)
+    p.lostu[size_t(tile0) * p.n_queries + q0 + j] = cnt > uint32_t(p.ocap) ? 0xffffffffu : 0u;
   }
 }
 
@@ -983,7 +1219,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap bank_map, const __grid_consta
   // (lists built from nothing, one insertion at a time).
   // (pairs: both CTAs run the leader's count; a missing last tile of the peer is all out-of-bounds rows)
   const int n_my = (p.n_tiles - (PAIR ? (tile0 & ~1) : tile0) + tile_step - 1) / tile_step;
-  const int boot = (SCANEPI && n_my >= 8 && tile_step >= p.k_true && p.gmax && !(p.flags & kDbgNoBoot)) ? 1 : 0;
+  const int boot = (SCANEPI && n_my >= 8 && tile_step >= p.k_true && p.gmax && !(p.flags & kDbgNoBoot) && !(FILT && p.emit)) ? 1 : 0;
   const int n_iter = n_my + boot;
   auto tile_at = [&](int it) { return tile0 + (it < n_my ? it : it - n_my) * tile_step; };
   const int set_kb = FILT ? nkb : kSetKBlocks;           // k-blocks accumulated inside the tensor core
@@ -1192,6 +1428,11 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap bank_map, const __grid_consta
     if constexpr (FILT)
       oneshot_epilogue<QP>(p, st, norms, norm_warps, tmem_base, tmem_full, tile0, tile_step, p.q0 / QP + pass_local, q0, nq_pass,
                            warp - 8, lane);
+  } else if (warp >= 8 && FILT && p.emit) {
+    // ===== epilogue warps, long scan without lists: survivors straight to the global candidate array =====
+    if constexpr (FILT)
+      emit_epilogue<QP>(p, st, norms, norm_warps, tmem_base, tmem_full, tmem_empty, tile0, tile_step, n_my, q0, nq_pass, warp - 8, lane,
+                        (PAIR && !leader) ? mapa_u32(smem_u32(&tmem_empty[0]), 0u) : 0u);
   } else if (warp >= 8 && SCANEPI) {
     // ===== epilogue warps: scan + hit queue (filt_epilogue) =====
     filt_epilogue<QP, FILT ? 1 : 3>(p, st, lists, norms, norm_warps, tmem_base, tmem_full, tmem_empty, tile0, tile_step, n_my, boot,
@@ -1316,7 +1557,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap bank_map, const __grid_consta
   // ---- teardown: candidates out, TMEM back ------------------------------------------------------
   tc_fence_before();
   __syncthreads();
-  for (int q = warp; q < nq_pass && !p.oneshot; q += kTcThreads / 32) {
+  for (int q = warp; q < nq_pass && !p.oneshot && !p.emit; q += kTcThreads / 32) {
     uint64_t* out = p.cand + (size_t(tile0) * p.n_queries + (q0 + q)) * p.kcap;
     const uint64_t* src = lists + size_t(q) * p.kcap;
     for (int i = lane; i < p.kcap; i += 32) out[i] = src[i];
@@ -1659,7 +1900,7 @@ int scan_tc_launch(const ScanParams& sp, int mode, const void* qcat, uint32_t* g
   p.top_k = sp.top_k; p.kcap = sp.kcap; p.stages = stages; p.passes = passes; p.flags = sp.flags;
   p.cand = sp.cand; p.gthr = gthr; p.idmap = sp.idmap; p.row_sumsq = sp.row_sumsq;
   p.need = sp.need;
-  p.oneshot = sp.oneshot; p.gbar = sp.gbar; p.ocount = sp.ocount; p.ocand = sp.ocand; p.ocap = sp.ocap;
+  p.oneshot = sp.oneshot; p.emit = sp.emit; p.gbar = sp.gbar; p.ocount = sp.ocount; p.ocand = sp.ocand; p.ocap = sp.ocap;
   p.gmax = sp.gmax; p.gmax_stride = sp.gmax_stride; p.lostu = sp.lostu; p.qerr = sp.qerr; p.seed_u = sp.seed_u; p.bank_max_sumsq = sp.bank_max_sumsq; p.k_true = sp.k_true > 0 ? sp.k_true : sp.top_k;
   // pass index = q0 / qp; one pass = n_kblocks * parts * qp rows of 128 bytes (32 words)
   p.qcat = static_cast<const float*>(qcat) + size_t(sp.q0 / qp) * size_t(n_kblocks) * parts * qp * 32;

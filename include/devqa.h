@@ -86,6 +86,8 @@ extern "C" {
                                               violated and the canary (devqa_filter_bound_violations) has to catch it */
 #define DEVQA_DEBUG_NO_ONESHOT (1u << 13)  /* tests/benchmarks: short scans through the persistent kernel's list epilogue
                                               instead of the one-shot mode (one tile per CTA, grid-wide threshold exchange) */
+#define DEVQA_DEBUG_NO_EMIT (1u << 3)      /* tests/benchmarks: long filter scans keep per-CTA sorted lists (the round-1 epilogue)
+                                              instead of appending survivors to the flat candidate array */
 #define DEVQA_DEBUG_FILTER_ONLY (1u << 22) /* tests: return the TF32 filter's approximate top-k as is (no exact
                                               re-scoring) so that its error bound can be checked            */
 

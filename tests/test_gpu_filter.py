@@ -333,17 +333,21 @@ def test_filter_midsize_banks_refine_from_the_per_cta_lists(n, d, nq, k):
 
 
 def test_duplicated_rows_midsize_take_the_exact_fallback():
+    """400 identical rows in a mid-size bank.  List epilogue (DEVQA_DEBUG_NO_EMIT): one CTA's list overflows with ties
+    -> flagged -> exact fallback.  Emit mode (default): all 400 ties are candidates and re-scored, no fallback."""
     bank = _randn(30000, 128, 61)
     bank[5000:5400] = bank[5000]
     q = torch.cat([bank[5000:5001] + 0.01 * _randn(1, 128, 62), _randn(31, 128, 63)])
     fb = FactBank.from_embeddings(bank)
     _fallbacks()
-    s, i = fb.search(q.cuda(), 32, flags=FILTER)
+    s, i = fb.search(q.cuda(), 32, flags=FILTER | L.DEBUG_NO_EMIT)
     assert _fallbacks() >= 1
     assert i[0].tolist() == list(range(5000, 5032))
     ss.compare_topk(s.cpu().numpy(), i.cpu().numpy(), ss.truth_scores_fp64(q, bank), 32, gap=GAP, rtol=RTOL, atol=ATOL)
     s2, i2 = fb.search(q.cuda(), 32, flags=L.FORCE_STREAM)
     assert torch.equal(i, i2) and torch.equal(s, s2)
+    s3, i3 = fb.search(q.cuda(), 32, flags=FILTER)
+    assert _fallbacks() == 0 and torch.equal(i3, i2) and torch.equal(s3, s2)
     fb.close()
 
 
@@ -610,4 +614,40 @@ def test_shadow_error_bound_on_the_constructed_worst_case(d):
     err = float(((exact - approx).abs() / scale).max())
     _record(f"shadow_worstcase_d{d}", {"max_err": err, "bound": rel, "fallbacks": nfb})
     assert 0.9 * 2.0 ** -7 < err < rel
+    fb.close()
+
+
+@pytest.mark.parametrize("n,d,nq,k,nb,shadow", [(40000, 768, 64, 32, "eps", True), (40000, 768, 64, 32, "eps", False),
+                                                (150000, 128, 300, 64, None, True), (19000, 384, 9, 5, "noeps", False),
+                                                (700000, 64, 1030, 16, "eps", True)])
+def test_emit_mode_equals_the_list_epilogue(n, d, nq, k, nb, shadow):
+    """Long filter scans append their survivors to a flat candidate array (emit mode) instead of keeping per-CTA
+    sorted lists: same results as the list epilogue (DEVQA_DEBUG_NO_EMIT) and as the stream kernel, bit for bit."""
+    bank, q = _randn(n, d, n + d, unit=False), _randn(nq, d, nq + d, unit=False)
+    fb = FactBank.from_embeddings(bank, shadow=shadow)
+    _fallbacks(); _violations()
+    a = fb.search(q.cuda(), k, normalize_bank=nb, normalize_query=nb, flags=L.FORCE_TENSOR)
+    nfb, nv = _fallbacks(), _violations()
+    b = fb.search(q.cuda(), k, normalize_bank=nb, normalize_query=nb, flags=L.FORCE_TENSOR | L.DEBUG_NO_EMIT)
+    _fallbacks()
+    c = fb.search(q[:8].cuda(), k, normalize_bank=nb, normalize_query=nb, flags=L.FORCE_STREAM)
+    assert nv == 0 and nfb <= max(1, nq // 16), (nfb, nv)
+    assert torch.equal(a[1], b[1]) and torch.equal(a[0], b[0])
+    assert torch.equal(a[1][:8], c[1]) and torch.equal(a[0][:8], c[0])
+    fb.close()
+
+
+def test_emit_mode_overflow_takes_the_fallback():
+    """20000 identical rows: every one of them beats any threshold, the candidate array (8192 per query) overflows,
+    the query is flagged and the exact pipeline answers it -- ties in ascending id order."""
+    bank = _randn(60000, 64, 5)
+    bank[10000:30000] = bank[10000]
+    q = torch.cat([bank[10000:10001], _randn(7, 64, 6)])
+    fb = FactBank.from_embeddings(bank)
+    _fallbacks()
+    s, i = fb.search(q.cuda(), 16, flags=L.FORCE_TENSOR)
+    assert _fallbacks() >= 1
+    assert i[0].tolist() == list(range(10000, 10016))
+    s2, i2 = fb.search(q.cuda(), 16, flags=L.FORCE_STREAM)
+    assert torch.equal(i, i2) and torch.equal(s, s2)
     fb.close()

@@ -5,7 +5,8 @@ import torch, devqa_b200
 L = devqa_b200._lib
 rows, q, flags = int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3]) if len(sys.argv) > 3 else 0
 dtype = sys.argv[4] if len(sys.argv) > 4 else "fp32"
-fb = devqa_b200.FactBank(768, capacity=rows, dtype=dtype)
+shadow = dtype == "shadow"
+fb = devqa_b200.FactBank(768, capacity=rows, dtype="fp32" if shadow else dtype, shadow=shadow)
 fb.append_synthetic(rows, 1)
 qs = torch.nn.functional.normalize(torch.randn(q, 768), dim=1).cuda()
 for _ in range(2):
