@@ -11,6 +11,6 @@ for r in d.get("regimes", []): print("   ", r["queries_per_call"], round(r["ms_p
 PY
 }
 run driver "DEVQA_P2P=1" "--steps 20 --warmup 5"
-run p2p "DEVQA_P2P=1" "--steps 200 --warmup 5 --no-regimes"
+run s200 "DEVQA_P2P=1" "--steps 200 --warmup 5 --no-regimes"
 run nccl "DEVQA_P2P=0" "--steps 200 --warmup 5 --no-regimes"
-run nopdl "DEVQA_P2P=1 DEVQA_PDL=0" "--steps 200 --warmup 5 --no-regimes"
+run noshadow "DEVQA_P2P=1" "--steps 20 --warmup 5 --no-shadow --no-regimes"
