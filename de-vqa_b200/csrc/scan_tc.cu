@@ -934,6 +934,8 @@ __device__ __forceinline__ void emit_epilogue(const TcParams& p, const FiltState
         mask |= (!(u[4 * i4 + 3] < th4.w) ? 1u : 0u) << (4 * i4 + 3);
       }
       if (!row_live) mask = 0u;
+      // (a NaN passes every comparison, also the +inf threshold of a padding query: those have no candidate region)
+      if (c + 16 > nq_pass) mask &= c < nq_pass ? (1u << (nq_pass - c)) - 1u : 0u;
       if (mask != 0u) {                                                // rare
         const uint32_t id = uint32_t(p.idmap(grow));
 #pragma unroll
@@ -1088,6 +1090,8 @@ __device__ __forceinline__ void oneshot_epilogue(const TcParams& p, const FiltSt
       mask |= (!(u[4 * i4 + 3] < th4.w) ? 1u : 0u) << (4 * i4 + 3);
     }
     if (!row_live) mask = 0u;
+    // (a NaN passes every comparison, also the +inf threshold of a padding query: those have no candidate array)
+    if (c + 16 > nq_pass) mask &= c < nq_pass ? (1u << (nq_pass - c)) - 1u : 0u;
     if (mask != 0u) {                                                  // rare
       const uint32_t id = uint32_t(p.idmap(grow));
 #pragma unroll

@@ -49,6 +49,13 @@ def _worker(rank, world, port, out_dir):
         small = FactBank.from_embeddings(rows, device=rank)
         ss_, si_ = small.search(q.cuda(), k)
         assert torch.equal(ci, si_) and torch.equal(cs, ss_)
+        # ---- sharded bank with a bf16 shadow: same results, bit for bit (the shards stream 2 bytes per element)
+        sbs = ShardedFactBank.synthetic(n, d, comm, seed=3234, shadow=True)
+        assert sbs.local.has_shadow
+        q40 = torch.nn.functional.normalize(torch.randn(40, d, generator=g), dim=1).cuda()
+        ss_, si_ = sbs.search(q40, k)
+        rs2, ri2 = full.search(q40, k)
+        assert torch.equal(si_, ri2) and torch.equal(ss_, rs2)
         # ---- the exchange: peer-to-peer mailboxes (default) vs ncclAllGather, bit for bit; batches beyond the mailbox
         # (Q > 512) take the NCCL path by themselves
         L = devqa_b200._lib

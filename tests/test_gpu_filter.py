@@ -651,3 +651,25 @@ def test_emit_mode_overflow_takes_the_fallback():
     s2, i2 = fb.search(q.cuda(), 16, flags=L.FORCE_STREAM)
     assert torch.equal(i, i2) and torch.equal(s, s2)
     fb.close()
+
+
+@pytest.mark.parametrize("shadow", [False, True])
+def test_emit_mode_with_nan_inf_and_zero_rows(shadow):
+    """Long scan (emit mode, with and without the bf16 shadow) over a bank with a zero row, NaN rows, an inf entry and
+    a row far beyond bf16's precision needs: NaN ranks first like torch.topk, everything else exact."""
+    bank = _randn(40000, 128, 91, unit=False)
+    bank[17] = 0
+    bank[99, 5] = float("nan")
+    bank[30000, 7] = float("nan")
+    bank[555] *= 1e30
+    bank[777] *= 1e-30
+    q = _randn(12, 128, 92, unit=False)
+    fb = FactBank.from_embeddings(bank, shadow=shadow)
+    for nb in ("eps", "noeps", None):
+        a = fb.search(q.cuda(), 8, normalize_bank=nb, normalize_query=nb, flags=L.FORCE_TENSOR)
+        b = fb.search(q.cuda(), 8, normalize_bank=nb, normalize_query=nb, flags=L.FORCE_STREAM)
+        assert torch.equal(a[1], b[1]), nb
+        assert torch.equal(torch.nan_to_num(a[0], nan=7.0), torch.nan_to_num(b[0], nan=7.0)), nb
+        nan_first = {99, 30000} | ({17} if nb == "noeps" else set())
+        assert set(a[1][0, :len(nan_first)].tolist()) == nan_first and bool(torch.isnan(a[0][:, 0]).all())
+    fb.close()
