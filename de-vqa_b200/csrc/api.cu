@@ -159,8 +159,10 @@ struct SearchArgs {
   const float* row_sumsq = nullptr;
   const uint32_t* max_sumsq = nullptr;   // library-owned banks: max ||row||^2 over every row ever appended (float bits)
   const uint64_t* below = nullptr;       // deep top-k passes: per-query exclusive upper bound key
-  const void* shadow = nullptr;          // fp32 library banks: optional bf16 copy of the rows (the filter scans IT)
+  const void* shadow = nullptr;          // fp32 library banks: optional scaled-fp16 copy of the rows (the filter scans IT)
   int64_t shadow_ld = 0;
+  const float* shadow_scale = nullptr;   // its per-row 2^-e
+  const float* row_scale = nullptr;      // (set on the args of the filter scan over the shadow)
 };
 
 static int validate(const SearchArgs& a) {
@@ -185,6 +187,7 @@ struct FilterSide {
   uint32_t* need = nullptr;      // [Q] set by refine: the exact fallback has to redo this query
   float* qinv = nullptr;         // [Q] scale applied by the query normalisation
   float* qerr = nullptr;         // [Q] tc_filter_relerr(dim) * ||query as used||
+  float* qscale = nullptr;       // [Q] fp16 shadow: 2^-f of each query's scaling
   uint32_t* seed_u = nullptr;    // [Q padded] k-th best upper bound of the prefix sample (score codes)
   uint32_t* lostu = nullptr;     // [grid, Q] per-CTA bound on the rows its full list lost
   uint32_t* gmax = nullptr;      // [Q padded, kGmaxStride] per-CTA best upper bound per query (threshold exchange)
@@ -258,6 +261,7 @@ static int tc_pipeline(Scratch* s, const SearchArgs& a, int mode, FilterSide* si
   p.n_rows = a.n_rows; p.dim = a.dim; p.bank_ld = a.bank_ld; p.bank = a.bank;
   p.queries = a.queries; p.query_ld = a.query_ld; p.n_queries = int32_t(a.n_queries);
   p.top_k = list_k; p.kcap = kcap; p.flags = a.flags; p.idmap = a.idmap; p.row_sumsq = a.row_sumsq;
+  p.row_scale = a.row_scale; p.qscale = (side && a.row_scale) ? side->qscale : nullptr;
   p.cand = s->cand; p.need = need;
   if (side) {
     p.qerr = side->qerr; p.k_true = a.top_k; p.lostu = side->lostu; p.bank_max_sumsq = a.max_sumsq;
@@ -276,7 +280,7 @@ static int tc_pipeline(Scratch* s, const SearchArgs& a, int mode, FilterSide* si
   if ((rc = scan_tc_prep_queries(mode, a.queries, a.query_ld, int(a.n_queries), qp, q_pad, a.dim, a.flags, s->qsplit, gthr,
                                  side ? side->qinv : nullptr, side ? side->qerr : nullptr, side ? side->seed_u : nullptr,
                                  gmax, kGmaxStride, need, stream, oneshot ? side->gbar : nullptr,
-                                 oneshot ? 128 + int(a.n_queries) : 0)))
+                                 oneshot ? 128 + int(a.n_queries) : 0, p.qscale ? side->qscale : nullptr)))
     return rc;
   // Threshold seeding: scan a prefix sample of the bank (one tile per CTA) first; the k-th best score of a
   // SUBSET is a lower bound of the k-th best of the whole bank, so the main scan starts with tight
@@ -371,9 +375,10 @@ static int run_search(Scratch* s, const SearchArgs& a, uint64_t* out_keys, float
                            (a.dtype == DEVQA_F32 ? ((a.flags & DEVQA_NORMALIZE_BANK) || (a.row_sumsq && a.max_sumsq))
                                                  : (a.row_sumsq != nullptr && a.max_sumsq != nullptr));
   // bf16 shadow: only where refine reads the per-CTA lists (its 512-candidate capacity takes the shadow's wide error band)
+  // (the scaled-fp16 accumulators are only understood by the emit-mode epilogue)
   const bool shadow_scan = filter_path && a.shadow != nullptr && a.dtype == DEVQA_F32 && a.top_k <= 64 &&
                            (a.n_rows + 127) / 128 >= s->sm_count && s->sm_count >= a.top_k &&
-                           !(a.flags & (DEVQA_DEBUG_FILTER_ONLY | DEVQA_NO_SHADOW));
+                           !(a.flags & (DEVQA_DEBUG_FILTER_ONLY | DEVQA_NO_SHADOW | DEVQA_DEBUG_NO_EMIT));
   if (tc_ok && filter_path) {
     const int64_t tiles = (a.n_rows + 127) / 128;
     // tiny banks (fewer tiles than SMs), up to 8 queries: ONE stream launch (~15 us) beats the seven-launch pipeline
@@ -431,7 +436,7 @@ static int run_search(Scratch* s, const SearchArgs& a, uint64_t* out_keys, float
       }
       const size_t nq = size_t(ac.n_queries), nq_pad = (nq + 255) / 256 * 256;   // >= q_pad of any plan
       if ((rc = grow(reinterpret_cast<void**>(&s->akeys), &s->akeys_bytes,
-                     nq * kp * 8 + nq * 12 + nq_pad * 4 + size_t(s->sm_count) * nq * 4 + nq_pad * kGmaxStride * 4 +
+                     nq * kp * 8 + nq * 16 + nq_pad * 4 + size_t(s->sm_count) * nq * 4 + nq_pad * kGmaxStride * 4 +
                          (128 + size_t(s->sm_count) * nq_pad) * 4 + 8 +
                          nq * (size_t(kOneshotCap) > size_t(s->sm_count) * kEmitCap ? size_t(kOneshotCap) : size_t(s->sm_count) * kEmitCap) * 8,
                      false)))
@@ -442,7 +447,8 @@ static int run_search(Scratch* s, const SearchArgs& a, uint64_t* out_keys, float
       side.need = reinterpret_cast<uint32_t*>(s->akeys + nq * kp);
       side.qinv = reinterpret_cast<float*>(side.need + nq);
       side.qerr = side.qinv + nq;
-      side.seed_u = reinterpret_cast<uint32_t*>(side.qerr + nq);
+      side.qscale = side.qerr + nq;
+      side.seed_u = reinterpret_cast<uint32_t*>(side.qscale + nq);
       side.lostu = side.seed_u + nq_pad;
       side.gmax = side.lostu + size_t(s->sm_count) * nq;
       side.gbar = side.gmax + nq_pad * kGmaxStride;                     // [128] counters, then [nq] candidate counts,
@@ -455,7 +461,10 @@ static int run_search(Scratch* s, const SearchArgs& a, uint64_t* out_keys, float
       side.merge = (a.flags & DEVQA_DEBUG_FILTER_ONLY) || tiles < s->sm_count || s->sm_count < a.top_k || a.top_k > 64;
       {
         SearchArgs as = ac;                                              // what the filter SCANS
-        if (shadow_scan) { as.bank = a.shadow; as.bank_ld = a.shadow_ld; as.dtype = DEVQA_BF16; as.flags |= kFlagShadowScan; }
+        if (shadow_scan) {
+          as.bank = a.shadow; as.bank_ld = a.shadow_ld; as.dtype = DEVQA_BF16 /* 2-byte rows */; as.flags |= kFlagShadowScan;
+          as.row_scale = a.shadow_scale;
+        }
         if ((rc = tc_pipeline(s, as, filt_mode, &side, nullptr, nullptr, nullptr, nullptr, stream))) return rc;
       }
       if (a.flags & DEVQA_DEBUG_FILTER_ONLY) {                           // tests: the filter's own upper bounds
@@ -549,6 +558,7 @@ struct devqa_bank {
   // element instead of 4, candidates are re-scored against the fp32 rows -- exact fp32 results from half the bytes.
   void* shadow = nullptr;
   devqa::VmmBuffer* shadow_vmm = nullptr;
+  float* shadow_scale = nullptr;   // per row: 2^-e of the power-of-two scaling its shadow row was stored with
   int64_t shadow_ld = 0, shadow_capacity = 0;
   float* sumsq = nullptr;          // cached ||row||^2 per stored row (bf16 banks: of the rounded row)
   uint32_t* max_sumsq = nullptr;   // device word: max of those over every row ever appended (float bits; never shrinks)
@@ -641,6 +651,20 @@ static int bank_grow(devqa_bank* b, int64_t want_rows, cudaStream_t stream) {
 static int shadow_grow(devqa_bank* b, int64_t cap, cudaStream_t stream) {
   if (!b->shadow_ld || cap <= b->shadow_capacity) return DEVQA_OK;
   const size_t bytes = size_t(cap) * b->shadow_ld * 2;
+  {                                                          // the per-row scales (4 bytes per row) are small enough to move
+    float* fresh_sc = nullptr;
+    cudaError_t e = cudaMalloc(&fresh_sc, size_t(cap) * 4);
+    if (e != cudaSuccess) {
+      set_error("cudaMalloc of %zu bytes for the shadow's row scales failed: %s", size_t(cap) * 4, cudaGetErrorString(e));
+      return DEVQA_E_NOMEM;
+    }
+    if (b->shadow_scale) {
+      if (b->size > 0) DEVQA_CUDA(cudaMemcpyAsync(fresh_sc, b->shadow_scale, size_t(b->size) * 4, cudaMemcpyDeviceToDevice, stream));
+      DEVQA_CUDA(cudaDeviceSynchronize());
+      DEVQA_CUDA(cudaFree(b->shadow_scale));
+    }
+    b->shadow_scale = fresh_sc;
+  }
   if (b->shadow_vmm) {
     bool moved = false;
     int rc = vmm_grow(b->shadow_vmm, bytes, &moved);
@@ -673,7 +697,7 @@ static int shadow_update(devqa_bank* b, int64_t first, int64_t n, cudaStream_t s
   if (rc) return rc;
   const float* src = static_cast<const float*>(b->data) + size_t(first) * b->ld;
   char* dst = static_cast<char*>(b->shadow) + size_t(first) * b->shadow_ld * 2;
-  return convert_rows_launch(src, b->ld, dst, DEVQA_BF16, b->shadow_ld, n, b->dim, stream);
+  return shadow_convert_launch(src, b->ld, dst, b->shadow_ld, b->shadow_scale + first, n, b->dim, stream);
 }
 
 static SearchArgs bank_args(const devqa_bank* b, const float* q, int64_t nq, int64_t qld, int k, unsigned flags) {
@@ -682,7 +706,7 @@ static SearchArgs bank_args(const devqa_bank* b, const float* q, int64_t nq, int
   a.queries = q; a.n_queries = nq; a.query_ld = qld; a.top_k = k; a.flags = flags; a.idmap = b->idmap;
   a.row_sumsq = b->sumsq;
   a.max_sumsq = b->max_sumsq;
-  a.shadow = b->shadow; a.shadow_ld = b->shadow_ld;
+  a.shadow = b->shadow; a.shadow_ld = b->shadow_ld; a.shadow_scale = b->shadow_scale;
   return a;
 }
 
@@ -904,6 +928,7 @@ int devqa_bank_destroy(devqa_bank* b) {
   DEVQA_ON_DEVICE(b->device);
   if (b->data || b->vmm) cudaDeviceSynchronize();
   if (b->shadow_vmm) vmm_destroy(b->shadow_vmm); else if (b->shadow) cudaFree(b->shadow);
+  if (b->shadow_scale) cudaFree(b->shadow_scale);
   if (b->vmm) { vmm_destroy(b->vmm); if (b->sumsq) cudaFree(b->sumsq); }
   else if (b->data) { cudaFree(b->data); cudaFree(b->sumsq); }
   if (b->max_sumsq) cudaFree(b->max_sumsq);
@@ -972,11 +997,12 @@ int devqa_bank_set_shadow(devqa_bank* b, int enable, void* stream_) {
     if (b->shadow_ld) {
       DEVQA_CUDA(cudaDeviceSynchronize());
       if (b->shadow_vmm) vmm_destroy(b->shadow_vmm); else if (b->shadow) cudaFree(b->shadow);
-      b->shadow = nullptr; b->shadow_vmm = nullptr; b->shadow_ld = 0; b->shadow_capacity = 0;
+      if (b->shadow_scale) cudaFree(b->shadow_scale);
+      b->shadow = nullptr; b->shadow_vmm = nullptr; b->shadow_scale = nullptr; b->shadow_ld = 0; b->shadow_capacity = 0;
     }
     return DEVQA_OK;
   }
-  if (b->dtype != DEVQA_F32) { set_error("a bf16 shadow only makes sense for an fp32 bank"); return DEVQA_E_UNSUPPORTED; }
+  if (b->dtype != DEVQA_F32) { set_error("a shadow only makes sense for an fp32 bank"); return DEVQA_E_UNSUPPORTED; }
   if (b->shadow_ld) return DEVQA_OK;
   static const bool vmm_on = getenv("DEVQA_VMM") == nullptr || atoi(getenv("DEVQA_VMM")) != 0;
   b->shadow_ld = (b->dim + 7) / 8 * 8;                       // rows stay 16-byte aligned
@@ -984,7 +1010,8 @@ int devqa_bank_set_shadow(devqa_bank* b, int enable, void* stream_) {
   int rc = shadow_update(b, 0, b->size, stream);
   if (rc) {
     if (b->shadow_vmm) vmm_destroy(b->shadow_vmm); else if (b->shadow) cudaFree(b->shadow);
-    b->shadow = nullptr; b->shadow_vmm = nullptr; b->shadow_ld = 0; b->shadow_capacity = 0;
+    if (b->shadow_scale) cudaFree(b->shadow_scale);
+    b->shadow = nullptr; b->shadow_vmm = nullptr; b->shadow_scale = nullptr; b->shadow_ld = 0; b->shadow_capacity = 0;
   }
   return rc;
 }

@@ -22,6 +22,8 @@ struct ScanParams {
   uint64_t* cand;          // [grid, n_queries, kcap] sorted candidate lists (output)
   IdMap idmap;
   const float* row_sumsq;  // optional cached ||row||^2 of library-owned banks (nullptr: computed in-kernel)
+  const float* row_scale;  // fp16 shadow: 2^-e per row (the accumulators of row r are multiplied by it); else nullptr
+  const float* qscale;     // fp16 shadow: 2^-f per query (written by the query-prep kernel); else nullptr
   const uint32_t* need;    // tcgen05 scan as a conditional fallback: [n_queries] flags, passes with none set exit at once
   // tcgen05 filter variant
   const float* qerr;       // [n_queries] tc_filter_relerr(dim) * ||query as used||
@@ -76,14 +78,16 @@ constexpr int kTcTf32x3 = 0, kTcBf16x3 = 1, kTcTf32x1 = 2, kTcBf16x1 = 3;   // k
 // (a few rows per query), while a violated bound would silently lose a row.  refine.cu checks  u - 2E <= s <= u  for
 // every candidate it re-scores (devqa_filter_bound_violations), tests/test_gpu_filter.py measures the actual error
 // on constructed worst cases against this bound.
-// bf16 SHADOW of an fp32 bank (shadow = true): the bank words were rounded to nearest bf16 as well (<= 2^-8 each), so
-// inputs = (1 + 2^-8)^2 - 1 = 2^-7 + 2^-16 relative to the ORIGINAL fp32 row's norm.
+// fp16 SHADOW of an fp32 bank (shadow = true): rows and queries are both rounded to nearest fp16 -- 11 significand bits,
+// <= 2^-11 each, after a per-row / per-query power-of-two scaling that keeps every value in fp16's normal range (see
+// synth.cu shadow_convert_kernel; the few elements that still go subnormal add < 2^-31) -- so
+// inputs = (1 + 2^-11)^2 - 1 = 2^-10 + 2^-22 relative to the ORIGINAL fp32 row's norm: tighter than the TF32 filter.
 __host__ __device__ inline float tc_filter_relerr(int64_t dim, bool bf16_bank = false, bool shadow = false) {
-  const float inputs = shadow ? 0.0078125f + 1.52587890625e-05f                // 2^-7 + 2^-16
+  const float inputs = shadow ? 0.0009765625f + 2.384185791015625e-07f         // 2^-10 + 2^-22
                               : (bf16_bank ? 0.00390625f : 1.5f * 0.0009765625f);   // 2^-8 | 2^-10 + 2^-11
   return inputs + 1.9073486328125e-06f + float(dim) * 2.384185791015625e-07f;  // + 2^-19 + dim * 2^-22
 }
-// internal flag bit (never set by callers): the bf16 bank being scanned is the shadow of an fp32 bank
+// internal flag bit (never set by callers): the 2-byte bank being scanned is the scaled-fp16 shadow of an fp32 bank
 constexpr unsigned kFlagShadowScan = 1u << 14;
 bool scan_tc_supported(int bank_dtype, const void* bank, int64_t dim, int64_t bank_ld, int top_k);
 int scan_tc_plan(int mode, int n_queries, int64_t dim, int kcap, bool cached_norms, int64_t n_tiles, int sm_count,
@@ -100,7 +104,8 @@ bool scan_tc_exchanges_thresholds(int mode, int64_t dim);   // scan-and-queue ep
 int scan_tc_prep_queries(int mode, const float* queries, int64_t query_ld, int n_queries, int qp, int q_pad,
                          int64_t dim, unsigned flags, void* qcat, uint32_t* gthr, float* qinv, float* qerr,
                          uint32_t* seed_u, uint32_t* gmax, int gmax_stride, const uint32_t* need, cudaStream_t stream,
-                         uint32_t* zero_words = nullptr, int n_zero = 0);   // filter modes: further words to zero
+                         uint32_t* zero_words = nullptr, int n_zero = 0,   // filter modes: further words to zero
+                         float* qscale = nullptr);                         // fp16 shadow: out [n_queries] 2^-f per query
 // one launch = `passes` consecutive query passes starting at p.q0, each on ctas_per_pass CTAs
 // (pair: clusters of two CTAs sharing the query operand, see scan_tc.cu)
 int scan_tc_launch(const ScanParams& p, int mode, const void* qcat, uint32_t* gthr, int qp, int stages, int passes,
@@ -222,5 +227,8 @@ int widen_rows_launch(const void* src, int64_t src_ld, float* dst, int64_t dst_l
                       cudaStream_t stream);
 int convert_rows_launch(const float* src, int64_t src_ld, void* dst, int dst_dtype, int64_t dst_ld,
                         int64_t n_rows, int64_t dim, cudaStream_t stream);
+// fp32 rows -> per-row scaled fp16 shadow rows + the scale to undo it (synth.cu)
+int shadow_convert_launch(const float* src, int64_t src_ld, void* dst, int64_t dst_ld, float* scale_out, int64_t n_rows,
+                          int64_t dim, cudaStream_t stream);
 
 }  // namespace devqa

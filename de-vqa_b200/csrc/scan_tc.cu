@@ -49,6 +49,7 @@
 // launch, so a launch runs several query passes side by side: CTA c works on pass c % passes and on
 // tiles c / passes, c / passes + ctas_per_pass, ...
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -298,6 +299,13 @@ struct RingPos {
   __device__ __forceinline__ void advance(int S) { if (++s == S) { s = 0; phase ^= 1u; } }
 };
 
+// the same with FP16 A and B (format field 0): the scaled-fp16 shadow of an fp32 bank
+__host__ __device__ constexpr uint32_t idesc_f16(int n) {
+  return (1u << 4) | (uint32_t(n >> 3) << 17) | (uint32_t(kTileRows >> 4) << 24);
+}
+__host__ __device__ constexpr uint32_t idesc_f16_pair(int n) {
+  return (1u << 4) | (uint32_t(n >> 3) << 17) | (uint32_t(256 >> 4) << 24);
+}
 // instruction descriptor: fp32 accumulate, BF16 A and B, both K-major, M = 128, N = n
 __host__ __device__ constexpr uint32_t idesc_bf16(int n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(n >> 3) << 17) | (uint32_t(kTileRows >> 4) << 24);
@@ -319,6 +327,8 @@ struct TcParams {
   const float* qcat;       // this pass's query operand: [n_kblocks][2*qp rows][32] fp32, rows 128B-swizzled
   uint64_t* cand;          // [grid, n_queries, kcap]
   const float* row_sumsq;  // optional cached ||row||^2 (bf16 / filter variants: replaces the in-kernel norm warps)
+  const float* row_scale;  // fp16 shadow of an fp32 bank: 2^-e per row (multiplies the row's accumulators); else nullptr
+  const float* qscale;     // fp16 shadow: 2^-f per query (from the query-prep kernel); else nullptr
   const uint32_t* need;    // optional [n_queries] flags: a CTA whose pass has none set exits at once (exact fallback)
   // filter variant only
   const float* qerr;       // [n_queries] relerr(dim) * ||query as used||: E = qerr * ||row|| (1 for normalised rows)
@@ -357,7 +367,7 @@ __host__ __device__ inline SmemLayout tc_layout(int stages, int qp, int kcap, in
   // [parts*qp rows x 128 B], 1024-aligned since qp % 16 == 0; a CTA pair holds half of the query rows each
   L.bq = off;    off += uint32_t(stages) * uint32_t(b_parts * (pair ? qp / 2 : qp)) * 128;
   L.lists = off; off += uint32_t(qp) * kcap * 8;
-  L.thr = off;   off += uint32_t(qp) * 16 + 16;                          // filter: eq / threshold / lost / service bound per query + counters
+  L.thr = off;   off += uint32_t(qp) * 20 + 16;                          // filter: eq / threshold / lost / service bound / query scale per query + counters
   L.scratch = off; off += hit_cap(qp) * 8;               // hit queue / dense [16][128] score tile (MULTI: score tile [HQ][128], same size)
   L.norms = off; off += qp > 128 ? 0 : kNormRing * kTileRows * 4;         // (256 queries per pass: cached row norms only)
   off = (off + 7) & ~7u;
@@ -436,6 +446,7 @@ __device__ __noinline__ float epilogue_insert_query(uint64_t* list, int kcap, in
 // (measured: 0.29 -> <0.01 list insertions per query and tile).  The otherwise idle warps 3-7 run this
 // selection continuously (service warps) and hand the result to the epilogue through shared memory.
 struct FiltState {            // per-query state in shared memory, [QP] each
+  float* qs;                  // fp16 shadow: 2^-f of the query's power-of-two scaling (1 otherwise)
   float* eq;                  // tc_filter_relerr * ||query||
   float* thr;                 // admission threshold on u: max(lower bounds T of the exact k-th best, full list's last entry)
   float* lost;                // upper bound of every row a full list turned away while its last entry was binding
@@ -865,12 +876,18 @@ __device__ __forceinline__ void emit_epilogue(const TcParams& p, const FiltState
     const int64_t g = int64_t(tile0 + it * tile_step) * kTileRows + row_in_tile;
     return (!norm_warps && it < n_my && g < p.n_rows) ? __ldg(p.row_sumsq + g) : 1.f;
   };
-  float ssq_next = ssq_of(0);
+  auto rs_of = [&](int it) {                                           // fp16 shadow: the row's 2^-e
+    const int64_t g = int64_t(tile0 + it * tile_step) * kTileRows + row_in_tile;
+    return (p.row_scale && it < n_my && g < p.n_rows) ? __ldg(p.row_scale + g) : 1.f;
+  };
+  const bool scaled = p.row_scale != nullptr;
+  float ssq_next = ssq_of(0), rs_next = rs_of(0);
   for (int it = 0; it < n_my; ++it) {
     const int tile = tile0 + it * tile_step;
     const int a = it & 1;
-    const float ssq_cached = ssq_next;
+    const float ssq_cached = ssq_next, rs_cached = rs_next;
     ssq_next = ssq_of(it + 1);
+    rs_next = rs_of(it + 1);
     mbar_wait(&tmem_full[a], (it >> 1) & 1);
     tc_fence_after();
     if (e == 0 && lane == 0) trace_at(p, 6, it);
@@ -884,14 +901,21 @@ __device__ __forceinline__ void emit_epilogue(const TcParams& p, const FiltState
       else inv = 1.0f / ((p.flags & DEVQA_NOEPS) ? nrm : fmaxf(nrm, kNormEps));
     }
     const uint32_t taddr = tmem_base + uint32_t(a) * QP + (uint32_t(e * 32) << 16);
+    // approximate score = accumulator * (2^-e of the row) * (2^-f of the query) * 1/||row||: the two power-of-two
+    // factors are exact, and they are applied BEFORE inv so that no intermediate leaves the float range
     auto to_u = [&](int c, const uint32_t (&d)[16], float (&u)[16]) {
 #pragma unroll
       for (int i4 = 0; i4 < 4; ++i4) {
         const float4 eq4 = *reinterpret_cast<const float4*>(st.eq + c + 4 * i4);
-        u[4 * i4 + 0] = fmaf(__uint_as_float(d[4 * i4 + 0]), inv, eq4.x * rowfac);
-        u[4 * i4 + 1] = fmaf(__uint_as_float(d[4 * i4 + 1]), inv, eq4.y * rowfac);
-        u[4 * i4 + 2] = fmaf(__uint_as_float(d[4 * i4 + 2]), inv, eq4.z * rowfac);
-        u[4 * i4 + 3] = fmaf(__uint_as_float(d[4 * i4 + 3]), inv, eq4.w * rowfac);
+        float4 f = make_float4(1.f, 1.f, 1.f, 1.f);
+        if (scaled) {
+          f = *reinterpret_cast<const float4*>(st.qs + c + 4 * i4);
+          f.x *= rs_cached; f.y *= rs_cached; f.z *= rs_cached; f.w *= rs_cached;
+        }
+        u[4 * i4 + 0] = fmaf(__uint_as_float(d[4 * i4 + 0]) * f.x, inv, eq4.x * rowfac);
+        u[4 * i4 + 1] = fmaf(__uint_as_float(d[4 * i4 + 1]) * f.y, inv, eq4.y * rowfac);
+        u[4 * i4 + 2] = fmaf(__uint_as_float(d[4 * i4 + 2]) * f.z, inv, eq4.z * rowfac);
+        u[4 * i4 + 3] = fmaf(__uint_as_float(d[4 * i4 + 3]) * f.w, inv, eq4.w * rowfac);
       }
     };
     if (it == 0) {
@@ -1173,8 +1197,8 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap bank_map, const __grid_consta
   float maxn = 1.f;                                      // un-normalised scores: E scales with ||row|| <= maxn
   if constexpr (SCANEPI) {
     float* fs = reinterpret_cast<float*>(smem + L.thr);
-    st.eq = fs; st.thr = fs + QP; st.lost = fs + 2 * QP; st.thr_ext = fs + 3 * QP;
-    st.qn = reinterpret_cast<uint32_t*>(fs + 4 * QP);
+    st.eq = fs; st.thr = fs + QP; st.lost = fs + 2 * QP; st.thr_ext = fs + 3 * QP; st.qs = fs + 4 * QP;
+    st.qn = reinterpret_cast<uint32_t*>(fs + 5 * QP);
     st.hit_u = reinterpret_cast<float*>(smem + L.scratch);
     st.hit_id = reinterpret_cast<uint32_t*>(smem + L.scratch) + hit_cap(QP);
     if (FILT && !(p.flags & DEVQA_NORMALIZE_BANK)) maxn = sqrtf(__uint_as_float(*p.bank_max_sumsq));
@@ -1188,6 +1212,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap bank_map, const __grid_consta
         if (ts > t) t = ts;
       }
       st.eq[j] = eq; st.thr[j] = t; st.lost[j] = -INFINITY; st.thr_ext[j] = -INFINITY;
+      st.qs[j] = (FILT && live && p.qscale) ? p.qscale[q0 + j] : 1.f;
     }
     if (threadIdx.x < 4) st.qn[threadIdx.x] = 0u;
   }
@@ -1269,7 +1294,9 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap bank_map, const __grid_consta
     if (PAIR && !leader) {
       // pair, peer CTA: no MMA issue (warps 4-7 forward "stage s is loaded" to the leader, below)
     } else if (lane == 0) {
-      const uint32_t idesc_cat = BFD ? (PAIR ? idesc_bf16_pair(QP) : idesc_bf16(kParts * QP))
+      const bool f16 = BFD && (p.flags & kFlagShadowScan) != 0;       // the shadow of an fp32 bank is (scaled) fp16, not bf16
+      const uint32_t idesc_cat = BFD ? (f16 ? (PAIR ? idesc_f16_pair(QP) : idesc_f16(kParts * QP))
+                                            : (PAIR ? idesc_bf16_pair(QP) : idesc_bf16(kParts * QP)))
                                      : (PAIR ? idesc_tf32_pair(QP) : idesc_tf32(kParts * QP));
       const uint32_t a_lo0 = (smem_u32(smem + L.a_raw) & 0x3ffffu) >> 4, b_lo0 = (smem_u32(smem + L.bq) & 0x3ffffu) >> 4;
       RingPos r;
@@ -1642,9 +1669,10 @@ __global__ void __launch_bounds__(128) prep_queries_filt_kernel(const float* __r
                                                                 void* __restrict__ qcat_, uint32_t* __restrict__ gthr,
                                                                 float* __restrict__ qinv, float* __restrict__ qerr,
                                                                 uint32_t* __restrict__ seed_u, uint32_t* __restrict__ gmax,
-                                                                int gmax_stride, uint32_t* __restrict__ zero_words, int n_zero) {
+                                                                int gmax_stride, uint32_t* __restrict__ zero_words, int n_zero,
+                                                                float* __restrict__ qscale) {
   extern __shared__ __align__(16) float srow[];          // [d_pad]
-  __shared__ float s_inv;
+  __shared__ float s_inv, s_up1, s_up2;
   constexpr int EK = BF16 ? 64 : 32;                     // columns per 128-byte k-block row
   const int tid = threadIdx.x, nthr = blockDim.x;
   pdl_wait();
@@ -1682,11 +1710,20 @@ __global__ void __launch_bounds__(128) prep_queries_filt_kernel(const float* __r
           inv = 1.0f / ((flags & DEVQA_NOEPS) ? nrm : fmaxf(nrm, kNormEps));
         }
       }
-      float nn = 0.f;                                    // ||query as used||^2
-      for (int c = lane; c < d_pad; c += 32) { const float x = srow[c] * inv; nn = fmaf(x, x, nn); }
+      float nn = 0.f, mx = 0.f;                          // ||query as used||^2, its largest magnitude
+      for (int c = lane; c < d_pad; c += 32) { const float x = srow[c] * inv; nn = fmaf(x, x, nn); mx = fmaxf(mx, fabsf(x)); }
 #pragma unroll
-      for (int off = 16; off >= 1; off >>= 1) nn += __shfl_xor_sync(kFull, nn, off);
+      for (int off = 16; off >= 1; off >>= 1) {
+        nn += __shfl_xor_sync(kFull, nn, off);
+        mx = fmaxf(mx, __shfl_xor_sync(kFull, mx, off));
+      }
       if (lane == 0) {
+        // fp16 shadow: the query is scaled by 2^f so that its largest magnitude lands in [2^13, 2^14) (as the rows are,
+        // synth.cu shadow_convert_kernel); the scan multiplies the accumulators by 2^-f
+        int f = 0;
+        if (BF16 && (flags & kFlagShadowScan) && mx > 0.f && mx <= 3.0e38f) { int ex; frexpf(mx, &ex); f = 14 - ex; }
+        s_up1 = exp2f(float(f / 2)); s_up2 = exp2f(float(f - f / 2));
+        if (qscale && live) qscale[r] = exp2f(float(-f));
         s_inv = inv;
         if (live) {
           qinv[r] = inv;
@@ -1700,9 +1737,18 @@ __global__ void __launch_bounds__(128) prep_queries_filt_kernel(const float* __r
     const int pass = r / qp, rp = r % qp;
     if constexpr (BF16) {
       __nv_bfloat16* base = static_cast<__nv_bfloat16*>(qcat_) + size_t(pass) * n_kblocks * (qp * 64);
-      for (int c = tid; c < d_pad; c += nthr) {
-        const int kb = c / 64, w = c % 64;
-        base[size_t(kb) * (qp * 64) + rp * 64 + (((w >> 3) ^ (rp & 7)) << 3) + (w & 7)] = __float2bfloat16_rn(srow[c] * inv);
+      if (flags & kFlagShadowScan) {                     // scaled fp16 (same 2-byte slots)
+        const float up1 = s_up1, up2 = s_up2;
+        __half* hbase = reinterpret_cast<__half*>(base);
+        for (int c = tid; c < d_pad; c += nthr) {
+          const int kb = c / 64, w = c % 64;
+          hbase[size_t(kb) * (qp * 64) + rp * 64 + (((w >> 3) ^ (rp & 7)) << 3) + (w & 7)] = __float2half_rn(srow[c] * inv * up1 * up2);
+        }
+      } else {
+        for (int c = tid; c < d_pad; c += nthr) {
+          const int kb = c / 64, w = c % 64;
+          base[size_t(kb) * (qp * 64) + rp * 64 + (((w >> 3) ^ (rp & 7)) << 3) + (w & 7)] = __float2bfloat16_rn(srow[c] * inv);
+        }
       }
     } else {
       float* base = static_cast<float*>(qcat_) + size_t(pass) * n_kblocks * (qp * kBlockK);
@@ -1773,7 +1819,8 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-int make_map(CUtensorMap* map, const void* base, bool bf16, uint64_t cols, uint64_t rows, uint64_t ld_bytes, uint32_t box_rows) {
+int make_map(CUtensorMap* map, const void* base, bool bf16, uint64_t cols, uint64_t rows, uint64_t ld_bytes, uint32_t box_rows,
+             bool f16 = false) {
   static EncodeTiledFn encode = nullptr;
   if (!encode) {
     void* fn = nullptr;
@@ -1789,7 +1836,7 @@ int make_map(CUtensorMap* map, const void* base, bool bf16, uint64_t cols, uint6
   const cuuint64_t gstride[1] = {ld_bytes};
   const cuuint32_t box[2] = {bf16 ? 64u : 32u, box_rows};     // 128 bytes of columns either way
   const cuuint32_t estride[2] = {1, 1};
-  CUresult r = encode(map, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), gdim, gstride, box, estride,
+  CUresult r = encode(map, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), gdim, gstride, box, estride,
                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -1858,7 +1905,7 @@ int scan_tc_plan(int mode, int n_queries, int64_t dim, int kcap, bool cached_nor
 int scan_tc_prep_queries(int mode, const float* queries, int64_t query_ld, int n_queries, int qp, int q_pad,
                          int64_t dim, unsigned flags, void* qcat, uint32_t* gthr, float* qinv, float* qerr,
                          uint32_t* seed_u, uint32_t* gmax, int gmax_stride, const uint32_t* need, cudaStream_t stream,
-                         uint32_t* zero_words, int n_zero) {
+                         uint32_t* zero_words, int n_zero, float* qscale) {
   const int n_kblocks = scan_tc_kblocks(mode, dim);
   const int grid = (q_pad + 7) / 8;
   if (mode == kTcTf32x3)
@@ -1874,7 +1921,7 @@ int scan_tc_prep_queries(int mode, const float* queries, int64_t query_ld, int n
     auto kern = mode == kTcBf16x1 ? prep_queries_filt_kernel<true> : prep_queries_filt_kernel<false>;
     if (smem > 40 * 1024) DEVQA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
     DEVQA_CUDA(launch_pdl(kern, dim3(fgrid), dim3(128), smem, stream, queries, query_ld, n_queries, int(dim), qp, n_kblocks,
-                          q_pad, flags, qcat, gthr, qinv, qerr, seed_u, gmax, gmax_stride, zero_words, n_zero));
+                          q_pad, flags, qcat, gthr, qinv, qerr, seed_u, gmax, gmax_stride, zero_words, n_zero, qscale));
   }
   DEVQA_CUDA(cudaGetLastError());
   count_launch();
@@ -1895,7 +1942,8 @@ int scan_tc_launch(const ScanParams& sp, int mode, const void* qcat, uint32_t* g
   const int parts = mode_parts(mode);
   const int n_kblocks = scan_tc_kblocks(mode, sp.dim);
   CUtensorMap bank_map;
-  int rc = make_map(&bank_map, sp.bank, bf, uint64_t(sp.dim), uint64_t(sp.n_rows), uint64_t(sp.bank_ld) * (bf ? 2 : 4), kTileRows);
+  int rc = make_map(&bank_map, sp.bank, bf, uint64_t(sp.dim), uint64_t(sp.n_rows), uint64_t(sp.bank_ld) * (bf ? 2 : 4), kTileRows,
+                    bf && (sp.flags & kFlagShadowScan) != 0);
   if (rc) return rc;
   TcParams p{};
   p.n_rows = sp.n_rows; p.dim = int(sp.dim); p.n_kblocks = n_kblocks;
@@ -1903,6 +1951,7 @@ int scan_tc_launch(const ScanParams& sp, int mode, const void* qcat, uint32_t* g
   p.qp = qp; p.nq_pass = sp.nq_pass; p.q0 = sp.q0; p.n_queries = sp.n_queries;
   p.top_k = sp.top_k; p.kcap = sp.kcap; p.stages = stages; p.passes = passes; p.flags = sp.flags;
   p.cand = sp.cand; p.gthr = gthr; p.idmap = sp.idmap; p.row_sumsq = sp.row_sumsq;
+  p.row_scale = sp.row_scale; p.qscale = sp.qscale;
   p.need = sp.need;
   p.oneshot = sp.oneshot; p.emit = sp.emit; p.gbar = sp.gbar; p.ocount = sp.ocount; p.ocand = sp.ocand; p.ocap = sp.ocap;
   p.gmax = sp.gmax; p.gmax_stride = sp.gmax_stride; p.lostu = sp.lostu; p.qerr = sp.qerr; p.seed_u = sp.seed_u; p.bank_max_sumsq = sp.bank_max_sumsq; p.k_true = sp.k_true > 0 ? sp.k_true : sp.top_k;

@@ -1,6 +1,8 @@
 // Counter-based synthetic bank generator (benchmarks and tests only; see devqa_fill_synthetic).
 // Every element is a pure function of (seed, global row, column), so any row sharding and any
 // append batching reproduce the same bank ("generated on device per shard").
+#include <cuda_fp16.h>
+
 #include "scan.cuh"
 
 namespace devqa {
@@ -77,7 +79,48 @@ __global__ void __launch_bounds__(256) widen_kernel(const __nv_bfloat16* __restr
   }
 }
 
+// Shadow rows: fp16 of the fp32 row scaled by a per-row power of two that puts the row's largest magnitude in
+// [2^13, 2^14) -- no overflow (fp16 max 65504), and only elements below 2^-27 of the row's maximum reach the subnormal
+// range (absolute error 2^-25 there: nothing against the 2^-11 relative rounding of everything else).  scale_out[r]
+// = 2^-e is what the scan multiplies the row's accumulators with.  One warp per row, two passes (the second from L2).
+__global__ void __launch_bounds__(256) shadow_convert_kernel(const float* __restrict__ src, int64_t src_ld, __half* dst,
+                                                             int64_t dst_ld, float* __restrict__ scale_out, int64_t n_rows,
+                                                             int dim) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warps = int64_t(gridDim.x) * (blockDim.x >> 5);
+  for (int64_t r = int64_t(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5); r < n_rows; r += warps) {
+    const float* in = src + r * src_ld;
+    float m = 0.f;
+    for (int c = lane; c < dim; c += 32) m = fmaxf(m, fabsf(in[c]));      // (fmaxf drops NaN: a NaN element stays NaN below)
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
+    int e = 0;
+    if (m > 0.f && m <= 3.0e38f) {
+      int ex;
+      frexpf(m, &ex);                          // m = f * 2^ex, f in [0.5, 1)  ->  m * 2^(14 - ex) in [2^13, 2^14)
+      e = 14 - ex;
+      if (e > 120) e = 120;                    // (rows of subnormal magnitude: ||row||^2 is 0 in fp32 anyway)
+    }
+    // two factors: 2^e itself may be out of float range for rows of subnormal magnitude
+    const float up1 = exp2f(float(e / 2)), up2 = exp2f(float(e - e / 2));
+    __half* out = dst + r * dst_ld;
+    for (int c = lane; c < dim; c += 32) out[c] = __float2half_rn(in[c] * up1 * up2);
+    if (lane == 0) scale_out[r] = exp2f(float(-e));                          // (e >= -113: representable or subnormal-exact)
+  }
+}
+
 }  // namespace
+
+int shadow_convert_launch(const float* src, int64_t src_ld, void* dst, int64_t dst_ld, float* scale_out, int64_t n_rows,
+                          int64_t dim, cudaStream_t stream) {
+  if (n_rows == 0) return DEVQA_OK;
+  const int64_t want = (n_rows + 7) / 8;
+  const unsigned grid = unsigned(want < 148 * 16 ? want : 148 * 16);
+  shadow_convert_kernel<<<grid, 256, 0, stream>>>(src, src_ld, static_cast<__half*>(dst), dst_ld, scale_out, n_rows, int(dim));
+  DEVQA_CUDA(cudaGetLastError());
+  count_launch();
+  return DEVQA_OK;
+}
 
 int widen_rows_launch(const void* src, int64_t src_ld, float* dst, int64_t dst_ld, int64_t n_rows, int64_t dim,
                       cudaStream_t stream) {

@@ -556,8 +556,8 @@ def test_filter_serves_top_k_up_to_128(n, d, nq, k, nb, dtype):
                                               (60000, 128, 130, 5, None, False), (19000, 100, 70, 64, "noeps", False),
                                               (300000, 64, 1, 32, "eps", True), (20000, 768, 300, 32, None, True)])
 def test_shadow_bank_returns_the_exact_fp32_results(n, d, nq, k, nb, unit):
-    """The filter scans a bf16 SHADOW of the fp32 bank (2 bytes per element), candidates are re-scored against the
-    fp32 rows: bit-identical to the stream kernel on the fp32 bank, canary silent."""
+    """The filter scans a scaled-fp16 SHADOW of the fp32 bank (2 bytes per element), candidates are re-scored against
+    the fp32 rows: bit-identical to the stream kernel on the fp32 bank, canary silent."""
     bank, q = _randn(n, d, n + d, unit=unit), _randn(nq, d, nq + k, unit=unit)
     if not unit:
         bank = bank * torch.exp(0.5 * torch.randn(n, 1, generator=torch.Generator().manual_seed(n)))
@@ -589,16 +589,19 @@ def test_shadow_bank_returns_the_exact_fp32_results(n, d, nq, k, nb, unit):
 
 @pytest.mark.parametrize("d", [768, 4096])
 def test_shadow_error_bound_on_the_constructed_worst_case(d):
-    """Rows AND queries one below the bf16 rounding midpoint, parallel, all positive: the per-element error reaches
-    2^-7 of ||row|| ||query||; the shadow's bound (2^-7 + 2^-16 + 2^-19 + D 2^-22) must hold for every pair, and the
-    real search must come back exact with the canary silent."""
+    """The shadow is fp16 with a power-of-two scale per row / per query (11 significand bits).  Rows AND queries one
+    below the fp16 rounding midpoint, parallel, all positive: the per-element error reaches 2^-10 of ||row|| ||query||;
+    the shadow's bound (2^-10 + 2^-22 + 2^-19 + D 2^-22) must hold, and the real search must come back exact with the
+    canary silent -- also for rows scaled far outside fp16's own range."""
     rng = np.random.default_rng(d)
     n, nq = 25000, 16                                         # >= 148 tiles: the shadow path is taken
     e = rng.integers(120, 128, size=(n, d), dtype=np.uint32)
-    rows = _bits_to_f32((e << np.uint32(23)) | np.uint32(0x7FFF))
-    queries = _bits_to_f32((e[:nq] << np.uint32(23)) | np.uint32(0x7FFF))
+    rows = _bits_to_f32((e << np.uint32(23)) | np.uint32(0x0FFF))
+    queries = _bits_to_f32((e[:nq] << np.uint32(23)) | np.uint32(0x0FFF))
+    big = torch.exp2(torch.randint(-40, 40, (n, 1), generator=torch.Generator().manual_seed(d)).float())   # (||row||^2 stays in fp32 range)
+    rows = rows * big                                          # exact (powers of two): fp16 alone could not hold these
     fb = FactBank.from_embeddings(rows, shadow=True)
-    rel = 2.0 ** -7 + 2.0 ** -16 + 2.0 ** -19 + d * 2.0 ** -22
+    rel = 2.0 ** -10 + 2.0 ** -22 + 2.0 ** -19 + d * 2.0 ** -22
     _fallbacks(); _violations()
     a = fb.search(queries.cuda(), 8, normalize_bank="eps", normalize_query=None, flags=L.FORCE_TENSOR)
     nfb, nv = _fallbacks(), _violations()
@@ -606,14 +609,20 @@ def test_shadow_error_bound_on_the_constructed_worst_case(d):
     assert nv == 0
     assert torch.equal(a[1], b[1]) and torch.equal(a[0], b[0])
     assert a[1][:, 0].cpu().tolist() == list(range(nq))        # query j is parallel to row j: cosine 1
-    # the measured error of the shadow product for the parallel pairs, against the bound
-    r16, q16 = rows[:nq].to(torch.bfloat16).double(), queries.to(torch.bfloat16).double()
-    exact = (rows[:nq].double() * queries.double()).sum(1)
+    # the measured error of the fp16 product for the parallel pairs (scales are exact powers of two), against the bound
+    r0 = rows[:nq] / big[:nq]
+    r16, q16 = r0.half().double(), queries.half().double()
+    exact = (r0.double() * queries.double()).sum(1)
     approx = (r16 * q16).sum(1)
-    scale = rows[:nq].double().norm(dim=1) * queries.double().norm(dim=1)
+    scale = r0.double().norm(dim=1) * queries.double().norm(dim=1)
     err = float(((exact - approx).abs() / scale).max())
-    _record(f"shadow_worstcase_d{d}", {"max_err": err, "bound": rel, "fallbacks": nfb})
-    assert 0.9 * 2.0 ** -7 < err < rel
+    _record(f"shadow_fp16_worstcase_d{d}", {"max_err": err, "bound": rel, "fallbacks": nfb})
+    assert 0.9 * 2.0 ** -10 < err < rel
+    # un-normalised scores over the same bank (E scales with ||row||: rows up to 2^40 dominate) stay exact too
+    c = fb.search(queries.cuda(), 8, normalize_bank=None, normalize_query=None, flags=L.FORCE_TENSOR)
+    dd = fb.search(queries.cuda(), 8, normalize_bank=None, normalize_query=None, flags=L.FORCE_STREAM)
+    assert _violations() == 0
+    assert torch.equal(c[1], dd[1]) and torch.equal(c[0], dd[0])
     fb.close()
 
 
