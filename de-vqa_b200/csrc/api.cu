@@ -375,10 +375,13 @@ static int run_search(Scratch* s, const SearchArgs& a, uint64_t* out_keys, float
                            (a.dtype == DEVQA_F32 ? ((a.flags & DEVQA_NORMALIZE_BANK) || (a.row_sumsq && a.max_sumsq))
                                                  : (a.row_sumsq != nullptr && a.max_sumsq != nullptr));
   // bf16 shadow: only where refine reads the per-CTA lists (its 512-candidate capacity takes the shadow's wide error band)
-  // (the scaled-fp16 accumulators are only understood by the emit-mode epilogue)
+  // fp16 shadow: where the scan runs one of the epilogues that understand the scaled accumulators -- emit mode (long
+  // scans) or one-shot mode (short scans); the conditions mirror tc_pipeline's
+  const int64_t sh_tiles = (a.n_rows + 127) / 128;
+  const bool sh_emit = sh_tiles >= s->sm_count && s->sm_count >= a.top_k && !(a.flags & DEVQA_DEBUG_NO_EMIT);
+  const bool sh_oneshot = sh_tiles <= s->sm_count && sh_tiles >= a.top_k && !(a.flags & DEVQA_DEBUG_NO_ONESHOT);
   const bool shadow_scan = filter_path && a.shadow != nullptr && a.dtype == DEVQA_F32 && a.top_k <= 64 &&
-                           (a.n_rows + 127) / 128 >= s->sm_count && s->sm_count >= a.top_k &&
-                           !(a.flags & (DEVQA_DEBUG_FILTER_ONLY | DEVQA_NO_SHADOW | DEVQA_DEBUG_NO_EMIT));
+                           (sh_emit || sh_oneshot) && !(a.flags & (DEVQA_DEBUG_FILTER_ONLY | DEVQA_NO_SHADOW));
   if (tc_ok && filter_path) {
     const int64_t tiles = (a.n_rows + 127) / 128;
     // tiny banks (fewer tiles than SMs), up to 8 queries: ONE stream launch (~15 us) beats the seven-launch pipeline

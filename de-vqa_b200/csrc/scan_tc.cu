@@ -1058,6 +1058,8 @@ __device__ __forceinline__ void oneshot_epilogue(const TcParams& p, const FiltSt
     else inv = 1.0f / ((p.flags & DEVQA_NOEPS) ? nrm : fmaxf(nrm, kNormEps));
   }
   const uint32_t taddr = tmem_base + (uint32_t(e * 32) << 16);
+  const bool scaled = p.row_scale != nullptr;                          // fp16 shadow: power-of-two scales of row and query
+  const float rs = (scaled && grow < p.n_rows) ? __ldg(p.row_scale + grow) : 1.f;
   auto load_u = [&](int c, float (&u)[16]) {
     uint32_t d[16];
     tmem_ld<16>(taddr + uint32_t(c), d);
@@ -1065,10 +1067,15 @@ __device__ __forceinline__ void oneshot_epilogue(const TcParams& p, const FiltSt
 #pragma unroll
     for (int i4 = 0; i4 < 4; ++i4) {
       const float4 eq4 = *reinterpret_cast<const float4*>(st.eq + c + 4 * i4);
-      u[4 * i4 + 0] = fmaf(__uint_as_float(d[4 * i4 + 0]), inv, eq4.x * rowfac);
-      u[4 * i4 + 1] = fmaf(__uint_as_float(d[4 * i4 + 1]), inv, eq4.y * rowfac);
-      u[4 * i4 + 2] = fmaf(__uint_as_float(d[4 * i4 + 2]), inv, eq4.z * rowfac);
-      u[4 * i4 + 3] = fmaf(__uint_as_float(d[4 * i4 + 3]), inv, eq4.w * rowfac);
+      float4 f = make_float4(1.f, 1.f, 1.f, 1.f);
+      if (scaled) {
+        f = *reinterpret_cast<const float4*>(st.qs + c + 4 * i4);
+        f.x *= rs; f.y *= rs; f.z *= rs; f.w *= rs;
+      }
+      u[4 * i4 + 0] = fmaf(__uint_as_float(d[4 * i4 + 0]) * f.x, inv, eq4.x * rowfac);
+      u[4 * i4 + 1] = fmaf(__uint_as_float(d[4 * i4 + 1]) * f.y, inv, eq4.y * rowfac);
+      u[4 * i4 + 2] = fmaf(__uint_as_float(d[4 * i4 + 2]) * f.z, inv, eq4.z * rowfac);
+      u[4 * i4 + 3] = fmaf(__uint_as_float(d[4 * i4 + 3]) * f.w, inv, eq4.w * rowfac);
     }
   };
   uint32_t* const best_s = st.hit_id;
