@@ -147,7 +147,7 @@ class FactBank:
             pass
 
     def set_shadow(self, enable: bool = True) -> None:
-        """Keep (or drop) a bf16 shadow of this fp32 bank: large scans stream 2 bytes per element instead of 4 and
+        """Keep (or drop) a 2-byte (scaled fp16) shadow of this fp32 bank: large scans stream 2 bytes per element instead of 4 and
         re-score their candidates against the fp32 rows -- results stay the exact fp32 results, bit for bit."""
         L.check(L.lib().devqa_bank_set_shadow(self._h, 1 if enable else 0, _stream_ptr(self.device_index)))
 

@@ -374,7 +374,7 @@ static int run_search(Scratch* s, const SearchArgs& a, uint64_t* out_keys, float
   const bool filter_path = !(a.flags & DEVQA_FORCE_TF32X3) && a.top_k <= 128 && a.dim <= 16384 &&
                            (a.dtype == DEVQA_F32 ? ((a.flags & DEVQA_NORMALIZE_BANK) || (a.row_sumsq && a.max_sumsq))
                                                  : (a.row_sumsq != nullptr && a.max_sumsq != nullptr));
-  // bf16 shadow: only where refine reads the per-CTA lists (its 512-candidate capacity takes the shadow's wide error band)
+
   // fp16 shadow: where the scan runs one of the epilogues that understand the scaled accumulators -- emit mode (long
   // scans) or one-shot mode (short scans); the conditions mirror tc_pipeline's
   const int64_t sh_tiles = (a.n_rows + 127) / 128;
@@ -557,7 +557,7 @@ struct devqa_bank {
   int64_t size = 0, capacity = 0;
   void* data = nullptr;
   devqa::VmmBuffer* vmm = nullptr; // rows live in a reserved virtual range that grows in place (vmm.cu); nullptr: cudaMalloc + copy
-  // Optional bf16 SHADOW of an fp32 bank (devqa_bank_set_shadow): the tensor-core filter streams these 2 bytes per
+  // Optional 2-byte (scaled fp16) SHADOW of an fp32 bank (devqa_bank_set_shadow): the tensor-core filter streams these 2 bytes per
   // element instead of 4, candidates are re-scored against the fp32 rows -- exact fp32 results from half the bytes.
   void* shadow = nullptr;
   devqa::VmmBuffer* shadow_vmm = nullptr;
@@ -650,7 +650,7 @@ static int bank_grow(devqa_bank* b, int64_t want_rows, cudaStream_t stream) {
   return DEVQA_OK;
 }
 
-// keep the bf16 shadow's storage in step with the bank's capacity
+// keep the shadow's storage in step with the bank's capacity
 static int shadow_grow(devqa_bank* b, int64_t cap, cudaStream_t stream) {
   if (!b->shadow_ld || cap <= b->shadow_capacity) return DEVQA_OK;
   const size_t bytes = size_t(cap) * b->shadow_ld * 2;
@@ -679,7 +679,7 @@ static int shadow_grow(devqa_bank* b, int64_t cap, cudaStream_t stream) {
   void* fresh = nullptr;
   cudaError_t e = cudaMalloc(&fresh, bytes);
   if (e != cudaSuccess) {
-    set_error("cudaMalloc of %zu bytes for the bf16 shadow failed: %s", bytes, cudaGetErrorString(e));
+    set_error("cudaMalloc of %zu bytes for the shadow failed: %s", bytes, cudaGetErrorString(e));
     return DEVQA_E_NOMEM;
   }
   if (b->shadow) {

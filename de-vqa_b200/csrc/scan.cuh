@@ -94,7 +94,7 @@ int scan_tc_plan(int mode, int n_queries, int64_t dim, int kcap, bool cached_nor
                  unsigned flags, int* qp_out, int* stages_out, bool* pair_out, bool oneshot = false);
 constexpr int kOneshotCap = 512;       // candidates per query the one-shot scan can emit (refine's first-cut capacity)
 constexpr int kEmitCap = 128;          // candidates per (CTA, query) a long scan can emit (everything that ever beat the running
-                                       // threshold: ~1500 per query over 148 CTAs with the bf16 shadow at top_k = 32)
+                                       // threshold: ~1500 per query over 148 CTAs with a bf16 shadow, far fewer with the fp16 one)
 size_t scan_tc_qcat_bytes(int mode, int64_t dim, int q_pad);
 bool scan_tc_exchanges_thresholds(int mode, int64_t dim);   // scan-and-queue epilogue + gmax exchange (else: seeded score-tile epilogue)
 // queries -> normalised, split (hi/lo TF32; hi/mid/lo bf16; hi TF32 only for the filter), laid out per pass as the

@@ -690,7 +690,7 @@ __device__ __forceinline__ void filt_epilogue(const TcParams& p, const FiltState
         // The queue is read 32 hits at a time, ONE load per lane; the warp then walks its own hits through shuffles
         // and has every shared-memory word an insertion needs (the list, the threshold, the error scale) in flight
         // together.  The previous form chained six dependent shared-memory round trips per hit on a pipe that TMA and
-        // UMMA keep ~90% busy -- ~1000 cycles per insertion, and with the bf16 shadow (tile period 7 k cycles instead
+        // UMMA keep ~90% busy -- ~1000 cycles per insertion, and with the 2-byte shadow (tile period 7 k cycles instead
         // of 14 k) the epilogue, not HBM, set the pace.
         for (uint32_t h0 = 0; h0 < n; h0 += 32) {
           const uint32_t h = h0 + uint32_t(lane);
@@ -843,7 +843,7 @@ __device__ __forceinline__ void filt_service(const TcParams& p, const FiltState 
 // ---- emit mode: long scans on the filter path without per-CTA lists ----------------------------------------------------
 // The list epilogue inserts every row that beats the running threshold into a sorted per-CTA list (~900 cycles per
 // insertion on a shared-memory pipe that TMA and UMMA keep busy).  The number of such rows is set by the filter's error
-// band: ~200 per query and scan with the TF32 filter, ~1500 with the bf16 shadow (band 2E = 0.43 sigma of the score
+// band: ~200 per query and scan with the TF32 filter, ~1500 with a bf16 shadow (the first version; band 2E = 0.43 sigma of the score
 // distribution) -- there the epilogue, not HBM, set the tile period (traced: 7.1 k cycles of epilogue per 7.9 k-cycle
 // tile; the first eight tiles 17 k each).  But nothing downstream needs the lists SORTED: refine.cu only wants every
 // row with u >= T.  So, like the one-shot mode's pass B, a thread that finds a survivor appends it to a flat per-query

@@ -79,7 +79,7 @@ extern "C" {
 #define DEVQA_FORCE_TF32X3 (1u << 10)   /* testing/benchmark: tcgen05 path without the TF32 filter + exact
                                            re-scoring stage (every score straight from the 3xTF32 split)  */
 
-#define DEVQA_NO_SHADOW (1u << 15)      /* search an fp32 bank that has a bf16 shadow as if it had none */
+#define DEVQA_NO_SHADOW (1u << 15)      /* search an fp32 bank that has a shadow as if it had none */
 #define DEVQA_FORCE_FILTER (1u << 11)   /* testing/benchmark: TF32 filter + exact re-scoring also on banks the
                                            library would scan with 3xTF32 alone (fewer than 8 tiles per SM)     */
 #define DEVQA_DEBUG_TIGHT_BOUND (1u << 12) /* tests: run the filter with 1/64 of its error bound, so that the bound IS
@@ -175,10 +175,11 @@ DEVQA_API int devqa_bank_reserve(devqa_bank* bank, int64_t capacity_rows, void* 
  * and the call stages + copies it (synchronous w.r.t. the host buffer).                   */
 DEVQA_API int devqa_bank_append(devqa_bank* bank, const float* rows, int64_t n, int64_t ld, int rows_is_host,
                       void* stream);
-/* Optional bf16 SHADOW of an fp32 bank.  The bank stays fp32 and every result stays the exact fp32 result (bit-identical
- * to a bank without a shadow); but large scans stream the 2-byte shadow instead of the 4-byte rows: the tensor-core
- * filter runs on it with an error bound that also covers the rounding of the rows (2^-7 instead of 1.5 * 2^-10), its
- * candidates (a few hundred per query on a 10M-row bank) are re-scored against the fp32 rows, and the usual proof /
+/* Optional 2-byte SHADOW of an fp32 bank: fp16 rows, each scaled by its own power of two (kept per row) so that any
+ * finite fp32 row fits fp16's normal range.  The bank stays fp32 and every result stays the exact fp32 result
+ * (bit-identical to a bank without a shadow); but scans stream the 2-byte shadow instead of the 4-byte rows: the
+ * tensor-core filter runs on it with an error bound that also covers the rounding of the rows (2^-10 in all, tighter
+ * than the TF32 filter's 1.5 * 2^-10), its candidates are re-scored against the fp32 rows, and the usual proof /
  * canary / exact fallback applies.  Costs 50% more device memory and one extra conversion pass per append; halves the
  * bytes of every HBM-bound search and doubles the tensor rate of the large-batch ones.  enable = 0 drops it. */
 DEVQA_API int devqa_bank_set_shadow(devqa_bank* bank, int enable, void* stream);
