@@ -270,7 +270,8 @@ static int tc_pipeline(Scratch* s, const SearchArgs& a, int mode, FilterSide* si
     side->emit = emit;
     side->ocap = oneshot ? kOneshotCap : kEmitCap;
     if (oneshot) { p.oneshot = 1; p.gbar = side->gbar; p.ocount = side->ocount; p.ocand = side->ocand; p.ocap = kOneshotCap; }
-    if (emit) { p.emit = 1; p.ocount = side->ocount; p.ocand = side->ocand; p.ocap = kEmitCap; }   // [grid][Q] / [grid][Q][cap]
+    if (emit) { p.emit = 1; p.gbar = side->gbar; p.ocount = side->ocount; p.ocand = side->ocand; p.ocap = kEmitCap; }   // [grid][Q] / [grid][Q][cap]
+    if (emit) DEVQA_REQUIRE(n_passes <= 64, "emit scan: too many passes for the arrival counters");
   }
   p.gmax = gmax; p.gmax_stride = kGmaxStride;
   DEVQA_REQUIRE(grid <= kGmaxStride, "more CTAs per pass than the threshold exchange holds");
@@ -279,8 +280,8 @@ static int tc_pipeline(Scratch* s, const SearchArgs& a, int mode, FilterSide* si
   if (prof) DEVQA_CUDA(cudaEventRecord(s->prof_ev[2 * s->prof_used], stream));
   if ((rc = scan_tc_prep_queries(mode, a.queries, a.query_ld, int(a.n_queries), qp, q_pad, a.dim, a.flags, s->qsplit, gthr,
                                  side ? side->qinv : nullptr, side ? side->qerr : nullptr, side ? side->seed_u : nullptr,
-                                 gmax, kGmaxStride, need, stream, oneshot ? side->gbar : nullptr,
-                                 oneshot ? 128 + int(a.n_queries) : 0, p.qscale ? side->qscale : nullptr)))
+                                 gmax, kGmaxStride, need, stream, (oneshot || emit) ? side->gbar : nullptr,
+                                 oneshot ? 128 + int(a.n_queries) : (emit ? 128 : 0), p.qscale ? side->qscale : nullptr)))
     return rc;
   // Threshold seeding: scan a prefix sample of the bank (one tile per CTA) first; the k-th best score of a
   // SUBSET is a lower bound of the k-th best of the whole bank, so the main scan starts with tight

@@ -763,6 +763,24 @@ __device__ __forceinline__ void filt_epilogue(const TcParams& p, const FiltState
     }
 }
 
+// Grid-wide arrival counters in global memory (all CTAs of the launch are co-resident: one per SM, grid <= SM count).
+__device__ __forceinline__ void grid_arrive(uint32_t* ctr) {
+  __threadfence();
+  atomicAdd(ctr, 1u);
+}
+// returns false when it gave up (the caller then carries on without what it waited for; results stay correct, the
+// queries concerned overflow their candidate arrays and are redone exactly)
+__device__ __forceinline__ bool grid_wait(const uint32_t* ctr, uint32_t want, long long max_cycles = 2000000000ll) {
+  const long long t0 = clock64();
+  uint32_t v;
+  do {
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+    if (v >= want) return true;
+    __nanosleep(100);
+  } while (clock64() - t0 < max_cycles);
+  return false;
+}
+
 // One round of the shared-out threshold selection: CTA `cta` derives T for the queries j = cta, cta + n_ctas, ... of
 // its pass from every CTA's best upper bound (gmax) and publishes it in gthr (atomicMax on the score code).
 __device__ __forceinline__ void service_select_round(const TcParams& p, const FiltState& st, int q0, int nq_pass, int n_ctas,
@@ -785,10 +803,12 @@ __device__ __forceinline__ void service_select_round(const TcParams& p, const Fi
     uint32_t x[NQ];
 #pragma unroll
     for (int t = 0; t < NQ; ++t) x[t] = 0u;
+    const int n_live = min(NQ, (nq_pass - jg + n_ctas - 1) / n_ctas);   // slots of this group that hold a query (warp-uniform)
 #pragma unroll 1
     for (int bit = 31; bit >= 12; --bit) {
 #pragma unroll
       for (int t = 0; t < NQ; ++t) {
+        if (t >= n_live) break;
         const uint32_t cand = x[t] | (1u << bit);
         int cnt = 0;
 #pragma unroll
@@ -818,6 +838,31 @@ __device__ __forceinline__ void filt_service(const TcParams& p, const FiltState 
   const int k = p.k_true;
   if (n_ctas < k || !p.gmax) return;                                  // the bound needs k distinct CTAs
   volatile float* const thr_ext = st.thr_ext;
+  if (p.emit && p.gbar) {
+    // Emit mode, first exchange.  The epilogue's first tile WAITS for thresholds, with the MMA pipeline stalled behind
+    // it: polling rounds (select ~3 k cycles + sleep, once here and once in the CTA that owns the query) made that
+    // wait ~28 k cycles (traced).  Instead, as in the one-shot mode: wait until every CTA has published its first-tile
+    // bests (arrival counter), select, publish, wait until every CTA has (second counter), pick the thresholds up.
+    // Bounded: if the grid is not co-resident the counters never fill, and the polling loop below takes over.
+    const int pg = p.q0 / p.qp + int(blockIdx.x) % p.passes;
+    uint32_t ok = 0u;
+    if (lane == 0) ok = grid_wait(p.gbar + 2 * pg, uint32_t(n_ctas), 400000) ? 1u : 0u;
+    ok = __shfl_sync(kFull, ok, 0);
+    if (lane == 0) trace_at(p, 12, 0);
+    if (ok) {
+      service_select_round(p, st, q0, nq_pass, n_ctas, cta, maxn, lane, k);
+      __syncwarp();
+      if (lane == 0) trace_at(p, 13, 0);
+      if (lane == 0) { grid_arrive(p.gbar + 2 * pg + 1); grid_wait(p.gbar + 2 * pg + 1, uint32_t(n_ctas), 400000); }
+      __syncwarp();
+      if (lane == 0) trace_at(p, 14, 0);
+      for (int j = lane; j < nq_pass; j += 32) {
+        uint32_t code;
+        asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(code) : "l"(p.gthr + q0 + j));
+        if (code != 0u) thr_ext[j] = code_score(code);
+      }
+    }
+  }
   // The k-th best of everything seen grows like log(rows): refresh eagerly at first, then back off (a spinning
   // warp costs issue slots and, on a power-capped part, clock).
   unsigned pause_ns = 500;
@@ -927,24 +972,37 @@ __device__ __forceinline__ void emit_epilogue(const TcParams& p, const FiltState
         tmem_ld<16>(taddr + uint32_t(c), d);
         tmem_ld_wait();
         to_u(c, d, u);
+        // 16 warp-wide maxima back to back (each result is in every lane), then lane i posts the i-th: ONE shared-memory
+        // atomic per 16 queries.  (A reduce + lane-0 atomic per query serialised to ~280 cycles each: 18 k cycles of
+        // the first tile, with the MMA pipeline stalled behind it.)
+        uint32_t mine = 0u;
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
           const uint32_t m = __reduce_max_sync(kFull, row_live ? score_code(u[i]) : 0u);
-          if (lane == 0) atomicMax(best_s + c + i, m);
+          mine = lane == i ? m : mine;
         }
+        if (lane < 16) atomicMax(best_s + c + lane, mine);
       }
       epilogue_barrier();
+      if (tid == 0) trace_at(p, 9, 0);
       for (int j = tid; j < nq_pass; j += 128) {
         const uint32_t b = best_s[j];
         pub_s[j] = b;
         p.gmax[size_t(q0 + j) * p.gmax_stride + tile0] = b;
       }
+      if (p.gbar) {                                                    // tell the service warps: this CTA's bests are in gmax
+        __threadfence();
+        epilogue_barrier();
+        if (tid == 0) atomicAdd(p.gbar + 2 * (p.q0 / p.qp + int(blockIdx.x) % p.passes), 1u);
+      }
+      if (tid == 0) trace_at(p, 10, 0);
       for (int j = tid; j < nq_pass; j += 128) {
         const long long t0 = clock64();                                // (no thresholds: every row would be a candidate)
         while (*reinterpret_cast<volatile float*>(st.thr_ext + j) == -INFINITY && clock64() - t0 < 400000) __nanosleep(200);
         st.thr[j] = fmaxf(st.thr[j], *reinterpret_cast<volatile float*>(st.thr_ext + j));
       }
       epilogue_barrier();
+      if (tid == 0) trace_at(p, 11, 0);
     }
     // ---- scan: 16 accumulators at a time, the next tensor-memory load in flight while these are compared ----
     auto consume = [&](int c, const float (&u)[16]) {
@@ -1026,20 +1084,6 @@ __device__ __forceinline__ void emit_epilogue(const TcParams& p, const FiltState
 //            whole bank) are appended to a global candidate array by atomic counter -- no lists, nothing is ever "lost".
 // refine.cu then re-scores the candidates exactly (refine_lists_kernel, direct mode).  A query whose candidates overflow
 // the array (no usable T: NaN, fewer than k tiles) is flagged there and redone by the exact pipeline.
-__device__ __forceinline__ void grid_arrive(uint32_t* ctr) {
-  __threadfence();
-  atomicAdd(ctr, 1u);
-}
-__device__ __forceinline__ void grid_wait(const uint32_t* ctr, uint32_t want) {
-  const long long t0 = clock64();
-  uint32_t v;
-  do {
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
-    if (v >= want) break;
-    __nanosleep(100);
-  } while (clock64() - t0 < 2000000000ll);      // ~1 s: give up (thresholds stay open, the queries overflow and are redone exactly)
-}
-
 template <int QP>
 __device__ __forceinline__ void oneshot_epilogue(const TcParams& p, const FiltState st, const float* norms, bool norm_warps,
                                                  uint32_t tmem_base, uint64_t* tmem_full, int tile, int n_ctas, int pass_global,
@@ -1086,11 +1130,13 @@ __device__ __forceinline__ void oneshot_epilogue(const TcParams& p, const FiltSt
   for (int c = 0; c < QP; c += 16) {
     float u[16];
     load_u(c, u);
+    uint32_t mine = 0u;                                                // (see emit_epilogue: one atomic per 16 queries)
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
       const uint32_t m = __reduce_max_sync(kFull, row_live ? score_code(u[i]) : 0u);
-      if (lane == 0) atomicMax(best_s + c + i, m);
+      mine = lane == i ? m : mine;
     }
+    if (lane < 16) atomicMax(best_s + c + lane, mine);
   }
   epilogue_barrier();
   for (int j = e * 32 + lane; j < nq_pass; j += 128) p.gmax[size_t(q0 + j) * p.gmax_stride + tile] = best_s[j];

@@ -25,8 +25,8 @@ for r in range(6):
 for r in (6, 7):
     print(names[r].ljust(14), " ".join(f"{int(x) - t0:7d}" if x else "      -" for x in t[r, :24]))
 print("slow_calls_w0".ljust(14), " ".join(f"{int(x):7d}" for x in t[8, :24]))
-for r, nm in ((13, "s0_ld_done"), (14, "s0_bits_done"), (9, "step0_body"), (10, "step0_bar"), (11, "step1_bar"), (12, "step2_bar")):
-    print(nm.ljust(14), " ".join(f"{int(x) - t0:7d}" if x else "      -" for x in t[r, :24]))
+for r, nm in ((9, "passA_done"), (10, "published"), (11, "thr_arrived"), (12, "svc_all_pub"), (13, "svc_selected"), (14, "svc_all_sel")):
+    print(nm.ljust(14), " ".join(f"{int(x) - t0:7d}" if x else "      -" for x in t[r, :2]))
 # summary over all recorded tiles
 import numpy as np
 got, done, slow = t[6].numpy().astype(np.int64), t[7].numpy().astype(np.int64), t[8].numpy()
