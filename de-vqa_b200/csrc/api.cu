@@ -715,6 +715,8 @@ static SearchArgs bank_args(const devqa_bank* b, const float* q, int64_t nq, int
 }
 
 // H2D of queries into scratch; returns device pointer
+// (tried: results up to 64 KB straight into pinned memory for any query batch -- end to end 26.2 k -> 23.2 k q/s at
+// Q = 64: 24 KB of scattered 4/8-byte stores over PCIe cost more than one D2H copy)
 static bool small_io(size_t qbytes, size_t obytes) { return qbytes <= 16 * 1024 && obytes <= 16 * 1024; }
 
 static int stage_queries(Scratch* s, const float* qh, int64_t nq, int64_t dim, int64_t qld, int top_k,

@@ -78,6 +78,7 @@ constexpr int kBlockK = 32;                          // fp32 columns per k-block
 constexpr int kATileBytes = kTileRows * kBlockK * 4; // 16 KB
 constexpr int kNormRing = 8;
 constexpr int kMaxStages = 8;
+constexpr int kMaxAccBufs = 8;                      // accumulator buffers in tensor memory (2, or 512 / queries-per-pass in emit mode)
 constexpr int kPrefetchAhead = 12;                  // bank k-blocks pulled into L2 ahead of the smem ring
 constexpr int kSetKBlocks = 32;
 // filter epilogue: hit queue entries; the same words hold the dense [16][128] score tile (8 KB), so >= 1024
@@ -371,7 +372,7 @@ __host__ __device__ inline SmemLayout tc_layout(int stages, int qp, int kcap, in
   L.scratch = off; off += hit_cap(qp) * 8;               // hit queue / dense [16][128] score tile (MULTI: score tile [HQ][128], same size)
   L.norms = off; off += qp > 128 ? 0 : kNormRing * kTileRows * 4;         // (256 queries per pass: cached row norms only)
   off = (off + 7) & ~7u;
-  L.bars = off;  off += (4 * kMaxStages + 4) * 8;        // full_tma, full_split, empty, peer_full (pairs), tmem_full/empty
+  L.bars = off;  off += (4 * kMaxStages + 2 * kMaxAccBufs) * 8;   // full_tma, full_split, empty, peer_full (pairs), tmem_full/empty
   L.tmem_slot = off; off += 16;
   L.total = off;
   return L;
@@ -900,7 +901,7 @@ __device__ __forceinline__ void filt_service(const TcParams& p, const FiltState 
 template <int QP>
 __device__ __forceinline__ void emit_epilogue(const TcParams& p, const FiltState st, const float* norms, bool norm_warps,
                                               uint32_t tmem_base, uint64_t* tmem_full, uint64_t* tmem_empty, int tile0,
-                                              int tile_step, int n_my, int q0, int nq_pass, int e, int lane,
+                                              int tile_step, int n_my, int q0, int nq_pass, int e, int lane, int n_acc,
                                               uint32_t tmem_empty_remote = 0u) {
   auto release_tmem = [&](int a) {
     if (tmem_empty_remote) mbar_arrive_cluster(tmem_empty_remote + uint32_t(a) * 8u);
@@ -929,11 +930,11 @@ __device__ __forceinline__ void emit_epilogue(const TcParams& p, const FiltState
   float ssq_next = ssq_of(0), rs_next = rs_of(0);
   for (int it = 0; it < n_my; ++it) {
     const int tile = tile0 + it * tile_step;
-    const int a = it & 1;
+    const int a = it % n_acc;
     const float ssq_cached = ssq_next, rs_cached = rs_next;
     ssq_next = ssq_of(it + 1);
     rs_next = rs_of(it + 1);
-    mbar_wait(&tmem_full[a], (it >> 1) & 1);
+    mbar_wait(&tmem_full[a], uint32_t(it / n_acc) & 1u);
     tc_fence_after();
     if (e == 0 && lane == 0) trace_at(p, 6, it);
     const int64_t grow = int64_t(tile) * kTileRows + row_in_tile;
@@ -1228,8 +1229,8 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap bank_map, const __grid_consta
   uint64_t* full_split = full_tma + kMaxStages;
   uint64_t* empty = full_split + kMaxStages;
   uint64_t* peer_full = empty + kMaxStages;        // pairs, leader only: the peer's stage s is loaded
-  uint64_t* tmem_full = peer_full + kMaxStages;    // [2]
-  uint64_t* tmem_empty = tmem_full + 2;            // [2]
+  uint64_t* tmem_full = peer_full + kMaxStages;    // [kMaxAccBufs]
+  uint64_t* tmem_empty = tmem_full + kMaxAccBufs;  // [kMaxAccBufs]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L.tmem_slot);
 
   // this CTA's share of the work
@@ -1277,7 +1278,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap bank_map, const __grid_consta
       mbar_init(&full_tma[s], 1); mbar_init(&full_split[s], 128); mbar_init(&empty[s], TWO_ISSUERS ? 2 : 1);
       mbar_init(&peer_full[s], 1);
     }
-    for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], TWO_ISSUERS ? 2 : 1); mbar_init(&tmem_empty[a], PAIR ? 256 : 128); }
+    for (int a = 0; a < kMaxAccBufs; ++a) { mbar_init(&tmem_full[a], TWO_ISSUERS ? 2 : 1); mbar_init(&tmem_empty[a], PAIR ? 256 : 128); }
     fence_barrier_init();
   }
   if (warp == 2) { if constexpr (PAIR) tmem_alloc_pair(tmem_slot, 512); else tmem_alloc(tmem_slot, 512); }
@@ -1304,6 +1305,12 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap bank_map, const __grid_consta
   const int boot = (SCANEPI && n_my >= 8 && tile_step >= p.k_true && p.gmax && !(p.flags & kDbgNoBoot) && !(FILT && p.emit)) ? 1 : 0;
   const int n_iter = n_my + boot;
   auto tile_at = [&](int it) { return tile0 + (it < n_my ? it : it - n_my) * tile_step; };
+  // Accumulator buffers.  Two everywhere -- except in emit mode, where the epilogue's first tile waits ~20 us for the
+  // first threshold exchange: with 512 / QP buffers (8 at 64 queries per pass) the MMA pipeline runs up to seven tiles
+  // ahead instead of stalling behind that wait, and the epilogue (2.7 k cycles per tile against a 7 k tile period)
+  // catches up afterwards.
+  // (in-kernel norm warps keep a ring of kNormRing tiles of row norms: the epilogue must not fall further behind)
+  const int n_acc = (FILT && p.emit && !(p.flags & kDbgNoBoot)) ? min(norm_warps ? 4 : kMaxAccBufs, 512 / QP) : 2;
   const int set_kb = FILT ? nkb : kSetKBlocks;           // k-blocks accumulated inside the tensor core
   const int nsets = (nkb + set_kb - 1) / set_kb;         // accumulation units per tile (1 unless MULTI)
 
@@ -1357,9 +1364,10 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap bank_map, const __grid_consta
       for (int it = 0; it < n_iter; ++it) {
         const int tile = tile_at(it); (void)tile;
         for (int set = 0; set < nsets; ++set, ++unit) {
-          const int a = unit & 1;
-          if constexpr (PAIR) mbar_wait_cluster(&tmem_empty[a], ((unit >> 1) & 1) ^ 1);   // both CTAs' epilogues
-          else mbar_wait(&tmem_empty[a], ((unit >> 1) & 1) ^ 1);
+          const int a = int(unit % uint32_t(n_acc));
+          const uint32_t a_par = (unit / uint32_t(n_acc)) & 1u;
+          if constexpr (PAIR) mbar_wait_cluster(&tmem_empty[a], a_par ^ 1);   // both CTAs' epilogues
+          else mbar_wait(&tmem_empty[a], a_par ^ 1);
           tc_fence_after();
           const uint32_t d = tmem_base + uint32_t(a) * kAccCols;
           const int kb_end = min(nkb, (set + 1) * set_kb);
@@ -1516,7 +1524,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap bank_map, const __grid_consta
     // ===== epilogue warps, long scan without lists: survivors straight to the global candidate array =====
     if constexpr (FILT)
       emit_epilogue<QP>(p, st, norms, norm_warps, tmem_base, tmem_full, tmem_empty, tile0, tile_step, n_my, q0, nq_pass, warp - 8, lane,
-                        (PAIR && !leader) ? mapa_u32(smem_u32(&tmem_empty[0]), 0u) : 0u);
+                        n_acc, (PAIR && !leader) ? mapa_u32(smem_u32(&tmem_empty[0]), 0u) : 0u);
   } else if (warp >= 8 && SCANEPI) {
     // ===== epilogue warps: scan + hit queue (filt_epilogue) =====
     filt_epilogue<QP, FILT ? 1 : 3>(p, st, lists, norms, norm_warps, tmem_base, tmem_full, tmem_empty, tile0, tile_step, n_my, boot,
