@@ -223,8 +223,13 @@ static int tc_pipeline(Scratch* s, const SearchArgs& a, int mode, FilterSide* si
   const int64_t n_tiles_all = (a.n_rows + 127) / 128;
   const bool oneshot = side != nullptr && side->ocand != nullptr && !need && n_tiles_all <= s->sm_count &&
                        n_tiles_all >= a.top_k && a.top_k <= 64 && !(a.flags & (DEVQA_DEBUG_FILTER_ONLY | DEVQA_DEBUG_NO_ONESHOT));
+  // Long scans whose candidates refine would otherwise pick out of the per-CTA lists: no lists at all, survivors go
+  // straight to the flat candidate array (scan_tc.cu emit_epilogue).  Needs the threshold exchange (>= top_k CTAs per
+  // pass; a long scan runs one pass per launch on every SM).
+  const bool emit = side != nullptr && side->ocand != nullptr && !oneshot && !need && !side->merge &&
+                    s->sm_count >= a.top_k && n_tiles_all >= s->sm_count && !(a.flags & (DEVQA_DEBUG_FILTER_ONLY | DEVQA_DEBUG_NO_EMIT));
   if ((rc = scan_tc_plan(mode, int(a.n_queries), a.dim, kcap, cached_norms, n_tiles_all, s->sm_count, a.flags,
-                         &qp, &stages, &pair, oneshot)))
+                         &qp, &stages, &pair, oneshot, emit)))
     return rc;
   const int q_pad = int((a.n_queries + qp - 1) / qp) * qp;
   const size_t qcat_bytes = scan_tc_qcat_bytes(mode, a.dim, q_pad);
@@ -244,10 +249,7 @@ static int tc_pipeline(Scratch* s, const SearchArgs& a, int mode, FilterSide* si
   int ctas_per_pass = s->sm_count / side_by;
   if (ctas_per_pass > tiles_cap) ctas_per_pass = tiles_cap;
   if (ctas_per_pass < 1) ctas_per_pass = 1;
-  // Long scans whose candidates refine would otherwise pick out of the per-CTA lists: no lists at all, survivors go
-  // straight to the flat candidate array (scan_tc.cu emit_epilogue).  Needs the threshold exchange (>= top_k CTAs).
-  const bool emit = side != nullptr && side->ocand != nullptr && !oneshot && !need && !side->merge &&
-                    ctas_per_pass >= a.top_k && tiles >= s->sm_count && !(a.flags & (DEVQA_DEBUG_FILTER_ONLY | DEVQA_DEBUG_NO_EMIT));
+  if (emit) DEVQA_REQUIRE(ctas_per_pass >= a.top_k, "emit scan: fewer CTAs per pass than top_k");
   if (oneshot) {                                             // one CTA per tile; as many passes per launch as fit
     ctas_per_pass = int(tiles);
     side_by = s->sm_count / ctas_per_pass;

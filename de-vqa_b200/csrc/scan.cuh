@@ -91,7 +91,7 @@ __host__ __device__ inline float tc_filter_relerr(int64_t dim, bool bf16_bank = 
 constexpr unsigned kFlagShadowScan = 1u << 14;
 bool scan_tc_supported(int bank_dtype, const void* bank, int64_t dim, int64_t bank_ld, int top_k);
 int scan_tc_plan(int mode, int n_queries, int64_t dim, int kcap, bool cached_norms, int64_t n_tiles, int sm_count,
-                 unsigned flags, int* qp_out, int* stages_out, bool* pair_out, bool oneshot = false);
+                 unsigned flags, int* qp_out, int* stages_out, bool* pair_out, bool oneshot = false, bool emit = false);
 constexpr int kOneshotCap = 512;       // candidates per query the one-shot scan can emit (refine's first-cut capacity)
 constexpr int kEmitCap = 128;          // candidates per (CTA, query) a long scan can emit (everything that ever beat the running
                                        // threshold: ~1500 per query over 148 CTAs with a bf16 shadow, far fewer with the fp16 one)

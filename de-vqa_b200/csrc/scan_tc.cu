@@ -84,7 +84,7 @@ constexpr int kSetKBlocks = 32;
 // filter epilogue: hit queue entries; the same words hold the dense [16][128] score tile (8 KB), so >= 1024
 __host__ __device__ constexpr int hit_cap(int qp) { return (qp > 128 || qp < 32) ? 1024 : 2048; }
 // undocumented debugging bits of `flags` (performance bisection only; results are wrong when set)
-constexpr unsigned kDbgNoInsert = 1u << 16, kDbgNoSplit = 1u << 17, kDbgNoMma2 = 1u << 18, kDbgNoQueryTma = 1u << 19, kDbgL2Prefetch = 1u << 20, kDbgNoBoot = 1u << 23, kDbgNoPair = 1u << 28, kDbgPairAll = 1u << 29, kDbgNoMma1 = 1u << 30;                     // k-blocks (of 32 columns) accumulated inside the tensor core
+constexpr unsigned kDbgNoInsert = 1u << 16, kDbgNoSplit = 1u << 17, kDbgNoMma2 = 1u << 18, kDbgNoQueryTma = 1u << 19, kDbgL2Prefetch = 1u << 20, kDbgNoBoot = 1u << 23, kDbgNoPair = 1u << 28, kDbgOneEpiGroup = 1u << 4, kDbgNoEvictFirst = 1u << 5, kDbgPairAll = 1u << 29, kDbgNoMma1 = 1u << 30;                     // k-blocks (of 32 columns) accumulated inside the tensor core
 
 // ---- PTX wrappers ---------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return uint32_t(__cvta_generic_to_shared(p)); }
@@ -123,6 +123,33 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, u
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+// Bank tiles are read once per pass: evict-first keeps them from pushing the query operand (re-read by every CTA for every
+// tile) and the kernel's own instructions out of L2.
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void tma_load_2d_hint(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, uint64_t pol) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "l"(pol)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair_hint(void* dst, const CUtensorMap* map, uint32_t leader_bar, int c0, int c1, uint64_t pol) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(leader_bar), "r"(c0), "r"(c1), "l"(pol)
+      : "memory");
+}
+// CTA pairs: the load lands in THIS CTA's shared memory, its bytes are counted on the LEADER's barrier (a shared::cluster
+// address) -- the MMA issuer waits on one barrier for both halves of a stage, nobody has to forward anything
+__device__ __forceinline__ void tma_load_2d_pair(void* dst, const CUtensorMap* map, uint32_t leader_bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(leader_bar), "r"(c0), "r"(c1)
       : "memory");
 }
 // contiguous global -> shared bulk copy (one request, no per-row tensor traversal)
@@ -208,6 +235,8 @@ __device__ __forceinline__ void tmem_ld<16>(uint32_t addr, uint32_t (&r)[16]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void epilogue_barrier() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+// (emit mode with two column groups of epilogue warps: 256 threads)
+__device__ __forceinline__ void epilogue_barrier_n(int threads) { asm volatile("bar.sync 1, %0;" ::"r"(threads) : "memory"); }
 
 // ---- CTA-pair (cta_group::2) helpers ------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
@@ -349,6 +378,7 @@ struct TcParams {
   int32_t ocap;
   IdMap idmap;
   long long* trace;        // optional [16][256] clock64 samples of CTA 0's roles (devqa_debug_tc_trace)
+  CUtensorMap qmap;        // CTA pairs: the query operand as [rows of 128 bytes] (each CTA loads its half of a k-block)
 };
 
 // Role timeline tracing (tools/tc_trace.py) is compiled in only with -DDEVQA_TC_TRACE.
@@ -902,22 +932,29 @@ template <int QP>
 __device__ __forceinline__ void emit_epilogue(const TcParams& p, const FiltState st, const float* norms, bool norm_warps,
                                               uint32_t tmem_base, uint64_t* tmem_full, uint64_t* tmem_empty, int tile0,
                                               int tile_step, int n_my, int q0, int nq_pass, int e, int lane, int n_acc,
-                                              uint32_t tmem_empty_remote = 0u) {
+                                              uint32_t tmem_empty_remote, int g, int ng) {
+  // ng = 2: a second set of four warps (g = 1: warps 4-7, idle when row norms are cached) takes the upper half of the
+  // accumulator columns.  A warp reaches only the 32 tensor-memory lanes of its quarter, so more warps can only split
+  // COLUMNS -- which is what a 256-query pass needs: one thread per row compared 256 scores per tile, 10.8 k cycles
+  // against 6.1 k of tensor-core time.
+  const int nthr = 128 * ng;
+  const int c_lo = g * (QP / ng), c_hi = c_lo + QP / ng;
+  auto ebar = [&]() { if (ng == 1) epilogue_barrier(); else epilogue_barrier_n(nthr); };
   auto release_tmem = [&](int a) {
     if (tmem_empty_remote) mbar_arrive_cluster(tmem_empty_remote + uint32_t(a) * 8u);
     else mbar_arrive(&tmem_empty[a]);
   };
   const int row_in_tile = e * 32 + lane;
-  const int tid = e * 32 + lane;
+  const int tid = g * 128 + e * 32 + lane;
   const bool dot_mode = !(p.flags & DEVQA_NORMALIZE_BANK);
   uint32_t* const best_s = st.hit_id;                                  // [QP] best upper bound this CTA has emitted, per query
   uint32_t* const pub_s = st.hit_id + QP;                              // [QP] what gmax holds
   uint32_t* const cnt_s = st.hit_id + 2 * QP;                          // [QP] candidates this CTA has emitted, per query
-  for (int j = tid; j < QP; j += 128) { best_s[j] = 0u; pub_s[j] = 0u; cnt_s[j] = 0u; }
+  for (int j = tid; j < QP; j += nthr) { best_s[j] = 0u; pub_s[j] = 0u; cnt_s[j] = 0u; }
   // this CTA's own region of the candidate array: [n_queries][ocap] -- private counters in shared memory, plain global
   // stores, nothing to wait for (a global atomicAdd per survivor stalled the finding thread for a full round trip)
   uint64_t* const my_cand = p.ocand + size_t(tile0) * p.n_queries * p.ocap;
-  epilogue_barrier();
+  ebar();
   auto ssq_of = [&](int it) {
     const int64_t g = int64_t(tile0 + it * tile_step) * kTileRows + row_in_tile;
     return (!norm_warps && it < n_my && g < p.n_rows) ? __ldg(p.row_sumsq + g) : 1.f;
@@ -936,7 +973,7 @@ __device__ __forceinline__ void emit_epilogue(const TcParams& p, const FiltState
     rs_next = rs_of(it + 1);
     mbar_wait(&tmem_full[a], uint32_t(it / n_acc) & 1u);
     tc_fence_after();
-    if (e == 0 && lane == 0) trace_at(p, 6, it);
+    if (tid == 0) trace_at(p, 6, it);
     const int64_t grow = int64_t(tile) * kTileRows + row_in_tile;
     const bool row_live = grow < p.n_rows && !(p.flags & kDbgNoInsert);
     float inv = 1.f, rowfac = 1.f;
@@ -967,7 +1004,7 @@ __device__ __forceinline__ void emit_epilogue(const TcParams& p, const FiltState
     if (it == 0) {
       // ---- first tile, pass A: each query's best upper bound -> exchange; then a bounded wait for the thresholds ----
 #pragma unroll 1
-      for (int c = 0; c < QP; c += 16) {
+      for (int c = c_lo; c < c_hi; c += 16) {
         uint32_t d[16];
         float u[16];
         tmem_ld<16>(taddr + uint32_t(c), d);
@@ -984,25 +1021,25 @@ __device__ __forceinline__ void emit_epilogue(const TcParams& p, const FiltState
         }
         if (lane < 16) atomicMax(best_s + c + lane, mine);
       }
-      epilogue_barrier();
+      ebar();
       if (tid == 0) trace_at(p, 9, 0);
-      for (int j = tid; j < nq_pass; j += 128) {
+      for (int j = tid; j < nq_pass; j += nthr) {
         const uint32_t b = best_s[j];
         pub_s[j] = b;
         p.gmax[size_t(q0 + j) * p.gmax_stride + tile0] = b;
       }
       if (p.gbar) {                                                    // tell the service warps: this CTA's bests are in gmax
         __threadfence();
-        epilogue_barrier();
+        ebar();
         if (tid == 0) atomicAdd(p.gbar + 2 * (p.q0 / p.qp + int(blockIdx.x) % p.passes), 1u);
       }
       if (tid == 0) trace_at(p, 10, 0);
-      for (int j = tid; j < nq_pass; j += 128) {
+      for (int j = tid; j < nq_pass; j += nthr) {
         const long long t0 = clock64();                                // (no thresholds: every row would be a candidate)
         while (*reinterpret_cast<volatile float*>(st.thr_ext + j) == -INFINITY && clock64() - t0 < 400000) __nanosleep(200);
         st.thr[j] = fmaxf(st.thr[j], *reinterpret_cast<volatile float*>(st.thr_ext + j));
       }
-      epilogue_barrier();
+      ebar();
       if (tid == 0) trace_at(p, 11, 0);
     }
     // ---- scan: 16 accumulators at a time, the next tensor-memory load in flight while these are compared ----
@@ -1033,17 +1070,17 @@ __device__ __forceinline__ void emit_epilogue(const TcParams& p, const FiltState
     };
     {
       uint32_t da[16], db[16];
-      tmem_ld<16>(taddr, da);
+      tmem_ld<16>(taddr + uint32_t(c_lo), da);
 #pragma unroll 1
-      for (int c = 0; c < QP; c += 32) {
+      for (int c = c_lo; c < c_hi; c += 32) {
         float u[16];
         tmem_ld_wait();
-        if (c + 16 < QP) tmem_ld<16>(taddr + uint32_t(c + 16), db);
+        if (c + 16 < c_hi) tmem_ld<16>(taddr + uint32_t(c + 16), db);
         to_u(c, da, u);
         consume(c, u);
-        if (c + 16 < QP) {
+        if (c + 16 < c_hi) {
           tmem_ld_wait();
-          if (c + 32 < QP) tmem_ld<16>(taddr + uint32_t(c + 32), da);
+          if (c + 32 < c_hi) tmem_ld<16>(taddr + uint32_t(c + 32), da);
           to_u(c + 16, db, u);
           consume(c + 16, u);
         }
@@ -1053,16 +1090,16 @@ __device__ __forceinline__ void emit_epilogue(const TcParams& p, const FiltState
     release_tmem(a);                                                   // this thread's reads of the buffer are done
     // ---- thresholds from the service warp; this CTA's bests to the exchange.  No barrier: thr only ever rises, and a
     // reader that still sees the old word merely emits a candidate more ----
-    for (int j = tid; j < nq_pass; j += 128) {
+    for (int j = tid; j < nq_pass; j += nthr) {
       st.thr[j] = fmaxf(st.thr[j], st.thr_ext[j]);
       const uint32_t b = best_s[j];
       if (b != pub_s[j]) { pub_s[j] = b; p.gmax[size_t(q0 + j) * p.gmax_stride + tile0] = b; }
     }
-    if (e == 0 && lane == 0) trace_at(p, 7, it);
+    if (tid == 0) trace_at(p, 7, it);
   }
-  epilogue_barrier();
-  if (e == 0 && lane == 0) *reinterpret_cast<volatile uint32_t*>(st.qn + 2) = 1u;   // service warp: stop
-  for (int j = tid; j < nq_pass; j += 128) {
+  ebar();
+  if (tid == 0) *reinterpret_cast<volatile uint32_t*>(st.qn + 2) = 1u;   // service warp: stop
+  for (int j = tid; j < nq_pass; j += nthr) {
     const uint32_t cnt = cnt_s[j];
     p.ocount[size_t(tile0) * p.n_queries + q0 + j] = cnt < uint32_t(p.ocap) ? cnt : uint32_t(p.ocap);
     // nothing is ever lost -- unless this CTA's region overflowed: then "anything may be missing" (NaN code: refine
@@ -1215,7 +1252,9 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap bank_map, const __grid_consta
   constexpr int kParts = BF ? 3 : (FILT ? 1 : 2);        // row groups of the query operand per k-block
   constexpr int kElemsK = BFD ? 64 : 32;                 // bank columns per k-block (always 128 bytes)
   static_assert(!PAIR || (FILT && QP >= 64), "CTA pairs: filter variant, 64+ queries per pass");
-  const SmemLayout L = tc_layout(p.stages, p.qp, p.kcap, kParts, PAIR);
+  // (emit and one-shot mode keep no per-CTA lists: the space goes to ring stages, see scan_tc_plan)
+  const int list_cap = (FILT && (p.emit || p.oneshot)) ? 0 : p.kcap;
+  const SmemLayout L = tc_layout(p.stages, p.qp, list_cap, kParts, PAIR);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int S = p.stages;
   constexpr int kBRows = PAIR ? QP / 2 : QP;             // query rows of the operand in THIS CTA's shared memory
@@ -1246,7 +1285,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap bank_map, const __grid_consta
   }
 
   // ---- one-time setup ------------------------------------------------------------------------
-  for (int i = threadIdx.x; i < QP * p.kcap; i += kTcThreads) lists[i] = kEmptyKey;
+  for (int i = threadIdx.x; i < QP * list_cap; i += kTcThreads) lists[i] = kEmptyKey;
   FiltState st{};
   float maxn = 1.f;                                      // un-normalised scores: E scales with ||row|| <= maxn
   if constexpr (SCANEPI) {
@@ -1273,12 +1312,21 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap bank_map, const __grid_consta
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&bank_map);
   }
+  // bf16 banks with cached row norms need no pass over the tile by CUDA cores at all; the filter variant
+  // needs ||row||^2 either way (normalised scores, or max ||row|| for the error bound of plain dot scores)
+  const bool norm_warps = FILT ? p.row_sumsq == nullptr
+                               : !(BF && (p.row_sumsq != nullptr || !(p.flags & DEVQA_NORMALIZE_BANK)));
+  // emit mode, 128+ queries per pass, cached norms: warps 4-7 are a second group of epilogue warps (emit_epilogue)
+  const int epi_groups = (FILT && QP >= 128 && p.emit && !norm_warps && !(p.flags & kDbgOneEpiGroup)) ? 2 : 1;
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < S; ++s) {
       mbar_init(&full_tma[s], 1); mbar_init(&full_split[s], 128); mbar_init(&empty[s], TWO_ISSUERS ? 2 : 1);
       mbar_init(&peer_full[s], 1);
     }
-    for (int a = 0; a < kMaxAccBufs; ++a) { mbar_init(&tmem_full[a], TWO_ISSUERS ? 2 : 1); mbar_init(&tmem_empty[a], PAIR ? 256 : 128); }
+    for (int a = 0; a < kMaxAccBufs; ++a) {
+      mbar_init(&tmem_full[a], TWO_ISSUERS ? 2 : 1);
+      mbar_init(&tmem_empty[a], uint32_t((PAIR ? 256 : 128) * epi_groups));
+    }
     fence_barrier_init();
   }
   if (warp == 2) { if constexpr (PAIR) tmem_alloc_pair(tmem_slot, 512); else tmem_alloc(tmem_slot, 512); }
@@ -1291,10 +1339,6 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap bank_map, const __grid_consta
   constexpr uint32_t kAccCols = FILT ? QP : 3 * QP;
   const uint32_t tmem_alo = tmem_base + 2 * kAccCols;
   const int nkb = p.n_kblocks;
-  // bf16 banks with cached row norms need no pass over the tile by CUDA cores at all; the filter variant
-  // needs ||row||^2 either way (normalised scores, or max ||row|| for the error bound of plain dot scores)
-  const bool norm_warps = FILT ? p.row_sumsq == nullptr
-                               : !(BF && (p.row_sumsq != nullptr || !(p.flags & DEVQA_NORMALIZE_BANK)));
   // Tile sequence of this CTA: its strided tiles, then (filter variant, 8+ tiles) the first tile AGAIN: on its
   // first visit the epilogue only learns each query's best upper bound from it (thresholds for everyone through
   // the service warps) and waits a bounded moment for them; on the second visit it is a tile like any other --
@@ -1323,6 +1367,9 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap bank_map, const __grid_consta
       const bool pf_on = (p.flags & kDbgL2Prefetch) != 0;
       const bool qtma = !(p.flags & kDbgNoQueryTma);
       const uint32_t tx_bytes = kATileBytes + (qtma ? b_stage_bytes : 0u);
+      const bool ef = !(p.flags & kDbgNoEvictFirst);
+      const uint64_t pol = l2_policy_evict_first();
+      const uint32_t leader_full0 = PAIR ? mapa_u32(smem_u32(&full_tma[0]), 0u) : 0u; (void)leader_full0;
       int pf_it = 0, pf_kb = 0;                           // next k-block to prefetch
       auto prefetch_next = [&]() {
         if (pf_it < n_iter) {
@@ -1339,11 +1386,22 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap bank_map, const __grid_consta
           prefetch_next();
           mbar_wait(&empty[r.s], r.phase ^ 1u);
           trace_at(p, 1, trace_it);
-          mbar_expect_tx(&full_tma[r.s], tx_bytes);
-          tma_load_2d(smem + L.a_raw + r.s * kATileBytes, &bank_map, &full_tma[r.s], kb * kElemsK, tile * kTileRows);
-          if (qtma)     // the whole [2QP x 32] query k-block is contiguous (and pre-swizzled) in global memory
-            bulk_load(smem + L.bq + r.s * b_stage_bytes, qcat + size_t(kb) * (kParts * QP * 32) + size_t(pair_rank) * (kBRows * 32),
-                      b_stage_bytes, &full_tma[r.s]);               // (pairs: this CTA's half of the rows)
+          if constexpr (PAIR) {
+            // both CTAs' bytes complete on the leader's barrier (the leader expects twice a stage)
+            const uint32_t lbar = leader_full0 + uint32_t(r.s) * 8u;
+            if (leader) mbar_expect_tx(&full_tma[r.s], 2u * tx_bytes);
+            if (ef) tma_load_2d_pair_hint(smem + L.a_raw + r.s * kATileBytes, &bank_map, lbar, kb * kElemsK, tile * kTileRows, pol);
+            else tma_load_2d_pair(smem + L.a_raw + r.s * kATileBytes, &bank_map, lbar, kb * kElemsK, tile * kTileRows);
+            if (qtma)   // this CTA's half of the k-block's query rows (pre-swizzled rows of 128 bytes)
+              tma_load_2d_pair(smem + L.bq + r.s * b_stage_bytes, &p.qmap, lbar, 0,
+                               (pass_local * nkb + kb) * (kParts * QP) + int(pair_rank) * kBRows);
+          } else {
+            mbar_expect_tx(&full_tma[r.s], tx_bytes);
+            if (ef) tma_load_2d_hint(smem + L.a_raw + r.s * kATileBytes, &bank_map, &full_tma[r.s], kb * kElemsK, tile * kTileRows, pol);
+            else tma_load_2d(smem + L.a_raw + r.s * kATileBytes, &bank_map, &full_tma[r.s], kb * kElemsK, tile * kTileRows);
+            if (qtma)     // the whole [2QP x 32] query k-block is contiguous (and pre-swizzled) in global memory
+              bulk_load(smem + L.bq + r.s * b_stage_bytes, qcat + size_t(kb) * (kParts * QP * 32), b_stage_bytes, &full_tma[r.s]);
+          }
           trace_at(p, 0, trace_it++);
           r.advance(S);
         }
@@ -1376,8 +1434,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap bank_map, const __grid_consta
             const uint32_t a_lo = a_lo0 + uint32_t(r.s) * (kATileBytes >> 4), b_lo = b_lo0 + uint32_t(r.s) * (b_stage_bytes >> 4);
             mbar_wait(&full_tma[r.s], r.phase);
             trace_at(p, 3, unit * uint32_t(nkb) + uint32_t(kb));
-            if constexpr (PAIR) mbar_wait_cluster(&peer_full[r.s], r.phase);     // ... and the peer's half
-            trace_at(p, 4, unit * uint32_t(nkb) + uint32_t(kb));
+            trace_at(p, 4, unit * uint32_t(nkb) + uint32_t(kb));            // (pairs: the barrier counts both CTAs' bytes)
             tc_fence_after();
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk) {              // four 32-byte K slices of the 128-byte rows
@@ -1428,21 +1485,6 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap bank_map, const __grid_consta
           }
           mma_commit(&tmem_full[a]);
         }
-      }
-    }
-  } else if (PAIR && !leader && warp >= 4 && warp < 8) {
-    // ===== pair, peer CTA: forward "stage s of my shared memory is loaded" to the leader's peer_full[s] =====
-    // One thread per stage residue: a cluster-scope release-arrive takes ~1500 cycles, a single forwarder would
-    // cap the ring at one k-block per that time (measured); four in flight keep up.
-    if (lane == 0) {
-      const uint32_t remote0 = mapa_u32(smem_u32(&peer_full[0]), 0u);
-      const int w = warp - 4;
-      const long long total = (long long)n_iter * nkb;
-      for (long long i = 0; i < total; ++i) {
-        const int st_i = int(i % S);
-        if ((st_i & 3) != w) continue;
-        mbar_wait(&full_tma[st_i], uint32_t((i / S) & 1));
-        mbar_arrive_cluster_relaxed(remote0 + uint32_t(st_i) * 8u);
       }
     }
   } else if (warp >= 4 && warp < 8 && norm_warps) {
@@ -1520,11 +1562,11 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap bank_map, const __grid_consta
     if constexpr (FILT)
       oneshot_epilogue<QP>(p, st, norms, norm_warps, tmem_base, tmem_full, tile0, tile_step, p.q0 / QP + pass_local, q0, nq_pass,
                            warp - 8, lane);
-  } else if (warp >= 8 && FILT && p.emit) {
+  } else if (FILT && p.emit && (warp >= 8 || (warp >= 4 && epi_groups == 2))) {
     // ===== epilogue warps, long scan without lists: survivors straight to the global candidate array =====
     if constexpr (FILT)
-      emit_epilogue<QP>(p, st, norms, norm_warps, tmem_base, tmem_full, tmem_empty, tile0, tile_step, n_my, q0, nq_pass, warp - 8, lane,
-                        n_acc, (PAIR && !leader) ? mapa_u32(smem_u32(&tmem_empty[0]), 0u) : 0u);
+      emit_epilogue<QP>(p, st, norms, norm_warps, tmem_base, tmem_full, tmem_empty, tile0, tile_step, n_my, q0, nq_pass, warp & 3, lane,
+                        n_acc, (PAIR && !leader) ? mapa_u32(smem_u32(&tmem_empty[0]), 0u) : 0u, warp >= 8 ? 0 : 1, epi_groups);
   } else if (warp >= 8 && SCANEPI) {
     // ===== epilogue warps: scan + hit queue (filt_epilogue) =====
     filt_epilogue<QP, FILT ? 1 : 3>(p, st, lists, norms, norm_warps, tmem_base, tmem_full, tmem_empty, tile0, tile_step, n_my, boot,
@@ -1880,19 +1922,26 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-int make_map(CUtensorMap* map, const void* base, bool bf16, uint64_t cols, uint64_t rows, uint64_t ld_bytes, uint32_t box_rows,
-             bool f16 = false) {
+EncodeTiledFn tensor_map_encoder() {
   static EncodeTiledFn encode = nullptr;
   if (!encode) {
     void* fn = nullptr;
     cudaDriverEntryPointQueryResult qres;
     cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
     if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) {
+      cudaGetLastError();
       set_error("cuTensorMapEncodeTiled is not available from the driver");
-      return DEVQA_E_CUDA;
+      return nullptr;
     }
     encode = reinterpret_cast<EncodeTiledFn>(fn);
   }
+  return encode;
+}
+
+int make_map(CUtensorMap* map, const void* base, bool bf16, uint64_t cols, uint64_t rows, uint64_t ld_bytes, uint32_t box_rows,
+             bool f16 = false) {
+  const EncodeTiledFn encode = tensor_map_encoder();
+  if (!encode) return DEVQA_E_CUDA;
   const cuuint64_t gdim[2] = {cols, rows};
   const cuuint64_t gstride[1] = {ld_bytes};
   const cuuint32_t box[2] = {bf16 ? 64u : 32u, box_rows};     // 128 bytes of columns either way
@@ -1903,6 +1952,24 @@ int make_map(CUtensorMap* map, const void* base, bool bf16, uint64_t cols, uint6
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed with CUresult %d (cols %llu rows %llu ld %llu)", int(r),
               (unsigned long long)cols, (unsigned long long)rows, (unsigned long long)ld_bytes);
+    return DEVQA_E_CUDA;
+  }
+  return DEVQA_OK;
+}
+
+// [rows][128 bytes], no swizzle (the query operand is stored pre-swizzled): box = box_rows whole rows
+int make_rows_map(CUtensorMap* map, const void* base, uint64_t rows, uint32_t box_rows) {
+  const EncodeTiledFn encode = tensor_map_encoder();
+  if (!encode) return DEVQA_E_CUDA;
+  const cuuint64_t gdim[2] = {128, rows ? rows : 1};
+  const cuuint64_t gstride[1] = {128};
+  const cuuint32_t box[2] = {128, box_rows};
+  const cuuint32_t estride[2] = {1, 1};
+  CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(base), gdim, gstride, box, estride,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (query operand) failed with CUresult %d (rows %llu)", int(r), (unsigned long long)rows);
     return DEVQA_E_CUDA;
   }
   return DEVQA_OK;
@@ -1926,7 +1993,7 @@ size_t scan_tc_qcat_bytes(int mode, int64_t dim, int q_pad) {
 
 // Queries per pass + pipeline depth that fit in shared memory / tensor memory for this list capacity.
 int scan_tc_plan(int mode, int n_queries, int64_t dim, int kcap, bool cached_norms, int64_t n_tiles, int sm_count,
-                 unsigned flags, int* qp_out, int* stages_out, bool* pair_out, bool oneshot) {
+                 unsigned flags, int* qp_out, int* stages_out, bool* pair_out, bool oneshot, bool emit) {
   *pair_out = false;
   const bool filt = mode == kTcTf32x1 || mode == kTcBf16x1;
   // more than one K-set (1024 fp32 / 2048 bf16 columns) sums K-sets in the epilogue's registers (MULTI):
@@ -1947,12 +2014,12 @@ int scan_tc_plan(int mode, int n_queries, int64_t dim, int kcap, bool cached_nor
   }
   for (; qp >= 16; qp >>= 1) {
     // 256 queries per pass on a long scan: CTA pairs (each CTA holds half of the query operand)
-    const bool pair = filt && cached_norms && (qp == 256 || (qp >= 64 && mode == kTcTf32x1 && (flags & kDbgPairAll))) &&
+    const bool pair = filt && cached_norms && (qp == 256 || (qp >= 64 && (flags & kDbgPairAll))) &&
                       n_tiles >= 2 * int64_t(sm_count) && sm_count % 2 == 0 && !(flags & kDbgNoPair);
     for (int stages = kMaxStages; stages >= 3; --stages) {
       // TMEM: 2 accumulator buffers of 3*qp (filter: qp) columns (+ one 32-column lo tile per stage for 3xTF32)
       if ((filt ? 2 : 6) * qp + (mode == kTcTf32x3 ? stages * kBlockK : 0) > 512) continue;
-      if (tc_layout(stages, qp, kcap, mode_parts(mode), pair).total + 1024 <= 225 * 1024) {
+      if (tc_layout(stages, qp, (filt && (oneshot || emit)) ? 0 : kcap, mode_parts(mode), pair).total + 1024 <= 225 * 1024) {
         *qp_out = qp; *stages_out = stages; *pair_out = pair;
         return DEVQA_OK;
       }
@@ -2019,7 +2086,12 @@ int scan_tc_launch(const ScanParams& sp, int mode, const void* qcat, uint32_t* g
   // pass index = q0 / qp; one pass = n_kblocks * parts * qp rows of 128 bytes (32 words)
   p.qcat = static_cast<const float*>(qcat) + size_t(sp.q0 / qp) * size_t(n_kblocks) * parts * qp * 32;
   p.trace = g_tc_trace;
-  const size_t smem = tc_layout(stages, qp, sp.kcap, parts, pair).total + 1024;
+  if (pair) {
+    // the query operand as a matrix of 128-byte rows: [passes x k-blocks x qp]; each CTA of a pair loads qp/2 rows per stage
+    const uint64_t q_rows = uint64_t((sp.n_queries - sp.q0 + qp - 1) / qp) * uint64_t(n_kblocks) * uint64_t(parts * qp);
+    if ((rc = make_rows_map(&p.qmap, p.qcat, q_rows, uint32_t(qp / 2)))) return rc;
+  }
+  const size_t smem = tc_layout(stages, qp, (filt && (sp.oneshot || sp.emit)) ? 0 : sp.kcap, parts, pair).total + 1024;
   const bool multi = !filt && p.n_kblocks > kSetKBlocks;
   void (*kern)(CUtensorMap, TcParams) = nullptr;
   if (mode == kTcTf32x3) {
@@ -2043,8 +2115,8 @@ int scan_tc_launch(const ScanParams& sp, int mode, const void* qcat, uint32_t* g
   if (pair) {
     DEVQA_REQUIRE(filt && qp >= 64 && passes == 1 && grid % 2 == 0, "tcgen05 scan: bad CTA-pair launch");
     if (mode == kTcBf16x1) {
-      DEVQA_REQUIRE(qp == 256, "tcgen05 scan: bf16 CTA pairs run 256 queries per pass");
-      kern = scan_tc_kernel<256, false, kBf16x1, true>;
+      kern = qp == 256 ? scan_tc_kernel<256, false, kBf16x1, true> : qp == 128 ? scan_tc_kernel<128, false, kBf16x1, true>
+                                                                                : scan_tc_kernel<64, false, kBf16x1, true>;
     } else {
       kern = qp == 256 ? scan_tc_kernel<256, false, kTf32x1, true> : qp == 128 ? scan_tc_kernel<128, false, kTf32x1, true>
                                                                                 : scan_tc_kernel<64, false, kTf32x1, true>;

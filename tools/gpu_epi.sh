@@ -1,0 +1,8 @@
+cd $GRAFT_REPO_ROOT
+mkdir -p gpurun_out
+timeout 1500 python -m pytest tests/test_gpu_filter.py tests/test_gpu_fullsize.py tests/test_gpu_tc.py -q -m gpu -x --timeout=900 > gpurun_out/pytest_epi.log 2>&1
+echo "pytest exit $?" >> gpurun_out/pytest_epi.log
+tail -5 gpurun_out/pytest_epi.log
+timeout 600 python tools/ab_epi.py 1250000 64,128,256,1024 2>&1 | tee gpurun_out/ab_epi_1250k.txt
+timeout 900 python tools/ab_epi.py 10000000 64,128,256,1024 1 2>&1 | tee gpurun_out/ab_epi_10m.txt
+timeout 900 python tools/ab_epi.py 10000000 64,128 0 2>&1 | tee -a gpurun_out/ab_epi_10m.txt

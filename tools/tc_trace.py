@@ -39,4 +39,5 @@ if n_rec > 8:
         if lo < n_rec:
             h = min(hi, n_rec)
             print(f"tiles {lo:3d}-{h:3d}: epilogue cycles/tile {dur[lo:h].mean():8.0f}  tile period {per[lo:h - 1].mean() if h - 1 > lo else 0:8.0f}  slow calls (warp 0)/tile {slow[lo:h].mean():5.2f}")
+    print(f"recorded tiles {n_rec}: first accumulator ready at {int(got[m][0]) - t0}, last epilogue done at {int(done[m][-1]) - t0} cycles after the producer's first issue")
     print("first tiles: epilogue cycles", " ".join(str(int(x)) for x in dur[:12]), "| slow calls", " ".join(str(int(x)) for x in slow[:12]))
