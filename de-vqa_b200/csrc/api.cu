@@ -216,7 +216,7 @@ static int tc_pipeline(Scratch* s, const SearchArgs& a, int mode, FilterSide* si
   const int list_k = side ? kcap : a.top_k;                 // entries a list keeps
   const bool cached_norms = a.row_sumsq != nullptr;
   int qp = 0, stages = 0;
-  bool pair = false;
+  bool pair = false, resident = false;
   // Short scans on the filter path: every CTA owns ONE tile, thresholds come from a grid-wide exchange of the tiles'
   // bests, candidates go straight to a global array (scan_tc.cu, oneshot_epilogue).  Needs at least top_k tiles (T is the
   // top_k-th largest of the tiles' bests) and all of them resident at once.
@@ -229,7 +229,7 @@ static int tc_pipeline(Scratch* s, const SearchArgs& a, int mode, FilterSide* si
   const bool emit = side != nullptr && side->ocand != nullptr && !oneshot && !need && !side->merge &&
                     s->sm_count >= a.top_k && n_tiles_all >= s->sm_count && !(a.flags & (DEVQA_DEBUG_FILTER_ONLY | DEVQA_DEBUG_NO_EMIT));
   if ((rc = scan_tc_plan(mode, int(a.n_queries), a.dim, kcap, cached_norms, n_tiles_all, s->sm_count, a.flags,
-                         &qp, &stages, &pair, oneshot, emit)))
+                         &qp, &stages, &pair, oneshot, emit, &resident)))
     return rc;
   const int q_pad = int((a.n_queries + qp - 1) / qp) * qp;
   const size_t qcat_bytes = scan_tc_qcat_bytes(mode, a.dim, q_pad);
@@ -272,6 +272,7 @@ static int tc_pipeline(Scratch* s, const SearchArgs& a, int mode, FilterSide* si
     side->emit = emit;
     side->ocap = oneshot ? kOneshotCap : kEmitCap;
     if (oneshot) { p.oneshot = 1; p.gbar = side->gbar; p.ocount = side->ocount; p.ocand = side->ocand; p.ocap = kOneshotCap; }
+    if (emit) p.b_resident = resident ? 1 : 0;
     if (emit) { p.emit = 1; p.gbar = side->gbar; p.ocount = side->ocount; p.ocand = side->ocand; p.ocap = kEmitCap; }   // [grid][Q] / [grid][Q][cap]
     if (emit) DEVQA_REQUIRE(n_passes <= 64, "emit scan: too many passes for the arrival counters");
   }
@@ -492,10 +493,20 @@ static int run_search(Scratch* s, const SearchArgs& a, uint64_t* out_keys, float
       // exit at once (the flags live on the device: no host round trip, graph-capturable).  The fallback's top-k
       // (3xTF32 scores) is then re-scored in the stream kernel's arithmetic like every other result, so scores
       // stay bit-identical across kernels, batch sizes and shardings even for flagged queries.
-      uint64_t* fkeys = side.akeys;                                      // [Q, top_k] keys; akeys is free again
-      if ((rc = tc_pipeline(s, ac, exact_mode, nullptr, side.need, fkeys, nullptr, nullptr, stream))) return rc;
+      // The fallback hands over a few rows MORE than top_k: two rows whose scores differ by less than the rounding
+      // difference between 3xTF32 and the stream kernel's fp32 sums may swap places across the cut, and the final
+      // selection has to be the stream kernel's.
+      uint64_t* fkeys = side.akeys;                                      // [Q, fk] keys; akeys is free again
+      SearchArgs af = ac;
+      int fk = a.top_k + 8;
+      if (fk > 128) fk = 128;
+      if (fk > kp) fk = kp;
+      if (int64_t(fk) > a.n_rows) fk = int(a.n_rows);
+      if (fk < a.top_k) fk = a.top_k;
+      af.top_k = fk;
+      if ((rc = tc_pipeline(s, af, exact_mode, nullptr, side.need, fkeys, nullptr, nullptr, stream))) return rc;
       RefineParams fr = rp;
-      fr.akeys = fkeys; fr.kp = a.top_k; fr.only_if = side.need; fr.lostu = nullptr; fr.n_lists = 0;
+      fr.akeys = fkeys; fr.kp = fk; fr.only_if = side.need; fr.lostu = nullptr; fr.n_lists = 0;
       if ((rc = refine_launch(fr, stream))) return rc;
     }
     return DEVQA_OK;

@@ -137,7 +137,8 @@ __global__ void __launch_bounds__(kRefineThreads) refine_kernel(const RefinePara
   const float prelim = s_prelim;
   for (int c = k1 + warp; c < p.kp; c += kRefineThreads / 32) {
     const uint64_t a = ak[c];
-    if (a != kEmptyKey && !(key_score(a) < prelim)) rescore(c);    // warp-uniform; NaN upper bounds are re-scored
+    // (after the exact fallback the keys are 3xTF32 scores, not upper bounds: its few surplus rows are all re-scored)
+    if (a != kEmptyKey && (p.only_if || !(key_score(a) < prelim))) rescore(c);    // warp-uniform; NaN upper bounds are re-scored
   }
   __syncthreads();
   rank_sort(ex, srt, p.kp <= 128 ? 128 : kMaxKp);                   // descending, empties last

@@ -46,6 +46,7 @@ struct ScanParams {
   // tcgen05 filter, one-shot mode (every CTA owns one tile; scan_tc.cu oneshot_epilogue)
   int32_t oneshot;
   int32_t emit;            // long scans: candidates to ocand instead of per-CTA lists (scan_tc.cu emit_epilogue)
+  int32_t b_resident;      // scan_tc_plan's choice: the pass's query operand stays in shared memory
   uint32_t* gbar;          // [2 * passes] zeroed arrival counters
   uint32_t* ocount;        // [n_queries] zeroed candidate counts
   uint64_t* ocand;         // [n_queries, ocap] candidates
@@ -91,7 +92,8 @@ __host__ __device__ inline float tc_filter_relerr(int64_t dim, bool bf16_bank = 
 constexpr unsigned kFlagShadowScan = 1u << 14;
 bool scan_tc_supported(int bank_dtype, const void* bank, int64_t dim, int64_t bank_ld, int top_k);
 int scan_tc_plan(int mode, int n_queries, int64_t dim, int kcap, bool cached_norms, int64_t n_tiles, int sm_count,
-                 unsigned flags, int* qp_out, int* stages_out, bool* pair_out, bool oneshot = false, bool emit = false);
+                 unsigned flags, int* qp_out, int* stages_out, bool* pair_out, bool oneshot = false, bool emit = false,
+                 bool* resident_out = nullptr);
 constexpr int kOneshotCap = 512;       // candidates per query the one-shot scan can emit (refine's first-cut capacity)
 constexpr int kEmitCap = 128;          // candidates per (CTA, query) a long scan can emit (everything that ever beat the running
                                        // threshold: ~1500 per query over 148 CTAs with a bf16 shadow, far fewer with the fp16 one)

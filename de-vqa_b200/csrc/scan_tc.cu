@@ -84,7 +84,7 @@ constexpr int kSetKBlocks = 32;
 // filter epilogue: hit queue entries; the same words hold the dense [16][128] score tile (8 KB), so >= 1024
 __host__ __device__ constexpr int hit_cap(int qp) { return (qp > 128 || qp < 32) ? 1024 : 2048; }
 // undocumented debugging bits of `flags` (performance bisection only; results are wrong when set)
-constexpr unsigned kDbgNoInsert = 1u << 16, kDbgNoSplit = 1u << 17, kDbgNoMma2 = 1u << 18, kDbgNoQueryTma = 1u << 19, kDbgL2Prefetch = 1u << 20, kDbgNoBoot = 1u << 23, kDbgNoPair = 1u << 28, kDbgOneEpiGroup = 1u << 4, kDbgNoEvictFirst = 1u << 5, kDbgPairAll = 1u << 29, kDbgNoMma1 = 1u << 30;                     // k-blocks (of 32 columns) accumulated inside the tensor core
+constexpr unsigned kDbgNoInsert = 1u << 16, kDbgNoSplit = 1u << 17, kDbgNoMma2 = 1u << 18, kDbgNoQueryTma = 1u << 19, kDbgL2Prefetch = 1u << 20, kDbgNoBoot = 1u << 23, kDbgNoPair = 1u << 28, kDbgOneEpiGroup = 1u << 4, kDbgNoEvictFirst = 1u << 5, kDbgNoResident = 1u << 6, kDbgPairAll = 1u << 29, kDbgNoMma1 = 1u << 30;                     // k-blocks (of 32 columns) accumulated inside the tensor core
 
 // ---- PTX wrappers ---------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return uint32_t(__cvta_generic_to_shared(p)); }
@@ -103,7 +103,22 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// Experiment knob (DEVQA_WAIT_HINT_NS): a suspend-time hint for every mbarrier wait of the scan kernel.  0 = the
+// hardware's default time limit.
+__constant__ uint32_t c_wait_hint_ns = 0;
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (c_wait_hint_ns) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "HWAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+        "@p bra HDONE_%=;\n\t"
+        "bra HWAIT_%=;\n\t"
+        "HDONE_%=:\n\t"
+        "}" ::"r"(smem_u32(bar)), "r"(parity), "r"(c_wait_hint_ns) : "memory");
+    return;
+  }
   asm volatile(
       "{\n\t"
       ".reg .pred p;\n\t"
@@ -378,6 +393,7 @@ struct TcParams {
   int32_t ocap;
   IdMap idmap;
   long long* trace;        // optional [16][256] clock64 samples of CTA 0's roles (devqa_debug_tc_trace)
+  int b_resident;          // filter, no pairs: the pass's whole query operand is loaded once and stays in shared memory
   CUtensorMap qmap;        // CTA pairs: the query operand as [rows of 128 bytes] (each CTA loads its half of a k-block)
 };
 
@@ -391,15 +407,17 @@ __device__ __forceinline__ void trace_at(const TcParams& p, int role, uint32_t i
 struct SmemLayout {        // byte offsets from the 1024-aligned base
   uint32_t a_raw, bq, lists, thr, scratch, norms, bars, tmem_slot, total;
 };
-__host__ __device__ inline SmemLayout tc_layout(int stages, int qp, int kcap, int b_parts = 2, bool pair = false) {
+// kcap = 0: a list-free mode (emit / one-shot) -- no lists and no hit queue, only three words per query of scratch.
+// b_kblocks > 0: the WHOLE query operand of the pass stays resident (b_kblocks k-blocks) instead of one k-block per stage.
+__host__ __device__ inline SmemLayout tc_layout(int stages, int qp, int kcap, int b_parts = 2, bool pair = false, int b_kblocks = 0) {
   SmemLayout L;
   uint32_t off = 0;
   L.a_raw = off; off += uint32_t(stages) * kATileBytes;
   // [parts*qp rows x 128 B], 1024-aligned since qp % 16 == 0; a CTA pair holds half of the query rows each
-  L.bq = off;    off += uint32_t(stages) * uint32_t(b_parts * (pair ? qp / 2 : qp)) * 128;
+  L.bq = off;    off += uint32_t(b_kblocks > 0 ? b_kblocks : stages) * uint32_t(b_parts * (pair ? qp / 2 : qp)) * 128;
   L.lists = off; off += uint32_t(qp) * kcap * 8;
   L.thr = off;   off += uint32_t(qp) * 20 + 16;                          // filter: eq / threshold / lost / service bound / query scale per query + counters
-  L.scratch = off; off += hit_cap(qp) * 8;               // hit queue / dense [16][128] score tile (MULTI: score tile [HQ][128], same size)
+  L.scratch = off; off += kcap == 0 ? uint32_t(qp) * 12 + 16 : hit_cap(qp) * 8;   // hit queue / dense [16][128] score tile (MULTI: score tile [HQ][128], same size)
   L.norms = off; off += qp > 128 ? 0 : kNormRing * kTileRows * 4;         // (256 queries per pass: cached row norms only)
   off = (off + 7) & ~7u;
   L.bars = off;  off += (4 * kMaxStages + 2 * kMaxAccBufs) * 8;   // full_tma, full_split, empty, peer_full (pairs), tmem_full/empty
@@ -1254,7 +1272,8 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap bank_map, const __grid_consta
   static_assert(!PAIR || (FILT && QP >= 64), "CTA pairs: filter variant, 64+ queries per pass");
   // (emit and one-shot mode keep no per-CTA lists: the space goes to ring stages, see scan_tc_plan)
   const int list_cap = (FILT && (p.emit || p.oneshot)) ? 0 : p.kcap;
-  const SmemLayout L = tc_layout(p.stages, p.qp, list_cap, kParts, PAIR);
+  const bool bres = FILT && !PAIR && p.b_resident != 0;
+  const SmemLayout L = tc_layout(p.stages, p.qp, list_cap, kParts, PAIR, bres ? p.n_kblocks : 0);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int S = p.stages;
   constexpr int kBRows = PAIR ? QP / 2 : QP;             // query rows of the operand in THIS CTA's shared memory
@@ -1293,7 +1312,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap bank_map, const __grid_consta
     st.eq = fs; st.thr = fs + QP; st.lost = fs + 2 * QP; st.thr_ext = fs + 3 * QP; st.qs = fs + 4 * QP;
     st.qn = reinterpret_cast<uint32_t*>(fs + 5 * QP);
     st.hit_u = reinterpret_cast<float*>(smem + L.scratch);
-    st.hit_id = reinterpret_cast<uint32_t*>(smem + L.scratch) + hit_cap(QP);
+    st.hit_id = reinterpret_cast<uint32_t*>(smem + L.scratch) + (list_cap ? hit_cap(QP) : 0);   // (list-free: best / published / count words only)
     if (FILT && !(p.flags & DEVQA_NORMALIZE_BANK)) maxn = sqrtf(__uint_as_float(*p.bank_max_sumsq));
     for (int j = threadIdx.x; j < QP; j += kTcThreads) {
       const bool live = j < nq_pass;
@@ -1366,8 +1385,17 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap bank_map, const __grid_consta
       // Q = 64 5.19 -> 4.90 ms, Q = 1024 31.8 -> 28.5 ms, 1M rows Q = 64 0.594 -> 0.524 ms.  Opt-in for experiments.)
       const bool pf_on = (p.flags & kDbgL2Prefetch) != 0;
       const bool qtma = !(p.flags & kDbgNoQueryTma);
-      const uint32_t tx_bytes = kATileBytes + (qtma ? b_stage_bytes : 0u);
-      const bool ef = !(p.flags & kDbgNoEvictFirst);
+      const uint32_t tx_bytes = kATileBytes + ((qtma && !bres) ? b_stage_bytes : 0u);
+      if (bres && qtma) {
+        // the query operand, once: every k-block of the pass (at 64 queries x 768 fp16 columns: 96 KB).  Streaming it
+        // with the stages made each SM pull 1.5x the bank's bytes out of L2 -- under the power cap (SM clock ~1.45 GHz)
+        // that, not HBM, set the tile period.
+        mbar_expect_tx(&peer_full[0], uint32_t(nkb) * b_stage_bytes);
+        for (int kb = 0; kb < nkb; ++kb)
+          bulk_load(smem + L.bq + kb * b_stage_bytes, qcat + size_t(kb) * (kParts * QP * 32), b_stage_bytes, &peer_full[0]);
+      }
+      // (a bank that fits in L2 should stay there between calls: C2 is 67-134 MB)
+      const bool ef = !(p.flags & kDbgNoEvictFirst) && int64_t(p.n_tiles) * nkb * int64_t(kATileBytes) > (int64_t(96) << 20);
       const uint64_t pol = l2_policy_evict_first();
       const uint32_t leader_full0 = PAIR ? mapa_u32(smem_u32(&full_tma[0]), 0u) : 0u; (void)leader_full0;
       int pf_it = 0, pf_kb = 0;                           // next k-block to prefetch
@@ -1399,7 +1427,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap bank_map, const __grid_consta
             mbar_expect_tx(&full_tma[r.s], tx_bytes);
             if (ef) tma_load_2d_hint(smem + L.a_raw + r.s * kATileBytes, &bank_map, &full_tma[r.s], kb * kElemsK, tile * kTileRows, pol);
             else tma_load_2d(smem + L.a_raw + r.s * kATileBytes, &bank_map, &full_tma[r.s], kb * kElemsK, tile * kTileRows);
-            if (qtma)     // the whole [2QP x 32] query k-block is contiguous (and pre-swizzled) in global memory
+            if (qtma && !bres)     // the whole [2QP x 32] query k-block is contiguous (and pre-swizzled) in global memory
               bulk_load(smem + L.bq + r.s * b_stage_bytes, qcat + size_t(kb) * (kParts * QP * 32), b_stage_bytes, &full_tma[r.s]);
           }
           trace_at(p, 0, trace_it++);
@@ -1419,6 +1447,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap bank_map, const __grid_consta
       const uint32_t a_lo0 = (smem_u32(smem + L.a_raw) & 0x3ffffu) >> 4, b_lo0 = (smem_u32(smem + L.bq) & 0x3ffffu) >> 4;
       RingPos r;
       uint32_t unit = 0;
+      if (bres && !(p.flags & kDbgNoQueryTma)) mbar_wait(&peer_full[0], 0);   // the resident query operand has landed
       for (int it = 0; it < n_iter; ++it) {
         const int tile = tile_at(it); (void)tile;
         for (int set = 0; set < nsets; ++set, ++unit) {
@@ -1431,7 +1460,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap bank_map, const __grid_consta
           const int kb_end = min(nkb, (set + 1) * set_kb);
           for (int kb = set * set_kb; kb < kb_end; ++kb) {
             const uint32_t first = kb == set * set_kb ? 0u : 1u;
-            const uint32_t a_lo = a_lo0 + uint32_t(r.s) * (kATileBytes >> 4), b_lo = b_lo0 + uint32_t(r.s) * (b_stage_bytes >> 4);
+            const uint32_t a_lo = a_lo0 + uint32_t(r.s) * (kATileBytes >> 4), b_lo = b_lo0 + uint32_t(bres ? kb : r.s) * (b_stage_bytes >> 4);
             mbar_wait(&full_tma[r.s], r.phase);
             trace_at(p, 3, unit * uint32_t(nkb) + uint32_t(kb));
             trace_at(p, 4, unit * uint32_t(nkb) + uint32_t(kb));            // (pairs: the barrier counts both CTAs' bytes)
@@ -1993,8 +2022,9 @@ size_t scan_tc_qcat_bytes(int mode, int64_t dim, int q_pad) {
 
 // Queries per pass + pipeline depth that fit in shared memory / tensor memory for this list capacity.
 int scan_tc_plan(int mode, int n_queries, int64_t dim, int kcap, bool cached_norms, int64_t n_tiles, int sm_count,
-                 unsigned flags, int* qp_out, int* stages_out, bool* pair_out, bool oneshot, bool emit) {
+                 unsigned flags, int* qp_out, int* stages_out, bool* pair_out, bool oneshot, bool emit, bool* resident_out) {
   *pair_out = false;
+  if (resident_out) *resident_out = false;
   const bool filt = mode == kTcTf32x1 || mode == kTcBf16x1;
   // more than one K-set (1024 fp32 / 2048 bf16 columns) sums K-sets in the epilogue's registers (MULTI):
   // 32 queries per pass at most.  The filter keeps the whole K chain in the tensor core (its error bound
@@ -2016,10 +2046,21 @@ int scan_tc_plan(int mode, int n_queries, int64_t dim, int kcap, bool cached_nor
     // 256 queries per pass on a long scan: CTA pairs (each CTA holds half of the query operand)
     const bool pair = filt && cached_norms && (qp == 256 || (qp >= 64 && (flags & kDbgPairAll))) &&
                       n_tiles >= 2 * int64_t(sm_count) && sm_count % 2 == 0 && !(flags & kDbgNoPair);
+    const int lcap = (filt && (oneshot || emit)) ? 0 : kcap;
+    // long filter scans: the whole query operand resident, if at least 5 ring stages of bank tiles still fit
+    if (filt && emit && !pair && resident_out && !(flags & kDbgNoResident) && 2 * qp <= 512) {
+      const int nkb = scan_tc_kblocks(mode, dim);
+      for (int stages = kMaxStages; stages >= 5; --stages) {
+        if (tc_layout(stages, qp, lcap, mode_parts(mode), false, nkb).total + 1024 <= 225 * 1024) {
+          *qp_out = qp; *stages_out = stages; *resident_out = true;
+          return DEVQA_OK;
+        }
+      }
+    }
     for (int stages = kMaxStages; stages >= 3; --stages) {
       // TMEM: 2 accumulator buffers of 3*qp (filter: qp) columns (+ one 32-column lo tile per stage for 3xTF32)
       if ((filt ? 2 : 6) * qp + (mode == kTcTf32x3 ? stages * kBlockK : 0) > 512) continue;
-      if (tc_layout(stages, qp, (filt && (oneshot || emit)) ? 0 : kcap, mode_parts(mode), pair).total + 1024 <= 225 * 1024) {
+      if (tc_layout(stages, qp, lcap, mode_parts(mode), pair).total + 1024 <= 225 * 1024) {
         *qp_out = qp; *stages_out = stages; *pair_out = pair;
         return DEVQA_OK;
       }
@@ -2069,6 +2110,13 @@ int scan_tc_launch(const ScanParams& sp, int mode, const void* qcat, uint32_t* g
   const bool filt = mode == kTcTf32x1 || mode == kTcBf16x1;
   const int parts = mode_parts(mode);
   const int n_kblocks = scan_tc_kblocks(mode, sp.dim);
+  static const bool hint_set = [] {
+    const char* e = getenv("DEVQA_WAIT_HINT_NS");
+    const uint32_t ns = e ? uint32_t(strtoul(e, nullptr, 10)) : 0u;
+    if (ns) cudaMemcpyToSymbol(c_wait_hint_ns, &ns, sizeof(ns));
+    return true;
+  }();
+  (void)hint_set;
   CUtensorMap bank_map;
   int rc = make_map(&bank_map, sp.bank, bf, uint64_t(sp.dim), uint64_t(sp.n_rows), uint64_t(sp.bank_ld) * (bf ? 2 : 4), kTileRows,
                     bf && (sp.flags & kFlagShadowScan) != 0);
@@ -2091,7 +2139,8 @@ int scan_tc_launch(const ScanParams& sp, int mode, const void* qcat, uint32_t* g
     const uint64_t q_rows = uint64_t((sp.n_queries - sp.q0 + qp - 1) / qp) * uint64_t(n_kblocks) * uint64_t(parts * qp);
     if ((rc = make_rows_map(&p.qmap, p.qcat, q_rows, uint32_t(qp / 2)))) return rc;
   }
-  const size_t smem = tc_layout(stages, qp, (filt && (sp.oneshot || sp.emit)) ? 0 : sp.kcap, parts, pair).total + 1024;
+  p.b_resident = (filt && !pair && sp.b_resident) ? 1 : 0;
+  const size_t smem = tc_layout(stages, qp, (filt && (sp.oneshot || sp.emit)) ? 0 : sp.kcap, parts, pair, p.b_resident ? n_kblocks : 0).total + 1024;
   const bool multi = !filt && p.n_kblocks > kSetKBlocks;
   void (*kern)(CUtensorMap, TcParams) = nullptr;
   if (mode == kTcTf32x3) {

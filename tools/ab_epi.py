@@ -1,5 +1,6 @@
 """A/B inside one process (alternating): scan variants selected by debug bits, same bank and queries.
 
+  no_resident  bit 6   the query operand streamed with the ring stages (default: resident in shared memory when it fits)
   no_evict_first  bit 5   bank tiles loaded without the L2 evict-first hint
   one_group  bit 4   emit mode with one group of epilogue warps (default: two at 128+ queries per pass)
   pair_all   bit 29  CTA pairs also at 64 / 128 queries per pass (default: only at 256)
@@ -12,7 +13,9 @@ L = devqa_b200._lib
 ROWS = int(sys.argv[1]) if len(sys.argv) > 1 else 10_000_000
 QS = [int(x) for x in sys.argv[2].split(",")] if len(sys.argv) > 2 else [64, 128, 256, 1024, 4096]
 SHADOWS = [x == "1" for x in sys.argv[3].split(",")] if len(sys.argv) > 3 else [True, False]
-VARIANTS = {"default": 0, "no_evict_first": 1 << 5}
+VARIANTS = {"default": 0, "no_resident": 1 << 6}
+if os.environ.get("AB_EVICT"):
+    VARIANTS["no_evict_first"] = 1 << 5
 if os.environ.get("AB_ALL"):
     VARIANTS.update({"one_group": 1 << 4, "pair_all": 1 << 29})
 def fallbacks():
