@@ -1394,8 +1394,8 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap bank_map, const __grid_consta
         for (int kb = 0; kb < nkb; ++kb)
           bulk_load(smem + L.bq + kb * b_stage_bytes, qcat + size_t(kb) * (kParts * QP * 32), b_stage_bytes, &peer_full[0]);
       }
-      // (a bank that fits in L2 should stay there between calls: C2 is 67-134 MB)
-      const bool ef = !(p.flags & kDbgNoEvictFirst) && int64_t(p.n_tiles) * nkb * int64_t(kATileBytes) > (int64_t(96) << 20);
+      // (a bank that about fits in L2 should stay there between calls and between the passes of a call: C2 is 67-134 MB)
+      const bool ef = !(p.flags & kDbgNoEvictFirst) && !p.oneshot && int64_t(p.n_tiles) * nkb * int64_t(kATileBytes) > (int64_t(192) << 20);
       const uint64_t pol = l2_policy_evict_first();
       const uint32_t leader_full0 = PAIR ? mapa_u32(smem_u32(&full_tma[0]), 0u) : 0u; (void)leader_full0;
       int pf_it = 0, pf_kb = 0;                           // next k-block to prefetch

@@ -10,7 +10,6 @@ tag = sys.argv[1]
 rows=[r for r in csv.reader(l for l in open(f"gpurun_out/launches_{tag}.csv") if not l.startswith("=="))]
 hdr=rows[0]; ki=hdr.index("Kernel Name"); vi=hdr.index("Metric Value")
 seq=[(r[ki][:90], float(r[vi].replace(",",""))/1e3) for r in rows[1:]]
-# the last search = everything after the last-but-one prep_queries_filt launch
 idx=[i for i,(k,_) in enumerate(seq) if "prep_queries_filt" in k]
 last=seq[idx[-1]:] if idx else seq[-12:]
 with open(f"gpurun_out/launches_{tag}.txt","w") as f:
@@ -19,5 +18,7 @@ with open(f"gpurun_out/launches_{tag}.txt","w") as f:
     tot=sum(v for _,v in last); line=f"{tot:9.1f} us  total"; print(line); f.write(line+"\n")
 PY
 }
-run 1250000 256 1 shard_q256
-run 1250000 1024 1 shard_q1024
+for spec in $SPECS; do
+  IFS=: read rows q sh tag <<< "$spec"
+  run $rows $q $sh $tag
+done
