@@ -35,6 +35,8 @@ SIGNATURES = {
     "devqa_profile_collect": (_i, [_i, C.POINTER(C.c_double), C.POINTER(_i64), C.POINTER(_i64)]),
     "devqa_search_raw": (_i, [_p, _i, _i64, _i64, _i64, _p, _i64, _i64, _i, _u, _i64, _p, _p, _p]),
     "devqa_search_raw_ex": (_i, [_p, _i, _i64, _i64, _i64, _p, _i64, _i64, _i, _u, _i64, _p, _p, _p, _p, _p]),
+    "devqa_search_raw_shadowed": (_i, [_p, _i, _i64, _i64, _i64, _p, _i64, _i64, _i, _u, _i64, _p, _p, _p, _i64, _p, _p, _p, _p]),
+    "devqa_make_shadow": (_i, [_p, _i64, _i64, _i64, _p, _i64, _p, _p]),
     "devqa_row_sumsq": (_i, [_p, _i, _i64, _i64, _i64, _p, _p, _p]),
     "devqa_normalize_rows": (_i, [_p, _i64, _p, _i64, _i64, _i64, _u, _p]),
     "devqa_bank_create": (_i, [C.POINTER(_p), _i, _i64, _i64, _i]),

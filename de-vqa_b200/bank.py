@@ -14,6 +14,7 @@ All arithmetic happens in libdevqa.so (hand-written sm_100a CUDA) through the C 
 from __future__ import annotations
 
 import ctypes as C
+import os
 import pickle
 from typing import List, Optional, Sequence, Tuple, Union
 
@@ -102,12 +103,29 @@ class FactBank:
         bank.append(emb)
         return bank
 
+    def auto_shadow(self) -> bool:
+        """Give a large fp32 bank its 2-byte shadow (``set_shadow``) if the scans that use it can occur (>= 148 tiles of
+        128 rows), it fits in a quarter of the free device memory, and ``DEVQA_SHADOW`` is not ``0``.  Results do not
+        change; searches of such banks stream half the bytes.  Returns whether the bank has a shadow afterwards."""
+        if self.has_shadow:
+            return True
+        if self.dtype != L.F32 or len(self) < 148 * 128 or os.environ.get("DEVQA_SHADOW", "auto") == "0":
+            return False
+        need = len(self) * ((self.dim + 7) // 8 * 8) * 2 + len(self) * 4
+        free, _total = torch.cuda.mem_get_info(self.device)
+        if need > free // 4:
+            return False
+        self.set_shadow(True)
+        return True
+
     @classmethod
-    def from_stored_data(cls, stored: dict, device=0, dtype: str = "fp32") -> "FactBank":
+    def from_stored_data(cls, stored: dict, device=0, dtype: str = "fp32", shadow="auto") -> "FactBank":
         """From the dict the reference pickles (util.py:27,50,85) or ``torch.save``s
         (multimodal_editor.py:1129-1130): keys ``sentences``, ``embeddings`` and optionally
-        ``images``, ``prompts``."""
-        bank = cls.from_embeddings(stored["embeddings"], device=device, dtype=dtype)
+        ``images``, ``prompts``.  ``shadow``: True / False / "auto" (``auto_shadow``)."""
+        bank = cls.from_embeddings(stored["embeddings"], device=device, dtype=dtype, shadow=shadow is True)
+        if shadow == "auto":
+            bank.auto_shadow()
         bank.sentences = list(stored.get("sentences", []))
         bank.images = list(stored.get("images", []))
         bank.prompts = [list(p) for p in stored.get("prompts", [])]

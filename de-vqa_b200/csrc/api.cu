@@ -860,13 +860,20 @@ int devqa_profile_collect(int device, double* scan_ms_total, int64_t* scan_launc
 static int search_raw_common(const void* bank, int bank_dtype, int64_t n_rows, int64_t dim, int64_t bank_ld,
                              const float* queries, int64_t n_queries, int64_t query_ld, int top_k, unsigned flags,
                              int64_t id_base, const float* row_sumsq, const uint32_t* max_sumsq_bits,
-                             float* out_scores, int64_t* out_ids, void* stream_) {
+                             float* out_scores, int64_t* out_ids, void* stream_, const void* shadow = nullptr,
+                             int64_t shadow_ld = 0, const float* shadow_scale = nullptr) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   SearchArgs a{bank, bank_dtype, n_rows, dim, bank_ld, queries, n_queries, query_ld, top_k, flags,
                IdMap{id_base, 0, 0, 1}};
   // fp32 banks only: for bf16 banks cached norms also enter the exact variants' final scores, and the stream
   // kernel would not use them -- results must not depend on which kernel served the call
   if (row_sumsq && max_sumsq_bits && bank_dtype == DEVQA_F32) { a.row_sumsq = row_sumsq; a.max_sumsq = max_sumsq_bits; }
+  if (shadow && shadow_scale && a.row_sumsq) {               // (the filter over the shadow needs the norms as well)
+    DEVQA_REQUIRE(bank_dtype == DEVQA_F32, "a shadow only makes sense for fp32 rows");
+    DEVQA_REQUIRE(shadow_ld >= dim && shadow_ld % 8 == 0 && reinterpret_cast<uintptr_t>(shadow) % 16 == 0,
+                  "shadow rows must be 16-byte aligned (shadow_ld a multiple of 8)");
+    a.shadow = shadow; a.shadow_ld = shadow_ld; a.shadow_scale = shadow_scale;
+  }
   int rc = validate(a);
   if (rc) return rc;
   DEVQA_REQUIRE(n_queries == 0 || (out_scores && out_ids), "output pointers are null");
@@ -894,6 +901,24 @@ int devqa_search_raw_ex(const void* bank, int bank_dtype, int64_t n_rows, int64_
                         int64_t* out_ids, void* stream_) {
   return search_raw_common(bank, bank_dtype, n_rows, dim, bank_ld, queries, n_queries, query_ld, top_k, flags, id_base,
                            row_sumsq, max_sumsq_bits, out_scores, out_ids, stream_);
+}
+
+int devqa_search_raw_shadowed(const void* bank, int bank_dtype, int64_t n_rows, int64_t dim, int64_t bank_ld,
+                              const float* queries, int64_t n_queries, int64_t query_ld, int top_k, unsigned flags,
+                              int64_t id_base, const float* row_sumsq, const uint32_t* max_sumsq_bits, const void* shadow,
+                              int64_t shadow_ld, const float* shadow_scale, float* out_scores, int64_t* out_ids,
+                              void* stream_) {
+  return search_raw_common(bank, bank_dtype, n_rows, dim, bank_ld, queries, n_queries, query_ld, top_k, flags, id_base,
+                           row_sumsq, max_sumsq_bits, out_scores, out_ids, stream_, shadow, shadow_ld, shadow_scale);
+}
+
+int devqa_make_shadow(const float* bank, int64_t n_rows, int64_t dim, int64_t bank_ld, void* shadow, int64_t shadow_ld,
+                      float* shadow_scale, void* stream_) {
+  DEVQA_REQUIRE(n_rows >= 0 && dim > 0 && bank_ld >= dim, "bad shape");
+  DEVQA_REQUIRE(shadow_ld >= dim && shadow_ld % 8 == 0, "shadow_ld must be >= dim and a multiple of 8 (16-byte rows)");
+  DEVQA_REQUIRE(n_rows == 0 || (bank && shadow && shadow_scale), "null pointers");
+  if (n_rows == 0) return DEVQA_OK;
+  return shadow_convert_launch(bank, bank_ld, shadow, shadow_ld, shadow_scale, n_rows, dim, static_cast<cudaStream_t>(stream_));
 }
 
 int devqa_row_sumsq(const void* bank, int bank_dtype, int64_t n_rows, int64_t dim, int64_t bank_ld, float* out_sumsq,

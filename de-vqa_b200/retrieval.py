@@ -170,6 +170,7 @@ def bank_from_stored_data(stored_data: Dict, device=0) -> FactBank:
         if version is not None:
             try:
                 _object_banks[(id(emb), dev)] = (weakref.ref(emb), version, bank)
+                bank.auto_shadow()                                             # (a bank that lives on: worth its shadow)
             except TypeError:
                 pass
     bank.sentences = stored_data['sentences']
@@ -185,6 +186,7 @@ def pin_stored_data(stored_data: Dict, device=0) -> FactBank:
     if old is not None:
         old[2].close()
     bank = FactBank.from_embeddings(emb, device=dev)
+    bank.auto_shadow()
     _object_banks[(id(emb), dev)] = (weakref.ref(emb), "pinned", bank)
     bank.sentences = stored_data['sentences']
     return bank

@@ -17,6 +17,7 @@ accepted and ignored (the scan never materialises a score matrix).
 """
 from __future__ import annotations
 
+import os
 import weakref
 from typing import Callable, List
 
@@ -65,11 +66,28 @@ def _ld(t: torch.Tensor) -> int:
 _NORM_CACHE_MIN_BYTES = 32 << 20          # below this the whole search is launch-latency bound anyway
 _norm_cache: dict = {}
 
+# A 2-byte SHADOW of the corpus (csrc/synth.cu shadow_convert_kernel) rides in the same cache entry: large
+# scans then stream half the bytes and re-score their candidates against the caller's fp32 rows -- results stay
+# bit-identical.  It costs rows x dim x 2 bytes of device memory for as long as the corpus tensor lives, so it is only
+# made for corpora of at least 148 tiles (the scans that would use it), only while it fits in a quarter of the free
+# memory, and never with DEVQA_LEVEL0_SHADOW=0.
+_SHADOW_MIN_ROWS = 148 * 128
 
-def _cached_row_norms(corpus: torch.Tensor):
-    """(row_sumsq device pointer, max-bits device pointer) for an fp32 CUDA corpus, or (None, None)."""
+
+def _shadow_wanted(corpus: torch.Tensor) -> bool:
+    if os.environ.get("DEVQA_LEVEL0_SHADOW", "1") == "0" or corpus.shape[0] < _SHADOW_MIN_ROWS:
+        return False
+    need = corpus.shape[0] * ((corpus.shape[1] + 7) // 8 * 8) * 2 + corpus.shape[0] * 4
+    free, _total = torch.cuda.mem_get_info(corpus.device)
+    return need <= free // 4
+
+
+def _cached_row_norms(corpus: torch.Tensor, with_shadow: bool = False):
+    """(row_sumsq device pointer, max-bits device pointer[, shadow tensor or None, scale tensor or None]) for an fp32 CUDA
+    corpus, or Nones."""
+    none = (None, None, None, None) if with_shadow else (None, None)
     if corpus.dtype != torch.float32 or corpus.numel() * 4 < _NORM_CACHE_MIN_BYTES:
-        return None, None
+        return none
     storage = corpus.untyped_storage()
     sid = storage._cdata
     view = (corpus.data_ptr(), tuple(corpus.shape), tuple(corpus.stride()))
@@ -80,7 +98,7 @@ def _cached_row_norms(corpus: torch.Tensor):
         try:
             entry = _norm_cache[sid] = (weakref.ref(storage, _drop), {})
         except TypeError:
-            return None, None
+            return none
     hit = entry[1].get(view)
     if hit is None or hit[0] != corpus._version:
         n = corpus.shape[0]
@@ -89,8 +107,21 @@ def _cached_row_norms(corpus: torch.Tensor):
                                         side.data_ptr() + 4 * n, _stream_ptr(corpus.device.index)))
         if len(entry[1]) >= 8:
             entry[1].clear()
-        hit = entry[1][view] = (corpus._version, side)
+        hit = entry[1][view] = [corpus._version, side, None, None]
+    if with_shadow and hit[2] is None and _shadow_wanted(corpus):
+        n, ld = corpus.shape[0], (corpus.shape[1] + 7) // 8 * 8
+        try:
+            shadow = torch.empty((n, ld), dtype=torch.float16, device=corpus.device)
+            scale = torch.empty(n, dtype=torch.float32, device=corpus.device)
+        except torch.cuda.OutOfMemoryError:
+            shadow = scale = None
+        if shadow is not None:
+            L.check(L.lib().devqa_make_shadow(corpus.data_ptr(), n, corpus.shape[1], _ld(corpus), shadow.data_ptr(), ld,
+                                              scale.data_ptr(), _stream_ptr(corpus.device.index)))
+            hit[2], hit[3] = shadow, scale
     side = hit[1]
+    if with_shadow:
+        return side.data_ptr(), side.data_ptr() + 4 * corpus.shape[0], hit[2], hit[3]
     return side.data_ptr(), side.data_ptr() + 4 * corpus.shape[0]
 
 
@@ -149,11 +180,15 @@ def semantic_search_arrays(query_embeddings, corpus_embeddings, top_k: int = 10,
     ids = torch.empty((nq, kk), dtype=torch.int64, device=corpus.device)
     with torch.cuda.device(corpus.device):
         # batches the tensor-core path serves: hand it ||row||^2 so that it can filter (see _cached_row_norms)
-        ss_ptr, max_ptr = _cached_row_norms(corpus) if (resident and nq > 2 and kk <= 64) else (None, None)
-        L.check(L.lib().devqa_search_raw_ex(corpus.data_ptr(), L.F32, n, corpus.shape[1], _ld(corpus),
-                                            queries.data_ptr(), nq, _ld(queries), kk, nflags | flags, 0,
-                                            ss_ptr, max_ptr, scores.data_ptr(), ids.data_ptr(),
-                                            _stream_ptr(corpus.device.index)))
+        # (and, for large corpora, a 2-byte shadow of the rows: half the bytes to stream, same results)
+        ss_ptr, max_ptr, shadow, scale = (_cached_row_norms(corpus, with_shadow=True) if (resident and kk <= 64 and
+                                          (nq > 2 or n >= 8 * _SHADOW_MIN_ROWS)) else (None, None, None, None))
+        L.check(L.lib().devqa_search_raw_shadowed(corpus.data_ptr(), L.F32, n, corpus.shape[1], _ld(corpus),
+                                                  queries.data_ptr(), nq, _ld(queries), kk, nflags | flags, 0,
+                                                  ss_ptr, max_ptr, shadow.data_ptr() if shadow is not None else None,
+                                                  shadow.shape[1] if shadow is not None else 0,
+                                                  scale.data_ptr() if scale is not None else None,
+                                                  scores.data_ptr(), ids.data_ptr(), _stream_ptr(corpus.device.index)))
     return scores, ids
 
 

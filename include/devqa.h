@@ -147,6 +147,22 @@ DEVQA_API int devqa_search_raw_ex(const void* bank, int bank_dtype, int64_t n_ro
                         const float* queries, int64_t n_queries, int64_t query_ld, int top_k,
                         unsigned flags, int64_t id_base, const float* row_sumsq,
                         const uint32_t* max_sumsq_bits, float* out_scores, int64_t* out_ids, void* stream);
+/* ... and with a 2-byte SHADOW of the caller-owned fp32 rows (devqa_make_shadow; both NULL = none): large scans with
+ * top_k <= 64 stream the shadow (half the bytes) and re-score their candidates against the fp32 rows -- results stay
+ * bit-identical to devqa_search_raw's.  The shadow needs row_sumsq / max_sumsq_bits as well and, like them, MUST describe
+ * the bank as it is now.  This is what devqa_bank_set_shadow does for a library-owned bank; Level-0 callers
+ * (de-vqa_b200/util.py: the reference's semantic_search(q, corpus) over the corpus tensor it already holds,
+ * dataset/vllm.py:68, ike_main.py:202) cache it per corpus tensor. */
+DEVQA_API int devqa_search_raw_shadowed(const void* bank, int bank_dtype, int64_t n_rows, int64_t dim, int64_t bank_ld,
+                              const float* queries, int64_t n_queries, int64_t query_ld, int top_k,
+                              unsigned flags, int64_t id_base, const float* row_sumsq,
+                              const uint32_t* max_sumsq_bits, const void* shadow, int64_t shadow_ld,
+                              const float* shadow_scale, float* out_scores, int64_t* out_ids, void* stream);
+/* Write the shadow of fp32 rows: shadow [n_rows, shadow_ld] 2-byte elements (scaled fp16: each row multiplied by a power
+ * of two so that its largest magnitude lands in [2^13, 2^14)), shadow_scale [n_rows] the inverse factors.  shadow_ld >=
+ * dim and a multiple of 8, shadow 16-byte aligned.  All DEVICE memory. */
+DEVQA_API int devqa_make_shadow(const float* bank, int64_t n_rows, int64_t dim, int64_t bank_ld, void* shadow,
+                                int64_t shadow_ld, float* shadow_scale, void* stream);
 /* ||row||^2 of every row of a caller-owned bank (one warp per row): out_sumsq [n_rows]; out_max_bits (optional) is a
  * device word the caller zeroed, which receives the bit pattern of the largest sum (atomicMax). */
 DEVQA_API int devqa_row_sumsq(const void* bank, int bank_dtype, int64_t n_rows, int64_t dim, int64_t bank_ld,

@@ -646,6 +646,24 @@ def test_emit_mode_equals_the_list_epilogue(n, d, nq, k, nb, shadow):
     fb.close()
 
 
+@pytest.mark.parametrize("n,d,nq,k,shadow", [(60000, 768, 300, 32, True), (45000, 768, 64, 32, True), (60000, 384, 130, 16, False)])
+def test_scan_variants_are_bit_identical(n, d, nq, k, shadow):
+    """The scan kernel's alternatives behind debug bits -- one group of epilogue warps instead of two (bit 4), bank tiles
+    without the L2 evict-first hint (5), query operand streamed with the stages instead of resident (6), CTA pairs also at
+    64 / 128 queries per pass (29) -- change how the tiles are multiplied and scanned, never what comes back."""
+    bank, q = _randn(n, d, 3 * n + d, unit=False), _randn(nq, d, 5 * nq + d, unit=False)
+    fb = FactBank.from_embeddings(bank, shadow=shadow)
+    _fallbacks(); _violations()
+    ref = fb.search(q.cuda(), k, normalize_bank="eps", normalize_query="eps", flags=L.FORCE_TENSOR)
+    for bit in (4, 5, 6, 29):
+        out = fb.search(q.cuda(), k, normalize_bank="eps", normalize_query="eps", flags=L.FORCE_TENSOR | (1 << bit))
+        assert torch.equal(out[1], ref[1]) and torch.equal(out[0], ref[0]), bit
+    assert _violations() == 0 and _fallbacks() <= 5 * max(1, nq // 16)
+    c = fb.search(q[:8].cuda(), k, normalize_bank="eps", normalize_query="eps", flags=L.FORCE_STREAM)
+    assert torch.equal(ref[1][:8], c[1]) and torch.equal(ref[0][:8], c[0])
+    fb.close()
+
+
 def test_emit_mode_overflow_takes_the_fallback():
     """20000 identical rows: every one of them beats any threshold, the candidate array (8192 per query) overflows,
     the query is flagged and the exact pipeline answers it -- ties in ascending id order."""

@@ -420,7 +420,10 @@ def test_level0_dot_score_over_a_prenormalised_tensor_takes_the_filter():
     first = L.lib().devqa_launch_count() - launches0
     s_again, i_again = dutil.semantic_search_arrays(q, bank, top_k=k, score_function=dutil.dot_score)
     second = L.lib().devqa_launch_count() - launches0 - first
-    assert second == first - 1                               # the ||row||^2 pass ran once
+    assert second == first - 2                               # the ||row||^2 pass and the shadow conversion ran once
+    (entry,) = dutil._norm_cache.values()
+    (hit,) = entry[1].values()
+    assert hit[2] is not None and hit[2].dtype == torch.float16 and hit[2].shape == (n, d)   # 313 tiles: shadowed
     s_ref, i_ref = dutil.semantic_search_arrays(q, bank, top_k=k, score_function=dutil.dot_score, flags=L.FORCE_STREAM)
     assert torch.equal(i, i_ref) and torch.equal(s, s_ref) and torch.equal(i_again, i_ref)
     L.check(L.lib().devqa_filter_fallbacks(0, C.byref(fb_count)))
@@ -442,6 +445,61 @@ def test_level0_dot_score_over_a_prenormalised_tensor_takes_the_filter():
     del bank, half
     import gc; gc.collect()
     assert len(dutil._norm_cache) == 0                        # the storage died, its entry went with it
+
+
+def test_level0_shadow_is_optional_and_changes_nothing(monkeypatch):
+    """DEVQA_LEVEL0_SHADOW=0: the shim keeps only the row norms for a caller-owned corpus (TF32 filter over the fp32
+    rows).  With the shadow (default, corpora of >= 148 tiles) the same call streams the 2-byte copy: same bits."""
+    n, d, nq, k = 60_000, 384, 70, 32
+    bank = dutil.normalize_embeddings(_randn(n, d, 21, unit=False).cuda())
+    q = dutil.normalize_embeddings(_randn(nq, d, 22, unit=False).cuda())
+    monkeypatch.setenv("DEVQA_LEVEL0_SHADOW", "0")
+    s0, i0 = dutil.semantic_search_arrays(q, bank, top_k=k, score_function=dutil.dot_score)
+    (entry,) = dutil._norm_cache.values()
+    (hit,) = entry[1].values()
+    assert hit[2] is None
+    monkeypatch.delenv("DEVQA_LEVEL0_SHADOW")
+    s1, i1 = dutil.semantic_search_arrays(q, bank, top_k=k, score_function=dutil.dot_score)
+    assert hit[2] is not None                                # made on the first call that may use it
+    s_ref, i_ref = dutil.semantic_search_arrays(q, bank, top_k=k, score_function=dutil.dot_score, flags=L.FORCE_STREAM)
+    assert torch.equal(i0, i_ref) and torch.equal(s0, s_ref) and torch.equal(i1, i_ref) and torch.equal(s1, s_ref)
+    # one query over a large corpus: served by the tensor path over the shadow as well, same bits as the stream kernel
+    big = dutil.normalize_embeddings(_randn(160_000, 384, 23, unit=False).cuda())
+    s2, i2 = dutil.semantic_search_arrays(q[:1], big, top_k=k, score_function=dutil.cos_sim)
+    s2r, i2r = dutil.semantic_search_arrays(q[:1], big, top_k=k, score_function=dutil.cos_sim, flags=L.FORCE_STREAM)
+    assert torch.equal(i2, i2r) and torch.equal(s2, s2r)
+    del bank, big, hit, entry
+    import gc; gc.collect()
+    assert len(dutil._norm_cache) == 0
+
+
+def test_reference_format_loaders_shadow_large_banks(tmp_path):
+    """FactBank.from_stored_data / from_pickle (what retrieval.py's bank_from_file uses for the reference's .pkl files)
+    give a large fp32 bank its shadow on their own (auto_shadow); small banks and DEVQA_SHADOW=0 stay as they are.
+    Results are the stream kernel's either way."""
+    import os, pickle
+    emb = _randn(30_000, 256, 31, unit=False)
+    stored = {"sentences": [f"s{i}" for i in range(len(emb))], "embeddings": emb.numpy()}
+    path = tmp_path / "evqa_embeddings.pkl"
+    with open(path, "wb") as f:
+        pickle.dump(stored, f)
+    fb = FactBank.from_pickle(str(path))
+    assert fb.has_shadow
+    small = FactBank.from_stored_data({"sentences": [], "embeddings": emb[:5000].numpy()})
+    assert not small.has_shadow
+    os.environ["DEVQA_SHADOW"] = "0"
+    try:
+        off = FactBank.from_stored_data(stored)
+        assert not off.has_shadow
+    finally:
+        del os.environ["DEVQA_SHADOW"]
+    q = _randn(20, 256, 32, unit=False).cuda()
+    a = fb.search(q, 16, normalize_bank="eps", normalize_query="eps")
+    b = off.search(q, 16, normalize_bank="eps", normalize_query="eps")
+    c = fb.search(q, 16, normalize_bank="eps", normalize_query="eps", flags=L.FORCE_STREAM)
+    assert torch.equal(a[1], c[1]) and torch.equal(a[0], c[0]) and torch.equal(b[1], c[1]) and torch.equal(b[0], c[0])
+    for x in (fb, small, off):
+        x.close()
 
 
 @pytest.mark.parametrize("n,d,nq,k,dtype", [(5000, 64, 3, 1025, "fp32"), (9000, 128, 2, 3000, "fp32"), (2500, 36, 1, 2500, "bf16"),

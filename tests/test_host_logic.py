@@ -41,6 +41,9 @@ class OracleBank:
         with open(path, "rb") as f:
             return cls.from_stored_data(pickle.load(f))
 
+    def auto_shadow(self):
+        return False
+
     def __len__(self):
         return len(self.emb)
 
