@@ -83,8 +83,19 @@ constexpr int kPrefetchAhead = 12;                  // bank k-blocks pulled into
 constexpr int kSetKBlocks = 32;
 // filter epilogue: hit queue entries; the same words hold the dense [16][128] score tile (8 KB), so >= 1024
 __host__ __device__ constexpr int hit_cap(int qp) { return (qp > 128 || qp < 32) ? 1024 : 2048; }
-// undocumented debugging bits of `flags` (performance bisection only; results are wrong when set)
-constexpr unsigned kDbgNoInsert = 1u << 16, kDbgNoSplit = 1u << 17, kDbgNoMma2 = 1u << 18, kDbgNoQueryTma = 1u << 19, kDbgL2Prefetch = 1u << 20, kDbgNoBoot = 1u << 23, kDbgNoPair = 1u << 28, kDbgOneEpiGroup = 1u << 4, kDbgNoEvictFirst = 1u << 5, kDbgNoResident = 1u << 6, kDbgPairAll = 1u << 29, kDbgNoMma1 = 1u << 30;                     // k-blocks (of 32 columns) accumulated inside the tensor core
+// Undocumented debugging bits of `flags`.
+// Bisection only -- results are WRONG when set:
+constexpr unsigned kDbgNoInsert = 1u << 16, kDbgNoSplit = 1u << 17, kDbgNoMma2 = 1u << 18, kDbgNoQueryTma = 1u << 19,
+                   kDbgNoMma1 = 1u << 30;
+// A/B switches -- same results, another way to get them (tools/ab_epi.py, tests/test_gpu_filter.py
+// test_scan_variants_are_bit_identical):
+constexpr unsigned kDbgOneEpiGroup = 1u << 4,    // emit mode: one group of epilogue warps also at 128+ queries per pass
+                   kDbgNoEvictFirst = 1u << 5,   // bank tiles without the L2 evict-first hint
+                   kDbgNoResident = 1u << 6,     // query operand streamed with the ring stages, never resident
+                   kDbgL2Prefetch = 1u << 20,    // L2 prefetch of tiles ahead of the ring (round 1; slower)
+                   kDbgNoBoot = 1u << 23,        // no first-tile bootstrap / 2 accumulator buffers
+                   kDbgNoPair = 1u << 28,        // no CTA pairs
+                   kDbgPairAll = 1u << 29;       // CTA pairs also at 64 / 128 queries per pass
 
 // ---- PTX wrappers ---------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return uint32_t(__cvta_generic_to_shared(p)); }
@@ -268,11 +279,6 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t local_addr, uint32_t rank)
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
-// Pure signal, no ordering of this thread's own writes: used to forward a TMA completion (the data was written by
-// the async proxy and is consumed by the tensor core, exactly as when TMA signals the leader's barrier itself).
-__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
-}
 // wait on a LOCAL barrier that a peer CTA arrives on (cluster-scope acquire)
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
   asm volatile(
@@ -420,7 +426,7 @@ __host__ __device__ inline SmemLayout tc_layout(int stages, int qp, int kcap, in
   L.scratch = off; off += kcap == 0 ? uint32_t(qp) * 12 + 16 : hit_cap(qp) * 8;   // hit queue / dense [16][128] score tile (MULTI: score tile [HQ][128], same size)
   L.norms = off; off += qp > 128 ? 0 : kNormRing * kTileRows * 4;         // (256 queries per pass: cached row norms only)
   off = (off + 7) & ~7u;
-  L.bars = off;  off += (4 * kMaxStages + 2 * kMaxAccBufs) * 8;   // full_tma, full_split, empty, peer_full (pairs), tmem_full/empty
+  L.bars = off;  off += (4 * kMaxStages + 2 * kMaxAccBufs) * 8;   // full_tma, full_split, empty, peer_full ([0]: resident query operand), tmem_full/empty
   L.tmem_slot = off; off += 16;
   L.total = off;
   return L;
@@ -1251,9 +1257,10 @@ __device__ __forceinline__ void oneshot_service(const TcParams& p, const FiltSta
 
 // PAIR: two CTAs of one TPC (cluster of 2) run ONE MMA of M = 256 per instruction (cta_group::2): each CTA streams
 // its own 128 bank rows and holds HALF of the query operand, which the tensor cores of both read -- 64 instead of
-// 96 KB of shared-memory traffic per k-block at 256 queries.  The leader (cluster rank 0) issues the MMAs; the peer's
-// warp 1 forwards "my stage is loaded" to the leader's barrier; commits are multicast to both CTAs' barriers; both
-// epilogues release the accumulator on the leader's barrier.  Everything else (lists, thresholds, exchange) is per CTA.
+// 96 KB of shared-memory traffic per k-block at 256 queries.  The leader (cluster rank 0) issues the MMAs; both CTAs'
+// TMA loads complete on the LEADER's full barrier (cta_group::2 loads, tma_load_2d_pair); commits are multicast to both
+// CTAs' barriers; both epilogues release the accumulator on the leader's barrier.  Everything else (thresholds,
+// exchange, candidates) is per CTA.
 template <int QP, bool MULTI, int MODE, bool PAIR = false>
 __global__ void __launch_bounds__(kTcThreads, 1)
 scan_tc_kernel(const __grid_constant__ CUtensorMap bank_map, const __grid_constant__ TcParams p) {
@@ -1286,7 +1293,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap bank_map, const __grid_consta
   uint64_t* full_tma = reinterpret_cast<uint64_t*>(smem + L.bars);
   uint64_t* full_split = full_tma + kMaxStages;
   uint64_t* empty = full_split + kMaxStages;
-  uint64_t* peer_full = empty + kMaxStages;        // pairs, leader only: the peer's stage s is loaded
+  uint64_t* peer_full = empty + kMaxStages;        // [0]: the resident query operand has landed (b_resident); others unused
   uint64_t* tmem_full = peer_full + kMaxStages;    // [kMaxAccBufs]
   uint64_t* tmem_empty = tmem_full + kMaxAccBufs;  // [kMaxAccBufs]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L.tmem_slot);
@@ -1438,7 +1445,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap bank_map, const __grid_consta
   } else if (warp == 1) {
     // ===== MMA issuer 1: A (hi by truncation, from shared memory) x [Qhi ; Qlo] -> cols [0, 2QP) =====
     if (PAIR && !leader) {
-      // pair, peer CTA: no MMA issue (warps 4-7 forward "stage s is loaded" to the leader, below)
+      // pair, peer CTA: no MMA issue (its loads complete on the leader's barrier)
     } else if (lane == 0) {
       const bool f16 = BFD && (p.flags & kFlagShadowScan) != 0;       // the shadow of an fp32 bank is (scaled) fp16, not bf16
       const uint32_t idesc_cat = BFD ? (f16 ? (PAIR ? idesc_f16_pair(QP) : idesc_f16(kParts * QP))
