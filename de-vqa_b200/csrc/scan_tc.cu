@@ -1279,7 +1279,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap bank_map, const __grid_consta
   static_assert(!PAIR || (FILT && QP >= 64), "CTA pairs: filter variant, 64+ queries per pass");
   // (emit and one-shot mode keep no per-CTA lists: the space goes to ring stages, see scan_tc_plan)
   const int list_cap = (FILT && (p.emit || p.oneshot)) ? 0 : p.kcap;
-  const bool bres = FILT && !PAIR && p.b_resident != 0;
+  const bool bres = FILT && p.b_resident != 0;
   const SmemLayout L = tc_layout(p.stages, p.qp, list_cap, kParts, PAIR, bres ? p.n_kblocks : 0);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int S = p.stages;
@@ -1397,9 +1397,18 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap bank_map, const __grid_consta
         // the query operand, once: every k-block of the pass (at 64 queries x 768 fp16 columns: 96 KB).  Streaming it
         // with the stages made each SM pull 1.5x the bank's bytes out of L2 -- under the power cap (SM clock ~1.45 GHz)
         // that, not HBM, set the tile period.
-        mbar_expect_tx(&peer_full[0], uint32_t(nkb) * b_stage_bytes);
-        for (int kb = 0; kb < nkb; ++kb)
-          bulk_load(smem + L.bq + kb * b_stage_bytes, qcat + size_t(kb) * (kParts * QP * 32), b_stage_bytes, &peer_full[0]);
+        if constexpr (PAIR) {
+          // each CTA its half of the rows; both halves are counted on the LEADER's barrier (it issues the MMAs)
+          const uint32_t rb = mapa_u32(smem_u32(&peer_full[0]), 0u);
+          if (leader) mbar_expect_tx(&peer_full[0], 2u * uint32_t(nkb) * b_stage_bytes);
+          for (int kb = 0; kb < nkb; ++kb)
+            tma_load_2d_pair(smem + L.bq + kb * b_stage_bytes, &p.qmap, rb, 0,
+                             (pass_local * nkb + kb) * (kParts * QP) + int(pair_rank) * kBRows);
+        } else {
+          mbar_expect_tx(&peer_full[0], uint32_t(nkb) * b_stage_bytes);
+          for (int kb = 0; kb < nkb; ++kb)
+            bulk_load(smem + L.bq + kb * b_stage_bytes, qcat + size_t(kb) * (kParts * QP * 32), b_stage_bytes, &peer_full[0]);
+        }
       }
       // (a bank that about fits in L2 should stay there between calls and between the passes of a call: C2 is 67-134 MB)
       const bool ef = !(p.flags & kDbgNoEvictFirst) && !p.oneshot && int64_t(p.n_tiles) * nkb * int64_t(kATileBytes) > (int64_t(192) << 20);
@@ -1427,7 +1436,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap bank_map, const __grid_consta
             if (leader) mbar_expect_tx(&full_tma[r.s], 2u * tx_bytes);
             if (ef) tma_load_2d_pair_hint(smem + L.a_raw + r.s * kATileBytes, &bank_map, lbar, kb * kElemsK, tile * kTileRows, pol);
             else tma_load_2d_pair(smem + L.a_raw + r.s * kATileBytes, &bank_map, lbar, kb * kElemsK, tile * kTileRows);
-            if (qtma)   // this CTA's half of the k-block's query rows (pre-swizzled rows of 128 bytes)
+            if (qtma && !bres)   // this CTA's half of the k-block's query rows (pre-swizzled rows of 128 bytes)
               tma_load_2d_pair(smem + L.bq + r.s * b_stage_bytes, &p.qmap, lbar, 0,
                                (pass_local * nkb + kb) * (kParts * QP) + int(pair_rank) * kBRows);
           } else {
@@ -2055,11 +2064,14 @@ int scan_tc_plan(int mode, int n_queries, int64_t dim, int kcap, bool cached_nor
                       n_tiles >= 2 * int64_t(sm_count) && sm_count % 2 == 0 && !(flags & kDbgNoPair);
     const int lcap = (filt && (oneshot || emit)) ? 0 : kcap;
     // long filter scans: the whole query operand resident, if at least 5 ring stages of bank tiles still fit
-    if (filt && emit && !pair && resident_out && !(flags & kDbgNoResident) && 2 * qp <= 512) {
+    // (What a wide pass can stream is bytes in flight / ring latency -- ~46 B/clk and SM with ~190 KB in flight, DESIGN.md
+    // 3.1h: the query operand out of the ring leaves it all to bank tiles.  A CTA pair holds half of the operand per
+    // CTA; 128-query passes AS PAIRS just to make it fit were tried: +4.5 % on a 1.25M-row shard, -4 % at 10M rows.)
+    if (filt && emit && resident_out && !(flags & kDbgNoResident) && 2 * qp <= 512) {
       const int nkb = scan_tc_kblocks(mode, dim);
       for (int stages = kMaxStages; stages >= 5; --stages) {
-        if (tc_layout(stages, qp, lcap, mode_parts(mode), false, nkb).total + 1024 <= 225 * 1024) {
-          *qp_out = qp; *stages_out = stages; *resident_out = true;
+        if (tc_layout(stages, qp, lcap, mode_parts(mode), pair, nkb).total + 1024 <= 225 * 1024) {
+          *qp_out = qp; *stages_out = stages; *resident_out = true; *pair_out = pair;
           return DEVQA_OK;
         }
       }
@@ -2146,7 +2158,7 @@ int scan_tc_launch(const ScanParams& sp, int mode, const void* qcat, uint32_t* g
     const uint64_t q_rows = uint64_t((sp.n_queries - sp.q0 + qp - 1) / qp) * uint64_t(n_kblocks) * uint64_t(parts * qp);
     if ((rc = make_rows_map(&p.qmap, p.qcat, q_rows, uint32_t(qp / 2)))) return rc;
   }
-  p.b_resident = (filt && !pair && sp.b_resident) ? 1 : 0;
+  p.b_resident = (filt && sp.b_resident) ? 1 : 0;
   const size_t smem = tc_layout(stages, qp, (filt && (sp.oneshot || sp.emit)) ? 0 : sp.kcap, parts, pair, p.b_resident ? n_kblocks : 0).total + 1024;
   const bool multi = !filt && p.n_kblocks > kSetKBlocks;
   void (*kern)(CUtensorMap, TcParams) = nullptr;

@@ -10,6 +10,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch, devqa_b200
 from devqa_b200 import FactBank
 L = devqa_b200._lib
+DIM = int(os.environ.get('AB_DIM', '768'))
 ROWS = int(sys.argv[1]) if len(sys.argv) > 1 else 10_000_000
 QS = [int(x) for x in sys.argv[2].split(",")] if len(sys.argv) > 2 else [64, 128, 256, 1024, 4096]
 SHADOWS = [x == "1" for x in sys.argv[3].split(",")] if len(sys.argv) > 3 else [True, False]
@@ -23,12 +24,12 @@ def fallbacks():
     L.check(L.lib().devqa_filter_fallbacks(0, C.byref(v)))
     return v.value
 for shadow in SHADOWS:
-    fb = FactBank(768, capacity=ROWS, shadow=shadow)
+    fb = FactBank(DIM, capacity=ROWS, shadow=shadow)
     for r0 in range(0, ROWS, 1 << 20):
         fb.append_synthetic(min(1 << 20, ROWS - r0), 4234, first_global_row=r0)
     g = torch.Generator().manual_seed(8678)
     for nq in QS:
-        q = torch.nn.functional.normalize(torch.randn(nq, 768, generator=g), dim=1).cuda()
+        q = torch.nn.functional.normalize(torch.randn(nq, DIM, generator=g), dim=1).cuda()
         outs = {k: fb.search(q, 32, flags=f) for k, f in VARIANTS.items()}
         if nq <= 256 and ROWS <= 2_000_000:
             outs["stream"] = fb.search(q, 32, flags=L.FORCE_STREAM)
