@@ -132,14 +132,15 @@ class FactBank:
         return bank
 
     @classmethod
-    def from_pickle(cls, path: str, device=0, dtype: str = "fp32") -> "FactBank":
-        """Load ``{task}_embeddings(_llava).pkl`` / ``vlkeb_embeddings_collect.pkl`` unchanged."""
+    def from_pickle(cls, path: str, device=0, dtype: str = "fp32", shadow="auto") -> "FactBank":
+        """Load ``{task}_embeddings(_llava).pkl`` / ``vlkeb_embeddings_collect.pkl`` unchanged.
+        ``shadow``: True / False / "auto" (``auto_shadow``)."""
         if str(path).endswith((".pth", ".pt")):
             stored = torch.load(path, map_location="cpu", weights_only=False)
         else:
             with open(path, "rb") as f:
                 stored = pickle.load(f)
-        return cls.from_stored_data(stored, device=device, dtype=dtype)
+        return cls.from_stored_data(stored, device=device, dtype=dtype, shadow=shadow)
 
     # ---- state -------------------------------------------------------------------------------
     def __len__(self) -> int:
