@@ -92,6 +92,7 @@ constexpr unsigned kDbgNoInsert = 1u << 16, kDbgNoSplit = 1u << 17, kDbgNoMma2 =
 constexpr unsigned kDbgOneEpiGroup = 1u << 4,    // emit mode: one group of epilogue warps also at 128+ queries per pass
                    kDbgNoEvictFirst = 1u << 5,   // bank tiles without the L2 evict-first hint
                    kDbgNoResident = 1u << 6,     // query operand streamed with the ring stages, never resident
+                   kDbgContigTiles = 1u << 7,    // TIMING ONLY (wrong results): bank tiles read as contiguous 16 KB boxes
                    kDbgL2Prefetch = 1u << 20,    // L2 prefetch of tiles ahead of the ring (round 1; slower)
                    kDbgNoBoot = 1u << 23,        // no first-tile bootstrap / 2 accumulator buffers
                    kDbgNoPair = 1u << 28,        // no CTA pairs
@@ -1411,6 +1412,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap bank_map, const __grid_consta
         }
       }
       // (a bank that about fits in L2 should stay there between calls and between the passes of a call: C2 is 67-134 MB)
+      const bool contig = (p.flags & kDbgContigTiles) != 0;            // (timing experiment: see scan_tc_launch)
       const bool ef = !(p.flags & kDbgNoEvictFirst) && !p.oneshot && int64_t(p.n_tiles) * nkb * int64_t(kATileBytes) > (int64_t(192) << 20);
       const uint64_t pol = l2_policy_evict_first();
       const uint32_t leader_full0 = PAIR ? mapa_u32(smem_u32(&full_tma[0]), 0u) : 0u; (void)leader_full0;
@@ -1434,15 +1436,15 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap bank_map, const __grid_consta
             // both CTAs' bytes complete on the leader's barrier (the leader expects twice a stage)
             const uint32_t lbar = leader_full0 + uint32_t(r.s) * 8u;
             if (leader) mbar_expect_tx(&full_tma[r.s], 2u * tx_bytes);
-            if (ef) tma_load_2d_pair_hint(smem + L.a_raw + r.s * kATileBytes, &bank_map, lbar, kb * kElemsK, tile * kTileRows, pol);
-            else tma_load_2d_pair(smem + L.a_raw + r.s * kATileBytes, &bank_map, lbar, kb * kElemsK, tile * kTileRows);
+            if (ef) tma_load_2d_pair_hint(smem + L.a_raw + r.s * kATileBytes, &bank_map, lbar, contig ? 0 : kb * kElemsK, contig ? (tile * nkb + kb) * kTileRows : tile * kTileRows, pol);
+            else tma_load_2d_pair(smem + L.a_raw + r.s * kATileBytes, &bank_map, lbar, contig ? 0 : kb * kElemsK, contig ? (tile * nkb + kb) * kTileRows : tile * kTileRows);
             if (qtma && !bres)   // this CTA's half of the k-block's query rows (pre-swizzled rows of 128 bytes)
               tma_load_2d_pair(smem + L.bq + r.s * b_stage_bytes, &p.qmap, lbar, 0,
                                (pass_local * nkb + kb) * (kParts * QP) + int(pair_rank) * kBRows);
           } else {
             mbar_expect_tx(&full_tma[r.s], tx_bytes);
-            if (ef) tma_load_2d_hint(smem + L.a_raw + r.s * kATileBytes, &bank_map, &full_tma[r.s], kb * kElemsK, tile * kTileRows, pol);
-            else tma_load_2d(smem + L.a_raw + r.s * kATileBytes, &bank_map, &full_tma[r.s], kb * kElemsK, tile * kTileRows);
+            if (ef) tma_load_2d_hint(smem + L.a_raw + r.s * kATileBytes, &bank_map, &full_tma[r.s], contig ? 0 : kb * kElemsK, contig ? (tile * nkb + kb) * kTileRows : tile * kTileRows, pol);
+            else tma_load_2d(smem + L.a_raw + r.s * kATileBytes, &bank_map, &full_tma[r.s], contig ? 0 : kb * kElemsK, contig ? (tile * nkb + kb) * kTileRows : tile * kTileRows);
             if (qtma && !bres)     // the whole [2QP x 32] query k-block is contiguous (and pre-swizzled) in global memory
               bulk_load(smem + L.bq + r.s * b_stage_bytes, qcat + size_t(kb) * (kParts * QP * 32), b_stage_bytes, &full_tma[r.s]);
           }
@@ -2137,8 +2139,14 @@ int scan_tc_launch(const ScanParams& sp, int mode, const void* qcat, uint32_t* g
   }();
   (void)hint_set;
   CUtensorMap bank_map;
-  int rc = make_map(&bank_map, sp.bank, bf, uint64_t(sp.dim), uint64_t(sp.n_rows), uint64_t(sp.bank_ld) * (bf ? 2 : 4), kTileRows,
-                    bf && (sp.flags & kFlagShadowScan) != 0);
+  int rc;
+  if ((sp.flags & kDbgContigTiles) && sp.bank_ld == sp.dim && sp.dim % (bf ? 64 : 32) == 0)
+    // timing experiment: the same bytes addressed as [rows * k-blocks][128 bytes] -- every box one contiguous 16 KB run
+    rc = make_map(&bank_map, sp.bank, bf, bf ? 64 : 32, uint64_t(sp.n_rows) * uint64_t(n_kblocks), 128, kTileRows,
+                  bf && (sp.flags & kFlagShadowScan) != 0);
+  else
+    rc = make_map(&bank_map, sp.bank, bf, uint64_t(sp.dim), uint64_t(sp.n_rows), uint64_t(sp.bank_ld) * (bf ? 2 : 4), kTileRows,
+                  bf && (sp.flags & kFlagShadowScan) != 0);
   if (rc) return rc;
   TcParams p{};
   p.n_rows = sp.n_rows; p.dim = int(sp.dim); p.n_kblocks = n_kblocks;
