@@ -282,3 +282,23 @@ def test_split_append_partitions_batches():
                 local_sizes[r] += cnt
         assert sorted(covered) == list(range(batch))
         total += batch
+
+
+def test_level0_shadow_policy(monkeypatch):
+    """util._shadow_wanted: a caller-owned corpus gets a 2-byte shadow only if the scans that would use it can occur
+    (>= 148 tiles of 128 rows), it fits in a quarter of the free device memory, and DEVQA_LEVEL0_SHADOW is not 0.
+    (Pure host logic: no GPU needed.)"""
+    from types import SimpleNamespace
+    from devqa_b200 import util as dutil
+    free = [64 << 30]
+    monkeypatch.setattr(torch.cuda, "mem_get_info", lambda dev=None: (free[0], 180 << 30))
+    big = SimpleNamespace(shape=(10_000_000, 768), device="cuda:0")
+    small = SimpleNamespace(shape=(148 * 128 - 1, 768), device="cuda:0")
+    edge = SimpleNamespace(shape=(148 * 128, 100), device="cuda:0")
+    monkeypatch.delenv("DEVQA_LEVEL0_SHADOW", raising=False)
+    assert dutil._shadow_wanted(big) and dutil._shadow_wanted(edge) and not dutil._shadow_wanted(small)
+    free[0] = 40 << 30                                        # 15.4 GB of shadow > a quarter of 40 GB
+    assert not dutil._shadow_wanted(big) and dutil._shadow_wanted(edge)
+    free[0] = 64 << 30
+    monkeypatch.setenv("DEVQA_LEVEL0_SHADOW", "0")
+    assert not dutil._shadow_wanted(big)
