@@ -115,7 +115,10 @@ class FactBank:
         free, _total = torch.cuda.mem_get_info(self.device)
         if need > free // 4:
             return False
-        self.set_shadow(True)
+        try:
+            self.set_shadow(True)
+        except L.DevqaError:                                   # (out of memory after all: the bank works without one)
+            return False
         return True
 
     @classmethod
